@@ -1,0 +1,94 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE — builds oracle/_ref/libref_lumix.so from the reference's OWN sources where they
+# lie under /root/reference (never copied into this repo; the patched overlay copy lives in a mktemp
+# dir that is deleted afterwards).  Does not run the reference's build system (GENie/MSBuild).
+#
+#   unmodified : src/core/{math,geometry,string,hash,log,stream,page_allocator,default_allocator,
+#                arena_allocator}.cpp, src/core/linux/{thread,atomic,fibers}.cpp,
+#                src/renderer/culling_system.cpp
+#   overlay    : SURVEY.md §8(c) — src/core/sync.h (SRWLock body), src/core/linux/sync.cpp (stale
+#                Semaphore::signal signature + SRWLock methods), src/core/simd.h (take the SSE branch
+#                on GCC), src/core/job_system.cpp (noinline on getWorker(): the reference's TLS guard
+#                is MSVC/clang pragmas only)
+#   stubs      : oracle/ref/ref_stubs.cpp (os::mem*, profiler no-ops, atomics missing on Linux)
+#
+# Flags mirror the reference's Linux config (scripts/genie.lua:339-342: -msse2, no FMA, no fast-math)
+# plus -msse3 for _mm_hadd_ps (simd_math.h:111-119) and -ffp-contract=off to make "no FMA" explicit.
+set -euo pipefail
+REF=${LUMIX_REFERENCE:-/root/reference}
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src/core" ]; then
+	echo "build_ref.sh: $REF not present — keeping prebuilt oracle/_ref as is" >&2
+	exit 0
+fi
+mkdir -p "$OUT"
+TMP="$(mktemp -d /tmp/lumix_ref_overlay.XXXXXX)"
+trap 'rm -rf "$TMP"' EXIT
+S="$TMP/src"
+mkdir -p "$S/core" "$S/engine" "$S/renderer" "$S/animation" "$TMP/obj"
+cp -r "$REF/src/core/." "$S/core/"
+cp "$REF"/src/engine/*.h "$S/engine/"
+cp "$REF"/src/renderer/*.h "$S/renderer/"
+cp -r "$REF/src/renderer/gpu" "$S/renderer/"
+cp "$REF/src/renderer/culling_system.cpp" "$REF/src/renderer/pose.cpp" "$S/renderer/"
+cp "$REF"/src/animation/*.h "$S/animation/"
+cp "$REF/src/animation/animation.cpp" "$S/animation/"
+
+# (1) sync.h: SRWLock has no Linux body
+sed -i 's|#error "Not implemented"|pthread_rwlock_t lock;|' "$S/core/sync.h"
+# (2) linux/sync.cpp: stale signature + missing SRWLock methods
+sed -i 's|^void Semaphore::signal()|void Semaphore::signal(u32)|' "$S/core/linux/sync.cpp"
+cat >> "$S/core/linux/sync.cpp" <<'EOF'
+namespace Lumix {
+SRWLock::SRWLock() { pthread_rwlock_init(&lock, nullptr); }
+SRWLock::~SRWLock() { pthread_rwlock_destroy(&lock); }
+void SRWLock::enterExclusive() { pthread_rwlock_wrlock(&lock); }
+void SRWLock::exitExclusive() { pthread_rwlock_unlock(&lock); }
+void SRWLock::enterShared() { pthread_rwlock_rdlock(&lock); }
+void SRWLock::exitShared() { pthread_rwlock_unlock(&lock); }
+}
+EOF
+# (3) simd.h: use the SSE (MSVC) branch on GCC; GCC's __m128 already has + - * built in, so the
+#     overloads of that branch must go (unary minus then differs from the reference's 0-a only in
+#     the sign of zero)
+python3 - "$S/core/simd.h" <<'EOF'
+import sys
+p = sys.argv[1]
+L = open(p).read().split('\n')
+out = []; i = 0; seen_else = False; in_sse = False
+while i < len(L):
+    line = L[i]
+    if 'using float4 = __m128;' in line: in_sse = True
+    if in_sse and line.strip().startswith('#else'): seen_else = True
+    if line.startswith('#if defined _WIN32 && !defined __clang__'):
+        out.append('#if 1'); i += 1; continue
+    if '#include <intrin.h>' in line:
+        out.append('\t#include <immintrin.h>\n\t#include <math.h>\n\t#include <string.h>'); i += 1; continue
+    if not seen_else and 'LUMIX_FORCE_INLINE float4 operator' in line:
+        i += 3
+        if i < len(L) and L[i].strip() == '': i += 1
+        continue
+    out.append(line); i += 1
+open(p, 'w').write('\n'.join(out))
+EOF
+# (4) job_system.cpp: keep getWorker() out of line so &g_worker is recomputed after a fiber switch
+sed -i 's|^WorkerTask\* getWorker()|__attribute__((noinline)) WorkerTask* getWorker()|' "$S/core/job_system.cpp"
+
+CXX=${CXX:-g++}
+FL="-std=c++20 -O2 -DSTATIC_PLUGINS -DNDEBUG -fno-exceptions -fno-rtti -msse2 -msse3 -ffp-contract=off -fPIC -w -fvisibility=hidden -I$S -I$REF/external"
+SRCS="renderer/culling_system core/job_system core/page_allocator core/default_allocator core/arena_allocator
+      core/linux/thread core/linux/sync core/linux/atomic core/linux/fibers core/math core/geometry core/string
+      core/hash core/log core/stream"
+OBJS=""
+for f in $SRCS; do
+	o="$TMP/obj/$(echo "$f" | tr / _).o"
+	$CXX $FL -c "$S/$f.cpp" -o "$o" &
+	OBJS="$OBJS $o"
+done
+$CXX $FL -c "$HERE/ref/ref_stubs.cpp" -o "$TMP/obj/ref_stubs.o" &
+$CXX $FL -c "$HERE/ref/ref_harness.cpp" -o "$TMP/obj/ref_harness.o" &
+wait
+$CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" -lpthread -Wl,--no-undefined
+( cd "$REF" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$OUT/REFERENCE_COMMIT"
+echo "built $OUT/libref_lumix.so"

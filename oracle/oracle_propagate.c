@@ -1,0 +1,50 @@
+/* TEST INFRASTRUCTURE — CPU restatement of the reference's hierarchy propagation (see oracle_math.h).
+ *
+ *   src/engine/world.cpp:255-282  World::transformEntity — DFS over first_child/next_sibling:
+ *                                  child.global = parent.global.compose(child.local_transform)
+ *   src/core/math.cpp:801-807     Transform::compose
+ *   src/renderer/render_module.cpp:1544-1554 onModelInstanceMoved: radius = bounding_radius * max(scale)
+ *
+ * The reference is event-driven; the per-node arithmetic does not depend on traversal
+ * order (each global is compose(parent global, own local)), so the DFS below yields exactly what any
+ * sequence of setTransform() calls on the roots yields.
+ */
+#include "oracle.h"
+
+#include <stdlib.h>
+
+void oracle_propagate(const int32_t* parents, const OTransform* locals, OTransform* globals, uint32_t n) {
+	/* world.h:157-164 Hierarchy{parent, first_child, next_sibling}; built as setParent does (world.cpp:672-676: new child becomes first_child) */
+	int32_t* first_child = (int32_t*)malloc(sizeof(int32_t) * n);
+	int32_t* next_sibling = (int32_t*)malloc(sizeof(int32_t) * n);
+	int32_t* stack = (int32_t*)malloc(sizeof(int32_t) * (n ? n : 1));
+	for (uint32_t i = 0; i < n; ++i) { first_child[i] = -1; next_sibling[i] = -1; }
+	for (uint32_t i = 0; i < n; ++i) {
+		const int32_t p = parents[i];
+		if (p >= 0) { next_sibling[i] = first_child[p]; first_child[p] = (int32_t)i; }
+	}
+	for (uint32_t r = 0; r < n; ++r) {
+		if (parents[r] >= 0) continue;
+		uint32_t sp = 0;
+		stack[sp++] = (int32_t)r;
+		while (sp) {
+			const int32_t e = stack[--sp];
+			const OTransform my_transform = globals[e];                    /* :264 */
+			for (int32_t child = first_child[e]; child >= 0; child = next_sibling[child]) {
+				globals[child] = otransform_compose(&my_transform, &locals[child]); /* :274-276 */
+				stack[sp++] = child;                                           /* :277 recurse */
+			}
+		}
+	}
+	free(first_child); free(next_sibling); free(stack);
+}
+
+void oracle_sphere_radius(const OTransform* globals, const float* bounding_radius, float* out_radius, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) {
+		const OVec3 s = globals[i].scale;
+		/* render_module.cpp:1552 maximum(scale.x, scale.y, scale.z) — math.h minimum/maximum variadic: max(a, max(b, c)) */
+		const float bc = s.y > s.z ? s.y : s.z;
+		const float m = s.x > bc ? s.x : bc;
+		out_radius[i] = bounding_radius[i] * m;
+	}
+}

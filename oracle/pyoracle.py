@@ -1,0 +1,295 @@
+"""TEST INFRASTRUCTURE — ctypes bindings for the CPU oracle (oracle/liboracle_lumix.so, the restatement)
+and, when present, the reference's own compiled code (oracle/_ref/libref_lumix.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module.  The product (lumixengine_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle_lumix.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_lumix.so")
+
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+
+def build(force=False):
+    """Compile the C restatement (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(ORACLE_SO) or any(
+        os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(ORACLE_SO)
+        for f in ("oracle_cull.c", "oracle_propagate.c", "oracle_anim.c", "oracle.h", "oracle_math.h")
+    ):
+        subprocess.check_call(["make", "-s", "-C", HERE])
+    ref_root = os.environ.get("LUMIX_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(ref_root, "src", "core")):
+        srcs = [os.path.join(HERE, "build_ref.sh"), os.path.join(HERE, "ref", "ref_harness.cpp"), os.path.join(HERE, "ref", "ref_stubs.cpp")]
+        if force or not os.path.exists(REF_SO) or any(os.path.getmtime(s) > os.path.getmtime(REF_SO) for s in srcs):
+            subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "pages_total", "pages_filtered", "pages_tested", "pages_inside", "pages_outside",
+        "entities_total", "entities_tested", "entities_inside", "visible", "visible_tested")]
+
+    def asdict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class Track(C.Structure):
+    _fields_ = [("bone_index", C.c_uint16), ("offset_bits", C.c_uint16), ("bitsizes", C.c_uint8 * 3),
+                ("skipped_channel", C.c_uint8), ("min", C.c_float * 3), ("to_range", C.c_float * 3)]
+
+
+class ConstTranslation(C.Structure):
+    _fields_ = [("bone_index", C.c_uint16), ("pad", C.c_uint16), ("value", C.c_float * 3)]
+
+
+class ConstRotation(C.Structure):
+    _fields_ = [("bone_index", C.c_uint16), ("pad", C.c_uint16), ("value", C.c_float * 4)]
+
+
+class Clip(C.Structure):
+    _fields_ = [("fps", C.c_float), ("frame_count", C.c_uint32),
+                ("translations_frame_size_bits", C.c_uint32), ("rotations_frame_size_bits", C.c_uint32),
+                ("n_translations", C.c_uint32), ("n_const_translations", C.c_uint32),
+                ("n_rotations", C.c_uint32), ("n_const_rotations", C.c_uint32),
+                ("translations", vp), ("const_translations", vp), ("rotations", vp), ("const_rotations", vp),
+                ("translation_stream", vp), ("rotation_stream", vp)]
+
+
+class Skeleton(C.Structure):
+    _fields_ = [("bone_count", C.c_uint32), ("first_nonroot_bone_index", C.c_int32),
+                ("parents", vp), ("bind_relative", vp), ("inverse_bind", vp)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        L = C.CDLL(ORACLE_SO)
+        L.oracle_culling_create.restype = vp
+        L.oracle_culling_cull.restype = C.c_uint32
+        L.oracle_culling_page_count.restype = C.c_uint32
+        L.oracle_culling_get_radius.restype = C.c_float
+        L.oracle_time_advance.restype = C.c_uint32
+        _lib = L
+    return _lib
+
+
+def frustum_perspective(pos, direction, up, fov, ratio, near, far):
+    """-> 256-byte ShiftedFrustum image (np.uint8[256]); geometry.cpp:470-499."""
+    out = np.zeros(256, np.uint8)
+    lib().oracle_frustum_perspective(_ptr(out), (C.c_double * 3)(*pos), (C.c_float * 3)(*direction), (C.c_float * 3)(*up),
+                                     C.c_float(fov), C.c_float(ratio), C.c_float(near), C.c_float(far))
+    return out
+
+
+def frustum_ortho(pos, direction, up, width, height, near, far):
+    out = np.zeros(256, np.uint8)
+    lib().oracle_frustum_ortho(_ptr(out), (C.c_double * 3)(*pos), (C.c_float * 3)(*direction), (C.c_float * 3)(*up),
+                               C.c_float(width), C.c_float(height), C.c_float(near), C.c_float(far))
+    return out
+
+
+def rng_floats(u, v, n):
+    uu, vv = C.c_uint32(u), C.c_uint32(v)
+    out = np.empty(n, np.float32)
+    lib().oracle_rng_floats(C.byref(uu), C.byref(vv), C.c_uint32(n), _ptr(out))
+    return out, (uu.value, vv.value)
+
+
+class OracleCulling:
+    """Restated CullingSystemImpl (culling_system.cpp:67-383)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = vp(self.L.oracle_culling_create())
+
+    def __del__(self):
+        try:
+            self.L.oracle_culling_destroy(self.h)
+        except Exception:
+            pass
+
+    def add(self, entities, types, pos, radius):
+        e = np.ascontiguousarray(entities, np.int32)
+        t = np.ascontiguousarray(types, np.uint8)
+        p = np.ascontiguousarray(pos, np.float64)
+        r = np.ascontiguousarray(radius, np.float32)
+        self.L.oracle_culling_add_many(self.h, _ptr(e), _ptr(t), _ptr(p), _ptr(r), C.c_uint32(len(e)))
+
+    def set(self, entities, pos, radius):
+        e = np.ascontiguousarray(entities, np.int32)
+        p = np.ascontiguousarray(pos, np.float64)
+        r = np.ascontiguousarray(radius, np.float32)
+        self.L.oracle_culling_set_many(self.h, _ptr(e), _ptr(p), _ptr(r), C.c_uint32(len(e)))
+
+    def set_position(self, entities, pos):
+        e = np.ascontiguousarray(entities, np.int32)
+        p = np.ascontiguousarray(pos, np.float64)
+        self.L.oracle_culling_set_position_many(self.h, _ptr(e), _ptr(p), C.c_uint32(len(e)))
+
+    def set_radius(self, entities, radius):
+        e = np.ascontiguousarray(entities, np.int32)
+        r = np.ascontiguousarray(radius, np.float32)
+        self.L.oracle_culling_set_radius_many(self.h, _ptr(e), _ptr(r), C.c_uint32(len(e)))
+
+    def remove(self, entities):
+        e = np.ascontiguousarray(entities, np.int32)
+        self.L.oracle_culling_remove_many(self.h, _ptr(e), C.c_uint32(len(e)))
+
+    def get_radius(self, entity):
+        return float(self.L.oracle_culling_get_radius(self.h, C.c_int32(entity)))
+
+    def is_added(self, entity):
+        return bool(self.L.oracle_culling_is_added(self.h, C.c_int32(entity)))
+
+    def page_count(self):
+        return int(self.L.oracle_culling_page_count(self.h))
+
+    def cull(self, frustum256, type=-1, cap=None, want_ids=True):
+        """-> (ids uint32[V], types uint8[V], stats dict); order = m_cells order (a legal order)."""
+        st = Stats()
+        f = np.ascontiguousarray(frustum256, np.uint8)
+        if not want_ids:
+            n = self.L.oracle_culling_cull(self.h, _ptr(f), C.c_int(type), None, None, C.c_uint32(0), C.byref(st))
+            return None, None, st.asdict()
+        if cap is None:
+            cap = self.L.oracle_culling_cull(self.h, _ptr(f), C.c_int(type), None, None, C.c_uint32(0), C.byref(st))
+        ids = np.empty(max(cap, 1), np.uint32)
+        tys = np.empty(max(cap, 1), np.uint8)
+        n = self.L.oracle_culling_cull(self.h, _ptr(f), C.c_int(type), _ptr(ids), _ptr(tys), C.c_uint32(cap), C.byref(st))
+        n = min(n, cap)
+        return ids[:n], tys[:n], st.asdict()
+
+    def pages(self):
+        """Dump of every page of m_cells: list of dicts (origin, indices, type, is_big, count, spheres, entities)."""
+        out = []
+        for i in range(self.page_count()):
+            o = (C.c_double * 3)()
+            ind = (C.c_int * 3)()
+            ty, big, cnt = C.c_uint8(), C.c_uint8(), C.c_int()
+            sph = np.empty((201, 4), np.float32)
+            ent = np.empty(201, np.int32)
+            self.L.oracle_culling_get_page(self.h, C.c_uint32(i), o, ind, C.byref(ty), C.byref(big), C.byref(cnt), _ptr(sph), _ptr(ent))
+            c = cnt.value
+            out.append(dict(origin=tuple(o), indices=tuple(ind), type=ty.value, is_big=big.value, count=c,
+                            spheres=sph[:c].copy(), entities=ent[:c].copy()))
+        return out
+
+
+def propagate(parents, locals56, globals56):
+    """world.cpp:255-282 over a forest. locals56/globals56: uint8[n,56] images of Transform. Returns new globals."""
+    p = np.ascontiguousarray(parents, np.int32)
+    l = np.ascontiguousarray(locals56, np.uint8)
+    g = np.array(globals56, np.uint8, copy=True, order="C")
+    lib().oracle_propagate(_ptr(p), _ptr(l), _ptr(g), C.c_uint32(len(p)))
+    return g
+
+
+def sphere_radius(globals56, bounding_radius):
+    g = np.ascontiguousarray(globals56, np.uint8)
+    b = np.ascontiguousarray(bounding_radius, np.float32)
+    out = np.empty(len(b), np.float32)
+    lib().oracle_sphere_radius(_ptr(g), _ptr(b), _ptr(out), C.c_uint32(len(b)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference's own compiled code
+# ---------------------------------------------------------------------------------------------------
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        L.ref_culling_create.restype = vp
+        L.ref_culling_cull.restype = C.c_uint32
+        L.ref_culling_get_radius.restype = C.c_float
+        _ref = L
+    return _ref
+
+
+def ref_frustum_perspective(pos, direction, up, fov, ratio, near, far):
+    out = np.zeros(256, np.uint8)
+    ref().ref_frustum_perspective((C.c_double * 3)(*pos), (C.c_float * 3)(*direction), (C.c_float * 3)(*up),
+                                  C.c_float(fov), C.c_float(ratio), C.c_float(near), C.c_float(far), _ptr(out))
+    return out
+
+
+def ref_frustum_ortho(pos, direction, up, width, height, near, far):
+    out = np.zeros(256, np.uint8)
+    ref().ref_frustum_ortho((C.c_double * 3)(*pos), (C.c_float * 3)(*direction), (C.c_float * 3)(*up),
+                            C.c_float(width), C.c_float(height), C.c_float(near), C.c_float(far), _ptr(out))
+    return out
+
+
+class RefCulling:
+    """The reference's CullingSystemImpl (overlay build) on the reference's job system."""
+
+    def __init__(self, workers=1):
+        self.L = ref()
+        self.workers = self.L.ref_jobs_init(C.c_int(workers))
+        if not self.workers:
+            raise RuntimeError("reference job system failed to initialise")
+        self.h = vp(self.L.ref_culling_create())
+
+    def add(self, entities, types, pos, radius):
+        e = np.ascontiguousarray(entities, np.int32)
+        t = np.ascontiguousarray(types, np.uint8)
+        p = np.ascontiguousarray(pos, np.float64)
+        r = np.ascontiguousarray(radius, np.float32)
+        self.L.ref_culling_add(self.h, _ptr(e), _ptr(t), _ptr(p), _ptr(r), C.c_uint32(len(e)))
+
+    def set(self, entities, pos, radius):
+        e = np.ascontiguousarray(entities, np.int32)
+        p = np.ascontiguousarray(pos, np.float64)
+        r = np.ascontiguousarray(radius, np.float32)
+        self.L.ref_culling_set(self.h, _ptr(e), _ptr(p), _ptr(r), C.c_uint32(len(e)))
+
+    def set_position(self, entities, pos):
+        e = np.ascontiguousarray(entities, np.int32)
+        p = np.ascontiguousarray(pos, np.float64)
+        self.L.ref_culling_set_position(self.h, _ptr(e), _ptr(p), C.c_uint32(len(e)))
+
+    def set_radius(self, entities, radius):
+        e = np.ascontiguousarray(entities, np.int32)
+        r = np.ascontiguousarray(radius, np.float32)
+        self.L.ref_culling_set_radius(self.h, _ptr(e), _ptr(r), C.c_uint32(len(e)))
+
+    def remove(self, entities):
+        e = np.ascontiguousarray(entities, np.int32)
+        self.L.ref_culling_remove(self.h, _ptr(e), C.c_uint32(len(e)))
+
+    def cull(self, frustum256, type=-1, cap=0, iters=1):
+        """-> (ids, types, dict(best_s, median_s, first_s, pages)); ids in the reference's job-completion order."""
+        f = np.ascontiguousarray(frustum256, np.uint8)
+        ids = np.empty(max(cap, 1), np.uint32)
+        tys = np.empty(max(cap, 1), np.uint8)
+        times = (C.c_double * 3)()
+        pages = C.c_uint32()
+        n = self.L.ref_culling_cull(self.h, _ptr(f), C.c_int(type), _ptr(ids), _ptr(tys), C.c_uint32(cap), C.c_int(iters), times, C.byref(pages))
+        if n == 0xFFFFFFFF:
+            raise RuntimeError("reference job system not initialised")
+        k = min(n, cap)
+        return ids[:k], tys[:k], dict(count=int(n), best_s=times[0], median_s=times[1], first_s=times[2], pages=int(pages.value))
