@@ -1,0 +1,275 @@
+/* lumix_b200.h — C-ABI of the B200-native LumixEngine hot path (cull / hierarchy propagate / pose + skin palette).
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  Every entry point returns LB200_OK (0) or a negative
+ * lb200_status; lb200_last_error() gives the text.  There is no CPU fallback: without a CUDA device every compute
+ * entry point fails with LB200_ERR_NO_DEVICE.
+ *
+ * Each block cites the reference interface it replaces (paths relative to the LumixEngine tree).
+ * INTEGRATION.md shows the engine-side C++ that binds these (CullingSystem::create body, World, AnimationModule).
+ */
+#ifndef LUMIX_B200_H
+#define LUMIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB200_API __attribute__((visibility("default")))
+
+typedef enum {
+	LB200_OK = 0,
+	LB200_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product has no CPU path */
+	LB200_ERR_CUDA = -2,        /* a CUDA runtime call failed; see lb200_last_error */
+	LB200_ERR_INVALID = -3,     /* bad argument (null pointer, type == 0xff where reserved, index out of range) */
+	LB200_ERR_CAPACITY = -4,    /* caller-provided output buffer too small */
+	LB200_ERR_NCCL = -5,        /* NCCL not loadable or a collective failed */
+	LB200_ERR_STATE = -6        /* call order violated (e.g. cull before any page was uploaded) */
+} lb200_status;
+
+typedef struct lb200_ctx lb200_ctx;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Context = one GPU, one stream.  Replaces nothing in the reference (it has no device); owned by the ISystem
+ * the plugin entry creates (src/engine/plugin.h:64-96).
+ * ---------------------------------------------------------------------------------------------------------- */
+LB200_API int lb200_init(int device_ordinal, lb200_ctx** out_ctx);
+LB200_API void lb200_shutdown(lb200_ctx* ctx);
+LB200_API const char* lb200_last_error(const lb200_ctx* ctx); /* ctx may be NULL: last init error */
+LB200_API int lb200_device_count(void);
+LB200_API int lb200_synchronize(lb200_ctx* ctx);
+/* Kernels this library launched on ctx since init (bench.py's gpu_launches). */
+LB200_API uint64_t lb200_launch_count(const lb200_ctx* ctx);
+/* cudaStream_t of the context as an integer (for CUDA-event timing on the launching stream). */
+LB200_API uint64_t lb200_stream_handle(const lb200_ctx* ctx);
+/* Page-locked host memory for result buffers (the engine would pass memory from its own allocators, registered once). */
+LB200_API void* lb200_host_alloc(lb200_ctx* ctx, size_t bytes);
+LB200_API void lb200_host_free(lb200_ctx* ctx, void* p);
+/* Device-time helpers: record a timestamp on the context stream / milliseconds between two of them (CUDA events). */
+LB200_API int lb200_event_create(lb200_ctx* ctx, void** out_event);
+LB200_API int lb200_event_record(lb200_ctx* ctx, void* event);
+LB200_API int lb200_event_elapsed_ms(lb200_ctx* ctx, void* start, void* stop, float* out_ms);
+LB200_API void lb200_event_destroy(lb200_ctx* ctx, void* event);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * POD images of reference structs that cross the boundary (layouts verified against the reference build,
+ * SURVEY.md §8a).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* ShiftedFrustum, src/core/geometry.h:99-149 — 256 bytes: xs[8] ys[8] zs[8] ds[8] (planes NEAR,FAR,LEFT,RIGHT,TOP,
+ * BOTTOM,EXTRA0,EXTRA1), Vec3 points[8], DVec3 origin at +224.  Built on the host by the engine's own
+ * ShiftedFrustum::computePerspective/computeOrtho (geometry.cpp:390-409,470-499) or by lb200_frustum_* below. */
+typedef struct {
+	float xs[8], ys[8], zs[8], ds[8];
+	float points[8][3];
+	double origin[3];
+	uint64_t pad_; /* the reference struct is alignas(16): sizeof == 256 */
+} lb200_shifted_frustum;
+
+/* Transform, src/core/math.h:306-327 — 56 bytes: DVec3 pos, Quat rot (xyzw), Vec3 scale. */
+typedef struct {
+	double pos[3];
+	float rot[4];
+	float scale[3];
+} lb200_transform;
+
+/* Host-side frustum construction, same arithmetic as geometry.cpp:390-409,470-499 (viewport {-1,-1}..{1,1}). */
+LB200_API void lb200_frustum_perspective(lb200_shifted_frustum* out, const double position[3], const float direction[3], const float up[3],
+	float fov, float ratio, float near_distance, float far_distance);
+LB200_API void lb200_frustum_ortho(lb200_shifted_frustum* out, const double position[3], const float direction[3], const float up[3],
+	float width, float height, float near_distance, float far_distance);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CullingSystem — replaces struct CullingSystem, src/renderer/culling_system.h:58-77 (one C function per virtual,
+ * same argument meaning), implementation src/renderer/culling_system.cpp:67-403.
+ *
+ * The host keeps the reference's bookkeeping (300 m cell grid, pages of <=200 spheres, entity->slot map,
+ * culling_system.cpp:98-258) and mirrors dirty pages to HBM before the next cull; cull itself runs on the GPU.
+ * entity = EntityRef::index (src/engine/lumix.h:10-44).  type = RenderableTypes value (render_module.h:293-301);
+ * 0xff is reserved for "all types" exactly as culling_system.cpp:310-319.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lb200_culling lb200_culling;
+
+#define LB200_TYPE_ALL 0xff
+#define LB200_PAGE_SLOTS 200u   /* CellPage::MAX_COUNT - 1, culling_system.cpp:61,103 */
+#define LB200_CELL_SIZE 300.0f  /* culling_system.cpp:75 */
+
+/* CullingSystem::create, culling_system.cpp:399-402 */
+LB200_API int lb200_culling_create(lb200_ctx* ctx, lb200_culling** out);
+LB200_API void lb200_culling_destroy(lb200_culling* cs);
+/* culling_system.cpp:131-157 / 160-187 / 198-214 / 242-258 / 222-240 / 217-220 / 372-375 */
+LB200_API int lb200_culling_add(lb200_culling* cs, int32_t entity, uint8_t type, const double pos[3], float radius);
+LB200_API int lb200_culling_remove(lb200_culling* cs, int32_t entity);
+LB200_API int lb200_culling_set_position(lb200_culling* cs, int32_t entity, const double pos[3]);
+LB200_API int lb200_culling_set_radius(lb200_culling* cs, int32_t entity, float radius);
+LB200_API int lb200_culling_set(lb200_culling* cs, int32_t entity, const double pos[3], float radius);
+LB200_API float lb200_culling_get_radius(const lb200_culling* cs, int32_t entity);
+LB200_API int lb200_culling_is_added(const lb200_culling* cs, int32_t entity);
+/* batch forms of the same calls (one FFI crossing for n entities) */
+LB200_API int lb200_culling_add_many(lb200_culling* cs, const int32_t* entities, const uint8_t* types, const double* pos3, const float* radius, uint32_t n);
+LB200_API int lb200_culling_set_many(lb200_culling* cs, const int32_t* entities, const double* pos3, const float* radius, uint32_t n);
+LB200_API int lb200_culling_set_position_many(lb200_culling* cs, const int32_t* entities, const double* pos3, uint32_t n);
+LB200_API int lb200_culling_set_radius_many(lb200_culling* cs, const int32_t* entities, const float* radius, uint32_t n);
+LB200_API int lb200_culling_remove_many(lb200_culling* cs, const int32_t* entities, uint32_t n);
+
+/* Bookkeeping introspection (tests compare it with the reference's m_cells state). */
+LB200_API uint32_t lb200_culling_page_count(const lb200_culling* cs);
+LB200_API uint32_t lb200_culling_entity_count(const lb200_culling* cs);
+LB200_API int lb200_culling_get_page(const lb200_culling* cs, uint32_t page, double origin[3], int32_t indices[3], uint8_t* type, uint8_t* is_big,
+	uint32_t* count, float* spheres4 /* count*4 or NULL */, int32_t* entities /* count or NULL */);
+
+/* Result of one cull: visible entity ids grouped by renderable type.  ids[type_offset[t] .. type_offset[t]+type_count[t])
+ * are the visible entities of type t (order inside a type is unspecified, as in the reference: SURVEY.md F4).
+ * This is the flat form of the CullResult page chain (culling_system.h:17-56): one chain page = <=1020 ids of one type. */
+typedef struct {
+	uint32_t total;            /* sum of type_count */
+	uint32_t n_types;          /* highest type with entities + 1 */
+	uint32_t type_count[256];
+	uint32_t type_offset[256];
+	/* counters of the last cull (pages by classification, culling_system.cpp:342-363) */
+	uint32_t pages_tested, pages_inside, pages_outside, pages_filtered;
+	uint32_t entities_tested, entities_inside;
+} lb200_cull_result;
+
+/* CullingSystem::cull(frustum, type) / cull(frustum), culling_system.cpp:310-369.
+ * Uploads dirty pages + the frustum, runs the cull kernel, copies the visible ids to `out_ids` (host, capacity in ids;
+ * pinned memory makes the copy faster).  type == LB200_TYPE_ALL culls every type.  Returns LB200_ERR_CAPACITY if
+ * `capacity` < visible count (result->total still holds the needed size).  With zero pages: total = 0 (the reference
+ * returns nullptr, culling_system.cpp:322). */
+LB200_API int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity,
+	lb200_cull_result* result);
+
+/* Device-resident form: the same cull, result left in HBM (no D2H of ids).  *out_dev_ids receives the device pointer of the
+ * id buffer (valid until the next cull on this object); counts land in `result` (a 2 KB D2H).  With want_counts = 0 nothing is
+ * read back and the call is fully asynchronous on the context stream (result may be NULL). */
+LB200_API int lb200_culling_cull_device(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
+	lb200_cull_result* result, int want_counts);
+/* Push pending page edits to HBM now (otherwise done lazily by the next cull). */
+LB200_API int lb200_culling_flush(lb200_culling* cs);
+/* Visibility bitmask of the last cull: bit (page*256 + slot); 8 words per page.  Copies page_count*8 words. */
+LB200_API int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t capacity_words);
+/* Bench support: keep `replicas` identical copies of the page arrays in HBM and rotate through them on successive culls so that
+ * back-to-back timed culls never re-read an L2-resident scene (B200_PROFILING.md "Timing hygiene"). */
+LB200_API int lb200_culling_set_replicas(lb200_culling* cs, uint32_t replicas);
+/* Algorithmic HBM bytes of the last cull: page descriptors + 16 B per tested sphere + 4 B per id read + 4 B per id written + mask. */
+LB200_API uint64_t lb200_culling_last_algorithmic_bytes(const lb200_culling* cs);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  NCCL is dlopen()ed; the unique id travels through the caller
+ * (torch.distributed store / any out-of-band channel).
+ * ---------------------------------------------------------------------------------------------------------- */
+LB200_API int lb200_comm_get_unique_id(lb200_ctx* ctx, uint8_t out_id[128]);
+LB200_API int lb200_comm_init(lb200_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]);
+LB200_API void lb200_comm_destroy(lb200_ctx* ctx);
+/* After a cull on every rank: all-gather the per-rank visible lists.  out_counts[r*256 + t] = rank r's count of type t;
+ * *out_dev_ids = device pointer to n_ranks slabs of `slab_ids` ids each (rank r's ids at r*slab_ids, laid out as its
+ * lb200_cull_result says).  One ncclAllGather of counts + one of the padded id slabs. */
+LB200_API int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_ids, uint32_t* out_counts /* n_ranks*256 */);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Hierarchy — replaces the recursion World::transformEntity, src/engine/world.cpp:255-282 (child.global =
+ * parent.global.compose(child.local), math.cpp:801-807) with a batched level-order pass.
+ * Nodes are given in any order with parent indices (-1 = root); the library orders them by depth once.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lb200_hierarchy lb200_hierarchy;
+
+LB200_API int lb200_hierarchy_create(lb200_ctx* ctx, const int32_t* parents, uint32_t n, lb200_hierarchy** out);
+LB200_API void lb200_hierarchy_destroy(lb200_hierarchy* h);
+LB200_API uint32_t lb200_hierarchy_depth(const lb200_hierarchy* h);
+/* World::setLocalTransform for all nodes (world.h:98-123): upload locals (n Transforms, caller's node order). */
+LB200_API int lb200_hierarchy_set_locals(lb200_hierarchy* h, const lb200_transform* locals);
+/* Root world transforms (entries of non-root nodes are ignored). */
+LB200_API int lb200_hierarchy_set_root_globals(lb200_hierarchy* h, const lb200_transform* globals);
+/* Run the propagation on the GPU; globals stay in HBM. */
+LB200_API int lb200_hierarchy_propagate(lb200_hierarchy* h);
+/* World::getTransforms (world.h:65): copy globals back in the caller's node order. */
+LB200_API int lb200_hierarchy_get_globals(lb200_hierarchy* h, lb200_transform* out_globals);
+/* RenderModuleImpl::onModelInstanceMoved, render_module.cpp:1544-1554: world sphere per node =
+ * (global.pos, bounding_radius * max(scale)); out_pos3 n*3 doubles, out_radius n floats (host). */
+LB200_API int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius, double* out_pos3, float* out_radius);
+LB200_API uint64_t lb200_hierarchy_algorithmic_bytes(const lb200_hierarchy* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Animation — replaces AnimationModuleImpl::updateAnimable (src/animation/animation_module.cpp:439-472):
+ * Model::getRelativePose (model.cpp:226-237) -> Animation::getRelativePose (animation.cpp:117-204) ->
+ * Pose::computeAbsolute (pose.cpp:66-133), then the palette builds computeSkeletonDualQuats
+ * (src/renderer/pipeline.cpp:2680-2745) / computeSkinMatrices (src/renderer/model.cpp:132-137) and the CPU
+ * skinning evaluateSkin (model.cpp:103-109).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Animation::TranslationTrack / RotationTrack, src/animation/animation.h:92-118, pointer-free */
+typedef struct {
+	uint16_t bone_index;
+	uint16_t offset_bits;
+	uint8_t bitsizes[3];
+	uint8_t skipped_channel; /* rotation tracks only */
+	float min[3];
+	float to_range[3];
+} lb200_track; /* 32 bytes */
+
+typedef struct { uint16_t bone_index; uint16_t pad; float value[3]; } lb200_const_translation; /* animation.h:86-90 */
+typedef struct { uint16_t bone_index; uint16_t pad; float value[4]; } lb200_const_rotation;    /* animation.h:100-104 */
+
+/* struct Animation, animation.h:158-170 (in-memory form after Animation::load, animation.cpp:397-493) */
+typedef struct {
+	float fps;
+	uint32_t frame_count;
+	uint32_t translations_frame_size_bits, rotations_frame_size_bits;
+	uint32_t n_translations, n_const_translations, n_rotations, n_const_rotations;
+	const lb200_track* translations;
+	const lb200_const_translation* const_translations;
+	const lb200_track* rotations;
+	const lb200_const_rotation* const_rotations;
+	const uint8_t* translation_stream; uint32_t translation_stream_bytes; /* incl. the 8-byte tail padding, animation.cpp:439 */
+	const uint8_t* rotation_stream; uint32_t rotation_stream_bytes;
+} lb200_clip;
+
+/* Model skeleton, src/renderer/model.h:154-166,225-244: parents (parent < child, model.cpp:381-384), bind pose relative
+ * transforms (Bone::relative_transform) and inverse bind transforms; each transform = 7 floats (pos xyz, rot xyzw). */
+typedef struct {
+	uint32_t bone_count;               /* <= 196, model.h:155 */
+	int32_t first_nonroot_bone_index;  /* model.h getFirstNonrootBoneIndex */
+	const int16_t* parents;
+	const float* bind_relative7;
+	const float* inverse_bind7;
+} lb200_skeleton;
+
+/* Mesh::Skin, model.h:81-84 + positions: n_vertices * {pos[3]}, {weights[4]}, {indices[4] i16} */
+typedef struct {
+	uint32_t n_vertices;
+	const float* positions3;
+	const float* weights4;
+	const int16_t* indices4;
+} lb200_mesh;
+
+typedef struct lb200_animation lb200_animation;
+
+#define LB200_PALETTE_DUAL_QUAT 1u  /* 32 B/bone, pipeline.cpp:2680-2745 */
+#define LB200_PALETTE_MATRIX 2u     /* 64 B/bone, model.cpp:132-137 */
+#define LB200_PALETTE_POSE 4u       /* absolute pose write-back (pos 12 B + rot 16 B per bone) for lockPose consumers */
+
+LB200_API int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* skeleton, const lb200_clip* clips, uint32_t n_clips,
+	const lb200_mesh* mesh /* may be NULL */, uint32_t max_instances, lb200_animation** out);
+LB200_API void lb200_animation_destroy(lb200_animation* a);
+/* Per-instance state: Animable{time, animation}, animation_module.h:17-21.  time in Time ticks (1 s = 32768, animation.h:17-43). */
+LB200_API int lb200_animation_set_instances(lb200_animation* a, const uint32_t* clip_index, const uint32_t* time_ticks, uint32_t n);
+/* One updateAnimables pass (animation_module.cpp:737-749) for all instances: evaluate at the current time, build the requested
+ * palettes in HBM, then advance time by time_delta seconds (time = (time + dt) % length, :458-461). */
+LB200_API int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t palette_flags);
+/* evaluateSkin (model.cpp:103-109) for every vertex of every instance from the matrix palette; output stays in HBM. */
+LB200_API int lb200_animation_skin(lb200_animation* a);
+/* Read-backs (host buffers).  Instances [first, first+count). */
+LB200_API int lb200_animation_get_dual_quats(lb200_animation* a, uint32_t first, uint32_t count, float* out8);
+LB200_API int lb200_animation_get_matrices(lb200_animation* a, uint32_t first, uint32_t count, float* out16);
+LB200_API int lb200_animation_get_pose(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3, float* out_rot4);
+LB200_API int lb200_animation_get_times(lb200_animation* a, uint32_t first, uint32_t count, uint32_t* out_ticks);
+LB200_API int lb200_animation_get_skinned(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3);
+/* Checksum of the skinned vertex buffer computed on the device (sum of the raw u32 bit patterns, mod 2^64) —
+ * a size-independent property for full-size parity runs. */
+LB200_API int lb200_animation_skinned_checksum(lb200_animation* a, uint64_t* out);
+LB200_API uint64_t lb200_animation_algorithmic_bytes(const lb200_animation* a, uint32_t palette_flags, int skin);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMIX_B200_H */

@@ -1,0 +1,544 @@
+// GPU pose evaluation + skinning palette + vertex skinning: kernels + C-ABI (include/lumix_b200.h "Animation").
+//
+// pose_palette_kernel — one warp per skeletal instance, the pose lives in shared memory:
+//   Model::getRelativePose (src/renderer/model.cpp:226-237)            bind pose -> smem
+//   AnimationSampler::getRelativePose<false,false> (src/animation/animation.cpp:117-204): const tracks, bit-packed
+//     translation tracks (unpackChannel through double, :313-334), smallest-three rotation tracks + simd_nlerp (:30-95)
+//   Pose::computeAbsolute (src/renderer/pose.cpp:66-133)               level-synchronous inside the warp
+//   computeSkeletonDualQuats (src/renderer/pipeline.cpp:2680-2745) / computeSkinMatrices (src/renderer/model.cpp:132-137)
+//     palette[j] = toDualQuat / toMatrix ({pos[j], rot[j]} * inverse_bind[j]) written once, coalesced
+//   time advance of updateAnimable (src/animation/animation_module.cpp:458-469)
+// skin_kernel — evaluateSkin (model.cpp:103-109): palette of each instance staged in shared memory as 3x4 rows,
+//   one thread per vertex, vertex data kept in registers across the instances of a group.
+// Clips, skeleton and mesh are shared by all instances (L2-resident); HBM traffic is the per-instance output.
+#include "lb200_internal.h"
+#include "lb200_math.cuh"
+
+#include <new>
+#include <vector>
+
+namespace {
+
+using namespace lb;
+
+struct DevClip {
+	float fps;
+	uint32_t frame_count;
+	uint32_t t_bits, r_bits;          // frame sizes in bits
+	uint32_t n_t, n_ct, n_r, n_cr;
+	uint32_t t_off, ct_off, r_off, cr_off; // first element in the flat track arrays
+	uint32_t t_stream, r_stream;      // byte offsets of the bit streams inside the stream blob (multiples of 4)
+	uint32_t length_ticks;            // Animation::getLength(), animation.h:128
+	uint32_t pad;
+};
+
+struct AnimParams {
+	const DevClip* clips;
+	const lb200_track* tracks;
+	const lb200_const_translation* const_t;
+	const lb200_const_rotation* const_r;
+	const uint32_t* stream; // all bit streams, word-addressed
+	const float* bind7;     // bone_count * 7
+	const float* inv_bind7; // bone_count * 7
+	const short* parents;
+	const unsigned char* levels; // depth of each bone below its root (0 = left as is)
+	uint32_t bone_count;
+	uint32_t max_level;
+	uint32_t n_instances;
+	const uint32_t* clip_index;
+	uint32_t* time_ticks;
+	float* out_dq;    // n * B * 8 or null
+	float* out_mtx;   // n * B * 16 or null
+	float* out_pos;   // n * B * 3 or null
+	float* out_rot;   // n * B * 4 or null
+	uint32_t dt_ticks;   // |time_delta| in ticks
+	int dt_negative;
+	int advance;
+};
+
+// unaligned little-endian u64 at byte address `byte` of a word-addressed stream (the reference memcpy's 8 bytes, animation.cpp:44)
+__device__ __forceinline__ unsigned long long load_u64_unaligned(const uint32_t* __restrict__ words, uint32_t byte) {
+	const uint32_t w = byte >> 2;
+	const uint32_t sh = (byte & 3u) * 8u;
+	const uint32_t a = __ldg(words + w), b = __ldg(words + w + 1), c = __ldg(words + w + 2);
+	const uint32_t lo = __funnelshift_r(a, b, sh);
+	const uint32_t hi = __funnelshift_r(b, c, sh);
+	return ((unsigned long long)hi << 32) | lo;
+}
+
+// animation.cpp:313-316 unpackChannel: float(min + to_float_range * double(val & mask))
+__device__ __forceinline__ float unpack_channel(unsigned long long val, float mn, float range, uint32_t bits) {
+	const unsigned long long mask = (1ull << bits) - 1ull;
+	return __double2float_rn(LB_DADD((double)mn, LB_DMUL((double)range, __ull2double_rn(val & mask))));
+}
+
+// animation.cpp:318-334 Animation::getTranslation
+__device__ __forceinline__ V3 get_translation(const uint32_t* __restrict__ stream, uint32_t frame_bits, uint32_t frame, const lb200_track& tr) {
+	const uint32_t offset = frame_bits * frame + tr.offset_bits;
+	unsigned long long tmp = load_u64_unaligned(stream, offset >> 3);
+	tmp >>= (offset & 7u);
+	V3 r;
+	r.x = unpack_channel(tmp, tr.min[0], tr.to_range[0], tr.bitsizes[0]);
+	tmp >>= tr.bitsizes[0];
+	r.y = unpack_channel(tmp, tr.min[1], tr.to_range[1], tr.bitsizes[1]);
+	tmp >>= tr.bitsizes[1];
+	r.z = unpack_channel(tmp, tr.min[2], tr.to_range[2], tr.bitsizes[2]);
+	return r;
+}
+
+// animation.cpp:51-77 one packed rotation sample -> quaternion (smallest-three)
+__device__ __forceinline__ Q4 unpack_rotation(unsigned long long packed, const lb200_track& tr) {
+	const bool is_negative = (packed & 1ull) != 0;
+	packed >>= 1;
+	const unsigned long long mask_x = (1ull << tr.bitsizes[0]) - 1ull;
+	const unsigned long long mask_y = (1ull << tr.bitsizes[1]) - 1ull;
+	const unsigned long long mask_z = (1ull << tr.bitsizes[2]) - 1ull;
+	const unsigned long long py = packed >> tr.bitsizes[0];
+	const unsigned long long pz = py >> tr.bitsizes[1];
+	V3 v;
+	v.x = LB_FADD(tr.min[0], LB_FMUL(tr.to_range[0], __ull2float_rn(packed & mask_x)));
+	v.y = LB_FADD(tr.min[1], LB_FMUL(tr.to_range[1], __ull2float_rn(py & mask_y)));
+	v.z = LB_FADD(tr.min[2], LB_FMUL(tr.to_range[2], __ull2float_rn(pz & mask_z)));
+	const float rem = LB_FSUB(1.0f, dot(v, v));
+	const float skipped = LB_FMUL(LB_FSQRT(rem > 0.f ? rem : 0.f), is_negative ? -1.0f : 1.0f); // maximum(0.f, x): 0 > x ? 0 : x
+	switch (tr.skipped_channel) {
+		case 0: return q4(skipped, v.x, v.y, v.z);
+		case 1: return q4(v.x, skipped, v.y, v.z);
+		case 2: return q4(v.x, v.y, skipped, v.z);
+		default: return q4(v.x, v.y, v.z, skipped);
+	}
+}
+
+constexpr int POSE_WARPS = 4;
+
+__global__ void __launch_bounds__(POSE_WARPS * 32) pose_palette_kernel(const __grid_constant__ AnimParams P) {
+	extern __shared__ float smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const uint32_t B = P.bone_count;
+	// per warp: pos[B] (3 floats) then rot[B] (4 floats)
+	float* s_pos = smem + (size_t)warp * B * 7;
+	float* s_rot = s_pos + (size_t)B * 3;
+	const uint32_t inst = blockIdx.x * POSE_WARPS + warp;
+	if (inst >= P.n_instances) return;
+
+	const DevClip clip = P.clips[P.clip_index[inst]];
+	const uint32_t ticks = P.time_ticks[inst];
+
+	// animation.h:27 toFrame: float(value / double(ONE_SECOND) * fps); animation.cpp:131-133
+	const float frame = __double2float_rn(LB_DMUL(__uint2double_rn(ticks) / 32768.0, (double)clip.fps));
+	const float hi = LB_FSUB(__uint2float_rn(clip.frame_count), 0.00001f);
+	float sample = frame > 0.f ? frame : 0.f; // maximum(value, min): value > min ? value : min
+	sample = sample < hi ? sample : hi;       // minimum(x, max)
+	const uint32_t sample_idx = (uint32_t)sample;
+	const float t = LB_FSUB(sample, __uint2float_rn(sample_idx));
+
+	// Model::getRelativePose
+	for (uint32_t b = lane; b < B; b += 32) {
+		const float* src = P.bind7 + (size_t)b * 7;
+		s_pos[b * 3 + 0] = src[0]; s_pos[b * 3 + 1] = src[1]; s_pos[b * 3 + 2] = src[2];
+		s_rot[b * 4 + 0] = src[3]; s_rot[b * 4 + 1] = src[4]; s_rot[b * 4 + 2] = src[5]; s_rot[b * 4 + 3] = src[6];
+	}
+	__syncwarp();
+	// animation.cpp:135-149 constant translations
+	for (uint32_t i = lane; i < clip.n_ct; i += 32) {
+		const lb200_const_translation ct = P.const_t[clip.ct_off + i];
+		s_pos[ct.bone_index * 3 + 0] = ct.value[0]; s_pos[ct.bone_index * 3 + 1] = ct.value[1]; s_pos[ct.bone_index * 3 + 2] = ct.value[2];
+	}
+	__syncwarp();
+	// :151-167 animated translations
+	const uint32_t* t_stream = P.stream + (clip.t_stream >> 2);
+	for (uint32_t i = lane; i < clip.n_t; i += 32) {
+		const lb200_track tr = P.tracks[clip.t_off + i];
+		const V3 a = get_translation(t_stream, clip.t_bits, sample_idx, tr);
+		const V3 b = get_translation(t_stream, clip.t_bits, sample_idx + 1, tr);
+		const V3 p = lerp(a, b, t);
+		s_pos[tr.bone_index * 3 + 0] = p.x; s_pos[tr.bone_index * 3 + 1] = p.y; s_pos[tr.bone_index * 3 + 2] = p.z;
+	}
+	// :169-183 constant rotations
+	for (uint32_t i = lane; i < clip.n_cr; i += 32) {
+		const lb200_const_rotation cr = P.const_r[clip.cr_off + i];
+		s_rot[cr.bone_index * 4 + 0] = cr.value[0]; s_rot[cr.bone_index * 4 + 1] = cr.value[1];
+		s_rot[cr.bone_index * 4 + 2] = cr.value[2]; s_rot[cr.bone_index * 4 + 3] = cr.value[3];
+	}
+	__syncwarp();
+	// :185-203 animated rotations
+	const uint32_t* r_stream = P.stream + (clip.r_stream >> 2);
+	for (uint32_t i = lane; i < clip.n_r; i += 32) {
+		const lb200_track tr = P.tracks[clip.r_off + i];
+		const uint32_t offset1 = clip.r_bits * sample_idx + tr.offset_bits;
+		const uint32_t offset2 = offset1 + clip.r_bits;
+		unsigned long long p1 = load_u64_unaligned(r_stream, offset1 >> 3);
+		p1 >>= (offset1 & 7u);
+		unsigned long long p2 = load_u64_unaligned(r_stream, offset2 >> 3);
+		p2 >>= (offset2 & 7u);
+		const Q4 q = simd_nlerp(unpack_rotation(p1, tr), unpack_rotation(p2, tr), t);
+		s_rot[tr.bone_index * 4 + 0] = q.x; s_rot[tr.bone_index * 4 + 1] = q.y; s_rot[tr.bone_index * 4 + 2] = q.z; s_rot[tr.bone_index * 4 + 3] = q.w;
+	}
+	__syncwarp();
+
+	// Pose::computeAbsolute, pose.cpp:66-133: bones of one depth level are independent (the reference's 4-wide path
+	// relies on the same fact); levels run in order so every parent is absolute before its children.
+	for (uint32_t lvl = 1; lvl <= P.max_level; ++lvl) {
+		for (uint32_t b = lane; b < B; b += 32) {
+			if (P.levels[b] != lvl) continue;
+			const int p = P.parents[b];
+			const Q4 prot = q4(s_rot[p * 4], s_rot[p * 4 + 1], s_rot[p * 4 + 2], s_rot[p * 4 + 3]);
+			const V3 ppos = v3(s_pos[p * 3], s_pos[p * 3 + 1], s_pos[p * 3 + 2]);
+			const V3 pos = add(rotate(prot, v3(s_pos[b * 3], s_pos[b * 3 + 1], s_pos[b * 3 + 2])), ppos); // :129
+			const Q4 rot = qmul(prot, q4(s_rot[b * 4], s_rot[b * 4 + 1], s_rot[b * 4 + 2], s_rot[b * 4 + 3])); // :130
+			s_pos[b * 3] = pos.x; s_pos[b * 3 + 1] = pos.y; s_pos[b * 3 + 2] = pos.z;
+			s_rot[b * 4] = rot.x; s_rot[b * 4 + 1] = rot.y; s_rot[b * 4 + 2] = rot.z; s_rot[b * 4 + 3] = rot.w;
+		}
+		__syncwarp();
+	}
+
+	// palettes
+	for (uint32_t b = lane; b < B; b += 32) {
+		Rigid pose;
+		pose.pos = v3(s_pos[b * 3], s_pos[b * 3 + 1], s_pos[b * 3 + 2]);
+		pose.rot = q4(s_rot[b * 4], s_rot[b * 4 + 1], s_rot[b * 4 + 2], s_rot[b * 4 + 3]);
+		const float* ib = P.inv_bind7 + (size_t)b * 7;
+		Rigid inv;
+		inv.pos = v3(ib[0], ib[1], ib[2]);
+		inv.rot = q4(ib[3], ib[4], ib[5], ib[6]);
+		const Rigid skin = rmul(pose, inv);
+		const size_t idx = (size_t)inst * B + b;
+		if (P.out_dq) {
+			const DualQ dq = to_dual_quat(skin);
+			float4* o = reinterpret_cast<float4*>(P.out_dq + idx * 8);
+			o[0] = make_float4(dq.r.x, dq.r.y, dq.r.z, dq.r.w);
+			o[1] = make_float4(dq.d.x, dq.d.y, dq.d.z, dq.d.w);
+		}
+		if (P.out_mtx) {
+			float m[16];
+			to_matrix(skin, m);
+			float4* o = reinterpret_cast<float4*>(P.out_mtx + idx * 16);
+			o[0] = make_float4(m[0], m[1], m[2], m[3]);
+			o[1] = make_float4(m[4], m[5], m[6], m[7]);
+			o[2] = make_float4(m[8], m[9], m[10], m[11]);
+			o[3] = make_float4(m[12], m[13], m[14], m[15]);
+		}
+		if (P.out_pos) {
+			P.out_pos[idx * 3] = pose.pos.x; P.out_pos[idx * 3 + 1] = pose.pos.y; P.out_pos[idx * 3 + 2] = pose.pos.z;
+			reinterpret_cast<float4*>(P.out_rot)[idx] = make_float4(pose.rot.x, pose.rot.y, pose.rot.z, pose.rot.w);
+		}
+	}
+
+	// animation_module.cpp:458-469
+	if (P.advance && lane == 0) {
+		const uint32_t l = clip.length_ticks;
+		uint32_t nt;
+		if (!P.dt_negative) nt = (ticks + P.dt_ticks) % l;
+		else nt = (ticks + l - (P.dt_ticks % l)) % l;
+		P.time_ticks[inst] = nt;
+	}
+}
+
+// ---- skinning ------------------------------------------------------------------------------------------------
+constexpr int SKIN_THREADS = 256;
+constexpr int SKIN_GROUP = 8; // instances per block: vertex data stays in registers across them
+
+__global__ void __launch_bounds__(SKIN_THREADS) skin_kernel(const float* __restrict__ palette_mtx, const float* __restrict__ positions3,
+	const float4* __restrict__ weights4, const short* __restrict__ indices4, uint32_t n_vertices, uint32_t bone_count, uint32_t n_instances,
+	float* __restrict__ out)
+{
+	extern __shared__ float4 s_rows[]; // [group][bone][3] rows of the 3x4 upper part
+	const uint32_t v = blockIdx.x * SKIN_THREADS + threadIdx.x;
+	const uint32_t inst0 = blockIdx.y * SKIN_GROUP;
+	const uint32_t n_inst = min((uint32_t)SKIN_GROUP, n_instances - inst0);
+
+	// stage palettes: matrix e = 16 floats column-major -> rows r0 = (m0,m4,m8,m12) ...
+	const uint32_t total = n_inst * bone_count;
+	for (uint32_t e = threadIdx.x; e < total; e += SKIN_THREADS) {
+		const float4* src = reinterpret_cast<const float4*>(palette_mtx + ((size_t)inst0 * bone_count + e) * 16);
+		const float4 c0 = __ldg(src), c1 = __ldg(src + 1), c2 = __ldg(src + 2), c3 = __ldg(src + 3);
+		s_rows[e * 3 + 0] = make_float4(c0.x, c1.x, c2.x, c3.x);
+		s_rows[e * 3 + 1] = make_float4(c0.y, c1.y, c2.y, c3.y);
+		s_rows[e * 3 + 2] = make_float4(c0.z, c1.z, c2.z, c3.z);
+	}
+	__syncthreads();
+	if (v >= n_vertices) return;
+
+	const float px = positions3[3 * (size_t)v], py = positions3[3 * (size_t)v + 1], pz = positions3[3 * (size_t)v + 2];
+	const float4 w = weights4[v];
+	const short4 idx = reinterpret_cast<const short4*>(indices4)[v];
+
+	for (uint32_t g = 0; g < n_inst; ++g) {
+		const float4* rows = s_rows + (size_t)g * bone_count * 3;
+		float o[3];
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			const float4 a = rows[idx.x * 3 + r], b = rows[idx.y * 3 + r], c = rows[idx.z * 3 + r], d = rows[idx.w * 3 + r];
+			// model.cpp:105-106: m = m0*w.x + m1*w.y + m2*w.z + m3*w.w, elementwise, left to right (math.cpp:1022-1071)
+			const float m0 = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(a.x, w.x), LB_FMUL(b.x, w.y)), LB_FMUL(c.x, w.z)), LB_FMUL(d.x, w.w));
+			const float m1 = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(a.y, w.x), LB_FMUL(b.y, w.y)), LB_FMUL(c.y, w.z)), LB_FMUL(d.y, w.w));
+			const float m2 = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(a.z, w.x), LB_FMUL(b.z, w.y)), LB_FMUL(c.z, w.z)), LB_FMUL(d.z, w.w));
+			const float m3 = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(a.w, w.x), LB_FMUL(b.w, w.y)), LB_FMUL(c.w, w.z)), LB_FMUL(d.w, w.w));
+			// math.cpp:1231-1235 transformPoint: c0.r*x + c1.r*y + c2.r*z + c3.r
+			o[r] = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(m0, px), LB_FMUL(m1, py)), LB_FMUL(m2, pz)), m3);
+		}
+		float* dst = out + ((size_t)(inst0 + g) * n_vertices + v) * 3;
+		dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+	}
+}
+
+__global__ void __launch_bounds__(256) checksum_kernel(const uint32_t* __restrict__ data, size_t n, unsigned long long* __restrict__ out) {
+	unsigned long long acc = 0;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += data[i];
+	for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+	if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+} // namespace
+
+struct lb200_animation {
+	lb200_ctx* ctx = nullptr;
+	uint32_t bone_count = 0, max_level = 0, n_clips = 0, max_instances = 0, n_instances = 0, n_vertices = 0;
+	DevClip* d_clips = nullptr;
+	lb200_track* d_tracks = nullptr;
+	lb200_const_translation* d_const_t = nullptr;
+	lb200_const_rotation* d_const_r = nullptr;
+	uint32_t* d_stream = nullptr;
+	float* d_bind7 = nullptr; float* d_inv_bind7 = nullptr;
+	short* d_parents = nullptr; unsigned char* d_levels = nullptr;
+	uint32_t* d_clip_index = nullptr; uint32_t* d_time = nullptr;
+	float* d_dq = nullptr; float* d_mtx = nullptr; float* d_pos = nullptr; float* d_rot = nullptr;
+	float* d_mesh_pos = nullptr; float4* d_mesh_w = nullptr; short* d_mesh_idx = nullptr;
+	float* d_skinned = nullptr;
+	unsigned long long* d_checksum = nullptr;
+};
+
+#define ANIM_MALLOC(ptr, bytes) LB200_CUDA(ctx, cudaMalloc(&(ptr), (size_t)(bytes) > 0 ? (size_t)(bytes) : (size_t)16))
+
+extern "C" {
+
+int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200_clip* clips, uint32_t n_clips, const lb200_mesh* mesh,
+	uint32_t max_instances, lb200_animation** out)
+{
+	if (!out || !sk || !clips || !n_clips || !max_instances) return LB200_ERR_INVALID;
+	if (!ctx) return LB200_ERR_NO_DEVICE;
+	*out = nullptr;
+	const uint32_t B = sk->bone_count;
+	if (!B || B > 196 || !sk->parents || !sk->bind_relative7 || !sk->inverse_bind7) { lb200_set_error(ctx, "bad skeleton (bone_count %u)", B); return LB200_ERR_INVALID; }
+	// pose.cpp:68-69 starts at first_nonroot; every later bone must have an earlier parent (model.cpp:381-384)
+	std::vector<unsigned char> levels(B, 0);
+	uint32_t max_level = 0;
+	const uint32_t first = sk->first_nonroot_bone_index < 0 ? B : (uint32_t)sk->first_nonroot_bone_index;
+	for (uint32_t i = first; i < B; ++i) {
+		const int p = sk->parents[i];
+		if (p < 0 || (uint32_t)p >= i) { lb200_set_error(ctx, "bone %u: parent %d is not an earlier bone", i, p); return LB200_ERR_INVALID; }
+		levels[i] = (unsigned char)(levels[p] + 1);
+		if (levels[i] > max_level) max_level = levels[i];
+	}
+	std::vector<DevClip> dc(n_clips);
+	std::vector<lb200_track> tracks;
+	std::vector<lb200_const_translation> cts;
+	std::vector<lb200_const_rotation> crs;
+	std::vector<uint32_t> stream;
+	auto appendStream = [&](const uint8_t* data, uint32_t bytes) -> uint32_t {
+		const uint32_t off = (uint32_t)stream.size() * 4;
+		const size_t words = (bytes + 3) / 4 + 4; // + 16 zero bytes: the 3-word unaligned read never leaves the blob
+		const size_t base = stream.size();
+		stream.resize(base + words, 0u);
+		if (bytes) memcpy(stream.data() + base, data, bytes);
+		return off;
+	};
+	for (uint32_t c = 0; c < n_clips; ++c) {
+		const lb200_clip& s = clips[c];
+		DevClip& d = dc[c];
+		if (!(s.fps > 0) || !s.frame_count) { lb200_set_error(ctx, "clip %u: fps/frame_count invalid", c); return LB200_ERR_INVALID; }
+		d.fps = s.fps; d.frame_count = s.frame_count;
+		d.t_bits = s.translations_frame_size_bits; d.r_bits = s.rotations_frame_size_bits;
+		d.n_t = s.n_translations; d.n_ct = s.n_const_translations; d.n_r = s.n_rotations; d.n_cr = s.n_const_rotations;
+		d.t_off = (uint32_t)tracks.size();
+		for (uint32_t i = 0; i < s.n_translations; ++i) { if (s.translations[i].bone_index >= B) return LB200_ERR_INVALID; tracks.push_back(s.translations[i]); }
+		d.r_off = (uint32_t)tracks.size();
+		for (uint32_t i = 0; i < s.n_rotations; ++i) { if (s.rotations[i].bone_index >= B || s.rotations[i].skipped_channel > 3) return LB200_ERR_INVALID; tracks.push_back(s.rotations[i]); }
+		d.ct_off = (uint32_t)cts.size();
+		for (uint32_t i = 0; i < s.n_const_translations; ++i) { if (s.const_translations[i].bone_index >= B) return LB200_ERR_INVALID; cts.push_back(s.const_translations[i]); }
+		d.cr_off = (uint32_t)crs.size();
+		for (uint32_t i = 0; i < s.n_const_rotations; ++i) { if (s.const_rotations[i].bone_index >= B) return LB200_ERR_INVALID; crs.push_back(s.const_rotations[i]); }
+		// streams must hold (frame_count + 1) frames + the loader's 8-byte tail (animation.cpp:439)
+		const uint64_t need_t = s.n_translations ? ((uint64_t)d.t_bits * (s.frame_count + 1) + 7) / 8 : 0;
+		const uint64_t need_r = s.n_rotations ? ((uint64_t)d.r_bits * (s.frame_count + 1) + 7) / 8 : 0;
+		if (s.translation_stream_bytes < need_t || s.rotation_stream_bytes < need_r) { lb200_set_error(ctx, "clip %u: bit stream shorter than (frame_count+1) frames", c); return LB200_ERR_INVALID; }
+		d.t_stream = appendStream(s.translation_stream, s.translation_stream_bytes);
+		d.r_stream = appendStream(s.rotation_stream, s.rotation_stream_bytes);
+		d.length_ticks = (uint32_t)(((float)s.frame_count / s.fps) * (float)(1 << 15)); // Time::fromSeconds(m_frame_count / m_fps)
+		if (!d.length_ticks) return LB200_ERR_INVALID;
+		d.pad = 0;
+	}
+
+	lb200_animation* a = new (std::nothrow) lb200_animation;
+	if (!a) return LB200_ERR_CUDA;
+	a->ctx = ctx; a->bone_count = B; a->max_level = max_level; a->n_clips = n_clips; a->max_instances = max_instances;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	ANIM_MALLOC(a->d_clips, sizeof(DevClip) * n_clips);
+	ANIM_MALLOC(a->d_tracks, sizeof(lb200_track) * tracks.size());
+	ANIM_MALLOC(a->d_const_t, sizeof(lb200_const_translation) * cts.size());
+	ANIM_MALLOC(a->d_const_r, sizeof(lb200_const_rotation) * crs.size());
+	ANIM_MALLOC(a->d_stream, sizeof(uint32_t) * stream.size());
+	ANIM_MALLOC(a->d_bind7, sizeof(float) * 7 * B);
+	ANIM_MALLOC(a->d_inv_bind7, sizeof(float) * 7 * B);
+	ANIM_MALLOC(a->d_parents, sizeof(short) * B);
+	ANIM_MALLOC(a->d_levels, B);
+	ANIM_MALLOC(a->d_clip_index, sizeof(uint32_t) * max_instances);
+	ANIM_MALLOC(a->d_time, sizeof(uint32_t) * max_instances);
+	ANIM_MALLOC(a->d_checksum, sizeof(unsigned long long));
+	cudaStream_t st = ctx->stream;
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_clips, dc.data(), sizeof(DevClip) * n_clips, cudaMemcpyHostToDevice, st));
+	if (!tracks.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_tracks, tracks.data(), sizeof(lb200_track) * tracks.size(), cudaMemcpyHostToDevice, st));
+	if (!cts.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_const_t, cts.data(), sizeof(lb200_const_translation) * cts.size(), cudaMemcpyHostToDevice, st));
+	if (!crs.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_const_r, crs.data(), sizeof(lb200_const_rotation) * crs.size(), cudaMemcpyHostToDevice, st));
+	if (!stream.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_stream, stream.data(), sizeof(uint32_t) * stream.size(), cudaMemcpyHostToDevice, st));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_bind7, sk->bind_relative7, sizeof(float) * 7 * B, cudaMemcpyHostToDevice, st));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_inv_bind7, sk->inverse_bind7, sizeof(float) * 7 * B, cudaMemcpyHostToDevice, st));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_parents, sk->parents, sizeof(short) * B, cudaMemcpyHostToDevice, st));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_levels, levels.data(), B, cudaMemcpyHostToDevice, st));
+	if (mesh && mesh->n_vertices) {
+		a->n_vertices = mesh->n_vertices;
+		for (uint32_t v = 0; v < mesh->n_vertices * 4; ++v) if (mesh->indices4[v] < 0 || (uint32_t)mesh->indices4[v] >= B) { lb200_animation_destroy(a); return LB200_ERR_INVALID; }
+		ANIM_MALLOC(a->d_mesh_pos, sizeof(float) * 3 * mesh->n_vertices);
+		ANIM_MALLOC(a->d_mesh_w, sizeof(float4) * mesh->n_vertices);
+		ANIM_MALLOC(a->d_mesh_idx, sizeof(short) * 4 * mesh->n_vertices);
+		LB200_CUDA(ctx, cudaMemcpyAsync(a->d_mesh_pos, mesh->positions3, sizeof(float) * 3 * mesh->n_vertices, cudaMemcpyHostToDevice, st));
+		LB200_CUDA(ctx, cudaMemcpyAsync(a->d_mesh_w, mesh->weights4, sizeof(float4) * mesh->n_vertices, cudaMemcpyHostToDevice, st));
+		LB200_CUDA(ctx, cudaMemcpyAsync(a->d_mesh_idx, mesh->indices4, sizeof(short) * 4 * mesh->n_vertices, cudaMemcpyHostToDevice, st));
+	}
+	LB200_CUDA(ctx, cudaStreamSynchronize(st));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POSE_WARPS * 196 * 7 * sizeof(float))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SKIN_GROUP * 196 * 3 * sizeof(float4))));
+	*out = a;
+	return LB200_OK;
+}
+
+void lb200_animation_destroy(lb200_animation* a) {
+	if (!a) return;
+	cudaSetDevice(a->ctx->device);
+	cudaStreamSynchronize(a->ctx->stream);
+	cudaFree(a->d_clips); cudaFree(a->d_tracks); cudaFree(a->d_const_t); cudaFree(a->d_const_r); cudaFree(a->d_stream);
+	cudaFree(a->d_bind7); cudaFree(a->d_inv_bind7); cudaFree(a->d_parents); cudaFree(a->d_levels);
+	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot);
+	cudaFree(a->d_mesh_pos); cudaFree(a->d_mesh_w); cudaFree(a->d_mesh_idx); cudaFree(a->d_skinned); cudaFree(a->d_checksum);
+	delete a;
+}
+
+int lb200_animation_set_instances(lb200_animation* a, const uint32_t* clip_index, const uint32_t* time_ticks, uint32_t n) {
+	if (!a || !clip_index || !time_ticks || n > a->max_instances) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	for (uint32_t i = 0; i < n; ++i) if (clip_index[i] >= a->n_clips) { lb200_set_error(ctx, "instance %u: clip %u out of range", i, clip_index[i]); return LB200_ERR_INVALID; }
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_clip_index, clip_index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_time, time_ticks, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	a->n_instances = n;
+	return LB200_OK;
+}
+
+int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags) {
+	if (!a) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	if (!a->n_instances) return LB200_OK;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t nb = (size_t)a->max_instances * a->bone_count;
+	if ((flags & LB200_PALETTE_DUAL_QUAT) && !a->d_dq) ANIM_MALLOC(a->d_dq, sizeof(float) * 8 * nb);
+	if ((flags & LB200_PALETTE_MATRIX) && !a->d_mtx) ANIM_MALLOC(a->d_mtx, sizeof(float) * 16 * nb);
+	if ((flags & LB200_PALETTE_POSE) && !a->d_pos) { ANIM_MALLOC(a->d_pos, sizeof(float) * 3 * nb); ANIM_MALLOC(a->d_rot, sizeof(float) * 4 * nb); }
+	AnimParams P;
+	P.clips = a->d_clips; P.tracks = a->d_tracks; P.const_t = a->d_const_t; P.const_r = a->d_const_r; P.stream = a->d_stream;
+	P.bind7 = a->d_bind7; P.inv_bind7 = a->d_inv_bind7; P.parents = a->d_parents; P.levels = a->d_levels;
+	P.bone_count = a->bone_count; P.max_level = a->max_level; P.n_instances = a->n_instances;
+	P.clip_index = a->d_clip_index; P.time_ticks = a->d_time;
+	P.out_dq = (flags & LB200_PALETTE_DUAL_QUAT) ? a->d_dq : nullptr;
+	P.out_mtx = (flags & LB200_PALETTE_MATRIX) ? a->d_mtx : nullptr;
+	P.out_pos = (flags & LB200_PALETTE_POSE) ? a->d_pos : nullptr;
+	P.out_rot = (flags & LB200_PALETTE_POSE) ? a->d_rot : nullptr;
+	// Time::fromSeconds: u32(time * ONE_SECOND), animation.h:21-24 (:462 uses -time_delta for rewinds)
+	P.dt_negative = time_delta < 0;
+	P.dt_ticks = (uint32_t)((P.dt_negative ? -time_delta : time_delta) * (float)(1 << 15));
+	P.advance = time_delta != 0;
+	const unsigned blocks = (a->n_instances + POSE_WARPS - 1) / POSE_WARPS;
+	const size_t smem = sizeof(float) * 7 * a->bone_count * POSE_WARPS;
+	pose_palette_kernel<<<blocks, POSE_WARPS * 32, smem, ctx->stream>>>(P);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
+int lb200_animation_skin(lb200_animation* a) {
+	if (!a) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	if (!a->n_vertices || !a->d_mtx) { lb200_set_error(ctx, "skin needs a mesh and a matrix palette (update with LB200_PALETTE_MATRIX first)"); return LB200_ERR_STATE; }
+	if (!a->n_instances) return LB200_OK;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!a->d_skinned) ANIM_MALLOC(a->d_skinned, sizeof(float) * 3 * (size_t)a->max_instances * a->n_vertices);
+	const dim3 grid((a->n_vertices + SKIN_THREADS - 1) / SKIN_THREADS, (a->n_instances + SKIN_GROUP - 1) / SKIN_GROUP);
+	if (grid.y > 65535) { lb200_set_error(ctx, "too many instances for one skin launch"); return LB200_ERR_INVALID; }
+	const size_t smem = sizeof(float4) * 3 * a->bone_count * SKIN_GROUP;
+	skin_kernel<<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
+static int readBack(lb200_animation* a, const void* dev, size_t elem_bytes, uint32_t first, uint32_t count, void* out) {
+	if (!a || !out || first + count > a->n_instances) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	if (!dev) { lb200_set_error(ctx, "requested buffer was never produced"); return LB200_ERR_STATE; }
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	LB200_CUDA(ctx, cudaMemcpyAsync(out, (const char*)dev + elem_bytes * first, elem_bytes * count, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
+int lb200_animation_get_dual_quats(lb200_animation* a, uint32_t first, uint32_t count, float* out8) {
+	return readBack(a, a ? a->d_dq : nullptr, sizeof(float) * 8 * (a ? a->bone_count : 0), first, count, out8);
+}
+int lb200_animation_get_matrices(lb200_animation* a, uint32_t first, uint32_t count, float* out16) {
+	return readBack(a, a ? a->d_mtx : nullptr, sizeof(float) * 16 * (a ? a->bone_count : 0), first, count, out16);
+}
+int lb200_animation_get_pose(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3, float* out_rot4) {
+	int rc = readBack(a, a ? a->d_pos : nullptr, sizeof(float) * 3 * (a ? a->bone_count : 0), first, count, out_pos3);
+	if (rc) return rc;
+	return readBack(a, a->d_rot, sizeof(float) * 4 * a->bone_count, first, count, out_rot4);
+}
+int lb200_animation_get_times(lb200_animation* a, uint32_t first, uint32_t count, uint32_t* out_ticks) {
+	return readBack(a, a ? a->d_time : nullptr, sizeof(uint32_t), first, count, out_ticks);
+}
+int lb200_animation_get_skinned(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3) {
+	return readBack(a, a ? a->d_skinned : nullptr, sizeof(float) * 3 * (a ? a->n_vertices : 0), first, count, out_pos3);
+}
+
+int lb200_animation_skinned_checksum(lb200_animation* a, uint64_t* out) {
+	if (!a || !out) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	if (!a->d_skinned) return LB200_ERR_STATE;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	LB200_CUDA(ctx, cudaMemsetAsync(a->d_checksum, 0, sizeof(unsigned long long), ctx->stream));
+	const size_t n = (size_t)a->n_instances * a->n_vertices * 3;
+	checksum_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(a->d_skinned), n, a->d_checksum);
+	LB200_CHECK_LAUNCH(ctx);
+	unsigned long long v = 0;
+	LB200_CUDA(ctx, cudaMemcpyAsync(&v, a->d_checksum, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	*out = v;
+	return LB200_OK;
+}
+
+uint64_t lb200_animation_algorithmic_bytes(const lb200_animation* a, uint32_t flags, int skin) {
+	if (!a) return 0;
+	const uint64_t nb = (uint64_t)a->n_instances * a->bone_count;
+	uint64_t bytes = 0;
+	if (skin) {
+		// 12 B written per vertex-instance + the instance's matrix palette read once
+		bytes += (uint64_t)a->n_instances * a->n_vertices * 12 + nb * 64;
+	}
+	else {
+		if (flags & LB200_PALETTE_DUAL_QUAT) bytes += nb * 32;
+		if (flags & LB200_PALETTE_MATRIX) bytes += nb * 64;
+		if (flags & LB200_PALETTE_POSE) bytes += nb * 28;
+		bytes += (uint64_t)a->n_instances * 12; // clip index + time read + time write
+	}
+	return bytes;
+}
+
+} // extern "C"

@@ -1,0 +1,639 @@
+// GPU CullingSystem: kernels + C-ABI (include/lumix_b200.h "CullingSystem").
+//
+// Replaces CullingSystemImpl::cullInternal + doCulling (src/renderer/culling_system.cpp:260-369): one warp per cell page —
+//   1. read the 32-byte page descriptor (origin, count, type, is_big),
+//   2. classify the cell against the ShiftedFrustum's own planes exactly as culling_system.cpp:342-363 does
+//      (is_big -> test; containsAABB(origin + cs, cs) -> copy every id; intersectsAABB(origin - cs, 2cs) -> test; else skip),
+//      one plane per lane (geometry.cpp:99-118,159-178),
+//   3. for tested pages re-express the plane offsets relative to the cell origin (ShiftedFrustum::getRelative,
+//      geometry.cpp:121-149; only d changes, the normals are shared by all cells), stream the <=200 spheres with 128-bit
+//      loads, evaluate the 6 distinct planes (EXTRA0/1 duplicate NEAR, geometry.cpp:134-136) with the reference's
+//      op order and sign-bit test (culling_system.cpp:284-295, simd.h:119),
+//   4. ballot + popc compaction; one shared-memory atomic per page, one global atomic per (block, type) to claim output space,
+//   5. write visible ids (grouped by type) and the per-page visibility bitmask.
+// HBM-bound: 16 B per tested sphere + 4 B read + 4 B write per visible id.  No tensor cores: there is no
+// contraction here.
+#include "culling_host.hpp"
+#include "lb200_math.cuh"
+
+#include <algorithm>
+#include <new>
+
+namespace {
+
+using namespace lb;
+
+constexpr int CULL_THREADS = 256;
+constexpr int WARPS_PER_BLOCK = CULL_THREADS / 32;
+constexpr int ROWS = 7; // ceil(200 / 32)
+constexpr int N_STATS = 8;
+enum { ST_PAGES_TESTED = 0, ST_PAGES_INSIDE, ST_PAGES_OUTSIDE, ST_PAGES_FILTERED, ST_ENT_TESTED, ST_ENT_INSIDE };
+constexpr int COUNTER_WORDS = 256 + N_STATS;
+static_assert(CULL_THREADS == 256, "one thread per renderable type in the output-claim step");
+
+struct CullParams {
+	// planes NEAR, FAR, LEFT, RIGHT, TOP, BOTTOM of the ShiftedFrustum (relative to `origin`)
+	float nx[6], ny[6], nz[6], d[6];
+	// the frustum point each plane is re-anchored on by getRelative (geometry.cpp:134-142): points[0,4,1,0,0,2]
+	float px[6], py[6], pz[6];
+	double ox, oy, oz;
+	uint32_t n_pages;
+	uint32_t type_filter; // 0xff = all
+	uint32_t type_base[256];
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+	float4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ int ldg_stream_i32(const int* p) {
+	int r;
+	asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+
+enum { CLS_SKIP = 0, CLS_COPY = 1, CLS_TEST = 2 };
+
+__global__ void __launch_bounds__(CULL_THREADS) cull_pages_kernel(const __grid_constant__ CullParams P,
+	const lb200_page_desc* __restrict__ desc, const float4* __restrict__ spheres, const int* __restrict__ entities,
+	uint32_t* __restrict__ out_ids, uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters, uint32_t* __restrict__ mask_out)
+{
+	__shared__ uint32_t s_cnt[256];
+	__shared__ uint32_t s_base[256];
+	__shared__ uint32_t s_stats[N_STATS];
+
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+
+	s_cnt[threadIdx.x] = 0;
+	if (threadIdx.x < N_STATS) s_stats[threadIdx.x] = 0;
+	__syncthreads();
+
+	// plane handled by this lane during cell classification (lanes >= 6 repeat plane 0: harmless under __all_sync)
+	const int pl = lane < 6 ? lane : 0;
+	const float l_nx = P.nx[pl], l_ny = P.ny[pl], l_nz = P.nz[pl], l_d = P.d[pl];
+	const float l_px = P.px[pl], l_py = P.py[pl], l_pz = P.pz[pl];
+
+	for (uint32_t base = blockIdx.x * WARPS_PER_BLOCK; base < P.n_pages; base += gridDim.x * WARPS_PER_BLOCK) {
+		const uint32_t page = base + warp;
+		int cls = CLS_SKIP;
+		uint32_t count = 0, type = 0;
+		float rd[6];
+		float4 s[ROWS];
+		uint32_t bal[ROWS];
+		uint32_t page_visible = 0;
+
+		if (page < P.n_pages) {
+			// 32-byte descriptor: every lane reads the same two 16-byte words (one sector, broadcast)
+			const int4* dp = reinterpret_cast<const int4*>(desc + page);
+			const int4 a = __ldg(dp);
+			const int4 b = __ldg(dp + 1);
+			const double org_x = __hiloint2double(a.y, a.x);
+			const double org_y = __hiloint2double(a.w, a.z);
+			const double org_z = __hiloint2double(b.y, b.x);
+			count = (uint32_t)b.z;
+			type = (uint32_t)b.w & 0xffu;
+			const bool is_big = (((uint32_t)b.w >> 8) & 0xffu) != 0;
+
+			if (count != 0 && (P.type_filter == 0xffu || type == P.type_filter)) {
+				// --- culling_system.cpp:342-363 ---
+				// containsAABB(cell.origin + Vec3(cs), Vec3(cs)), geometry.cpp:99-118 (DVec3 + Vec3: math.cpp:512)
+				const float cs = LB200_CELL_SIZE;
+				const V3 rel_c = tofloat(sub(d3(LB_DADD(org_x, (double)cs), LB_DADD(org_y, (double)cs), LB_DADD(org_z, (double)cs)), d3(P.ox, P.oy, P.oz)));
+				const V3 max_c = add(rel_c, v3(cs, cs, cs));
+				const float cbx = l_nx < 0.0f ? max_c.x : rel_c.x;
+				const float cby = l_ny < 0.0f ? max_c.y : rel_c.y;
+				const float cbz = l_nz < 0.0f ? max_c.z : rel_c.z;
+				const float dp_c = LB_FADD(LB_FADD(LB_FMUL(l_nx, cbx), LB_FMUL(l_ny, cby)), LB_FMUL(l_nz, cbz));
+				const bool fail_c = dp_c < -l_d;
+				// intersectsAABB(cell.origin - Vec3(cs), Vec3(2cs)), geometry.cpp:159-178 (DVec3 - Vec3: math.cpp:510)
+				const float cs2 = 2 * LB200_CELL_SIZE;
+				const V3 rel_i = tofloat(sub(d3(LB_DSUB(org_x, (double)cs), LB_DSUB(org_y, (double)cs), LB_DSUB(org_z, (double)cs)), d3(P.ox, P.oy, P.oz)));
+				const V3 max_i = add(rel_i, v3(cs2, cs2, cs2));
+				const float ibx = l_nx > 0.0f ? max_i.x : rel_i.x;
+				const float iby = l_ny > 0.0f ? max_i.y : rel_i.y;
+				const float ibz = l_nz > 0.0f ? max_i.z : rel_i.z;
+				const float dp_i = LB_FADD(LB_FADD(LB_FMUL(l_nx, ibx), LB_FMUL(l_ny, iby)), LB_FMUL(l_nz, ibz));
+				const bool fail_i = dp_i < -l_d;
+				const bool contains = __all_sync(0xffffffffu, !fail_c);
+				const bool intersects = __all_sync(0xffffffffu, !fail_i);
+				if (is_big) cls = CLS_TEST;
+				else if (contains) cls = CLS_COPY;
+				else if (intersects) cls = CLS_TEST;
+				else if (lane == 0) atomicAdd(&s_stats[ST_PAGES_OUTSIDE], 1u);
+			}
+			else if (count != 0 && lane == 0) atomicAdd(&s_stats[ST_PAGES_FILTERED], 1u);
+
+			if (cls == CLS_TEST) {
+				// issue the sphere loads first: everything below until the first use overlaps their latency
+				const float4* sp = spheres + (size_t)page * PAGE_SLOTS;
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) {
+					const uint32_t slot = k * 32 + lane;
+					if (slot < count) s[k] = ldg_stream(sp + slot);
+				}
+				// ShiftedFrustum::getRelative(cell.origin), geometry.cpp:121-149: offset = Vec3(this->origin - origin);
+				// d = -dot(point + offset, normal) (setPlane, geometry.cpp:412-418)
+				const V3 offset = tofloat(sub(d3(P.ox, P.oy, P.oz), d3(org_x, org_y, org_z)));
+				const V3 pnt = add(v3(l_px, l_py, l_pz), offset);
+				const float my_d = -dot(pnt, v3(l_nx, l_ny, l_nz));
+#pragma unroll
+				for (int p = 0; p < 6; ++p) rd[p] = __shfl_sync(0xffffffffu, my_d, p);
+
+				// doCulling, culling_system.cpp:260-308
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) {
+					const uint32_t slot = k * 32 + lane;
+					bool visible = false;
+					if (slot < count) {
+						const float cx = s[k].x, cy = s[k].y, cz = s[k].z;
+						const float r = -s[k].w; // :282 f4Splat(-sphere->radius)
+						uint32_t sign_acc = 0;
+#pragma unroll
+						for (int p = 0; p < 6; ++p) {
+							// :284,291  t = cx*px + cy*py + cz*pz + pd ;  t = t - r ;  movemask = sign bits
+							float t = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(cx, P.nx[p]), LB_FMUL(cy, P.ny[p])), LB_FMUL(cz, P.nz[p])), rd[p]);
+							t = LB_FSUB(t, r);
+							sign_acc |= __float_as_uint(t);
+						}
+						visible = (sign_acc >> 31) == 0;
+					}
+					bal[k] = __ballot_sync(0xffffffffu, visible);
+					page_visible += __popc(bal[k]);
+				}
+				if (lane == 0) {
+					atomicAdd(&s_stats[ST_PAGES_TESTED], 1u);
+					atomicAdd(&s_stats[ST_ENT_TESTED], count);
+				}
+			}
+			else if (cls == CLS_COPY) {
+				// :345-360 every entity of the page is visible
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) {
+					const int rem = (int)count - k * 32;
+					bal[k] = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+				}
+				page_visible = count;
+				if (lane == 0) {
+					atomicAdd(&s_stats[ST_PAGES_INSIDE], 1u);
+					atomicAdd(&s_stats[ST_ENT_INSIDE], count);
+				}
+			}
+			else {
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) bal[k] = 0;
+			}
+
+			if (mask_out && lane == 0) {
+				uint4* m = reinterpret_cast<uint4*>(mask_out + (size_t)page * 8);
+				m[0] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
+				m[1] = make_uint4(bal[4], bal[5], bal[6], 0u);
+			}
+		}
+
+		// claim output space: per-page offset inside the block (shared atomics), one global atomic per (block, type)
+		uint32_t my_off = 0;
+		if (lane == 0 && page_visible) my_off = atomicAdd(&s_cnt[type], page_visible);
+		__syncthreads();
+		{
+			const uint32_t c = s_cnt[threadIdx.x];
+			if (c) {
+				s_base[threadIdx.x] = atomicAdd(&counters[threadIdx.x], c);
+				s_cnt[threadIdx.x] = 0;
+			}
+		}
+		__syncthreads();
+		if (page_visible) {
+			my_off = __shfl_sync(0xffffffffu, my_off, 0);
+			uint32_t* dst = out_ids + P.type_base[type] + s_base[type] + my_off;
+			const int* ep = entities + (size_t)page * PAGE_SLOTS;
+			uint32_t prefix = 0;
+#pragma unroll
+			for (int k = 0; k < ROWS; ++k) {
+				if ((bal[k] >> lane) & 1u) {
+					const int id = ldg_stream_i32(ep + k * 32 + lane);
+					dst[prefix + __popc(bal[k] & lt_mask)] = (uint32_t)id;
+				}
+				prefix += __popc(bal[k]);
+			}
+		}
+	}
+
+	__syncthreads();
+	if (threadIdx.x < N_STATS && s_stats[threadIdx.x]) atomicAdd(&counters[256 + threadIdx.x], s_stats[threadIdx.x]);
+	// the other counter buffer is the next cull's: zero it now so no memset sits between two culls
+	if (blockIdx.x == 0) {
+		for (int i = threadIdx.x; i < COUNTER_WORDS; i += CULL_THREADS) next_counters[i] = 0;
+	}
+}
+
+// scatter packed dirty pages from a staging buffer into the page arrays (one block per page)
+__global__ void __launch_bounds__(256) scatter_pages_kernel(const uint32_t* __restrict__ page_idx, const lb200_page_desc* __restrict__ st_desc,
+	const float4* __restrict__ st_spheres, const int* __restrict__ st_entities, lb200_page_desc* __restrict__ desc, float4* __restrict__ spheres,
+	int* __restrict__ entities)
+{
+	const uint32_t i = blockIdx.x;
+	const uint32_t p = page_idx[i];
+	if (threadIdx.x < PAGE_SLOTS) {
+		spheres[(size_t)p * PAGE_SLOTS + threadIdx.x] = st_spheres[(size_t)i * PAGE_SLOTS + threadIdx.x];
+		entities[(size_t)p * PAGE_SLOTS + threadIdx.x] = st_entities[(size_t)i * PAGE_SLOTS + threadIdx.x];
+	}
+	if (threadIdx.x < 2) reinterpret_cast<int4*>(desc + p)[threadIdx.x] = reinterpret_cast<const int4*>(st_desc + i)[threadIdx.x];
+}
+
+void* pinnedAlloc(size_t n) {
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+void pinnedFree(void* p) { if (p) cudaFreeHost(p); }
+void* plainAlloc(size_t n) { return malloc(n ? n : 1); }
+void plainFree(void* p) { free(p); }
+
+} // namespace
+
+struct lb200_culling {
+	lb200_culling(lb200_ctx* c) : ctx(c), host(c ? pinnedAlloc : plainAlloc, c ? pinnedFree : plainFree) {}
+	lb200_ctx* ctx;
+	lb::CullingHost host;
+
+	// HBM mirror
+	uint32_t dev_cap = 0; // pages per replica
+	uint32_t replicas = 1;
+	uint32_t next_replica = 0;
+	float4* d_spheres = nullptr;
+	int* d_entities = nullptr;
+	lb200_page_desc* d_desc = nullptr;
+	uint32_t* d_out_ids = nullptr;
+	uint32_t out_cap = 0;
+	uint32_t* d_mask = nullptr;
+	uint32_t* d_counters = nullptr; // 2 * COUNTER_WORDS
+	uint32_t* h_counters = nullptr; // pinned, COUNTER_WORDS
+	uint32_t parity = 0;
+	int grid = 0;
+	// staging for sparse dirty uploads
+	uint8_t* h_stage = nullptr;
+	uint8_t* d_stage = nullptr;
+	size_t stage_pages = 0;
+	// multi-GPU gather buffers
+	uint32_t* d_gather_ids = nullptr;
+	uint32_t* d_gather_counts = nullptr;
+	size_t gather_ids_cap = 0;
+	uint32_t* d_slab = nullptr;
+	size_t slab_cap = 0;
+
+	uint32_t last_type_base[256];
+	lb200_cull_result last = {};
+	bool has_last = false;
+	uint64_t last_bytes = 0;
+	uint32_t last_pages = 0;
+};
+
+namespace {
+
+int ensureDevice(lb200_culling* cs) {
+	lb200_ctx* ctx = cs->ctx;
+	lb::CullingHost& h = cs->host;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!cs->d_counters) {
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * COUNTER_WORDS));
+		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * COUNTER_WORDS, ctx->stream));
+		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocDefault));
+		int per_sm = 0;
+		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel, CULL_THREADS, 0));
+		if (per_sm < 1) per_sm = 1;
+		cs->grid = ctx->sm_count * per_sm;
+	}
+	if (cs->dev_cap < h.high_water) {
+		uint32_t cap = cs->dev_cap ? cs->dev_cap : 1024;
+		while (cap < h.high_water) cap *= 2;
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_mask);
+		cs->d_spheres = nullptr; cs->d_entities = nullptr; cs->d_desc = nullptr; cs->d_mask = nullptr;
+		const size_t R = cs->replicas;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_spheres, sizeof(float4) * PAGE_SLOTS * (size_t)cap * R));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_entities, sizeof(int) * PAGE_SLOTS * (size_t)cap * R));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_desc, sizeof(lb200_page_desc) * (size_t)cap * R));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_mask, sizeof(uint32_t) * 8 * (size_t)cap));
+		// free / never-used pages must read count == 0
+		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_desc, 0, sizeof(lb200_page_desc) * (size_t)cap * R, ctx->stream));
+		cs->dev_cap = cap;
+		h.all_dirty = true;
+	}
+	if (cs->out_cap < h.n_entities || !cs->d_out_ids) {
+		uint32_t cap = cs->out_cap ? cs->out_cap : 4096;
+		while (cap < h.n_entities) cap *= 2;
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(cs->d_out_ids);
+		cs->d_out_ids = nullptr;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_out_ids, sizeof(uint32_t) * (size_t)cap));
+		cs->out_cap = cap;
+	}
+	return LB200_OK;
+}
+
+int flushPages(lb200_culling* cs) {
+	lb200_ctx* ctx = cs->ctx;
+	lb::CullingHost& h = cs->host;
+	int rc = ensureDevice(cs);
+	if (rc) return rc;
+	if (!h.all_dirty && h.dirty_list.empty()) return LB200_OK;
+	const uint32_t n = h.high_water;
+	const bool full = h.all_dirty || h.dirty_list.size() * 8 > n;
+	if (full) {
+		LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_spheres, h.spheres, sizeof(float4) * PAGE_SLOTS * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+		LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_entities, h.entities, sizeof(int) * PAGE_SLOTS * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+		LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_desc, h.desc, sizeof(lb200_page_desc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+		for (uint32_t r = 1; r < cs->replicas; ++r) { // bench replicas: copy inside HBM
+			const size_t off = (size_t)r * cs->dev_cap;
+			LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_spheres + off * PAGE_SLOTS, cs->d_spheres, sizeof(float4) * PAGE_SLOTS * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+			LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_entities + off * PAGE_SLOTS, cs->d_entities, sizeof(int) * PAGE_SLOTS * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+			LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_desc + off, cs->d_desc, sizeof(lb200_page_desc) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
+	}
+	else {
+		const size_t m = h.dirty_list.size();
+		const size_t per_page = sizeof(float4) * PAGE_SLOTS + sizeof(int) * PAGE_SLOTS + sizeof(lb200_page_desc) + sizeof(uint32_t);
+		if (cs->stage_pages < m) {
+			size_t cap = cs->stage_pages ? cs->stage_pages : 256;
+			while (cap < m) cap *= 2;
+			LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (cs->h_stage) cudaFreeHost(cs->h_stage);
+			cudaFree(cs->d_stage);
+			cs->h_stage = nullptr; cs->d_stage = nullptr;
+			LB200_CUDA(ctx, cudaHostAlloc(&cs->h_stage, per_page * cap, cudaHostAllocDefault));
+			LB200_CUDA(ctx, cudaMalloc(&cs->d_stage, per_page * cap));
+			cs->stage_pages = cap;
+		}
+		else {
+			// the previous scatter may still be reading the staging buffer
+			LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		}
+		// staging layout: [spheres m][entities m][desc m][idx m]
+		const size_t cap = cs->stage_pages;
+		float* st_s = reinterpret_cast<float*>(cs->h_stage);
+		int* st_e = reinterpret_cast<int*>(cs->h_stage + sizeof(float4) * PAGE_SLOTS * cap);
+		lb200_page_desc* st_d = reinterpret_cast<lb200_page_desc*>(cs->h_stage + (sizeof(float4) + sizeof(int)) * PAGE_SLOTS * cap);
+		uint32_t* st_i = reinterpret_cast<uint32_t*>(cs->h_stage + (sizeof(float4) + sizeof(int)) * PAGE_SLOTS * cap + sizeof(lb200_page_desc) * cap);
+		for (size_t i = 0; i < m; ++i) {
+			const uint32_t p = h.dirty_list[i];
+			memcpy(st_s + 4 * PAGE_SLOTS * i, h.spheres + 4 * PAGE_SLOTS * (size_t)p, sizeof(float4) * PAGE_SLOTS);
+			memcpy(st_e + PAGE_SLOTS * i, h.entities + PAGE_SLOTS * (size_t)p, sizeof(int) * PAGE_SLOTS);
+			st_d[i] = h.desc[p];
+			st_i[i] = p;
+		}
+		LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_stage, cs->h_stage, per_page * cap, cudaMemcpyHostToDevice, ctx->stream));
+		const float4* d_s = reinterpret_cast<const float4*>(cs->d_stage);
+		const int* d_e = reinterpret_cast<const int*>(cs->d_stage + sizeof(float4) * PAGE_SLOTS * cap);
+		const lb200_page_desc* d_d = reinterpret_cast<const lb200_page_desc*>(cs->d_stage + (sizeof(float4) + sizeof(int)) * PAGE_SLOTS * cap);
+		const uint32_t* d_i = reinterpret_cast<const uint32_t*>(cs->d_stage + (sizeof(float4) + sizeof(int)) * PAGE_SLOTS * cap + sizeof(lb200_page_desc) * cap);
+		for (uint32_t r = 0; r < cs->replicas; ++r) {
+			const size_t off = (size_t)r * cs->dev_cap;
+			scatter_pages_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(d_i, d_d, d_s, d_e, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS);
+			LB200_CHECK_LAUNCH(ctx);
+		}
+	}
+	h.clearDirty();
+	return LB200_OK;
+}
+
+int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type) {
+	lb200_ctx* ctx = cs->ctx;
+	lb::CullingHost& h = cs->host;
+	int rc = flushPages(cs);
+	if (rc) return rc;
+
+	CullParams P;
+	static const int point_of_plane[6] = {0, 4, 1, 0, 0, 2}; // geometry.cpp:134-142
+	for (int i = 0; i < 6; ++i) {
+		P.nx[i] = f->xs[i]; P.ny[i] = f->ys[i]; P.nz[i] = f->zs[i]; P.d[i] = f->ds[i];
+		P.px[i] = f->points[point_of_plane[i]][0];
+		P.py[i] = f->points[point_of_plane[i]][1];
+		P.pz[i] = f->points[point_of_plane[i]][2];
+	}
+	P.ox = f->origin[0]; P.oy = f->origin[1]; P.oz = f->origin[2];
+	P.n_pages = h.high_water;
+	P.type_filter = type;
+	uint32_t acc = 0;
+	for (int t = 0; t < 256; ++t) { P.type_base[t] = acc; acc += h.type_counts[t]; }
+	memcpy(cs->last_type_base, P.type_base, sizeof(P.type_base));
+
+	const uint32_t r = cs->next_replica;
+	cs->next_replica = (cs->next_replica + 1) % cs->replicas;
+	const size_t off = (size_t)r * cs->dev_cap;
+	uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
+	uint32_t* nxt = cs->d_counters + (size_t)(cs->parity ^ 1) * COUNTER_WORDS;
+	const unsigned blocks = (unsigned)std::max(1, std::min(cs->grid, (int)((h.high_water + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK)));
+	cull_pages_kernel<<<blocks, CULL_THREADS, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
+		cs->d_out_ids, cur, nxt, cs->d_mask);
+	LB200_CHECK_LAUNCH(ctx);
+	cs->last_pages = h.high_water;
+	return LB200_OK;
+}
+
+int readCounts(lb200_culling* cs, lb200_cull_result* result) {
+	lb200_ctx* ctx = cs->ctx;
+	const uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->h_counters, cur, sizeof(uint32_t) * COUNTER_WORDS, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	lb200_cull_result& res = cs->last;
+	memset(&res, 0, sizeof(res));
+	for (int t = 0; t < 256; ++t) {
+		res.type_count[t] = cs->h_counters[t];
+		res.type_offset[t] = cs->last_type_base[t];
+		res.total += res.type_count[t];
+		if (cs->host.type_counts[t]) res.n_types = t + 1;
+	}
+	res.pages_tested = cs->h_counters[256 + ST_PAGES_TESTED];
+	res.pages_inside = cs->h_counters[256 + ST_PAGES_INSIDE];
+	res.pages_outside = cs->h_counters[256 + ST_PAGES_OUTSIDE];
+	res.pages_filtered = cs->h_counters[256 + ST_PAGES_FILTERED];
+	res.entities_tested = cs->h_counters[256 + ST_ENT_TESTED];
+	res.entities_inside = cs->h_counters[256 + ST_ENT_INSIDE];
+	cs->has_last = true;
+	// descriptor per page + 16 B per tested sphere + (4 B id read + 4 B id write) per visible + 32 B mask per page
+	cs->last_bytes = (uint64_t)cs->last_pages * 32 + (uint64_t)res.entities_tested * 16 + (uint64_t)res.total * 8 + (uint64_t)cs->last_pages * 32;
+	if (result) *result = res;
+	return LB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int lb200_culling_create(lb200_ctx* ctx, lb200_culling** out) {
+	if (!out) return LB200_ERR_INVALID;
+	if (ctx && cudaSetDevice(ctx->device) != cudaSuccess) { cudaGetLastError(); return LB200_ERR_CUDA; }
+	*out = new (std::nothrow) lb200_culling(ctx);
+	return *out ? LB200_OK : LB200_ERR_CUDA;
+}
+
+void lb200_culling_destroy(lb200_culling* cs) {
+	if (!cs) return;
+	if (cs->ctx) {
+		cudaSetDevice(cs->ctx->device);
+		cudaStreamSynchronize(cs->ctx->stream);
+		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_out_ids); cudaFree(cs->d_mask);
+		cudaFree(cs->d_counters); cudaFree(cs->d_stage); cudaFree(cs->d_gather_ids); cudaFree(cs->d_gather_counts); cudaFree(cs->d_slab);
+		if (cs->h_counters) cudaFreeHost(cs->h_counters);
+		if (cs->h_stage) cudaFreeHost(cs->h_stage);
+	}
+	delete cs;
+}
+
+int lb200_culling_add(lb200_culling* cs, int32_t entity, uint8_t type, const double pos[3], float radius) {
+	if (!cs || !pos || type == LB200_TYPE_ALL) return LB200_ERR_INVALID;
+	return cs->host.add(entity, type, pos, radius);
+}
+int lb200_culling_remove(lb200_culling* cs, int32_t entity) { return cs ? cs->host.remove(entity) : LB200_ERR_INVALID; }
+int lb200_culling_set_position(lb200_culling* cs, int32_t entity, const double pos[3]) { return cs && pos ? cs->host.setPosition(entity, pos) : LB200_ERR_INVALID; }
+int lb200_culling_set_radius(lb200_culling* cs, int32_t entity, float radius) { return cs ? cs->host.setRadius(entity, radius) : LB200_ERR_INVALID; }
+int lb200_culling_set(lb200_culling* cs, int32_t entity, const double pos[3], float radius) { return cs && pos ? cs->host.set(entity, pos, radius) : LB200_ERR_INVALID; }
+float lb200_culling_get_radius(const lb200_culling* cs, int32_t entity) { return cs && cs->host.isAdded(entity) ? cs->host.getRadius(entity) : 0.0f; }
+int lb200_culling_is_added(const lb200_culling* cs, int32_t entity) { return cs && cs->host.isAdded(entity) ? 1 : 0; }
+
+int lb200_culling_add_many(lb200_culling* cs, const int32_t* entities, const uint8_t* types, const double* pos3, const float* radius, uint32_t n) {
+	if (!cs || (n && (!entities || !types || !pos3 || !radius))) return LB200_ERR_INVALID;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (types[i] == LB200_TYPE_ALL) return LB200_ERR_INVALID;
+		const int rc = cs->host.add(entities[i], types[i], pos3 + 3 * (size_t)i, radius[i]);
+		if (rc) return rc;
+	}
+	return LB200_OK;
+}
+int lb200_culling_set_many(lb200_culling* cs, const int32_t* entities, const double* pos3, const float* radius, uint32_t n) {
+	if (!cs || (n && (!entities || !pos3 || !radius))) return LB200_ERR_INVALID;
+	for (uint32_t i = 0; i < n; ++i) {
+		const int rc = cs->host.set(entities[i], pos3 + 3 * (size_t)i, radius[i]);
+		if (rc) return rc;
+	}
+	return LB200_OK;
+}
+int lb200_culling_set_position_many(lb200_culling* cs, const int32_t* entities, const double* pos3, uint32_t n) {
+	if (!cs || (n && (!entities || !pos3))) return LB200_ERR_INVALID;
+	for (uint32_t i = 0; i < n; ++i) {
+		const int rc = cs->host.setPosition(entities[i], pos3 + 3 * (size_t)i);
+		if (rc) return rc;
+	}
+	return LB200_OK;
+}
+int lb200_culling_set_radius_many(lb200_culling* cs, const int32_t* entities, const float* radius, uint32_t n) {
+	if (!cs || (n && (!entities || !radius))) return LB200_ERR_INVALID;
+	for (uint32_t i = 0; i < n; ++i) {
+		const int rc = cs->host.setRadius(entities[i], radius[i]);
+		if (rc) return rc;
+	}
+	return LB200_OK;
+}
+int lb200_culling_remove_many(lb200_culling* cs, const int32_t* entities, uint32_t n) {
+	if (!cs || (n && !entities)) return LB200_ERR_INVALID;
+	for (uint32_t i = 0; i < n; ++i) cs->host.remove(entities[i]);
+	return LB200_OK;
+}
+
+uint32_t lb200_culling_page_count(const lb200_culling* cs) { return cs ? (uint32_t)cs->host.cells.size() : 0; }
+uint32_t lb200_culling_entity_count(const lb200_culling* cs) { return cs ? cs->host.n_entities : 0; }
+
+int lb200_culling_get_page(const lb200_culling* cs, uint32_t page, double origin[3], int32_t indices[3], uint8_t* type, uint8_t* is_big,
+	uint32_t* count, float* spheres4, int32_t* entities)
+{
+	if (!cs || page >= cs->host.cells.size()) return LB200_ERR_INVALID;
+	const lb::CullingHost& h = cs->host;
+	const uint32_t p = h.cells[page];
+	if (origin) memcpy(origin, h.desc[p].origin, sizeof(double) * 3);
+	if (indices) { indices[0] = h.keys[p].x; indices[1] = h.keys[p].y; indices[2] = h.keys[p].z; }
+	if (type) *type = h.desc[p].type;
+	if (is_big) *is_big = h.desc[p].is_big;
+	if (count) *count = h.desc[p].count;
+	if (spheres4) memcpy(spheres4, h.spheres + 4 * PAGE_SLOTS * (size_t)p, sizeof(float) * 4 * h.desc[p].count);
+	if (entities) memcpy(entities, h.entities + PAGE_SLOTS * (size_t)p, sizeof(int32_t) * h.desc[p].count);
+	return LB200_OK;
+}
+
+int lb200_culling_flush(lb200_culling* cs) {
+	if (!cs) return LB200_ERR_INVALID;
+	if (!cs->ctx) { return LB200_ERR_NO_DEVICE; }
+	return flushPages(cs);
+}
+
+int lb200_culling_set_replicas(lb200_culling* cs, uint32_t replicas) {
+	if (!cs || replicas < 1 || replicas > 64) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	if (replicas == cs->replicas) return LB200_OK;
+	LB200_CUDA(cs->ctx, cudaStreamSynchronize(cs->ctx->stream));
+	cs->replicas = replicas;
+	cs->next_replica = 0;
+	cs->dev_cap = 0; // forces reallocation + full upload at the next flush
+	return LB200_OK;
+}
+
+int lb200_culling_cull_device(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
+	lb200_cull_result* result, int want_counts)
+{
+	if (!cs || !frustum) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	if (cs->host.cells.empty()) { // culling_system.cpp:322
+		if (result) memset(result, 0, sizeof(*result));
+		if (out_dev_ids) *out_dev_ids = nullptr;
+		memset(&cs->last, 0, sizeof(cs->last));
+		return LB200_OK;
+	}
+	int rc = launchCull(cs, frustum, type);
+	if (rc) return rc;
+	if (out_dev_ids) *out_dev_ids = cs->d_out_ids;
+	if (want_counts) rc = readCounts(cs, result);
+	else cs->has_last = false;
+	cs->parity ^= 1;
+	return rc;
+}
+
+int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity,
+	lb200_cull_result* result)
+{
+	if (!cs || !frustum || !result) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	lb200_cull_result dev;
+	const uint32_t* d_ids = nullptr;
+	int rc = lb200_culling_cull_device(cs, frustum, type, &d_ids, &dev, 1);
+	if (rc) return rc;
+	*result = dev;
+	uint32_t off = 0;
+	for (int t = 0; t < 256; ++t) { result->type_offset[t] = off; off += dev.type_count[t]; }
+	if (dev.total > capacity || (dev.total && !out_ids)) return LB200_ERR_CAPACITY;
+	lb200_ctx* ctx = cs->ctx;
+	for (int t = 0; t < 256; ++t) {
+		if (!dev.type_count[t]) continue;
+		LB200_CUDA(ctx, cudaMemcpyAsync(out_ids + result->type_offset[t], d_ids + dev.type_offset[t], sizeof(uint32_t) * dev.type_count[t], cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
+int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t capacity_words) {
+	if (!cs || !out_words) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	// bitmask is indexed by page id; report it in m_cells order like lb200_culling_get_page
+	const lb::CullingHost& h = cs->host;
+	const size_t n = h.cells.size();
+	if (capacity_words < n * 8) return LB200_ERR_CAPACITY;
+	std::vector<uint32_t> tmp((size_t)h.high_water * 8);
+	LB200_CUDA(cs->ctx, cudaMemcpyAsync(tmp.data(), cs->d_mask, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, cs->ctx->stream));
+	LB200_CUDA(cs->ctx, cudaStreamSynchronize(cs->ctx->stream));
+	for (size_t i = 0; i < n; ++i) memcpy(out_words + 8 * i, tmp.data() + 8 * (size_t)h.cells[i], sizeof(uint32_t) * 8);
+	return LB200_OK;
+}
+
+uint64_t lb200_culling_last_algorithmic_bytes(const lb200_culling* cs) { return cs && cs->has_last ? cs->last_bytes : 0; }
+
+} // extern "C"
+
+// ---- accessors for comm.cu ----
+lb200_ctx* lb200_culling_ctx(lb200_culling* cs) { return cs->ctx; }
+const uint32_t* lb200_culling_dev_ids(lb200_culling* cs) { return cs->d_out_ids; }
+const lb200_cull_result* lb200_culling_last_result(lb200_culling* cs) { return cs->has_last ? &cs->last : nullptr; }
+uint32_t** lb200_culling_gather_ids_slot(lb200_culling* cs, size_t** cap) { *cap = &cs->gather_ids_cap; return &cs->d_gather_ids; }
+uint32_t** lb200_culling_gather_counts_slot(lb200_culling* cs) { return &cs->d_gather_counts; }
+uint32_t** lb200_culling_slab_slot(lb200_culling* cs, size_t** cap) { *cap = &cs->slab_cap; return &cs->d_slab; }

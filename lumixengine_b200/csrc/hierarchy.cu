@@ -1,0 +1,266 @@
+// GPU hierarchy propagation: kernels + C-ABI (include/lumix_b200.h "Hierarchy").
+//
+// Replaces the serial recursion World::transformEntity (src/engine/world.cpp:255-282):
+//     child.global = parent.global.compose(child.local_transform)            (world.cpp:274-276)
+// with a batched level-order pass: nodes are sorted by depth once (children of one parent adjacent), every depth level
+// is one launch over a contiguous index range, and each thread evaluates Transform::compose (src/core/math.cpp:801-807)
+// with the reference's op order — fp64 position (Quat::rotate(DVec3), math.cpp:177-188), fp32 rotation / scale.
+// HBM layout is SoA (px,py,pz fp64; rot float4; sx,sy,sz fp32) so that every load/store instruction is fully coalesced;
+// the 56-byte engine Transform (math.h:306-327) exists only at the API boundary.
+// HBM-bound: 52 B local read + 4 B parent index + 52 B global write per node, + 52 B/fan-out for the parent gather.
+#include "lb200_internal.h"
+#include "lb200_math.cuh"
+
+#include <new>
+#include <vector>
+
+namespace {
+
+using namespace lb;
+
+struct SoaTransforms {
+	double* px = nullptr; double* py = nullptr; double* pz = nullptr;
+	float4* rot = nullptr;
+	float* sx = nullptr; float* sy = nullptr; float* sz = nullptr;
+};
+
+constexpr int HT = 256;
+
+// AoS (engine Transform, 56 B) in caller order -> SoA in level order.  only_roots: touch level-0 nodes only.
+__global__ void __launch_bounds__(HT) aos_to_soa_kernel(const lb200_transform* __restrict__ in, const uint32_t* __restrict__ order, uint32_t n,
+	SoaTransforms out)
+{
+	const uint32_t i = blockIdx.x * HT + threadIdx.x;
+	if (i >= n) return;
+	const lb200_transform t = in[order[i]];
+	out.px[i] = t.pos[0]; out.py[i] = t.pos[1]; out.pz[i] = t.pos[2];
+	out.rot[i] = make_float4(t.rot[0], t.rot[1], t.rot[2], t.rot[3]);
+	out.sx[i] = t.scale[0]; out.sy[i] = t.scale[1]; out.sz[i] = t.scale[2];
+}
+
+__global__ void __launch_bounds__(HT) soa_to_aos_kernel(SoaTransforms in, const uint32_t* __restrict__ order, uint32_t n, lb200_transform* __restrict__ out) {
+	const uint32_t i = blockIdx.x * HT + threadIdx.x;
+	if (i >= n) return;
+	lb200_transform t;
+	t.pos[0] = in.px[i]; t.pos[1] = in.py[i]; t.pos[2] = in.pz[i];
+	const float4 r = in.rot[i];
+	t.rot[0] = r.x; t.rot[1] = r.y; t.rot[2] = r.z; t.rot[3] = r.w;
+	t.scale[0] = in.sx[i]; t.scale[1] = in.sy[i]; t.scale[2] = in.sz[i];
+	out[order[i]] = t;
+}
+
+// One depth level: nodes [begin, end) in level order; parents live in earlier levels.
+__global__ void __launch_bounds__(HT) propagate_level_kernel(uint32_t begin, uint32_t end, const int* __restrict__ parent, SoaTransforms L, SoaTransforms G) {
+	const uint32_t i = begin + blockIdx.x * HT + threadIdx.x;
+	if (i >= end) return;
+	const int p = parent[i];
+	// parent global (siblings are adjacent: these loads coalesce to a few sectors per warp)
+	const D3 ppos = d3(G.px[p], G.py[p], G.pz[p]);
+	const float4 pr = G.rot[p];
+	const Q4 prot = q4(pr.x, pr.y, pr.z, pr.w);
+	const V3 pscale = v3(G.sx[p], G.sy[p], G.sz[p]);
+	// own local
+	const D3 lpos = d3(L.px[i], L.py[i], L.pz[i]);
+	const float4 lr = L.rot[i];
+	const V3 lscale = v3(L.sx[i], L.sy[i], L.sz[i]);
+	// math.cpp:801-807: { rot.rotate(rhs.pos * scale) + pos, rot * rhs.rot, scale * rhs.scale }
+	const D3 scaled = d3(LB_DMUL(lpos.x, (double)pscale.x), LB_DMUL(lpos.y, (double)pscale.y), LB_DMUL(lpos.z, (double)pscale.z)); // DVec3 * Vec3, math.cpp:498
+	const D3 gpos = add(rotate(prot, scaled), ppos);
+	const Q4 grot = qmul(prot, q4(lr.x, lr.y, lr.z, lr.w));
+	const V3 gscale = mul(pscale, lscale);
+	G.px[i] = gpos.x; G.py[i] = gpos.y; G.pz[i] = gpos.z;
+	G.rot[i] = make_float4(grot.x, grot.y, grot.z, grot.w);
+	G.sx[i] = gscale.x; G.sy[i] = gscale.y; G.sz[i] = gscale.z;
+}
+
+// render_module.cpp:1544-1554: world bounding sphere of a moved model instance
+__global__ void __launch_bounds__(HT) spheres_kernel(SoaTransforms G, const uint32_t* __restrict__ order, const float* __restrict__ bounding_radius, uint32_t n,
+	double* __restrict__ out_pos3, float* __restrict__ out_radius)
+{
+	const uint32_t i = blockIdx.x * HT + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t node = order[i];
+	const float sx = G.sx[i], sy = G.sy[i], sz = G.sz[i];
+	const float bc = sy > sz ? sy : sz; // maximum(a, b, c) = a > max(b, c) ? a : max(b, c), math.h:468-475
+	const float m = sx > bc ? sx : bc;
+	out_pos3[3 * (size_t)node + 0] = G.px[i];
+	out_pos3[3 * (size_t)node + 1] = G.py[i];
+	out_pos3[3 * (size_t)node + 2] = G.pz[i];
+	out_radius[node] = LB_FMUL(bounding_radius[node], m);
+}
+
+} // namespace
+
+struct lb200_hierarchy {
+	lb200_ctx* ctx = nullptr;
+	uint32_t n = 0;
+	std::vector<uint32_t> level_start; // size depth + 1
+	uint32_t* d_order = nullptr;       // level position -> caller node index
+	int* d_parent = nullptr;           // level position -> parent's level position
+	SoaTransforms L, G;
+	lb200_transform* d_stage = nullptr; // n Transforms (API boundary)
+	float* d_radius_in = nullptr;
+	double* d_sphere_pos = nullptr;
+	float* d_sphere_radius = nullptr;
+	uint64_t gather_bytes = 0;
+};
+
+namespace {
+
+int allocSoa(lb200_ctx* ctx, SoaTransforms& s, uint32_t n) {
+	LB200_CUDA(ctx, cudaMalloc(&s.px, sizeof(double) * n));
+	LB200_CUDA(ctx, cudaMalloc(&s.py, sizeof(double) * n));
+	LB200_CUDA(ctx, cudaMalloc(&s.pz, sizeof(double) * n));
+	LB200_CUDA(ctx, cudaMalloc(&s.rot, sizeof(float4) * n));
+	LB200_CUDA(ctx, cudaMalloc(&s.sx, sizeof(float) * n));
+	LB200_CUDA(ctx, cudaMalloc(&s.sy, sizeof(float) * n));
+	LB200_CUDA(ctx, cudaMalloc(&s.sz, sizeof(float) * n));
+	return LB200_OK;
+}
+
+void freeSoa(SoaTransforms& s) {
+	cudaFree(s.px); cudaFree(s.py); cudaFree(s.pz); cudaFree(s.rot); cudaFree(s.sx); cudaFree(s.sy); cudaFree(s.sz);
+}
+
+int upload(lb200_hierarchy* h, const lb200_transform* src, SoaTransforms dst, uint32_t count_levelorder) {
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_stage, src, sizeof(lb200_transform) * (size_t)h->n, cudaMemcpyHostToDevice, ctx->stream));
+	aos_to_soa_kernel<<<(count_levelorder + HT - 1) / HT, HT, 0, ctx->stream>>>(h->d_stage, h->d_order, count_levelorder, dst);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int lb200_hierarchy_create(lb200_ctx* ctx, const int32_t* parents, uint32_t n, lb200_hierarchy** out) {
+	if (!out || !parents || !n) return LB200_ERR_INVALID;
+	if (!ctx) return LB200_ERR_NO_DEVICE;
+	*out = nullptr;
+	// level order: children lists (as World::setParent keeps them, world.cpp:619-701), then BFS from the roots
+	std::vector<int32_t> first_child(n, -1), next_sibling(n, -1);
+	std::vector<uint32_t> order;
+	order.reserve(n);
+	for (uint32_t i = n; i-- > 0;) {
+		const int32_t p = parents[i];
+		if (p >= (int32_t)n) { lb200_set_error(ctx, "parent index %d out of range", p); return LB200_ERR_INVALID; }
+		if (p >= 0) { next_sibling[i] = first_child[p]; first_child[p] = (int32_t)i; }
+	}
+	std::vector<uint32_t> level_start;
+	level_start.push_back(0);
+	for (uint32_t i = 0; i < n; ++i) if (parents[i] < 0) order.push_back(i);
+	std::vector<int> parent_pos(n, -1);
+	std::vector<uint32_t> pos_of(n, 0);
+	uint32_t begin = 0;
+	while (begin < order.size()) {
+		const uint32_t end = (uint32_t)order.size();
+		level_start.push_back(end);
+		for (uint32_t k = begin; k < end; ++k) {
+			pos_of[order[k]] = k;
+			for (int32_t c = first_child[order[k]]; c >= 0; c = next_sibling[c]) {
+				parent_pos[order.size()] = (int)k;
+				order.push_back((uint32_t)c);
+			}
+		}
+		begin = end;
+	}
+	if (order.size() != n) { lb200_set_error(ctx, "hierarchy has a cycle (%zu of %u nodes reachable from roots)", order.size(), n); return LB200_ERR_INVALID; }
+
+	lb200_hierarchy* h = new (std::nothrow) lb200_hierarchy;
+	if (!h) return LB200_ERR_CUDA;
+	h->ctx = ctx;
+	h->n = n;
+	h->level_start = level_start;
+	// distinct parents per level -> bytes of the parent-global gather
+	uint64_t distinct = 0;
+	for (size_t l = 1; l + 1 < level_start.size(); ++l) {
+		int last = -1;
+		for (uint32_t k = level_start[l]; k < level_start[l + 1]; ++k) if (parent_pos[k] != last) { ++distinct; last = parent_pos[k]; }
+	}
+	h->gather_bytes = distinct * 52;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	LB200_CUDA(ctx, cudaMalloc(&h->d_order, sizeof(uint32_t) * n));
+	LB200_CUDA(ctx, cudaMalloc(&h->d_parent, sizeof(int) * n));
+	LB200_CUDA(ctx, cudaMalloc(&h->d_stage, sizeof(lb200_transform) * (size_t)n));
+	int rc = allocSoa(ctx, h->L, n);
+	if (!rc) rc = allocSoa(ctx, h->G, n);
+	if (rc) { lb200_hierarchy_destroy(h); return rc; }
+	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_order, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_parent, parent_pos.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	*out = h;
+	return LB200_OK;
+}
+
+void lb200_hierarchy_destroy(lb200_hierarchy* h) {
+	if (!h) return;
+	cudaSetDevice(h->ctx->device);
+	cudaStreamSynchronize(h->ctx->stream);
+	cudaFree(h->d_order); cudaFree(h->d_parent); cudaFree(h->d_stage); cudaFree(h->d_radius_in); cudaFree(h->d_sphere_pos); cudaFree(h->d_sphere_radius);
+	freeSoa(h->L); freeSoa(h->G);
+	delete h;
+}
+
+uint32_t lb200_hierarchy_depth(const lb200_hierarchy* h) { return h ? (uint32_t)h->level_start.size() - 1 : 0; }
+
+int lb200_hierarchy_set_locals(lb200_hierarchy* h, const lb200_transform* locals) {
+	if (!h || !locals) return LB200_ERR_INVALID;
+	return upload(h, locals, h->L, h->n);
+}
+
+int lb200_hierarchy_set_root_globals(lb200_hierarchy* h, const lb200_transform* globals) {
+	if (!h || !globals) return LB200_ERR_INVALID;
+	return upload(h, globals, h->G, h->level_start[1]); // level 0 only: everything else is produced by propagate
+}
+
+int lb200_hierarchy_propagate(lb200_hierarchy* h) {
+	if (!h) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	for (size_t l = 1; l + 1 < h->level_start.size(); ++l) {
+		const uint32_t begin = h->level_start[l], end = h->level_start[l + 1];
+		if (end == begin) continue;
+		propagate_level_kernel<<<(end - begin + HT - 1) / HT, HT, 0, ctx->stream>>>(begin, end, h->d_parent, h->L, h->G);
+		LB200_CHECK_LAUNCH(ctx);
+	}
+	return LB200_OK;
+}
+
+int lb200_hierarchy_get_globals(lb200_hierarchy* h, lb200_transform* out_globals) {
+	if (!h || !out_globals) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	soa_to_aos_kernel<<<(h->n + HT - 1) / HT, HT, 0, ctx->stream>>>(h->G, h->d_order, h->n, h->d_stage);
+	LB200_CHECK_LAUNCH(ctx);
+	LB200_CUDA(ctx, cudaMemcpyAsync(out_globals, h->d_stage, sizeof(lb200_transform) * (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
+int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius, double* out_pos3, float* out_radius) {
+	if (!h || !bounding_radius || !out_pos3 || !out_radius) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!h->d_radius_in) {
+		LB200_CUDA(ctx, cudaMalloc(&h->d_radius_in, sizeof(float) * h->n));
+		LB200_CUDA(ctx, cudaMalloc(&h->d_sphere_pos, sizeof(double) * 3 * (size_t)h->n));
+		LB200_CUDA(ctx, cudaMalloc(&h->d_sphere_radius, sizeof(float) * h->n));
+	}
+	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_radius_in, bounding_radius, sizeof(float) * h->n, cudaMemcpyHostToDevice, ctx->stream));
+	spheres_kernel<<<(h->n + HT - 1) / HT, HT, 0, ctx->stream>>>(h->G, h->d_order, h->d_radius_in, h->n, h->d_sphere_pos, h->d_sphere_radius);
+	LB200_CHECK_LAUNCH(ctx);
+	LB200_CUDA(ctx, cudaMemcpyAsync(out_pos3, h->d_sphere_pos, sizeof(double) * 3 * (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(out_radius, h->d_sphere_radius, sizeof(float) * h->n, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
+uint64_t lb200_hierarchy_algorithmic_bytes(const lb200_hierarchy* h) {
+	if (!h) return 0;
+	const uint64_t non_root = h->n - h->level_start[1];
+	return non_root * (52 + 4 + 52) + h->gather_bytes;
+}
+
+} // extern "C"

@@ -1,0 +1,59 @@
+// Internal declarations shared by the translation units of liblumix_b200.so.
+#pragma once
+
+#include "../../include/lumix_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+struct lb200_ctx {
+	int device = -1;
+	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;
+	int sm_count = 0;
+	std::atomic<uint64_t> launches{0};
+	char error[512] = {0};
+	// NCCL (dlopen) state, see comm.cu
+	void* nccl_lib = nullptr;
+	void* nccl_comm = nullptr;
+	int n_ranks = 1;
+	int rank = 0;
+};
+
+void lb200_set_error(lb200_ctx* ctx, const char* fmt, ...);
+
+#define LB200_CUDA(ctx, expr)                                                                        \
+	do {                                                                                             \
+		cudaError_t e__ = (expr);                                                                    \
+		if (e__ != cudaSuccess) {                                                                    \
+			lb200_set_error((ctx), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+			return LB200_ERR_CUDA;                                                                   \
+		}                                                                                            \
+	} while (0)
+
+#define LB200_CHECK_LAUNCH(ctx)                                                                      \
+	do {                                                                                             \
+		(ctx)->launches.fetch_add(1, std::memory_order_relaxed);                                     \
+		cudaError_t e__ = cudaGetLastError();                                                        \
+		if (e__ != cudaSuccess) {                                                                    \
+			lb200_set_error((ctx), "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+			return LB200_ERR_CUDA;                                                                   \
+		}                                                                                            \
+	} while (0)
+
+// Device page layout: page p owns slots [p*200, p*200+200) of the sphere / entity arrays.
+struct alignas(32) lb200_page_desc {
+	double origin[3]; // CellPage::header.origin, culling_system.cpp:55
+	uint32_t count;   // header.count (0 = free page, skipped by the kernel)
+	uint8_t type;     // header.indices.type
+	uint8_t is_big;   // header.indices.is_big
+	uint16_t pad;
+};
+static_assert(sizeof(lb200_page_desc) == 32, "page descriptor is one 32-byte sector");
+static_assert(sizeof(lb200_shifted_frustum) == 256, "ShiftedFrustum image, geometry.h:99-149");
+static_assert(sizeof(lb200_transform) == 56, "Transform image, math.h:306-327");
+static_assert(sizeof(lb200_track) == 32, "track descriptor");

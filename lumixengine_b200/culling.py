@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's CullingSystem interface (src/renderer/culling_system.h:58-77) over the C-ABI.
+
+Method names and argument meaning follow the reference (`add`, `remove`, `setPosition`, `setRadius`, `set`,
+`getRadius`, `isAdded`, `cull(frustum[, type])`); array arguments are the batched form of the same calls.
+`cull` returns a CullResult-like object (visible ids grouped per renderable type, culling_system.h:17-56).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ShiftedFrustum, check, ptr, vp
+
+TYPE_ALL = _lib.TYPE_ALL
+
+
+def frustum_perspective(position, direction, up, fov, ratio, near, far):
+    """ShiftedFrustum::computePerspective (src/core/geometry.cpp:470-499) -> ShiftedFrustum POD."""
+    f = ShiftedFrustum()
+    _lib.lib().lb200_frustum_perspective(C.byref(f), (C.c_double * 3)(*position), (C.c_float * 3)(*direction), (C.c_float * 3)(*up),
+                                         C.c_float(fov), C.c_float(ratio), C.c_float(near), C.c_float(far))
+    return f
+
+
+def frustum_ortho(position, direction, up, width, height, near, far):
+    """ShiftedFrustum::computeOrtho (src/core/geometry.cpp:390-409)."""
+    f = ShiftedFrustum()
+    _lib.lib().lb200_frustum_ortho(C.byref(f), (C.c_double * 3)(*position), (C.c_float * 3)(*direction), (C.c_float * 3)(*up),
+                                   C.c_float(width), C.c_float(height), C.c_float(near), C.c_float(far))
+    return f
+
+
+def frustum_bytes(f):
+    return np.frombuffer(bytes(f), np.uint8).copy()
+
+
+def frustum_from_bytes(b):
+    return ShiftedFrustum.from_buffer_copy(np.ascontiguousarray(b, np.uint8).tobytes())
+
+
+class CullResult:
+    """Flat form of the CullResult page chain: ids grouped by type; `pages()` re-chunks into <=1020-id pages."""
+
+    PAGE_IDS = 1020  # (4096 - 16) / 4, culling_system.h:55
+
+    def __init__(self, ids, raw):
+        self.ids = ids
+        self.raw = raw
+        self.total = int(raw.total)
+        self.type_count = np.ctypeslib.as_array(raw.type_count).copy()
+        self.type_offset = np.ctypeslib.as_array(raw.type_offset).copy()
+        self.stats = dict(pages_tested=int(raw.pages_tested), pages_inside=int(raw.pages_inside), pages_outside=int(raw.pages_outside),
+                          pages_filtered=int(raw.pages_filtered), entities_tested=int(raw.entities_tested), entities_inside=int(raw.entities_inside))
+
+    def count(self):  # CullResult::count, culling_system.h:26-34
+        return self.total
+
+    def of_type(self, t):
+        o, c = int(self.type_offset[t]), int(self.type_count[t])
+        return self.ids[o:o + c]
+
+    def types(self):
+        """uint8 type of every id, aligned with `ids`."""
+        out = np.empty(self.total, np.uint8)
+        for t in np.nonzero(self.type_count)[0]:
+            o, c = int(self.type_offset[t]), int(self.type_count[t])
+            out[o:o + c] = t
+        return out
+
+    def pages(self):
+        """[(type, ids<=1020)] — what the engine-side shim writes into PageAllocator pages."""
+        out = []
+        for t in np.nonzero(self.type_count)[0]:
+            seg = self.of_type(int(t))
+            for s in range(0, len(seg), self.PAGE_IDS):
+                out.append((int(t), seg[s:s + self.PAGE_IDS]))
+        return out
+
+
+class CullingSystem:
+    """CullingSystem::create(allocator, page_allocator) -> here CullingSystem(ctx).  ctx=None gives the host bookkeeping only
+    (no device; `cull` raises NoDeviceError)."""
+
+    def __init__(self, ctx=None):
+        self.L = _lib.lib()
+        self.ctx = ctx
+        h = vp()
+        check(self.L.lb200_culling_create(ctx.h if ctx else None, C.byref(h)), ctx.h if ctx else None)
+        self.h = h
+        self._out = None
+        self._out_pinned = None
+
+    def close(self):
+        if self.h:
+            self.L.lb200_culling_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, rc):
+        check(rc, self.ctx.h if self.ctx else None)
+
+    # ---- CullingSystem virtuals (scalar or array arguments) ----
+    def add(self, entity, type, pos, radius):
+        e = np.atleast_1d(np.asarray(entity, np.int32))
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(type, np.uint8), e.shape))
+        p = np.ascontiguousarray(np.asarray(pos, np.float64).reshape(-1, 3))
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), e.shape))
+        self._err(self.L.lb200_culling_add_many(self.h, ptr(e), ptr(t), ptr(p), ptr(r), C.c_uint32(len(e))))
+
+    def remove(self, entity):
+        e = np.atleast_1d(np.asarray(entity, np.int32))
+        self._err(self.L.lb200_culling_remove_many(self.h, ptr(e), C.c_uint32(len(e))))
+
+    def setPosition(self, entity, pos):
+        e = np.atleast_1d(np.asarray(entity, np.int32))
+        p = np.ascontiguousarray(np.asarray(pos, np.float64).reshape(-1, 3))
+        self._err(self.L.lb200_culling_set_position_many(self.h, ptr(e), ptr(p), C.c_uint32(len(e))))
+
+    def setRadius(self, entity, radius):
+        e = np.atleast_1d(np.asarray(entity, np.int32))
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), e.shape))
+        self._err(self.L.lb200_culling_set_radius_many(self.h, ptr(e), ptr(r), C.c_uint32(len(e))))
+
+    def set(self, entity, pos, radius):
+        e = np.atleast_1d(np.asarray(entity, np.int32))
+        p = np.ascontiguousarray(np.asarray(pos, np.float64).reshape(-1, 3))
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), e.shape))
+        self._err(self.L.lb200_culling_set_many(self.h, ptr(e), ptr(p), ptr(r), C.c_uint32(len(e))))
+
+    def getRadius(self, entity):
+        return float(self.L.lb200_culling_get_radius(self.h, C.c_int32(entity)))
+
+    def isAdded(self, entity):
+        return bool(self.L.lb200_culling_is_added(self.h, C.c_int32(entity)))
+
+    # ---- introspection ----
+    def page_count(self):
+        return int(self.L.lb200_culling_page_count(self.h))
+
+    def entity_count(self):
+        return int(self.L.lb200_culling_entity_count(self.h))
+
+    def pages(self):
+        out = []
+        for i in range(self.page_count()):
+            o = (C.c_double * 3)()
+            ind = (C.c_int32 * 3)()
+            ty, big, cnt = C.c_uint8(), C.c_uint8(), C.c_uint32()
+            sph = np.empty((_lib.PAGE_SLOTS, 4), np.float32)
+            ent = np.empty(_lib.PAGE_SLOTS, np.int32)
+            self._err(self.L.lb200_culling_get_page(self.h, C.c_uint32(i), o, ind, C.byref(ty), C.byref(big), C.byref(cnt), ptr(sph), ptr(ent)))
+            c = cnt.value
+            out.append(dict(origin=tuple(o), indices=tuple(ind), type=ty.value, is_big=big.value, count=c, spheres=sph[:c].copy(), entities=ent[:c].copy()))
+        return out
+
+    # ---- cull ----
+    def _out_buffer(self, n):
+        if self._out is None or len(self._out) < n:
+            cap = max(n, 1024)
+            self._out = self.ctx.host_alloc(cap, np.uint32) if self.ctx else np.empty(cap, np.uint32)
+        return self._out
+
+    def cull(self, frustum, type=TYPE_ALL):
+        """CullingSystem::cull(frustum[, type]) (culling_system.cpp:310-369): host frustum in, visible ids out (host)."""
+        if type != TYPE_ALL and not 0 <= type < 0xFF:
+            raise ValueError("type must be 0..254 (0xff is reserved for all types, culling_system.cpp:312)")
+        out = self._out_buffer(self.entity_count())
+        res = _lib.CullResult()
+        rc = self.L.lb200_culling_cull(self.h, C.byref(frustum), C.c_uint8(type), ptr(out), C.c_uint32(len(out)), C.byref(res))
+        self._err(rc)
+        return CullResult(out[:res.total].copy(), res)
+
+    def cull_device(self, frustum, type=TYPE_ALL, want_counts=True):
+        """Same cull, ids stay in HBM: returns (device pointer int, lb200_cull_result or None)."""
+        dev = vp()
+        res = _lib.CullResult()
+        rc = self.L.lb200_culling_cull_device(self.h, C.byref(frustum), C.c_uint8(type), C.byref(dev), C.byref(res) if want_counts else None,
+                                              C.c_int(1 if want_counts else 0))
+        self._err(rc)
+        return (dev.value or 0), (res if want_counts else None)
+
+    def flush(self):
+        self._err(self.L.lb200_culling_flush(self.h))
+
+    def set_replicas(self, n):
+        self._err(self.L.lb200_culling_set_replicas(self.h, C.c_uint32(n)))
+
+    def read_bitmask(self):
+        n = self.page_count()
+        out = np.zeros(max(n, 1) * 8, np.uint32)
+        self._err(self.L.lb200_culling_read_bitmask(self.h, ptr(out), C.c_uint32(len(out))))
+        return out[:n * 8].reshape(n, 8)
+
+    def last_algorithmic_bytes(self):
+        return int(self.L.lb200_culling_last_algorithmic_bytes(self.h))
+
+    def allgather(self, slab_ids, n_ranks):
+        counts = np.zeros(n_ranks * 256, np.uint32)
+        dev = vp()
+        self._err(self.L.lb200_culling_allgather(self.h, C.c_uint32(slab_ids), C.byref(dev), ptr(counts)))
+        return (dev.value or 0), counts.reshape(n_ranks, 256)

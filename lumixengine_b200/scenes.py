@@ -1,0 +1,147 @@
+"""Seeded synthetic scenes of the BASELINE.json configs (SURVEY.md §8d C1–C5).  Pure numpy: these are inputs, handed
+identically to the GPU path and to whatever checks it.
+"""
+import numpy as np
+
+from .animation import AnimationClip, SkinnedMesh, Skeleton
+from .hierarchy import TRANSFORM_DTYPE
+
+FOV_60 = 1.0472
+RATIO_16_9 = 16.0 / 9.0
+
+
+def cull_scene(n, extent=(2000.0, 200.0, 2000.0), seed=1, big_fraction=0.0, type_probs=(1.0,), radius=(0.5, 5.0)):
+    """n spheres uniform in [-ex,ex]x[-ey,ey]x[-ez,ez]; radius U[radius]; `big_fraction` get radius U[300,600] (is_big cells);
+    types drawn with `type_probs`.  Returns dict(entities i32, types u8, pos f64[n,3], radius f32)."""
+    rng = np.random.default_rng(seed)
+    ext = np.asarray(extent, np.float64)
+    pos = (rng.random((n, 3), np.float32).astype(np.float64) * 2.0 - 1.0) * ext
+    rad = (np.float32(radius[0]) + np.float32(radius[1] - radius[0]) * rng.random(n, np.float32)).astype(np.float32)
+    if big_fraction > 0:
+        big = rng.random(n) < big_fraction
+        rad[big] = (np.float32(300.0) + np.float32(300.0) * rng.random(int(big.sum()), np.float32)).astype(np.float32) + np.float32(0.5)
+    probs = np.asarray(type_probs, np.float64)
+    types = rng.choice(len(probs), size=n, p=probs / probs.sum()).astype(np.uint8)
+    return dict(entities=np.arange(n, dtype=np.int32), types=types, pos=np.ascontiguousarray(pos), radius=rad)
+
+
+def c1_scene(n=100_000, seed=1):
+    """C1: 100 k static spheres, type 0 (MESH); frustum c1_frustum_args()."""
+    return cull_scene(n, (2000.0, 200.0, 2000.0), seed)
+
+
+def c2_scene(n=10_000_000, seed=2):
+    """C2: 10 M entities, C1's box scaled x3 (x,z) / x1.5 (y), 0.1 % is_big, 4 renderable types 85/5/5/5 %."""
+    return cull_scene(n, (6000.0, 300.0, 6000.0), seed, big_fraction=0.001, type_probs=(0.85, 0.05, 0.05, 0.05))
+
+
+def c1_frustum_args():
+    return dict(position=(0.0, 0.0, 0.0), direction=(0.0, 0.0, -1.0), up=(0.0, 1.0, 0.0), fov=FOV_60, ratio=RATIO_16_9, near=0.1, far=1500.0)
+
+
+def c2_frustum_args():
+    """Same view as C1 with the far plane scaled with the box (x3) so the visible share stays in C1's regime (~15 %)."""
+    a = c1_frustum_args()
+    a["far"] = 4500.0
+    return a
+
+
+def random_unit_quats(rng, n):
+    q = rng.normal(size=(n, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32)
+    return q.astype(np.float32)
+
+
+def hierarchy_forest(n_total=1_000_000, depth=8, fanout=7, seed=3, root_extent=(6000.0, 300.0, 6000.0)):
+    """C3: forest of complete `fanout`-ary trees of exactly `depth` levels, truncated to n_total nodes.
+    Returns parents i32[n], locals TRANSFORM[n], root_globals TRANSFORM[n] (only roots meaningful)."""
+    rng = np.random.default_rng(seed)
+    per_tree = sum(fanout ** l for l in range(depth))
+    n_trees = max(1, n_total // per_tree)
+    # node numbering: tree-major, level-major inside a tree
+    level_sizes = [fanout ** l for l in range(depth)]
+    level_off = np.concatenate([[0], np.cumsum(level_sizes)])
+    local_parent = np.full(per_tree, -1, np.int64)
+    for l in range(1, depth):
+        idx = np.arange(level_sizes[l])
+        local_parent[level_off[l] + idx] = level_off[l - 1] + idx // fanout
+    parents = (local_parent[None, :] + (np.arange(n_trees, dtype=np.int64) * per_tree)[:, None])
+    parents[:, 0] = -1
+    parents = parents.reshape(-1)
+    n = len(parents)
+    if n < n_total:  # pad with extra roots so the node count is exact
+        parents = np.concatenate([parents, np.full(n_total - n, -1, np.int64)])
+        n = n_total
+    locals_ = np.zeros(n, TRANSFORM_DTYPE)
+    locals_["pos"] = (rng.random((n, 3)) * 20.0 - 10.0)
+    locals_["rot"] = random_unit_quats(rng, n)
+    locals_["scale"] = (np.float32(0.8) + np.float32(0.45) * rng.random((n, 3), np.float32)).astype(np.float32)
+    globals_ = np.zeros(n, TRANSFORM_DTYPE)
+    ext = np.asarray(root_extent, np.float64)
+    globals_["pos"] = (rng.random((n, 3)) * 2.0 - 1.0) * ext
+    globals_["rot"] = random_unit_quats(rng, n)
+    globals_["scale"] = (np.float32(0.8) + np.float32(0.45) * rng.random((n, 3), np.float32)).astype(np.float32)
+    return parents.astype(np.int32), locals_, globals_
+
+
+def skeleton(n_bones=64, seed=4):
+    """C4 skeleton: root + chains hanging off a 4-ary tree, parent < child."""
+    rng = np.random.default_rng(seed)
+    parents = np.full(n_bones, -1, np.int16)
+    for i in range(1, n_bones):
+        parents[i] = (i - 1) // 4 if i < 21 else i - 4  # 4-ary tree for the first 21 bones, then 4 parallel chains
+    rel_pos = (rng.random((n_bones, 3), np.float32) - np.float32(0.5)) * np.float32(0.6)
+    rel_rot = random_unit_quats(rng, n_bones)
+    from .animation import _qmul, _rotate
+    abs7 = np.zeros((n_bones, 7), np.float32)
+    for i in range(n_bones):
+        p = int(parents[i])
+        if p < 0:
+            abs7[i, :3], abs7[i, 3:] = rel_pos[i], rel_rot[i]
+        else:
+            abs7[i, :3] = _rotate(abs7[p, 3:][None], rel_pos[i][None])[0] + abs7[p, :3]
+            q = _qmul(abs7[p, 3:][None], rel_rot[i][None])[0]
+            abs7[i, 3:] = q / np.float32(np.linalg.norm(q))
+    return Skeleton(parents, abs7)
+
+
+def clip(skel, frames=60, fps=30.0, seed=5, pos_bits=(16, 16, 16), rot_bits=(15, 15, 15), const_fraction=0.25):
+    """Synthetic clip: smooth random walk around the bind pose; `const_fraction` of the bones keep constant tracks."""
+    rng = np.random.default_rng(seed)
+    B = skel.bone_count
+    n = frames + 1
+    base_p, base_r = skel.bind_relative7[:, :3], skel.bind_relative7[:, 3:]
+    t = np.linspace(0, 2 * np.pi, n, dtype=np.float32)[:, None, None]
+    amp = (rng.random((1, B, 3), np.float32) * np.float32(0.2))
+    phase = rng.random((1, B, 3), np.float32) * np.float32(6.28)
+    pos = base_p[None] + amp * np.sin(t + phase)
+    dq = rng.normal(size=(1, B, 4)).astype(np.float32) * np.float32(0.35)
+    rot = base_r[None] + dq * np.sin(t * np.float32(1.0) + phase[..., :1])
+    rot = rot / np.linalg.norm(rot, axis=-1, keepdims=True)
+    const = rng.random(B) < const_fraction
+    pos[:, const, :] = base_p[None, const, :]
+    const_r = rng.random(B) < const_fraction
+    rot[:, const_r, :] = base_r[None, const_r, :]
+    return AnimationClip.encode(fps, pos.astype(np.float32), rot.astype(np.float32), pos_bits, rot_bits)
+
+
+def mesh(skel, n_vertices=5000, seed=6):
+    """C4 mesh: 4 influences per vertex, weights normalised from u16 (model.cpp:544-547)."""
+    rng = np.random.default_rng(seed)
+    B = skel.bone_count
+    home = rng.integers(0, B, n_vertices)
+    idx = np.stack([home, np.maximum(skel.parents[home].astype(np.int64), 0), rng.integers(0, B, n_vertices), rng.integers(0, B, n_vertices)], axis=1)
+    w = rng.random((n_vertices, 4)) * np.array([1.0, 0.6, 0.3, 0.1])
+    w = w / w.sum(axis=1, keepdims=True)
+    w16 = np.round(w * 65535.0).astype(np.uint16)
+    weights = (w16.astype(np.float32) / np.float32(65535.0)).astype(np.float32)
+    pos = skel.bind_abs7[home, :3] + (rng.random((n_vertices, 3), np.float32) - np.float32(0.5)) * np.float32(0.3)
+    return SkinnedMesh(pos.astype(np.float32), weights, idx.astype(np.int16))
+
+
+def instance_times(n, clips, seed=7):
+    rng = np.random.default_rng(seed)
+    ci = rng.integers(0, len(clips), n).astype(np.uint32)
+    lengths = np.array([c.length_ticks for c in clips], np.uint32)
+    tt = (rng.random(n) * lengths[ci]).astype(np.uint32)
+    return ci, tt

@@ -75,7 +75,7 @@ EOF
 # (4) job_system.cpp: keep getWorker() out of line so &g_worker is recomputed after a fiber switch
 sed -i 's|^WorkerTask\* getWorker()|__attribute__((noinline)) WorkerTask* getWorker()|' "$S/core/job_system.cpp"
 
-CXX=${CXX:-g++}
+CXX=${LUMIX_REF_CXX:-/usr/bin/g++} # not $CXX: a wrapper there may link libstdc++ statically, which clashes with other C++ libs at exit
 FL="-std=c++20 -O2 -DSTATIC_PLUGINS -DNDEBUG -fno-exceptions -fno-rtti -msse2 -msse3 -ffp-contract=off -fPIC -w -fvisibility=hidden -I$S -I$REF/external"
 SRCS="renderer/culling_system core/job_system core/page_allocator core/default_allocator core/arena_allocator
       core/linux/thread core/linux/sync core/linux/atomic core/linux/fibers core/math core/geometry core/string
@@ -89,6 +89,6 @@ done
 $CXX $FL -c "$HERE/ref/ref_stubs.cpp" -o "$TMP/obj/ref_stubs.o" &
 $CXX $FL -c "$HERE/ref/ref_harness.cpp" -o "$TMP/obj/ref_harness.o" &
 wait
-$CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" -lpthread -Wl,--no-undefined
+$CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL
 ( cd "$REF" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$OUT/REFERENCE_COMMIT"
 echo "built $OUT/libref_lumix.so"

@@ -293,3 +293,38 @@ class RefCulling:
             raise RuntimeError("reference job system not initialised")
         k = min(n, cap)
         return ids[:k], tys[:k], dict(count=int(n), best_s=times[0], median_s=times[1], first_s=times[2], pages=int(pages.value))
+
+
+# ---------------------------------------------------------------------------------------------------
+# animation oracle (oracle_anim.c).  `skeleton` / `clips` are objects with .as_struct(cls) and numpy fields
+# (the product's lumixengine_b200.animation.Skeleton / AnimationClip are plain data holders and fit).
+# ---------------------------------------------------------------------------------------------------
+def animate_instances(skeleton, clips, clip_index, time_ticks, want=("pos", "rot", "dq", "mtx")):
+    """Model::getRelativePose -> Animation::getRelativePose -> Pose::computeAbsolute -> palettes, per instance."""
+    sk = skeleton.as_struct(Skeleton)
+    arr = (Clip * len(clips))(*[c.as_struct(Clip) for c in clips])
+    ci = np.ascontiguousarray(clip_index, np.uint32)
+    tt = np.ascontiguousarray(time_ticks, np.uint32)
+    n, B = len(ci), skeleton.bone_count
+    out = {}
+    pos = np.empty((n, B, 3), np.float32) if "pos" in want else None
+    rot = np.empty((n, B, 4), np.float32) if "rot" in want else None
+    dq = np.empty((n, B, 8), np.float32) if "dq" in want else None
+    mtx = np.empty((n, B, 16), np.float32) if "mtx" in want else None
+    lib().oracle_animate_instances(C.byref(sk), arr, _ptr(ci), _ptr(tt), C.c_uint32(n), _ptr(pos), _ptr(rot), _ptr(dq), _ptr(mtx))
+    out.update(pos=pos, rot=rot, dq=dq, mtx=mtx)
+    return out
+
+
+def skin_vertices(matrices, positions, weights, indices):
+    m = np.ascontiguousarray(matrices, np.float32)
+    p = np.ascontiguousarray(positions, np.float32)
+    w = np.ascontiguousarray(weights, np.float32)
+    i = np.ascontiguousarray(indices, np.int16)
+    out = np.empty_like(p)
+    lib().oracle_skin_vertices(_ptr(m), _ptr(p), _ptr(w), _ptr(i), _ptr(out), C.c_uint32(len(p)))
+    return out
+
+
+def time_advance(time_ticks, time_delta, fps, frame_count):
+    return int(lib().oracle_time_advance(C.c_uint32(int(time_ticks)), C.c_float(time_delta), C.c_float(fps), C.c_uint32(frame_count)))

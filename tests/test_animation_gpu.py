@@ -1,0 +1,124 @@
+"""GPU parity of pose evaluation, skinning palettes and CPU-path skinning against the oracle.
+
+north_star tolerance: 1e-5 relative for skin matrices.  The kernels keep the reference's op order without FMA, so the
+tests first try bit-exactness and otherwise enforce the 1e-5 bound (relative to the largest magnitude of the row).
+"""
+import numpy as np
+import pytest
+
+import lumixengine_b200 as lb
+from lumixengine_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+
+
+def _close(got, exp, what):
+    if np.array_equal(got.view(np.uint32), exp.view(np.uint32)):
+        return True
+    g, e = got.astype(np.float64), exp.astype(np.float64)
+    scale = np.maximum(np.abs(e).max(axis=-1, keepdims=True), 1e-6)
+    bad = np.abs(g - e) > REL_TOL * scale
+    assert not bad.any(), f"{what}: {bad.sum()} values beyond 1e-5 relative (max abs err {np.abs(g - e).max()})"
+    return False
+
+
+def _setup(ctx, n_bones, n_clips, n_inst, n_verts=0, seed=0, **clip_kw):
+    sk = scenes.skeleton(n_bones, seed=seed + 4)
+    clips = [scenes.clip(sk, frames=30 + 7 * i, fps=30.0 if i % 2 == 0 else 24.0, seed=seed + 10 + i, **clip_kw) for i in range(n_clips)]
+    mesh = scenes.mesh(sk, n_verts, seed=seed + 6) if n_verts else None
+    anim = lb.AnimationSystem(ctx, sk, clips, mesh, max_instances=n_inst)
+    ci, tt = scenes.instance_times(n_inst, clips, seed=seed + 7)
+    anim.setInstances(ci, tt)
+    return sk, clips, mesh, anim, ci, tt
+
+
+@pytest.mark.parametrize("n_bones,n_clips,n_inst", [(64, 4, 3000), (5, 1, 33), (196, 2, 500), (1, 1, 10)])
+def test_pose_and_palettes_match_oracle(ctx, oracle, n_bones, n_clips, n_inst):
+    sk, clips, _, anim, ci, tt = _setup(ctx, n_bones, n_clips, n_inst, seed=n_bones)
+    anim.update(0.0, lb.PALETTE_DUAL_QUAT | lb.PALETTE_MATRIX | lb.PALETTE_POSE)
+    exp = oracle.animate_instances(sk, clips, ci, tt)
+    pos, rot = anim.getPose()
+    exact = [_close(pos, exp["pos"], "pose.pos"), _close(rot, exp["rot"], "pose.rot"),
+             _close(anim.getDualQuats(), exp["dq"], "dual quats"), _close(anim.getMatrices(), exp["mtx"], "matrices")]
+    assert np.array_equal(anim.getTimes(), tt)  # time_delta == 0 leaves the animables' time alone
+    print("bit-exact:", exact)
+
+
+def test_clip_edges_and_bit_widths(ctx, oracle):
+    """t = 0, t = length-1, times beyond the clip (clamped by frame_count - 1e-5), odd bit widths (11..16 + 57-bit tracks)."""
+    sk = scenes.skeleton(24, seed=2)
+    clips = [scenes.clip(sk, frames=17, fps=30.0, seed=3, pos_bits=(11, 13, 16), rot_bits=(12, 14, 16), const_fraction=0.0),
+             scenes.clip(sk, frames=60, fps=60.0, seed=4, pos_bits=(16, 16, 16), rot_bits=(16, 16, 16), const_fraction=0.5),
+             scenes.clip(sk, frames=2, fps=1.0, seed=5, pos_bits=(5, 3, 7), rot_bits=(9, 9, 9), const_fraction=1.0)]
+    anim = lb.AnimationSystem(ctx, sk, clips, None, max_instances=64)
+    ci, tt = [], []
+    for c, clip in enumerate(clips):
+        L = clip.length_ticks
+        for t in (0, 1, L // 2, L - 1, L, L + 5000, 2 ** 31):
+            ci.append(c); tt.append(t)
+    ci, tt = np.array(ci, np.uint32), np.array(tt, np.uint32)
+    anim.setInstances(ci, tt)
+    anim.update(0.0, lb.PALETTE_DUAL_QUAT | lb.PALETTE_POSE)
+    exp = oracle.animate_instances(sk, clips, ci, tt, want=("pos", "rot", "dq"))
+    pos, rot = anim.getPose()
+    _close(pos, exp["pos"], "pos"); _close(rot, exp["rot"], "rot"); _close(anim.getDualQuats(), exp["dq"], "dq")
+
+
+def test_time_advance(ctx, oracle):
+    sk, clips, _, anim, ci, tt = _setup(ctx, 16, 3, 2000, seed=40)
+    for dt in (1.0 / 60.0, 0.5, 3.7, -0.25):
+        anim.setInstances(ci, tt)
+        anim.update(dt, lb.PALETTE_DUAL_QUAT)
+        got = anim.getTimes()
+        if dt > 0:
+            exp = np.array([oracle.time_advance(t, dt, clips[c].fps, clips[c].frame_count) for c, t in zip(ci, tt)], np.uint32)
+        else:  # animation_module.cpp:462-468
+            exp = []
+            for c, t in zip(ci, tt):
+                l = clips[c].length_ticks
+                d = int(np.uint32(np.float32(-dt) * np.float32(32768))) % l
+                exp.append((int(t) + l - d) % l)
+            exp = np.array(exp, np.uint32)
+        assert np.array_equal(got, exp)
+
+
+def test_skinning_matches_oracle(ctx, oracle):
+    sk, clips, mesh, anim, ci, tt = _setup(ctx, 64, 2, 37, n_verts=1777, seed=70)
+    anim.update(0.0, lb.PALETTE_MATRIX)
+    anim.skin()
+    got = anim.getSkinned()
+    mtx = anim.getMatrices()
+    for i in (0, 5, 36):
+        exp = oracle.skin_vertices(mtx[i], mesh.positions, mesh.weights, mesh.indices)
+        _close(got[i], exp, f"skinned verts of instance {i}")
+    # checksum of the device buffer equals the checksum of what was read back
+    assert anim.skinnedChecksum() == int(got.view(np.uint32).astype(np.uint64).sum())
+
+
+def test_c4_size_properties(ctx):
+    """Config 4 shapes at reduced instance count that still exceeds L2 (20 k x 64 bones x 5 k verts = 1.2 GB out):
+    rigid property — with every weight on one bone, skinning equals the bone matrix applied to the vertex."""
+    sk = scenes.skeleton(64)
+    clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
+    mesh = scenes.mesh(sk, 5000)
+    mesh.weights[:] = 0
+    mesh.weights[:, 0] = 1.0
+    n = 20_000
+    anim = lb.AnimationSystem(ctx, sk, clips, mesh, max_instances=n)
+    ci, tt = scenes.instance_times(n, clips)
+    anim.setInstances(ci, tt)
+    anim.update(1.0 / 30.0, lb.PALETTE_MATRIX | lb.PALETTE_DUAL_QUAT)
+    anim.skin()
+    for first in (0, n - 3):
+        m = anim.getMatrices(first, 3).reshape(3, 64, 4, 4)  # [col][row]
+        v = anim.getSkinned(first, 3)
+        mv = m[:, mesh.indices[:, 0]]  # (3, V, 4, 4)
+        p = mesh.positions
+        exp = mv[:, :, 0, :3] * p[None, :, 0:1] + mv[:, :, 1, :3] * p[None, :, 1:2] + mv[:, :, 2, :3] * p[None, :, 2:3] + mv[:, :, 3, :3]
+        assert np.allclose(v, exp, rtol=1e-5, atol=1e-5)
+    # dual quaternion palette: real part is a unit quaternion, dual part orthogonal to it
+    dq = anim.getDualQuats(0, 100)
+    assert np.allclose(np.linalg.norm(dq[..., :4], axis=-1), 1.0, atol=1e-4)
+    assert np.all(np.abs((dq[..., :4] * dq[..., 4:]).sum(axis=-1)) < 1e-3)

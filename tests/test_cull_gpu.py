@@ -1,0 +1,166 @@
+"""GPU parity of CullingSystem::cull against the oracle (bit-exact visible sets per renderable type)."""
+import numpy as np
+import pytest
+
+import lumixengine_b200 as lb
+from lumixengine_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(ctx, oracle, scene):
+    cs = lb.CullingSystem(ctx)
+    cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    oc = oracle.OracleCulling()
+    oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    return cs, oc
+
+
+def _assert_same(res, oids, otys):
+    assert res.total == len(oids)
+    got = np.sort(res.ids.astype(np.int64) * 256 + res.types())
+    exp = np.sort(oids.astype(np.int64) * 256 + otys)
+    assert np.array_equal(got, exp)
+
+
+def _frustums():
+    a = scenes.c1_frustum_args()
+    yield "c1", a
+    b = dict(a); b["position"] = (123.456, -20.0, 987.0); b["direction"] = (0.3, -0.1, -0.9); b["far"] = 900.0
+    yield "tilted", b
+    c = dict(a); c["position"] = (-1500.0, 50.0, -1500.0); c["direction"] = (1.0, 0.0, 1.0); c["far"] = 5000.0
+    yield "diag_far", c
+    d = dict(a); d["position"] = (1e6 + 0.25, 0.0, -2e6 + 0.5); d["far"] = 100.0
+    yield "nothing", d
+
+
+@pytest.mark.parametrize("name,args", list(_frustums()))
+def test_c1_100k_matches_oracle(ctx, oracle, name, args):
+    scene = scenes.c1_scene(100_000)
+    cs, oc = _both(ctx, oracle, scene)
+    f = lb.frustum_perspective(**args)
+    fo = oracle.frustum_perspective(args["position"], args["direction"], args["up"], args["fov"], args["ratio"], args["near"], args["far"])
+    assert bytes(f) == fo.tobytes()
+    res = cs.cull(f)
+    oids, otys, st = oc.cull(fo)
+    _assert_same(res, oids, otys)
+    assert res.stats["pages_tested"] == st["pages_tested"]
+    assert res.stats["pages_inside"] == st["pages_inside"]
+    assert res.stats["pages_outside"] == st["pages_outside"]
+    assert res.stats["entities_tested"] == st["entities_tested"]
+
+
+def test_types_big_and_filter(ctx, oracle):
+    scene = scenes.cull_scene(300_000, (3000.0, 300.0, 3000.0), seed=11, big_fraction=0.01, type_probs=(0.6, 0.2, 0.1, 0.1))
+    cs, oc = _both(ctx, oracle, scene)
+    args = scenes.c1_frustum_args(); args["far"] = 2500.0
+    f = lb.frustum_perspective(**args)
+    fo = lb.culling.frustum_bytes(f)
+    res = cs.cull(f)
+    oids, otys, _ = oc.cull(fo)
+    _assert_same(res, oids, otys)
+    for t in range(5):
+        r = cs.cull(f, t)
+        i2, t2, _ = oc.cull(fo, type=t)
+        _assert_same(r, i2, t2)
+        assert set(np.unique(r.types())) <= {t}
+
+
+def test_ortho_frustum(ctx, oracle):
+    scene = scenes.c1_scene(50_000, seed=5)
+    cs, oc = _both(ctx, oracle, scene)
+    f = lb.frustum_ortho((10.0, 500.0, -20.0), (0.0, 1.0, 0.05), (0.0, 0.0, 1.0), 700.0, 400.0, 0.0, 1200.0)
+    res = cs.cull(f)
+    oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f))
+    _assert_same(res, oids, otys)
+
+
+def test_incremental_updates_and_bitmask(ctx, oracle):
+    rng = np.random.default_rng(3)
+    scene = scenes.c1_scene(60_000, seed=9)
+    cs, oc = _both(ctx, oracle, scene)
+    f = lb.frustum_perspective(**scenes.c1_frustum_args())
+    fo = lb.culling.frustum_bytes(f)
+    for step in range(4):
+        n = 3000
+        ids = rng.choice(60_000, n, replace=False).astype(np.int32)
+        alive = np.array([cs.isAdded(int(i)) for i in ids])
+        ids = ids[alive]
+        third = len(ids) // 3
+        mv, rs, rm = ids[:third], ids[third:2 * third], ids[2 * third:]
+        newpos = scene["pos"][mv] + rng.normal(size=(len(mv), 3)) * np.array([400.0, 40.0, 400.0])
+        cs.setPosition(mv, newpos); oc.set_position(mv, newpos)
+        newrad = (rng.random(len(rs)) * 700.0).astype(np.float32)  # crosses the is_big threshold both ways
+        cs.setRadius(rs, newrad); oc.set_radius(rs, newrad)
+        cs.remove(rm); oc.remove(rm)
+        res = cs.cull(f)
+        oids, otys, _ = oc.cull(fo)
+        _assert_same(res, oids, otys)
+    # visibility bitmask (page, slot) agrees with the id list
+    res = cs.cull(f)
+    mask = cs.read_bitmask()
+    pages = cs.pages()
+    from_mask = []
+    for p, words in zip(pages, mask):
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:p["count"]]
+        from_mask.append(p["entities"][bits.astype(bool)])
+    from_mask = np.sort(np.concatenate(from_mask))
+    assert np.array_equal(from_mask, np.sort(res.ids.astype(np.int32)))
+
+
+def test_empty_and_tiny(ctx, oracle):
+    cs = lb.CullingSystem(ctx)
+    f = lb.frustum_perspective(**scenes.c1_frustum_args())
+    assert cs.cull(f).total == 0  # culling_system.cpp:322: no cells -> nothing
+    cs.add(7, 2, (0.0, 0.0, -10.0), 1.0)
+    r = cs.cull(f)
+    assert r.total == 1 and r.ids[0] == 7 and r.types()[0] == 2
+    cs.remove(7)
+    assert cs.cull(f).total == 0
+
+
+def test_tangent_and_border_cases(ctx, oracle):
+    """Spheres within a few ulps of the planes, entities on cell borders and at negative coordinates."""
+    rng = np.random.default_rng(21)
+    args = scenes.c1_frustum_args()
+    f = lb.frustum_perspective(**args)
+    fb = lb.culling.frustum_bytes(f)
+    xs, ys, zs, ds = (np.array(getattr(f, k)[:6], np.float64) for k in ("xs", "ys", "zs", "ds"))
+    n = 40_000
+    pos = (rng.random((n, 3)) * 2 - 1) * np.array([1800.0, 180.0, 1800.0])
+    rad = (rng.random(n) * 4 + 0.5).astype(np.float32)
+    # push each point onto a random plane at distance ~radius (tangent within rounding)
+    k = rng.integers(0, 6, n)
+    nrm = np.stack([xs[k], ys[k], zs[k]], axis=1)
+    dist = (pos * nrm).sum(axis=1) + ds[k]
+    pos = pos - nrm * (dist + rad.astype(np.float64))[:, None] + nrm * rng.normal(size=(n, 1)) * 1e-5
+    # and a batch exactly on multiples of the cell size, incl. negative ones
+    grid = (rng.integers(-6, 7, (5000, 3)) * 300.0).astype(np.float64)
+    pos = np.concatenate([pos, grid])
+    rad = np.concatenate([rad, np.full(5000, 2.0, np.float32)])
+    scene = dict(entities=np.arange(len(pos), dtype=np.int32), types=np.zeros(len(pos), np.uint8), pos=pos, radius=rad)
+    cs, oc = _both(ctx, oracle, scene)
+    res = cs.cull(f)
+    oids, otys, _ = oc.cull(fb)
+    _assert_same(res, oids, otys)
+
+
+def test_10m_properties(ctx):
+    """Full C2 size: size-independent properties (the oracle is not run at this size inside the GPU suite)."""
+    scene = scenes.c2_scene(10_000_000)
+    cs = lb.CullingSystem(ctx)
+    cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    f = lb.frustum_perspective(**scenes.c2_frustum_args())
+    r1 = cs.cull(f)
+    # unique ids, all valid, type segments consistent with the scene's types
+    assert len(np.unique(r1.ids)) == r1.total
+    assert np.array_equal(scene["types"][r1.ids], r1.types())
+    # idempotence + invariance to replica rotation
+    r2 = cs.cull(f)
+    assert np.array_equal(np.sort(r1.ids), np.sort(r2.ids))
+    # per-type culls partition the all-types cull
+    parts = [cs.cull(f, t).ids for t in range(4)]
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.sort(r1.ids))
+    # a frustum containing the whole scene returns everything
+    big = lb.frustum_ortho((0.0, 0.0, 20000.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0), 20000.0, 20000.0, 0.0, 40000.0)
+    assert cs.cull(big).total == 10_000_000
