@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the LumixEngine hot path on B200 (contract: task brief "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, liblumix_b200.so)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU cull on the host cores
+
+Metric (BASELINE.json): M entities culled/s.  Workload at N=1: configs[1] = "10M static entities, 1 camera frustum cull,
+single B200" (scene C2 of SURVEY.md §8d).  A step = one CullingSystem::cull of the whole scene for one frustum.
+N>1 (torchrun, one rank per GPU): weak scaling — every rank owns its own 10 M-entity shard (whole cell pages, no
+data-path collective for the cull itself) and each step ends with the one exchange the path has: the NCCL all-gather of the
+compacted visible lists.  `value` = all ranks' entities / max-over-ranks device time.
+The JSON line also carries the secondary BASELINE metric (M skinned verts/s) and the other stages of the path under "paths".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ENTITIES = 10_000_000
+REPLICAS = 8  # scene copies rotated through by successive culls: 8 x ~200 MB > 126 MB L2
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write bytes)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def traffic_from_profile(kernel):
+    """dram bytes per launch from the committed ncu capture, if any (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under our load (B200_PROFILING.md 'clocks line')."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9 or not (t0 <= ts <= t1 + 0.1):
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "sampled": "50 ms nvidia-smi samples over the timed regions plus a ~1.5 s probe loop of the same cull kernel"}
+
+
+def run_cpu_worker(args, timeout=900):
+    cmd = [sys.executable, "-m", "oracle.cpu_baseline"] + args
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    for line in out.stdout.splitlines():
+        if line.startswith("CPU_BASELINE_JSON "):
+            return json.loads(line[len("CPU_BASELINE_JSON "):])
+    raise RuntimeError("cpu baseline worker failed: " + out.stderr[-2000:])
+
+
+def reference_arm(a, rank):
+    """The reference's own CPU implementation (oracle/_ref) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    r = run_cpu_worker(["--workload", "cull", "--n", str(N_ENTITIES), "--scene", "c2", "--steps", str(a.steps), "--warmup", str(a.warmup)])
+    ms = r["median_s"] * 1e3
+    line = {
+        "impl": "reference", "metric": "M entities culled/s", "value": r["value"], "unit": "M entities/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: 10M static entities, 1 camera frustum cull", "entities_per_step": N_ENTITIES, "visible": r["visible"],
+                   "note": "one 10M shard culled on the host whatever --gpus is (bounded sample of the N-shard job)"},
+        "cpu_baseline": {"value": r["value"], "unit": "M entities/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "impl": r["impl"]},
+        "e2e": {"value": r["value"], "unit": "M entities/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def time_region(ctx, fn, steps):
+    e0, e1 = ctx.event(), ctx.event()
+    ctx.synchronize()
+    ctx.record(e0)
+    for _ in range(steps):
+        fn()
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1)
+    return ms
+
+
+def secondary_paths(ctx, lb, scenes, peak, steps, warmup):
+    """Other stages of the hot path: 1M-node propagate (config 3), 100k x 64-bone pose+palette and 100k x 5k-vert skin (config 4)."""
+    out = {}
+    # --- propagate ---
+    parents, locals_, roots = scenes.hierarchy_forest(1_000_000, 8, 7, seed=3)
+    h = lb.Hierarchy(ctx, parents)
+    h.setLocalTransforms(locals_)
+    h.setRootTransforms(roots)
+    for _ in range(max(warmup, 3)):
+        h.propagate()
+    ms = time_region(ctx, h.propagate, steps) / steps
+    b = h.algorithmic_bytes()
+    out["propagate_1m_depth8"] = {"value": len(parents) / ms / 1e3, "unit": "M nodes/s", "ms_per_step": ms,
+                                  "roofline": {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": b / ms / 1e6 / peak, "algorithmic_bytes": b},
+                                  "note": "7 level launches per step; 112 MB working set is L2-resident across steps (not flushed) — kernel-chain latency bound"}
+    h.close()
+    # --- pose + palette, skin ---
+    sk = scenes.skeleton(64)
+    clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
+    mesh = scenes.mesh(sk, 5000)
+    n_inst = 100_000
+    anim = lb.AnimationSystem(ctx, sk, clips, mesh, max_instances=n_inst)
+    ci, tt = scenes.instance_times(n_inst, clips)
+    anim.setInstances(ci, tt)
+    flags = lb.PALETTE_DUAL_QUAT
+    for _ in range(max(warmup, 3)):
+        anim.update(1.0 / 60.0, flags)
+    ms = time_region(ctx, lambda: anim.update(1.0 / 60.0, flags), steps) / steps
+    b = anim.algorithmic_bytes(flags)
+    out["pose_palette_100k_x64"] = {"value": n_inst * 64 / ms / 1e3, "unit": "M bone-instances/s", "ms_per_step": ms,
+                                    "roofline": {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": b / ms / 1e6 / peak, "algorithmic_bytes": b},
+                                    "note": "dual-quaternion palette (pipeline.cpp:2680-2745), 205 MB written per step (> L2)"}
+    anim.update(0.0, lb.PALETTE_MATRIX)
+    for _ in range(max(warmup, 3)):
+        anim.skin()
+    sk_steps = max(3, min(steps, 10))
+    ms = time_region(ctx, anim.skin, sk_steps) / sk_steps
+    b = anim.algorithmic_bytes(lb.PALETTE_MATRIX, skin=True)
+    out["skin_100k_x5k"] = {"value": n_inst * 5000 / ms / 1e3, "unit": "M skinned verts/s", "ms_per_step": ms,
+                            "roofline": {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": b / ms / 1e6 / peak, "algorithmic_bytes": b},
+                            "note": "evaluateSkin (model.cpp:103-109), 6 GB written per step"}
+    anim.close()
+    return out
+
+
+def ours(a, rank, world):
+    import lumixengine_b200 as lb
+    from lumixengine_b200 import scenes
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        device = local
+    else:
+        device = 0
+    ctx = lb.Context(device)  # NoDeviceError without a GPU / ImportError without the .so: no fallback
+    peak, peak_src = measured_peaks()
+
+    # ---- scene: C2 shard of this rank (distinct seed per rank) ----
+    scene = scenes.c2_scene(N_ENTITIES, seed=2 + rank)
+    cs = lb.CullingSystem(ctx)
+    cs.set_replicas(REPLICAS)
+    t0 = time.time()
+    cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    build_s = time.time() - t0
+    cs.flush()
+    f = lb.frustum_perspective(**scenes.c2_frustum_args())
+
+    if world > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(ctx.comm_unique_id()))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, uid.cpu().numpy())
+
+    first = cs.cull(f)  # also the warm-up of every buffer; gives the visible count for sizing the gather slab
+    visible = first.total
+    slab = 0
+    if world > 1:
+        import torch
+        t = torch.tensor([visible], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        slab = int(t.item()) + 1024
+
+    def step_device():
+        if world > 1:
+            cs.cull_device(f, want_counts=True)  # the gather needs the per-type counts on the host
+            cs.allgather(slab, world)
+        else:
+            cs.cull_device(f, want_counts=False)
+
+    sampler = ClockSampler(device)
+    sampler.start()
+    t_load0 = time.time()
+    for _ in range(max(a.warmup, 3) + 50):
+        step_device()
+    ctx.synchronize()
+
+    # ---- timed region: EXACTLY K steps, barrier + sync both sides, device time, max over ranks ----
+    if world > 1:
+        dist.barrier()
+    launches0 = ctx.launches
+    ms_total = time_region(ctx, step_device, a.steps)
+    launches = ctx.launches - launches0
+    if world > 1:
+        import torch
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        dist.barrier()
+    ms_step = ms_total / a.steps
+
+    # algorithmic bytes of one cull (needs counts: one more cull, untimed)
+    cs.cull_device(f, want_counts=True)
+    alg_bytes = cs.last_algorithmic_bytes()
+    stats = cs.cull(f).stats
+
+    # kernel-only timing for the roofline (N>1 steps also contain the gather): K launches of the cull kernel alone
+    ms_kernel = time_region(ctx, lambda: cs.cull_device(f, want_counts=False), a.steps) / a.steps
+
+    # ---- e2e: the public host API, frustum in host memory -> visible ids in pinned host memory, every step ----
+    for _ in range(3):
+        cs.cull(f)
+    e2e_steps = max(3, min(a.steps, 50))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = cs.cull(f)
+    ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    # clock probe: the same kernel back to back for ~1.5 s so that nvidia-smi has samples under this load
+    t_probe = time.time()
+    while time.time() - t_probe < 1.5:
+        for _ in range(200):
+            cs.cull_device(f, want_counts=False)
+        ctx.synchronize()
+    clocks = sampler.stop(t_load0, time.time())
+
+    if rank != 0:
+        ctx.close()
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    total_entities = N_ENTITIES * world
+    line = {
+        "metric": "M entities culled/s", "value": total_entities / ms_step / 1e3, "unit": "M entities/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: 10M static entities, 1 camera frustum cull (BASELINE.json configs[1]); per GPU at N>1", "entities_per_gpu": N_ENTITIES,
+                   "visible_per_gpu": int(visible), "pages": cs.page_count(), "frustum": "perspective fov 60deg 16:9 near 0.1 far 4500 at origin looking -z",
+                   "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{cs.page_count() * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
+                   "parallelism": f"dp{world}: whole cell pages per rank" + ("; ncclAllGather of the visible lists each step" if world > 1 else ""),
+                   "scene_build_s": build_s, "page_stats": stats},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": total_entities / e2e_s / 1e6, "unit": "M entities/s", "h2d_bytes_per_step": 256 + 1024 + 8, "d2h_bytes_per_step": int(r.total) * 4 + 264 * 4,
+                "ms_per_step": e2e_s * 1e3, "api": "CullingSystem.cull(frustum): host frustum -> kernel params, visible ids + counts copied to pinned host memory"},
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / ms_kernel / 1e6, "peak": peak, "unit": "GB/s", "frac": alg_bytes / ms_kernel / 1e6 / peak,
+                     "traffic": traffic_from_profile("cull_pages_kernel"), "kernel": "cull_pages_kernel", "kernel_ms": ms_kernel, "algorithmic_bytes": int(alg_bytes),
+                     "peak_source": peak_src,
+                     "scan_all_equivalent_gbs": (16 * N_ENTITIES + 8 * visible + N_ENTITIES / 8) / ms_kernel / 1e6},
+    }
+    if world == 1 and not a.only_cull:
+        try:
+            line["paths"] = secondary_paths(ctx, lb, scenes, peak, a.steps, a.warmup)
+            sk = line["paths"]["skin_100k_x5k"]
+            line["secondary"] = {"metric": "M skinned verts/s", "value": sk["value"], "unit": sk["unit"], "roofline_frac": sk["roofline"]["frac"]}
+        except Exception as e:  # the headline number stands on its own
+            line["paths_error"] = repr(e)
+        try:
+            cb = run_cpu_worker(["--workload", "cull", "--n", str(N_ENTITIES), "--scene", "c2", "--steps", "20", "--warmup", "2"])
+            line["cpu_baseline"] = {"value": cb["value"], "unit": "M entities/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+                                    "impl": cb["impl"], "median_ms": cb["median_s"] * 1e3, "visible": cb["visible"]}
+            assert cb["visible"] == visible, "CPU reference and GPU disagree on the visible count"
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "M entities/s", "cores": 0, "kind": "reference", "sample": "failed: " + repr(e)}
+    print(json.dumps(line))
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--only-cull", action="store_true", help="skip the secondary paths and the CPU baseline leg (profiling runs)")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        reference_arm(a, rank)
+    else:
+        ours(a, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,7 @@ compute object, a missing GPU raises NoDeviceError from Context().
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "liblumix_b200.so")
@@ -172,6 +173,10 @@ class Context:
         check(self.L.lb200_init(C.c_int(device), C.byref(h)), None)
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()  # objects that hold device memory of this context
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def synchronize(self):
         check(self.L.lb200_synchronize(self.h), self.h)
@@ -186,6 +191,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for child in list(self._children):
+                child.close()
             self.L.lb200_shutdown(self.h)
             self.h = None
 

@@ -231,6 +231,7 @@ class AnimationSystem:
         check(self.L.lb200_animation_create(ctx.h, C.byref(sk), arr, C.c_uint32(len(self.clips)), C.byref(m) if m is not None else None,
                                             C.c_uint32(max_instances), C.byref(h)), ctx.h)
         self.h = h
+        ctx._adopt(self)
         self.n = 0
 
     def close(self):

@@ -87,6 +87,8 @@ class CullingSystem:
         h = vp()
         check(self.L.lb200_culling_create(ctx.h if ctx else None, C.byref(h)), ctx.h if ctx else None)
         self.h = h
+        if ctx is not None:
+            ctx._adopt(self)
         self._out = None
         self._out_pinned = None
 

@@ -26,6 +26,7 @@ class Hierarchy:
         h = vp()
         check(self.L.lb200_hierarchy_create(ctx.h, ptr(p), C.c_uint32(self.n), C.byref(h)), ctx.h)
         self.h = h
+        ctx._adopt(self)
 
     def close(self):
         if self.h:

@@ -1,0 +1,138 @@
+"""TEST / BENCH INFRASTRUCTURE — times the reference's CPU path of the hot path on the host cores.
+
+Run as a subprocess (`python -m oracle.cpu_baseline ...`) by bench.py's cpu_baseline leg and by `bench.py --impl reference`;
+prints one JSON object and leaves with os._exit (the reference's static teardown is broken on Linux).
+
+  cull      : the reference's own CullingSystemImpl::cull on its own job_system (oracle/_ref, kind "reference"),
+              W = min(host cores, 64) workers (studio's cap, studio_app.cpp:583); falls back to the serial C restatement
+              (kind "port") if oracle/_ref is absent.
+  propagate : serial DFS restatement of World::transformEntity (the reference is serial) — kind "port".
+  pose/skin : restatement of updateAnimable / evaluateSkin, serial — kind "port".
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def bench_cull(n, steps, warmup, workers, scene_name):
+    from lumixengine_b200 import scenes  # numpy scene generators only (inputs, not the product's compute path)
+    from oracle import pyoracle as po
+    po.build()
+    scene = scenes.c2_scene(n) if scene_name == "c2" else scenes.c1_scene(n)
+    fa = scenes.c2_frustum_args() if scene_name == "c2" else scenes.c1_frustum_args()
+    f = po.frustum_perspective(fa["position"], fa["direction"], fa["up"], fa["fov"], fa["ratio"], fa["near"], fa["far"])
+    out = {}
+    if po.ref_available():
+        cores = _cores()
+        w = max(1, min(cores, 64)) if workers <= 0 else workers
+        rc = po.RefCulling(workers=w)
+        t0 = time.time()
+        rc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+        build_s = time.time() - t0
+        if warmup:
+            rc.cull(f, cap=0, iters=warmup)
+        times = []
+        count = 0
+        for _ in range(steps):
+            _, _, info = rc.cull(f, cap=0, iters=1)
+            times.append(info["best_s"])
+            count = info["count"]
+        out.update(kind="reference", cores=rc.workers, impl="CullingSystemImpl::cull on jobs:: (oracle/_ref overlay build)")
+    else:
+        oc = po.OracleCulling()
+        t0 = time.time()
+        oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+        build_s = time.time() - t0
+        times = []
+        count = 0
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            _, _, st = oc.cull(f, want_ids=False)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            count = st["visible"]
+        out.update(kind="port", cores=1, impl="serial C restatement (oracle/oracle_cull.c)")
+    times = np.array(times)
+    out.update(n=n, visible=int(count), build_s=build_s, total_s=float(times.sum()), median_s=float(np.median(times)), best_s=float(times.min()),
+               steps=steps, value=float(n / np.median(times) / 1e6), unit="M entities culled/s",
+               sample=f"{steps} x cull() of the full {n}-entity {scene_name.upper()} scene, result freed each call")
+    return out
+
+
+def bench_propagate(n, steps):
+    from lumixengine_b200 import scenes
+    from oracle import pyoracle as po
+    po.build()
+    parents, locals_, roots = scenes.hierarchy_forest(n, 8, 7, seed=3)
+    lb = np.ascontiguousarray(locals_).view(np.uint8).reshape(len(parents), 56)
+    gb = np.ascontiguousarray(roots).view(np.uint8).reshape(len(parents), 56)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        po.propagate(parents, lb, gb)
+        times.append(time.perf_counter() - t0)
+    m = float(np.median(times))
+    return dict(kind="port", cores=1, n=len(parents), median_s=m, value=len(parents) / m / 1e6, unit="M nodes/s",
+                sample=f"{steps} x serial DFS over {len(parents)} nodes (depth 8), includes the 56 MB globals copy")
+
+
+def bench_anim(n_inst, n_verts, skin_instances):
+    from lumixengine_b200 import scenes
+    from oracle import pyoracle as po
+    po.build()
+    sk = scenes.skeleton(64)
+    clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
+    mesh = scenes.mesh(sk, n_verts)
+    ci, tt = scenes.instance_times(n_inst, clips)
+    t0 = time.perf_counter()
+    out = po.animate_instances(sk, clips, ci, tt, want=("dq", "mtx"))
+    pose_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(skin_instances):
+        po.skin_vertices(out["mtx"][i], mesh.positions, mesh.weights, mesh.indices)
+    skin_s = time.perf_counter() - t0
+    return dict(kind="port", cores=1,
+                pose=dict(value=n_inst * 64 / pose_s / 1e6, unit="M bone-instances/s", sample=f"{n_inst} instances x 64 bones, DQ + matrix palettes, serial"),
+                skin=dict(value=skin_instances * n_verts / skin_s / 1e6, unit="M skinned verts/s", sample=f"{skin_instances} instances x {n_verts} verts, serial"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cull")
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--scene", default="c2")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--workers", type=int, default=0)
+    a = ap.parse_args()
+    if a.workload == "cull":
+        res = bench_cull(a.n, a.steps, a.warmup, a.workers, a.scene)
+    elif a.workload == "propagate":
+        res = bench_propagate(a.n, a.steps)
+    elif a.workload == "anim":
+        res = bench_anim(a.n, 5000, 200)
+    else:
+        raise SystemExit("unknown workload")
+    sys.stdout.write("CPU_BASELINE_JSON " + json.dumps(res) + "\n")
+    sys.stdout.flush()
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()
