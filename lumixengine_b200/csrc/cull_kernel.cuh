@@ -1,0 +1,270 @@
+// cull_pages_kernel — CullingSystemImpl::cullInternal + doCulling (src/renderer/culling_system.cpp:260-369) on the GPU.
+//
+// One block owns a chunk of consecutive cell pages and runs four phases:
+//   A. classify   one THREAD per page: coalesced read of the 32-byte descriptors, the cell tests of
+//                 culling_system.cpp:342-363 (is_big -> test; containsAABB(origin + cs, cs) -> copy all ids;
+//                 intersectsAABB(origin - cs, 2cs) -> test; else nothing) with ShiftedFrustum::containsAABB /
+//                 intersectsAABB arithmetic (geometry.cpp:99-118,159-178); pages with work go to a block-local list.
+//   B. test       one WARP per listed page: plane offsets re-based to the cell origin (ShiftedFrustum::getRelative,
+//                 geometry.cpp:121-149 — only d changes), <=200 spheres streamed with 128-bit loads, 6 distinct planes
+//                 (EXTRA0/1 duplicate NEAR, geometry.cpp:134-136) in the reference's op order, sign-bit test
+//                 (culling_system.cpp:284-295, simd.h:119); ballots kept in shared memory, per-type counts by shared atomics.
+//   C. claim      one global atomic per (block, renderable type) reserves the block's output range.
+//   D. write      one warp per listed page: visible ids gathered (4 B) and written compacted, grouped by type.
+// Two block barriers per chunk, no per-page global atomics, every warp in B/D has real work (skipped pages never reach a warp).
+// HBM-bound: 32 B descriptor per page + 16 B per tested sphere + 4 B read + 4 B write per visible id (+ 32 B mask per page).
+#pragma once
+
+#include "lb200_internal.h"
+#include "lb200_math.cuh"
+
+namespace lbcull {
+
+using namespace lb;
+
+constexpr int CULL_THREADS = 512;
+constexpr int CULL_WARPS = CULL_THREADS / 32;
+constexpr int MAX_CHUNK = CULL_THREADS; // pages per block per round (one classify thread each)
+constexpr int ROWS = 7;                 // ceil(200 / 32)
+constexpr int N_STATS = 8;
+enum { ST_PAGES_TESTED = 0, ST_PAGES_INSIDE, ST_PAGES_OUTSIDE, ST_PAGES_FILTERED, ST_ENT_TESTED, ST_ENT_INSIDE };
+constexpr int COUNTER_WORDS = 256 + N_STATS;
+static_assert(CULL_THREADS >= 256, "one thread per renderable type in the claim phase");
+
+struct CullParams {
+	// planes NEAR, FAR, LEFT, RIGHT, TOP, BOTTOM of the ShiftedFrustum (relative to `origin`)
+	float nx[6], ny[6], nz[6], d[6];
+	// the frustum point each plane is re-anchored on by getRelative (geometry.cpp:134-142): points[0,4,1,0,0,2]
+	float px[6], py[6], pz[6];
+	double ox, oy, oz;
+	uint32_t n_pages;
+	uint32_t type_filter; // 0xff = all
+	uint32_t chunk;       // pages per block per round, <= MAX_CHUNK
+	uint32_t type_base[256];
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+	float4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ int ldg_stream_i32(const int* p) {
+	int r;
+	asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+
+enum { CLS_SKIP = 0, CLS_COPY = 1, CLS_TEST = 2 };
+
+struct WorkItem {
+	double ox, oy, oz; // cell origin
+	uint32_t page;
+	uint32_t meta;     // count | type << 8 | cls << 16   (count <= 200 fits 8 bits)
+};
+static_assert(sizeof(WorkItem) == 32, "");
+
+__global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __grid_constant__ CullParams P,
+	const lb200_page_desc* __restrict__ desc, const float4* __restrict__ spheres, const int* __restrict__ entities,
+	uint32_t* __restrict__ out_ids, uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters, uint32_t* __restrict__ mask_out)
+{
+	__shared__ WorkItem s_item[MAX_CHUNK];
+	__shared__ uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // [ROWS] = offset of the page inside the block's range of its type
+	__shared__ uint32_t s_cnt[256];
+	__shared__ uint32_t s_base[256];
+	__shared__ uint32_t s_stats[N_STATS];
+	__shared__ uint32_t s_nwork;
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int warp = tid >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+
+	if (tid < 256) s_cnt[tid] = 0;
+	if (tid < N_STATS) s_stats[tid] = 0;
+	if (tid == 0) s_nwork = 0;
+	__syncthreads();
+
+	for (uint32_t chunk_idx = blockIdx.x; chunk_idx * P.chunk < P.n_pages; chunk_idx += gridDim.x) {
+		// ---------------- A. classify: one thread per page ----------------
+		if ((uint32_t)tid < P.chunk) {
+			const uint32_t page = chunk_idx * P.chunk + tid;
+			if (page < P.n_pages) {
+				const int4* dp = reinterpret_cast<const int4*>(desc + page);
+				const int4 a = __ldg(dp);
+				const int4 b = __ldg(dp + 1);
+				const double org_x = __hiloint2double(a.y, a.x);
+				const double org_y = __hiloint2double(a.w, a.z);
+				const double org_z = __hiloint2double(b.y, b.x);
+				const uint32_t count = (uint32_t)b.z;
+				const uint32_t type = (uint32_t)b.w & 0xffu;
+				const bool is_big = (((uint32_t)b.w >> 8) & 0xffu) != 0;
+				int cls = CLS_SKIP;
+				if (count != 0) {
+					if (P.type_filter == 0xffu || type == P.type_filter) {
+						// containsAABB(cell.origin + Vec3(cs), Vec3(cs)), geometry.cpp:99-118 (DVec3 + Vec3: math.cpp:512)
+						const float cs = LB200_CELL_SIZE;
+						const V3 rel_c = tofloat(sub(d3(LB_DADD(org_x, (double)cs), LB_DADD(org_y, (double)cs), LB_DADD(org_z, (double)cs)), d3(P.ox, P.oy, P.oz)));
+						const V3 max_c = add(rel_c, v3(cs, cs, cs));
+						// intersectsAABB(cell.origin - Vec3(cs), Vec3(2cs)), geometry.cpp:159-178 (DVec3 - Vec3: math.cpp:510)
+						const float cs2 = 2 * LB200_CELL_SIZE;
+						const V3 rel_i = tofloat(sub(d3(LB_DSUB(org_x, (double)cs), LB_DSUB(org_y, (double)cs), LB_DSUB(org_z, (double)cs)), d3(P.ox, P.oy, P.oz)));
+						const V3 max_i = add(rel_i, v3(cs2, cs2, cs2));
+						bool contains = true, intersects = true;
+#pragma unroll
+						for (int p = 0; p < 6; ++p) {
+							const float nx = P.nx[p], ny = P.ny[p], nz = P.nz[p], nd = -P.d[p];
+							const float cbx = nx < 0.0f ? max_c.x : rel_c.x;
+							const float cby = ny < 0.0f ? max_c.y : rel_c.y;
+							const float cbz = nz < 0.0f ? max_c.z : rel_c.z;
+							const float dp_c = LB_FADD(LB_FADD(LB_FMUL(nx, cbx), LB_FMUL(ny, cby)), LB_FMUL(nz, cbz));
+							if (dp_c < nd) contains = false;
+							const float ibx = nx > 0.0f ? max_i.x : rel_i.x;
+							const float iby = ny > 0.0f ? max_i.y : rel_i.y;
+							const float ibz = nz > 0.0f ? max_i.z : rel_i.z;
+							const float dp_i = LB_FADD(LB_FADD(LB_FMUL(nx, ibx), LB_FMUL(ny, iby)), LB_FMUL(nz, ibz));
+							if (dp_i < nd) intersects = false;
+						}
+						// culling_system.cpp:342-363
+						if (is_big) cls = CLS_TEST;
+						else if (contains) cls = CLS_COPY;
+						else if (intersects) cls = CLS_TEST;
+						else atomicAdd(&s_stats[ST_PAGES_OUTSIDE], 1u);
+					}
+					else atomicAdd(&s_stats[ST_PAGES_FILTERED], 1u);
+				}
+				if (cls != CLS_SKIP) {
+					const uint32_t slot = atomicAdd(&s_nwork, 1u);
+					WorkItem it;
+					it.ox = org_x; it.oy = org_y; it.oz = org_z;
+					it.page = page;
+					it.meta = count | (type << 8) | ((uint32_t)cls << 16);
+					s_item[slot] = it;
+				}
+				else if (mask_out) {
+					uint4* m = reinterpret_cast<uint4*>(mask_out + (size_t)page * 8);
+					m[0] = make_uint4(0u, 0u, 0u, 0u);
+					m[1] = make_uint4(0u, 0u, 0u, 0u);
+				}
+			}
+		}
+		__syncthreads();
+		const uint32_t n_work = s_nwork;
+
+		// ---------------- B. test / copy: one warp per listed page ----------------
+		for (uint32_t w = warp; w < n_work; w += CULL_WARPS) {
+			const WorkItem it = s_item[w];
+			const uint32_t count = it.meta & 0xffu;
+			const uint32_t type = (it.meta >> 8) & 0xffu;
+			const int cls = (int)(it.meta >> 16);
+			uint32_t bal[ROWS];
+			uint32_t page_visible = 0;
+			if (cls == CLS_TEST) {
+				float4 s[ROWS];
+				const float4* sp = spheres + (size_t)it.page * LB200_PAGE_SLOTS;
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) {
+					const uint32_t slot = k * 32 + lane;
+					if (slot < count) s[k] = ldg_stream(sp + slot);
+				}
+				// ShiftedFrustum::getRelative(cell.origin), geometry.cpp:121-149: offset = Vec3(this->origin - origin);
+				// d = -dot(point + offset, normal) (setPlane, geometry.cpp:412-418); lane p < 6 computes plane p
+				const int pl = lane < 6 ? lane : 0;
+				const V3 offset = tofloat(sub(d3(P.ox, P.oy, P.oz), d3(it.ox, it.oy, it.oz)));
+				const V3 pnt = add(v3(P.px[pl], P.py[pl], P.pz[pl]), offset);
+				const float my_d = -dot(pnt, v3(P.nx[pl], P.ny[pl], P.nz[pl]));
+				float rd[6];
+#pragma unroll
+				for (int p = 0; p < 6; ++p) rd[p] = __shfl_sync(0xffffffffu, my_d, p);
+				// doCulling, culling_system.cpp:260-308
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) {
+					const uint32_t slot = k * 32 + lane;
+					bool visible = false;
+					if (slot < count) {
+						const float cx = s[k].x, cy = s[k].y, cz = s[k].z;
+						const float r = -s[k].w; // :282 f4Splat(-sphere->radius)
+						uint32_t sign_acc = 0;
+#pragma unroll
+						for (int p = 0; p < 6; ++p) {
+							// :284,291  t = cx*px + cy*py + cz*pz + pd ;  t = t - r ;  movemask = sign bits
+							float t = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(cx, P.nx[p]), LB_FMUL(cy, P.ny[p])), LB_FMUL(cz, P.nz[p])), rd[p]);
+							t = LB_FSUB(t, r);
+							sign_acc |= __float_as_uint(t);
+						}
+						visible = (sign_acc >> 31) == 0;
+					}
+					bal[k] = __ballot_sync(0xffffffffu, visible);
+					page_visible += __popc(bal[k]);
+				}
+				if (lane == 0) {
+					atomicAdd(&s_stats[ST_PAGES_TESTED], 1u);
+					atomicAdd(&s_stats[ST_ENT_TESTED], count);
+				}
+			}
+			else { // CLS_COPY, culling_system.cpp:345-360: every entity of the page is visible
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) {
+					const int rem = (int)count - k * 32;
+					bal[k] = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+				}
+				page_visible = count;
+				if (lane == 0) {
+					atomicAdd(&s_stats[ST_PAGES_INSIDE], 1u);
+					atomicAdd(&s_stats[ST_ENT_INSIDE], count);
+				}
+			}
+			if (lane == 0) {
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) s_bal[w][k] = bal[k];
+				s_bal[w][ROWS] = page_visible ? atomicAdd(&s_cnt[type], page_visible) : 0u;
+				if (mask_out) {
+					uint4* m = reinterpret_cast<uint4*>(mask_out + (size_t)it.page * 8);
+					m[0] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
+					m[1] = make_uint4(bal[4], bal[5], bal[6], 0u);
+				}
+			}
+		}
+		__syncthreads();
+
+		// ---------------- C. claim: one global atomic per (block, type) ----------------
+		if (tid < 256) {
+			const uint32_t c = s_cnt[tid];
+			if (c) {
+				s_base[tid] = atomicAdd(&counters[tid], c);
+				s_cnt[tid] = 0;
+			}
+		}
+		if (tid == 0) s_nwork = 0;
+		__syncthreads();
+
+		// ---------------- D. write: gather the visible ids of each listed page ----------------
+		for (uint32_t w = warp; w < n_work; w += CULL_WARPS) {
+			const uint32_t page = s_item[w].page;
+			const uint32_t type = (s_item[w].meta >> 8) & 0xffu;
+			uint32_t bal[ROWS];
+#pragma unroll
+			for (int k = 0; k < ROWS; ++k) bal[k] = s_bal[w][k];
+			uint32_t* dst = out_ids + P.type_base[type] + s_base[type] + s_bal[w][ROWS];
+			const int* ep = entities + (size_t)page * LB200_PAGE_SLOTS;
+			int id[ROWS];
+#pragma unroll
+			for (int k = 0; k < ROWS; ++k) if ((bal[k] >> lane) & 1u) id[k] = ldg_stream_i32(ep + k * 32 + lane);
+			uint32_t prefix = 0;
+#pragma unroll
+			for (int k = 0; k < ROWS; ++k) {
+				if ((bal[k] >> lane) & 1u) dst[prefix + __popc(bal[k] & lt_mask)] = (uint32_t)id[k];
+				prefix += __popc(bal[k]);
+			}
+		}
+		__syncthreads(); // s_item / s_bal are reused by the next round
+	}
+
+	if (tid < N_STATS && s_stats[tid]) atomicAdd(&counters[256 + tid], s_stats[tid]);
+	// the other counter buffer is the next cull's: zero it now so no memset sits between two culls
+	if (blockIdx.x == 0) {
+		for (int i = tid; i < COUNTER_WORDS; i += CULL_THREADS) next_counters[i] = 0;
+	}
+}
+
+} // namespace lbcull

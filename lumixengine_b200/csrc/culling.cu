@@ -13,6 +13,7 @@
 //   5. write visible ids (grouped by type) and the per-page visibility bitmask.
 // HBM-bound: 16 B per tested sphere + 4 B read + 4 B write per visible id.  No tensor cores: there is no
 // contraction here.
+#include "cull_kernel.cuh"
 #include "culling_host.hpp"
 #include "lb200_math.cuh"
 
@@ -23,212 +24,7 @@ namespace {
 
 using namespace lb;
 
-constexpr int CULL_THREADS = 256;
-constexpr int WARPS_PER_BLOCK = CULL_THREADS / 32;
-constexpr int ROWS = 7; // ceil(200 / 32)
-constexpr int N_STATS = 8;
-enum { ST_PAGES_TESTED = 0, ST_PAGES_INSIDE, ST_PAGES_OUTSIDE, ST_PAGES_FILTERED, ST_ENT_TESTED, ST_ENT_INSIDE };
-constexpr int COUNTER_WORDS = 256 + N_STATS;
-static_assert(CULL_THREADS == 256, "one thread per renderable type in the output-claim step");
-
-struct CullParams {
-	// planes NEAR, FAR, LEFT, RIGHT, TOP, BOTTOM of the ShiftedFrustum (relative to `origin`)
-	float nx[6], ny[6], nz[6], d[6];
-	// the frustum point each plane is re-anchored on by getRelative (geometry.cpp:134-142): points[0,4,1,0,0,2]
-	float px[6], py[6], pz[6];
-	double ox, oy, oz;
-	uint32_t n_pages;
-	uint32_t type_filter; // 0xff = all
-	uint32_t type_base[256];
-};
-
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-	float4 r;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-	return r;
-}
-
-__device__ __forceinline__ int ldg_stream_i32(const int* p) {
-	int r;
-	asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
-	return r;
-}
-
-enum { CLS_SKIP = 0, CLS_COPY = 1, CLS_TEST = 2 };
-
-__global__ void __launch_bounds__(CULL_THREADS) cull_pages_kernel(const __grid_constant__ CullParams P,
-	const lb200_page_desc* __restrict__ desc, const float4* __restrict__ spheres, const int* __restrict__ entities,
-	uint32_t* __restrict__ out_ids, uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters, uint32_t* __restrict__ mask_out)
-{
-	__shared__ uint32_t s_cnt[256];
-	__shared__ uint32_t s_base[256];
-	__shared__ uint32_t s_stats[N_STATS];
-
-	const int lane = threadIdx.x & 31;
-	const int warp = threadIdx.x >> 5;
-	const uint32_t lt_mask = (1u << lane) - 1u;
-
-	s_cnt[threadIdx.x] = 0;
-	if (threadIdx.x < N_STATS) s_stats[threadIdx.x] = 0;
-	__syncthreads();
-
-	// plane handled by this lane during cell classification (lanes >= 6 repeat plane 0: harmless under __all_sync)
-	const int pl = lane < 6 ? lane : 0;
-	const float l_nx = P.nx[pl], l_ny = P.ny[pl], l_nz = P.nz[pl], l_d = P.d[pl];
-	const float l_px = P.px[pl], l_py = P.py[pl], l_pz = P.pz[pl];
-
-	for (uint32_t base = blockIdx.x * WARPS_PER_BLOCK; base < P.n_pages; base += gridDim.x * WARPS_PER_BLOCK) {
-		const uint32_t page = base + warp;
-		int cls = CLS_SKIP;
-		uint32_t count = 0, type = 0;
-		float rd[6];
-		float4 s[ROWS];
-		uint32_t bal[ROWS];
-		uint32_t page_visible = 0;
-
-		if (page < P.n_pages) {
-			// 32-byte descriptor: every lane reads the same two 16-byte words (one sector, broadcast)
-			const int4* dp = reinterpret_cast<const int4*>(desc + page);
-			const int4 a = __ldg(dp);
-			const int4 b = __ldg(dp + 1);
-			const double org_x = __hiloint2double(a.y, a.x);
-			const double org_y = __hiloint2double(a.w, a.z);
-			const double org_z = __hiloint2double(b.y, b.x);
-			count = (uint32_t)b.z;
-			type = (uint32_t)b.w & 0xffu;
-			const bool is_big = (((uint32_t)b.w >> 8) & 0xffu) != 0;
-
-			if (count != 0 && (P.type_filter == 0xffu || type == P.type_filter)) {
-				// --- culling_system.cpp:342-363 ---
-				// containsAABB(cell.origin + Vec3(cs), Vec3(cs)), geometry.cpp:99-118 (DVec3 + Vec3: math.cpp:512)
-				const float cs = LB200_CELL_SIZE;
-				const V3 rel_c = tofloat(sub(d3(LB_DADD(org_x, (double)cs), LB_DADD(org_y, (double)cs), LB_DADD(org_z, (double)cs)), d3(P.ox, P.oy, P.oz)));
-				const V3 max_c = add(rel_c, v3(cs, cs, cs));
-				const float cbx = l_nx < 0.0f ? max_c.x : rel_c.x;
-				const float cby = l_ny < 0.0f ? max_c.y : rel_c.y;
-				const float cbz = l_nz < 0.0f ? max_c.z : rel_c.z;
-				const float dp_c = LB_FADD(LB_FADD(LB_FMUL(l_nx, cbx), LB_FMUL(l_ny, cby)), LB_FMUL(l_nz, cbz));
-				const bool fail_c = dp_c < -l_d;
-				// intersectsAABB(cell.origin - Vec3(cs), Vec3(2cs)), geometry.cpp:159-178 (DVec3 - Vec3: math.cpp:510)
-				const float cs2 = 2 * LB200_CELL_SIZE;
-				const V3 rel_i = tofloat(sub(d3(LB_DSUB(org_x, (double)cs), LB_DSUB(org_y, (double)cs), LB_DSUB(org_z, (double)cs)), d3(P.ox, P.oy, P.oz)));
-				const V3 max_i = add(rel_i, v3(cs2, cs2, cs2));
-				const float ibx = l_nx > 0.0f ? max_i.x : rel_i.x;
-				const float iby = l_ny > 0.0f ? max_i.y : rel_i.y;
-				const float ibz = l_nz > 0.0f ? max_i.z : rel_i.z;
-				const float dp_i = LB_FADD(LB_FADD(LB_FMUL(l_nx, ibx), LB_FMUL(l_ny, iby)), LB_FMUL(l_nz, ibz));
-				const bool fail_i = dp_i < -l_d;
-				const bool contains = __all_sync(0xffffffffu, !fail_c);
-				const bool intersects = __all_sync(0xffffffffu, !fail_i);
-				if (is_big) cls = CLS_TEST;
-				else if (contains) cls = CLS_COPY;
-				else if (intersects) cls = CLS_TEST;
-				else if (lane == 0) atomicAdd(&s_stats[ST_PAGES_OUTSIDE], 1u);
-			}
-			else if (count != 0 && lane == 0) atomicAdd(&s_stats[ST_PAGES_FILTERED], 1u);
-
-			if (cls == CLS_TEST) {
-				// issue the sphere loads first: everything below until the first use overlaps their latency
-				const float4* sp = spheres + (size_t)page * PAGE_SLOTS;
-#pragma unroll
-				for (int k = 0; k < ROWS; ++k) {
-					const uint32_t slot = k * 32 + lane;
-					if (slot < count) s[k] = ldg_stream(sp + slot);
-				}
-				// ShiftedFrustum::getRelative(cell.origin), geometry.cpp:121-149: offset = Vec3(this->origin - origin);
-				// d = -dot(point + offset, normal) (setPlane, geometry.cpp:412-418)
-				const V3 offset = tofloat(sub(d3(P.ox, P.oy, P.oz), d3(org_x, org_y, org_z)));
-				const V3 pnt = add(v3(l_px, l_py, l_pz), offset);
-				const float my_d = -dot(pnt, v3(l_nx, l_ny, l_nz));
-#pragma unroll
-				for (int p = 0; p < 6; ++p) rd[p] = __shfl_sync(0xffffffffu, my_d, p);
-
-				// doCulling, culling_system.cpp:260-308
-#pragma unroll
-				for (int k = 0; k < ROWS; ++k) {
-					const uint32_t slot = k * 32 + lane;
-					bool visible = false;
-					if (slot < count) {
-						const float cx = s[k].x, cy = s[k].y, cz = s[k].z;
-						const float r = -s[k].w; // :282 f4Splat(-sphere->radius)
-						uint32_t sign_acc = 0;
-#pragma unroll
-						for (int p = 0; p < 6; ++p) {
-							// :284,291  t = cx*px + cy*py + cz*pz + pd ;  t = t - r ;  movemask = sign bits
-							float t = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(cx, P.nx[p]), LB_FMUL(cy, P.ny[p])), LB_FMUL(cz, P.nz[p])), rd[p]);
-							t = LB_FSUB(t, r);
-							sign_acc |= __float_as_uint(t);
-						}
-						visible = (sign_acc >> 31) == 0;
-					}
-					bal[k] = __ballot_sync(0xffffffffu, visible);
-					page_visible += __popc(bal[k]);
-				}
-				if (lane == 0) {
-					atomicAdd(&s_stats[ST_PAGES_TESTED], 1u);
-					atomicAdd(&s_stats[ST_ENT_TESTED], count);
-				}
-			}
-			else if (cls == CLS_COPY) {
-				// :345-360 every entity of the page is visible
-#pragma unroll
-				for (int k = 0; k < ROWS; ++k) {
-					const int rem = (int)count - k * 32;
-					bal[k] = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
-				}
-				page_visible = count;
-				if (lane == 0) {
-					atomicAdd(&s_stats[ST_PAGES_INSIDE], 1u);
-					atomicAdd(&s_stats[ST_ENT_INSIDE], count);
-				}
-			}
-			else {
-#pragma unroll
-				for (int k = 0; k < ROWS; ++k) bal[k] = 0;
-			}
-
-			if (mask_out && lane == 0) {
-				uint4* m = reinterpret_cast<uint4*>(mask_out + (size_t)page * 8);
-				m[0] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
-				m[1] = make_uint4(bal[4], bal[5], bal[6], 0u);
-			}
-		}
-
-		// claim output space: per-page offset inside the block (shared atomics), one global atomic per (block, type)
-		uint32_t my_off = 0;
-		if (lane == 0 && page_visible) my_off = atomicAdd(&s_cnt[type], page_visible);
-		__syncthreads();
-		{
-			const uint32_t c = s_cnt[threadIdx.x];
-			if (c) {
-				s_base[threadIdx.x] = atomicAdd(&counters[threadIdx.x], c);
-				s_cnt[threadIdx.x] = 0;
-			}
-		}
-		__syncthreads();
-		if (page_visible) {
-			my_off = __shfl_sync(0xffffffffu, my_off, 0);
-			uint32_t* dst = out_ids + P.type_base[type] + s_base[type] + my_off;
-			const int* ep = entities + (size_t)page * PAGE_SLOTS;
-			uint32_t prefix = 0;
-#pragma unroll
-			for (int k = 0; k < ROWS; ++k) {
-				if ((bal[k] >> lane) & 1u) {
-					const int id = ldg_stream_i32(ep + k * 32 + lane);
-					dst[prefix + __popc(bal[k] & lt_mask)] = (uint32_t)id;
-				}
-				prefix += __popc(bal[k]);
-			}
-		}
-	}
-
-	__syncthreads();
-	if (threadIdx.x < N_STATS && s_stats[threadIdx.x]) atomicAdd(&counters[256 + threadIdx.x], s_stats[threadIdx.x]);
-	// the other counter buffer is the next cull's: zero it now so no memset sits between two culls
-	if (blockIdx.x == 0) {
-		for (int i = threadIdx.x; i < COUNTER_WORDS; i += CULL_THREADS) next_counters[i] = 0;
-	}
-}
+using namespace lbcull;
 
 // scatter packed dirty pages from a staging buffer into the page arrays (one block per page)
 __global__ void __launch_bounds__(256) scatter_pages_kernel(const uint32_t* __restrict__ page_idx, const lb200_page_desc* __restrict__ st_desc,
@@ -426,7 +222,11 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type) 
 	const size_t off = (size_t)r * cs->dev_cap;
 	uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
 	uint32_t* nxt = cs->d_counters + (size_t)(cs->parity ^ 1) * COUNTER_WORDS;
-	const unsigned blocks = (unsigned)std::max(1, std::min(cs->grid, (int)((h.high_water + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK)));
+	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
+	uint32_t chunk = (h.high_water + cs->grid - 1) / cs->grid;
+	chunk = std::max(32u, std::min((uint32_t)MAX_CHUNK, chunk));
+	P.chunk = chunk;
+	const unsigned blocks = (unsigned)std::max(1u, std::min((uint32_t)cs->grid, (h.high_water + chunk - 1) / chunk));
 	cull_pages_kernel<<<blocks, CULL_THREADS, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
 		cs->d_out_ids, cur, nxt, cs->d_mask);
 	LB200_CHECK_LAUNCH(ctx);

@@ -4,8 +4,8 @@
 # dir that is deleted afterwards).  Does not run the reference's build system (GENie/MSBuild).
 #
 #   unmodified : src/core/{math,geometry,string,hash,log,stream,page_allocator,default_allocator,
-#                arena_allocator}.cpp, src/core/linux/{thread,atomic,fibers}.cpp,
-#                src/renderer/culling_system.cpp
+#                arena_allocator,path}.cpp, src/core/linux/{thread,atomic,fibers}.cpp, src/engine/resource.cpp,
+#                src/renderer/{culling_system,pose}.cpp, src/animation/animation.cpp
 #   overlay    : SURVEY.md §8(c) — src/core/sync.h (SRWLock body), src/core/linux/sync.cpp (stale
 #                Semaphore::signal signature + SRWLock methods), src/core/simd.h (take the SSE branch
 #                on GCC), src/core/job_system.cpp (noinline on getWorker(): the reference's TLS guard
@@ -34,6 +34,7 @@ cp -r "$REF/src/renderer/gpu" "$S/renderer/"
 cp "$REF/src/renderer/culling_system.cpp" "$REF/src/renderer/pose.cpp" "$S/renderer/"
 cp "$REF"/src/animation/*.h "$S/animation/"
 cp "$REF/src/animation/animation.cpp" "$S/animation/"
+cp "$REF/src/engine/resource.cpp" "$S/engine/"
 
 # (1) sync.h: SRWLock has no Linux body
 sed -i 's|#error "Not implemented"|pthread_rwlock_t lock;|' "$S/core/sync.h"
@@ -79,7 +80,7 @@ CXX=${LUMIX_REF_CXX:-/usr/bin/g++} # not $CXX: a wrapper there may link libstdc+
 FL="-std=c++20 -O2 -DSTATIC_PLUGINS -DNDEBUG -fno-exceptions -fno-rtti -msse2 -msse3 -ffp-contract=off -fPIC -w -fvisibility=hidden -I$S -I$REF/external"
 SRCS="renderer/culling_system core/job_system core/page_allocator core/default_allocator core/arena_allocator
       core/linux/thread core/linux/sync core/linux/atomic core/linux/fibers core/math core/geometry core/string
-      core/hash core/log core/stream"
+      core/hash core/log core/stream core/path engine/resource renderer/pose animation/animation"
 OBJS=""
 for f in $SRCS; do
 	o="$TMP/obj/$(echo "$f" | tr / _).o"
@@ -88,7 +89,8 @@ for f in $SRCS; do
 done
 $CXX $FL -c "$HERE/ref/ref_stubs.cpp" -o "$TMP/obj/ref_stubs.o" &
 $CXX $FL -c "$HERE/ref/ref_harness.cpp" -o "$TMP/obj/ref_harness.o" &
+$CXX $FL -c "$HERE/ref/ref_anim_harness.cpp" -o "$TMP/obj/ref_anim_harness.o" &
 wait
-$CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL
+$CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" "$TMP/obj/ref_anim_harness.o" -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL
 ( cd "$REF" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$OUT/REFERENCE_COMMIT"
 echo "built $OUT/libref_lumix.so"

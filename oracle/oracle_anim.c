@@ -191,3 +191,22 @@ void oracle_animate_instances(const OracleSkeleton* sk, const OracleClip* clips,
 		if (out_mtx) oracle_palette_matrices(sk, pos, rot, out_mtx + (size_t)i * B);
 	}
 }
+
+/* ---- element-wise shims over oracle_math.h so that tests can pin each primitive against the reference build ---- */
+void oracle_transform_compose(const OTransform* a, const OTransform* b, OTransform* out, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) out[i] = otransform_compose(&a[i], &b[i]);
+}
+void oracle_quat_mul(const OQuat* a, const OQuat* b, OQuat* out, uint32_t n) { for (uint32_t i = 0; i < n; ++i) out[i] = oquat_mul(a[i], b[i]); }
+void oracle_quat_rotate(const OQuat* q, const OVec3* v, OVec3* out, uint32_t n) { for (uint32_t i = 0; i < n; ++i) out[i] = oquat_rotate(q[i], v[i]); }
+void oracle_nlerp(const OQuat* a, const OQuat* b, const float* t, OQuat* out, uint32_t n, int simd) {
+	for (uint32_t i = 0; i < n; ++i) out[i] = simd ? oquat_simd_nlerp(a[i], b[i], t[i]) : oquat_nlerp(a[i], b[i], t[i]);
+}
+void oracle_lerp_vec3(const OVec3* a, const OVec3* b, const float* t, OVec3* out, uint32_t n) { for (uint32_t i = 0; i < n; ++i) out[i] = ov3_lerp(a[i], b[i], t[i]); }
+void oracle_lrt_mul(const OLocalRigidTransform* a, const OLocalRigidTransform* b, OLocalRigidTransform* out, uint32_t n) { for (uint32_t i = 0; i < n; ++i) out[i] = olrt_mul(a[i], b[i]); }
+void oracle_lrt_inverted(const OLocalRigidTransform* a, OLocalRigidTransform* out, uint32_t n) { for (uint32_t i = 0; i < n; ++i) out[i] = olrt_inverted(a[i]); }
+void oracle_lrt_to_dual_quat(const OLocalRigidTransform* a, ODualQuat* out, uint32_t n) { for (uint32_t i = 0; i < n; ++i) out[i] = olrt_to_dual_quat(a[i]); }
+void oracle_lrt_to_matrix(const OLocalRigidTransform* a, OMatrix* out, uint32_t n) { for (uint32_t i = 0; i < n; ++i) out[i] = olrt_to_matrix(a[i]); }
+void oracle_cell_indices(const double* pos, float cell_size, int* out3) {
+	const OIVec3 i = oiv3_from_d(odv3_muls(odv3(pos[0], pos[1], pos[2]), 1 / cell_size));
+	out3[0] = i.x; out3[1] = i.y; out3[2] = i.z;
+}

@@ -328,3 +328,69 @@ def skin_vertices(matrices, positions, weights, indices):
 
 def time_advance(time_ticks, time_delta, fps, frame_count):
     return int(lib().oracle_time_advance(C.c_uint32(int(time_ticks)), C.c_float(time_delta), C.c_float(fps), C.c_uint32(frame_count)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# element-wise pins: the same call on the restatement (oracle_math.h via small C shims) and on the reference build
+# ---------------------------------------------------------------------------------------------------
+class RefClip(C.Structure):
+    _fields_ = Clip._fields_
+
+
+class RefSkeleton(C.Structure):
+    _fields_ = [("bone_count", C.c_uint32), ("first_nonroot", C.c_int32), ("parents", vp), ("bind_relative7", vp), ("inverse_bind7", vp)]
+
+
+def _skeleton_struct(skeleton, cls):
+    s = cls()
+    s.bone_count = skeleton.bone_count
+    if cls is RefSkeleton:
+        s.first_nonroot = skeleton.first_nonroot_bone_index
+        s.bind_relative7 = skeleton.bind_relative7.ctypes.data
+        s.inverse_bind7 = skeleton.inverse_bind7.ctypes.data
+    else:
+        s.first_nonroot_bone_index = skeleton.first_nonroot_bone_index
+        s.bind_relative = skeleton.bind_relative7.ctypes.data
+        s.inverse_bind = skeleton.inverse_bind7.ctypes.data
+    s.parents = skeleton.parents.ctypes.data
+    return s
+
+
+def ref_pose_evaluate(skeleton, clip, time_ticks, weight=1.0, start_from_bind=True, compute_absolute=True, pos=None, rot=None):
+    """The reference's own Animation::getRelativePose (+ Pose::computeAbsolute) on one instance."""
+    sk = _skeleton_struct(skeleton, RefSkeleton)
+    c = clip.as_struct(RefClip)
+    B = skeleton.bone_count
+    p = np.zeros((B, 3), np.float32) if pos is None else np.array(pos, np.float32, copy=True)
+    r = np.zeros((B, 4), np.float32) if rot is None else np.array(rot, np.float32, copy=True)
+    ref().ref_pose_evaluate(C.byref(sk), C.byref(c), C.c_uint32(int(time_ticks)), C.c_float(weight), C.c_int(1 if start_from_bind else 0),
+                            C.c_int(1 if compute_absolute else 0), _ptr(p), _ptr(r))
+    return p, r
+
+
+def pose_evaluate(skeleton, clip, time_ticks, weight=1.0, start_from_bind=True, compute_absolute=True, pos=None, rot=None):
+    """Same call on the restatement (oracle_anim.c)."""
+    sk = _skeleton_struct(skeleton, Skeleton)
+    c = clip.as_struct(Clip)
+    B = skeleton.bone_count
+    if start_from_bind:
+        p = np.ascontiguousarray(skeleton.bind_relative7[:, :3], np.float32).copy()
+        r = np.ascontiguousarray(skeleton.bind_relative7[:, 3:], np.float32).copy()
+    else:
+        p = np.array(pos, np.float32, copy=True)
+        r = np.array(rot, np.float32, copy=True)
+    lib().oracle_pose_sample_weighted(C.byref(c), C.c_uint32(B), C.c_uint32(int(time_ticks)), C.c_float(weight), _ptr(p), _ptr(r))
+    if compute_absolute:
+        lib().oracle_pose_compute_absolute(C.byref(sk), _ptr(p), _ptr(r))
+    return p, r
+
+
+def palettes(skeleton, pos, rot):
+    sk = _skeleton_struct(skeleton, Skeleton)
+    p = np.ascontiguousarray(pos, np.float32)
+    r = np.ascontiguousarray(rot, np.float32)
+    dq = np.empty((skeleton.bone_count, 8), np.float32)
+    mtx = np.empty((skeleton.bone_count, 16), np.float32)
+    lib().oracle_palette_dual_quats(C.byref(sk), _ptr(p), _ptr(r), _ptr(dq))
+    lib().oracle_palette_matrices(C.byref(sk), _ptr(p), _ptr(r), _ptr(mtx))
+    return dq, mtx

@@ -1,0 +1,152 @@
+// TEST INFRASTRUCTURE — not product code.  Runs the REFERENCE'S OWN Animation::getRelativePose
+// (src/animation/animation.cpp:117-204,294-311) and Pose::computeAbsolute (src/renderer/pose.cpp:66-133) on
+// caller-supplied clip / skeleton data, to pin oracle/oracle_anim.c.
+//
+// Animation and Model are engine Resources that cannot be constructed without the whole engine, so this file reaches
+// their data members through `#define private public` and fills zero-initialised storage by hand; only the member
+// functions under test run (they read data members only).  No reference source is copied.
+#define private public
+#define protected public
+#include "animation/animation.h"
+#include "renderer/model.h"
+#include "renderer/pose.h"
+#undef private
+#undef protected
+#include "core/default_allocator.h"
+#include "engine/resource_manager.h"
+
+#include <new>
+#include <stdint.h>
+#include <string.h>
+
+using namespace Lumix;
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+// link-time stubs for the three symbols resource.cpp / animation.cpp reference but this harness never reaches
+namespace Lumix {
+ResourceManagerHub::LoadHook::Action ResourceManagerHub::onBeforeLoad(Resource&) const { return LoadHook::Action::IMMEDIATE; }
+Resource* ResourceManagerHub::load(ResourceType, const Path&) { return nullptr; }
+const ResourceType Model::TYPE("model");
+}
+
+struct RefTrack { // same layout as OracleTrack / lb200_track
+	uint16_t bone_index, offset_bits;
+	uint8_t bitsizes[3];
+	uint8_t skipped_channel;
+	float min[3], to_range[3];
+};
+struct RefConstT { uint16_t bone_index, pad; float value[3]; };
+struct RefConstR { uint16_t bone_index, pad; float value[4]; };
+struct RefClip {
+	float fps;
+	uint32_t frame_count, t_bits, r_bits, n_t, n_ct, n_r, n_cr;
+	const RefTrack* t; const RefConstT* ct; const RefTrack* r; const RefConstR* cr;
+	const uint8_t* t_stream; const uint8_t* r_stream;
+};
+struct RefSkeleton {
+	uint32_t bone_count; int32_t first_nonroot;
+	const int16_t* parents; const float* bind_relative7; const float* inverse_bind7;
+};
+
+template <typename T> struct RawStorage {
+	RawStorage() { memset(mem, 0, sizeof(mem)); }
+	T* get() { return reinterpret_cast<T*>(mem); }
+	alignas(alignof(T)) unsigned char mem[sizeof(T)];
+};
+
+// pos: bone_count*3, rot: bone_count*4 (in: relative pose to blend onto when weight < 0.9999; out: result)
+REF_API void ref_pose_evaluate(const RefSkeleton* sk, const RefClip* clip, uint32_t time_ticks, float weight, int start_from_bind, int compute_absolute,
+	float* pos3, float* rot4)
+{
+	static DefaultAllocator allocator;
+	RawStorage<Model> model_mem;
+	Model* model = model_mem.get();
+	new (&model->m_parents) Array<i16>(allocator);
+	for (uint32_t i = 0; i < sk->bone_count; ++i) model->m_parents.push(sk->parents[i]);
+	model->m_first_nonroot_bone_index = sk->first_nonroot;
+
+	RawStorage<Animation> anim_mem;
+	Animation* anim = anim_mem.get();
+	new (&anim->m_translations) Array<Animation::TranslationTrack>(allocator);
+	new (&anim->m_const_translations) Array<Animation::ConstTranslationTrack>(allocator);
+	new (&anim->m_rotations) Array<Animation::RotationTrack>(allocator);
+	new (&anim->m_const_rotations) Array<Animation::ConstRotationTrack>(allocator);
+	for (uint32_t i = 0; i < clip->n_t; ++i) {
+		Animation::TranslationTrack& t = anim->m_translations.emplace();
+		t.bone_index = clip->t[i].bone_index;
+		t.min = Vec3(clip->t[i].min[0], clip->t[i].min[1], clip->t[i].min[2]);
+		t.to_range = Vec3(clip->t[i].to_range[0], clip->t[i].to_range[1], clip->t[i].to_range[2]);
+		t.offset_bits = clip->t[i].offset_bits;
+		memcpy(t.bitsizes, clip->t[i].bitsizes, 3);
+	}
+	for (uint32_t i = 0; i < clip->n_ct; ++i) {
+		Animation::ConstTranslationTrack& t = anim->m_const_translations.emplace();
+		t.bone_index = clip->ct[i].bone_index;
+		t.value = Vec3(clip->ct[i].value[0], clip->ct[i].value[1], clip->ct[i].value[2]);
+	}
+	for (uint32_t i = 0; i < clip->n_r; ++i) {
+		Animation::RotationTrack& t = anim->m_rotations.emplace();
+		t.bone_index = clip->r[i].bone_index;
+		t.min = Vec3(clip->r[i].min[0], clip->r[i].min[1], clip->r[i].min[2]);
+		t.to_range = Vec3(clip->r[i].to_range[0], clip->r[i].to_range[1], clip->r[i].to_range[2]);
+		t.offset_bits = clip->r[i].offset_bits;
+		memcpy(t.bitsizes, clip->r[i].bitsizes, 3);
+		t.skipped_channel = clip->r[i].skipped_channel;
+	}
+	for (uint32_t i = 0; i < clip->n_cr; ++i) {
+		Animation::ConstRotationTrack& t = anim->m_const_rotations.emplace();
+		t.bone_index = clip->cr[i].bone_index;
+		t.value = Quat(clip->cr[i].value[0], clip->cr[i].value[1], clip->cr[i].value[2], clip->cr[i].value[3]);
+	}
+	anim->m_translation_stream = clip->t_stream;
+	anim->m_rotation_stream = clip->r_stream;
+	anim->m_translations_frame_size_bits = clip->t_bits;
+	anim->m_rotations_frame_size_bits = clip->r_bits;
+	anim->m_frame_count = clip->frame_count;
+	anim->m_fps = clip->fps;
+	anim->m_max_accessed_bone_index = 0;
+	anim->m_root_motion.rotation_track_idx = -1;
+	anim->m_root_motion.translation_track_idx = -1;
+
+	{
+		Pose pose(allocator);
+		pose.resize((int)sk->bone_count);
+		for (uint32_t i = 0; i < sk->bone_count; ++i) {
+			if (start_from_bind) { // Model::getRelativePose, model.cpp:226-237
+				const float* b = sk->bind_relative7 + 7 * i;
+				pose.positions[i] = Vec3(b[0], b[1], b[2]);
+				pose.rotations[i] = Quat(b[3], b[4], b[5], b[6]);
+			}
+			else {
+				pose.positions[i] = Vec3(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2]);
+				pose.rotations[i] = Quat(rot4[4 * i], rot4[4 * i + 1], rot4[4 * i + 2], rot4[4 * i + 3]);
+			}
+		}
+		pose.is_absolute = false;
+		Animation::SampleContext ctx;
+		ctx.pose = &pose;
+		ctx.model = model;
+		ctx.time = Time(time_ticks);
+		ctx.weight = weight;
+		ctx.mask = nullptr;
+		anim->getRelativePose(ctx);
+		if (compute_absolute) pose.computeAbsolute(*model);
+		for (uint32_t i = 0; i < sk->bone_count; ++i) {
+			pos3[3 * i] = pose.positions[i].x; pos3[3 * i + 1] = pose.positions[i].y; pos3[3 * i + 2] = pose.positions[i].z;
+			rot4[4 * i] = pose.rotations[i].x; rot4[4 * i + 1] = pose.rotations[i].y; rot4[4 * i + 2] = pose.rotations[i].z; rot4[4 * i + 3] = pose.rotations[i].w;
+		}
+	}
+	anim->m_translations.~Array();
+	anim->m_const_translations.~Array();
+	anim->m_rotations.~Array();
+	anim->m_const_rotations.~Array();
+	model->m_parents.~Array();
+}
+
+REF_API uint32_t ref_clip_length_ticks(float fps, uint32_t frame_count) {
+	// Animation::getLength, animation.h:128
+	return Time::fromSeconds(frame_count / fps).raw();
+}
+
+REF_API uint32_t ref_time_from_seconds(float s) { return Time::fromSeconds(s).raw(); }

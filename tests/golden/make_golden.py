@@ -1,0 +1,171 @@
+"""Generates tests/golden/*.npz from the REFERENCE'S OWN compiled code (oracle/_ref/libref_lumix.so, built by
+oracle/build_ref.sh from /root/reference).  Run in the build container only:  python tests/golden/make_golden.py
+
+The reference has no golden vectors of its own for this path, so these reference-run outputs are the pin:
+inputs are seeded numpy draws, outputs come from unmodified math.cpp / geometry.cpp / culling_system.cpp / pose.cpp /
+animation.cpp.  tests/test_oracle_golden.py replays them against the restatement on any box.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from lumixengine_b200 import scenes  # noqa: E402  (numpy input generators)
+from oracle import pyoracle as po  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+
+def unit_quats(rng, n):
+    q = rng.normal(size=(n, 4)).astype(np.float32)
+    return (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+
+
+def math_kat():
+    L = po.ref()
+    rng = np.random.default_rng(1234)
+    n = 2000
+    tr_dtype = np.dtype({"names": ["pos", "rot", "scale"], "formats": [(np.float64, 3), (np.float32, 4), (np.float32, 3)], "offsets": [0, 24, 40], "itemsize": 56})
+    a = np.zeros(n, tr_dtype); b = np.zeros(n, tr_dtype)
+    for t, s in ((a, 1e5), (b, 50.0)):
+        t["pos"] = rng.normal(size=(n, 3)) * s
+        t["rot"] = unit_quats(rng, n)
+        t["scale"] = (0.5 + rng.random((n, 3))).astype(np.float32)
+    out = np.zeros(n, tr_dtype)
+    L.ref_transform_compose(P(a), P(b), P(out), C.c_uint32(n))
+    d = dict(tr_a=a.view(np.uint8).reshape(n, 56), tr_b=b.view(np.uint8).reshape(n, 56), compose=out.view(np.uint8).reshape(n, 56))
+    qa, qb = unit_quats(rng, n), unit_quats(rng, n)
+    qb[: n // 4] = -qa[: n // 4] + rng.normal(size=(n // 4, 4)).astype(np.float32) * 0.01  # negative-dot branch of nlerp
+    v = (rng.normal(size=(n, 3)) * 10).astype(np.float32)
+    v2 = (rng.normal(size=(n, 3)) * 10).astype(np.float32)
+    t = rng.random(n).astype(np.float32)
+    o4 = np.zeros((n, 4), np.float32); o3 = np.zeros((n, 3), np.float32)
+    L.ref_quat_mul(P(qa), P(qb), P(o4), C.c_uint32(n)); d.update(qa=qa, qb=qb, quat_mul=o4.copy())
+    L.ref_quat_rotate(P(qa), P(v), P(o3), C.c_uint32(n)); d.update(v=v, quat_rotate=o3.copy())
+    L.ref_nlerp(P(qa), P(qb), P(t), P(o4), C.c_uint32(n), C.c_int(0)); d.update(t=t, nlerp=o4.copy())
+    L.ref_nlerp(P(qa), P(qb), P(t), P(o4), C.c_uint32(n), C.c_int(1)); d.update(simd_nlerp=o4.copy())
+    L.ref_lerp_vec3(P(v), P(v2), P(t), P(o3), C.c_uint32(n)); d.update(v2=v2, lerp=o3.copy())
+    la = np.concatenate([v, qa], axis=1).astype(np.float32); lb_ = np.concatenate([v2, qb], axis=1).astype(np.float32)
+    o7 = np.zeros((n, 7), np.float32); o8 = np.zeros((n, 8), np.float32); o16 = np.zeros((n, 16), np.float32)
+    L.ref_lrt_mul(P(la), P(lb_), P(o7), C.c_uint32(n)); d.update(lrt_a=la, lrt_b=lb_, lrt_mul=o7.copy())
+    L.ref_lrt_inverted(P(la), P(o7), C.c_uint32(n)); d.update(lrt_inverted=o7.copy())
+    L.ref_lrt_to_dual_quat(P(la), P(o8), C.c_uint32(n)); d.update(lrt_to_dual_quat=o8.copy())
+    L.ref_lrt_to_matrix(P(la), P(o16), C.c_uint32(n)); d.update(lrt_to_matrix=o16.copy())
+    # skinning of n vertices against a 32-matrix palette
+    pal = np.zeros((32, 16), np.float32)
+    pl = np.concatenate([(rng.normal(size=(32, 3)) * 3).astype(np.float32), unit_quats(rng, 32)], axis=1).astype(np.float32)
+    L.ref_lrt_to_matrix(P(pl), P(pal), C.c_uint32(32))
+    w = rng.random((n, 4)); w = (np.round(w / w.sum(1, keepdims=True) * 65535) / 65535.0).astype(np.float32)
+    idx = rng.integers(0, 32, (n, 4)).astype(np.int16)
+    L.ref_skin_vertex(P(pal), P(v), P(w), P(idx), P(o3), C.c_uint32(n)); d.update(skin_palette=pal, skin_w=w, skin_idx=idx, skin_out=o3.copy())
+    # cell indices incl. negative coordinates and exact multiples of 300
+    cp = np.concatenate([rng.normal(size=(500, 3)) * 2000, (rng.integers(-8, 9, (200, 3)) * 300.0), (rng.integers(-8, 9, (200, 3)) * 300.0) - 1e-9])
+    ci = np.zeros((len(cp), 3), np.int32)
+    for i in range(len(cp)):
+        L.ref_cell_indices(P(cp[i]), C.c_float(300.0), P(ci[i]))
+    d.update(cell_pos=cp, cell_idx=ci)
+    # frustums: construction, getRelative, contains / intersects
+    fr_args, fr_out, rel_origin, rel_out, box_pos, box_size, box_c, box_i = [], [], [], [], [], [], [], []
+    for k in range(40):
+        pos = rng.normal(size=3) * (1000.0 if k % 2 else 1e6)
+        dirv = rng.normal(size=3); dirv /= np.linalg.norm(dirv)
+        up = np.cross(np.cross(dirv, rng.normal(size=3)), dirv); up /= np.linalg.norm(up)
+        fov, ratio, near, far = 0.3 + rng.random() * 1.5, 0.5 + rng.random() * 2, 0.05 + rng.random(), 100 + rng.random() * 5000
+        f = po.ref_frustum_perspective(pos, dirv.astype(np.float32), up.astype(np.float32), fov, ratio, near, far) if k % 4 else \
+            po.ref_frustum_ortho(pos, dirv.astype(np.float32), up.astype(np.float32), 50 + far * 0.1, 30 + far * 0.05, 0.0, far)
+        fr_args.append(np.concatenate([pos, dirv, up, [fov, ratio, near, far, float(k % 4 != 0)]]))
+        fr_out.append(f.copy())
+        for j in range(25):
+            o = pos + rng.normal(size=3) * far * 0.7
+            o = np.floor(o / 300.0) * 300.0
+            rel = np.zeros(224, np.uint8)
+            L.ref_frustum_get_relative(P(f), P(o), P(rel))
+            rel_origin.append(o); rel_out.append(rel)
+            sz = np.float32(300.0 * (1 + j % 2))
+            size = np.array([sz, sz, sz], np.float32)
+            box_pos.append(o); box_size.append(size)
+            box_c.append(L.ref_frustum_contains_aabb(P(f), P(o), P(size)))
+            box_i.append(L.ref_frustum_intersects_aabb(P(f), P(o), P(size)))
+    d.update(fr_args=np.array(fr_args), fr_out=np.array(fr_out), rel_origin=np.array(rel_origin), rel_out=np.array(rel_out)[:, :128],
+             box_pos=np.array(box_pos), box_size=np.array(box_size), box_contains=np.array(box_c, np.int8), box_intersects=np.array(box_i, np.int8))
+    # RNG
+    r = np.zeros(64, np.float32)
+    L.ref_rng_floats(C.c_uint32(521288629), C.c_uint32(362436069), C.c_uint32(64), P(r), None)
+    d.update(rng64=r)
+    np.savez_compressed(os.path.join(OUT, "math_kat.npz"), **d)
+    print("math_kat.npz", sum(v.nbytes for v in d.values()))
+
+
+def cull_kat():
+    """Visible sets of the reference's CullingSystemImpl (on its own job system, 4 workers) for seeded scenes, incl. incremental edits."""
+    d = {}
+    rng = np.random.default_rng(99)
+    scene = scenes.cull_scene(30_000, (2500.0, 300.0, 2500.0), seed=31, big_fraction=0.01, type_probs=(0.7, 0.2, 0.1))
+    rc = po.RefCulling(workers=4)
+    rc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    frusta = [dict(scenes.c1_frustum_args()),
+              dict(scenes.c1_frustum_args(), position=(700.0, 40.0, -300.0), direction=(-0.5, -0.05, -0.8), far=2500.0),
+              dict(scenes.c1_frustum_args(), position=(-2000.0, 0.0, 2000.0), direction=(1.0, 0.0, -1.0), far=6000.0, fov=0.35)]
+    fb = [po.ref_frustum_perspective(a["position"], a["direction"], a["up"], a["fov"], a["ratio"], a["near"], a["far"]) for a in frusta]
+    d["frusta"] = np.array(fb)
+    for i, f in enumerate(fb):
+        ids, tys, info = rc.cull(f, cap=30_000)
+        o = np.argsort(ids)
+        d[f"vis{i}_ids"], d[f"vis{i}_types"] = ids[o], tys[o]
+        for t in range(3):
+            ids_t, _, _ = rc.cull(f, type=t, cap=30_000)
+            d[f"vis{i}_type{t}"] = np.sort(ids_t)
+    # incremental edits, then cull again
+    mv = rng.choice(30_000, 4000, replace=False).astype(np.int32)
+    a, b, c, e = np.array_split(mv, 4)
+    pa = scene["pos"][a] + rng.normal(size=(len(a), 3)) * np.array([500.0, 50.0, 500.0])
+    rb = (rng.random(len(b)) * 650).astype(np.float32)
+    pc = scene["pos"][c] * 0.3; rcc = (rng.random(len(c)) * 400).astype(np.float32)
+    rc.set_position(a, pa); rc.set_radius(b, rb); rc.set(c, pc, rcc); rc.remove(e)
+    d.update(edit_a=a, edit_pa=pa, edit_b=b, edit_rb=rb, edit_c=c, edit_pc=pc, edit_rc=rcc, edit_e=e)
+    for i, f in enumerate(fb):
+        ids, tys, _ = rc.cull(f, cap=30_000)
+        o = np.argsort(ids)
+        d[f"edited{i}_ids"], d[f"edited{i}_types"] = ids[o], tys[o]
+    np.savez_compressed(os.path.join(OUT, "cull_kat.npz"), **d)
+    print("cull_kat.npz", sum(v.nbytes for v in d.values()))
+
+
+def pose_kat():
+    """The reference's Animation::getRelativePose + Pose::computeAbsolute on synthetic clips (bit widths 5..16)."""
+    d = {}
+    cfgs = [(24, 17, 30.0, (11, 13, 16), (12, 14, 16), 0.25), (64, 60, 30.0, (16, 16, 16), (15, 15, 15), 0.25), (7, 3, 1.0, (5, 3, 7), (9, 9, 9), 0.0)]
+    for k, (bones, frames, fps, pb, rb, cf) in enumerate(cfgs):
+        sk = scenes.skeleton(bones, seed=40 + k)
+        clip = scenes.clip(sk, frames=frames, fps=fps, seed=50 + k, pos_bits=pb, rot_bits=rb, const_fraction=cf)
+        L = clip.length_ticks
+        times = np.unique(np.concatenate([[0, 1, L // 3, L // 2, L - 1, L, L + 12345, 2 ** 31], np.random.default_rng(k).integers(0, L, 40)])).astype(np.uint32)
+        rel, abs_, blend = [], [], []
+        for t in times:
+            rel.append(np.concatenate(po.ref_pose_evaluate(sk, clip, t, compute_absolute=False), axis=1))
+            abs_.append(np.concatenate(po.ref_pose_evaluate(sk, clip, t, compute_absolute=True), axis=1))
+            p0, r0 = rel[-1][:, :3], rel[-1][:, 3:]
+            blend.append(np.concatenate(po.ref_pose_evaluate(sk, clip, (int(t) * 7 + 11) % max(L, 1), weight=0.37, start_from_bind=False,
+                                                              compute_absolute=False, pos=p0, rot=r0), axis=1))
+        d[f"c{k}_times"] = times
+        d[f"c{k}_rel"], d[f"c{k}_abs"], d[f"c{k}_blend"] = np.array(rel), np.array(abs_), np.array(blend)
+        d[f"c{k}_length"] = np.array([po.ref().ref_clip_length_ticks(C.c_float(clip.fps), C.c_uint32(clip.frame_count))], np.uint32)
+    d["time_from_seconds_in"] = np.array([0.0, 1 / 60, 1 / 30, 0.5, 3.7, 100.25], np.float32)
+    d["time_from_seconds_out"] = np.array([po.ref().ref_time_from_seconds(C.c_float(float(x))) for x in d["time_from_seconds_in"]], np.uint32)
+    np.savez_compressed(os.path.join(OUT, "pose_kat.npz"), **d)
+    print("pose_kat.npz", sum(v.nbytes for v in d.values()))
+
+
+if __name__ == "__main__":
+    po.build()
+    po.ref().ref_clip_length_ticks.restype = C.c_uint32
+    po.ref().ref_time_from_seconds.restype = C.c_uint32
+    math_kat()
+    pose_kat()
+    cull_kat()
+    sys.stdout.flush()
+    os._exit(0)

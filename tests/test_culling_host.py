@@ -1,0 +1,84 @@
+"""Host-side bookkeeping of the product's CullingSystem (cell grid, page chains, entity->slot map; no GPU needed)
+against the oracle's restatement of culling_system.cpp:98-258 — page for page, in m_cells order."""
+import numpy as np
+
+import lumixengine_b200 as lb
+from lumixengine_b200 import scenes
+
+
+def _same_state(cs, oc):
+    pa, pb = cs.pages(), oc.pages()
+    assert len(pa) == len(pb)
+    for a, b in zip(pa, pb):
+        assert a["origin"] == b["origin"] and a["indices"] == b["indices"]
+        assert a["type"] == b["type"] and a["is_big"] == b["is_big"] and a["count"] == b["count"]
+        assert np.array_equal(a["entities"], b["entities"])
+        assert np.array_equal(a["spheres"].view(np.uint32), b["spheres"].view(np.uint32))
+
+
+def test_build_matches_reference_layout(oracle):
+    scene = scenes.cull_scene(50_000, (1500.0, 300.0, 1500.0), seed=4, big_fraction=0.01, type_probs=(0.7, 0.2, 0.1))
+    cs = lb.CullingSystem(None)
+    oc = oracle.OracleCulling()
+    cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    assert cs.entity_count() == 50_000
+    _same_state(cs, oc)
+    # pages hold at most 200 spheres (count < MAX_COUNT - 1, culling_system.cpp:103), cells with more chain pages
+    counts = [p["count"] for p in cs.pages()]
+    assert max(counts) == 200 and min(counts) >= 1
+
+
+def test_incremental_api_matches(oracle):
+    rng = np.random.default_rng(12)
+    n = 30_000
+    scene = scenes.cull_scene(n, (900.0, 100.0, 900.0), seed=8)
+    cs = lb.CullingSystem(None)
+    oc = oracle.OracleCulling()
+    cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    alive = np.ones(n, bool)
+    for step in range(6):
+        ids = rng.choice(np.nonzero(alive)[0], 2500, replace=False).astype(np.int32)
+        a, b, c, d = np.array_split(ids, 4)
+        p = scene["pos"][a] + rng.normal(size=(len(a), 3)) * np.array([300.0, 30.0, 300.0])  # many cross cell borders
+        cs.setPosition(a, p); oc.set_position(a, p)
+        r = (rng.random(len(b)) * 650.0).astype(np.float32)  # crosses the is_big threshold (radius > 300)
+        cs.setRadius(b, r); oc.set_radius(b, r)
+        p2 = scene["pos"][c] * 0.5
+        r2 = (rng.random(len(c)) * 400.0).astype(np.float32)
+        cs.set(c, p2, r2); oc.set(c, p2, r2)
+        cs.remove(d); oc.remove(d)
+        alive[d] = False
+        _same_state(cs, oc)
+        for e in (int(a[0]), int(b[0]), int(d[0])):
+            assert cs.isAdded(e) == oc.is_added(e)
+        assert cs.getRadius(int(b[1])) == oc.get_radius(int(b[1]))
+    # re-adding removed entities reuses freed pages without disturbing the order of m_cells
+    back = np.nonzero(~alive)[0].astype(np.int32)
+    cs.add(back, scene["types"][back], scene["pos"][back], scene["radius"][back])
+    oc.add(back, scene["types"][back], scene["pos"][back], scene["radius"][back])
+    _same_state(cs, oc)
+    assert cs.entity_count() == n
+
+
+def test_cell_index_truncates_toward_zero(oracle):
+    """culling_system.cpp:27 + math.cpp:133-138: int(double) — cells (-300,300) share index 0."""
+    cs = lb.CullingSystem(None)
+    pts = np.array([[-299.9, 0.0, 0.0], [299.9, 0.0, 0.0], [-300.1, 0.0, 0.0], [300.0, -0.5, 599.999], [-1e-9, -299.0, -600.0]])
+    cs.add(np.arange(5), 0, pts, 1.0)
+    idx = sorted(p["indices"] for p in cs.pages())
+    assert idx == sorted({(0, 0, 0), (-1, 0, 0), (1, 0, 1), (0, 0, -2)})
+    oc = oracle.OracleCulling()
+    oc.add(np.arange(5), np.zeros(5, np.uint8), pts, np.ones(5, np.float32))
+    _same_state(cs, oc)
+
+
+def test_type_0xff_is_reserved():
+    cs = lb.CullingSystem(None)
+    try:
+        cs.add(1, 0xFF, (0.0, 0.0, 0.0), 1.0)
+    except lb.LumixB200Error as e:
+        assert e.code == lb._lib.ERR_INVALID
+    else:
+        raise AssertionError("type 0xff must be rejected (culling_system.cpp:312)")

@@ -1,0 +1,129 @@
+"""Pins the CPU oracle (restatement) against golden vectors produced by the reference's own compiled code
+(tests/golden/*.npz, generator: tests/golden/make_golden.py).  Runs anywhere: needs gcc only."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from lumixengine_b200 import scenes
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32 if a.dtype.itemsize == 4 else np.uint8)
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(os.path.join(G, "math_kat.npz"))
+
+
+def test_math_primitives_bit_exact(oracle, kat):
+    L = oracle.lib()
+    n = len(kat["qa"])
+    c = lambda a: np.ascontiguousarray(a)  # noqa: E731
+    out = np.zeros((n, 56), np.uint8)
+    L.oracle_transform_compose(P(c(kat["tr_a"])), P(c(kat["tr_b"])), P(out), C.c_uint32(n))
+    assert np.array_equal(out[:, :52], kat["compose"][:, :52])  # math.cpp:801-807 (bytes 52..55 are struct padding)
+    qa, qb, v, v2, t = (c(kat[k]) for k in ("qa", "qb", "v", "v2", "t"))
+    o4, o3 = np.zeros((n, 4), np.float32), np.zeros((n, 3), np.float32)
+    L.oracle_quat_mul(P(qa), P(qb), P(o4), C.c_uint32(n)); assert np.array_equal(bits(o4), bits(kat["quat_mul"]))
+    L.oracle_quat_rotate(P(qa), P(v), P(o3), C.c_uint32(n)); assert np.array_equal(bits(o3), bits(kat["quat_rotate"]))
+    L.oracle_nlerp(P(qa), P(qb), P(t), P(o4), C.c_uint32(n), C.c_int(0)); assert np.array_equal(bits(o4), bits(kat["nlerp"]))
+    L.oracle_nlerp(P(qa), P(qb), P(t), P(o4), C.c_uint32(n), C.c_int(1)); assert np.array_equal(bits(o4), bits(kat["simd_nlerp"]))
+    L.oracle_lerp_vec3(P(v), P(v2), P(t), P(o3), C.c_uint32(n)); assert np.array_equal(bits(o3), bits(kat["lerp"]))
+    la, lb_ = c(kat["lrt_a"]), c(kat["lrt_b"])
+    o7, o8, o16 = np.zeros((n, 7), np.float32), np.zeros((n, 8), np.float32), np.zeros((n, 16), np.float32)
+    L.oracle_lrt_mul(P(la), P(lb_), P(o7), C.c_uint32(n)); assert np.array_equal(bits(o7), bits(kat["lrt_mul"]))
+    L.oracle_lrt_inverted(P(la), P(o7), C.c_uint32(n)); assert np.array_equal(bits(o7), bits(kat["lrt_inverted"]))
+    L.oracle_lrt_to_matrix(P(la), P(o16), C.c_uint32(n)); assert np.array_equal(bits(o16), bits(kat["lrt_to_matrix"]))
+    L.oracle_lrt_to_dual_quat(P(la), P(o8), C.c_uint32(n))
+    # the reference's SSE toDualQuat negates with 0 - x (simd.h:187-189): results agree except for the sign of zero
+    assert np.array_equal(o8, kat["lrt_to_dual_quat"])
+    got = oracle.skin_vertices(kat["skin_palette"], v, kat["skin_w"], kat["skin_idx"])
+    assert np.array_equal(bits(got), bits(kat["skin_out"]))  # model.cpp:103-109
+
+
+def test_cell_indices_and_rng(oracle, kat):
+    L = oracle.lib()
+    cp = np.ascontiguousarray(kat["cell_pos"])
+    out = np.zeros(3, np.int32)
+    for p, exp in zip(cp, kat["cell_idx"]):
+        L.oracle_cell_indices(P(p), C.c_float(300.0), P(out))
+        assert tuple(out) == tuple(exp)
+    r, _ = oracle.rng_floats(521288629, 362436069, 64)
+    assert np.array_equal(bits(r), bits(kat["rng64"]))  # math.cpp:1333-1378
+
+
+def test_frustum_construction_and_cell_tests(oracle, kat):
+    L = oracle.lib()
+    k = 0
+    for args, exp in zip(kat["fr_args"], kat["fr_out"]):
+        pos, dirv, up = args[0:3], args[3:6].astype(np.float32), args[6:9].astype(np.float32)
+        fov, ratio, near, far, persp = args[9:14]
+        f = oracle.frustum_perspective(pos, dirv, up, fov, ratio, near, far) if persp else oracle.frustum_ortho(pos, dirv, up, 50 + far * 0.1, 30 + far * 0.05, 0.0, far)
+        assert np.array_equal(f[:248], exp[:248])  # geometry.cpp:390-409,470-499
+        for _ in range(25):
+            o = np.ascontiguousarray(kat["rel_origin"][k])
+            rel = np.zeros(224, np.uint8)
+            L.oracle_frustum_get_relative.argtypes = None
+            # ODVec3 by value: pass through a tiny struct
+            class D3(C.Structure):
+                _fields_ = [("x", C.c_double), ("y", C.c_double), ("z", C.c_double)]
+
+            class V3(C.Structure):
+                _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+            L.oracle_frustum_get_relative(P(f), D3(*o), P(rel))
+            assert np.array_equal(rel[:128], kat["rel_out"][k])  # the 8 planes; geometry.cpp:121-149
+            sz = kat["box_size"][k]
+            assert L.oracle_frustum_contains_aabb(P(f), D3(*kat["box_pos"][k]), V3(*sz)) == kat["box_contains"][k]
+            assert L.oracle_frustum_intersects_aabb(P(f), D3(*kat["box_pos"][k]), V3(*sz)) == kat["box_intersects"][k]
+            k += 1
+    assert kat["box_contains"].sum() > 5 and kat["box_intersects"].sum() > 50  # the fixture exercises both outcomes
+
+
+def test_cull_visible_sets(oracle):
+    """Sorted visible ids (+ types) of the reference's CullingSystemImpl on its own job system."""
+    g = np.load(os.path.join(G, "cull_kat.npz"))
+    scene = scenes.cull_scene(30_000, (2500.0, 300.0, 2500.0), seed=31, big_fraction=0.01, type_probs=(0.7, 0.2, 0.1))
+    oc = oracle.OracleCulling()
+    oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+
+    def check(prefix):
+        for i, f in enumerate(g["frusta"]):
+            ids, tys, _ = oc.cull(f)
+            o = np.argsort(ids)
+            assert np.array_equal(ids[o], g[f"{prefix}{i}_ids"]) and np.array_equal(tys[o], g[f"{prefix}{i}_types"])
+            assert len(ids) > 100
+            if prefix == "vis":
+                for t in range(3):
+                    it, _, _ = oc.cull(f, type=t)
+                    assert np.array_equal(np.sort(it), g[f"vis{i}_type{t}"])
+    check("vis")
+    oc.set_position(g["edit_a"], g["edit_pa"]); oc.set_radius(g["edit_b"], g["edit_rb"]); oc.set(g["edit_c"], g["edit_pc"], g["edit_rc"]); oc.remove(g["edit_e"])
+    check("edited")
+
+
+def test_pose_sampling_and_absolute(oracle):
+    """Animation::getRelativePose (weight 1 and blended) + Pose::computeAbsolute from the reference build."""
+    g = np.load(os.path.join(G, "pose_kat.npz"))
+    cfgs = [(24, 17, 30.0, (11, 13, 16), (12, 14, 16), 0.25), (64, 60, 30.0, (16, 16, 16), (15, 15, 15), 0.25), (7, 3, 1.0, (5, 3, 7), (9, 9, 9), 0.0)]
+    for k, (bones, frames, fps, pb, rb, cf) in enumerate(cfgs):
+        sk = scenes.skeleton(bones, seed=40 + k)
+        clip = scenes.clip(sk, frames=frames, fps=fps, seed=50 + k, pos_bits=pb, rot_bits=rb, const_fraction=cf)
+        assert clip.length_ticks == int(g[f"c{k}_length"][0])
+        L = clip.length_ticks
+        for j, t in enumerate(g[f"c{k}_times"]):
+            rel = np.concatenate(oracle.pose_evaluate(sk, clip, t, compute_absolute=False), axis=1)
+            assert np.array_equal(bits(rel), bits(g[f"c{k}_rel"][j])), (k, t)
+            ab = np.concatenate(oracle.pose_evaluate(sk, clip, t, compute_absolute=True), axis=1)
+            assert np.array_equal(bits(ab), bits(g[f"c{k}_abs"][j])), (k, t)
+            bl = np.concatenate(oracle.pose_evaluate(sk, clip, (int(t) * 7 + 11) % max(L, 1), weight=0.37, start_from_bind=False, compute_absolute=False,
+                                                     pos=rel[:, :3], rot=rel[:, 3:]), axis=1)
+            assert np.array_equal(bits(bl), bits(g[f"c{k}_blend"][j])), (k, t)
+    for s, exp in zip(g["time_from_seconds_in"], g["time_from_seconds_out"]):
+        assert int(np.uint32(np.float32(s) * np.float32(32768))) == int(exp)  # Time::fromSeconds, animation.h:21-24
