@@ -150,7 +150,7 @@ def secondary_paths(ctx, lb, scenes, peak, steps, warmup):
     b = h.algorithmic_bytes()
     out["propagate_1m_depth8"] = {"value": len(parents) / ms / 1e3, "unit": "M nodes/s", "ms_per_step": ms,
                                   "roofline": {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": b / ms / 1e6 / peak, "algorithmic_bytes": b},
-                                  "note": "7 level launches per step; 112 MB working set is L2-resident across steps (not flushed) — kernel-chain latency bound"}
+                                  "note": "narrow levels fused into one block + one launch per wide level; the 112 MB working set is not flushed between steps (locals stay partly L2-resident)"}
     h.close()
     # --- pose + palette, skin ---
     sk = scenes.skeleton(64)

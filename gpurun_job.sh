@@ -1,5 +1,9 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_cull_gpu.py -q -m gpu 2>&1 | tail -5
-python bench.py --steps 200 --warmup 10 --only-cull > gpurun_out/bench_v2.json 2> gpurun_out/bench_v2.err; tail -c 2000 gpurun_out/bench_v2.err; cat gpurun_out/bench_v2.json
-ncu --set full --clock-control none --import-source on -k regex:cull_pages -s 70 -c 2 -o gpurun_out/cull_v2 python bench.py --steps 20 --warmup 3 --only-cull > gpurun_out/ncu_full.log 2>&1
+python -m pytest tests -q -m gpu 2>&1 | tail -8
+python bench.py --steps 200 --warmup 10 > gpurun_out/bench_v3.json 2> gpurun_out/bench_v3.err; tail -c 1500 gpurun_out/bench_v3.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_v3.json'))
+print('cull', j['value'], j['ms_per_step'], j['roofline']['frac'], 'e2e', j['e2e']['value'])
+for k,v in j.get('paths',{}).items(): print(k, v['value'], v['unit'], v['ms_per_step'], v['roofline']['frac'])
+print(j.get('paths_error'), j.get('cpu_baseline'))
+"

@@ -41,7 +41,8 @@ struct AnimParams {
 	const float* bind7;     // bone_count * 7
 	const float* inv_bind7; // bone_count * 7
 	const short* parents;
-	const unsigned char* levels; // depth of each bone below its root (0 = left as is)
+	const unsigned char* level_bones; // bones of depth >= 1 sorted by depth (bone_count <= 196 fits a byte)
+	const uint32_t* level_start;      // [max_level + 2]: level l occupies level_bones[level_start[l] .. level_start[l + 1])
 	uint32_t bone_count;
 	uint32_t max_level;
 	uint32_t n_instances;
@@ -109,129 +110,139 @@ __device__ __forceinline__ Q4 unpack_rotation(unsigned long long packed, const l
 	}
 }
 
-constexpr int POSE_WARPS = 4;
+constexpr int POSE_THREADS = 128;
 
-__global__ void __launch_bounds__(POSE_WARPS * 32) pose_palette_kernel(const __grid_constant__ AnimParams P) {
-	extern __shared__ float smem[];
+// G lanes cooperate on one instance (32 / G instances per warp): per-bone phases stride the bones by G, the absolute pass
+// walks depth levels with up to G bones of a level in flight.  G is chosen on the host from the skeleton's level widths.
+template <int G>
+__global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid_constant__ AnimParams P) {
+	extern __shared__ float4 smem4[];
+	constexpr int INST_PER_BLOCK = POSE_THREADS / G;
 	const int lane = threadIdx.x & 31;
-	const int warp = threadIdx.x >> 5;
+	const int sub = threadIdx.x % G;          // lane inside the instance group
+	const int grp = threadIdx.x / G;          // instance slot inside the block
 	const uint32_t B = P.bone_count;
-	// per warp: pos[B] (3 floats) then rot[B] (4 floats)
-	float* s_pos = smem + (size_t)warp * B * 7;
-	float* s_rot = s_pos + (size_t)B * 3;
-	const uint32_t inst = blockIdx.x * POSE_WARPS + warp;
-	if (inst >= P.n_instances) return;
+	const uint32_t Bp = (B + 3u) & ~3u;
+	// per instance: rot[Bp] (float4) then pos[Bp] (float4, w unused): 128-bit shared accesses, conflict-free per quarter warp
+	float4* s_rot = smem4 + (size_t)grp * Bp * 2;
+	float4* s_pos = s_rot + Bp;
+	const uint32_t inst = blockIdx.x * INST_PER_BLOCK + grp;
+	const bool valid = inst < P.n_instances;
+	// the lanes of one group share a mask so that __syncwarp only joins what must be joined
+	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
 
-	const DevClip clip = P.clips[P.clip_index[inst]];
-	const uint32_t ticks = P.time_ticks[inst];
+	if (valid) {
+		const DevClip clip = P.clips[P.clip_index[inst]];
+		const uint32_t ticks = P.time_ticks[inst];
 
-	// animation.h:27 toFrame: float(value / double(ONE_SECOND) * fps); animation.cpp:131-133
-	const float frame = __double2float_rn(LB_DMUL(__uint2double_rn(ticks) / 32768.0, (double)clip.fps));
-	const float hi = LB_FSUB(__uint2float_rn(clip.frame_count), 0.00001f);
-	float sample = frame > 0.f ? frame : 0.f; // maximum(value, min): value > min ? value : min
-	sample = sample < hi ? sample : hi;       // minimum(x, max)
-	const uint32_t sample_idx = (uint32_t)sample;
-	const float t = LB_FSUB(sample, __uint2float_rn(sample_idx));
+		// animation.h:27 toFrame: float(value / double(ONE_SECOND) * fps); animation.cpp:131-133
+		const float frame = __double2float_rn(LB_DMUL(__uint2double_rn(ticks) / 32768.0, (double)clip.fps));
+		const float hi = LB_FSUB(__uint2float_rn(clip.frame_count), 0.00001f);
+		float sample = frame > 0.f ? frame : 0.f; // maximum(value, min): value > min ? value : min
+		sample = sample < hi ? sample : hi;       // minimum(x, max)
+		const uint32_t sample_idx = (uint32_t)sample;
+		const float t = LB_FSUB(sample, __uint2float_rn(sample_idx));
 
-	// Model::getRelativePose
-	for (uint32_t b = lane; b < B; b += 32) {
-		const float* src = P.bind7 + (size_t)b * 7;
-		s_pos[b * 3 + 0] = src[0]; s_pos[b * 3 + 1] = src[1]; s_pos[b * 3 + 2] = src[2];
-		s_rot[b * 4 + 0] = src[3]; s_rot[b * 4 + 1] = src[4]; s_rot[b * 4 + 2] = src[5]; s_rot[b * 4 + 3] = src[6];
-	}
-	__syncwarp();
-	// animation.cpp:135-149 constant translations
-	for (uint32_t i = lane; i < clip.n_ct; i += 32) {
-		const lb200_const_translation ct = P.const_t[clip.ct_off + i];
-		s_pos[ct.bone_index * 3 + 0] = ct.value[0]; s_pos[ct.bone_index * 3 + 1] = ct.value[1]; s_pos[ct.bone_index * 3 + 2] = ct.value[2];
-	}
-	__syncwarp();
-	// :151-167 animated translations
-	const uint32_t* t_stream = P.stream + (clip.t_stream >> 2);
-	for (uint32_t i = lane; i < clip.n_t; i += 32) {
-		const lb200_track tr = P.tracks[clip.t_off + i];
-		const V3 a = get_translation(t_stream, clip.t_bits, sample_idx, tr);
-		const V3 b = get_translation(t_stream, clip.t_bits, sample_idx + 1, tr);
-		const V3 p = lerp(a, b, t);
-		s_pos[tr.bone_index * 3 + 0] = p.x; s_pos[tr.bone_index * 3 + 1] = p.y; s_pos[tr.bone_index * 3 + 2] = p.z;
-	}
-	// :169-183 constant rotations
-	for (uint32_t i = lane; i < clip.n_cr; i += 32) {
-		const lb200_const_rotation cr = P.const_r[clip.cr_off + i];
-		s_rot[cr.bone_index * 4 + 0] = cr.value[0]; s_rot[cr.bone_index * 4 + 1] = cr.value[1];
-		s_rot[cr.bone_index * 4 + 2] = cr.value[2]; s_rot[cr.bone_index * 4 + 3] = cr.value[3];
-	}
-	__syncwarp();
-	// :185-203 animated rotations
-	const uint32_t* r_stream = P.stream + (clip.r_stream >> 2);
-	for (uint32_t i = lane; i < clip.n_r; i += 32) {
-		const lb200_track tr = P.tracks[clip.r_off + i];
-		const uint32_t offset1 = clip.r_bits * sample_idx + tr.offset_bits;
-		const uint32_t offset2 = offset1 + clip.r_bits;
-		unsigned long long p1 = load_u64_unaligned(r_stream, offset1 >> 3);
-		p1 >>= (offset1 & 7u);
-		unsigned long long p2 = load_u64_unaligned(r_stream, offset2 >> 3);
-		p2 >>= (offset2 & 7u);
-		const Q4 q = simd_nlerp(unpack_rotation(p1, tr), unpack_rotation(p2, tr), t);
-		s_rot[tr.bone_index * 4 + 0] = q.x; s_rot[tr.bone_index * 4 + 1] = q.y; s_rot[tr.bone_index * 4 + 2] = q.z; s_rot[tr.bone_index * 4 + 3] = q.w;
-	}
-	__syncwarp();
-
-	// Pose::computeAbsolute, pose.cpp:66-133: bones of one depth level are independent (the reference's 4-wide path
-	// relies on the same fact); levels run in order so every parent is absolute before its children.
-	for (uint32_t lvl = 1; lvl <= P.max_level; ++lvl) {
-		for (uint32_t b = lane; b < B; b += 32) {
-			if (P.levels[b] != lvl) continue;
-			const int p = P.parents[b];
-			const Q4 prot = q4(s_rot[p * 4], s_rot[p * 4 + 1], s_rot[p * 4 + 2], s_rot[p * 4 + 3]);
-			const V3 ppos = v3(s_pos[p * 3], s_pos[p * 3 + 1], s_pos[p * 3 + 2]);
-			const V3 pos = add(rotate(prot, v3(s_pos[b * 3], s_pos[b * 3 + 1], s_pos[b * 3 + 2])), ppos); // :129
-			const Q4 rot = qmul(prot, q4(s_rot[b * 4], s_rot[b * 4 + 1], s_rot[b * 4 + 2], s_rot[b * 4 + 3])); // :130
-			s_pos[b * 3] = pos.x; s_pos[b * 3 + 1] = pos.y; s_pos[b * 3 + 2] = pos.z;
-			s_rot[b * 4] = rot.x; s_rot[b * 4 + 1] = rot.y; s_rot[b * 4 + 2] = rot.z; s_rot[b * 4 + 3] = rot.w;
+		// Model::getRelativePose, model.cpp:226-237
+		for (uint32_t b = sub; b < B; b += G) {
+			const float* src = P.bind7 + (size_t)b * 7;
+			s_pos[b] = make_float4(src[0], src[1], src[2], 0.f);
+			s_rot[b] = make_float4(src[3], src[4], src[5], src[6]);
 		}
-		__syncwarp();
-	}
+		__syncwarp(gmask);
+		// animation.cpp:135-149 constant translations
+		for (uint32_t i = sub; i < clip.n_ct; i += G) {
+			const lb200_const_translation ct = P.const_t[clip.ct_off + i];
+			s_pos[ct.bone_index] = make_float4(ct.value[0], ct.value[1], ct.value[2], 0.f);
+		}
+		// :169-183 constant rotations
+		for (uint32_t i = sub; i < clip.n_cr; i += G) {
+			const lb200_const_rotation cr = P.const_r[clip.cr_off + i];
+			s_rot[cr.bone_index] = make_float4(cr.value[0], cr.value[1], cr.value[2], cr.value[3]);
+		}
+		__syncwarp(gmask);
+		// :151-167 animated translations
+		const uint32_t* t_stream = P.stream + (clip.t_stream >> 2);
+		for (uint32_t i = sub; i < clip.n_t; i += G) {
+			const lb200_track tr = P.tracks[clip.t_off + i];
+			const V3 a = get_translation(t_stream, clip.t_bits, sample_idx, tr);
+			const V3 b = get_translation(t_stream, clip.t_bits, sample_idx + 1, tr);
+			const V3 p = lerp(a, b, t);
+			s_pos[tr.bone_index] = make_float4(p.x, p.y, p.z, 0.f);
+		}
+		// :185-203 animated rotations
+		const uint32_t* r_stream = P.stream + (clip.r_stream >> 2);
+		for (uint32_t i = sub; i < clip.n_r; i += G) {
+			const lb200_track tr = P.tracks[clip.r_off + i];
+			const uint32_t offset1 = clip.r_bits * sample_idx + tr.offset_bits;
+			const uint32_t offset2 = offset1 + clip.r_bits;
+			unsigned long long p1 = load_u64_unaligned(r_stream, offset1 >> 3);
+			p1 >>= (offset1 & 7u);
+			unsigned long long p2 = load_u64_unaligned(r_stream, offset2 >> 3);
+			p2 >>= (offset2 & 7u);
+			const Q4 q = simd_nlerp(unpack_rotation(p1, tr), unpack_rotation(p2, tr), t);
+			s_rot[tr.bone_index] = make_float4(q.x, q.y, q.z, q.w);
+		}
+		__syncwarp(gmask);
 
-	// palettes
-	for (uint32_t b = lane; b < B; b += 32) {
-		Rigid pose;
-		pose.pos = v3(s_pos[b * 3], s_pos[b * 3 + 1], s_pos[b * 3 + 2]);
-		pose.rot = q4(s_rot[b * 4], s_rot[b * 4 + 1], s_rot[b * 4 + 2], s_rot[b * 4 + 3]);
-		const float* ib = P.inv_bind7 + (size_t)b * 7;
-		Rigid inv;
-		inv.pos = v3(ib[0], ib[1], ib[2]);
-		inv.rot = q4(ib[3], ib[4], ib[5], ib[6]);
-		const Rigid skin = rmul(pose, inv);
-		const size_t idx = (size_t)inst * B + b;
-		if (P.out_dq) {
-			const DualQ dq = to_dual_quat(skin);
-			float4* o = reinterpret_cast<float4*>(P.out_dq + idx * 8);
-			o[0] = make_float4(dq.r.x, dq.r.y, dq.r.z, dq.r.w);
-			o[1] = make_float4(dq.d.x, dq.d.y, dq.d.z, dq.d.w);
+		// Pose::computeAbsolute, pose.cpp:66-133: bones of one depth level are independent (the reference's 4-wide path
+		// relies on the same fact); levels run in order so every parent is absolute before its children.
+		for (uint32_t lvl = 1; lvl <= P.max_level; ++lvl) {
+			const uint32_t lb = P.level_start[lvl], le = P.level_start[lvl + 1];
+			for (uint32_t k = lb + sub; k < le; k += G) {
+				const uint32_t b = P.level_bones[k];
+				const int p = P.parents[b];
+				const float4 pr = s_rot[p], pp = s_pos[p], cr = s_rot[b], cp = s_pos[b];
+				const Q4 prot = q4(pr.x, pr.y, pr.z, pr.w);
+				const V3 pos = add(rotate(prot, v3(cp.x, cp.y, cp.z)), v3(pp.x, pp.y, pp.z)); // :129
+				const Q4 rot = qmul(prot, q4(cr.x, cr.y, cr.z, cr.w));                          // :130
+				s_pos[b] = make_float4(pos.x, pos.y, pos.z, 0.f);
+				s_rot[b] = make_float4(rot.x, rot.y, rot.z, rot.w);
+			}
+			__syncwarp(gmask);
 		}
-		if (P.out_mtx) {
-			float m[16];
-			to_matrix(skin, m);
-			float4* o = reinterpret_cast<float4*>(P.out_mtx + idx * 16);
-			o[0] = make_float4(m[0], m[1], m[2], m[3]);
-			o[1] = make_float4(m[4], m[5], m[6], m[7]);
-			o[2] = make_float4(m[8], m[9], m[10], m[11]);
-			o[3] = make_float4(m[12], m[13], m[14], m[15]);
-		}
-		if (P.out_pos) {
-			P.out_pos[idx * 3] = pose.pos.x; P.out_pos[idx * 3 + 1] = pose.pos.y; P.out_pos[idx * 3 + 2] = pose.pos.z;
-			reinterpret_cast<float4*>(P.out_rot)[idx] = make_float4(pose.rot.x, pose.rot.y, pose.rot.z, pose.rot.w);
-		}
-	}
 
-	// animation_module.cpp:458-469
-	if (P.advance && lane == 0) {
-		const uint32_t l = clip.length_ticks;
-		uint32_t nt;
-		if (!P.dt_negative) nt = (ticks + P.dt_ticks) % l;
-		else nt = (ticks + l - (P.dt_ticks % l)) % l;
-		P.time_ticks[inst] = nt;
+		// palettes: pipeline.cpp:2680-2745 / model.cpp:132-137
+		for (uint32_t b = sub; b < B; b += G) {
+			const float4 cr = s_rot[b], cp = s_pos[b];
+			Rigid pose;
+			pose.pos = v3(cp.x, cp.y, cp.z);
+			pose.rot = q4(cr.x, cr.y, cr.z, cr.w);
+			const float* ib = P.inv_bind7 + (size_t)b * 7;
+			Rigid inv;
+			inv.pos = v3(ib[0], ib[1], ib[2]);
+			inv.rot = q4(ib[3], ib[4], ib[5], ib[6]);
+			const Rigid skin = rmul(pose, inv);
+			const size_t idx = (size_t)inst * B + b;
+			if (P.out_dq) {
+				const DualQ dq = to_dual_quat(skin);
+				float4* o = reinterpret_cast<float4*>(P.out_dq + idx * 8);
+				o[0] = make_float4(dq.r.x, dq.r.y, dq.r.z, dq.r.w);
+				o[1] = make_float4(dq.d.x, dq.d.y, dq.d.z, dq.d.w);
+			}
+			if (P.out_mtx) {
+				float m[16];
+				to_matrix(skin, m);
+				float4* o = reinterpret_cast<float4*>(P.out_mtx + idx * 16);
+				o[0] = make_float4(m[0], m[1], m[2], m[3]);
+				o[1] = make_float4(m[4], m[5], m[6], m[7]);
+				o[2] = make_float4(m[8], m[9], m[10], m[11]);
+				o[3] = make_float4(m[12], m[13], m[14], m[15]);
+			}
+			if (P.out_pos) {
+				P.out_pos[idx * 3] = pose.pos.x; P.out_pos[idx * 3 + 1] = pose.pos.y; P.out_pos[idx * 3 + 2] = pose.pos.z;
+				reinterpret_cast<float4*>(P.out_rot)[idx] = cr;
+			}
+		}
+
+		// animation_module.cpp:458-469
+		if (P.advance && sub == 0) {
+			const uint32_t l = clip.length_ticks;
+			uint32_t nt;
+			if (!P.dt_negative) nt = (ticks + P.dt_ticks) % l;
+			else nt = (ticks + l - (P.dt_ticks % l)) % l;
+			P.time_ticks[inst] = nt;
+		}
 	}
 }
 
@@ -301,7 +312,8 @@ struct lb200_animation {
 	lb200_const_rotation* d_const_r = nullptr;
 	uint32_t* d_stream = nullptr;
 	float* d_bind7 = nullptr; float* d_inv_bind7 = nullptr;
-	short* d_parents = nullptr; unsigned char* d_levels = nullptr;
+	short* d_parents = nullptr; unsigned char* d_level_bones = nullptr; uint32_t* d_level_start = nullptr;
+	int lanes_per_instance = 8;
 	uint32_t* d_clip_index = nullptr; uint32_t* d_time = nullptr;
 	float* d_dq = nullptr; float* d_mtx = nullptr; float* d_pos = nullptr; float* d_rot = nullptr;
 	float* d_mesh_pos = nullptr; float4* d_mesh_w = nullptr; short* d_mesh_idx = nullptr;
@@ -330,6 +342,23 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		if (p < 0 || (uint32_t)p >= i) { lb200_set_error(ctx, "bone %u: parent %d is not an earlier bone", i, p); return LB200_ERR_INVALID; }
 		levels[i] = (unsigned char)(levels[p] + 1);
 		if (levels[i] > max_level) max_level = levels[i];
+	}
+	// bones of depth >= 1 grouped by depth (stable in bone order)
+	std::vector<unsigned char> level_bones;
+	std::vector<uint32_t> level_start(max_level + 2, 0);
+	for (uint32_t l = 1; l <= max_level; ++l) {
+		level_start[l] = (uint32_t)level_bones.size();
+		for (uint32_t i = first; i < B; ++i) if (levels[i] == l) level_bones.push_back((unsigned char)i);
+	}
+	level_start[max_level + 1] = (uint32_t)level_bones.size();
+	// lanes per instance: minimise the lane-steps of the absolute pass, G * sum_l ceil(width_l / G), keeping >= 8 lanes for occupancy
+	int best_g = 8;
+	uint64_t best_cost = ~0ull;
+	for (int g = 8; g <= 32; g *= 2) {
+		uint64_t steps = 0;
+		for (uint32_t l = 1; l <= max_level; ++l) steps += (level_start[l + 1] - level_start[l] + g - 1) / g;
+		const uint64_t cost = steps * g;
+		if (cost < best_cost) { best_cost = cost; best_g = g; }
 	}
 	std::vector<DevClip> dc(n_clips);
 	std::vector<lb200_track> tracks;
@@ -382,7 +411,9 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	ANIM_MALLOC(a->d_bind7, sizeof(float) * 7 * B);
 	ANIM_MALLOC(a->d_inv_bind7, sizeof(float) * 7 * B);
 	ANIM_MALLOC(a->d_parents, sizeof(short) * B);
-	ANIM_MALLOC(a->d_levels, B);
+	ANIM_MALLOC(a->d_level_bones, level_bones.size());
+	ANIM_MALLOC(a->d_level_start, sizeof(uint32_t) * level_start.size());
+	a->lanes_per_instance = best_g;
 	ANIM_MALLOC(a->d_clip_index, sizeof(uint32_t) * max_instances);
 	ANIM_MALLOC(a->d_time, sizeof(uint32_t) * max_instances);
 	ANIM_MALLOC(a->d_checksum, sizeof(unsigned long long));
@@ -395,7 +426,8 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_bind7, sk->bind_relative7, sizeof(float) * 7 * B, cudaMemcpyHostToDevice, st));
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_inv_bind7, sk->inverse_bind7, sizeof(float) * 7 * B, cudaMemcpyHostToDevice, st));
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_parents, sk->parents, sizeof(short) * B, cudaMemcpyHostToDevice, st));
-	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_levels, levels.data(), B, cudaMemcpyHostToDevice, st));
+	if (!level_bones.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_level_bones, level_bones.data(), level_bones.size(), cudaMemcpyHostToDevice, st));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_level_start, level_start.data(), sizeof(uint32_t) * level_start.size(), cudaMemcpyHostToDevice, st));
 	if (mesh && mesh->n_vertices) {
 		a->n_vertices = mesh->n_vertices;
 		for (uint32_t v = 0; v < mesh->n_vertices * 4; ++v) if (mesh->indices4[v] < 0 || (uint32_t)mesh->indices4[v] >= B) { lb200_animation_destroy(a); return LB200_ERR_INVALID; }
@@ -407,7 +439,12 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		LB200_CUDA(ctx, cudaMemcpyAsync(a->d_mesh_idx, mesh->indices4, sizeof(short) * 4 * mesh->n_vertices, cudaMemcpyHostToDevice, st));
 	}
 	LB200_CUDA(ctx, cudaStreamSynchronize(st));
-	LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POSE_WARPS * 196 * 7 * sizeof(float))));
+	{
+		const int smem_max = (int)(sizeof(float4) * 2 * 196 * (POSE_THREADS / 8));
+		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+	}
 	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SKIN_GROUP * 196 * 3 * sizeof(float4))));
 	*out = a;
 	return LB200_OK;
@@ -418,7 +455,7 @@ void lb200_animation_destroy(lb200_animation* a) {
 	cudaSetDevice(a->ctx->device);
 	cudaStreamSynchronize(a->ctx->stream);
 	cudaFree(a->d_clips); cudaFree(a->d_tracks); cudaFree(a->d_const_t); cudaFree(a->d_const_r); cudaFree(a->d_stream);
-	cudaFree(a->d_bind7); cudaFree(a->d_inv_bind7); cudaFree(a->d_parents); cudaFree(a->d_levels);
+	cudaFree(a->d_bind7); cudaFree(a->d_inv_bind7); cudaFree(a->d_parents); cudaFree(a->d_level_bones); cudaFree(a->d_level_start);
 	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot);
 	cudaFree(a->d_mesh_pos); cudaFree(a->d_mesh_w); cudaFree(a->d_mesh_idx); cudaFree(a->d_skinned); cudaFree(a->d_checksum);
 	delete a;
@@ -447,7 +484,7 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	if ((flags & LB200_PALETTE_POSE) && !a->d_pos) { ANIM_MALLOC(a->d_pos, sizeof(float) * 3 * nb); ANIM_MALLOC(a->d_rot, sizeof(float) * 4 * nb); }
 	AnimParams P;
 	P.clips = a->d_clips; P.tracks = a->d_tracks; P.const_t = a->d_const_t; P.const_r = a->d_const_r; P.stream = a->d_stream;
-	P.bind7 = a->d_bind7; P.inv_bind7 = a->d_inv_bind7; P.parents = a->d_parents; P.levels = a->d_levels;
+	P.bind7 = a->d_bind7; P.inv_bind7 = a->d_inv_bind7; P.parents = a->d_parents; P.level_bones = a->d_level_bones; P.level_start = a->d_level_start;
 	P.bone_count = a->bone_count; P.max_level = a->max_level; P.n_instances = a->n_instances;
 	P.clip_index = a->d_clip_index; P.time_ticks = a->d_time;
 	P.out_dq = (flags & LB200_PALETTE_DUAL_QUAT) ? a->d_dq : nullptr;
@@ -458,9 +495,13 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	P.dt_negative = time_delta < 0;
 	P.dt_ticks = (uint32_t)((P.dt_negative ? -time_delta : time_delta) * (float)(1 << 15));
 	P.advance = time_delta != 0;
-	const unsigned blocks = (a->n_instances + POSE_WARPS - 1) / POSE_WARPS;
-	const size_t smem = sizeof(float) * 7 * a->bone_count * POSE_WARPS;
-	pose_palette_kernel<<<blocks, POSE_WARPS * 32, smem, ctx->stream>>>(P);
+	const int G = a->lanes_per_instance;
+	const unsigned per_block = POSE_THREADS / G;
+	const unsigned blocks = (a->n_instances + per_block - 1) / per_block;
+	const size_t smem = sizeof(float4) * 2 * ((a->bone_count + 3u) & ~3u) * per_block;
+	if (G == 8) pose_palette_kernel<8><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
+	else if (G == 16) pose_palette_kernel<16><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
+	else pose_palette_kernel<32><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
 	LB200_CHECK_LAUNCH(ctx);
 	return LB200_OK;
 }

@@ -49,10 +49,8 @@ __global__ void __launch_bounds__(HT) soa_to_aos_kernel(SoaTransforms in, const 
 	out[order[i]] = t;
 }
 
-// One depth level: nodes [begin, end) in level order; parents live in earlier levels.
-__global__ void __launch_bounds__(HT) propagate_level_kernel(uint32_t begin, uint32_t end, const int* __restrict__ parent, SoaTransforms L, SoaTransforms G) {
-	const uint32_t i = begin + blockIdx.x * HT + threadIdx.x;
-	if (i >= end) return;
+// compose one node (level position i) from its parent's global: Transform::compose, math.cpp:801-807
+__device__ __forceinline__ void compose_node(uint32_t i, const int* __restrict__ parent, const SoaTransforms& L, const SoaTransforms& G) {
 	const int p = parent[i];
 	// parent global (siblings are adjacent: these loads coalesce to a few sectors per warp)
 	const D3 ppos = d3(G.px[p], G.py[p], G.pz[p]);
@@ -63,7 +61,7 @@ __global__ void __launch_bounds__(HT) propagate_level_kernel(uint32_t begin, uin
 	const D3 lpos = d3(L.px[i], L.py[i], L.pz[i]);
 	const float4 lr = L.rot[i];
 	const V3 lscale = v3(L.sx[i], L.sy[i], L.sz[i]);
-	// math.cpp:801-807: { rot.rotate(rhs.pos * scale) + pos, rot * rhs.rot, scale * rhs.scale }
+	// { rot.rotate(rhs.pos * scale) + pos, rot * rhs.rot, scale * rhs.scale }
 	const D3 scaled = d3(LB_DMUL(lpos.x, (double)pscale.x), LB_DMUL(lpos.y, (double)pscale.y), LB_DMUL(lpos.z, (double)pscale.z)); // DVec3 * Vec3, math.cpp:498
 	const D3 gpos = add(rotate(prot, scaled), ppos);
 	const Q4 grot = qmul(prot, q4(lr.x, lr.y, lr.z, lr.w));
@@ -71,6 +69,26 @@ __global__ void __launch_bounds__(HT) propagate_level_kernel(uint32_t begin, uin
 	G.px[i] = gpos.x; G.py[i] = gpos.y; G.pz[i] = gpos.z;
 	G.rot[i] = make_float4(grot.x, grot.y, grot.z, grot.w);
 	G.sx[i] = gscale.x; G.sy[i] = gscale.y; G.sz[i] = gscale.z;
+}
+
+// One depth level: nodes [begin, end) in level order; parents live in earlier levels.
+__global__ void __launch_bounds__(HT) propagate_level_kernel(uint32_t begin, uint32_t end, const int* __restrict__ parent, SoaTransforms L, SoaTransforms G) {
+	const uint32_t i = begin + blockIdx.x * HT + threadIdx.x;
+	if (i >= end) return;
+	compose_node(i, parent, L, G);
+}
+
+// The narrow top of the hierarchy (levels of at most a few thousand nodes) in ONE block: a launch per tiny level would cost
+// more than the level itself.  __syncthreads() orders a level's global writes before the next level's reads.
+constexpr int SMALL_THREADS = 1024;
+constexpr int MAX_SMALL_LEVELS = 30;
+struct SmallLevels { uint32_t start[MAX_SMALL_LEVELS + 1]; uint32_t n; };
+
+__global__ void __launch_bounds__(SMALL_THREADS) propagate_small_levels_kernel(const __grid_constant__ SmallLevels S, const int* __restrict__ parent, SoaTransforms L, SoaTransforms G) {
+	for (uint32_t l = 0; l < S.n; ++l) {
+		for (uint32_t i = S.start[l] + threadIdx.x; i < S.start[l + 1]; i += SMALL_THREADS) compose_node(i, parent, L, G);
+		__syncthreads();
+	}
 }
 
 // render_module.cpp:1544-1554: world bounding sphere of a moved model instance
@@ -219,7 +237,23 @@ int lb200_hierarchy_propagate(lb200_hierarchy* h) {
 	if (!h) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = h->ctx;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
-	for (size_t l = 1; l + 1 < h->level_start.size(); ++l) {
+	const size_t n_levels = h->level_start.size() - 1;
+	size_t l = 1;
+	// levels up to SMALL_LEVEL_NODES nodes run inside one block (no launch per level)
+	const uint32_t SMALL_LEVEL_NODES = 8192;
+	SmallLevels S;
+	S.n = 0;
+	while (l < n_levels && S.n < MAX_SMALL_LEVELS && h->level_start[l + 1] - h->level_start[l] <= SMALL_LEVEL_NODES) {
+		S.start[S.n] = h->level_start[l];
+		S.start[S.n + 1] = h->level_start[l + 1];
+		++S.n;
+		++l;
+	}
+	if (S.n) {
+		propagate_small_levels_kernel<<<1, SMALL_THREADS, 0, ctx->stream>>>(S, h->d_parent, h->L, h->G);
+		LB200_CHECK_LAUNCH(ctx);
+	}
+	for (; l < n_levels; ++l) {
 		const uint32_t begin = h->level_start[l], end = h->level_start[l + 1];
 		if (end == begin) continue;
 		propagate_level_kernel<<<(end - begin + HT - 1) / HT, HT, 0, ctx->stream>>>(begin, end, h->d_parent, h->L, h->G);

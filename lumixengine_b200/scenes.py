@@ -129,8 +129,14 @@ def mesh(skel, n_vertices=5000, seed=6):
     """C4 mesh: 4 influences per vertex, weights normalised from u16 (model.cpp:544-547)."""
     rng = np.random.default_rng(seed)
     B = skel.bone_count
-    home = rng.integers(0, B, n_vertices)
-    idx = np.stack([home, np.maximum(skel.parents[home].astype(np.int64), 0), rng.integers(0, B, n_vertices), rng.integers(0, B, n_vertices)], axis=1)
+    # vertices grouped by the bone they belong to, influences from that bone's neighbourhood (parent, a child, grandparent),
+    # as importers emit them: mesh parts are contiguous and skinned to adjacent bones
+    home = np.sort(rng.integers(0, B, n_vertices))
+    par = np.maximum(skel.parents.astype(np.int64), 0)
+    child = np.arange(B)
+    for b in range(B - 1, 0, -1):
+        child[par[b]] = b  # some child of each bone (itself for leaves)
+    idx = np.stack([home, par[home], child[home], par[par[home]]], axis=1)
     w = rng.random((n_vertices, 4)) * np.array([1.0, 0.6, 0.3, 0.1])
     w = w / w.sum(axis=1, keepdims=True)
     w16 = np.round(w * 65535.0).astype(np.uint16)
