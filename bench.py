@@ -227,8 +227,7 @@ def ours(a, rank, world):
 
     def step_device():
         if world > 1:
-            cs.cull_device(f, want_counts=True)  # the gather needs the per-type counts on the host
-            cs.allgather(slab, world)
+            cs.cull_gather(f, slab)  # cull + device-side pack + one ncclAllGather, no host synchronisation
         else:
             cs.cull_device(f, want_counts=False)
 

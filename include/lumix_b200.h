@@ -47,6 +47,8 @@ LB200_API uint64_t lb200_stream_handle(const lb200_ctx* ctx);
 /* Page-locked host memory for result buffers (the engine would pass memory from its own allocators, registered once). */
 LB200_API void* lb200_host_alloc(lb200_ctx* ctx, size_t bytes);
 LB200_API void lb200_host_free(lb200_ctx* ctx, void* p);
+/* Copy `bytes` from a device pointer handed out by this library (e.g. *out_dev_ids) to host memory, ordered after the context stream. */
+LB200_API int lb200_copy_to_host(lb200_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
 /* Device-time helpers: record a timestamp on the context stream / milliseconds between two of them (CUDA events). */
 LB200_API int lb200_event_create(lb200_ctx* ctx, void** out_event);
 LB200_API int lb200_event_record(lb200_ctx* ctx, void* event);
@@ -162,10 +164,15 @@ LB200_API uint64_t lb200_culling_last_algorithmic_bytes(const lb200_culling* cs)
 LB200_API int lb200_comm_get_unique_id(lb200_ctx* ctx, uint8_t out_id[128]);
 LB200_API int lb200_comm_init(lb200_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]);
 LB200_API void lb200_comm_destroy(lb200_ctx* ctx);
-/* After a cull on every rank: all-gather the per-rank visible lists.  out_counts[r*256 + t] = rank r's count of type t;
- * *out_dev_ids = device pointer to n_ranks slabs of `slab_ids` ids each (rank r's ids at r*slab_ids, laid out as its
- * lb200_cull_result says).  One ncclAllGather of counts + one of the padded id slabs. */
-LB200_API int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_ids, uint32_t* out_counts /* n_ranks*256 */);
+/* Slab layout of the exchange: every rank contributes `256 + slab_ids` u32 words = [256 per-type counts][its visible ids packed type after
+ * type]; the gathered buffer holds n_ranks such slabs back to back (rank r at word r * (256 + slab_ids)).
+ *
+ * lb200_culling_cull_gather: the per-frame multi-GPU step — cull, pack on the device (no host round trip), ONE ncclAllGather of the slabs.
+ * Fully asynchronous on the context stream.  *out_dev_slabs = device pointer of the gathered buffer.
+ * lb200_culling_allgather: the same exchange for the cull that was just issued, plus a read-back of the counts
+ * (out_counts[r*256 + t] = rank r's count of type t) and a stream synchronisation. */
+LB200_API int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t slab_ids, const uint32_t** out_dev_slabs);
+LB200_API int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_slabs, uint32_t* out_counts /* n_ranks*256 */);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hierarchy — replaces the recursion World::transformEntity, src/engine/world.cpp:255-282 (child.global =

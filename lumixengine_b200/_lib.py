@@ -86,7 +86,7 @@ class Mesh(C.Structure):
 # every symbol include/lumix_b200.h declares (tests/test_abi.py checks the header against this and the .so)
 SYMBOLS = [
     "lb200_init", "lb200_shutdown", "lb200_last_error", "lb200_device_count", "lb200_synchronize", "lb200_launch_count", "lb200_stream_handle",
-    "lb200_host_alloc", "lb200_host_free", "lb200_event_create", "lb200_event_record", "lb200_event_elapsed_ms", "lb200_event_destroy",
+    "lb200_host_alloc", "lb200_host_free", "lb200_copy_to_host", "lb200_event_create", "lb200_event_record", "lb200_event_elapsed_ms", "lb200_event_destroy",
     "lb200_frustum_perspective", "lb200_frustum_ortho",
     "lb200_culling_create", "lb200_culling_destroy", "lb200_culling_add", "lb200_culling_remove", "lb200_culling_set_position",
     "lb200_culling_set_radius", "lb200_culling_set", "lb200_culling_get_radius", "lb200_culling_is_added",
@@ -94,7 +94,7 @@ SYMBOLS = [
     "lb200_culling_page_count", "lb200_culling_entity_count", "lb200_culling_get_page",
     "lb200_culling_cull", "lb200_culling_cull_device", "lb200_culling_flush", "lb200_culling_read_bitmask", "lb200_culling_set_replicas",
     "lb200_culling_last_algorithmic_bytes",
-    "lb200_comm_get_unique_id", "lb200_comm_init", "lb200_comm_destroy", "lb200_culling_allgather",
+    "lb200_comm_get_unique_id", "lb200_comm_init", "lb200_comm_destroy", "lb200_culling_allgather", "lb200_culling_cull_gather",
     "lb200_hierarchy_create", "lb200_hierarchy_destroy", "lb200_hierarchy_depth", "lb200_hierarchy_set_locals", "lb200_hierarchy_set_root_globals",
     "lb200_hierarchy_propagate", "lb200_hierarchy_get_globals", "lb200_hierarchy_get_spheres", "lb200_hierarchy_algorithmic_bytes",
     "lb200_animation_create", "lb200_animation_destroy", "lb200_animation_set_instances", "lb200_animation_update", "lb200_animation_skin",
@@ -205,6 +205,13 @@ class Context:
             check(ERR_CUDA, self.h)
         buf = (C.c_uint8 * (max(n, 1) * dt.itemsize)).from_address(p)
         return np.frombuffer(buf, dtype=dt, count=n)
+
+    def copy_to_host(self, dev_ptr, n, dtype):
+        """numpy array of n elements read from a device pointer this library handed out."""
+        import numpy as np
+        out = np.empty(n, dtype)
+        check(self.L.lb200_copy_to_host(self.h, ptr(out), vp(dev_ptr), C.c_size_t(out.nbytes)), self.h)
+        return out
 
     def event(self):
         e = vp()

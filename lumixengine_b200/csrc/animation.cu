@@ -32,14 +32,38 @@ struct DevClip {
 	uint32_t pad;
 };
 
+// device-internal forms of the track descriptors: two 128-bit loads per animated track, one per constant track
+struct alignas(16) DevTrack {
+	float min[3]; uint32_t bone_offset;  // bone_index | offset_bits << 16
+	float to_range[3]; uint32_t bits;    // bitsizes[0] | [1] << 8 | [2] << 16 | skipped_channel << 24
+};
+static_assert(sizeof(DevTrack) == 32, "");
+
+struct Track { // unpacked in registers
+	float min[3], to_range[3];
+	uint32_t bone_index, offset_bits, bitsizes[3], skipped_channel;
+};
+
+__device__ __forceinline__ Track load_track(const DevTrack* __restrict__ p) {
+	const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+	const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+	Track t;
+	t.min[0] = __uint_as_float(a.x); t.min[1] = __uint_as_float(a.y); t.min[2] = __uint_as_float(a.z);
+	t.bone_index = a.w & 0xffffu; t.offset_bits = a.w >> 16;
+	t.to_range[0] = __uint_as_float(b.x); t.to_range[1] = __uint_as_float(b.y); t.to_range[2] = __uint_as_float(b.z);
+	t.bitsizes[0] = b.w & 0xffu; t.bitsizes[1] = (b.w >> 8) & 0xffu; t.bitsizes[2] = (b.w >> 16) & 0xffu; t.skipped_channel = b.w >> 24;
+	return t;
+}
+
 struct AnimParams {
 	const DevClip* clips;
-	const lb200_track* tracks;
-	const lb200_const_translation* const_t;
-	const lb200_const_rotation* const_r;
+	const DevTrack* tracks;
+	const float4* const_t;        // xyz value, w = bone index bits
+	const float4* const_r_value;  // quaternion
+	const uint32_t* const_r_bone;
 	const uint32_t* stream; // all bit streams, word-addressed
-	const float* bind7;     // bone_count * 7
-	const float* inv_bind7; // bone_count * 7
+	const float4* bind_pos; const float4* bind_rot;         // Bone::relative_transform
+	const float4* inv_bind_pos; const float4* inv_bind_rot; // inverse bind transforms
 	const short* parents;
 	const unsigned char* level_bones; // bones of depth >= 1 sorted by depth (bone_count <= 196 fits a byte)
 	const uint32_t* level_start;      // [max_level + 2]: level l occupies level_bones[level_start[l] .. level_start[l + 1])
@@ -67,18 +91,36 @@ __device__ __forceinline__ unsigned long long load_u64_unaligned(const uint32_t*
 	return ((unsigned long long)hi << 32) | lo;
 }
 
+// low 32 bits of (v >> s), 0 <= s < 64
+__device__ __forceinline__ uint32_t shr64_lo32(unsigned long long v, uint32_t s) {
+	const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+	return s >= 32u ? (hi >> (s - 32u)) : __funnelshift_r(lo, hi, s);
+}
+__device__ __forceinline__ uint32_t mask32(uint32_t bits) { return bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u); }
+
 // animation.cpp:313-316 unpackChannel: float(min + to_float_range * double(val & mask))
 __device__ __forceinline__ float unpack_channel(unsigned long long val, float mn, float range, uint32_t bits) {
 	const unsigned long long mask = (1ull << bits) - 1ull;
 	return __double2float_rn(LB_DADD((double)mn, LB_DMUL((double)range, __ull2double_rn(val & mask))));
 }
+__device__ __forceinline__ float unpack_channel32(uint32_t field, float mn, float range) {
+	return __double2float_rn(LB_DADD((double)mn, LB_DMUL((double)range, __uint2double_rn(field))));
+}
 
 // animation.cpp:318-334 Animation::getTranslation
-__device__ __forceinline__ V3 get_translation(const uint32_t* __restrict__ stream, uint32_t frame_bits, uint32_t frame, const lb200_track& tr) {
+__device__ __forceinline__ V3 get_translation(const uint32_t* __restrict__ stream, uint32_t frame_bits, uint32_t frame, const Track& tr) {
 	const uint32_t offset = frame_bits * frame + tr.offset_bits;
 	unsigned long long tmp = load_u64_unaligned(stream, offset >> 3);
 	tmp >>= (offset & 7u);
 	V3 r;
+	if ((tr.bitsizes[0] | tr.bitsizes[1] | tr.bitsizes[2]) <= 32u) {
+		// every channel fits 32 bits (always true for importer output): same values, 32-bit integer path
+		const uint32_t s1 = tr.bitsizes[0], s2 = s1 + tr.bitsizes[1];
+		r.x = unpack_channel32((uint32_t)tmp & mask32(tr.bitsizes[0]), tr.min[0], tr.to_range[0]);
+		r.y = unpack_channel32(shr64_lo32(tmp, s1) & mask32(tr.bitsizes[1]), tr.min[1], tr.to_range[1]);
+		r.z = unpack_channel32(shr64_lo32(tmp, s2) & mask32(tr.bitsizes[2]), tr.min[2], tr.to_range[2]);
+		return r;
+	}
 	r.x = unpack_channel(tmp, tr.min[0], tr.to_range[0], tr.bitsizes[0]);
 	tmp >>= tr.bitsizes[0];
 	r.y = unpack_channel(tmp, tr.min[1], tr.to_range[1], tr.bitsizes[1]);
@@ -88,18 +130,26 @@ __device__ __forceinline__ V3 get_translation(const uint32_t* __restrict__ strea
 }
 
 // animation.cpp:51-77 one packed rotation sample -> quaternion (smallest-three)
-__device__ __forceinline__ Q4 unpack_rotation(unsigned long long packed, const lb200_track& tr) {
+__device__ __forceinline__ Q4 unpack_rotation(unsigned long long packed, const Track& tr) {
 	const bool is_negative = (packed & 1ull) != 0;
 	packed >>= 1;
-	const unsigned long long mask_x = (1ull << tr.bitsizes[0]) - 1ull;
-	const unsigned long long mask_y = (1ull << tr.bitsizes[1]) - 1ull;
-	const unsigned long long mask_z = (1ull << tr.bitsizes[2]) - 1ull;
-	const unsigned long long py = packed >> tr.bitsizes[0];
-	const unsigned long long pz = py >> tr.bitsizes[1];
 	V3 v;
-	v.x = LB_FADD(tr.min[0], LB_FMUL(tr.to_range[0], __ull2float_rn(packed & mask_x)));
-	v.y = LB_FADD(tr.min[1], LB_FMUL(tr.to_range[1], __ull2float_rn(py & mask_y)));
-	v.z = LB_FADD(tr.min[2], LB_FMUL(tr.to_range[2], __ull2float_rn(pz & mask_z)));
+	if ((tr.bitsizes[0] | tr.bitsizes[1] | tr.bitsizes[2]) <= 32u) {
+		const uint32_t s1 = tr.bitsizes[0], s2 = s1 + tr.bitsizes[1];
+		v.x = LB_FADD(tr.min[0], LB_FMUL(tr.to_range[0], __uint2float_rn((uint32_t)packed & mask32(tr.bitsizes[0]))));
+		v.y = LB_FADD(tr.min[1], LB_FMUL(tr.to_range[1], __uint2float_rn(shr64_lo32(packed, s1) & mask32(tr.bitsizes[1]))));
+		v.z = LB_FADD(tr.min[2], LB_FMUL(tr.to_range[2], __uint2float_rn(shr64_lo32(packed, s2) & mask32(tr.bitsizes[2]))));
+	}
+	else {
+		const unsigned long long mask_x = (1ull << tr.bitsizes[0]) - 1ull;
+		const unsigned long long mask_y = (1ull << tr.bitsizes[1]) - 1ull;
+		const unsigned long long mask_z = (1ull << tr.bitsizes[2]) - 1ull;
+		const unsigned long long py = packed >> tr.bitsizes[0];
+		const unsigned long long pz = py >> tr.bitsizes[1];
+		v.x = LB_FADD(tr.min[0], LB_FMUL(tr.to_range[0], __ull2float_rn(packed & mask_x)));
+		v.y = LB_FADD(tr.min[1], LB_FMUL(tr.to_range[1], __ull2float_rn(py & mask_y)));
+		v.z = LB_FADD(tr.min[2], LB_FMUL(tr.to_range[2], __ull2float_rn(pz & mask_z)));
+	}
 	const float rem = LB_FSUB(1.0f, dot(v, v));
 	const float skipped = LB_FMUL(LB_FSQRT(rem > 0.f ? rem : 0.f), is_negative ? -1.0f : 1.0f); // maximum(0.f, x): 0 > x ? 0 : x
 	switch (tr.skipped_channel) {
@@ -145,26 +195,24 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 
 		// Model::getRelativePose, model.cpp:226-237
 		for (uint32_t b = sub; b < B; b += G) {
-			const float* src = P.bind7 + (size_t)b * 7;
-			s_pos[b] = make_float4(src[0], src[1], src[2], 0.f);
-			s_rot[b] = make_float4(src[3], src[4], src[5], src[6]);
+			s_pos[b] = __ldg(P.bind_pos + b);
+			s_rot[b] = __ldg(P.bind_rot + b);
 		}
 		__syncwarp(gmask);
 		// animation.cpp:135-149 constant translations
 		for (uint32_t i = sub; i < clip.n_ct; i += G) {
-			const lb200_const_translation ct = P.const_t[clip.ct_off + i];
-			s_pos[ct.bone_index] = make_float4(ct.value[0], ct.value[1], ct.value[2], 0.f);
+			const float4 ct = __ldg(P.const_t + clip.ct_off + i);
+			s_pos[__float_as_uint(ct.w)] = ct;
 		}
 		// :169-183 constant rotations
 		for (uint32_t i = sub; i < clip.n_cr; i += G) {
-			const lb200_const_rotation cr = P.const_r[clip.cr_off + i];
-			s_rot[cr.bone_index] = make_float4(cr.value[0], cr.value[1], cr.value[2], cr.value[3]);
+			s_rot[__ldg(P.const_r_bone + clip.cr_off + i)] = __ldg(P.const_r_value + clip.cr_off + i);
 		}
 		__syncwarp(gmask);
 		// :151-167 animated translations
 		const uint32_t* t_stream = P.stream + (clip.t_stream >> 2);
 		for (uint32_t i = sub; i < clip.n_t; i += G) {
-			const lb200_track tr = P.tracks[clip.t_off + i];
+			const Track tr = load_track(P.tracks + clip.t_off + i);
 			const V3 a = get_translation(t_stream, clip.t_bits, sample_idx, tr);
 			const V3 b = get_translation(t_stream, clip.t_bits, sample_idx + 1, tr);
 			const V3 p = lerp(a, b, t);
@@ -173,7 +221,7 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 		// :185-203 animated rotations
 		const uint32_t* r_stream = P.stream + (clip.r_stream >> 2);
 		for (uint32_t i = sub; i < clip.n_r; i += G) {
-			const lb200_track tr = P.tracks[clip.r_off + i];
+			const Track tr = load_track(P.tracks + clip.r_off + i);
 			const uint32_t offset1 = clip.r_bits * sample_idx + tr.offset_bits;
 			const uint32_t offset2 = offset1 + clip.r_bits;
 			unsigned long long p1 = load_u64_unaligned(r_stream, offset1 >> 3);
@@ -208,10 +256,10 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 			Rigid pose;
 			pose.pos = v3(cp.x, cp.y, cp.z);
 			pose.rot = q4(cr.x, cr.y, cr.z, cr.w);
-			const float* ib = P.inv_bind7 + (size_t)b * 7;
+			const float4 ip = __ldg(P.inv_bind_pos + b), ir = __ldg(P.inv_bind_rot + b);
 			Rigid inv;
-			inv.pos = v3(ib[0], ib[1], ib[2]);
-			inv.rot = q4(ib[3], ib[4], ib[5], ib[6]);
+			inv.pos = v3(ip.x, ip.y, ip.z);
+			inv.rot = q4(ir.x, ir.y, ir.z, ir.w);
 			const Rigid skin = rmul(pose, inv);
 			const size_t idx = (size_t)inst * B + b;
 			if (P.out_dq) {
@@ -307,11 +355,12 @@ struct lb200_animation {
 	lb200_ctx* ctx = nullptr;
 	uint32_t bone_count = 0, max_level = 0, n_clips = 0, max_instances = 0, n_instances = 0, n_vertices = 0;
 	DevClip* d_clips = nullptr;
-	lb200_track* d_tracks = nullptr;
-	lb200_const_translation* d_const_t = nullptr;
-	lb200_const_rotation* d_const_r = nullptr;
+	DevTrack* d_tracks = nullptr;
+	float4* d_const_t = nullptr;
+	float4* d_const_r_value = nullptr;
+	uint32_t* d_const_r_bone = nullptr;
 	uint32_t* d_stream = nullptr;
-	float* d_bind7 = nullptr; float* d_inv_bind7 = nullptr;
+	float4* d_bind = nullptr; // bind_pos[B], bind_rot[B], inv_bind_pos[B], inv_bind_rot[B]
 	short* d_parents = nullptr; unsigned char* d_level_bones = nullptr; uint32_t* d_level_start = nullptr;
 	int lanes_per_instance = 8;
 	uint32_t* d_clip_index = nullptr; uint32_t* d_time = nullptr;
@@ -361,9 +410,17 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		if (cost < best_cost) { best_cost = cost; best_g = g; }
 	}
 	std::vector<DevClip> dc(n_clips);
-	std::vector<lb200_track> tracks;
-	std::vector<lb200_const_translation> cts;
-	std::vector<lb200_const_rotation> crs;
+	std::vector<DevTrack> tracks;
+	std::vector<float4> cts, cr_values;
+	std::vector<uint32_t> cr_bones;
+	auto packTrack = [](const lb200_track& t) {
+		DevTrack d;
+		memcpy(d.min, t.min, sizeof(d.min));
+		memcpy(d.to_range, t.to_range, sizeof(d.to_range));
+		d.bone_offset = (uint32_t)t.bone_index | ((uint32_t)t.offset_bits << 16);
+		d.bits = (uint32_t)t.bitsizes[0] | ((uint32_t)t.bitsizes[1] << 8) | ((uint32_t)t.bitsizes[2] << 16) | ((uint32_t)t.skipped_channel << 24);
+		return d;
+	};
 	std::vector<uint32_t> stream;
 	auto appendStream = [&](const uint8_t* data, uint32_t bytes) -> uint32_t {
 		const uint32_t off = (uint32_t)stream.size() * 4;
@@ -381,13 +438,13 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		d.t_bits = s.translations_frame_size_bits; d.r_bits = s.rotations_frame_size_bits;
 		d.n_t = s.n_translations; d.n_ct = s.n_const_translations; d.n_r = s.n_rotations; d.n_cr = s.n_const_rotations;
 		d.t_off = (uint32_t)tracks.size();
-		for (uint32_t i = 0; i < s.n_translations; ++i) { if (s.translations[i].bone_index >= B) return LB200_ERR_INVALID; tracks.push_back(s.translations[i]); }
+		for (uint32_t i = 0; i < s.n_translations; ++i) { if (s.translations[i].bone_index >= B) return LB200_ERR_INVALID; tracks.push_back(packTrack(s.translations[i])); }
 		d.r_off = (uint32_t)tracks.size();
-		for (uint32_t i = 0; i < s.n_rotations; ++i) { if (s.rotations[i].bone_index >= B || s.rotations[i].skipped_channel > 3) return LB200_ERR_INVALID; tracks.push_back(s.rotations[i]); }
+		for (uint32_t i = 0; i < s.n_rotations; ++i) { if (s.rotations[i].bone_index >= B || s.rotations[i].skipped_channel > 3) return LB200_ERR_INVALID; tracks.push_back(packTrack(s.rotations[i])); }
 		d.ct_off = (uint32_t)cts.size();
-		for (uint32_t i = 0; i < s.n_const_translations; ++i) { if (s.const_translations[i].bone_index >= B) return LB200_ERR_INVALID; cts.push_back(s.const_translations[i]); }
-		d.cr_off = (uint32_t)crs.size();
-		for (uint32_t i = 0; i < s.n_const_rotations; ++i) { if (s.const_rotations[i].bone_index >= B) return LB200_ERR_INVALID; crs.push_back(s.const_rotations[i]); }
+		for (uint32_t i = 0; i < s.n_const_translations; ++i) { if (s.const_translations[i].bone_index >= B) return LB200_ERR_INVALID; const lb200_const_translation& c0 = s.const_translations[i]; cts.push_back(make_float4(c0.value[0], c0.value[1], c0.value[2], __builtin_bit_cast(float, (uint32_t)c0.bone_index))); }
+		d.cr_off = (uint32_t)cr_values.size();
+		for (uint32_t i = 0; i < s.n_const_rotations; ++i) { if (s.const_rotations[i].bone_index >= B) return LB200_ERR_INVALID; const lb200_const_rotation& c0 = s.const_rotations[i]; cr_values.push_back(make_float4(c0.value[0], c0.value[1], c0.value[2], c0.value[3])); cr_bones.push_back(c0.bone_index); }
 		// streams must hold (frame_count + 1) frames + the loader's 8-byte tail (animation.cpp:439)
 		const uint64_t need_t = s.n_translations ? ((uint64_t)d.t_bits * (s.frame_count + 1) + 7) / 8 : 0;
 		const uint64_t need_r = s.n_rotations ? ((uint64_t)d.r_bits * (s.frame_count + 1) + 7) / 8 : 0;
@@ -404,12 +461,21 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	a->ctx = ctx; a->bone_count = B; a->max_level = max_level; a->n_clips = n_clips; a->max_instances = max_instances;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	ANIM_MALLOC(a->d_clips, sizeof(DevClip) * n_clips);
-	ANIM_MALLOC(a->d_tracks, sizeof(lb200_track) * tracks.size());
-	ANIM_MALLOC(a->d_const_t, sizeof(lb200_const_translation) * cts.size());
-	ANIM_MALLOC(a->d_const_r, sizeof(lb200_const_rotation) * crs.size());
+	ANIM_MALLOC(a->d_tracks, sizeof(DevTrack) * tracks.size());
+	ANIM_MALLOC(a->d_const_t, sizeof(float4) * cts.size());
+	ANIM_MALLOC(a->d_const_r_value, sizeof(float4) * cr_values.size());
+	ANIM_MALLOC(a->d_const_r_bone, sizeof(uint32_t) * cr_bones.size());
 	ANIM_MALLOC(a->d_stream, sizeof(uint32_t) * stream.size());
-	ANIM_MALLOC(a->d_bind7, sizeof(float) * 7 * B);
-	ANIM_MALLOC(a->d_inv_bind7, sizeof(float) * 7 * B);
+	ANIM_MALLOC(a->d_bind, sizeof(float4) * 4 * B);
+	std::vector<float4> bind(4 * (size_t)B);
+	for (uint32_t i = 0; i < B; ++i) {
+		const float* r = sk->bind_relative7 + 7 * (size_t)i;
+		const float* v = sk->inverse_bind7 + 7 * (size_t)i;
+		bind[i] = make_float4(r[0], r[1], r[2], 0.f);
+		bind[B + i] = make_float4(r[3], r[4], r[5], r[6]);
+		bind[2 * B + i] = make_float4(v[0], v[1], v[2], 0.f);
+		bind[3 * B + i] = make_float4(v[3], v[4], v[5], v[6]);
+	}
 	ANIM_MALLOC(a->d_parents, sizeof(short) * B);
 	ANIM_MALLOC(a->d_level_bones, level_bones.size());
 	ANIM_MALLOC(a->d_level_start, sizeof(uint32_t) * level_start.size());
@@ -419,12 +485,12 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	ANIM_MALLOC(a->d_checksum, sizeof(unsigned long long));
 	cudaStream_t st = ctx->stream;
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_clips, dc.data(), sizeof(DevClip) * n_clips, cudaMemcpyHostToDevice, st));
-	if (!tracks.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_tracks, tracks.data(), sizeof(lb200_track) * tracks.size(), cudaMemcpyHostToDevice, st));
-	if (!cts.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_const_t, cts.data(), sizeof(lb200_const_translation) * cts.size(), cudaMemcpyHostToDevice, st));
-	if (!crs.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_const_r, crs.data(), sizeof(lb200_const_rotation) * crs.size(), cudaMemcpyHostToDevice, st));
+	if (!tracks.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_tracks, tracks.data(), sizeof(DevTrack) * tracks.size(), cudaMemcpyHostToDevice, st));
+	if (!cts.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_const_t, cts.data(), sizeof(float4) * cts.size(), cudaMemcpyHostToDevice, st));
+	if (!cr_values.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_const_r_value, cr_values.data(), sizeof(float4) * cr_values.size(), cudaMemcpyHostToDevice, st));
+	if (!cr_bones.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_const_r_bone, cr_bones.data(), sizeof(uint32_t) * cr_bones.size(), cudaMemcpyHostToDevice, st));
 	if (!stream.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_stream, stream.data(), sizeof(uint32_t) * stream.size(), cudaMemcpyHostToDevice, st));
-	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_bind7, sk->bind_relative7, sizeof(float) * 7 * B, cudaMemcpyHostToDevice, st));
-	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_inv_bind7, sk->inverse_bind7, sizeof(float) * 7 * B, cudaMemcpyHostToDevice, st));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_bind, bind.data(), sizeof(float4) * bind.size(), cudaMemcpyHostToDevice, st));
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_parents, sk->parents, sizeof(short) * B, cudaMemcpyHostToDevice, st));
 	if (!level_bones.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(a->d_level_bones, level_bones.data(), level_bones.size(), cudaMemcpyHostToDevice, st));
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_level_start, level_start.data(), sizeof(uint32_t) * level_start.size(), cudaMemcpyHostToDevice, st));
@@ -454,8 +520,8 @@ void lb200_animation_destroy(lb200_animation* a) {
 	if (!a) return;
 	cudaSetDevice(a->ctx->device);
 	cudaStreamSynchronize(a->ctx->stream);
-	cudaFree(a->d_clips); cudaFree(a->d_tracks); cudaFree(a->d_const_t); cudaFree(a->d_const_r); cudaFree(a->d_stream);
-	cudaFree(a->d_bind7); cudaFree(a->d_inv_bind7); cudaFree(a->d_parents); cudaFree(a->d_level_bones); cudaFree(a->d_level_start);
+	cudaFree(a->d_clips); cudaFree(a->d_tracks); cudaFree(a->d_const_t); cudaFree(a->d_const_r_value); cudaFree(a->d_const_r_bone); cudaFree(a->d_stream);
+	cudaFree(a->d_bind); cudaFree(a->d_parents); cudaFree(a->d_level_bones); cudaFree(a->d_level_start);
 	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot);
 	cudaFree(a->d_mesh_pos); cudaFree(a->d_mesh_w); cudaFree(a->d_mesh_idx); cudaFree(a->d_skinned); cudaFree(a->d_checksum);
 	delete a;
@@ -483,8 +549,8 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	if ((flags & LB200_PALETTE_MATRIX) && !a->d_mtx) ANIM_MALLOC(a->d_mtx, sizeof(float) * 16 * nb);
 	if ((flags & LB200_PALETTE_POSE) && !a->d_pos) { ANIM_MALLOC(a->d_pos, sizeof(float) * 3 * nb); ANIM_MALLOC(a->d_rot, sizeof(float) * 4 * nb); }
 	AnimParams P;
-	P.clips = a->d_clips; P.tracks = a->d_tracks; P.const_t = a->d_const_t; P.const_r = a->d_const_r; P.stream = a->d_stream;
-	P.bind7 = a->d_bind7; P.inv_bind7 = a->d_inv_bind7; P.parents = a->d_parents; P.level_bones = a->d_level_bones; P.level_start = a->d_level_start;
+	P.clips = a->d_clips; P.tracks = a->d_tracks; P.const_t = a->d_const_t; P.const_r_value = a->d_const_r_value; P.const_r_bone = a->d_const_r_bone; P.stream = a->d_stream;
+	P.bind_pos = a->d_bind; P.bind_rot = a->d_bind + a->bone_count; P.inv_bind_pos = a->d_bind + 2 * a->bone_count; P.inv_bind_rot = a->d_bind + 3 * a->bone_count; P.parents = a->d_parents; P.level_bones = a->d_level_bones; P.level_start = a->d_level_start;
 	P.bone_count = a->bone_count; P.max_level = a->max_level; P.n_instances = a->n_instances;
 	P.clip_index = a->d_clip_index; P.time_ticks = a->d_time;
 	P.out_dq = (flags & LB200_PALETTE_DUAL_QUAT) ? a->d_dq : nullptr;

@@ -26,14 +26,6 @@ static PFN_ncclCommDestroy p_ncclCommDestroy;
 static PFN_ncclAllGather p_ncclAllGather;
 static PFN_ncclGetErrorString p_ncclGetErrorString;
 
-// from culling.cu
-struct lb200_culling;
-lb200_ctx* lb200_culling_ctx(lb200_culling* cs);
-const uint32_t* lb200_culling_dev_ids(lb200_culling* cs);
-const lb200_cull_result* lb200_culling_last_result(lb200_culling* cs);
-uint32_t** lb200_culling_gather_ids_slot(lb200_culling* cs, size_t** cap);
-uint32_t** lb200_culling_gather_counts_slot(lb200_culling* cs);
-uint32_t** lb200_culling_slab_slot(lb200_culling* cs, size_t** cap);
 
 static int loadNccl(lb200_ctx* ctx) {
 	if (ctx->nccl_lib) return LB200_OK;
@@ -65,6 +57,14 @@ static int loadNccl(lb200_ctx* ctx) {
 			return LB200_ERR_NCCL;                                                                             \
 		}                                                                                                      \
 	} while (0)
+
+// used by culling.cu: all-gather `words` u32 per rank on the context stream (asynchronous)
+int lb200_comm_allgather_u32(lb200_ctx* ctx, const uint32_t* send, uint32_t* recv, size_t words) {
+	if (!ctx->nccl_comm) { lb200_set_error(ctx, "lb200_comm_init has not been called"); return LB200_ERR_STATE; }
+	LB200_NCCL(ctx, p_ncclAllGather(send, recv, words, ncclUint32_dt, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	ctx->launches.fetch_add(1, std::memory_order_relaxed);
+	return LB200_OK;
+}
 
 extern "C" {
 
@@ -101,58 +101,6 @@ void lb200_comm_destroy(lb200_ctx* ctx) {
 	ctx->nccl_comm = nullptr;
 	ctx->n_ranks = 1;
 	ctx->rank = 0;
-}
-
-int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_ids, uint32_t* out_counts) {
-	if (!cs) return LB200_ERR_INVALID;
-	lb200_ctx* ctx = lb200_culling_ctx(cs);
-	if (!ctx) return LB200_ERR_NO_DEVICE;
-	if (!ctx->nccl_comm) { lb200_set_error(ctx, "lb200_comm_init has not been called"); return LB200_ERR_STATE; }
-	const lb200_cull_result* last = lb200_culling_last_result(cs);
-	if (!last) { lb200_set_error(ctx, "allgather needs a preceding cull with counts"); return LB200_ERR_STATE; }
-	const int R = ctx->n_ranks;
-	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
-
-	size_t* ids_cap = nullptr;
-	uint32_t** d_ids = lb200_culling_gather_ids_slot(cs, &ids_cap);
-	uint32_t** d_counts = lb200_culling_gather_counts_slot(cs);
-	size_t* slab_cap = nullptr;
-	uint32_t** d_slab = lb200_culling_slab_slot(cs, &slab_cap);
-	if (!*d_counts) LB200_CUDA(ctx, cudaMalloc(d_counts, sizeof(uint32_t) * 256 * (size_t)(R + 1)));
-	if (*ids_cap < (size_t)slab_ids * R) {
-		cudaFree(*d_ids);
-		*d_ids = nullptr;
-		LB200_CUDA(ctx, cudaMalloc(d_ids, sizeof(uint32_t) * (size_t)slab_ids * R));
-		*ids_cap = (size_t)slab_ids * R;
-	}
-	if (*slab_cap < slab_ids) {
-		cudaFree(*d_slab);
-		*d_slab = nullptr;
-		LB200_CUDA(ctx, cudaMalloc(d_slab, sizeof(uint32_t) * (size_t)slab_ids));
-		*slab_cap = slab_ids;
-	}
-	// pack this rank's per-type segments contiguously into the send slab
-	uint32_t off = 0;
-	const uint32_t* src = lb200_culling_dev_ids(cs);
-	uint32_t packed_counts[256];
-	for (int t = 0; t < 256; ++t) {
-		packed_counts[t] = last->type_count[t];
-		if (!last->type_count[t]) continue;
-		if (off + last->type_count[t] > slab_ids) { lb200_set_error(ctx, "slab_ids too small"); return LB200_ERR_CAPACITY; }
-		LB200_CUDA(ctx, cudaMemcpyAsync(*d_slab + off, src + last->type_offset[t], sizeof(uint32_t) * last->type_count[t], cudaMemcpyDeviceToDevice, ctx->stream));
-		off += last->type_count[t];
-	}
-	uint32_t* d_my_counts = *d_counts + 256 * (size_t)R;
-	LB200_CUDA(ctx, cudaMemcpyAsync(d_my_counts, packed_counts, sizeof(packed_counts), cudaMemcpyHostToDevice, ctx->stream));
-	LB200_NCCL(ctx, p_ncclAllGather(d_my_counts, *d_counts, 256, ncclUint32_dt, (ncclComm_t)ctx->nccl_comm, ctx->stream));
-	LB200_NCCL(ctx, p_ncclAllGather(*d_slab, *d_ids, slab_ids, ncclUint32_dt, (ncclComm_t)ctx->nccl_comm, ctx->stream));
-	ctx->launches.fetch_add(2, std::memory_order_relaxed);
-	if (out_counts) {
-		LB200_CUDA(ctx, cudaMemcpyAsync(out_counts, *d_counts, sizeof(uint32_t) * 256 * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
-	}
-	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	if (out_dev_ids) *out_dev_ids = *d_ids;
-	return LB200_OK;
 }
 
 } // extern "C"

@@ -84,6 +84,14 @@ void lb200_host_free(lb200_ctx* ctx, void* p) {
 	if (p) cudaFreeHost(p);
 }
 
+int lb200_copy_to_host(lb200_ctx* ctx, void* dst_host, const void* src_device, size_t bytes) {
+	if (!ctx || (bytes && (!dst_host || !src_device))) return LB200_ERR_INVALID;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	LB200_CUDA(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
 int lb200_event_create(lb200_ctx* ctx, void** out_event) {
 	if (!ctx || !out_event) return LB200_ERR_INVALID;
 	cudaEvent_t e;

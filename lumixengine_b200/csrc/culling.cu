@@ -40,6 +40,34 @@ __global__ void __launch_bounds__(256) scatter_pages_kernel(const uint32_t* __re
 	if (threadIdx.x < 2) reinterpret_cast<int4*>(desc + p)[threadIdx.x] = reinterpret_cast<const int4*>(st_desc + i)[threadIdx.x];
 }
 
+// Pack this rank's visible ids (per-type segments of out_ids) behind a 256-word header of per-type counts: the send slab of the
+// multi-GPU exchange.  Reads the counters on the device: no host round trip between the cull and the all-gather.
+struct PackParams { uint32_t type_base[256]; uint32_t slab_ids; };
+
+__global__ void __launch_bounds__(256) pack_slab_kernel(const __grid_constant__ PackParams P, const uint32_t* __restrict__ counters,
+	const uint32_t* __restrict__ out_ids, uint32_t* __restrict__ slab)
+{
+	__shared__ uint32_t s_cnt[256];
+	__shared__ uint32_t s_off[257];
+	s_cnt[threadIdx.x] = counters[threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int t = 0; t < 256; ++t) { s_off[t] = acc; acc += s_cnt[t]; }
+		s_off[256] = acc;
+	}
+	__syncthreads();
+	if (blockIdx.x == 0) slab[threadIdx.x] = s_cnt[threadIdx.x];
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	for (int t = 0; t < 256; ++t) {
+		const uint32_t c = s_cnt[t];
+		if (!c) continue;
+		const uint32_t* src = out_ids + P.type_base[t];
+		const uint32_t off = s_off[t];
+		for (uint32_t i = gtid; i < c; i += gsize) if (off + i < P.slab_ids) slab[256 + off + i] = src[i];
+	}
+}
+
 void* pinnedAlloc(size_t n) {
 	void* p = nullptr;
 	if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -430,10 +458,81 @@ uint64_t lb200_culling_last_algorithmic_bytes(const lb200_culling* cs) { return 
 
 } // extern "C"
 
-// ---- accessors for comm.cu ----
-lb200_ctx* lb200_culling_ctx(lb200_culling* cs) { return cs->ctx; }
-const uint32_t* lb200_culling_dev_ids(lb200_culling* cs) { return cs->d_out_ids; }
-const lb200_cull_result* lb200_culling_last_result(lb200_culling* cs) { return cs->has_last ? &cs->last : nullptr; }
-uint32_t** lb200_culling_gather_ids_slot(lb200_culling* cs, size_t** cap) { *cap = &cs->gather_ids_cap; return &cs->d_gather_ids; }
-uint32_t** lb200_culling_gather_counts_slot(lb200_culling* cs) { return &cs->d_gather_counts; }
-uint32_t** lb200_culling_slab_slot(lb200_culling* cs, size_t** cap) { *cap = &cs->slab_cap; return &cs->d_slab; }
+// ---- multi-GPU exchange ----
+int lb200_comm_allgather_u32(lb200_ctx* ctx, const uint32_t* send, uint32_t* recv, size_t words); // comm.cu
+
+namespace {
+
+int ensureGather(lb200_culling* cs, uint32_t slab_ids) {
+	lb200_ctx* ctx = cs->ctx;
+	const size_t words = 256 + (size_t)slab_ids;
+	const size_t R = (size_t)ctx->n_ranks;
+	if (cs->slab_cap < words) {
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(cs->d_slab);
+		cs->d_slab = nullptr;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_slab, sizeof(uint32_t) * words));
+		cs->slab_cap = words;
+	}
+	if (cs->gather_ids_cap < words * R) {
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(cs->d_gather_ids);
+		cs->d_gather_ids = nullptr;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_ids, sizeof(uint32_t) * words * R));
+		cs->gather_ids_cap = words * R;
+	}
+	return LB200_OK;
+}
+
+// pack the counters + ids of the cull whose counters live in `cur`, then all-gather the slabs
+int packAndGather(lb200_culling* cs, const uint32_t* cur, uint32_t slab_ids) {
+	lb200_ctx* ctx = cs->ctx;
+	int rc = ensureGather(cs, slab_ids);
+	if (rc) return rc;
+	PackParams PP;
+	memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
+	PP.slab_ids = slab_ids;
+	pack_slab_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, cs->d_slab);
+	LB200_CHECK_LAUNCH(ctx);
+	return lb200_comm_allgather_u32(ctx, cs->d_slab, cs->d_gather_ids, 256 + (size_t)slab_ids);
+}
+
+} // namespace
+
+extern "C" {
+
+int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t slab_ids, const uint32_t** out_dev_slabs) {
+	if (!cs || !frustum) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	if (cs->host.cells.empty()) { lb200_set_error(cs->ctx, "cull_gather on an empty culling system"); return LB200_ERR_STATE; }
+	int rc = launchCull(cs, frustum, type);
+	if (rc) return rc;
+	const uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
+	cs->parity ^= 1;
+	cs->has_last = false;
+	rc = packAndGather(cs, cur, slab_ids);
+	if (rc) return rc;
+	if (out_dev_slabs) *out_dev_slabs = cs->d_gather_ids;
+	return LB200_OK;
+}
+
+int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_ids, uint32_t* out_counts) {
+	if (!cs) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = cs->ctx;
+	if (!ctx) return LB200_ERR_NO_DEVICE;
+	if (!cs->last_pages) { lb200_set_error(ctx, "allgather needs a preceding cull"); return LB200_ERR_STATE; }
+	// the preceding cull's counters: the buffer the next cull will NOT use
+	const uint32_t* cur = cs->d_counters + (size_t)(cs->parity ^ 1) * COUNTER_WORDS;
+	int rc = packAndGather(cs, cur, slab_ids);
+	if (rc) return rc;
+	const size_t words = 256 + (size_t)slab_ids;
+	if (out_counts) {
+		for (int r = 0; r < ctx->n_ranks; ++r)
+			LB200_CUDA(ctx, cudaMemcpyAsync(out_counts + 256 * (size_t)r, cs->d_gather_ids + words * r, sizeof(uint32_t) * 256, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (out_dev_ids) *out_dev_ids = cs->d_gather_ids;
+	return LB200_OK;
+}
+
+} // extern "C"

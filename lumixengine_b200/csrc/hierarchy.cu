@@ -72,10 +72,35 @@ __device__ __forceinline__ void compose_node(uint32_t i, const int* __restrict__
 }
 
 // One depth level: nodes [begin, end) in level order; parents live in earlier levels.
+// Launched with programmatic stream serialization: the block starts while the previous level is still draining, loads its
+// own locals (independent of that level) and only then waits for the parents' globals.
 __global__ void __launch_bounds__(HT) propagate_level_kernel(uint32_t begin, uint32_t end, const int* __restrict__ parent, SoaTransforms L, SoaTransforms G) {
 	const uint32_t i = begin + blockIdx.x * HT + threadIdx.x;
-	if (i >= end) return;
-	compose_node(i, parent, L, G);
+	const bool active = i < end;
+	int p = 0;
+	D3 lpos = d3(0, 0, 0);
+	float4 lr = make_float4(0, 0, 0, 1);
+	V3 lscale = v3(1, 1, 1);
+	if (active) {
+		p = parent[i];
+		lpos = d3(L.px[i], L.py[i], L.pz[i]);
+		lr = L.rot[i];
+		lscale = v3(L.sx[i], L.sy[i], L.sz[i]);
+	}
+	cudaGridDependencySynchronize();
+	if (!active) return;
+	const D3 ppos = d3(G.px[p], G.py[p], G.pz[p]);
+	const float4 pr = G.rot[p];
+	const Q4 prot = q4(pr.x, pr.y, pr.z, pr.w);
+	const V3 pscale = v3(G.sx[p], G.sy[p], G.sz[p]);
+	// math.cpp:801-807 { rot.rotate(rhs.pos * scale) + pos, rot * rhs.rot, scale * rhs.scale }
+	const D3 scaled = d3(LB_DMUL(lpos.x, (double)pscale.x), LB_DMUL(lpos.y, (double)pscale.y), LB_DMUL(lpos.z, (double)pscale.z)); // DVec3 * Vec3, math.cpp:498
+	const D3 gpos = add(rotate(prot, scaled), ppos);
+	const Q4 grot = qmul(prot, q4(lr.x, lr.y, lr.z, lr.w));
+	const V3 gscale = mul(pscale, lscale);
+	G.px[i] = gpos.x; G.py[i] = gpos.y; G.pz[i] = gpos.z;
+	G.rot[i] = make_float4(grot.x, grot.y, grot.z, grot.w);
+	G.sx[i] = gscale.x; G.sy[i] = gscale.y; G.sz[i] = gscale.z;
 }
 
 // The narrow top of the hierarchy (levels of at most a few thousand nodes) in ONE block: a launch per tiny level would cost
@@ -256,7 +281,16 @@ int lb200_hierarchy_propagate(lb200_hierarchy* h) {
 	for (; l < n_levels; ++l) {
 		const uint32_t begin = h->level_start[l], end = h->level_start[l + 1];
 		if (end == begin) continue;
-		propagate_level_kernel<<<(end - begin + HT - 1) / HT, HT, 0, ctx->stream>>>(begin, end, h->d_parent, h->L, h->G);
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3((end - begin + HT - 1) / HT);
+		cfg.blockDim = dim3(HT);
+		cfg.stream = ctx->stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+		LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, propagate_level_kernel, begin, end, (const int*)h->d_parent, h->L, h->G));
 		LB200_CHECK_LAUNCH(ctx);
 	}
 	return LB200_OK;

@@ -202,7 +202,20 @@ class CullingSystem:
         return int(self.L.lb200_culling_last_algorithmic_bytes(self.h))
 
     def allgather(self, slab_ids, n_ranks):
+        """Exchange of the cull just issued: returns (device pointer of the gathered slabs, counts[n_ranks, 256])."""
         counts = np.zeros(n_ranks * 256, np.uint32)
         dev = vp()
         self._err(self.L.lb200_culling_allgather(self.h, C.c_uint32(slab_ids), C.byref(dev), ptr(counts)))
         return (dev.value or 0), counts.reshape(n_ranks, 256)
+
+    def cull_gather(self, frustum, slab_ids, type=TYPE_ALL):
+        """Per-frame multi-GPU step, asynchronous: cull + device-side pack + one NCCL all-gather.  Returns the device pointer."""
+        dev = vp()
+        self._err(self.L.lb200_culling_cull_gather(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(slab_ids), C.byref(dev)))
+        return dev.value or 0
+
+    def read_gathered(self, dev_ptr, slab_ids, n_ranks):
+        """Host copy of the gathered buffer -> (slabs[r] = ids of rank r, counts[n_ranks, 256])."""
+        words = 256 + slab_ids
+        host = self.ctx.copy_to_host(dev_ptr, words * n_ranks, np.uint32).reshape(n_ranks, words)
+        return [host[r, 256:] for r in range(n_ranks)], host[:, :256].copy()
