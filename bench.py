@@ -187,6 +187,7 @@ def ours(a, rank, world):
 
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         import torch
         import torch.distributed as dist
         local = int(os.environ.get("LOCAL_RANK", rank))
@@ -224,6 +225,8 @@ def ours(a, rank, world):
         t = torch.tensor([visible], dtype=torch.int64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         slab = int(t.item()) + 1024
+        if os.environ.get("LB200_NO_P2P") != "1":
+            ctx.comm_enable_p2p(slab)  # per-frame exchange = fused pack + NVLink peer stores + epoch flags (no NCCL call per step)
 
     def step_device():
         if world > 1:
@@ -298,7 +301,7 @@ def ours(a, rank, world):
         "config": {"workload": "C2: 10M static entities, 1 camera frustum cull (BASELINE.json configs[1]); per GPU at N>1", "entities_per_gpu": N_ENTITIES,
                    "visible_per_gpu": int(visible), "pages": cs.page_count(), "frustum": "perspective fov 60deg 16:9 near 0.1 far 4500 at origin looking -z",
                    "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{cs.page_count() * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
-                   "parallelism": f"dp{world}: whole cell pages per rank" + ("; ncclAllGather of the visible lists each step" if world > 1 else ""),
+                   "parallelism": f"dp{world}: whole cell pages per rank" + (("; visible lists exchanged each step: " + ("fused pack + NVLink peer push" if os.environ.get("LB200_NO_P2P") != "1" else "pack + ncclAllGather")) if world > 1 else ""),
                    "scene_build_s": build_s, "page_stats": stats},
         "gpu_launches": int(launches),
         "clocks": clocks,

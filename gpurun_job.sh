@@ -1,12 +1,9 @@
-set -x
 mkdir -p gpurun_out
-nvidia-smi -L
-python -m pytest tests -q -m gpu 2>&1 | tail -8
-python bench.py --steps 200 --warmup 10 > gpurun_out/bench_v4.json 2> gpurun_out/bench_v4.err; tail -c 1500 gpurun_out/bench_v4.err; python -c "
-import json; j=json.load(open('gpurun_out/bench_v4.json'))
-print('cull', j['value'], j['ms_per_step'], j['roofline']['frac'], 'e2e', j['e2e']['value'])
-for k,v in j.get('paths',{}).items(): print(k, v['value'], v['unit'], v['ms_per_step'], v['roofline']['frac'])
-print(j.get('paths_error'))
-"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 1500 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json | cut -c1-1500
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 5 --warmup 3 2>&1 | tail -2 | cut -c1-600
+timeout 600 python -m pytest tests/test_multi_gpu.py -q -m gpu -x 2>&1 | tail -15
+for mode in 0 1; do
+LB200_NO_P2P=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$mode bench.py --gpus 2 --steps 100 --warmup 5 > gpurun_out/bench_n2_$mode.json 2> gpurun_out/bench_n2_$mode.err; echo "rc=$?"; tail -c 600 gpurun_out/bench_n2_$mode.err; python -c "
+import json
+for l in open('gpurun_out/bench_n2_$mode.json'):
+    if l.startswith('{'):
+        j=json.loads(l); print('N2 nop2p=$mode', j['value'], j['ms_per_step'], j['gpu_launches'], j['config']['parallelism'])"
+done

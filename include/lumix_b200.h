@@ -164,6 +164,10 @@ LB200_API uint64_t lb200_culling_last_algorithmic_bytes(const lb200_culling* cs)
 LB200_API int lb200_comm_get_unique_id(lb200_ctx* ctx, uint8_t out_id[128]);
 LB200_API int lb200_comm_init(lb200_ctx* ctx, int n_ranks, int rank, const uint8_t unique_id[128]);
 LB200_API void lb200_comm_destroy(lb200_ctx* ctx);
+/* Optional, collective (every rank, same argument): map every rank's gather buffers into every process over NVLink peer access
+ * (CUDA IPC).  After it lb200_culling_cull_gather pushes each rank's slab straight into its peers' memory from one fused kernel
+ * and synchronises with per-epoch flags instead of calling NCCL on the per-frame path.  Up to 8 ranks (one NVSwitch box). */
+LB200_API int lb200_comm_enable_p2p(lb200_ctx* ctx, uint32_t max_slab_ids);
 /* Slab layout of the exchange: every rank contributes `256 + slab_ids` u32 words = [256 per-type counts][its visible ids packed type after
  * type]; the gathered buffer holds n_ranks such slabs back to back (rank r at word r * (256 + slab_ids)).
  *
@@ -173,6 +177,9 @@ LB200_API void lb200_comm_destroy(lb200_ctx* ctx);
  * (out_counts[r*256 + t] = rank r's count of type t) and a stream synchronisation. */
 LB200_API int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t slab_ids, const uint32_t** out_dev_slabs);
 LB200_API int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_slabs, uint32_t* out_counts /* n_ranks*256 */);
+/* Distance in u32 words between consecutive ranks' slabs inside the buffer lb200_culling_cull_gather returns for this slab_ids
+ * (256 + slab_ids on the NCCL path, the fixed peer-buffer stride after lb200_comm_enable_p2p). */
+LB200_API uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, uint32_t slab_ids);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hierarchy — replaces the recursion World::transformEntity, src/engine/world.cpp:255-282 (child.global =

@@ -94,7 +94,7 @@ SYMBOLS = [
     "lb200_culling_page_count", "lb200_culling_entity_count", "lb200_culling_get_page",
     "lb200_culling_cull", "lb200_culling_cull_device", "lb200_culling_flush", "lb200_culling_read_bitmask", "lb200_culling_set_replicas",
     "lb200_culling_last_algorithmic_bytes",
-    "lb200_comm_get_unique_id", "lb200_comm_init", "lb200_comm_destroy", "lb200_culling_allgather", "lb200_culling_cull_gather",
+    "lb200_comm_get_unique_id", "lb200_comm_init", "lb200_comm_destroy", "lb200_comm_enable_p2p", "lb200_culling_gather_stride_words", "lb200_culling_allgather", "lb200_culling_cull_gather",
     "lb200_hierarchy_create", "lb200_hierarchy_destroy", "lb200_hierarchy_depth", "lb200_hierarchy_set_locals", "lb200_hierarchy_set_root_globals",
     "lb200_hierarchy_propagate", "lb200_hierarchy_get_globals", "lb200_hierarchy_get_spheres", "lb200_hierarchy_algorithmic_bytes",
     "lb200_animation_create", "lb200_animation_destroy", "lb200_animation_set_instances", "lb200_animation_update", "lb200_animation_skin",
@@ -126,6 +126,7 @@ def lib():
     L.lb200_culling_get_radius.restype = C.c_float
     L.lb200_culling_page_count.restype = C.c_uint32
     L.lb200_culling_entity_count.restype = C.c_uint32
+    L.lb200_culling_gather_stride_words.restype = C.c_uint32
     L.lb200_culling_last_algorithmic_bytes.restype = C.c_uint64
     L.lb200_hierarchy_depth.restype = C.c_uint32
     L.lb200_hierarchy_algorithmic_bytes.restype = C.c_uint64
@@ -237,6 +238,10 @@ class Context:
         import numpy as np
         uid = np.ascontiguousarray(unique_id, np.uint8)
         check(self.L.lb200_comm_init(self.h, C.c_int(n_ranks), C.c_int(rank), ptr(uid)), self.h)
+
+    def comm_enable_p2p(self, max_slab_ids):
+        """Collective: NVLink peer exchange for cull_gather (lb200_comm_enable_p2p)."""
+        check(self.L.lb200_comm_enable_p2p(self.h, C.c_uint32(max_slab_ids)), self.h)
 
 
 def device_count():

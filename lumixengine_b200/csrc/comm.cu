@@ -93,10 +93,70 @@ int lb200_comm_init(lb200_ctx* ctx, int n_ranks, int rank, const uint8_t unique_
 	return LB200_OK;
 }
 
+// Map every rank's gather buffers into every process (CUDA IPC over NVLink peer access).  Collective: all ranks call it with the same
+// max_slab_ids.  The IPC handles travel through one ncclAllGather, so the caller needs no extra side channel.
+int lb200_comm_enable_p2p(lb200_ctx* ctx, uint32_t max_slab_ids) {
+	if (!ctx) return LB200_ERR_INVALID;
+	if (!ctx->nccl_comm) { lb200_set_error(ctx, "lb200_comm_init has not been called"); return LB200_ERR_STATE; }
+	const int R = ctx->n_ranks;
+	if (R > LB200_MAX_RANKS) { lb200_set_error(ctx, "peer exchange supports up to %d ranks (one NVSwitch box)", LB200_MAX_RANKS); return LB200_ERR_INVALID; }
+	if (ctx->peer.ready) return LB200_OK;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	lb200_ctx::Peer& P = ctx->peer;
+	P.slab_words = (256 + (size_t)max_slab_ids + 63) & ~(size_t)63;
+	const size_t flag_bytes = 256;
+	const size_t buf_bytes = sizeof(uint32_t) * P.slab_words * (size_t)R;
+	const size_t total = flag_bytes + 2 * buf_bytes;
+	LB200_CUDA(ctx, cudaMalloc(&P.local_block, total));
+	LB200_CUDA(ctx, cudaMemsetAsync(P.local_block, 0, flag_bytes, ctx->stream));
+	LB200_CUDA(ctx, cudaMalloc(&P.done_counter, sizeof(uint32_t)));
+	LB200_CUDA(ctx, cudaMemsetAsync(P.done_counter, 0, sizeof(uint32_t), ctx->stream));
+	cudaIpcMemHandle_t mine;
+	LB200_CUDA(ctx, cudaIpcGetMemHandle(&mine, P.local_block));
+	// exchange the 64-byte handles with NCCL
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "");
+	uint32_t* d_h = nullptr;
+	LB200_CUDA(ctx, cudaMalloc(&d_h, 64 * (size_t)(R + 1)));
+	LB200_CUDA(ctx, cudaMemcpyAsync(d_h + 16 * (size_t)R, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_NCCL(ctx, p_ncclAllGather(d_h + 16 * (size_t)R, d_h, 16, ncclUint32_dt, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	cudaIpcMemHandle_t all[LB200_MAX_RANKS];
+	LB200_CUDA(ctx, cudaMemcpyAsync(all, d_h, 64 * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_h);
+	for (int r = 0; r < R; ++r) {
+		char* base;
+		if (r == ctx->rank) base = (char*)P.local_block;
+		else {
+			void* p = nullptr;
+			LB200_CUDA(ctx, cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+			P.opened[r] = p;
+			base = (char*)p;
+		}
+		P.flags[r] = (uint32_t*)base;
+		P.gather[0][r] = (uint32_t*)(base + flag_bytes);
+		P.gather[1][r] = (uint32_t*)(base + flag_bytes + buf_bytes);
+	}
+	// nobody may start pushing before every rank has mapped every buffer (and zeroed its flags): one more collective as a barrier
+	uint32_t* d_b = nullptr;
+	LB200_CUDA(ctx, cudaMalloc(&d_b, sizeof(uint32_t) * (size_t)(R + 1)));
+	LB200_NCCL(ctx, p_ncclAllGather(d_b + R, d_b, 1, ncclUint32_dt, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_b);
+	P.epoch = 0;
+	P.ready = true;
+	return LB200_OK;
+}
+
 void lb200_comm_destroy(lb200_ctx* ctx) {
 	if (!ctx || !ctx->nccl_comm) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	if (ctx->peer.local_block) {
+		for (int r = 0; r < LB200_MAX_RANKS; ++r) if (ctx->peer.opened[r]) cudaIpcCloseMemHandle(ctx->peer.opened[r]);
+		cudaFree(ctx->peer.local_block);
+		cudaFree(ctx->peer.done_counter);
+		ctx->peer = lb200_ctx::Peer();
+	}
 	p_ncclCommDestroy((ncclComm_t)ctx->nccl_comm);
 	ctx->nccl_comm = nullptr;
 	ctx->n_ranks = 1;

@@ -55,6 +55,13 @@ __device__ __forceinline__ int ldg_stream_i32(const int* p) {
 	return r;
 }
 
+// Ask the L2 to fetch `bytes` (multiple of 16) starting at a 16-byte aligned global address: no registers, no shared memory,
+// nothing to wait on.  Issued by the classify thread the moment a page is known to need its spheres / ids, so that the warps of
+// phases B and D find them in L2 instead of paying a DRAM round trip per page.
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 enum { CLS_SKIP = 0, CLS_COPY = 1, CLS_TEST = 2 };
 
 struct WorkItem {
@@ -133,6 +140,8 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 					}
 					else atomicAdd(&s_stats[ST_PAGES_FILTERED], 1u);
 				}
+				if (cls == CLS_TEST) prefetch_l2(spheres + (size_t)page * LB200_PAGE_SLOTS, count * 16u);
+				else if (cls == CLS_COPY) prefetch_l2(entities + (size_t)page * LB200_PAGE_SLOTS, (count * 4u + 15u) & ~15u);
 				if (cls != CLS_SKIP) {
 					const uint32_t slot = atomicAdd(&s_nwork, 1u);
 					WorkItem it;

@@ -68,6 +68,75 @@ __global__ void __launch_bounds__(256) pack_slab_kernel(const __grid_constant__ 
 	}
 }
 
+// Fused pack + NVLink push: the slab is written straight into every rank's gather buffer through peer-mapped pointers (P2P stores
+// over NVSwitch), then the last block publishes this rank's epoch in every rank's flag block.  No NCCL call on the per-frame path.
+struct PushParams {
+	uint32_t type_base[256];
+	uint32_t slab_ids;
+	uint32_t n_ranks, rank, epoch;
+	uint32_t* dst[LB200_MAX_RANKS];   // rank r's gather buffer of this epoch, already offset to MY slab inside it
+	uint32_t* flags[LB200_MAX_RANKS]; // rank r's flag block: [2][LB200_MAX_RANKS]
+};
+
+__global__ void __launch_bounds__(256) pack_push_kernel(const __grid_constant__ PushParams P, const uint32_t* __restrict__ counters,
+	const uint32_t* __restrict__ out_ids, uint32_t* __restrict__ done_counter)
+{
+	__shared__ uint32_t s_cnt[256];
+	__shared__ uint32_t s_off[257];
+	__shared__ bool s_last;
+	s_cnt[threadIdx.x] = counters[threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int t = 0; t < 256; ++t) { s_off[t] = acc; acc += s_cnt[t]; }
+		s_off[256] = acc;
+	}
+	__syncthreads();
+	if (blockIdx.x == 0) for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][threadIdx.x] = s_cnt[threadIdx.x];
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	for (int t = 0; t < 256; ++t) {
+		const uint32_t c = s_cnt[t];
+		if (!c) continue;
+		const uint32_t* src = out_ids + P.type_base[t];
+		const uint32_t off = s_off[t];
+		const uint32_t lim = min(c, P.slab_ids > off ? P.slab_ids - off : 0u);
+		for (uint32_t i = gtid; i < lim; i += 4 * gsize) {
+			uint32_t v[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) if (i + k * gsize < lim) v[k] = src[i + k * gsize];
+			for (uint32_t r = 0; r < P.n_ranks; ++r) {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) if (i + k * gsize < lim) P.dst[r][256 + off + i + k * gsize] = v[k];
+			}
+		}
+	}
+	// publish: all stores of all blocks must be visible system-wide before the flag
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+	__syncthreads();
+	if (s_last) {
+		__threadfence_system();
+		if (threadIdx.x < P.n_ranks) {
+			volatile uint32_t* f = P.flags[threadIdx.x] + (P.epoch & 1u) * LB200_MAX_RANKS + P.rank;
+			*f = P.epoch;
+		}
+		if (threadIdx.x == 0) *done_counter = 0;
+	}
+}
+
+// Wait until every rank's slab of `epoch` has landed in this rank's gather buffer.  Spins on local memory; gives up after ~4 s.
+__global__ void wait_peers_kernel(const uint32_t* flags, uint32_t n_ranks, uint32_t epoch, uint32_t* timed_out) {
+	if (threadIdx.x < n_ranks) {
+		const volatile uint32_t* f = flags + (epoch & 1u) * LB200_MAX_RANKS + threadIdx.x;
+		const long long t0 = clock64();
+		while ((int)(*f - epoch) < 0) {
+			if (clock64() - t0 > 8000000000ll) { *timed_out = 1; break; }
+		}
+	}
+	__threadfence_system();
+}
+
 void* pinnedAlloc(size_t n) {
 	void* p = nullptr;
 	if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -492,7 +561,7 @@ int packAndGather(lb200_culling* cs, const uint32_t* cur, uint32_t slab_ids) {
 	PackParams PP;
 	memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
 	PP.slab_ids = slab_ids;
-	pack_slab_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, cs->d_slab);
+	pack_slab_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, cs->d_slab);
 	LB200_CHECK_LAUNCH(ctx);
 	return lb200_comm_allgather_u32(ctx, cs->d_slab, cs->d_gather_ids, 256 + (size_t)slab_ids);
 }
@@ -504,16 +573,46 @@ extern "C" {
 int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t slab_ids, const uint32_t** out_dev_slabs) {
 	if (!cs || !frustum) return LB200_ERR_INVALID;
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
-	if (cs->host.cells.empty()) { lb200_set_error(cs->ctx, "cull_gather on an empty culling system"); return LB200_ERR_STATE; }
+	lb200_ctx* ctx = cs->ctx;
+	if (cs->host.cells.empty()) { lb200_set_error(ctx, "cull_gather on an empty culling system"); return LB200_ERR_STATE; }
 	int rc = launchCull(cs, frustum, type);
 	if (rc) return rc;
 	const uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
 	cs->parity ^= 1;
 	cs->has_last = false;
+	lb200_ctx::Peer& peer = ctx->peer;
+	if (peer.ready && 256 + (size_t)slab_ids <= peer.slab_words) {
+		// NVLink peer path: fused pack + push, then wait for the peers' slabs.  Slabs are peer.slab_words apart.
+		const uint32_t epoch = ++peer.epoch;
+		PushParams PP;
+		memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
+		PP.slab_ids = slab_ids;
+		PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = epoch;
+		for (int r = 0; r < LB200_MAX_RANKS; ++r) {
+			PP.dst[r] = r < ctx->n_ranks ? peer.gather[epoch & 1u][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+			PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
+		}
+		pack_push_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, peer.done_counter);
+		LB200_CHECK_LAUNCH(ctx);
+		if (!cs->d_gather_counts) {
+			LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
+			LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
+		}
+		wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, epoch, cs->d_gather_counts);
+		LB200_CHECK_LAUNCH(ctx);
+		if (out_dev_slabs) *out_dev_slabs = peer.gather[epoch & 1u][ctx->rank];
+		return LB200_OK;
+	}
 	rc = packAndGather(cs, cur, slab_ids);
 	if (rc) return rc;
 	if (out_dev_slabs) *out_dev_slabs = cs->d_gather_ids;
 	return LB200_OK;
+}
+
+uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, uint32_t slab_ids) {
+	if (!cs || !cs->ctx) return 0;
+	const lb200_ctx::Peer& peer = cs->ctx->peer;
+	return (peer.ready && 256 + (size_t)slab_ids <= peer.slab_words) ? (uint32_t)peer.slab_words : 256 + slab_ids;
 }
 
 int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_ids, uint32_t* out_counts) {

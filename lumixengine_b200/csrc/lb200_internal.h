@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#define LB200_MAX_RANKS 8
+
 struct lb200_ctx {
 	int device = -1;
 	cudaStream_t stream = nullptr;
@@ -22,6 +24,17 @@ struct lb200_ctx {
 	void* nccl_comm = nullptr;
 	int n_ranks = 1;
 	int rank = 0;
+	// NVLink peer exchange (comm.cu lb200_comm_enable_p2p): every rank's gather buffers mapped into every process
+	struct Peer {
+		bool ready = false;
+		size_t slab_words = 0;            // capacity of one rank's slab (header + ids)
+		void* local_block = nullptr;      // this rank's allocation: [flags 2 x 8 x u32, padded to 256 B][gather 0][gather 1]
+		uint32_t* gather[2][LB200_MAX_RANKS] = {}; // gather[b][r] = rank r's buffer b as seen from this process
+		uint32_t* flags[LB200_MAX_RANKS] = {};     // flags[r] = rank r's flag block
+		void* opened[LB200_MAX_RANKS] = {};        // cudaIpcOpenMemHandle results to close
+		uint32_t* done_counter = nullptr; // local, for the last-block election
+		uint32_t epoch = 0;
+	} peer;
 };
 
 void lb200_set_error(lb200_ctx* ctx, const char* fmt, ...);

@@ -214,8 +214,8 @@ class CullingSystem:
         self._err(self.L.lb200_culling_cull_gather(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(slab_ids), C.byref(dev)))
         return dev.value or 0
 
-    def read_gathered(self, dev_ptr, slab_ids, n_ranks):
+    def read_gathered(self, dev_ptr, slab_ids, n_ranks, stride=None):
         """Host copy of the gathered buffer -> (slabs[r] = ids of rank r, counts[n_ranks, 256])."""
-        words = 256 + slab_ids
-        host = self.ctx.copy_to_host(dev_ptr, words * n_ranks, np.uint32).reshape(n_ranks, words)
-        return [host[r, 256:] for r in range(n_ranks)], host[:, :256].copy()
+        stride = int(self.L.lb200_culling_gather_stride_words(self.h, C.c_uint32(slab_ids))) if stride is None else stride
+        host = self.ctx.copy_to_host(dev_ptr, stride * n_ranks, np.uint32).reshape(n_ranks, stride)
+        return [host[r, 256:256 + slab_ids] for r in range(n_ranks)], host[:, :256].copy()

@@ -44,17 +44,25 @@ def _worker(rank, world, port, q):
     dist.all_reduce(n, op=dist.ReduceOp.MAX)
     slab = int(n.item()) + 64
     dev_ptr, counts = cs.allgather(slab, world)
-    slabs, counts2 = cs.read_gathered(dev_ptr, slab, world)
+    slabs, counts2 = cs.read_gathered(dev_ptr, slab, world, stride=256 + slab)
     assert np.array_equal(counts, counts2)
     merged = sharding.merge_gathered(slabs, counts)
-    # the asynchronous per-frame form gives the same buffer
-    dev2 = cs.cull_gather(f, slab)
-    slabs_b, counts_b = cs.read_gathered(dev2, slab, world)
-    assert np.array_equal(counts_b, counts)
-    for r in range(world):
-        for t in range(3):
-            o = int(counts[r, :t].sum())
-            assert np.array_equal(np.sort(slabs_b[r][o:o + counts[r, t]]), np.sort(slabs[r][o:o + counts[r, t]]))
+    # the asynchronous per-frame form gives the same buffer: first over NCCL, then over the NVLink peer path (several epochs)
+    def check_async():
+        dev2 = cs.cull_gather(f, slab)
+        slabs_b, counts_b = cs.read_gathered(dev2, slab, world)
+        assert np.array_equal(counts_b, counts)
+        for r in range(world):
+            for t in range(3):
+                o = int(counts[r, :t].sum())
+                assert np.array_equal(np.sort(slabs_b[r][o:o + counts[r, t]]), np.sort(slabs[r][o:o + counts[r, t]]))
+    check_async()
+    ctx.comm_enable_p2p(slab)
+    for _ in range(5):
+        check_async()
+    for _ in range(50):  # back-to-back epochs without host synchronisation in between
+        cs.cull_gather(f, slab)
+    check_async()
     ok = True
     if rank == 0:
         from oracle import pyoracle as po
