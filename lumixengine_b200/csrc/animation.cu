@@ -29,7 +29,8 @@ struct DevClip {
 	uint32_t t_off, ct_off, r_off, cr_off; // first element in the flat track arrays
 	uint32_t t_stream, r_stream;      // byte offsets of the bit streams inside the stream blob (multiples of 4)
 	uint32_t length_ticks;            // Animation::getLength(), animation.h:128
-	uint32_t pad;
+	uint32_t key_off;                 // first float4 of this clip's decoded keyframes: [(frame_count + 1)][Bp] entries
+	uint32_t flag_off, pad[3];        // first byte of this clip's per-bone track flags
 };
 
 // device-internal forms of the track descriptors: two 128-bit loads per animated track, one per constant track
@@ -62,6 +63,8 @@ struct AnimParams {
 	const float4* const_r_value;  // quaternion
 	const uint32_t* const_r_bone;
 	const uint32_t* stream; // all bit streams, word-addressed
+	const float4* key_pos; const float4* key_rot; // decoded keyframes (decode_clips_kernel)
+	const unsigned char* key_flags;               // per (clip, bone): bit0 translation animated, bit1 rotation animated
 	const float4* bind_pos; const float4* bind_rot;         // Bone::relative_transform
 	const float4* inv_bind_pos; const float4* inv_bind_rot; // inverse bind transforms
 	const short* parents;
@@ -160,6 +163,59 @@ __device__ __forceinline__ Q4 unpack_rotation(unsigned long long packed, const T
 	}
 }
 
+// Unpack every frame of every clip once (clips are shared by all instances): block = (clip, frame), threads over bones / tracks.
+// Same arithmetic as the per-sample path of the reference: Animation::getTranslation (animation.cpp:318-334, unpackChannel through
+// double) and the smallest-three reconstruction of AnimationSampler::getRotation (animation.cpp:51-77).
+struct DecodeParams {
+	const DevClip* clips;
+	const DevTrack* tracks;
+	const float4* const_t; const float4* const_r_value; const uint32_t* const_r_bone;
+	const uint32_t* stream;
+	const float4* bind_pos; const float4* bind_rot;
+	float4* key_pos; float4* key_rot; unsigned char* key_flags;
+	const uint32_t* frame_clip;  // block -> clip
+	const uint32_t* frame_index; // block -> frame inside the clip
+	uint32_t bone_count;
+};
+
+__global__ void __launch_bounds__(256) decode_clips_kernel(const __grid_constant__ DecodeParams P) {
+	const uint32_t B = P.bone_count, Bp = (B + 3u) & ~3u;
+	const uint32_t c = P.frame_clip[blockIdx.x], frame = P.frame_index[blockIdx.x];
+	const DevClip clip = P.clips[c];
+	float4* kp = P.key_pos + clip.key_off + (size_t)frame * Bp;
+	float4* kr = P.key_rot + clip.key_off + (size_t)frame * Bp;
+	unsigned char* kf = P.key_flags + clip.flag_off;
+	for (uint32_t b = threadIdx.x; b < Bp; b += blockDim.x) {
+		kp[b] = b < B ? P.bind_pos[b] : make_float4(0, 0, 0, 0);
+		kr[b] = b < B ? P.bind_rot[b] : make_float4(0, 0, 0, 1);
+		if (frame == 0) kf[b] = 0;
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < clip.n_ct; i += blockDim.x) {
+		const float4 ct = P.const_t[clip.ct_off + i];
+		kp[__float_as_uint(ct.w)] = make_float4(ct.x, ct.y, ct.z, 0.f);
+	}
+	for (uint32_t i = threadIdx.x; i < clip.n_cr; i += blockDim.x) kr[P.const_r_bone[clip.cr_off + i]] = P.const_r_value[clip.cr_off + i];
+	__syncthreads();
+	const uint32_t* t_stream = P.stream + (clip.t_stream >> 2);
+	for (uint32_t i = threadIdx.x; i < clip.n_t; i += blockDim.x) {
+		const Track tr = load_track(P.tracks + clip.t_off + i);
+		const V3 v = get_translation(t_stream, clip.t_bits, frame, tr);
+		kp[tr.bone_index] = make_float4(v.x, v.y, v.z, 0.f);
+		if (frame == 0) atomicOr(reinterpret_cast<unsigned int*>(kf + (tr.bone_index & ~3u)), 1u << (8u * (tr.bone_index & 3u)));
+	}
+	const uint32_t* r_stream = P.stream + (clip.r_stream >> 2);
+	for (uint32_t i = threadIdx.x; i < clip.n_r; i += blockDim.x) {
+		const Track tr = load_track(P.tracks + clip.r_off + i);
+		const uint32_t offset = clip.r_bits * frame + tr.offset_bits;
+		unsigned long long p = load_u64_unaligned(r_stream, offset >> 3);
+		p >>= (offset & 7u);
+		const Q4 q = unpack_rotation(p, tr);
+		kr[tr.bone_index] = make_float4(q.x, q.y, q.z, q.w);
+		if (frame == 0) atomicOr(reinterpret_cast<unsigned int*>(kf + (tr.bone_index & ~3u)), 2u << (8u * (tr.bone_index & 3u)));
+	}
+}
+
 constexpr int POSE_THREADS = 128;
 
 // G lanes cooperate on one instance (32 / G instances per warp): per-bone phases stride the bones by G, the absolute pass
@@ -193,43 +249,29 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 		const uint32_t sample_idx = (uint32_t)sample;
 		const float t = LB_FSUB(sample, __uint2float_rn(sample_idx));
 
-		// Model::getRelativePose, model.cpp:226-237
+		// Model::getRelativePose (model.cpp:226-237) + Animation::getRelativePose (animation.cpp:117-204) from the decoded keyframes:
+		// the two frames of a track do not depend on the instance, so they were unpacked once per clip (decode_clips_kernel) with the
+		// reference's arithmetic; here only the per-instance part remains: lerp (math.cpp:194-201) / simd_nlerp (simd_math.h:107-123)
+		// for animated tracks, plain copy for constant tracks and untracked bones (which keep the bind pose).
+		const float4* k0p = P.key_pos + clip.key_off + (size_t)sample_idx * Bp;
+		const float4* k0r = P.key_rot + clip.key_off + (size_t)sample_idx * Bp;
+		const unsigned char* kf = P.key_flags + clip.flag_off;
 		for (uint32_t b = sub; b < B; b += G) {
-			s_pos[b] = __ldg(P.bind_pos + b);
-			s_rot[b] = __ldg(P.bind_rot + b);
-		}
-		__syncwarp(gmask);
-		// animation.cpp:135-149 constant translations
-		for (uint32_t i = sub; i < clip.n_ct; i += G) {
-			const float4 ct = __ldg(P.const_t + clip.ct_off + i);
-			s_pos[__float_as_uint(ct.w)] = ct;
-		}
-		// :169-183 constant rotations
-		for (uint32_t i = sub; i < clip.n_cr; i += G) {
-			s_rot[__ldg(P.const_r_bone + clip.cr_off + i)] = __ldg(P.const_r_value + clip.cr_off + i);
-		}
-		__syncwarp(gmask);
-		// :151-167 animated translations
-		const uint32_t* t_stream = P.stream + (clip.t_stream >> 2);
-		for (uint32_t i = sub; i < clip.n_t; i += G) {
-			const Track tr = load_track(P.tracks + clip.t_off + i);
-			const V3 a = get_translation(t_stream, clip.t_bits, sample_idx, tr);
-			const V3 b = get_translation(t_stream, clip.t_bits, sample_idx + 1, tr);
-			const V3 p = lerp(a, b, t);
-			s_pos[tr.bone_index] = make_float4(p.x, p.y, p.z, 0.f);
-		}
-		// :185-203 animated rotations
-		const uint32_t* r_stream = P.stream + (clip.r_stream >> 2);
-		for (uint32_t i = sub; i < clip.n_r; i += G) {
-			const Track tr = load_track(P.tracks + clip.r_off + i);
-			const uint32_t offset1 = clip.r_bits * sample_idx + tr.offset_bits;
-			const uint32_t offset2 = offset1 + clip.r_bits;
-			unsigned long long p1 = load_u64_unaligned(r_stream, offset1 >> 3);
-			p1 >>= (offset1 & 7u);
-			unsigned long long p2 = load_u64_unaligned(r_stream, offset2 >> 3);
-			p2 >>= (offset2 & 7u);
-			const Q4 q = simd_nlerp(unpack_rotation(p1, tr), unpack_rotation(p2, tr), t);
-			s_rot[tr.bone_index] = make_float4(q.x, q.y, q.z, q.w);
+			const uint32_t fl = kf[b];
+			float4 p = __ldg(k0p + b);
+			float4 r = __ldg(k0r + b);
+			if (fl & 1u) {
+				const float4 p1 = __ldg(k0p + Bp + b);
+				const V3 v = lerp(v3(p.x, p.y, p.z), v3(p1.x, p1.y, p1.z), t);
+				p = make_float4(v.x, v.y, v.z, 0.f);
+			}
+			if (fl & 2u) {
+				const float4 r1 = __ldg(k0r + Bp + b);
+				const Q4 q = simd_nlerp(q4(r.x, r.y, r.z, r.w), q4(r1.x, r1.y, r1.z, r1.w), t);
+				r = make_float4(q.x, q.y, q.z, q.w);
+			}
+			s_pos[b] = p;
+			s_rot[b] = r;
 		}
 		__syncwarp(gmask);
 
@@ -361,6 +403,7 @@ struct lb200_animation {
 	uint32_t* d_const_r_bone = nullptr;
 	uint32_t* d_stream = nullptr;
 	float4* d_bind = nullptr; // bind_pos[B], bind_rot[B], inv_bind_pos[B], inv_bind_rot[B]
+	float4* d_key_pos = nullptr; float4* d_key_rot = nullptr; unsigned char* d_key_flags = nullptr;
 	short* d_parents = nullptr; unsigned char* d_level_bones = nullptr; uint32_t* d_level_start = nullptr;
 	int lanes_per_instance = 8;
 	uint32_t* d_clip_index = nullptr; uint32_t* d_time = nullptr;
@@ -453,7 +496,18 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		d.r_stream = appendStream(s.rotation_stream, s.rotation_stream_bytes);
 		d.length_ticks = (uint32_t)(((float)s.frame_count / s.fps) * (float)(1 << 15)); // Time::fromSeconds(m_frame_count / m_fps)
 		if (!d.length_ticks) return LB200_ERR_INVALID;
-		d.pad = 0;
+		d.pad[0] = d.pad[1] = d.pad[2] = 0;
+	}
+	// decoded keyframe tables: (frame_count + 1) frames x Bp bones per clip
+	const uint32_t Bp = (B + 3u) & ~3u;
+	std::vector<uint32_t> frame_clip, frame_index;
+	size_t key_entries = 0;
+	for (uint32_t c = 0; c < n_clips; ++c) {
+		dc[c].key_off = (uint32_t)key_entries;
+		dc[c].flag_off = c * Bp;
+		for (uint32_t f = 0; f <= dc[c].frame_count; ++f) { frame_clip.push_back(c); frame_index.push_back(f); }
+		key_entries += (size_t)(dc[c].frame_count + 1) * Bp;
+		if (key_entries > 0x7fffffffull) { lb200_set_error(ctx, "decoded clips exceed 2^31 keyframe entries"); return LB200_ERR_INVALID; }
 	}
 
 	lb200_animation* a = new (std::nothrow) lb200_animation;
@@ -504,6 +558,25 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		LB200_CUDA(ctx, cudaMemcpyAsync(a->d_mesh_w, mesh->weights4, sizeof(float4) * mesh->n_vertices, cudaMemcpyHostToDevice, st));
 		LB200_CUDA(ctx, cudaMemcpyAsync(a->d_mesh_idx, mesh->indices4, sizeof(short) * 4 * mesh->n_vertices, cudaMemcpyHostToDevice, st));
 	}
+	{
+		ANIM_MALLOC(a->d_key_pos, sizeof(float4) * key_entries);
+		ANIM_MALLOC(a->d_key_rot, sizeof(float4) * key_entries);
+		ANIM_MALLOC(a->d_key_flags, (size_t)n_clips * Bp);
+		uint32_t* d_fc = nullptr; uint32_t* d_fi = nullptr;
+		ANIM_MALLOC(d_fc, sizeof(uint32_t) * frame_clip.size());
+		ANIM_MALLOC(d_fi, sizeof(uint32_t) * frame_index.size());
+		LB200_CUDA(ctx, cudaMemcpyAsync(d_fc, frame_clip.data(), sizeof(uint32_t) * frame_clip.size(), cudaMemcpyHostToDevice, st));
+		LB200_CUDA(ctx, cudaMemcpyAsync(d_fi, frame_index.data(), sizeof(uint32_t) * frame_index.size(), cudaMemcpyHostToDevice, st));
+		DecodeParams D;
+		D.clips = a->d_clips; D.tracks = a->d_tracks; D.const_t = a->d_const_t; D.const_r_value = a->d_const_r_value; D.const_r_bone = a->d_const_r_bone;
+		D.stream = a->d_stream; D.bind_pos = a->d_bind; D.bind_rot = a->d_bind + B;
+		D.key_pos = a->d_key_pos; D.key_rot = a->d_key_rot; D.key_flags = a->d_key_flags;
+		D.frame_clip = d_fc; D.frame_index = d_fi; D.bone_count = B;
+		decode_clips_kernel<<<(unsigned)frame_clip.size(), 256, 0, st>>>(D);
+		LB200_CHECK_LAUNCH(ctx);
+		LB200_CUDA(ctx, cudaStreamSynchronize(st));
+		cudaFree(d_fc); cudaFree(d_fi);
+	}
 	LB200_CUDA(ctx, cudaStreamSynchronize(st));
 	{
 		const int smem_max = (int)(sizeof(float4) * 2 * 196 * (POSE_THREADS / 8));
@@ -521,7 +594,7 @@ void lb200_animation_destroy(lb200_animation* a) {
 	cudaSetDevice(a->ctx->device);
 	cudaStreamSynchronize(a->ctx->stream);
 	cudaFree(a->d_clips); cudaFree(a->d_tracks); cudaFree(a->d_const_t); cudaFree(a->d_const_r_value); cudaFree(a->d_const_r_bone); cudaFree(a->d_stream);
-	cudaFree(a->d_bind); cudaFree(a->d_parents); cudaFree(a->d_level_bones); cudaFree(a->d_level_start);
+	cudaFree(a->d_bind); cudaFree(a->d_key_pos); cudaFree(a->d_key_rot); cudaFree(a->d_key_flags); cudaFree(a->d_parents); cudaFree(a->d_level_bones); cudaFree(a->d_level_start);
 	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot);
 	cudaFree(a->d_mesh_pos); cudaFree(a->d_mesh_w); cudaFree(a->d_mesh_idx); cudaFree(a->d_skinned); cudaFree(a->d_checksum);
 	delete a;
@@ -550,6 +623,7 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	if ((flags & LB200_PALETTE_POSE) && !a->d_pos) { ANIM_MALLOC(a->d_pos, sizeof(float) * 3 * nb); ANIM_MALLOC(a->d_rot, sizeof(float) * 4 * nb); }
 	AnimParams P;
 	P.clips = a->d_clips; P.tracks = a->d_tracks; P.const_t = a->d_const_t; P.const_r_value = a->d_const_r_value; P.const_r_bone = a->d_const_r_bone; P.stream = a->d_stream;
+	P.key_pos = a->d_key_pos; P.key_rot = a->d_key_rot; P.key_flags = a->d_key_flags;
 	P.bind_pos = a->d_bind; P.bind_rot = a->d_bind + a->bone_count; P.inv_bind_pos = a->d_bind + 2 * a->bone_count; P.inv_bind_rot = a->d_bind + 3 * a->bone_count; P.parents = a->d_parents; P.level_bones = a->d_level_bones; P.level_start = a->d_level_start;
 	P.bone_count = a->bone_count; P.max_level = a->max_level; P.n_instances = a->n_instances;
 	P.clip_index = a->d_clip_index; P.time_ticks = a->d_time;

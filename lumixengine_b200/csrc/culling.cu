@@ -40,6 +40,29 @@ __global__ void __launch_bounds__(256) scatter_pages_kernel(const uint32_t* __re
 	if (threadIdx.x < 2) reinterpret_cast<int4*>(desc + p)[threadIdx.x] = reinterpret_cast<const int4*>(st_desc + i)[threadIdx.x];
 }
 
+// 256 per-type counts -> exclusive offsets + compact list of the non-empty types (block of 256 threads)
+__device__ __forceinline__ void scan_types(const uint32_t* __restrict__ counters, uint32_t* s_cnt, uint32_t* s_off, uint32_t* s_list, uint32_t* s_nnz) {
+	__shared__ uint32_t s_warp[8];
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t c = counters[tid];
+	uint32_t x = c;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+		if (lane >= (uint32_t)d) x += y;
+	}
+	if (lane == 31) s_warp[warp] = x;
+	if (tid == 0) *s_nnz = 0;
+	__syncthreads();
+	uint32_t base = 0;
+	for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+	s_cnt[tid] = c;
+	s_off[tid] = base + x - c;
+	if (tid == 255) s_off[256] = base + x;
+	if (c) s_list[atomicAdd(s_nnz, 1u)] = tid;
+	__syncthreads();
+}
+
 // Pack this rank's visible ids (per-type segments of out_ids) behind a 256-word header of per-type counts: the send slab of the
 // multi-GPU exchange.  Reads the counters on the device: no host round trip between the cull and the all-gather.
 struct PackParams { uint32_t type_base[256]; uint32_t slab_ids; };
@@ -49,19 +72,14 @@ __global__ void __launch_bounds__(256) pack_slab_kernel(const __grid_constant__ 
 {
 	__shared__ uint32_t s_cnt[256];
 	__shared__ uint32_t s_off[257];
-	s_cnt[threadIdx.x] = counters[threadIdx.x];
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		uint32_t acc = 0;
-		for (int t = 0; t < 256; ++t) { s_off[t] = acc; acc += s_cnt[t]; }
-		s_off[256] = acc;
-	}
-	__syncthreads();
+	__shared__ uint32_t s_list[256];
+	__shared__ uint32_t s_nnz;
+	scan_types(counters, s_cnt, s_off, s_list, &s_nnz);
 	if (blockIdx.x == 0) slab[threadIdx.x] = s_cnt[threadIdx.x];
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-	for (int t = 0; t < 256; ++t) {
+	for (uint32_t k = 0; k < s_nnz; ++k) {
+		const uint32_t t = s_list[k];
 		const uint32_t c = s_cnt[t];
-		if (!c) continue;
 		const uint32_t* src = out_ids + P.type_base[t];
 		const uint32_t off = s_off[t];
 		for (uint32_t i = gtid; i < c; i += gsize) if (off + i < P.slab_ids) slab[256 + off + i] = src[i];
@@ -74,6 +92,7 @@ struct PushParams {
 	uint32_t type_base[256];
 	uint32_t slab_ids;
 	uint32_t n_ranks, rank, epoch;
+	uint32_t debug; // profiling switches (LB200_GATHER_DEBUG): 2 = store to self only, 4 = no system fence
 	uint32_t* dst[LB200_MAX_RANKS];   // rank r's gather buffer of this epoch, already offset to MY slab inside it
 	uint32_t* flags[LB200_MAX_RANKS]; // rank r's flag block: [2][LB200_MAX_RANKS]
 };
@@ -83,35 +102,40 @@ __global__ void __launch_bounds__(256) pack_push_kernel(const __grid_constant__ 
 {
 	__shared__ uint32_t s_cnt[256];
 	__shared__ uint32_t s_off[257];
+	__shared__ uint32_t s_list[256];
+	__shared__ uint32_t s_nnz;
 	__shared__ bool s_last;
-	s_cnt[threadIdx.x] = counters[threadIdx.x];
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		uint32_t acc = 0;
-		for (int t = 0; t < 256; ++t) { s_off[t] = acc; acc += s_cnt[t]; }
-		s_off[256] = acc;
-	}
-	__syncthreads();
+	scan_types(counters, s_cnt, s_off, s_list, &s_nnz);
 	if (blockIdx.x == 0) for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][threadIdx.x] = s_cnt[threadIdx.x];
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-	for (int t = 0; t < 256; ++t) {
+	for (uint32_t k = 0; k < s_nnz; ++k) {
+		const uint32_t t = s_list[k];
 		const uint32_t c = s_cnt[t];
-		if (!c) continue;
 		const uint32_t* src = out_ids + P.type_base[t];
 		const uint32_t off = s_off[t];
 		const uint32_t lim = min(c, P.slab_ids > off ? P.slab_ids - off : 0u);
-		for (uint32_t i = gtid; i < lim; i += 4 * gsize) {
-			uint32_t v[4];
-#pragma unroll
-			for (int k = 0; k < 4; ++k) if (i + k * gsize < lim) v[k] = src[i + k * gsize];
-			for (uint32_t r = 0; r < P.n_ranks; ++r) {
-#pragma unroll
-				for (int k = 0; k < 4; ++k) if (i + k * gsize < lim) P.dst[r][256 + off + i + k * gsize] = v[k];
+		if (((P.type_base[t] ^ off) & 3u) == 0) {
+			// source and destination share their 16-byte phase: scalar head, 128-bit body, scalar tail
+			const uint32_t head = min(lim, (4u - (off & 3u)) & 3u);
+			if (gtid < head) { const uint32_t v = src[gtid]; for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][256 + off + gtid] = v; }
+			const uint32_t n4 = (lim - head) / 4;
+			const uint4* src4 = reinterpret_cast<const uint4*>(src + head);
+			for (uint32_t i = gtid; i < n4; i += gsize) {
+				const uint4 v = src4[i];
+				for (uint32_t r = 0; r < P.n_ranks; ++r) reinterpret_cast<uint4*>(P.dst[r] + 256 + off + head)[i] = v;
+			}
+			const uint32_t done = head + 4 * n4;
+			if (gtid < lim - done) { const uint32_t v = src[done + gtid]; for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][256 + off + done + gtid] = v; }
+		}
+		else {
+			for (uint32_t i = gtid; i < lim; i += gsize) {
+				const uint32_t v = src[i];
+				for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][256 + off + i] = v;
 			}
 		}
 	}
 	// publish: all stores of all blocks must be visible system-wide before the flag
-	__threadfence_system();
+	if (!(P.debug & 4u)) __threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
 	__syncthreads();
@@ -532,6 +556,11 @@ int lb200_comm_allgather_u32(lb200_ctx* ctx, const uint32_t* send, uint32_t* rec
 
 namespace {
 
+int pushGridMul() {
+	static int mul = [] { const char* e = getenv("LB200_PUSH_GRID"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+	return mul;
+}
+
 int ensureGather(lb200_culling* cs, uint32_t slab_ids) {
 	lb200_ctx* ctx = cs->ctx;
 	const size_t words = 256 + (size_t)slab_ids;
@@ -587,19 +616,22 @@ int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* fr
 		PushParams PP;
 		memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
 		PP.slab_ids = slab_ids;
-		PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = epoch;
+		static const uint32_t dbg = [] { const char* e = getenv("LB200_GATHER_DEBUG"); return e ? (uint32_t)atoi(e) : 0u; }();
+		PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = epoch; PP.debug = dbg;
 		for (int r = 0; r < LB200_MAX_RANKS; ++r) {
-			PP.dst[r] = r < ctx->n_ranks ? peer.gather[epoch & 1u][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+			PP.dst[r] = r < ctx->n_ranks ? peer.gather[epoch & 1u][(dbg & 2u) ? ctx->rank : r] + peer.slab_words * (size_t)ctx->rank : nullptr;
 			PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
 		}
-		pack_push_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, peer.done_counter);
+		pack_push_kernel<<<ctx->sm_count * pushGridMul(), 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, peer.done_counter);
 		LB200_CHECK_LAUNCH(ctx);
 		if (!cs->d_gather_counts) {
 			LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
 			LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
 		}
-		wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, epoch, cs->d_gather_counts);
-		LB200_CHECK_LAUNCH(ctx);
+		if (!(dbg & 1u)) {
+			wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, epoch, cs->d_gather_counts);
+			LB200_CHECK_LAUNCH(ctx);
+		}
 		if (out_dev_slabs) *out_dev_slabs = peer.gather[epoch & 1u][ctx->rank];
 		return LB200_OK;
 	}
