@@ -229,8 +229,25 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 	const int grp = threadIdx.x / G;          // instance slot inside the block
 	const uint32_t B = P.bone_count;
 	const uint32_t Bp = (B + 3u) & ~3u;
+	// block-shared skeleton data first (read by every instance at every depth level: keep it out of the L2 round trips):
+	//   inverse bind pos[Bp], rot[Bp] (float4) | level_start[max_level + 2] (u32) | parents[Bp] (i16) | level_bones[Bp] (u8)
+	float4* s_ibp = smem4;
+	float4* s_ibr = s_ibp + Bp;
+	uint32_t* s_level_start = reinterpret_cast<uint32_t*>(s_ibr + Bp);
+	const uint32_t n_ls = (P.max_level + 2u + 3u) & ~3u;
+	short* s_parents = reinterpret_cast<short*>(s_level_start + n_ls);
+	unsigned char* s_level_bones = reinterpret_cast<unsigned char*>(s_parents + Bp);
+	float4* inst_base = reinterpret_cast<float4*>(smem4 + 2 * Bp + (n_ls * 4 + Bp * 2 + Bp + 15) / 16);
+	for (uint32_t i = threadIdx.x; i < B; i += POSE_THREADS) {
+		s_ibp[i] = __ldg(P.inv_bind_pos + i);
+		s_ibr[i] = __ldg(P.inv_bind_rot + i);
+		s_parents[i] = P.parents[i];
+	}
+	for (uint32_t i = threadIdx.x; i < P.max_level + 2u; i += POSE_THREADS) s_level_start[i] = P.level_start[i];
+	for (uint32_t i = threadIdx.x; i < P.level_start[P.max_level + 1]; i += POSE_THREADS) s_level_bones[i] = P.level_bones[i];
+	__syncthreads();
 	// per instance: rot[Bp] (float4) then pos[Bp] (float4, w unused): 128-bit shared accesses, conflict-free per quarter warp
-	float4* s_rot = smem4 + (size_t)grp * Bp * 2;
+	float4* s_rot = inst_base + (size_t)grp * Bp * 2;
 	float4* s_pos = s_rot + Bp;
 	const uint32_t inst = blockIdx.x * INST_PER_BLOCK + grp;
 	const bool valid = inst < P.n_instances;
@@ -278,10 +295,10 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 		// Pose::computeAbsolute, pose.cpp:66-133: bones of one depth level are independent (the reference's 4-wide path
 		// relies on the same fact); levels run in order so every parent is absolute before its children.
 		for (uint32_t lvl = 1; lvl <= P.max_level; ++lvl) {
-			const uint32_t lb = P.level_start[lvl], le = P.level_start[lvl + 1];
+			const uint32_t lb = s_level_start[lvl], le = s_level_start[lvl + 1];
 			for (uint32_t k = lb + sub; k < le; k += G) {
-				const uint32_t b = P.level_bones[k];
-				const int p = P.parents[b];
+				const uint32_t b = s_level_bones[k];
+				const int p = s_parents[b];
 				const float4 pr = s_rot[p], pp = s_pos[p], cr = s_rot[b], cp = s_pos[b];
 				const Q4 prot = q4(pr.x, pr.y, pr.z, pr.w);
 				const V3 pos = add(rotate(prot, v3(cp.x, cp.y, cp.z)), v3(pp.x, pp.y, pp.z)); // :129
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 			Rigid pose;
 			pose.pos = v3(cp.x, cp.y, cp.z);
 			pose.rot = q4(cr.x, cr.y, cr.z, cr.w);
-			const float4 ip = __ldg(P.inv_bind_pos + b), ir = __ldg(P.inv_bind_rot + b);
+			const float4 ip = s_ibp[b], ir = s_ibr[b];
 			Rigid inv;
 			inv.pos = v3(ip.x, ip.y, ip.z);
 			inv.rot = q4(ir.x, ir.y, ir.z, ir.w);
@@ -579,7 +596,7 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	}
 	LB200_CUDA(ctx, cudaStreamSynchronize(st));
 	{
-		const int smem_max = (int)(sizeof(float4) * 2 * 196 * (POSE_THREADS / 8));
+		const int smem_max = (int)(sizeof(float4) * (2 * 196 * (POSE_THREADS / 8) + 2 * 196 + 128));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -638,7 +655,10 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	const int G = a->lanes_per_instance;
 	const unsigned per_block = POSE_THREADS / G;
 	const unsigned blocks = (a->n_instances + per_block - 1) / per_block;
-	const size_t smem = sizeof(float4) * 2 * ((a->bone_count + 3u) & ~3u) * per_block;
+	const uint32_t Bp_ = (a->bone_count + 3u) & ~3u;
+	const uint32_t n_ls_ = (a->max_level + 2u + 3u) & ~3u;
+	const size_t shared_words16 = 2 * Bp_ + (n_ls_ * 4 + Bp_ * 2 + Bp_ + 15) / 16; // inverse bind + topology, in float4 units
+	const size_t smem = sizeof(float4) * (shared_words16 + 2 * (size_t)Bp_ * per_block);
 	if (G == 8) pose_palette_kernel<8><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
 	else if (G == 16) pose_palette_kernel<16><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
 	else pose_palette_kernel<32><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);

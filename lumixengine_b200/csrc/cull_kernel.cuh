@@ -22,14 +22,11 @@ namespace lbcull {
 
 using namespace lb;
 
-constexpr int CULL_THREADS = 512;
-constexpr int CULL_WARPS = CULL_THREADS / 32;
-constexpr int MAX_CHUNK = CULL_THREADS; // pages per block per round (one classify thread each)
+// block size is a template parameter: 256 threads x 4 blocks/SM or 512 x 2 (pages per block per round = one classify thread each)
 constexpr int ROWS = 7;                 // ceil(200 / 32)
 constexpr int N_STATS = 8;
-enum { ST_PAGES_TESTED = 0, ST_PAGES_INSIDE, ST_PAGES_OUTSIDE, ST_PAGES_FILTERED, ST_ENT_TESTED, ST_ENT_INSIDE };
+enum { ST_PAGES_TESTED = 0, ST_PAGES_INSIDE, ST_PAGES_OUTSIDE, ST_PAGES_FILTERED, ST_ENT_TESTED, ST_ENT_INSIDE, ST_ENT_STREAMED };
 constexpr int COUNTER_WORDS = 256 + N_STATS;
-static_assert(CULL_THREADS >= 256, "one thread per renderable type in the claim phase");
 
 struct CullParams {
 	// planes NEAR, FAR, LEFT, RIGHT, TOP, BOTTOM of the ShiftedFrustum (relative to `origin`)
@@ -40,6 +37,7 @@ struct CullParams {
 	uint32_t n_pages;
 	uint32_t type_filter; // 0xff = all
 	uint32_t chunk;       // pages per block per round, <= MAX_CHUNK
+	uint32_t plane_masking; // 1 unless some sphere has a negative / NaN radius
 	uint32_t type_base[256];
 };
 
@@ -63,6 +61,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
 }
 
 enum { CLS_SKIP = 0, CLS_COPY = 1, CLS_TEST = 2 };
+// meta word of a work item: count | type << 8 | cls << 16 | counted_as_test << 18 | planes_needed << 24
 
 struct WorkItem {
 	double ox, oy, oz; // cell origin
@@ -71,10 +70,14 @@ struct WorkItem {
 };
 static_assert(sizeof(WorkItem) == 32, "");
 
-__global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __grid_constant__ CullParams P,
+template <int CULL_THREADS>
+__global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_kernel(const __grid_constant__ CullParams P,
 	const lb200_page_desc* __restrict__ desc, const float4* __restrict__ spheres, const int* __restrict__ entities,
 	uint32_t* __restrict__ out_ids, uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters, uint32_t* __restrict__ mask_out)
 {
+	constexpr int CULL_WARPS = CULL_THREADS / 32;
+	constexpr int MAX_CHUNK = CULL_THREADS;
+	static_assert(CULL_THREADS >= 256, "one thread per renderable type in the claim phase");
 	__shared__ WorkItem s_item[MAX_CHUNK];
 	__shared__ uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // [ROWS] = offset of the page inside the block's range of its type
 	__shared__ uint32_t s_cnt[256];
@@ -92,10 +95,12 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 	if (tid == 0) s_nwork = 0;
 	__syncthreads();
 
-	for (uint32_t chunk_idx = blockIdx.x; chunk_idx * P.chunk < P.n_pages; chunk_idx += gridDim.x) {
+	// Pages are dealt to blocks round-robin (page = j * gridDim + block): pages that always need sphere tests (is_big cells) and
+	// frustum-boundary cells cluster in page-id space, and contiguous chunks left a few blocks with twice the work of the rest.
+	for (uint32_t round = 0; round * P.chunk * gridDim.x < P.n_pages; ++round) {
 		// ---------------- A. classify: one thread per page ----------------
 		if ((uint32_t)tid < P.chunk) {
-			const uint32_t page = chunk_idx * P.chunk + tid;
+			const uint32_t page = (round * P.chunk + tid) * gridDim.x + blockIdx.x;
 			if (page < P.n_pages) {
 				const int4* dp = reinterpret_cast<const int4*>(desc + page);
 				const int4 a = __ldg(dp);
@@ -140,6 +145,33 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 					}
 					else atomicAdd(&s_stats[ST_PAGES_FILTERED], 1u);
 				}
+				uint32_t need = 0x3fu, as_test = 0;
+				if (cls == CLS_TEST) {
+					as_test = 1;
+					if (P.plane_masking) {
+						// Plane masking: a plane cannot cull any sphere of this cell when its signed distance is positive over the whole cell box
+						// by more than every rounding error of the reference's expression — then sign(t - r) is 0 for every sphere (radius >= 0)
+						// and evaluating the plane changes nothing.  Cell box relative to the cell origin: [0,300] for positive cell indices,
+						// [-300,0] for negative ones, [-300,300] for index 0 (truncation toward zero, math.cpp:133-138), widened by `e` because
+						// the cell index comes from pos * float(1/300) and may put a sphere marginally outside its nominal cell.
+						const float cs = LB200_CELL_SIZE;
+						const float e = 1.0f + 1e-6f * fmaxf(fmaxf(fabsf((float)org_x), fabsf((float)org_y)), fabsf((float)org_z));
+						const float lox = (org_x > 0.0 ? 0.0f : -cs) - e, hix = (org_x < 0.0 ? 0.0f : cs) + e;
+						const float loy = (org_y > 0.0 ? 0.0f : -cs) - e, hiy = (org_y < 0.0 ? 0.0f : cs) + e;
+						const float loz = (org_z > 0.0 ? 0.0f : -cs) - e, hiz = (org_z < 0.0 ? 0.0f : cs) + e;
+						const V3 offset = tofloat(sub(d3(P.ox, P.oy, P.oz), d3(org_x, org_y, org_z))); // getRelative, geometry.cpp:124
+						need = 0;
+#pragma unroll 1
+						for (int p = 0; p < 6; ++p) {
+							const float nx = P.nx[p], ny = P.ny[p], nz = P.nz[p];
+							const float dp = -dot(add(v3(P.px[p], P.py[p], P.pz[p]), offset), v3(nx, ny, nz));
+							const float low = dp + fminf(nx * lox, nx * hix) + fminf(ny * loy, ny * hiy) + fminf(nz * loz, nz * hiz);
+							const float margin = 1e-5f * (fabsf(dp) + 1000.0f * (fabsf(nx) + fabsf(ny) + fabsf(nz))) + 1e-3f;
+							if (!(low > margin)) need |= 1u << p; // NaN keeps the plane
+						}
+						if (need == 0) cls = CLS_COPY; // every sphere of the page is visible: ids only, no sphere traffic
+					}
+				}
 				if (cls == CLS_TEST) prefetch_l2(spheres + (size_t)page * LB200_PAGE_SLOTS, count * 16u);
 				else if (cls == CLS_COPY) prefetch_l2(entities + (size_t)page * LB200_PAGE_SLOTS, (count * 4u + 15u) & ~15u);
 				if (cls != CLS_SKIP) {
@@ -147,7 +179,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 					WorkItem it;
 					it.ox = org_x; it.oy = org_y; it.oz = org_z;
 					it.page = page;
-					it.meta = count | (type << 8) | ((uint32_t)cls << 16);
+					it.meta = count | (type << 8) | ((uint32_t)cls << 16) | (as_test << 18) | (need << 24);
 					s_item[slot] = it;
 				}
 				else if (mask_out) {
@@ -165,7 +197,9 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 			const WorkItem it = s_item[w];
 			const uint32_t count = it.meta & 0xffu;
 			const uint32_t type = (it.meta >> 8) & 0xffu;
-			const int cls = (int)(it.meta >> 16);
+			const int cls = (int)((it.meta >> 16) & 3u);
+			const uint32_t as_test = (it.meta >> 18) & 1u;
+			const uint32_t need = it.meta >> 24;
 			uint32_t bal[ROWS];
 			uint32_t page_visible = 0;
 			if (cls == CLS_TEST) {
@@ -196,10 +230,12 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 						uint32_t sign_acc = 0;
 #pragma unroll
 						for (int p = 0; p < 6; ++p) {
-							// :284,291  t = cx*px + cy*py + cz*pz + pd ;  t = t - r ;  movemask = sign bits
-							float t = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(cx, P.nx[p]), LB_FMUL(cy, P.ny[p])), LB_FMUL(cz, P.nz[p])), rd[p]);
-							t = LB_FSUB(t, r);
-							sign_acc |= __float_as_uint(t);
+							if (need & (1u << p)) { // warp-uniform: planes that cannot cull anything in this cell are skipped
+								// :284,291  t = cx*px + cy*py + cz*pz + pd ;  t = t - r ;  movemask = sign bits
+								float t = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(cx, P.nx[p]), LB_FMUL(cy, P.ny[p])), LB_FMUL(cz, P.nz[p])), rd[p]);
+								t = LB_FSUB(t, r);
+								sign_acc |= __float_as_uint(t);
+							}
 						}
 						visible = (sign_acc >> 31) == 0;
 					}
@@ -209,6 +245,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 				if (lane == 0) {
 					atomicAdd(&s_stats[ST_PAGES_TESTED], 1u);
 					atomicAdd(&s_stats[ST_ENT_TESTED], count);
+					atomicAdd(&s_stats[ST_ENT_STREAMED], count);
 				}
 			}
 			else { // CLS_COPY, culling_system.cpp:345-360: every entity of the page is visible
@@ -218,9 +255,9 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 					bal[k] = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
 				}
 				page_visible = count;
-				if (lane == 0) {
-					atomicAdd(&s_stats[ST_PAGES_INSIDE], 1u);
-					atomicAdd(&s_stats[ST_ENT_INSIDE], count);
+				if (lane == 0) { // statistics follow the reference's classification (culling_system.cpp:342-363), not the masking shortcut
+					atomicAdd(&s_stats[as_test ? ST_PAGES_TESTED : ST_PAGES_INSIDE], 1u);
+					atomicAdd(&s_stats[as_test ? ST_ENT_TESTED : ST_ENT_INSIDE], count);
 				}
 			}
 			if (lane == 0) {
@@ -248,6 +285,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 2) cull_pages_kernel(const __gri
 		__syncthreads();
 
 		// ---------------- D. write: gather the visible ids of each listed page ----------------
+		// (two pages per warp iteration was tried and was slower: register pressure)
 		for (uint32_t w = warp; w < n_work; w += CULL_WARPS) {
 			const uint32_t page = s_item[w].page;
 			const uint32_t type = (s_item[w].meta >> 8) & 0xffu;

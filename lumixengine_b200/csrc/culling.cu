@@ -191,6 +191,7 @@ struct lb200_culling {
 	uint32_t* h_counters = nullptr; // pinned, COUNTER_WORDS
 	uint32_t parity = 0;
 	int grid = 0;
+	int threads = 256;
 	// staging for sparse dirty uploads
 	uint8_t* h_stage = nullptr;
 	uint8_t* d_stage = nullptr;
@@ -219,8 +220,11 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * COUNTER_WORDS));
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * COUNTER_WORDS, ctx->stream));
 		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocDefault));
+		const char* e = getenv("LB200_CULL_THREADS");
+		cs->threads = (e && atoi(e) == 512) ? 512 : 256;
 		int per_sm = 0;
-		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel, CULL_THREADS, 0));
+		if (cs->threads == 512) LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<512>, 512, 0));
+		else LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<256>, 256, 0));
 		if (per_sm < 1) per_sm = 1;
 		cs->grid = ctx->sm_count * per_sm;
 	}
@@ -345,11 +349,17 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type) 
 	uint32_t* nxt = cs->d_counters + (size_t)(cs->parity ^ 1) * COUNTER_WORDS;
 	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
 	uint32_t chunk = (h.high_water + cs->grid - 1) / cs->grid;
-	chunk = std::max(32u, std::min((uint32_t)MAX_CHUNK, chunk));
+	chunk = std::max(32u, std::min((uint32_t)cs->threads, chunk));
 	P.chunk = chunk;
+	static const bool no_mask = getenv("LB200_NO_PLANE_MASKING") != nullptr;
+	P.plane_masking = (h.n_bad_radius == 0 && !no_mask) ? 1u : 0u;
 	const unsigned blocks = (unsigned)std::max(1u, std::min((uint32_t)cs->grid, (h.high_water + chunk - 1) / chunk));
-	cull_pages_kernel<<<blocks, CULL_THREADS, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
-		cs->d_out_ids, cur, nxt, cs->d_mask);
+	if (cs->threads == 512)
+		cull_pages_kernel<512><<<blocks, 512, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
+			cs->d_out_ids, cur, nxt, cs->d_mask);
+	else
+		cull_pages_kernel<256><<<blocks, 256, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
+			cs->d_out_ids, cur, nxt, cs->d_mask);
 	LB200_CHECK_LAUNCH(ctx);
 	cs->last_pages = h.high_water;
 	return LB200_OK;
@@ -509,6 +519,19 @@ int lb200_culling_cull_device(lb200_culling* cs, const lb200_shifted_frustum* fr
 	else cs->has_last = false;
 	cs->parity ^= 1;
 	return rc;
+}
+
+int lb200_culling_cull_device_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n) {
+	if (!cs || !frustum) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	if (cs->host.cells.empty()) return LB200_OK;
+	for (uint32_t i = 0; i < n; ++i) {
+		const int rc = launchCull(cs, frustum, type);
+		if (rc) return rc;
+		cs->parity ^= 1;
+	}
+	cs->has_last = false;
+	return LB200_OK;
 }
 
 int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity,

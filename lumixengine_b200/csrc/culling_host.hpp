@@ -58,6 +58,9 @@ struct CullingHost {
 	std::vector<uint32_t> entity_to_slot; // m_entity_to_cell: page*200 + index, NO_SLOT = not added
 	uint32_t type_counts[256];
 	uint32_t n_entities = 0;
+	uint32_t n_bad_radius = 0; // spheres with radius < 0 or NaN: the GPU's plane masking assumes radius >= 0 and is switched off while any exist
+
+	static bool badRadius(float r) { return !(r >= 0.0f); }
 
 	// ---- dirty tracking for the HBM mirror ----
 	std::vector<uint8_t> dirty_flag;
@@ -142,6 +145,7 @@ struct CullingHost {
 		s[1] = (float)(pos[1] - d.origin[1]);
 		s[2] = (float)(pos[2] - d.origin[2]);
 		s[3] = radius;
+		if (badRadius(radius)) ++n_bad_radius;
 		entities[(size_t)page * PAGE_SLOTS + idx] = entity;
 	}
 
@@ -210,6 +214,7 @@ struct CullingHost {
 		const uint32_t cell = slot / PAGE_SLOTS;
 		--type_counts[desc[cell].type];
 		--n_entities;
+		if (badRadius(spheres[4 * (size_t)slot + 3])) --n_bad_radius;
 		if (desc[cell].count == 1) {
 			if (prev[cell] == NO_PAGE) {
 				if (next[cell] == NO_PAGE) cell_map.erase(keys[cell]);
@@ -275,6 +280,7 @@ struct CullingHost {
 		const bool is_big = radius > LB200_CELL_SIZE;
 		if (was_big == is_big && sameCell(nk, keys[cell])) {
 			float* s = spheres + 4 * (size_t)slot;
+			n_bad_radius += (badRadius(radius) ? 1 : 0) - (badRadius(s[3]) ? 1 : 0);
 			s[3] = radius;
 			s[0] = (float)(pos[0] - desc[cell].origin[0]);
 			s[1] = (float)(pos[1] - desc[cell].origin[1]);
@@ -296,6 +302,7 @@ struct CullingHost {
 		const bool is_big = radius > LB200_CELL_SIZE;
 		float* s = spheres + 4 * (size_t)slot;
 		if (was_big == is_big) {
+			n_bad_radius += (badRadius(radius) ? 1 : 0) - (badRadius(s[3]) ? 1 : 0);
 			s[3] = radius;
 			markDirty(cell);
 			return LB200_OK;

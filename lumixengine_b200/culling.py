@@ -175,7 +175,8 @@ class CullingSystem:
         res = _lib.CullResult()
         rc = self.L.lb200_culling_cull(self.h, C.byref(frustum), C.c_uint8(type), ptr(out), C.c_uint32(len(out)), C.byref(res))
         self._err(rc)
-        return CullResult(out[:res.total].copy(), res)
+        # a view of the page-locked result buffer, valid until the next cull on this object (the engine shim copies it into CullResult pages)
+        return CullResult(out[:res.total], res)
 
     def cull_device(self, frustum, type=TYPE_ALL, want_counts=True):
         """Same cull, ids stay in HBM: returns (device pointer int, lb200_cull_result or None)."""
@@ -185,6 +186,10 @@ class CullingSystem:
                                               C.c_int(1 if want_counts else 0))
         self._err(rc)
         return (dev.value or 0), (res if want_counts else None)
+
+    def cull_device_n(self, frustum, n, type=TYPE_ALL):
+        """n back-to-back asynchronous culls issued from C (no per-call Python overhead)."""
+        self._err(self.L.lb200_culling_cull_device_n(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(n)))
 
     def flush(self):
         self._err(self.L.lb200_culling_flush(self.h))

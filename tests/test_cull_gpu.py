@@ -152,6 +152,7 @@ def test_10m_properties(ctx):
     cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
     f = lb.frustum_perspective(**scenes.c2_frustum_args())
     r1 = cs.cull(f)
+    r1.ids = r1.ids.copy()  # cull() returns a view of the result buffer, valid until the next cull
     # unique ids, all valid, type segments consistent with the scene's types
     assert len(np.unique(r1.ids)) == r1.total
     assert np.array_equal(scene["types"][r1.ids], r1.types())
@@ -159,8 +160,35 @@ def test_10m_properties(ctx):
     r2 = cs.cull(f)
     assert np.array_equal(np.sort(r1.ids), np.sort(r2.ids))
     # per-type culls partition the all-types cull
-    parts = [cs.cull(f, t).ids for t in range(4)]
+    parts = [cs.cull(f, t).ids.copy() for t in range(4)]
     assert np.array_equal(np.sort(np.concatenate(parts)), np.sort(r1.ids))
     # a frustum containing the whole scene returns everything
     big = lb.frustum_ortho((0.0, 0.0, 20000.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0), 20000.0, 20000.0, 0.0, 40000.0)
     assert cs.cull(big).total == 10_000_000
+
+
+def test_far_from_world_origin_and_negative_radius(ctx, oracle):
+    """World coordinates of several thousand km (fp64 positions, fp32 cell-relative spheres) and a few negative radii
+    (which switch the plane-masking shortcut off): visibility stays bit-exact."""
+    rng = np.random.default_rng(77)
+    n = 120_000
+    base = np.array([3.0e6 + 17.25, -2.0e5 + 0.5, -7.5e6 + 3.125])
+    pos = base + (rng.random((n, 3)) * 2 - 1) * np.array([2500.0, 250.0, 2500.0])
+    rad = (rng.random(n) * 6 + 0.25).astype(np.float32)
+    scene = dict(entities=np.arange(n, dtype=np.int32), types=(np.arange(n) % 2).astype(np.uint8), pos=pos, radius=rad)
+    cs, oc = _both(ctx, oracle, scene)
+    for d, far in (((0.0, 0.0, -1.0), 1500.0), ((0.6, -0.1, 0.79), 3000.0), ((-1.0, 0.02, 0.01), 800.0)):
+        a = dict(scenes.c1_frustum_args(), position=tuple(base + np.array([100.0, 10.0, -50.0])), direction=d, far=far)
+        f = lb.frustum_perspective(**a)
+        res = cs.cull(f)
+        oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f))
+        _assert_same(res, oids, otys)
+        assert res.total > 100
+    # negative radii: plane masking must switch itself off and results stay identical to the reference arithmetic
+    neg = rng.choice(n, 200, replace=False).astype(np.int32)
+    nr = -(rng.random(200) * 50).astype(np.float32)
+    cs.setRadius(neg, nr); oc.set_radius(neg, nr)
+    f = lb.frustum_perspective(**dict(scenes.c1_frustum_args(), position=tuple(base), far=2500.0))
+    res = cs.cull(f)
+    oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f))
+    _assert_same(res, oids, otys)
