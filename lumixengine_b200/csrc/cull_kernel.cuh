@@ -9,9 +9,10 @@
 //                 geometry.cpp:121-149 — only d changes), <=200 spheres streamed with 128-bit loads, 6 distinct planes
 //                 (EXTRA0/1 duplicate NEAR, geometry.cpp:134-136) in the reference's op order, sign-bit test
 //                 (culling_system.cpp:284-295, simd.h:119); ballots kept in shared memory, per-type counts by shared atomics.
-//   C. claim      one global atomic per (block, renderable type) reserves the block's output range.
+//   C. claim      one global atomic per (warp, renderable type) reserves the output range of the warp's pages.
 //   D. write      one warp per listed page: visible ids gathered (4 B) and written compacted, grouped by type.
-// Two block barriers per chunk, no per-page global atomics, every warp in B/D has real work (skipped pages never reach a warp).
+// One block barrier per round (after A): B, C and D run warp-autonomously, so a warp with cheap pages never waits for one with
+// expensive pages.  No per-page global atomics; skipped pages never reach a warp.
 // HBM-bound: 32 B descriptor per page + 16 B per tested sphere + 4 B read + 4 B write per visible id (+ 32 B mask per page).
 #pragma once
 
@@ -38,6 +39,7 @@ struct CullParams {
 	uint32_t type_filter; // 0xff = all
 	uint32_t chunk;       // pages per block per round, <= MAX_CHUNK
 	uint32_t plane_masking; // 1 unless some sphere has a negative / NaN radius
+	uint32_t prefetch_test_ids; // also pull the id rows of tested pages into L2 (a few % more DRAM traffic, one DRAM latency less in phase D)
 	uint32_t type_base[256];
 };
 
@@ -77,11 +79,8 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 {
 	constexpr int CULL_WARPS = CULL_THREADS / 32;
 	constexpr int MAX_CHUNK = CULL_THREADS;
-	static_assert(CULL_THREADS >= 256, "one thread per renderable type in the claim phase");
 	__shared__ WorkItem s_item[MAX_CHUNK];
-	__shared__ uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // [ROWS] = offset of the page inside the block's range of its type
-	__shared__ uint32_t s_cnt[256];
-	__shared__ uint32_t s_base[256];
+	__shared__ uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // [ROWS] = visible count, then offset of the page inside its type's output segment
 	__shared__ uint32_t s_stats[N_STATS];
 	__shared__ uint32_t s_nwork;
 
@@ -90,7 +89,6 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 	const int warp = tid >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 
-	if (tid < 256) s_cnt[tid] = 0;
 	if (tid < N_STATS) s_stats[tid] = 0;
 	if (tid == 0) s_nwork = 0;
 	__syncthreads();
@@ -173,7 +171,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 					}
 				}
 				if (cls == CLS_TEST) prefetch_l2(spheres + (size_t)page * LB200_PAGE_SLOTS, count * 16u);
-				else if (cls == CLS_COPY) prefetch_l2(entities + (size_t)page * LB200_PAGE_SLOTS, (count * 4u + 15u) & ~15u);
+				if (cls != CLS_SKIP && (cls == CLS_COPY || P.prefetch_test_ids)) prefetch_l2(entities + (size_t)page * LB200_PAGE_SLOTS, (count * 4u + 15u) & ~15u);
 				if (cls != CLS_SKIP) {
 					const uint32_t slot = atomicAdd(&s_nwork, 1u);
 					WorkItem it;
@@ -263,7 +261,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 			if (lane == 0) {
 #pragma unroll
 				for (int k = 0; k < ROWS; ++k) s_bal[w][k] = bal[k];
-				s_bal[w][ROWS] = page_visible ? atomicAdd(&s_cnt[type], page_visible) : 0u;
+				s_bal[w][ROWS] = page_visible;
 				if (mask_out) {
 					uint4* m = reinterpret_cast<uint4*>(mask_out + (size_t)it.page * 8);
 					m[0] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
@@ -271,28 +269,40 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 				}
 			}
 		}
-		__syncthreads();
-
-		// ---------------- C. claim: one global atomic per (block, type) ----------------
-		if (tid < 256) {
-			const uint32_t c = s_cnt[tid];
-			if (c) {
-				s_base[tid] = atomicAdd(&counters[tid], c);
-				s_cnt[tid] = 0;
+		// ---------------- C. claim: one global atomic per (warp, type) — no block barrier between B, C and D ----------------
+		// lane i stands for the warp's i-th page (w = warp + i * CULL_WARPS; at most 32 per warp since chunk <= CULL_THREADS)
+		__syncwarp();
+		{
+			const uint32_t wi = warp + (uint32_t)lane * CULL_WARPS;
+			const bool has = wi < n_work;
+			const uint32_t my_type = has ? ((s_item[wi].meta >> 8) & 0xffu) : 0xffffffffu;
+			const uint32_t my_count = has ? s_bal[wi][ROWS] : 0u;
+			const uint32_t n_mine = (n_work + CULL_WARPS - 1 - warp) / CULL_WARPS; // pages of this warp (warp-uniform)
+			uint32_t prefix = 0, total = 0;
+			for (uint32_t l = 0; l < n_mine; ++l) {
+				const uint32_t c = __shfl_sync(0xffffffffu, my_count, (int)l);
+				const uint32_t t = __shfl_sync(0xffffffffu, my_type, (int)l);
+				if (t == my_type) { total += c; if (l < (uint32_t)lane) prefix += c; }
 			}
+			const unsigned grp = __match_any_sync(0xffffffffu, my_type);
+			const int leader = __ffs((int)grp) - 1;
+			uint32_t base = 0;
+			if (has && lane == leader && total) base = atomicAdd(&counters[my_type], total);
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (has) s_bal[wi][ROWS] = base + prefix; // offset of the page inside its type's output segment
 		}
-		if (tid == 0) s_nwork = 0;
-		__syncthreads();
+		__syncwarp();
 
 		// ---------------- D. write: gather the visible ids of each listed page ----------------
-		// (two pages per warp iteration was tried and was slower: register pressure)
+		// Memory-level parallelism bounds this phase (Little's law at ~1 us loaded latency: 32 warps x 7 x 128 B per SM).  Batching two
+		// or four pages per warp iteration was tried twice and lost to register spills under the 64-register cap of 4 blocks/SM.
 		for (uint32_t w = warp; w < n_work; w += CULL_WARPS) {
 			const uint32_t page = s_item[w].page;
 			const uint32_t type = (s_item[w].meta >> 8) & 0xffu;
 			uint32_t bal[ROWS];
 #pragma unroll
 			for (int k = 0; k < ROWS; ++k) bal[k] = s_bal[w][k];
-			uint32_t* dst = out_ids + P.type_base[type] + s_base[type] + s_bal[w][ROWS];
+			uint32_t* dst = out_ids + P.type_base[type] + s_bal[w][ROWS];
 			const int* ep = entities + (size_t)page * LB200_PAGE_SLOTS;
 			int id[ROWS];
 #pragma unroll
@@ -305,6 +315,8 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 			}
 		}
 		__syncthreads(); // s_item / s_bal are reused by the next round
+		if (tid == 0) s_nwork = 0;
+		__syncthreads();
 	}
 
 	if (tid < N_STATS && s_stats[tid]) atomicAdd(&counters[256 + tid], s_stats[tid]);

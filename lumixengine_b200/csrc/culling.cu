@@ -353,6 +353,8 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type) 
 	P.chunk = chunk;
 	static const bool no_mask = getenv("LB200_NO_PLANE_MASKING") != nullptr;
 	P.plane_masking = (h.n_bad_radius == 0 && !no_mask) ? 1u : 0u;
+	static const bool pf_ids = getenv("LB200_PREFETCH_TEST_IDS") ? atoi(getenv("LB200_PREFETCH_TEST_IDS")) != 0 : false;
+	P.prefetch_test_ids = pf_ids ? 1u : 0u;
 	const unsigned blocks = (unsigned)std::max(1u, std::min((uint32_t)cs->grid, (h.high_water + chunk - 1) / chunk));
 	if (cs->threads == 512)
 		cull_pages_kernel<512><<<blocks, 512, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
