@@ -355,8 +355,9 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 
 // ---- skinning ------------------------------------------------------------------------------------------------
 constexpr int SKIN_THREADS = 256;
-constexpr int SKIN_GROUP = 8; // instances per block: vertex data stays in registers across them
+// SKIN_GROUP = instances per block (template parameter): vertex data stays in registers across them
 
+template <int SKIN_GROUP>
 __global__ void __launch_bounds__(SKIN_THREADS) skin_kernel(const float* __restrict__ palette_mtx, const float* __restrict__ positions3,
 	const float4* __restrict__ weights4, const short* __restrict__ indices4, uint32_t n_vertices, uint32_t bone_count, uint32_t n_instances,
 	float* __restrict__ out)
@@ -601,7 +602,9 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 	}
-	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SKIN_GROUP * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * 196 * 3 * sizeof(float4))));
 	*out = a;
 	return LB200_OK;
 }
@@ -652,7 +655,8 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	P.dt_negative = time_delta < 0;
 	P.dt_ticks = (uint32_t)((P.dt_negative ? -time_delta : time_delta) * (float)(1 << 15));
 	P.advance = time_delta != 0;
-	const int G = a->lanes_per_instance;
+	static const int g_env = [] { const char* e = getenv("LB200_POSE_LANES"); const int v = e ? atoi(e) : 0; return (v == 8 || v == 16 || v == 32) ? v : 0; }();
+	const int G = g_env ? g_env : a->lanes_per_instance;
 	const unsigned per_block = POSE_THREADS / G;
 	const unsigned blocks = (a->n_instances + per_block - 1) / per_block;
 	const uint32_t Bp_ = (a->bone_count + 3u) & ~3u;
@@ -673,10 +677,13 @@ int lb200_animation_skin(lb200_animation* a) {
 	if (!a->n_instances) return LB200_OK;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (!a->d_skinned) ANIM_MALLOC(a->d_skinned, sizeof(float) * 3 * (size_t)a->max_instances * a->n_vertices);
-	const dim3 grid((a->n_vertices + SKIN_THREADS - 1) / SKIN_THREADS, (a->n_instances + SKIN_GROUP - 1) / SKIN_GROUP);
+	static const int group = [] { const char* e = getenv("LB200_SKIN_GROUP"); const int v = e ? atoi(e) : 8; return (v == 4 || v == 16) ? v : 8; }();
+	const dim3 grid((a->n_vertices + SKIN_THREADS - 1) / SKIN_THREADS, (a->n_instances + group - 1) / group);
 	if (grid.y > 65535) { lb200_set_error(ctx, "too many instances for one skin launch"); return LB200_ERR_INVALID; }
-	const size_t smem = sizeof(float4) * 3 * a->bone_count * SKIN_GROUP;
-	skin_kernel<<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
+	const size_t smem = sizeof(float4) * 3 * a->bone_count * group;
+	if (group == 4) skin_kernel<4><<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
+	else if (group == 16) skin_kernel<16><<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
+	else skin_kernel<8><<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
 	LB200_CHECK_LAUNCH(ctx);
 	return LB200_OK;
 }
