@@ -220,11 +220,9 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * COUNTER_WORDS));
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * COUNTER_WORDS, ctx->stream));
 		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocDefault));
-		const char* e = getenv("LB200_CULL_THREADS");
-		cs->threads = (e && atoi(e) == 512) ? 512 : 256;
+		cs->threads = 256; // 512-thread blocks measured no better (profiles/)
 		int per_sm = 0;
-		if (cs->threads == 512) LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<512>, 512, 0));
-		else LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<256>, 256, 0));
+		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<256>, 256, 0));
 		if (per_sm < 1) per_sm = 1;
 		cs->grid = ctx->sm_count * per_sm;
 	}
@@ -356,12 +354,8 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type) 
 	static const bool pf_ids = getenv("LB200_PREFETCH_TEST_IDS") ? atoi(getenv("LB200_PREFETCH_TEST_IDS")) != 0 : false;
 	P.prefetch_test_ids = pf_ids ? 1u : 0u;
 	const unsigned blocks = (unsigned)std::max(1u, std::min((uint32_t)cs->grid, (h.high_water + chunk - 1) / chunk));
-	if (cs->threads == 512)
-		cull_pages_kernel<512><<<blocks, 512, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
-			cs->d_out_ids, cur, nxt, cs->d_mask);
-	else
-		cull_pages_kernel<256><<<blocks, 256, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
-			cs->d_out_ids, cur, nxt, cs->d_mask);
+	cull_pages_kernel<256><<<blocks, 256, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
+		cs->d_out_ids, cur, nxt, cs->d_mask);
 	LB200_CHECK_LAUNCH(ctx);
 	cs->last_pages = h.high_water;
 	return LB200_OK;
