@@ -7,8 +7,10 @@
 Metric (BASELINE.json): M entities culled/s.  Workload at N=1: configs[1] = "10M static entities, 1 camera frustum cull,
 single B200" (scene C2 of SURVEY.md §8d).  A step = one CullingSystem::cull of the whole scene for one frustum.
 N>1 (torchrun, one rank per GPU): weak scaling — every rank owns its own 10 M-entity shard (whole cell pages, no
-data-path collective for the cull itself) and each step ends with the one exchange the path has: the NCCL all-gather of the
-compacted visible lists.  `value` = all ranks' entities / max-over-ranks device time.
+data-path collective for the cull itself) and each step carries the one exchange the path has: the visibility
+bitmask + per-type counts of every rank reach every other rank, stored into peer memory over NVLink by the cull kernel itself
+(lb200_culling_cull_exchange); the compacted id lists stay sharded with their entities.  LB200_EXCHANGE=ids gathers the id lists
+instead (fused pack + peer push; LB200_NO_P2P=1: pack + ncclAllGather).  `value` = all ranks' entities / max-over-ranks device time.
 The JSON line also carries the secondary BASELINE metric (M skinned verts/s) and the other stages of the path under "paths".
 """
 import argparse
@@ -225,12 +227,23 @@ def ours(a, rank, world):
         t = torch.tensor([visible], dtype=torch.int64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         slab = int(t.item()) + 1024
-        if os.environ.get("LB200_NO_P2P") != "1":
+        exchange = os.environ.get("LB200_EXCHANGE", "mask")
+        if exchange == "mask":
+            t = torch.tensor([cs.exchange_slab_words()], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ctx.comm_enable_p2p(int(t.item()) - 256)
+            exchange_desc = "visibility bitmask rows + per-type counts stored into every rank's memory by the cull kernel (NVLink peer stores, epoch flags); id lists stay sharded"
+        elif os.environ.get("LB200_NO_P2P") != "1":
             ctx.comm_enable_p2p(slab)  # per-frame exchange = fused pack + NVLink peer stores + epoch flags (no NCCL call per step)
+            exchange_desc = "visible id lists: fused pack + NVLink peer push"
+        else:
+            exchange_desc = "visible id lists: pack + ncclAllGather"
 
     def step_device():
-        if world > 1:
-            cs.cull_gather(f, slab)  # cull + device-side pack + one ncclAllGather, no host synchronisation
+        if world > 1 and exchange == "mask":
+            cs.cull_exchange(f)  # one kernel: cull + peer stores of the mask rows; then the flag wait
+        elif world > 1:
+            cs.cull_gather(f, slab)  # cull + device-side pack + exchange of the id slabs, no host synchronisation
         else:
             cs.cull_device(f, want_counts=False)
 
@@ -301,7 +314,7 @@ def ours(a, rank, world):
         "config": {"workload": "C2: 10M static entities, 1 camera frustum cull (BASELINE.json configs[1]); per GPU at N>1", "entities_per_gpu": N_ENTITIES,
                    "visible_per_gpu": int(visible), "pages": cs.page_count(), "frustum": "perspective fov 60deg 16:9 near 0.1 far 4500 at origin looking -z",
                    "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{cs.page_count() * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
-                   "parallelism": f"dp{world}: whole cell pages per rank" + (("; visible lists exchanged each step: " + ("fused pack + NVLink peer push" if os.environ.get("LB200_NO_P2P") != "1" else "pack + ncclAllGather")) if world > 1 else ""),
+                   "parallelism": f"dp{world}: whole cell pages per rank" + (("; exchanged each step: " + exchange_desc) if world > 1 else ""),
                    "scene_build_s": build_s, "page_stats": stats},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -120,6 +120,8 @@ LB200_API uint32_t lb200_culling_page_count(const lb200_culling* cs);
 LB200_API uint32_t lb200_culling_entity_count(const lb200_culling* cs);
 LB200_API int lb200_culling_get_page(const lb200_culling* cs, uint32_t page, double origin[3], int32_t indices[3], uint8_t* type, uint8_t* is_big,
 	uint32_t* count, float* spheres4 /* count*4 or NULL */, int32_t* entities /* count or NULL */);
+/* Device page id (row index of the page in the HBM arrays and in the visibility bitmask) of the page-th entry of m_cells; -1 if out of range. */
+LB200_API int32_t lb200_culling_page_id(const lb200_culling* cs, uint32_t page);
 
 /* Result of one cull: visible entity ids grouped by renderable type.  ids[type_offset[t] .. type_offset[t]+type_count[t])
  * are the visible entities of type t (order inside a type is unspecified, as in the reference: SURVEY.md F4).
@@ -183,6 +185,20 @@ LB200_API int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, cons
 /* Distance in u32 words between consecutive ranks' slabs inside the buffer lb200_culling_cull_gather returns for this slab_ids
  * (256 + slab_ids on the NCCL path, the fixed peer-buffer stride after lb200_comm_enable_p2p). */
 LB200_API uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, uint32_t slab_ids);
+
+/* Bitmask exchange (the fixed-size product): the cull kernel itself stores each page's 32-byte visibility row and, at its
+ * end, the per-type visible counts straight into EVERY rank's memory over NVLink (no separate pack / collective launch); the visible
+ * ids stay sharded on the rank that owns the entities (*out_dev_ids, per-type segments as in lb200_culling_cull_device).
+ * Needs lb200_comm_enable_p2p(ctx, max over ranks of lb200_culling_exchange_slab_words(cs) - 256).  Asynchronous on the context
+ * stream; when the stream reaches the end of this call every rank's slab of this step is complete in *out_dev_slabs.
+ * Slab of rank r = words [r * stride, (r + 1) * stride):
+ *   [0,256)   visible count per renderable type
+ *   [256,264) n_pages, blocks, rows_per_block, chunk, 0, 0, 0, 0
+ *   [264, ..) 8 words per mask row; the row of page p (page id on rank r) is (p % blocks) * rows_per_block + p / blocks;
+ *             bit s of the 256-bit row = slot s of the page is visible (slots >= 200 are 0) */
+LB200_API int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
+                                          const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words);
+LB200_API uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hierarchy — replaces the recursion World::transformEntity, src/engine/world.cpp:255-282 (child.global =

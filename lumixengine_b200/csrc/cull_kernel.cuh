@@ -11,8 +11,13 @@
 //                 (culling_system.cpp:284-295, simd.h:119); ballots kept in shared memory, per-type counts by shared atomics.
 //   C. claim      one global atomic per (warp, renderable type) reserves the output range of the warp's pages.
 //   D. write      one warp per listed page: visible ids gathered (4 B) and written compacted, grouped by type.
+//   E. mask       the round's visibility rows (32 B per page) leave the block as one contiguous, 128-bit coalesced run:
+//                 row(page) = (page % gridDim) * rows_per_block + page / gridDim ("block-transposed").  In exchange mode the same
+//                 run is stored straight into every rank's memory over NVLink (the bitmask is the exchanged product).
 // One block barrier per round (after A): B, C and D run warp-autonomously, so a warp with cheap pages never waits for one with
 // expensive pages.  No per-page global atomics; skipped pages never reach a warp.
+// Everything before cudaGridDependencySynchronize() (launch, descriptor reads, classification, L2 prefetch) only READS scene data:
+// when culls are issued back to back with programmatic stream serialization it overlaps the tail of the previous cull.
 // HBM-bound: 32 B descriptor per page + 16 B per tested sphere + 4 B read + 4 B write per visible id (+ 32 B mask per page).
 #pragma once
 
@@ -40,8 +45,16 @@ struct CullParams {
 	uint32_t chunk;       // pages per block per round, <= MAX_CHUNK
 	uint32_t plane_masking; // 1 unless some sphere has a negative / NaN radius
 	uint32_t prefetch_test_ids; // also pull the id rows of tested pages into L2 (a few % more DRAM traffic, one DRAM latency less in phase D)
+	uint32_t rows_per_block;    // mask rows owned by one block = rounds * chunk
+	// exchange mode (n_ranks > 0): mask rows + per-type counts go to every rank's slab, then an epoch flag (culling.cu)
+	uint32_t n_ranks, rank, epoch;
+	uint32_t* xdst[LB200_MAX_RANKS];   // rank r's exchange buffer of this epoch, already offset to MY slab inside it
+	uint32_t* xflags[LB200_MAX_RANKS]; // rank r's flag block: [2][LB200_MAX_RANKS]
+	uint32_t* done_counter;            // local, for the last-block election
 	uint32_t type_base[256];
 };
+constexpr uint32_t XHEADER_WORDS = 264; // slab = [256 per-type counts][n_pages, grid, rows_per_block, chunk, 0, 0, 0, 0][mask rows]
+constexpr uint32_t SLOT_NONE = 0xffffu;
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 	float4 r;
@@ -80,9 +93,14 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 	constexpr int CULL_WARPS = CULL_THREADS / 32;
 	constexpr int MAX_CHUNK = CULL_THREADS;
 	__shared__ WorkItem s_item[MAX_CHUNK];
-	__shared__ uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // [ROWS] = visible count, then offset of the page inside its type's output segment
+	__shared__ __align__(16) uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // [ROWS] = visible count, then offset of the page inside its type's output segment
+	__shared__ uint16_t s_slot[MAX_CHUNK]; // classify thread -> work slot of its page (SLOT_NONE: skipped / no page)
 	__shared__ uint32_t s_stats[N_STATS];
 	__shared__ uint32_t s_nwork;
+	__shared__ bool s_last;
+
+	// let the next cull of the stream start its read-only prologue as soon as SM resources free up
+	cudaTriggerProgrammaticLaunchCompletion();
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
@@ -99,6 +117,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 		// ---------------- A. classify: one thread per page ----------------
 		if ((uint32_t)tid < P.chunk) {
 			const uint32_t page = (round * P.chunk + tid) * gridDim.x + blockIdx.x;
+			uint32_t my_slot = SLOT_NONE;
 			if (page < P.n_pages) {
 				const int4* dp = reinterpret_cast<const int4*>(desc + page);
 				const int4 a = __ldg(dp);
@@ -179,14 +198,13 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 					it.page = page;
 					it.meta = count | (type << 8) | ((uint32_t)cls << 16) | (as_test << 18) | (need << 24);
 					s_item[slot] = it;
-				}
-				else if (mask_out) {
-					uint4* m = reinterpret_cast<uint4*>(mask_out + (size_t)page * 8);
-					m[0] = make_uint4(0u, 0u, 0u, 0u);
-					m[1] = make_uint4(0u, 0u, 0u, 0u);
+					my_slot = slot;
 				}
 			}
+			s_slot[tid] = (uint16_t)my_slot;
 		}
+		// nothing above wrote global memory; everything below may (ids, masks, counters) and must see the previous kernel's results
+		if (round == 0) cudaGridDependencySynchronize();
 		__syncthreads();
 		const uint32_t n_work = s_nwork;
 
@@ -262,11 +280,6 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 #pragma unroll
 				for (int k = 0; k < ROWS; ++k) s_bal[w][k] = bal[k];
 				s_bal[w][ROWS] = page_visible;
-				if (mask_out) {
-					uint4* m = reinterpret_cast<uint4*>(mask_out + (size_t)it.page * 8);
-					m[0] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
-					m[1] = make_uint4(bal[4], bal[5], bal[6], 0u);
-				}
 			}
 		}
 		// ---------------- C. claim: one global atomic per (warp, type) — no block barrier between B, C and D ----------------
@@ -314,7 +327,23 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 				prefix += __popc(bal[k]);
 			}
 		}
-		__syncthreads(); // s_item / s_bal are reused by the next round
+		__syncthreads(); // every warp is done with s_item / s_bal
+		// ---------------- E. mask rows of this round: one contiguous run per block, 128-bit stores ----------------
+		if (mask_out || P.n_ranks) {
+			const size_t run = ((size_t)blockIdx.x * P.rows_per_block + (size_t)round * P.chunk) * 2; // in uint4
+			for (uint32_t i = tid; i < P.chunk * 2; i += CULL_THREADS) {
+				const uint32_t slot = s_slot[i >> 1];
+				uint4 v = make_uint4(0u, 0u, 0u, 0u);
+				if (slot != SLOT_NONE) {
+					v = *reinterpret_cast<const uint4*>(&s_bal[slot][(i & 1u) * 4]);
+					if (i & 1u) v.w = 0u; // that word holds the output offset
+				}
+				if (P.n_ranks == 0) reinterpret_cast<uint4*>(mask_out)[run + i] = v;
+				else {
+					for (uint32_t r = 0; r < P.n_ranks; ++r) reinterpret_cast<uint4*>(P.xdst[r] + XHEADER_WORDS)[run + i] = v;
+				}
+			}
+		}
 		if (tid == 0) s_nwork = 0;
 		__syncthreads();
 	}
@@ -323,6 +352,31 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 	// the other counter buffer is the next cull's: zero it now so no memset sits between two culls
 	if (blockIdx.x == 0) {
 		for (int i = tid; i < COUNTER_WORDS; i += CULL_THREADS) next_counters[i] = 0;
+	}
+	// exchange mode: once every block's rows have landed everywhere, the last block sends the per-type counts and raises the epoch flag
+	if (P.n_ranks) {
+		__threadfence_system();
+		__syncthreads();
+		if (tid == 0) s_last = atomicAdd(P.done_counter, 1u) == gridDim.x - 1;
+		__syncthreads();
+		if (s_last) {
+			for (uint32_t i = tid; i < XHEADER_WORDS; i += CULL_THREADS) {
+				uint32_t v = 0;
+				if (i < 256) v = *(volatile const uint32_t*)(counters + i);
+				else if (i == 256) v = P.n_pages;
+				else if (i == 257) v = gridDim.x;
+				else if (i == 258) v = P.rows_per_block;
+				else if (i == 259) v = P.chunk;
+				for (uint32_t r = 0; r < P.n_ranks; ++r) P.xdst[r][i] = v;
+			}
+			__threadfence_system();
+			__syncthreads();
+			if ((uint32_t)tid < P.n_ranks) {
+				volatile uint32_t* f = P.xflags[tid] + (P.epoch & 1u) * LB200_MAX_RANKS + P.rank;
+				*f = P.epoch;
+			}
+			if (tid == 0) *P.done_counter = 0;
+		}
 	}
 }
 

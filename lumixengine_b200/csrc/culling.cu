@@ -204,6 +204,7 @@ struct lb200_culling {
 	size_t slab_cap = 0;
 
 	uint32_t last_type_base[256];
+	uint32_t last_blocks = 0, last_rows_per_block = 0; // mask row of page p = (p % blocks) * rows_per_block + p / blocks
 	lb200_cull_result last = {};
 	bool has_last = false;
 	uint64_t last_bytes = 0;
@@ -236,7 +237,8 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_spheres, sizeof(float4) * PAGE_SLOTS * (size_t)cap * R));
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_entities, sizeof(int) * PAGE_SLOTS * (size_t)cap * R));
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_desc, sizeof(lb200_page_desc) * (size_t)cap * R));
-		LB200_CUDA(ctx, cudaMalloc(&cs->d_mask, sizeof(uint32_t) * 8 * (size_t)cap));
+		// block-transposed rows (cull_kernel.cuh phase E): at most one chunk of padding rows per block
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_mask, sizeof(uint32_t) * 8 * ((size_t)cap + 256 * (size_t)cs->grid)));
 		// free / never-used pages must read count == 0
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_desc, 0, sizeof(lb200_page_desc) * (size_t)cap * R, ctx->stream));
 		cs->dev_cap = cap;
@@ -319,9 +321,23 @@ int flushPages(lb200_culling* cs) {
 	return LB200_OK;
 }
 
-int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type) {
+// rounds / rows per block of a cull over n_pages (the kernel's dealing: page = j * blocks + block)
+void cullGeometry(const lb200_culling* cs, uint32_t n_pages, uint32_t* chunk_out, uint32_t* blocks_out, uint32_t* rpb_out) {
+	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
+	uint32_t chunk = (n_pages + cs->grid - 1) / cs->grid;
+	chunk = std::max(32u, std::min((uint32_t)cs->threads, chunk));
+	const uint32_t blocks = std::max(1u, std::min((uint32_t)cs->grid, (n_pages + chunk - 1) / chunk));
+	const uint32_t per_round = chunk * blocks;
+	const uint32_t rounds = std::max(1u, (n_pages + per_round - 1) / per_round);
+	*chunk_out = chunk; *blocks_out = blocks; *rpb_out = rounds * chunk;
+}
+
+struct Exchange { uint32_t epoch; }; // non-null: store mask rows + counts into every rank's slab (peer memory)
+
+int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, const Exchange* xchg = nullptr) {
 	lb200_ctx* ctx = cs->ctx;
 	lb::CullingHost& h = cs->host;
+	const bool had_dirty = h.all_dirty || !h.dirty_list.empty() || !cs->d_counters;
 	int rc = flushPages(cs);
 	if (rc) return rc;
 
@@ -345,19 +361,46 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type) 
 	const size_t off = (size_t)r * cs->dev_cap;
 	uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
 	uint32_t* nxt = cs->d_counters + (size_t)(cs->parity ^ 1) * COUNTER_WORDS;
-	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
-	uint32_t chunk = (h.high_water + cs->grid - 1) / cs->grid;
-	chunk = std::max(32u, std::min((uint32_t)cs->threads, chunk));
+	uint32_t chunk, blocks, rpb;
+	cullGeometry(cs, h.high_water, &chunk, &blocks, &rpb);
 	P.chunk = chunk;
+	P.rows_per_block = rpb;
+	P.n_ranks = 0; P.rank = 0; P.epoch = 0; P.done_counter = nullptr;
+	for (int r = 0; r < LB200_MAX_RANKS; ++r) { P.xdst[r] = nullptr; P.xflags[r] = nullptr; }
+	if (xchg) {
+		lb200_ctx::Peer& peer = ctx->peer;
+		P.n_ranks = (uint32_t)ctx->n_ranks; P.rank = (uint32_t)ctx->rank; P.epoch = xchg->epoch; P.done_counter = peer.done_counter;
+		for (int r = 0; r < ctx->n_ranks; ++r) {
+			P.xdst[r] = peer.gather[xchg->epoch & 1u][r] + peer.slab_words * (size_t)ctx->rank;
+			P.xflags[r] = peer.flags[r];
+		}
+	}
 	static const bool no_mask = getenv("LB200_NO_PLANE_MASKING") != nullptr;
 	P.plane_masking = (h.n_bad_radius == 0 && !no_mask) ? 1u : 0u;
 	static const bool pf_ids = getenv("LB200_PREFETCH_TEST_IDS") ? atoi(getenv("LB200_PREFETCH_TEST_IDS")) != 0 : false;
 	P.prefetch_test_ids = pf_ids ? 1u : 0u;
-	const unsigned blocks = (unsigned)std::max(1u, std::min((uint32_t)cs->grid, (h.high_water + chunk - 1) / chunk));
-	cull_pages_kernel<256><<<blocks, 256, 0, ctx->stream>>>(P, cs->d_desc + off, cs->d_spheres + off * PAGE_SLOTS, cs->d_entities + off * PAGE_SLOTS,
-		cs->d_out_ids, cur, nxt, cs->d_mask);
+	// Programmatic stream serialization: the kernel's prologue (up to cudaGridDependencySynchronize) reads only the page descriptors
+	// and issues L2 prefetches of page data.  Those arrays are written by flushPages alone, so unless this call uploaded something the
+	// prologue may overlap the tail of whatever kernel precedes it on the stream — for back-to-back views (main, shadow cascades,
+	// lights) that is the previous cull, which releases its dependents at its first instruction.
+	static const bool no_pdl = getenv("LB200_NO_PDL") != nullptr;
+	const bool pdl = !no_pdl && !had_dirty && !xchg;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(blocks);
+	cfg.blockDim = dim3(256);
+	cfg.stream = ctx->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl ? 1 : 0;
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cull_pages_kernel<256>, P, (const lb200_page_desc*)(cs->d_desc + off),
+		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), cs->d_out_ids, cur, nxt,
+		xchg ? (uint32_t*)nullptr : cs->d_mask));
 	LB200_CHECK_LAUNCH(ctx);
 	cs->last_pages = h.high_water;
+	cs->last_blocks = blocks;
+	cs->last_rows_per_block = rpb;
 	return LB200_OK;
 }
 
@@ -480,6 +523,10 @@ int lb200_culling_get_page(const lb200_culling* cs, uint32_t page, double origin
 	return LB200_OK;
 }
 
+int32_t lb200_culling_page_id(const lb200_culling* cs, uint32_t page) {
+	return cs && page < cs->host.cells.size() ? (int32_t)cs->host.cells[page] : -1;
+}
+
 int lb200_culling_flush(lb200_culling* cs) {
 	if (!cs) return LB200_ERR_INVALID;
 	if (!cs->ctx) { return LB200_ERR_NO_DEVICE; }
@@ -559,10 +606,16 @@ int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t 
 	const lb::CullingHost& h = cs->host;
 	const size_t n = h.cells.size();
 	if (capacity_words < n * 8) return LB200_ERR_CAPACITY;
-	std::vector<uint32_t> tmp((size_t)h.high_water * 8);
+	if (!cs->last_blocks) { lb200_set_error(cs->ctx, "read_bitmask needs a preceding cull"); return LB200_ERR_STATE; }
+	std::vector<uint32_t> tmp((size_t)cs->last_blocks * cs->last_rows_per_block * 8);
 	LB200_CUDA(cs->ctx, cudaMemcpyAsync(tmp.data(), cs->d_mask, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, cs->ctx->stream));
 	LB200_CUDA(cs->ctx, cudaStreamSynchronize(cs->ctx->stream));
-	for (size_t i = 0; i < n; ++i) memcpy(out_words + 8 * i, tmp.data() + 8 * (size_t)h.cells[i], sizeof(uint32_t) * 8);
+	for (size_t i = 0; i < n; ++i) {
+		const uint32_t p = h.cells[i];
+		if (p >= cs->last_pages) { memset(out_words + 8 * i, 0, sizeof(uint32_t) * 8); continue; } // page created after the last cull
+		const size_t row = (size_t)(p % cs->last_blocks) * cs->last_rows_per_block + p / cs->last_blocks;
+		memcpy(out_words + 8 * i, tmp.data() + 8 * row, sizeof(uint32_t) * 8);
+	}
 	return LB200_OK;
 }
 
@@ -664,6 +717,48 @@ uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, uint32_t sla
 	if (!cs || !cs->ctx) return 0;
 	const lb200_ctx::Peer& peer = cs->ctx->peer;
 	return (peer.ready && 256 + (size_t)slab_ids <= peer.slab_words) ? (uint32_t)peer.slab_words : 256 + slab_ids;
+}
+
+int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
+	const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words)
+{
+	if (!cs || !frustum) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	lb200_ctx* ctx = cs->ctx;
+	lb200_ctx::Peer& peer = ctx->peer;
+	if (!peer.ready) { lb200_set_error(ctx, "cull_exchange needs lb200_comm_enable_p2p"); return LB200_ERR_STATE; }
+	if (cs->host.cells.empty()) { lb200_set_error(ctx, "cull_exchange on an empty culling system"); return LB200_ERR_STATE; }
+	int rc = ensureDevice(cs);
+	if (rc) return rc;
+	uint32_t chunk, blocks, rpb;
+	cullGeometry(cs, cs->host.high_water, &chunk, &blocks, &rpb);
+	if (XHEADER_WORDS + 8 * (size_t)blocks * rpb > peer.slab_words) {
+		lb200_set_error(ctx, "exchange slab too small: %zu words needed, %zu mapped", XHEADER_WORDS + 8 * (size_t)blocks * rpb, peer.slab_words);
+		return LB200_ERR_CAPACITY;
+	}
+	Exchange x;
+	x.epoch = ++peer.epoch;
+	rc = launchCull(cs, frustum, type, &x);
+	if (rc) return rc;
+	cs->parity ^= 1;
+	cs->has_last = false;
+	if (!cs->d_gather_counts) {
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
+		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
+	}
+	wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, cs->d_gather_counts);
+	LB200_CHECK_LAUNCH(ctx);
+	if (out_dev_ids) *out_dev_ids = cs->d_out_ids;
+	if (out_dev_slabs) *out_dev_slabs = peer.gather[x.epoch & 1u][ctx->rank];
+	if (out_slab_stride_words) *out_slab_stride_words = (uint32_t)peer.slab_words;
+	return LB200_OK;
+}
+
+uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs) {
+	if (!cs || !cs->ctx || ensureDevice(cs) != LB200_OK) return 0;
+	uint32_t chunk, blocks, rpb;
+	cullGeometry(cs, cs->host.high_water, &chunk, &blocks, &rpb);
+	return XHEADER_WORDS + 8u * blocks * rpb;
 }
 
 int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_ids, uint32_t* out_counts) {

@@ -278,6 +278,7 @@ int lb200_hierarchy_propagate(lb200_hierarchy* h) {
 		propagate_small_levels_kernel<<<1, SMALL_THREADS, 0, ctx->stream>>>(S, h->d_parent, h->L, h->G);
 		LB200_CHECK_LAUNCH(ctx);
 	}
+	bool chained = S.n != 0; // the first kernel of a propagate is a plain launch: whatever precedes it has fully completed
 	for (; l < n_levels; ++l) {
 		const uint32_t begin = h->level_start[l], end = h->level_start[l + 1];
 		if (end == begin) continue;
@@ -289,7 +290,8 @@ int lb200_hierarchy_propagate(lb200_hierarchy* h) {
 		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		attr[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = attr;
-		cfg.numAttrs = 1;
+		cfg.numAttrs = chained ? 1 : 0;
+		chained = true;
 		LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, propagate_level_kernel, begin, end, (const int*)h->d_parent, h->L, h->G));
 		LB200_CHECK_LAUNCH(ctx);
 	}

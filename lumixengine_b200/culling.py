@@ -219,6 +219,33 @@ class CullingSystem:
         self._err(self.L.lb200_culling_cull_gather(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(slab_ids), C.byref(dev)))
         return dev.value or 0
 
+    def page_ids(self):
+        """Device page id of every m_cells entry (row of the page in the HBM arrays and the visibility bitmask)."""
+        return np.array([self.L.lb200_culling_page_id(self.h, C.c_uint32(i)) for i in range(self.page_count())], np.int64)
+
+    def exchange_slab_words(self):
+        """u32 words one rank contributes to the bitmask exchange; pass max over ranks - 256 to Context.comm_enable_p2p."""
+        return int(self.L.lb200_culling_exchange_slab_words(self.h))
+
+    def cull_exchange(self, frustum, type=TYPE_ALL):
+        """Per-frame multi-GPU step, asynchronous: the cull kernel stores visibility rows + per-type counts into every rank's memory
+        (NVLink peer stores); ids stay sharded.  Returns (device ids pointer, device slabs pointer, slab stride in words)."""
+        ids, slabs, stride = vp(), vp(), C.c_uint32()
+        self._err(self.L.lb200_culling_cull_exchange(self.h, C.byref(frustum), C.c_uint8(type), C.byref(ids), C.byref(slabs), C.byref(stride)))
+        return (ids.value or 0), (slabs.value or 0), int(stride.value)
+
+    def read_exchanged(self, slabs_ptr, stride, n_ranks):
+        """Host copy of the exchanged slabs -> per rank dict(counts[256], n_pages, blocks, rows_per_block, mask[n_pages, 8] by page id)."""
+        host = self.ctx.copy_to_host(slabs_ptr, stride * n_ranks, np.uint32).reshape(n_ranks, stride)
+        out = []
+        for r in range(n_ranks):
+            n_pages, blocks, rpb, chunk = (int(v) for v in host[r, 256:260])
+            rows = host[r, 264:264 + 8 * blocks * rpb].reshape(blocks * rpb, 8)
+            p = np.arange(n_pages)
+            out.append(dict(counts=host[r, :256].copy(), n_pages=n_pages, blocks=blocks, rows_per_block=rpb, chunk=chunk,
+                            mask=rows[(p % max(blocks, 1)) * rpb + p // max(blocks, 1)].copy()))
+        return out
+
     def read_gathered(self, dev_ptr, slab_ids, n_ranks, stride=None):
         """Host copy of the gathered buffer -> (slabs[r] = ids of rank r, counts[n_ranks, 256])."""
         stride = int(self.L.lb200_culling_gather_stride_words(self.h, C.c_uint32(slab_ids))) if stride is None else stride
