@@ -149,9 +149,13 @@ LB200_API int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum*
  * read back and the call is fully asynchronous on the context stream (result may be NULL). */
 LB200_API int lb200_culling_cull_device(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
 	lb200_cull_result* result, int want_counts);
-/* n back-to-back asynchronous culls of the same view issued from one call (a frame culls several views — main, shadow cascades, lights,
- * pipeline.cpp:996-1063,3380 — and a benchmark wants device time without per-call host overhead); results of the last one stay in HBM. */
+/* n asynchronous culls issued from one call (a frame culls several views — main, shadow cascades, lights, pipeline.cpp:996-1063,3380,
+ * which the engine runs concurrently from jobs — and a benchmark wants device time without per-call host overhead).  Consecutive culls
+ * are independent: they go to different internal streams and output lanes, so the device overlaps them; the call forks from and joins
+ * back into the context stream.  Results of the last one stay in HBM: lb200_culling_last_result / lb200_culling_read_bitmask. */
 LB200_API int lb200_culling_cull_device_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n);
+/* Device id list (per-type segments) and counts of the cull issued last, whichever entry point issued it.  Synchronises the stream. */
+LB200_API int lb200_culling_last_result(lb200_culling* cs, const uint32_t** out_dev_ids, lb200_cull_result* result);
 /* Push pending page edits to HBM now (otherwise done lazily by the next cull). */
 LB200_API int lb200_culling_flush(lb200_culling* cs);
 /* Visibility bitmask of the last cull: bit (page*256 + slot); 8 words per page.  Copies page_count*8 words. */

@@ -203,8 +203,6 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 			}
 			s_slot[tid] = (uint16_t)my_slot;
 		}
-		// nothing above wrote global memory; everything below may (ids, masks, counters) and must see the previous kernel's results
-		if (round == 0) cudaGridDependencySynchronize();
 		__syncthreads();
 		const uint32_t n_work = s_nwork;
 
@@ -282,6 +280,9 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 				s_bal[w][ROWS] = page_visible;
 			}
 		}
+		// nothing above wrote global memory (A and B read scene data, results sit in shared memory); everything below does
+		// (counters, ids, mask rows) and has to wait for the previous kernel of the stream
+		if (round == 0) cudaGridDependencySynchronize();
 		// ---------------- C. claim: one global atomic per (warp, type) — no block barrier between B, C and D ----------------
 		// lane i stands for the warp's i-th page (w = warp + i * CULL_WARPS; at most 32 per warp since chunk <= CULL_THREADS)
 		__syncwarp();

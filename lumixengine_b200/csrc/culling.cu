@@ -184,13 +184,27 @@ struct lb200_culling {
 	float4* d_spheres = nullptr;
 	int* d_entities = nullptr;
 	lb200_page_desc* d_desc = nullptr;
-	uint32_t* d_out_ids = nullptr;
+	// Output lanes: cull number `seq` writes ids to d_out_ids[seq % lanes], mask rows to d_mask[seq % lanes], counts to counter buffer
+	// seq % (2 * lanes) and zeroes counter buffer (seq + lanes) % (2 * lanes) for the cull `lanes` later.  Culls that share buffers are
+	// `lanes` apart and run on the same stream; the ones in between are independent and may run concurrently (cull_device_n).
+	static constexpr uint32_t MAX_LANES = 4;
+	uint32_t lanes = 3;
+	cudaStream_t lane_stream[MAX_LANES] = {};
+	cudaEvent_t lane_event[MAX_LANES] = {};
+	cudaEvent_t fork_event = nullptr;
+	uint64_t seq = 0;
+	uint32_t* d_out_ids = nullptr;  // lanes * out_cap
 	uint32_t out_cap = 0;
-	uint32_t* d_mask = nullptr;
-	uint32_t* d_counters = nullptr; // 2 * COUNTER_WORDS
+	uint32_t* d_mask = nullptr;     // lanes * mask_words
+	size_t mask_words = 0;
+	uint32_t* d_counters = nullptr; // 2 * lanes * COUNTER_WORDS
+	// the cull issued last
+	uint32_t* last_counters = nullptr;
+	uint32_t* last_out = nullptr;
+	uint32_t* last_mask = nullptr;
 	uint32_t* h_counters = nullptr; // pinned, COUNTER_WORDS
-	uint32_t parity = 0;
-	int grid = 0;
+	int grid = 0;       // resident blocks of a cull that has the device to itself
+	int grid_lanes = 0; // resident blocks of a cull issued by cull_device_n (runs next to its neighbours)
 	int threads = 256;
 	// staging for sparse dirty uploads
 	uint8_t* h_stage = nullptr;
@@ -218,14 +232,20 @@ int ensureDevice(lb200_culling* cs) {
 	lb::CullingHost& h = cs->host;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (!cs->d_counters) {
-		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * COUNTER_WORDS));
-		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * COUNTER_WORDS, ctx->stream));
+		if (const char* e = getenv("LB200_CULL_LANES")) cs->lanes = (uint32_t)std::max(1, std::min((int)lb200_culling::MAX_LANES, atoi(e)));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS));
+		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS, ctx->stream));
 		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocDefault));
 		cs->threads = 256; // 512-thread blocks measured no better (profiles/)
 		int per_sm = 0;
 		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<256>, 256, 0));
 		if (per_sm < 1) per_sm = 1;
 		cs->grid = ctx->sm_count * per_sm;
+		// cull_device_n runs independent culls concurrently: half-occupancy grids let two of them share every SM, so one cull's
+		// classify / test phases fill the memory pipeline while another is in its claim / write phases (measured: profiles/)
+		int lane_per_sm = std::min(per_sm, 2);
+		if (const char* e = getenv("LB200_CULL_BLOCKS_PER_SM")) lane_per_sm = std::max(1, std::min(per_sm, atoi(e))); // tuning knob
+		cs->grid_lanes = ctx->sm_count * lane_per_sm;
 	}
 	if (cs->dev_cap < h.high_water) {
 		uint32_t cap = cs->dev_cap ? cs->dev_cap : 1024;
@@ -238,7 +258,8 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_entities, sizeof(int) * PAGE_SLOTS * (size_t)cap * R));
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_desc, sizeof(lb200_page_desc) * (size_t)cap * R));
 		// block-transposed rows (cull_kernel.cuh phase E): at most one chunk of padding rows per block
-		LB200_CUDA(ctx, cudaMalloc(&cs->d_mask, sizeof(uint32_t) * 8 * ((size_t)cap + 256 * (size_t)cs->grid)));
+		cs->mask_words = 8 * ((size_t)cap + 256 * (size_t)cs->grid);
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_mask, sizeof(uint32_t) * cs->mask_words * cs->lanes));
 		// free / never-used pages must read count == 0
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_desc, 0, sizeof(lb200_page_desc) * (size_t)cap * R, ctx->stream));
 		cs->dev_cap = cap;
@@ -250,7 +271,7 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		cudaFree(cs->d_out_ids);
 		cs->d_out_ids = nullptr;
-		LB200_CUDA(ctx, cudaMalloc(&cs->d_out_ids, sizeof(uint32_t) * (size_t)cap));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_out_ids, sizeof(uint32_t) * (size_t)cap * cs->lanes));
 		cs->out_cap = cap;
 	}
 	return LB200_OK;
@@ -322,11 +343,11 @@ int flushPages(lb200_culling* cs) {
 }
 
 // rounds / rows per block of a cull over n_pages (the kernel's dealing: page = j * blocks + block)
-void cullGeometry(const lb200_culling* cs, uint32_t n_pages, uint32_t* chunk_out, uint32_t* blocks_out, uint32_t* rpb_out) {
+void cullGeometry(const lb200_culling* cs, uint32_t grid, uint32_t n_pages, uint32_t* chunk_out, uint32_t* blocks_out, uint32_t* rpb_out) {
 	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
-	uint32_t chunk = (n_pages + cs->grid - 1) / cs->grid;
+	uint32_t chunk = (n_pages + grid - 1) / grid;
 	chunk = std::max(32u, std::min((uint32_t)cs->threads, chunk));
-	const uint32_t blocks = std::max(1u, std::min((uint32_t)cs->grid, (n_pages + chunk - 1) / chunk));
+	const uint32_t blocks = std::max(1u, std::min(grid, (n_pages + chunk - 1) / chunk));
 	const uint32_t per_round = chunk * blocks;
 	const uint32_t rounds = std::max(1u, (n_pages + per_round - 1) / per_round);
 	*chunk_out = chunk; *blocks_out = blocks; *rpb_out = rounds * chunk;
@@ -334,7 +355,7 @@ void cullGeometry(const lb200_culling* cs, uint32_t n_pages, uint32_t* chunk_out
 
 struct Exchange { uint32_t epoch; }; // non-null: store mask rows + counts into every rank's slab (peer memory)
 
-int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, const Exchange* xchg = nullptr) {
+int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, const Exchange* xchg = nullptr, cudaStream_t stream = nullptr) {
 	lb200_ctx* ctx = cs->ctx;
 	lb::CullingHost& h = cs->host;
 	const bool had_dirty = h.all_dirty || !h.dirty_list.empty() || !cs->d_counters;
@@ -359,10 +380,13 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	const uint32_t r = cs->next_replica;
 	cs->next_replica = (cs->next_replica + 1) % cs->replicas;
 	const size_t off = (size_t)r * cs->dev_cap;
-	uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
-	uint32_t* nxt = cs->d_counters + (size_t)(cs->parity ^ 1) * COUNTER_WORDS;
+	const uint32_t L = cs->lanes;
+	uint32_t* cur = cs->d_counters + (size_t)(cs->seq % (2 * L)) * COUNTER_WORDS;
+	uint32_t* nxt = cs->d_counters + (size_t)((cs->seq + L) % (2 * L)) * COUNTER_WORDS;
+	uint32_t* out = cs->d_out_ids + (size_t)(cs->seq % L) * cs->out_cap;
+	uint32_t* mask = cs->d_mask + (size_t)(cs->seq % L) * cs->mask_words;
 	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, h.high_water, &chunk, &blocks, &rpb);
+	cullGeometry(cs, (uint32_t)(stream ? cs->grid_lanes : cs->grid), h.high_water, &chunk, &blocks, &rpb);
 	P.chunk = chunk;
 	P.rows_per_block = rpb;
 	P.n_ranks = 0; P.rank = 0; P.epoch = 0; P.done_counter = nullptr;
@@ -388,16 +412,18 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(blocks);
 	cfg.blockDim = dim3(256);
-	cfg.stream = ctx->stream;
+	cfg.stream = stream ? stream : ctx->stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = pdl ? 1 : 0;
 	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cull_pages_kernel<256>, P, (const lb200_page_desc*)(cs->d_desc + off),
-		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), cs->d_out_ids, cur, nxt,
-		xchg ? (uint32_t*)nullptr : cs->d_mask));
+		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), out, cur, nxt,
+		xchg ? (uint32_t*)nullptr : mask));
 	LB200_CHECK_LAUNCH(ctx);
+	cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask;
+	++cs->seq;
 	cs->last_pages = h.high_water;
 	cs->last_blocks = blocks;
 	cs->last_rows_per_block = rpb;
@@ -406,7 +432,7 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 
 int readCounts(lb200_culling* cs, lb200_cull_result* result) {
 	lb200_ctx* ctx = cs->ctx;
-	const uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
+	const uint32_t* cur = cs->last_counters;
 	LB200_CUDA(ctx, cudaMemcpyAsync(cs->h_counters, cur, sizeof(uint32_t) * COUNTER_WORDS, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	lb200_cull_result& res = cs->last;
@@ -446,6 +472,11 @@ void lb200_culling_destroy(lb200_culling* cs) {
 	if (cs->ctx) {
 		cudaSetDevice(cs->ctx->device);
 		cudaStreamSynchronize(cs->ctx->stream);
+		for (uint32_t l = 0; l < lb200_culling::MAX_LANES; ++l) {
+			if (cs->lane_stream[l]) { cudaStreamSynchronize(cs->lane_stream[l]); cudaStreamDestroy(cs->lane_stream[l]); }
+			if (cs->lane_event[l]) cudaEventDestroy(cs->lane_event[l]);
+		}
+		if (cs->fork_event) cudaEventDestroy(cs->fork_event);
 		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_out_ids); cudaFree(cs->d_mask);
 		cudaFree(cs->d_counters); cudaFree(cs->d_stage); cudaFree(cs->d_gather_ids); cudaFree(cs->d_gather_counts); cudaFree(cs->d_slab);
 		if (cs->h_counters) cudaFreeHost(cs->h_counters);
@@ -557,10 +588,9 @@ int lb200_culling_cull_device(lb200_culling* cs, const lb200_shifted_frustum* fr
 	}
 	int rc = launchCull(cs, frustum, type);
 	if (rc) return rc;
-	if (out_dev_ids) *out_dev_ids = cs->d_out_ids;
+	if (out_dev_ids) *out_dev_ids = cs->last_out;
 	if (want_counts) rc = readCounts(cs, result);
 	else cs->has_last = false;
-	cs->parity ^= 1;
 	return rc;
 }
 
@@ -568,13 +598,46 @@ int lb200_culling_cull_device_n(lb200_culling* cs, const lb200_shifted_frustum* 
 	if (!cs || !frustum) return LB200_ERR_INVALID;
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
 	if (cs->host.cells.empty()) return LB200_OK;
-	for (uint32_t i = 0; i < n; ++i) {
-		const int rc = launchCull(cs, frustum, type);
-		if (rc) return rc;
-		cs->parity ^= 1;
-	}
 	cs->has_last = false;
+	lb200_ctx* ctx = cs->ctx;
+	int rc = flushPages(cs); // uploads (if any) go to the context stream before the lanes fork from it
+	if (rc) return rc;
+	const uint32_t L = std::min(cs->lanes, n);
+	if (L < 2) {
+		for (uint32_t i = 0; i < n; ++i) {
+			rc = launchCull(cs, frustum, type);
+			if (rc) return rc;
+		}
+		return LB200_OK;
+	}
+	// independent views: consecutive culls go to different streams and different output lanes, so the device overlaps them freely;
+	// culls `lanes` apart share buffers and stay ordered on their stream.  Fork from / join into the context stream.
+	if (!cs->fork_event) {
+		LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->fork_event, cudaEventDisableTiming));
+		for (uint32_t l = 0; l < cs->lanes; ++l) {
+			LB200_CUDA(ctx, cudaStreamCreateWithFlags(&cs->lane_stream[l], cudaStreamNonBlocking));
+			LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->lane_event[l], cudaEventDisableTiming));
+		}
+	}
+	LB200_CUDA(ctx, cudaEventRecord(cs->fork_event, ctx->stream));
+	for (uint32_t l = 0; l < cs->lanes; ++l) LB200_CUDA(ctx, cudaStreamWaitEvent(cs->lane_stream[l], cs->fork_event, 0));
+	for (uint32_t i = 0; i < n; ++i) {
+		rc = launchCull(cs, frustum, type, nullptr, cs->lane_stream[cs->seq % cs->lanes]);
+		if (rc) return rc;
+	}
+	for (uint32_t l = 0; l < cs->lanes; ++l) {
+		LB200_CUDA(ctx, cudaEventRecord(cs->lane_event[l], cs->lane_stream[l]));
+		LB200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cs->lane_event[l], 0));
+	}
 	return LB200_OK;
+}
+
+int lb200_culling_last_result(lb200_culling* cs, const uint32_t** out_dev_ids, lb200_cull_result* result) {
+	if (!cs) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	if (!cs->last_counters) { lb200_set_error(cs->ctx, "last_result needs a preceding cull"); return LB200_ERR_STATE; }
+	if (out_dev_ids) *out_dev_ids = cs->last_out;
+	return readCounts(cs, result);
 }
 
 int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity,
@@ -608,7 +671,7 @@ int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t 
 	if (capacity_words < n * 8) return LB200_ERR_CAPACITY;
 	if (!cs->last_blocks) { lb200_set_error(cs->ctx, "read_bitmask needs a preceding cull"); return LB200_ERR_STATE; }
 	std::vector<uint32_t> tmp((size_t)cs->last_blocks * cs->last_rows_per_block * 8);
-	LB200_CUDA(cs->ctx, cudaMemcpyAsync(tmp.data(), cs->d_mask, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, cs->ctx->stream));
+	LB200_CUDA(cs->ctx, cudaMemcpyAsync(tmp.data(), cs->last_mask, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, cs->ctx->stream));
 	LB200_CUDA(cs->ctx, cudaStreamSynchronize(cs->ctx->stream));
 	for (size_t i = 0; i < n; ++i) {
 		const uint32_t p = h.cells[i];
@@ -662,7 +725,7 @@ int packAndGather(lb200_culling* cs, const uint32_t* cur, uint32_t slab_ids) {
 	PackParams PP;
 	memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
 	PP.slab_ids = slab_ids;
-	pack_slab_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, cs->d_slab);
+	pack_slab_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(PP, cur, cs->last_out, cs->d_slab);
 	LB200_CHECK_LAUNCH(ctx);
 	return lb200_comm_allgather_u32(ctx, cs->d_slab, cs->d_gather_ids, 256 + (size_t)slab_ids);
 }
@@ -678,8 +741,7 @@ int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* fr
 	if (cs->host.cells.empty()) { lb200_set_error(ctx, "cull_gather on an empty culling system"); return LB200_ERR_STATE; }
 	int rc = launchCull(cs, frustum, type);
 	if (rc) return rc;
-	const uint32_t* cur = cs->d_counters + (size_t)cs->parity * COUNTER_WORDS;
-	cs->parity ^= 1;
+	const uint32_t* cur = cs->last_counters;
 	cs->has_last = false;
 	lb200_ctx::Peer& peer = ctx->peer;
 	if (peer.ready && 256 + (size_t)slab_ids <= peer.slab_words) {
@@ -694,7 +756,7 @@ int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* fr
 			PP.dst[r] = r < ctx->n_ranks ? peer.gather[epoch & 1u][(dbg & 2u) ? ctx->rank : r] + peer.slab_words * (size_t)ctx->rank : nullptr;
 			PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
 		}
-		pack_push_kernel<<<ctx->sm_count * pushGridMul(), 256, 0, ctx->stream>>>(PP, cur, cs->d_out_ids, peer.done_counter);
+		pack_push_kernel<<<ctx->sm_count * pushGridMul(), 256, 0, ctx->stream>>>(PP, cur, cs->last_out, peer.done_counter);
 		LB200_CHECK_LAUNCH(ctx);
 		if (!cs->d_gather_counts) {
 			LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
@@ -731,7 +793,7 @@ int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* 
 	int rc = ensureDevice(cs);
 	if (rc) return rc;
 	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, cs->host.high_water, &chunk, &blocks, &rpb);
+	cullGeometry(cs, (uint32_t)cs->grid, cs->host.high_water, &chunk, &blocks, &rpb);
 	if (XHEADER_WORDS + 8 * (size_t)blocks * rpb > peer.slab_words) {
 		lb200_set_error(ctx, "exchange slab too small: %zu words needed, %zu mapped", XHEADER_WORDS + 8 * (size_t)blocks * rpb, peer.slab_words);
 		return LB200_ERR_CAPACITY;
@@ -740,7 +802,6 @@ int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* 
 	x.epoch = ++peer.epoch;
 	rc = launchCull(cs, frustum, type, &x);
 	if (rc) return rc;
-	cs->parity ^= 1;
 	cs->has_last = false;
 	if (!cs->d_gather_counts) {
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
@@ -748,7 +809,7 @@ int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* 
 	}
 	wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, cs->d_gather_counts);
 	LB200_CHECK_LAUNCH(ctx);
-	if (out_dev_ids) *out_dev_ids = cs->d_out_ids;
+	if (out_dev_ids) *out_dev_ids = cs->last_out;
 	if (out_dev_slabs) *out_dev_slabs = peer.gather[x.epoch & 1u][ctx->rank];
 	if (out_slab_stride_words) *out_slab_stride_words = (uint32_t)peer.slab_words;
 	return LB200_OK;
@@ -757,7 +818,7 @@ int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* 
 uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs) {
 	if (!cs || !cs->ctx || ensureDevice(cs) != LB200_OK) return 0;
 	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, cs->host.high_water, &chunk, &blocks, &rpb);
+	cullGeometry(cs, (uint32_t)cs->grid, cs->host.high_water, &chunk, &blocks, &rpb);
 	return XHEADER_WORDS + 8u * blocks * rpb;
 }
 
@@ -766,8 +827,7 @@ int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t
 	lb200_ctx* ctx = cs->ctx;
 	if (!ctx) return LB200_ERR_NO_DEVICE;
 	if (!cs->last_pages) { lb200_set_error(ctx, "allgather needs a preceding cull"); return LB200_ERR_STATE; }
-	// the preceding cull's counters: the buffer the next cull will NOT use
-	const uint32_t* cur = cs->d_counters + (size_t)(cs->parity ^ 1) * COUNTER_WORDS;
+	const uint32_t* cur = cs->last_counters; // the preceding cull's
 	int rc = packAndGather(cs, cur, slab_ids);
 	if (rc) return rc;
 	const size_t words = 256 + (size_t)slab_ids;

@@ -188,8 +188,15 @@ class CullingSystem:
         return (dev.value or 0), (res if want_counts else None)
 
     def cull_device_n(self, frustum, n, type=TYPE_ALL):
-        """n back-to-back asynchronous culls issued from C (no per-call Python overhead)."""
+        """n independent asynchronous culls issued from C: consecutive ones run on different streams / output lanes and overlap."""
         self._err(self.L.lb200_culling_cull_device_n(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(n)))
+
+    def last_result(self):
+        """(device ids pointer, lb200_cull_result) of the cull issued last (e.g. the last one of cull_device_n)."""
+        dev = vp()
+        res = _lib.CullResult()
+        self._err(self.L.lb200_culling_last_result(self.h, C.byref(dev), C.byref(res)))
+        return (dev.value or 0), res
 
     def flush(self):
         self._err(self.L.lb200_culling_flush(self.h))

@@ -192,3 +192,47 @@ def test_far_from_world_origin_and_negative_radius(ctx, oracle):
     res = cs.cull(f)
     oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f))
     _assert_same(res, oids, otys)
+
+
+def test_overlapped_views_keep_results_apart(ctx, oracle):
+    """cull_device_n issues independent culls on several streams / output lanes (and with programmatic dependent launch); whatever
+    overlaps, the cull issued last must read exactly like a lone cull, also when single culls and batches interleave."""
+    scene = scenes.cull_scene(400_000, (3000.0, 300.0, 3000.0), seed=31, big_fraction=0.004, type_probs=(0.7, 0.2, 0.1))
+    cs, oc = _both(ctx, oracle, scene)
+    a = scenes.c1_frustum_args()
+    views = [lb.frustum_perspective(**dict(a, far=2500.0)),
+             lb.frustum_perspective(**dict(a, position=(800.0, 0.0, 900.0), direction=(-0.5, 0.0, -0.8), far=1700.0)),
+             lb.frustum_ortho((0.0, 0.0, 4000.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0), 3000.0, 3000.0, 0.0, 8000.0)]
+    base = np.concatenate([[0], np.cumsum(np.bincount(scene["types"], minlength=256))])
+
+    def check_last(f):
+        ptr, res = cs.last_result()
+        oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f))
+        assert res.total == len(oids) > 0
+        for t in range(3):
+            got = ctx.copy_to_host(ptr + 4 * int(base[t]), int(res.type_count[t]), np.uint32)
+            assert np.array_equal(np.sort(got).astype(np.int64), np.sort(oids[otys == t]).astype(np.int64))
+        bits = cs.read_bitmask()
+        assert int(np.unpackbits(bits.view(np.uint8)).sum()) == len(oids)
+
+    for n in (1, 2, 3, 4, 7, 16):
+        for f in views:
+            cs.cull_device_n(f, n)
+            check_last(f)
+    # batches of different views back to back, nothing read in between; then a single cull right behind a batch
+    cs.cull_device_n(views[0], 5)
+    cs.cull_device_n(views[2], 4)
+    cs.cull_device_n(views[1], 3)
+    check_last(views[1])
+    cs.cull_device_n(views[2], 6)
+    cs.cull_device(views[0], want_counts=False)
+    check_last(views[0])
+    assert np.array_equal(np.sort(cs.cull(views[2]).ids), np.sort(oc.cull(lb.culling.frustum_bytes(views[2]))[0]).astype(np.uint32))
+    # an edit between batches goes through the context stream before the lanes fork
+    moved = scene["entities"][:5000]
+    newpos = scene["pos"][:5000] + np.array([40.0, 0.0, -25.0])
+    cs.set(moved, newpos, scene["radius"][:5000])
+    oc.set(moved, newpos, scene["radius"][:5000])
+    cs.cull_device_n(views[0], 5)
+    check_last(views[0])
+    cs.close()
