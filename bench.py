@@ -32,6 +32,28 @@ N_ENTITIES = 10_000_000
 REPLICAS = 8  # scene copies rotated through by successive culls: 8 x ~200 MB > 126 MB L2
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded into this process print banners to fd 1 (NCCL's version line at any
+    NCCL_DEBUG level >= VERSION, glog, ...): point fd 1 at stderr for the whole run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -124,7 +146,7 @@ def reference_arm(a, rank):
         "e2e": {"value": r["value"], "unit": "M entities/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def time_region(ctx, fn, steps):
@@ -355,7 +377,7 @@ def ours(a, rank, world):
             assert cb["visible"] == visible, "CPU reference and GPU disagree on the visible count"
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": "M entities/s", "cores": 0, "kind": "reference", "sample": "failed: " + repr(e)}
-    print(json.dumps(line))
+    emit(line)
     ctx.close()
     if dist:
         dist.destroy_process_group()
@@ -370,6 +392,7 @@ def main():
     ap.add_argument("--only-cull", action="store_true", help="skip the secondary paths and the CPU baseline leg (profiling runs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":

@@ -202,6 +202,8 @@ LB200_API uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, ui
  *             bit s of the 256-bit row = slot s of the page is visible (slots >= 200 are 0) */
 LB200_API int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
                                           const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words);
+/* n exchange steps issued from one call (no per-step host overhead of the caller). */
+LB200_API int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n);
 LB200_API uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -225,6 +227,10 @@ LB200_API int lb200_hierarchy_get_globals(lb200_hierarchy* h, lb200_transform* o
 /* RenderModuleImpl::onModelInstanceMoved, render_module.cpp:1544-1554: world sphere per node =
  * (global.pos, bounding_radius * max(scale)); out_pos3 n*3 doubles, out_radius n floats (host). */
 LB200_API int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius, double* out_pos3, float* out_radius);
+/* World::getRelativeMatrix (src/engine/world.cpp:370-377) of every node against one base position (the camera): out_matrices = n x 16
+ * floats, column-major like Matrix (math.h:329-392), indexed like `parents`.  Consumers of the propagated transforms
+ * (pipeline.cpp instance setup) take these instead of calling getRelativeMatrix per entity. */
+LB200_API int lb200_hierarchy_get_relative_matrices(lb200_hierarchy* h, const double base_pos[3], float* out_matrices);
 LB200_API uint64_t lb200_hierarchy_algorithmic_bytes(const lb200_hierarchy* h);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -151,6 +151,10 @@ __global__ void __launch_bounds__(256) pack_push_kernel(const __grid_constant__ 
 
 // Wait until every rank's slab of `epoch` has landed in this rank's gather buffer.  Spins on local memory; gives up after ~4 s.
 __global__ void wait_peers_kernel(const uint32_t* flags, uint32_t n_ranks, uint32_t epoch, uint32_t* timed_out) {
+	// Launched with programmatic stream serialization behind the kernel that publishes this rank's flag, and releasing its own
+	// dependents at once: the next cull's read-only prologue runs while this block spins.  Its own flag is among the awaited ones,
+	// so the wait cannot end before the local producer has published; the grid dependency below covers that kernel's last stores.
+	cudaTriggerProgrammaticLaunchCompletion();
 	if (threadIdx.x < n_ranks) {
 		const volatile uint32_t* f = flags + (epoch & 1u) * LB200_MAX_RANKS + threadIdx.x;
 		const long long t0 = clock64();
@@ -158,6 +162,7 @@ __global__ void wait_peers_kernel(const uint32_t* flags, uint32_t n_ranks, uint3
 			if (clock64() - t0 > 8000000000ll) { *timed_out = 1; break; }
 		}
 	}
+	cudaGridDependencySynchronize();
 	__threadfence_system();
 }
 
@@ -386,7 +391,7 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	uint32_t* out = cs->d_out_ids + (size_t)(cs->seq % L) * cs->out_cap;
 	uint32_t* mask = cs->d_mask + (size_t)(cs->seq % L) * cs->mask_words;
 	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, (uint32_t)(stream ? cs->grid_lanes : cs->grid), h.high_water, &chunk, &blocks, &rpb);
+	cullGeometry(cs, (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid), h.high_water, &chunk, &blocks, &rpb);
 	P.chunk = chunk;
 	P.rows_per_block = rpb;
 	P.n_ranks = 0; P.rank = 0; P.epoch = 0; P.done_counter = nullptr;
@@ -408,7 +413,7 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	// prologue may overlap the tail of whatever kernel precedes it on the stream — for back-to-back views (main, shadow cascades,
 	// lights) that is the previous cull, which releases its dependents at its first instruction.
 	static const bool no_pdl = getenv("LB200_NO_PDL") != nullptr;
-	const bool pdl = !no_pdl && !had_dirty && !xchg;
+	const bool pdl = !no_pdl && !had_dirty;
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(blocks);
 	cfg.blockDim = dim3(256);
@@ -793,7 +798,7 @@ int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* 
 	int rc = ensureDevice(cs);
 	if (rc) return rc;
 	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, (uint32_t)cs->grid, cs->host.high_water, &chunk, &blocks, &rpb);
+	cullGeometry(cs, (uint32_t)cs->grid_lanes, cs->host.high_water, &chunk, &blocks, &rpb);
 	if (XHEADER_WORDS + 8 * (size_t)blocks * rpb > peer.slab_words) {
 		lb200_set_error(ctx, "exchange slab too small: %zu words needed, %zu mapped", XHEADER_WORDS + 8 * (size_t)blocks * rpb, peer.slab_words);
 		return LB200_ERR_CAPACITY;
@@ -807,18 +812,37 @@ int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* 
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
 	}
-	wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, cs->d_gather_counts);
-	LB200_CHECK_LAUNCH(ctx);
+	{
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(1);
+		cfg.blockDim = dim3(32);
+		cfg.stream = ctx->stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+		LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, wait_peers_kernel, (const uint32_t*)peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, cs->d_gather_counts));
+		LB200_CHECK_LAUNCH(ctx);
+	}
 	if (out_dev_ids) *out_dev_ids = cs->last_out;
 	if (out_dev_slabs) *out_dev_slabs = peer.gather[x.epoch & 1u][ctx->rank];
 	if (out_slab_stride_words) *out_slab_stride_words = (uint32_t)peer.slab_words;
 	return LB200_OK;
 }
 
+int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) {
+		const int rc = lb200_culling_cull_exchange(cs, frustum, type, nullptr, nullptr, nullptr);
+		if (rc) return rc;
+	}
+	return LB200_OK;
+}
+
 uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs) {
 	if (!cs || !cs->ctx || ensureDevice(cs) != LB200_OK) return 0;
 	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, (uint32_t)cs->grid, cs->host.high_water, &chunk, &blocks, &rpb);
+	cullGeometry(cs, (uint32_t)cs->grid_lanes, cs->host.high_water, &chunk, &blocks, &rpb);
 	return XHEADER_WORDS + 8u * blocks * rpb;
 }
 

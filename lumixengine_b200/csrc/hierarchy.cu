@@ -132,6 +132,30 @@ __global__ void __launch_bounds__(HT) spheres_kernel(SoaTransforms G, const uint
 	out_radius[node] = LB_FMUL(bounding_radius[node], m);
 }
 
+// World::getRelativeMatrix, world.cpp:370-377: rot.toMatrix(), translation = Vec3(pos - base), multiply3x3(scale).
+// One thread per node: 52 B of SoA globals in (coalesced), one 64-byte matrix out at the caller's node index (two full sectors).
+__global__ void __launch_bounds__(HT) relative_matrices_kernel(SoaTransforms G, const uint32_t* __restrict__ order, uint32_t n,
+	double bx, double by, double bz, float4* __restrict__ out)
+{
+	const uint32_t i = blockIdx.x * HT + threadIdx.x;
+	if (i >= n) return;
+	Rigid r;
+	r.pos = v3((float)LB_DSUB(G.px[i], bx), (float)LB_DSUB(G.py[i], by), (float)LB_DSUB(G.pz[i], bz));
+	const float4 q = G.rot[i];
+	r.rot = q4(q.x, q.y, q.z, q.w);
+	float m[16];
+	to_matrix(r, m);
+	const float sx = G.sx[i], sy = G.sy[i], sz = G.sz[i];
+	m[0] = LB_FMUL(m[0], sx); m[1] = LB_FMUL(m[1], sx); m[2] = LB_FMUL(m[2], sx);   // math.cpp:1207-1217
+	m[4] = LB_FMUL(m[4], sy); m[5] = LB_FMUL(m[5], sy); m[6] = LB_FMUL(m[6], sy);
+	m[8] = LB_FMUL(m[8], sz); m[9] = LB_FMUL(m[9], sz); m[10] = LB_FMUL(m[10], sz);
+	float4* dst = out + 4 * (size_t)order[i];
+	dst[0] = make_float4(m[0], m[1], m[2], m[3]);
+	dst[1] = make_float4(m[4], m[5], m[6], m[7]);
+	dst[2] = make_float4(m[8], m[9], m[10], m[11]);
+	dst[3] = make_float4(m[12], m[13], m[14], m[15]);
+}
+
 } // namespace
 
 struct lb200_hierarchy {
@@ -142,6 +166,7 @@ struct lb200_hierarchy {
 	int* d_parent = nullptr;           // level position -> parent's level position
 	SoaTransforms L, G;
 	lb200_transform* d_stage = nullptr; // n Transforms (API boundary)
+	float4* d_matrices = nullptr;       // n relative matrices (lb200_hierarchy_get_relative_matrices)
 	float* d_radius_in = nullptr;
 	double* d_sphere_pos = nullptr;
 	float* d_sphere_radius = nullptr;
@@ -241,7 +266,7 @@ void lb200_hierarchy_destroy(lb200_hierarchy* h) {
 	if (!h) return;
 	cudaSetDevice(h->ctx->device);
 	cudaStreamSynchronize(h->ctx->stream);
-	cudaFree(h->d_order); cudaFree(h->d_parent); cudaFree(h->d_stage); cudaFree(h->d_radius_in); cudaFree(h->d_sphere_pos); cudaFree(h->d_sphere_radius);
+	cudaFree(h->d_order); cudaFree(h->d_parent); cudaFree(h->d_stage); cudaFree(h->d_matrices); cudaFree(h->d_radius_in); cudaFree(h->d_sphere_pos); cudaFree(h->d_sphere_radius);
 	freeSoa(h->L); freeSoa(h->G);
 	delete h;
 }
@@ -323,6 +348,18 @@ int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius
 	LB200_CHECK_LAUNCH(ctx);
 	LB200_CUDA(ctx, cudaMemcpyAsync(out_pos3, h->d_sphere_pos, sizeof(double) * 3 * (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaMemcpyAsync(out_radius, h->d_sphere_radius, sizeof(float) * h->n, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
+int lb200_hierarchy_get_relative_matrices(lb200_hierarchy* h, const double base_pos[3], float* out_matrices) {
+	if (!h || !base_pos || !out_matrices) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!h->d_matrices) LB200_CUDA(ctx, cudaMalloc(&h->d_matrices, sizeof(float) * 16 * (size_t)h->n));
+	relative_matrices_kernel<<<(h->n + HT - 1) / HT, HT, 0, ctx->stream>>>(h->G, h->d_order, h->n, base_pos[0], base_pos[1], base_pos[2], h->d_matrices);
+	LB200_CHECK_LAUNCH(ctx);
+	LB200_CUDA(ctx, cudaMemcpyAsync(out_matrices, h->d_matrices, sizeof(float) * 16 * (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return LB200_OK;
 }

@@ -241,6 +241,10 @@ class CullingSystem:
         self._err(self.L.lb200_culling_cull_exchange(self.h, C.byref(frustum), C.c_uint8(type), C.byref(ids), C.byref(slabs), C.byref(stride)))
         return (ids.value or 0), (slabs.value or 0), int(stride.value)
 
+    def cull_exchange_n(self, frustum, n, type=TYPE_ALL):
+        """n exchange steps issued from C."""
+        self._err(self.L.lb200_culling_cull_exchange_n(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(n)))
+
     def read_exchanged(self, slabs_ptr, stride, n_ranks):
         """Host copy of the exchanged slabs -> per rank dict(counts[256], n_pages, blocks, rows_per_block, mask[n_pages, 8] by page id)."""
         host = self.ctx.copy_to_host(slabs_ptr, stride * n_ranks, np.uint32).reshape(n_ranks, stride)

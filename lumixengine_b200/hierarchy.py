@@ -71,5 +71,12 @@ class Hierarchy:
         check(self.L.lb200_hierarchy_get_spheres(self.h, ptr(b), ptr(pos), ptr(rad)), self.ctx.h)
         return pos, rad
 
+    def getRelativeMatrices(self, base_pos):
+        """World::getRelativeMatrix(entity, base_pos) (world.cpp:370-377) for every node: float32[n,16], column-major."""
+        b = np.ascontiguousarray(base_pos, np.float64)
+        out = np.empty((self.n, 16), np.float32)
+        check(self.L.lb200_hierarchy_get_relative_matrices(self.h, ptr(b), ptr(out)), self.ctx.h)
+        return out
+
     def algorithmic_bytes(self):
         return int(self.L.lb200_hierarchy_algorithmic_bytes(self.h))

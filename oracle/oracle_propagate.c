@@ -48,3 +48,23 @@ void oracle_sphere_radius(const OTransform* globals, const float* bounding_radiu
 		out_radius[i] = bounding_radius[i] * m;
 	}
 }
+
+/* World::getRelativeMatrix, world.cpp:370-377:
+ *   Matrix mtx = transform.rot.toMatrix();            math.cpp:727-756
+ *   mtx.setTranslation(Vec3(transform.pos - base));   DVec3 - DVec3 in fp64 (math.cpp:505), then narrowed per component (math.cpp:443)
+ *   mtx.multiply3x3(transform.scale);                 math.cpp:1207-1217: column k scaled by scale[k], rows x,y,z only */
+void oracle_relative_matrices(const OTransform* globals, const double* base_pos3, OMatrix* out, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) {
+		const OTransform* t = &globals[i];
+		OLocalRigidTransform r;
+		r.pos.x = (float)(t->pos.x - base_pos3[0]);
+		r.pos.y = (float)(t->pos.y - base_pos3[1]);
+		r.pos.z = (float)(t->pos.z - base_pos3[2]);
+		r.rot = t->rot;
+		OMatrix m = olrt_to_matrix(r); /* toMatrix + setTranslation: same stores as Matrix(pos, rot) */
+		m.m[0] *= t->scale.x; m.m[1] *= t->scale.x; m.m[2] *= t->scale.x;
+		m.m[4] *= t->scale.y; m.m[5] *= t->scale.y; m.m[6] *= t->scale.y;
+		m.m[8] *= t->scale.z; m.m[9] *= t->scale.z; m.m[10] *= t->scale.z;
+		out[i] = m;
+	}
+}

@@ -201,6 +201,24 @@ def propagate(parents, locals56, globals56):
     return g
 
 
+def relative_matrices(globals56, base_pos):
+    """World::getRelativeMatrix (world.cpp:370-377) for every transform: float32[n,16], column-major like Matrix."""
+    g = np.ascontiguousarray(globals56, np.uint8)
+    b = np.ascontiguousarray(base_pos, np.float64)
+    out = np.empty((len(g), 16), np.float32)
+    lib().oracle_relative_matrices(_ptr(g), _ptr(b), _ptr(out), C.c_uint32(len(g)))
+    return out
+
+
+def ref_relative_matrices(globals56, base_pos):
+    """The same through the reference's own Quat::toMatrix / Matrix::setTranslation / multiply3x3 (oracle/_ref)."""
+    g = np.ascontiguousarray(globals56, np.uint8)
+    b = np.ascontiguousarray(base_pos, np.float64)
+    out = np.empty((len(g), 16), np.float32)
+    ref().ref_relative_matrix(_ptr(g), _ptr(b), _ptr(out), C.c_uint32(len(g)))
+    return out
+
+
 def sphere_radius(globals56, bounding_radius):
     g = np.ascontiguousarray(globals56, np.uint8)
     b = np.ascontiguousarray(bounding_radius, np.float32)

@@ -120,6 +120,18 @@ REF_API void ref_transform_compose(const void* parent56, const void* local56, vo
 	for (uint32_t i = 0; i < n; ++i) o[i] = a[i].compose(b[i]);
 }
 
+// World::getRelativeMatrix (world.cpp:370-377) needs a World; its body is these three reference calls on m_transforms[entity]
+REF_API void ref_relative_matrix(const void* tr56, const double* base_pos, float* out16, uint32_t n) {
+	const Transform* t = (const Transform*)tr56;
+	const DVec3 base(base_pos[0], base_pos[1], base_pos[2]);
+	for (uint32_t i = 0; i < n; ++i) {
+		Matrix mtx = t[i].rot.toMatrix();
+		mtx.setTranslation(Vec3(t[i].pos - base));
+		mtx.multiply3x3(t[i].scale);
+		memcpy(out16 + 16 * (size_t)i, &mtx, sizeof(mtx));
+	}
+}
+
 REF_API void ref_quat_mul(const float* a, const float* b, float* out, uint32_t n) {
 	for (uint32_t i = 0; i < n; ++i) {
 		const Quat r = Quat(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]) * Quat(b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);

@@ -160,6 +160,23 @@ def pose_kat():
     print("pose_kat.npz", sum(v.nbytes for v in d.values()))
 
 
+def world_kat():
+    """World::getRelativeMatrix (world.cpp:370-377) through the reference's Quat::toMatrix / setTranslation / multiply3x3."""
+    rng = np.random.default_rng(4321)
+    n = 1500
+    tr_dtype = np.dtype({"names": ["pos", "rot", "scale"], "formats": [(np.float64, 3), (np.float32, 4), (np.float32, 3)], "offsets": [0, 24, 40], "itemsize": 56})
+    t = np.zeros(n, tr_dtype)
+    t["pos"] = rng.normal(size=(n, 3)) * np.where(rng.random((n, 1)) < 0.5, 1e3, 1e7)
+    t["rot"] = unit_quats(rng, n)
+    t["scale"] = (0.25 + 2 * rng.random((n, 3))).astype(np.float32)
+    bases = np.array([[0.0, 0.0, 0.0], [1234.5, -20.25, 987.125], [9.99e6, 1e3, -1.0001e7]])
+    d = dict(tr=t.view(np.uint8).reshape(n, 56), bases=bases)
+    for k, b in enumerate(bases):
+        d[f"rel{k}"] = po.ref_relative_matrices(d["tr"], b)
+    np.savez_compressed(os.path.join(OUT, "world_kat.npz"), **d)
+    print("world_kat.npz", sum(v.nbytes for v in d.values()))
+
+
 if __name__ == "__main__":
     po.build()
     po.ref().ref_clip_length_ticks.restype = C.c_uint32
@@ -167,5 +184,6 @@ if __name__ == "__main__":
     math_kat()
     pose_kat()
     cull_kat()
+    world_kat()
     sys.stdout.flush()
     os._exit(0)

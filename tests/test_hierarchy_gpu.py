@@ -116,3 +116,20 @@ def test_1m_depth8_properties(ctx):
     b = h.getTransforms()
     assert np.array_equal(_as_bytes(a)[:, :52], _as_bytes(b)[:, :52])
     assert np.all(np.isfinite(a["pos"]))
+
+
+def test_relative_matrices_match_oracle(ctx, oracle):
+    """World::getRelativeMatrix of every propagated node against a camera position (world.cpp:370-377): bit-exact, 1e-5 documented."""
+    parents, locals_, roots = scenes.hierarchy_forest(30_000, 6, 4, seed=77)
+    h = lb.Hierarchy(ctx, parents)
+    h.setLocalTransforms(locals_)
+    h.setRootTransforms(roots)
+    h.propagate()
+    globals_ = h.getTransforms()
+    for base in ((0.0, 0.0, 0.0), (1500.25, -80.0, 3000.5), (-5999.0, 299.0, 5999.0)):
+        got = h.getRelativeMatrices(base)
+        exp = oracle.relative_matrices(_as_bytes(globals_), base)
+        if not np.array_equal(got.view(np.uint32), exp.view(np.uint32)):
+            scale = np.maximum(np.abs(exp).max(axis=1, keepdims=True), 1e-30)
+            assert np.all(np.abs(got.astype(np.float64) - exp) <= REL_TOL * scale)
+    h.close()

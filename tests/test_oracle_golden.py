@@ -127,3 +127,11 @@ def test_pose_sampling_and_absolute(oracle):
             assert np.array_equal(bits(bl), bits(g[f"c{k}_blend"][j])), (k, t)
     for s, exp in zip(g["time_from_seconds_in"], g["time_from_seconds_out"]):
         assert int(np.uint32(np.float32(s) * np.float32(32768))) == int(exp)  # Time::fromSeconds, animation.h:21-24
+
+
+def test_relative_matrices(oracle):
+    """World::getRelativeMatrix (world.cpp:370-377): the restatement against the reference's own toMatrix/setTranslation/multiply3x3."""
+    k = np.load(os.path.join(G, "world_kat.npz"))
+    for i, base in enumerate(k["bases"]):
+        got = oracle.relative_matrices(k["tr"], base)
+        assert np.array_equal(got.view(np.uint32), k[f"rel{i}"].view(np.uint32))
