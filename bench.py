@@ -265,7 +265,9 @@ def ours(a, rank, world):
         """n steps = n culls of the whole scene.  N=1: ONE lb200_culling_cull_device_n call — the engine culls its views (main,
         shadow cascades, lights) concurrently (pipeline.cpp:996-1063), so consecutive culls are independent submissions: they go
         to 3 internal streams / output lanes with programmatic dependent launch and the device overlaps them."""
-        if world > 1:
+        if world > 1 and exchange == "mask":
+            cs.cull_exchange_n(f, n)  # independent steps on the internal lanes; every step = cull + peer stores + epoch-flag wait
+        elif world > 1:
             for _ in range(n):
                 step_device()
         else:
@@ -351,7 +353,7 @@ def ours(a, rank, world):
                    "visible_per_gpu": int(visible), "pages": cs.page_count(), "frustum": "perspective fov 60deg 16:9 near 0.1 far 4500 at origin looking -z",
                    "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{cs.page_count() * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
                    "parallelism": f"dp{world}: whole cell pages per rank" + (("; exchanged each step: " + exchange_desc) if world > 1 else ""),
-                   "submission": "K culls = one lb200_culling_cull_device_n call: consecutive (independent) culls on 3 streams / output lanes, half-occupancy grids, programmatic dependent launch" if world == 1 else "one cull_exchange per step on the context stream",
+                   "submission": "K culls = one lb200_culling_cull_device_n call: consecutive (independent) culls on 3 streams / output lanes, half-occupancy grids, programmatic dependent launch" if world == 1 else "K exchange steps = one lb200_culling_cull_exchange_n call (steps on 3 streams, 6 exchange buffers per rank)",
                    "lone_cull_ms": ms_lone,
                    "scene_build_s": build_s, "page_stats": stats},
         "gpu_launches": int(launches),

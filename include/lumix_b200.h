@@ -202,8 +202,11 @@ LB200_API uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, ui
  *             bit s of the 256-bit row = slot s of the page is visible (slots >= 200 are 0) */
 LB200_API int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
                                           const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words);
-/* n exchange steps issued from one call (no per-step host overhead of the caller). */
-LB200_API int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n);
+/* n independent exchange steps issued from one call: step (epoch) e runs on internal stream e % lanes on every rank, so the remote
+ * stores, fences and flag round trip of one step overlap the culls of its neighbours (2 x lanes exchange buffers per rank).  Forks
+ * from and joins back into the context stream; the out parameters describe the LAST step. */
+LB200_API int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n,
+                                            const uint32_t** out_dev_ids, const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words);
 LB200_API uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -106,11 +106,14 @@ int lb200_comm_enable_p2p(lb200_ctx* ctx, uint32_t max_slab_ids) {
 	P.slab_words = (256 + (size_t)max_slab_ids + 63) & ~(size_t)63;
 	const size_t flag_bytes = 256;
 	const size_t buf_bytes = sizeof(uint32_t) * P.slab_words * (size_t)R;
-	const size_t total = flag_bytes + 2 * buf_bytes;
+	P.lanes = lb200_cull_lanes(); // the same on every rank (same environment)
+	P.n_buffers = 2 * P.lanes;
+	static_assert(2 * LB200_MAX_LANES * LB200_MAX_RANKS * sizeof(uint32_t) <= 256, "flag block");
+	const size_t total = flag_bytes + P.n_buffers * buf_bytes;
 	LB200_CUDA(ctx, cudaMalloc(&P.local_block, total));
 	LB200_CUDA(ctx, cudaMemsetAsync(P.local_block, 0, flag_bytes, ctx->stream));
-	LB200_CUDA(ctx, cudaMalloc(&P.done_counter, sizeof(uint32_t)));
-	LB200_CUDA(ctx, cudaMemsetAsync(P.done_counter, 0, sizeof(uint32_t), ctx->stream));
+	LB200_CUDA(ctx, cudaMalloc(&P.done_counter, sizeof(uint32_t) * LB200_MAX_LANES));
+	LB200_CUDA(ctx, cudaMemsetAsync(P.done_counter, 0, sizeof(uint32_t) * LB200_MAX_LANES, ctx->stream));
 	cudaIpcMemHandle_t mine;
 	LB200_CUDA(ctx, cudaIpcGetMemHandle(&mine, P.local_block));
 	// exchange the 64-byte handles with NCCL
@@ -133,8 +136,7 @@ int lb200_comm_enable_p2p(lb200_ctx* ctx, uint32_t max_slab_ids) {
 			base = (char*)p;
 		}
 		P.flags[r] = (uint32_t*)base;
-		P.gather[0][r] = (uint32_t*)(base + flag_bytes);
-		P.gather[1][r] = (uint32_t*)(base + flag_bytes + buf_bytes);
+		for (uint32_t b = 0; b < P.n_buffers; ++b) P.gather[b][r] = (uint32_t*)(base + flag_bytes + b * buf_bytes);
 	}
 	// nobody may start pushing before every rank has mapped every buffer (and zeroed its flags): one more collective as a barrier
 	uint32_t* d_b = nullptr;

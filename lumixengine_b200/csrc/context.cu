@@ -1,8 +1,18 @@
 // Context lifecycle + host-side frustum construction of the C-ABI (include/lumix_b200.h).
 #include "lb200_internal.h"
+#include <stdlib.h>
 #include "lb200_math.cuh"
 
 static char g_init_error[512] = {0};
+
+uint32_t lb200_cull_lanes() {
+	static const uint32_t lanes = [] {
+		const char* e = getenv("LB200_CULL_LANES");
+		const int v = e ? atoi(e) : 3;
+		return (uint32_t)(v < 1 ? 1 : (v > LB200_MAX_LANES ? LB200_MAX_LANES : v));
+	}();
+	return lanes;
+}
 
 void lb200_set_error(lb200_ctx* ctx, const char* fmt, ...) {
 	char* dst = ctx ? ctx->error : g_init_error;

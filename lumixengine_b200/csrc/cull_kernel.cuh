@@ -47,9 +47,9 @@ struct CullParams {
 	uint32_t prefetch_test_ids; // also pull the id rows of tested pages into L2 (a few % more DRAM traffic, one DRAM latency less in phase D)
 	uint32_t rows_per_block;    // mask rows owned by one block = rounds * chunk
 	// exchange mode (n_ranks > 0): mask rows + per-type counts go to every rank's slab, then an epoch flag (culling.cu)
-	uint32_t n_ranks, rank, epoch;
+	uint32_t n_ranks, rank, epoch, n_buffers;
 	uint32_t* xdst[LB200_MAX_RANKS];   // rank r's exchange buffer of this epoch, already offset to MY slab inside it
-	uint32_t* xflags[LB200_MAX_RANKS]; // rank r's flag block: [2][LB200_MAX_RANKS]
+	uint32_t* xflags[LB200_MAX_RANKS]; // rank r's flag block: [n_buffers][LB200_MAX_RANKS]
 	uint32_t* done_counter;            // local, for the last-block election
 	uint32_t type_base[256];
 };
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 			__threadfence_system();
 			__syncthreads();
 			if ((uint32_t)tid < P.n_ranks) {
-				volatile uint32_t* f = P.xflags[tid] + (P.epoch & 1u) * LB200_MAX_RANKS + P.rank;
+				volatile uint32_t* f = P.xflags[tid] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + P.rank;
 				*f = P.epoch;
 			}
 			if (tid == 0) *P.done_counter = 0;

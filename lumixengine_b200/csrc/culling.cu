@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) pack_slab_kernel(const __grid_constant__ 
 struct PushParams {
 	uint32_t type_base[256];
 	uint32_t slab_ids;
-	uint32_t n_ranks, rank, epoch;
+	uint32_t n_ranks, rank, epoch, n_buffers;
 	uint32_t debug; // profiling switches (LB200_GATHER_DEBUG): 2 = store to self only, 4 = no system fence
 	uint32_t* dst[LB200_MAX_RANKS];   // rank r's gather buffer of this epoch, already offset to MY slab inside it
 	uint32_t* flags[LB200_MAX_RANKS]; // rank r's flag block: [2][LB200_MAX_RANKS]
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) pack_push_kernel(const __grid_constant__ 
 	if (s_last) {
 		__threadfence_system();
 		if (threadIdx.x < P.n_ranks) {
-			volatile uint32_t* f = P.flags[threadIdx.x] + (P.epoch & 1u) * LB200_MAX_RANKS + P.rank;
+			volatile uint32_t* f = P.flags[threadIdx.x] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + P.rank;
 			*f = P.epoch;
 		}
 		if (threadIdx.x == 0) *done_counter = 0;
@@ -150,13 +150,13 @@ __global__ void __launch_bounds__(256) pack_push_kernel(const __grid_constant__ 
 }
 
 // Wait until every rank's slab of `epoch` has landed in this rank's gather buffer.  Spins on local memory; gives up after ~4 s.
-__global__ void wait_peers_kernel(const uint32_t* flags, uint32_t n_ranks, uint32_t epoch, uint32_t* timed_out) {
+__global__ void wait_peers_kernel(const uint32_t* flags, uint32_t n_ranks, uint32_t epoch, uint32_t n_buffers, uint32_t* timed_out) {
 	// Launched with programmatic stream serialization behind the kernel that publishes this rank's flag, and releasing its own
 	// dependents at once: the next cull's read-only prologue runs while this block spins.  Its own flag is among the awaited ones,
 	// so the wait cannot end before the local producer has published; the grid dependency below covers that kernel's last stores.
 	cudaTriggerProgrammaticLaunchCompletion();
 	if (threadIdx.x < n_ranks) {
-		const volatile uint32_t* f = flags + (epoch & 1u) * LB200_MAX_RANKS + threadIdx.x;
+		const volatile uint32_t* f = flags + (epoch % n_buffers) * LB200_MAX_RANKS + threadIdx.x;
 		const long long t0 = clock64();
 		while ((int)(*f - epoch) < 0) {
 			if (clock64() - t0 > 8000000000ll) { *timed_out = 1; break; }
@@ -189,11 +189,13 @@ struct lb200_culling {
 	float4* d_spheres = nullptr;
 	int* d_entities = nullptr;
 	lb200_page_desc* d_desc = nullptr;
-	// Output lanes: cull number `seq` writes ids to d_out_ids[seq % lanes], mask rows to d_mask[seq % lanes], counts to counter buffer
-	// seq % (2 * lanes) and zeroes counter buffer (seq + lanes) % (2 * lanes) for the cull `lanes` later.  Culls that share buffers are
-	// `lanes` apart and run on the same stream; the ones in between are independent and may run concurrently (cull_device_n).
-	static constexpr uint32_t MAX_LANES = 4;
+	// Output lanes: a cull on lane l writes ids to d_out_ids[l], mask rows to d_mask[l], counts to one of lane l's two counter buffers
+	// and zeroes the other one for the lane's next cull.  Plain culls take lane seq % lanes, exchange culls lane epoch % lanes.  Culls
+	// of one lane are always ordered (same stream inside a batch; batches fork from / join into the context stream, single culls run
+	// on it); culls of different lanes share nothing they write and may run concurrently (cull_device_n, cull_exchange_n).
+	static constexpr uint32_t MAX_LANES = LB200_MAX_LANES;
 	uint32_t lanes = 3;
+	uint8_t lane_parity[MAX_LANES] = {};
 	cudaStream_t lane_stream[MAX_LANES] = {};
 	cudaEvent_t lane_event[MAX_LANES] = {};
 	cudaEvent_t fork_event = nullptr;
@@ -202,7 +204,7 @@ struct lb200_culling {
 	uint32_t out_cap = 0;
 	uint32_t* d_mask = nullptr;     // lanes * mask_words
 	size_t mask_words = 0;
-	uint32_t* d_counters = nullptr; // 2 * lanes * COUNTER_WORDS
+	uint32_t* d_counters = nullptr; // lanes * 2 * COUNTER_WORDS: [lane][parity]
 	// the cull issued last
 	uint32_t* last_counters = nullptr;
 	uint32_t* last_out = nullptr;
@@ -237,7 +239,7 @@ int ensureDevice(lb200_culling* cs) {
 	lb::CullingHost& h = cs->host;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (!cs->d_counters) {
-		if (const char* e = getenv("LB200_CULL_LANES")) cs->lanes = (uint32_t)std::max(1, std::min((int)lb200_culling::MAX_LANES, atoi(e)));
+		cs->lanes = lb200_cull_lanes();
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS));
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS, ctx->stream));
 		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocDefault));
@@ -358,7 +360,7 @@ void cullGeometry(const lb200_culling* cs, uint32_t grid, uint32_t n_pages, uint
 	*chunk_out = chunk; *blocks_out = blocks; *rpb_out = rounds * chunk;
 }
 
-struct Exchange { uint32_t epoch; }; // non-null: store mask rows + counts into every rank's slab (peer memory)
+struct Exchange { uint32_t epoch; }; // non-null: store mask rows + counts into every rank's slab (peer memory); lane = epoch % lanes
 
 int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, const Exchange* xchg = nullptr, cudaStream_t stream = nullptr) {
 	lb200_ctx* ctx = cs->ctx;
@@ -385,22 +387,23 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	const uint32_t r = cs->next_replica;
 	cs->next_replica = (cs->next_replica + 1) % cs->replicas;
 	const size_t off = (size_t)r * cs->dev_cap;
-	const uint32_t L = cs->lanes;
-	uint32_t* cur = cs->d_counters + (size_t)(cs->seq % (2 * L)) * COUNTER_WORDS;
-	uint32_t* nxt = cs->d_counters + (size_t)((cs->seq + L) % (2 * L)) * COUNTER_WORDS;
-	uint32_t* out = cs->d_out_ids + (size_t)(cs->seq % L) * cs->out_cap;
-	uint32_t* mask = cs->d_mask + (size_t)(cs->seq % L) * cs->mask_words;
+	const uint32_t lane = (uint32_t)((xchg ? (uint64_t)xchg->epoch : cs->seq) % cs->lanes);
+	uint32_t* cur = cs->d_counters + ((size_t)lane * 2 + cs->lane_parity[lane]) * COUNTER_WORDS;
+	uint32_t* nxt = cs->d_counters + ((size_t)lane * 2 + (cs->lane_parity[lane] ^ 1u)) * COUNTER_WORDS;
+	uint32_t* out = cs->d_out_ids + (size_t)lane * cs->out_cap;
+	uint32_t* mask = cs->d_mask + (size_t)lane * cs->mask_words;
 	uint32_t chunk, blocks, rpb;
 	cullGeometry(cs, (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid), h.high_water, &chunk, &blocks, &rpb);
 	P.chunk = chunk;
 	P.rows_per_block = rpb;
-	P.n_ranks = 0; P.rank = 0; P.epoch = 0; P.done_counter = nullptr;
+	P.n_ranks = 0; P.rank = 0; P.epoch = 0; P.n_buffers = 2; P.done_counter = nullptr;
 	for (int r = 0; r < LB200_MAX_RANKS; ++r) { P.xdst[r] = nullptr; P.xflags[r] = nullptr; }
 	if (xchg) {
 		lb200_ctx::Peer& peer = ctx->peer;
-		P.n_ranks = (uint32_t)ctx->n_ranks; P.rank = (uint32_t)ctx->rank; P.epoch = xchg->epoch; P.done_counter = peer.done_counter;
+		P.n_ranks = (uint32_t)ctx->n_ranks; P.rank = (uint32_t)ctx->rank; P.epoch = xchg->epoch; P.n_buffers = peer.n_buffers;
+		P.done_counter = peer.done_counter + lane;
 		for (int r = 0; r < ctx->n_ranks; ++r) {
-			P.xdst[r] = peer.gather[xchg->epoch & 1u][r] + peer.slab_words * (size_t)ctx->rank;
+			P.xdst[r] = peer.gather[xchg->epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank;
 			P.xflags[r] = peer.flags[r];
 		}
 	}
@@ -428,10 +431,34 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 		xchg ? (uint32_t*)nullptr : mask));
 	LB200_CHECK_LAUNCH(ctx);
 	cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask;
-	++cs->seq;
+	cs->lane_parity[lane] ^= 1u;
+	if (!xchg) ++cs->seq;
 	cs->last_pages = h.high_water;
 	cs->last_blocks = blocks;
 	cs->last_rows_per_block = rpb;
+	return LB200_OK;
+}
+
+int forkLanes(lb200_culling* cs) {
+	lb200_ctx* ctx = cs->ctx;
+	if (!cs->fork_event) {
+		LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->fork_event, cudaEventDisableTiming));
+		for (uint32_t l = 0; l < cs->lanes; ++l) {
+			LB200_CUDA(ctx, cudaStreamCreateWithFlags(&cs->lane_stream[l], cudaStreamNonBlocking));
+			LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->lane_event[l], cudaEventDisableTiming));
+		}
+	}
+	LB200_CUDA(ctx, cudaEventRecord(cs->fork_event, ctx->stream));
+	for (uint32_t l = 0; l < cs->lanes; ++l) LB200_CUDA(ctx, cudaStreamWaitEvent(cs->lane_stream[l], cs->fork_event, 0));
+	return LB200_OK;
+}
+
+int joinLanes(lb200_culling* cs) {
+	lb200_ctx* ctx = cs->ctx;
+	for (uint32_t l = 0; l < cs->lanes; ++l) {
+		LB200_CUDA(ctx, cudaEventRecord(cs->lane_event[l], cs->lane_stream[l]));
+		LB200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cs->lane_event[l], 0));
+	}
 	return LB200_OK;
 }
 
@@ -616,25 +643,14 @@ int lb200_culling_cull_device_n(lb200_culling* cs, const lb200_shifted_frustum* 
 		return LB200_OK;
 	}
 	// independent views: consecutive culls go to different streams and different output lanes, so the device overlaps them freely;
-	// culls `lanes` apart share buffers and stay ordered on their stream.  Fork from / join into the context stream.
-	if (!cs->fork_event) {
-		LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->fork_event, cudaEventDisableTiming));
-		for (uint32_t l = 0; l < cs->lanes; ++l) {
-			LB200_CUDA(ctx, cudaStreamCreateWithFlags(&cs->lane_stream[l], cudaStreamNonBlocking));
-			LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->lane_event[l], cudaEventDisableTiming));
-		}
-	}
-	LB200_CUDA(ctx, cudaEventRecord(cs->fork_event, ctx->stream));
-	for (uint32_t l = 0; l < cs->lanes; ++l) LB200_CUDA(ctx, cudaStreamWaitEvent(cs->lane_stream[l], cs->fork_event, 0));
+	// culls of one lane share buffers and stay ordered on their stream.  Fork from / join into the context stream.
+	rc = forkLanes(cs);
+	if (rc) return rc;
 	for (uint32_t i = 0; i < n; ++i) {
 		rc = launchCull(cs, frustum, type, nullptr, cs->lane_stream[cs->seq % cs->lanes]);
 		if (rc) return rc;
 	}
-	for (uint32_t l = 0; l < cs->lanes; ++l) {
-		LB200_CUDA(ctx, cudaEventRecord(cs->lane_event[l], cs->lane_stream[l]));
-		LB200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cs->lane_event[l], 0));
-	}
-	return LB200_OK;
+	return joinLanes(cs);
 }
 
 int lb200_culling_last_result(lb200_culling* cs, const uint32_t** out_dev_ids, lb200_cull_result* result) {
@@ -756,9 +772,9 @@ int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* fr
 		memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
 		PP.slab_ids = slab_ids;
 		static const uint32_t dbg = [] { const char* e = getenv("LB200_GATHER_DEBUG"); return e ? (uint32_t)atoi(e) : 0u; }();
-		PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = epoch; PP.debug = dbg;
+		PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = epoch; PP.n_buffers = peer.n_buffers; PP.debug = dbg;
 		for (int r = 0; r < LB200_MAX_RANKS; ++r) {
-			PP.dst[r] = r < ctx->n_ranks ? peer.gather[epoch & 1u][(dbg & 2u) ? ctx->rank : r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+			PP.dst[r] = r < ctx->n_ranks ? peer.gather[epoch % peer.n_buffers][(dbg & 2u) ? ctx->rank : r] + peer.slab_words * (size_t)ctx->rank : nullptr;
 			PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
 		}
 		pack_push_kernel<<<ctx->sm_count * pushGridMul(), 256, 0, ctx->stream>>>(PP, cur, cs->last_out, peer.done_counter);
@@ -768,10 +784,10 @@ int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* fr
 			LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
 		}
 		if (!(dbg & 1u)) {
-			wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, epoch, cs->d_gather_counts);
+			wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, epoch, peer.n_buffers, cs->d_gather_counts);
 			LB200_CHECK_LAUNCH(ctx);
 		}
-		if (out_dev_slabs) *out_dev_slabs = peer.gather[epoch & 1u][ctx->rank];
+		if (out_dev_slabs) *out_dev_slabs = peer.gather[epoch % peer.n_buffers][ctx->rank];
 		return LB200_OK;
 	}
 	rc = packAndGather(cs, cur, slab_ids);
@@ -786,57 +802,102 @@ uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, uint32_t sla
 	return (peer.ready && 256 + (size_t)slab_ids <= peer.slab_words) ? (uint32_t)peer.slab_words : 256 + slab_ids;
 }
 
-int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
-	const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words)
-{
+static int prepareExchange(lb200_culling* cs, const lb200_shifted_frustum* frustum) {
 	if (!cs || !frustum) return LB200_ERR_INVALID;
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
 	lb200_ctx* ctx = cs->ctx;
 	lb200_ctx::Peer& peer = ctx->peer;
 	if (!peer.ready) { lb200_set_error(ctx, "cull_exchange needs lb200_comm_enable_p2p"); return LB200_ERR_STATE; }
 	if (cs->host.cells.empty()) { lb200_set_error(ctx, "cull_exchange on an empty culling system"); return LB200_ERR_STATE; }
-	int rc = ensureDevice(cs);
+	int rc = flushPages(cs); // uploads (if any) go to the context stream, before any lane forks from it
 	if (rc) return rc;
+	if (peer.lanes != cs->lanes) { lb200_set_error(ctx, "exchange lanes (%u) differ from cull lanes (%u)", peer.lanes, cs->lanes); return LB200_ERR_STATE; }
 	uint32_t chunk, blocks, rpb;
 	cullGeometry(cs, (uint32_t)cs->grid_lanes, cs->host.high_water, &chunk, &blocks, &rpb);
 	if (XHEADER_WORDS + 8 * (size_t)blocks * rpb > peer.slab_words) {
 		lb200_set_error(ctx, "exchange slab too small: %zu words needed, %zu mapped", XHEADER_WORDS + 8 * (size_t)blocks * rpb, peer.slab_words);
 		return LB200_ERR_CAPACITY;
 	}
-	Exchange x;
-	x.epoch = ++peer.epoch;
-	rc = launchCull(cs, frustum, type, &x);
-	if (rc) return rc;
-	cs->has_last = false;
 	if (!cs->d_gather_counts) {
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
 	}
-	{
-		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3(1);
-		cfg.blockDim = dim3(32);
-		cfg.stream = ctx->stream;
-		cudaLaunchAttribute attr[1];
-		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-		attr[0].val.programmaticStreamSerializationAllowed = 1;
-		cfg.attrs = attr;
-		cfg.numAttrs = 1;
-		LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, wait_peers_kernel, (const uint32_t*)peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, cs->d_gather_counts));
-		LB200_CHECK_LAUNCH(ctx);
-	}
+	return LB200_OK;
+}
+
+// one exchange step on `stream` (nullptr = the context stream): the cull kernel stores rows + counts into every rank and raises this
+// rank's epoch flag everywhere; the wait kernel then holds the stream until every rank's flag of this epoch is here
+static int exchangeStep(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, cudaStream_t stream, uint32_t* epoch_out) {
+	lb200_ctx* ctx = cs->ctx;
+	lb200_ctx::Peer& peer = ctx->peer;
+	Exchange x;
+	x.epoch = ++peer.epoch;
+	int rc = launchCull(cs, frustum, type, &x, stream);
+	if (rc) return rc;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(1);
+	cfg.blockDim = dim3(32);
+	cfg.stream = stream ? stream : ctx->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, wait_peers_kernel, (const uint32_t*)peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, peer.n_buffers, cs->d_gather_counts));
+	LB200_CHECK_LAUNCH(ctx);
+	if (epoch_out) *epoch_out = x.epoch;
+	return LB200_OK;
+}
+
+static void lastExchange(lb200_culling* cs, const uint32_t** out_dev_ids, const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words) {
+	const lb200_ctx::Peer& peer = cs->ctx->peer;
 	if (out_dev_ids) *out_dev_ids = cs->last_out;
-	if (out_dev_slabs) *out_dev_slabs = peer.gather[x.epoch & 1u][ctx->rank];
+	if (out_dev_slabs) *out_dev_slabs = peer.gather[peer.epoch % peer.n_buffers][cs->ctx->rank];
+	if (out_slab_stride_words) *out_slab_stride_words = (uint32_t)peer.slab_words;
+}
+
+int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
+	const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words)
+{
+	int rc = prepareExchange(cs, frustum);
+	if (rc) return rc;
+	lb200_ctx::Peer& peer = cs->ctx->peer;
+	uint32_t epoch = 0;
+	rc = exchangeStep(cs, frustum, type, nullptr, &epoch);
+	if (rc) return rc;
+	cs->has_last = false;
+	if (out_dev_ids) *out_dev_ids = cs->last_out;
+	if (out_dev_slabs) *out_dev_slabs = peer.gather[epoch % peer.n_buffers][cs->ctx->rank];
 	if (out_slab_stride_words) *out_slab_stride_words = (uint32_t)peer.slab_words;
 	return LB200_OK;
 }
 
-int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n) {
+int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t n, const uint32_t** out_dev_ids,
+	const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words)
+{
+	if (n == 0) return LB200_ERR_INVALID;
+	int rc = prepareExchange(cs, frustum);
+	if (rc) return rc;
+	lb200_ctx* ctx = cs->ctx;
+	cs->has_last = false;
+	if (cs->lanes < 2 || n < 2) {
+		for (uint32_t i = 0; i < n; ++i) {
+			rc = exchangeStep(cs, frustum, type, nullptr, nullptr);
+			if (rc) return rc;
+		}
+		lastExchange(cs, out_dev_ids, out_dev_slabs, out_slab_stride_words);
+		return LB200_OK;
+	}
+	// independent steps: epoch e runs on stream e % lanes (every rank makes the same choice), so one step's remote stores, fences and
+	// flag round trip overlap the neighbouring steps' culls; see lb200_ctx::Peer for why 2 x lanes exchange buffers make that safe
+	rc = forkLanes(cs);
+	if (rc) return rc;
 	for (uint32_t i = 0; i < n; ++i) {
-		const int rc = lb200_culling_cull_exchange(cs, frustum, type, nullptr, nullptr, nullptr);
+		rc = exchangeStep(cs, frustum, type, cs->lane_stream[(ctx->peer.epoch + 1) % cs->lanes], nullptr);
 		if (rc) return rc;
 	}
-	return LB200_OK;
+	lastExchange(cs, out_dev_ids, out_dev_slabs, out_slab_stride_words);
+	return joinLanes(cs);
 }
 
 uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs) {

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #define LB200_MAX_RANKS 8
+#define LB200_MAX_LANES 4  // concurrent culls (streams / output lanes); exchange buffers = 2 x lanes
 
 struct lb200_ctx {
 	int device = -1;
@@ -28,16 +29,21 @@ struct lb200_ctx {
 	struct Peer {
 		bool ready = false;
 		size_t slab_words = 0;            // capacity of one rank's slab (header + ids)
-		void* local_block = nullptr;      // this rank's allocation: [flags 2 x 8 x u32, padded to 256 B][gather 0][gather 1]
-		uint32_t* gather[2][LB200_MAX_RANKS] = {}; // gather[b][r] = rank r's buffer b as seen from this process
+		// Exchange epoch e uses buffer e % n_buffers, n_buffers = 2 x lanes.  With lanes > 1 (lb200_culling_cull_exchange_n) epoch e is
+		// issued on stream e % lanes.  A rank overwrites buffer b for epoch e only after its wait for epoch e - lanes on the same
+		// stream, i.e. after every rank published e - lanes, which every rank issues behind whatever consumed e - 2 x lanes there.
+		uint32_t lanes = 1, n_buffers = 2;
+		void* local_block = nullptr;      // this rank's allocation: [flags n_buffers x 8 x u32 in 256 B][gather 0] .. [gather n_buffers-1]
+		uint32_t* gather[2 * LB200_MAX_LANES][LB200_MAX_RANKS] = {}; // gather[b][r] = rank r's buffer b as seen from this process
 		uint32_t* flags[LB200_MAX_RANKS] = {};     // flags[r] = rank r's flag block
 		void* opened[LB200_MAX_RANKS] = {};        // cudaIpcOpenMemHandle results to close
-		uint32_t* done_counter = nullptr; // local, for the last-block election
+		uint32_t* done_counter = nullptr; // local, one per lane, for the last-block election
 		uint32_t epoch = 0;
 	} peer;
 };
 
 void lb200_set_error(lb200_ctx* ctx, const char* fmt, ...);
+uint32_t lb200_cull_lanes(); // LB200_CULL_LANES, default 3, 1..LB200_MAX_LANES (context.cu)
 
 #define LB200_CUDA(ctx, expr)                                                                        \
 	do {                                                                                             \

@@ -242,8 +242,10 @@ class CullingSystem:
         return (ids.value or 0), (slabs.value or 0), int(stride.value)
 
     def cull_exchange_n(self, frustum, n, type=TYPE_ALL):
-        """n exchange steps issued from C."""
-        self._err(self.L.lb200_culling_cull_exchange_n(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(n)))
+        """n independent exchange steps issued from C on the internal lanes; returns the (ids, slabs, stride) of the last step."""
+        ids, slabs, stride = vp(), vp(), C.c_uint32()
+        self._err(self.L.lb200_culling_cull_exchange_n(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(n), C.byref(ids), C.byref(slabs), C.byref(stride)))
+        return (ids.value or 0), (slabs.value or 0), int(stride.value)
 
     def read_exchanged(self, slabs_ptr, stride, n_ranks):
         """Host copy of the exchanged slabs -> per rank dict(counts[256], n_pages, blocks, rows_per_block, mask[n_pages, 8] by page id)."""

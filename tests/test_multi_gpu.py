@@ -121,10 +121,14 @@ def _exchange_worker(rank, world, port, q):
     tables = [(systems[r].pages(), systems[r].page_ids()) for r in range(world)]
     frusta = [lb.frustum_perspective(**dict(scenes.c1_frustum_args(), far=2500.0)),
               lb.frustum_perspective(position=(500.0, 20.0, -300.0), direction=(0.6, -0.1, 0.79), up=(0, 1, 0), fov=0.9, ratio=1.6, near=0.5, far=1800.0)]
-    for step in range(6):  # several epochs: both buffer parities, two views
+    for step in range(14):  # many epochs: every exchange buffer and lane; single steps and batches on the internal streams
         f = frusta[step % 2]
         fb = lb.culling.frustum_bytes(f)
-        ids_ptr, slabs_ptr, stride = cs.cull_exchange(f)
+        if step % 3 == 2:
+            cs.cull_exchange_n(frusta[(step + 1) % 2], 1 + step % 4)  # unread steps of the other view right before
+            ids_ptr, slabs_ptr, stride = cs.cull_exchange_n(f, 2 + step)
+        else:
+            ids_ptr, slabs_ptr, stride = cs.cull_exchange(f)
         got = cs.read_exchanged(slabs_ptr, stride, world)
         for r in range(world):
             oc = po.OracleCulling()
@@ -150,9 +154,10 @@ def _exchange_worker(rank, world, port, q):
                 base = np.concatenate([[0], np.cumsum(np.bincount(shards[r]["types"], minlength=256))])
                 mine = [ctx.copy_to_host(ids_ptr + 4 * int(base[t]), int(got[r]["counts"][t]), np.uint32) for t in range(3)]
                 chk(np.array_equal(np.sort(np.concatenate(mine)).astype(np.int64), vis) and total == len(vis), f'step {step}: own id list differs from own rows')
-    for _ in range(40):  # back-to-back epochs without host synchronisation in between
+    for _ in range(10):  # back-to-back epochs without host synchronisation in between
         cs.cull_exchange(frusta[0])
-    _, slabs_ptr, stride = cs.cull_exchange(frusta[1])
+    cs.cull_exchange_n(frusta[0], 40)
+    _, slabs_ptr, stride = cs.cull_exchange_n(frusta[1], 5)
     got = cs.read_exchanged(slabs_ptr, stride, world)
     digest = torch.tensor([sum(int(g["mask"].astype(np.uint64).sum()) + int(g["counts"].sum()) for g in got)])
     gathered = [torch.zeros_like(digest) for _ in range(world)]
