@@ -46,11 +46,9 @@ struct CullParams {
 	uint32_t plane_masking; // 1 unless some sphere has a negative / NaN radius
 	uint32_t prefetch_test_ids; // also pull the id rows of tested pages into L2 (a few % more DRAM traffic, one DRAM latency less in phase D)
 	uint32_t rows_per_block;    // mask rows owned by one block = rounds * chunk
-	// exchange mode (n_ranks > 0): mask rows + per-type counts go to every rank's slab, then an epoch flag (culling.cu)
-	uint32_t n_ranks, rank, epoch, n_buffers;
+	// exchange mode (n_ranks > 0): the mask rows go straight into every rank's slab (peer memory)
+	uint32_t n_ranks;
 	uint32_t* xdst[LB200_MAX_RANKS];   // rank r's exchange buffer of this epoch, already offset to MY slab inside it
-	uint32_t* xflags[LB200_MAX_RANKS]; // rank r's flag block: [n_buffers][LB200_MAX_RANKS]
-	uint32_t* done_counter;            // local, for the last-block election
 	uint32_t type_base[256];
 };
 constexpr uint32_t XHEADER_WORDS = 264; // slab = [256 per-type counts][n_pages, grid, rows_per_block, chunk, 0, 0, 0, 0][mask rows]
@@ -97,7 +95,6 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 	__shared__ uint16_t s_slot[MAX_CHUNK]; // classify thread -> work slot of its page (SLOT_NONE: skipped / no page)
 	__shared__ uint32_t s_stats[N_STATS];
 	__shared__ uint32_t s_nwork;
-	__shared__ bool s_last;
 
 	// let the next cull of the stream start its read-only prologue as soon as SM resources free up
 	cudaTriggerProgrammaticLaunchCompletion();
@@ -354,31 +351,8 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 	if (blockIdx.x == 0) {
 		for (int i = tid; i < COUNTER_WORDS; i += CULL_THREADS) next_counters[i] = 0;
 	}
-	// exchange mode: once every block's rows have landed everywhere, the last block sends the per-type counts and raises the epoch flag
-	if (P.n_ranks) {
-		__threadfence_system();
-		__syncthreads();
-		if (tid == 0) s_last = atomicAdd(P.done_counter, 1u) == gridDim.x - 1;
-		__syncthreads();
-		if (s_last) {
-			for (uint32_t i = tid; i < XHEADER_WORDS; i += CULL_THREADS) {
-				uint32_t v = 0;
-				if (i < 256) v = *(volatile const uint32_t*)(counters + i);
-				else if (i == 256) v = P.n_pages;
-				else if (i == 257) v = gridDim.x;
-				else if (i == 258) v = P.rows_per_block;
-				else if (i == 259) v = P.chunk;
-				for (uint32_t r = 0; r < P.n_ranks; ++r) P.xdst[r][i] = v;
-			}
-			__threadfence_system();
-			__syncthreads();
-			if ((uint32_t)tid < P.n_ranks) {
-				volatile uint32_t* f = P.xflags[tid] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + P.rank;
-				*f = P.epoch;
-			}
-			if (tid == 0) *P.done_counter = 0;
-		}
-	}
+	// exchange mode: nothing more to do here.  The rows were stored without a fence; publish_wait_kernel (culling.cu), which runs
+	// after this grid has completed, sends the per-type counts, fences once at system scope and raises the epoch flags.
 }
 
 } // namespace lbcull

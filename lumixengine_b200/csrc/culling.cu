@@ -166,6 +166,47 @@ __global__ void wait_peers_kernel(const uint32_t* flags, uint32_t n_ranks, uint3
 	__threadfence_system();
 }
 
+// Second half of an exchange step (lb200_culling_cull_exchange): runs behind the cull kernel that stored this rank's mask rows into
+// every rank's slab.  Once that grid has completed (its peer stores are performed, its counters final) one block sends the slab
+// header, fences ONCE at system scope and raises this rank's epoch flag everywhere, then holds the stream until every rank's flag of
+// this epoch is here.  Launched with programmatic stream serialization and releasing its own dependents at once: the next cull of
+// the stream runs its read-only prologue meanwhile.
+struct PublishParams {
+	uint32_t n_ranks, rank, epoch, n_buffers;
+	uint32_t n_pages, blocks, rows_per_block, chunk;
+	uint32_t* dst[LB200_MAX_RANKS];   // rank r's exchange buffer of this epoch, already offset to MY slab inside it
+	uint32_t* flags[LB200_MAX_RANKS]; // rank r's flag block: [n_buffers][LB200_MAX_RANKS]
+};
+
+__global__ void __launch_bounds__(288) publish_wait_kernel(const __grid_constant__ PublishParams P, const uint32_t* counters, uint32_t* timed_out) {
+	cudaTriggerProgrammaticLaunchCompletion();
+	cudaGridDependencySynchronize();
+	const uint32_t i = threadIdx.x;
+	if (i < XHEADER_WORDS) {
+		uint32_t v = 0;
+		if (i < 256) v = __ldcg(counters + i);
+		else if (i == 256) v = P.n_pages;
+		else if (i == 257) v = P.blocks;
+		else if (i == 258) v = P.rows_per_block;
+		else if (i == 259) v = P.chunk;
+		for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][i] = v;
+	}
+	// release: everything that happened before this fence — the cull grid's rows (ordered before us by the grid dependency) and the
+	// header just written — is visible to whoever observes the flag
+	__threadfence_system();
+	__syncthreads();
+	if (i < P.n_ranks) {
+		volatile uint32_t* f = P.flags[i] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + P.rank;
+		*f = P.epoch;
+		const volatile uint32_t* mine = P.flags[P.rank] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + i;
+		const long long t0 = clock64();
+		while ((int)(*mine - P.epoch) < 0) {
+			if (clock64() - t0 > 8000000000ll) { *timed_out = 1; break; }
+		}
+	}
+	__threadfence_system();
+}
+
 void* pinnedAlloc(size_t n) {
 	void* p = nullptr;
 	if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -225,7 +266,7 @@ struct lb200_culling {
 	size_t slab_cap = 0;
 
 	uint32_t last_type_base[256];
-	uint32_t last_blocks = 0, last_rows_per_block = 0; // mask row of page p = (p % blocks) * rows_per_block + p / blocks
+	uint32_t last_blocks = 0, last_rows_per_block = 0, last_chunk = 0; // mask row of page p = (p % blocks) * rows_per_block + p / blocks
 	lb200_cull_result last = {};
 	bool has_last = false;
 	uint64_t last_bytes = 0;
@@ -396,16 +437,12 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	cullGeometry(cs, (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid), h.high_water, &chunk, &blocks, &rpb);
 	P.chunk = chunk;
 	P.rows_per_block = rpb;
-	P.n_ranks = 0; P.rank = 0; P.epoch = 0; P.n_buffers = 2; P.done_counter = nullptr;
-	for (int r = 0; r < LB200_MAX_RANKS; ++r) { P.xdst[r] = nullptr; P.xflags[r] = nullptr; }
+	P.n_ranks = 0;
+	for (int r = 0; r < LB200_MAX_RANKS; ++r) P.xdst[r] = nullptr;
 	if (xchg) {
 		lb200_ctx::Peer& peer = ctx->peer;
-		P.n_ranks = (uint32_t)ctx->n_ranks; P.rank = (uint32_t)ctx->rank; P.epoch = xchg->epoch; P.n_buffers = peer.n_buffers;
-		P.done_counter = peer.done_counter + lane;
-		for (int r = 0; r < ctx->n_ranks; ++r) {
-			P.xdst[r] = peer.gather[xchg->epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank;
-			P.xflags[r] = peer.flags[r];
-		}
+		P.n_ranks = (uint32_t)ctx->n_ranks;
+		for (int r = 0; r < ctx->n_ranks; ++r) P.xdst[r] = peer.gather[xchg->epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank;
 	}
 	static const bool no_mask = getenv("LB200_NO_PLANE_MASKING") != nullptr;
 	P.plane_masking = (h.n_bad_radius == 0 && !no_mask) ? 1u : 0u;
@@ -435,6 +472,7 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	if (!xchg) ++cs->seq;
 	cs->last_pages = h.high_water;
 	cs->last_blocks = blocks;
+	cs->last_chunk = chunk;
 	cs->last_rows_per_block = rpb;
 	return LB200_OK;
 }
@@ -834,16 +872,23 @@ static int exchangeStep(lb200_culling* cs, const lb200_shifted_frustum* frustum,
 	x.epoch = ++peer.epoch;
 	int rc = launchCull(cs, frustum, type, &x, stream);
 	if (rc) return rc;
+	PublishParams PP;
+	PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = x.epoch; PP.n_buffers = peer.n_buffers;
+	PP.n_pages = cs->last_pages; PP.blocks = cs->last_blocks; PP.rows_per_block = cs->last_rows_per_block; PP.chunk = cs->last_chunk;
+	for (int r = 0; r < LB200_MAX_RANKS; ++r) {
+		PP.dst[r] = r < ctx->n_ranks ? peer.gather[x.epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+		PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
+	}
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(1);
-	cfg.blockDim = dim3(32);
+	cfg.blockDim = dim3(288);
 	cfg.stream = stream ? stream : ctx->stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, wait_peers_kernel, (const uint32_t*)peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, peer.n_buffers, cs->d_gather_counts));
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, publish_wait_kernel, PP, (const uint32_t*)cs->last_counters, cs->d_gather_counts));
 	LB200_CHECK_LAUNCH(ctx);
 	if (epoch_out) *epoch_out = x.epoch;
 	return LB200_OK;

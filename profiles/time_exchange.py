@@ -40,7 +40,7 @@ timed("cull_device_n, peers mapped", lambda: cs.cull_device_n(f, N))
 dist.barrier()
 timed("cull_exchange x N from python", lambda: [cs.cull_exchange(f) for _ in range(N)])
 dist.barrier()
-timed("cull_exchange_n from C", lambda: cs.cull_exchange_n(f, N))
+timed("cull_exchange_n from C (lanes)", lambda: cs.cull_exchange_n(f, N))
 dist.barrier()
 os.environ["X"] = "1"
 cs.close(); ctx.close(); dist.destroy_process_group()
