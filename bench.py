@@ -359,7 +359,7 @@ def ours(a, rank, world):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": total_entities / e2e_s / 1e6, "unit": "M entities/s", "h2d_bytes_per_step": 256 + 1024 + 8, "d2h_bytes_per_step": int(r.total) * 4 + 264 * 4,
-                "ms_per_step": e2e_s * 1e3, "api": "CullingSystem.cull(frustum): host frustum -> kernel params, visible ids + counts copied to pinned host memory"},
+                "ms_per_step": e2e_s * 1e3, "api": "CullingSystem.cull(frustum): host frustum -> kernel params; visible ids + counts written into pinned host memory by the device right behind the cull, one synchronisation"},
         "roofline": {"bound": "hbm", "achieved": alg_bytes / ms_kernel / 1e6, "peak": peak, "unit": "GB/s", "frac": alg_bytes / ms_kernel / 1e6 / peak,
                      "traffic": traffic_from_profile("cull_pages_kernel"), "kernel": "cull_pages_kernel", "kernel_ms": ms_kernel, "algorithmic_bytes": int(alg_bytes),
                      "peak_source": peak_src,

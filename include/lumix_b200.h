@@ -137,9 +137,11 @@ typedef struct {
 } lb200_cull_result;
 
 /* CullingSystem::cull(frustum, type) / cull(frustum), culling_system.cpp:310-369.
- * Uploads dirty pages + the frustum, runs the cull kernel, copies the visible ids to `out_ids` (host, capacity in ids;
- * pinned memory makes the copy faster).  type == LB200_TYPE_ALL culls every type.  Returns LB200_ERR_CAPACITY if
- * `capacity` < visible count (result->total still holds the needed size).  With zero pages: total = 0 (the reference
+ * Uploads dirty pages + the frustum, runs the cull kernel, delivers the visible ids in `out_ids` (host, capacity in ids) packed
+ * type after type (result->type_offset).  A page-locked destination (lb200_host_alloc, cudaHostAlloc, cudaHostRegister) is written
+ * by the device itself right behind the cull — one synchronisation, no count round trip, copy engine idle; pageable memory takes
+ * cudaMemcpyAsync per type.  type == LB200_TYPE_ALL culls every type.  Returns LB200_ERR_CAPACITY if `capacity` < visible count
+ * (result->total still holds the needed size; the content of out_ids is then unspecified).  With zero pages: total = 0 (the reference
  * returns nullptr, culling_system.cpp:322). */
 LB200_API int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity,
 	lb200_cull_result* result);

@@ -1,6 +1,6 @@
 // cull_pages_kernel — CullingSystemImpl::cullInternal + doCulling (src/renderer/culling_system.cpp:260-369) on the GPU.
 //
-// One block owns a chunk of consecutive cell pages and runs four phases:
+// Pages are dealt to the blocks round-robin; per round a block runs five phases:
 //   A. classify   one THREAD per page: coalesced read of the 32-byte descriptors, the cell tests of
 //                 culling_system.cpp:342-363 (is_big -> test; containsAABB(origin + cs, cs) -> copy all ids;
 //                 intersectsAABB(origin - cs, 2cs) -> test; else nothing) with ShiftedFrustum::containsAABB /
@@ -16,9 +16,10 @@
 //                 run is stored straight into every rank's memory over NVLink (the bitmask is the exchanged product).
 // One block barrier per round (after A): B, C and D run warp-autonomously, so a warp with cheap pages never waits for one with
 // expensive pages.  No per-page global atomics; skipped pages never reach a warp.
-// Everything before cudaGridDependencySynchronize() (launch, descriptor reads, classification, L2 prefetch) only READS scene data:
-// when culls are issued back to back with programmatic stream serialization it overlaps the tail of the previous cull.
-// HBM-bound: 32 B descriptor per page + 16 B per tested sphere + 4 B read + 4 B write per visible id (+ 32 B mask per page).
+// Everything before cudaGridDependencySynchronize() (launch, descriptor reads, classification, L2 prefetch, the sphere tests of
+// phase B whose results sit in shared memory) only READS scene data: when culls are issued back to back with programmatic stream
+// serialization it overlaps the tail of the previous cull.
+// HBM-bound: 32 B descriptor per page + 16 B per tested sphere + 4 B read + 4 B write per visible id + 32 B mask row per page.
 #pragma once
 
 #include "lb200_internal.h"
@@ -28,7 +29,7 @@ namespace lbcull {
 
 using namespace lb;
 
-// block size is a template parameter: 256 threads x 4 blocks/SM or 512 x 2 (pages per block per round = one classify thread each)
+// block size is a template parameter (256 in the build: 4 blocks/SM at 64 registers); pages per block per round <= one classify thread each
 constexpr int ROWS = 7;                 // ceil(200 / 32)
 constexpr int N_STATS = 8;
 enum { ST_PAGES_TESTED = 0, ST_PAGES_INSIDE, ST_PAGES_OUTSIDE, ST_PAGES_FILTERED, ST_ENT_TESTED, ST_ENT_INSIDE, ST_ENT_STREAMED };

@@ -86,6 +86,29 @@ __global__ void __launch_bounds__(256) pack_slab_kernel(const __grid_constant__ 
 	}
 }
 
+// Result of one cull straight into page-locked HOST memory (lb200_culling_cull with a pinned destination): all counters into
+// host_counters, the visible ids packed type after type into host_ids — posted writes over PCIe while the copy engine stays idle, and no
+// count round trip between the cull and the transfer.  Ids beyond `slab_ids` (the caller's capacity) are dropped; the host sees the
+// counts and reports LB200_ERR_CAPACITY.
+__global__ void __launch_bounds__(256) pack_host_kernel(const __grid_constant__ PackParams P, const uint32_t* __restrict__ counters,
+	const uint32_t* __restrict__ out_ids, uint32_t* __restrict__ host_ids, uint32_t* __restrict__ host_counters)
+{
+	__shared__ uint32_t s_cnt[256];
+	__shared__ uint32_t s_off[257];
+	__shared__ uint32_t s_list[256];
+	__shared__ uint32_t s_nnz;
+	scan_types(counters, s_cnt, s_off, s_list, &s_nnz);
+	if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < (uint32_t)COUNTER_WORDS; i += blockDim.x) host_counters[i] = counters[i];
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	for (uint32_t k = 0; k < s_nnz; ++k) {
+		const uint32_t t = s_list[k];
+		const uint32_t c = s_cnt[t];
+		const uint32_t* src = out_ids + P.type_base[t];
+		const uint32_t off = s_off[t];
+		for (uint32_t i = gtid; i < c; i += gsize) if (off + i < P.slab_ids) host_ids[off + i] = src[i];
+	}
+}
+
 // Fused pack + NVLink push: the slab is written straight into every rank's gather buffer through peer-mapped pointers (P2P stores
 // over NVSwitch), then the last block publishes this rank's epoch in every rank's flag block.  No NCCL call on the per-frame path.
 struct PushParams {
@@ -251,6 +274,7 @@ struct lb200_culling {
 	uint32_t* last_out = nullptr;
 	uint32_t* last_mask = nullptr;
 	uint32_t* h_counters = nullptr; // pinned, COUNTER_WORDS
+	uint32_t* h_counters_dev = nullptr; // the same memory as the device addresses it (null: no direct host writes)
 	int grid = 0;       // resident blocks of a cull that has the device to itself
 	int grid_lanes = 0; // resident blocks of a cull issued by cull_device_n (runs next to its neighbours)
 	int threads = 256;
@@ -283,7 +307,8 @@ int ensureDevice(lb200_culling* cs) {
 		cs->lanes = lb200_cull_lanes();
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS));
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS, ctx->stream));
-		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocDefault));
+		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocMapped));
+		if (cudaHostGetDevicePointer((void**)&cs->h_counters_dev, cs->h_counters, 0) != cudaSuccess) { cudaGetLastError(); cs->h_counters_dev = nullptr; }
 		cs->threads = 256; // 512-thread blocks measured no better (profiles/)
 		int per_sm = 0;
 		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<256>, 256, 0));
@@ -500,11 +525,19 @@ int joinLanes(lb200_culling* cs) {
 	return LB200_OK;
 }
 
+void parseCounts(lb200_culling* cs, lb200_cull_result* result);
+
 int readCounts(lb200_culling* cs, lb200_cull_result* result) {
 	lb200_ctx* ctx = cs->ctx;
 	const uint32_t* cur = cs->last_counters;
 	LB200_CUDA(ctx, cudaMemcpyAsync(cs->h_counters, cur, sizeof(uint32_t) * COUNTER_WORDS, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	parseCounts(cs, result);
+	return LB200_OK;
+}
+
+// h_counters (already on the host) -> cs->last / *result
+void parseCounts(lb200_culling* cs, lb200_cull_result* result) {
 	lb200_cull_result& res = cs->last;
 	memset(&res, 0, sizeof(res));
 	for (int t = 0; t < 256; ++t) {
@@ -523,7 +556,6 @@ int readCounts(lb200_culling* cs, lb200_cull_result* result) {
 	// descriptor per page + 16 B per tested sphere + (4 B id read + 4 B id write) per visible + 32 B mask per page
 	cs->last_bytes = (uint64_t)cs->last_pages * 32 + (uint64_t)res.entities_tested * 16 + (uint64_t)res.total * 8 + (uint64_t)cs->last_pages * 32;
 	if (result) *result = res;
-	return LB200_OK;
 }
 
 } // namespace
@@ -704,6 +736,28 @@ int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, 
 {
 	if (!cs || !frustum || !result) return LB200_ERR_INVALID;
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	lb200_ctx* ctx = cs->ctx;
+	// Destination in page-locked host memory (lb200_host_alloc / cudaHostAlloc / cudaHostRegister): the device writes the result there
+	// itself — one launch behind the cull, one synchronisation, no count round trip.  Pageable destinations take the copy path below.
+	static const bool no_direct = getenv("LB200_CULL_HOST_MEMCPY") != nullptr;
+	if (!no_direct && out_ids && capacity && !cs->host.cells.empty() && ensureDevice(cs) == LB200_OK && cs->h_counters_dev) {
+		cudaPointerAttributes attr = {};
+		if (cudaPointerGetAttributes(&attr, out_ids) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+			int rc = launchCull(cs, frustum, type);
+			if (rc) return rc;
+			PackParams PP;
+			memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
+			PP.slab_ids = capacity;
+			pack_host_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(PP, cs->last_counters, cs->last_out, (uint32_t*)attr.devicePointer, cs->h_counters_dev);
+			LB200_CHECK_LAUNCH(ctx);
+			LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			parseCounts(cs, result);
+			uint32_t off = 0;
+			for (int t = 0; t < 256; ++t) { result->type_offset[t] = off; off += result->type_count[t]; }
+			return result->total > capacity ? LB200_ERR_CAPACITY : LB200_OK;
+		}
+		cudaGetLastError(); // unregistered host memory makes cudaPointerGetAttributes fail on old drivers: not an error here
+	}
 	lb200_cull_result dev;
 	const uint32_t* d_ids = nullptr;
 	int rc = lb200_culling_cull_device(cs, frustum, type, &d_ids, &dev, 1);
@@ -712,7 +766,6 @@ int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, 
 	uint32_t off = 0;
 	for (int t = 0; t < 256; ++t) { result->type_offset[t] = off; off += dev.type_count[t]; }
 	if (dev.total > capacity || (dev.total && !out_ids)) return LB200_ERR_CAPACITY;
-	lb200_ctx* ctx = cs->ctx;
 	for (int t = 0; t < 256; ++t) {
 		if (!dev.type_count[t]) continue;
 		LB200_CUDA(ctx, cudaMemcpyAsync(out_ids + result->type_offset[t], d_ids + dev.type_offset[t], sizeof(uint32_t) * dev.type_count[t], cudaMemcpyDeviceToHost, ctx->stream));

@@ -236,3 +236,29 @@ def test_overlapped_views_keep_results_apart(ctx, oracle):
     cs.cull_device_n(views[0], 5)
     check_last(views[0])
     cs.close()
+
+
+def test_pinned_and_pageable_destinations_agree(ctx, oracle):
+    """lb200_culling_cull writes straight into a page-locked destination from the device and falls back to copies for pageable
+    memory; both must hand back the oracle's sets, per type, and report the same counts; a too-small buffer is LB200_ERR_CAPACITY."""
+    import ctypes as C
+    from lumixengine_b200 import _lib
+    scene = scenes.cull_scene(150_000, (3000.0, 300.0, 3000.0), seed=41, big_fraction=0.003, type_probs=(0.5, 0.3, 0.2))
+    cs, oc = _both(ctx, oracle, scene)
+    f = lb.frustum_perspective(**dict(scenes.c1_frustum_args(), far=2200.0))
+    oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f))
+    pinned = cs.cull(f)
+    _assert_same(pinned, oids, otys)
+    pageable = np.zeros(cs.entity_count(), np.uint32)  # plain numpy memory
+    res = _lib.CullResult()
+    rc = cs.L.lb200_culling_cull(cs.h, C.byref(f), C.c_uint8(0xFF), pageable.ctypes.data_as(C.c_void_p), C.c_uint32(len(pageable)), C.byref(res))
+    assert rc == 0 and res.total == pinned.total
+    assert list(res.type_count[:4]) == [int((otys == t).sum()) for t in range(4)]
+    for t in range(3):
+        o, c = int(res.type_offset[t]), int(res.type_count[t])
+        assert np.array_equal(np.sort(pageable[o:o + c]).astype(np.int64), np.sort(oids[otys == t]).astype(np.int64))
+        assert np.array_equal(np.sort(pinned.of_type(t)).astype(np.int64), np.sort(oids[otys == t]).astype(np.int64))
+    small = ctx.host_alloc(16, np.uint32)
+    rc = cs.L.lb200_culling_cull(cs.h, C.byref(f), C.c_uint8(0xFF), small.ctypes.data_as(C.c_void_p), C.c_uint32(16), C.byref(res))
+    assert rc == _lib.ERR_CAPACITY and res.total == pinned.total
+    cs.close()
