@@ -232,6 +232,13 @@ LB200_API int lb200_hierarchy_get_globals(lb200_hierarchy* h, lb200_transform* o
 /* RenderModuleImpl::onModelInstanceMoved, render_module.cpp:1544-1554: world sphere per node =
  * (global.pos, bounding_radius * max(scale)); out_pos3 n*3 doubles, out_radius n floats (host). */
 LB200_API int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius, double* out_pos3, float* out_radius);
+/* The other direction, World::transformEntity(entity, update_local = true) (world.cpp:267-270) / World::setParent (world.cpp:619-701):
+ * world transforms are authoritative (physics, editor gizmo, re-parenting) and the local transforms follow:
+ * local = Transform::computeLocal(parent global, own global) (math.cpp:809-816) for every non-root node, one launch.
+ * set_globals uploads all n world transforms (caller's node order); get_locals copies the locals back (roots: as uploaded). */
+LB200_API int lb200_hierarchy_set_globals(lb200_hierarchy* h, const lb200_transform* globals);
+LB200_API int lb200_hierarchy_compute_locals(lb200_hierarchy* h);
+LB200_API int lb200_hierarchy_get_locals(lb200_hierarchy* h, lb200_transform* out_locals);
 /* World::getRelativeMatrix (src/engine/world.cpp:370-377) of every node against one base position (the camera): out_matrices = n x 16
  * floats, column-major like Matrix (math.h:329-392), indexed like `parents`.  Consumers of the propagated transforms
  * (pipeline.cpp instance setup) take these instead of calling getRelativeMatrix per entity. */

@@ -71,6 +71,28 @@ __device__ __forceinline__ void compose_node(uint32_t i, const int* __restrict__
 	G.sx[i] = gscale.x; G.sy[i] = gscale.y; G.sz[i] = gscale.z;
 }
 
+// The update_local branch of World::transformEntity (world.cpp:267-270) for every non-root node at once:
+// local = Transform::computeLocal(parent global, own global), math.cpp:809-816.  No dependency between nodes: one flat launch.
+__global__ void __launch_bounds__(HT) compute_locals_kernel(uint32_t begin, uint32_t end, const int* __restrict__ parent, SoaTransforms G, SoaTransforms L) {
+	const uint32_t i = begin + blockIdx.x * HT + threadIdx.x;
+	if (i >= end) return;
+	const int p = parent[i];
+	const float4 pr = G.rot[p];
+	const Q4 c = q4(pr.x, pr.y, pr.z, -pr.w); // Quat::conjugated() = (x, y, z, -w), math.cpp:664-667
+	const double psx = (double)G.sx[p], psy = (double)G.sy[p], psz = (double)G.sz[p];
+	// inv_parent_pos = conj.rotate(-parent.pos) / parent.scale      (DVec3 / Vec3: double / float per component, math.cpp:502)
+	const D3 rp = rotate(c, d3(-G.px[p], -G.py[p], -G.pz[p]));
+	const D3 inv_parent_pos = d3(LB_DDIV(rp.x, psx), LB_DDIV(rp.y, psy), LB_DDIV(rp.z, psz));
+	// pos = conj.rotate(child.pos) / parent.scale + inv_parent_pos
+	const D3 rc = rotate(c, d3(G.px[i], G.py[i], G.pz[i]));
+	const D3 lpos = add(d3(LB_DDIV(rc.x, psx), LB_DDIV(rc.y, psy), LB_DDIV(rc.z, psz)), inv_parent_pos);
+	const float4 cr = G.rot[i];
+	const Q4 lrot = qmul(c, q4(cr.x, cr.y, cr.z, cr.w));
+	L.px[i] = lpos.x; L.py[i] = lpos.y; L.pz[i] = lpos.z;
+	L.rot[i] = make_float4(lrot.x, lrot.y, lrot.z, lrot.w);
+	L.sx[i] = LB_FDIV(G.sx[i], G.sx[p]); L.sy[i] = LB_FDIV(G.sy[i], G.sy[p]); L.sz[i] = LB_FDIV(G.sz[i], G.sz[p]); // Vec3 / Vec3, math.cpp:468
+}
+
 // One depth level: nodes [begin, end) in level order; parents live in earlier levels.
 // Launched with programmatic stream serialization: the block starts while the previous level is still draining, loads its
 // own locals (independent of that level) and only then waits for the parents' globals.
@@ -348,6 +370,34 @@ int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius
 	LB200_CHECK_LAUNCH(ctx);
 	LB200_CUDA(ctx, cudaMemcpyAsync(out_pos3, h->d_sphere_pos, sizeof(double) * 3 * (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaMemcpyAsync(out_radius, h->d_sphere_radius, sizeof(float) * h->n, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
+int lb200_hierarchy_set_globals(lb200_hierarchy* h, const lb200_transform* globals) {
+	if (!h || !globals) return LB200_ERR_INVALID;
+	return upload(h, globals, h->G, h->n);
+}
+
+int lb200_hierarchy_compute_locals(lb200_hierarchy* h) {
+	if (!h) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	const uint32_t begin = h->level_start[1], end = h->n; // level 0 = roots: no parent, local transform left alone
+	if (end > begin) {
+		compute_locals_kernel<<<(end - begin + HT - 1) / HT, HT, 0, ctx->stream>>>(begin, end, h->d_parent, h->G, h->L);
+		LB200_CHECK_LAUNCH(ctx);
+	}
+	return LB200_OK;
+}
+
+int lb200_hierarchy_get_locals(lb200_hierarchy* h, lb200_transform* out_locals) {
+	if (!h || !out_locals) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	soa_to_aos_kernel<<<(h->n + HT - 1) / HT, HT, 0, ctx->stream>>>(h->L, h->d_order, h->n, h->d_stage);
+	LB200_CHECK_LAUNCH(ctx);
+	LB200_CUDA(ctx, cudaMemcpyAsync(out_locals, h->d_stage, sizeof(lb200_transform) * (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return LB200_OK;
 }

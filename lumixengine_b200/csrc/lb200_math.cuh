@@ -18,6 +18,7 @@
 #define LB_DMUL(a, b) __dmul_rn((a), (b))
 #define LB_DADD(a, b) __dadd_rn((a), (b))
 #define LB_DSUB(a, b) __dsub_rn((a), (b))
+#define LB_DDIV(a, b) __ddiv_rn((a), (b))
 #define LB_FSQRT(a) __fsqrt_rn((a))
 #define LB_FDIV(a, b) __fdiv_rn((a), (b))
 #else
@@ -28,6 +29,7 @@
 #define LB_DMUL(a, b) ((a) * (b))
 #define LB_DADD(a, b) ((a) + (b))
 #define LB_DSUB(a, b) ((a) - (b))
+#define LB_DDIV(a, b) ((a) / (b))
 #define LB_FSQRT(a) sqrtf((a))
 #define LB_FDIV(a, b) ((a) / (b))
 #endif

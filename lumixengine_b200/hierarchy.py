@@ -53,6 +53,22 @@ class Hierarchy:
         assert len(a) == self.n
         check(self.L.lb200_hierarchy_set_root_globals(self.h, ptr(a)), self.ctx.h)
 
+    def setTransforms(self, globals_):
+        """World transforms of ALL nodes (authoritative globals: physics, gizmo, re-parenting)."""
+        a = np.ascontiguousarray(globals_, TRANSFORM_DTYPE)
+        assert len(a) == self.n
+        check(self.L.lb200_hierarchy_set_globals(self.h, ptr(a)), self.ctx.h)
+
+    def computeLocalTransforms(self):
+        """transformEntity(update_local=true) (world.cpp:267-270) for every non-root node: local = computeLocal(parent, own)."""
+        check(self.L.lb200_hierarchy_compute_locals(self.h), self.ctx.h)
+
+    def getLocalTransforms(self, out=None):
+        if out is None:
+            out = np.empty(self.n, TRANSFORM_DTYPE)
+        check(self.L.lb200_hierarchy_get_locals(self.h, ptr(out)), self.ctx.h)
+        return out
+
     def propagate(self):
         check(self.L.lb200_hierarchy_propagate(self.h), self.ctx.h)
 

@@ -52,6 +52,10 @@ void oracle_rng_floats(uint32_t* u, uint32_t* v, uint32_t n, float* out);
 void oracle_propagate(const int32_t* parents, const OTransform* locals, OTransform* globals, uint32_t n);
 /* render_module.cpp:1544-1554: radius = bounding_radius * max(scale.xyz) */
 void oracle_sphere_radius(const OTransform* globals, const float* bounding_radius, float* out_radius, uint32_t n);
+/* The update_local branch of World::transformEntity (world.cpp:267-270) for every non-root node:
+ * locals[i] = Transform::computeLocal(globals[parents[i]], globals[i]) (math.cpp:809-816); roots keep locals[i] untouched. */
+void oracle_compute_locals(const int32_t* parents, const OTransform* globals, OTransform* locals, uint32_t n);
+void oracle_transform_compute_local(const OTransform* parent, const OTransform* child, OTransform* out, uint32_t n);
 /* world.cpp:370-377 World::getRelativeMatrix: rot.toMatrix(), translation = Vec3(pos - base_pos), multiply3x3(scale) */
 void oracle_relative_matrices(const OTransform* globals, const double* base_pos3, OMatrix* out, uint32_t n);
 

@@ -147,6 +147,20 @@ static inline OTransform otransform_compose(const OTransform* a, const OTransfor
 	return r;
 }
 
+/* math.cpp:809-816 Transform::computeLocal(parent, child): conjugated() = (x, y, z, -w) (math.cpp:664-667), DVec3 unary minus
+ * (math.cpp:494), Quat::rotate(DVec3) in fp64, DVec3 / Vec3 = double / float per component (math.cpp:502), Vec3 / Vec3 (math.cpp:468) */
+static inline OTransform otransform_compute_local(const OTransform* parent, const OTransform* child) {
+	const OQuat c = oquat_conjugated(parent->rot);
+	const ODVec3 rp = oquat_rotate_d(c, odv3(-parent->pos.x, -parent->pos.y, -parent->pos.z));
+	const ODVec3 inv_parent_pos = odv3(rp.x / parent->scale.x, rp.y / parent->scale.y, rp.z / parent->scale.z);
+	const ODVec3 rc = oquat_rotate_d(c, child->pos);
+	OTransform r;
+	r.pos = odv3_add(odv3(rc.x / parent->scale.x, rc.y / parent->scale.y, rc.z / parent->scale.z), inv_parent_pos);
+	r.rot = oquat_mul(c, child->rot);
+	r.scale = ov3(child->scale.x / parent->scale.x, child->scale.y / parent->scale.y, child->scale.z / parent->scale.z);
+	return r;
+}
+
 /* math.cpp:859-861 LocalRigidTransform::operator* */
 static inline OLocalRigidTransform olrt_mul(OLocalRigidTransform a, OLocalRigidTransform b) {
 	OLocalRigidTransform r;

@@ -68,3 +68,14 @@ void oracle_relative_matrices(const OTransform* globals, const double* base_pos3
 		out[i] = m;
 	}
 }
+
+void oracle_compute_locals(const int32_t* parents, const OTransform* globals, OTransform* locals, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) {
+		if (parents[i] < 0) continue; /* world.cpp:267: only entities with a valid parent */
+		locals[i] = otransform_compute_local(&globals[parents[i]], &globals[i]);
+	}
+}
+
+void oracle_transform_compute_local(const OTransform* parent, const OTransform* child, OTransform* out, uint32_t n) {
+	for (uint32_t i = 0; i < n; ++i) out[i] = otransform_compute_local(&parent[i], &child[i]);
+}

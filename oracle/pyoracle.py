@@ -201,6 +201,36 @@ def propagate(parents, locals56, globals56):
     return g
 
 
+def transform_compose(parent56, local56):
+    """Element-wise Transform::compose (math.cpp:801-807)."""
+    a = np.ascontiguousarray(parent56, np.uint8)
+    b = np.ascontiguousarray(local56, np.uint8)
+    out = np.zeros_like(a)
+    lib().oracle_transform_compose(_ptr(a), _ptr(b), _ptr(out), C.c_uint32(len(a)))
+    return out
+
+
+def compute_locals(parents, globals56, locals56):
+    """World::transformEntity(update_local) for every non-root node: local = Transform::computeLocal(parent global, own global)."""
+    p = np.ascontiguousarray(parents, np.int32)
+    g = np.ascontiguousarray(globals56, np.uint8)
+    l = np.array(locals56, np.uint8, copy=True, order="C")
+    lib().oracle_compute_locals(_ptr(p), _ptr(g), _ptr(l), C.c_uint32(len(p)))
+    return l
+
+
+def transform_compute_local(parent56, child56, use_ref=False):
+    """Element-wise Transform::computeLocal (math.cpp:809-816); use_ref=True runs the reference's own function (oracle/_ref)."""
+    a = np.ascontiguousarray(parent56, np.uint8)
+    b = np.ascontiguousarray(child56, np.uint8)
+    out = np.zeros_like(a)
+    if use_ref:
+        ref().ref_transform_compute_local(_ptr(a), _ptr(b), _ptr(out), C.c_uint32(len(a)))
+    else:
+        lib().oracle_transform_compute_local(_ptr(a), _ptr(b), _ptr(out), C.c_uint32(len(a)))
+    return out
+
+
 def relative_matrices(globals56, base_pos):
     """World::getRelativeMatrix (world.cpp:370-377) for every transform: float32[n,16], column-major like Matrix."""
     g = np.ascontiguousarray(globals56, np.uint8)

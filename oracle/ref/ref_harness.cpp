@@ -132,6 +132,13 @@ REF_API void ref_relative_matrix(const void* tr56, const double* base_pos, float
 	}
 }
 
+REF_API void ref_transform_compute_local(const void* parent56, const void* child56, void* out56, uint32_t n) {
+	const Transform* p = (const Transform*)parent56;
+	const Transform* c = (const Transform*)child56;
+	Transform* o = (Transform*)out56;
+	for (uint32_t i = 0; i < n; ++i) o[i] = Transform::computeLocal(p[i], c[i]);
+}
+
 REF_API void ref_quat_mul(const float* a, const float* b, float* out, uint32_t n) {
 	for (uint32_t i = 0; i < n; ++i) {
 		const Quat r = Quat(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]) * Quat(b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);

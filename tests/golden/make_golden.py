@@ -173,6 +173,17 @@ def world_kat():
     d = dict(tr=t.view(np.uint8).reshape(n, 56), bases=bases)
     for k, b in enumerate(bases):
         d[f"rel{k}"] = po.ref_relative_matrices(d["tr"], b)
+    # Transform::computeLocal (math.cpp:809-816): parents with non-uniform scale, children near and far from them
+    par = np.zeros(n, tr_dtype); chi = np.zeros(n, tr_dtype)
+    par["pos"] = rng.normal(size=(n, 3)) * np.where(rng.random((n, 1)) < 0.5, 1e3, 1e6)
+    par["rot"] = unit_quats(rng, n)
+    par["scale"] = (0.25 + 2 * rng.random((n, 3))).astype(np.float32)
+    chi["pos"] = par["pos"] + rng.normal(size=(n, 3)) * np.where(rng.random((n, 1)) < 0.5, 5.0, 5e3)
+    chi["rot"] = unit_quats(rng, n)
+    chi["scale"] = (0.25 + 2 * rng.random((n, 3))).astype(np.float32)
+    d["cl_parent"] = par.view(np.uint8).reshape(n, 56)
+    d["cl_child"] = chi.view(np.uint8).reshape(n, 56)
+    d["cl_out"] = po.transform_compute_local(d["cl_parent"], d["cl_child"], use_ref=True)
     np.savez_compressed(os.path.join(OUT, "world_kat.npz"), **d)
     print("world_kat.npz", sum(v.nbytes for v in d.values()))
 

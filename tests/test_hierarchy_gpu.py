@@ -133,3 +133,35 @@ def test_relative_matrices_match_oracle(ctx, oracle):
             scale = np.maximum(np.abs(exp).max(axis=1, keepdims=True), 1e-30)
             assert np.all(np.abs(got.astype(np.float64) - exp) <= REL_TOL * scale)
     h.close()
+
+
+def test_compute_locals_match_oracle(ctx, oracle):
+    """World::transformEntity(update_local) batched: locals from authoritative globals (Transform::computeLocal, math.cpp:809-816),
+    bit-exact against the oracle; then propagate brings the globals back within the 1e-5 relative tolerance of north_star."""
+    parents, locals_, roots = scenes.hierarchy_forest(40_000, 7, 3, seed=5)
+    h = lb.Hierarchy(ctx, parents)
+    h.setLocalTransforms(locals_)
+    h.setRootTransforms(roots)
+    h.propagate()
+    globals_ = h.getTransforms()
+    # move every node in world space (as physics would), then ask for the locals that reproduce it
+    rng = np.random.default_rng(9)
+    moved = globals_.copy()
+    moved["pos"] += rng.normal(size=moved["pos"].shape) * 3.0
+    h.setTransforms(moved)
+    h.computeLocalTransforms()
+    got = h.getLocalTransforms()
+    exp = oracle.compute_locals(parents, _as_bytes(moved), _as_bytes(locals_)).view(lb.TRANSFORM_DTYPE).reshape(-1)
+    nonroot = parents >= 0
+    assert nonroot.sum() > 30_000
+    if not np.array_equal(_as_bytes(got)[nonroot, :52], _as_bytes(exp)[nonroot, :52]):
+        for k in ("pos", "rot", "scale"):
+            g, e = got[k][nonroot].astype(np.float64), exp[k][nonroot].astype(np.float64)
+            scale = np.maximum(np.abs(e).max(axis=1, keepdims=True), 1e-30)
+            assert np.all(np.abs(g - e) <= REL_TOL * scale), k
+    # round trip: propagate with the new locals reproduces the moved world transforms
+    h.propagate()
+    back = h.getTransforms()
+    err = np.abs(back["pos"] - moved["pos"]).max()
+    assert err < 1e-5 * max(1.0, np.abs(moved["pos"]).max()), err
+    h.close()

@@ -135,3 +135,17 @@ def test_relative_matrices(oracle):
     for i, base in enumerate(k["bases"]):
         got = oracle.relative_matrices(k["tr"], base)
         assert np.array_equal(got.view(np.uint32), k[f"rel{i}"].view(np.uint32))
+
+
+def test_compute_local(oracle):
+    """Transform::computeLocal (math.cpp:809-816) against the reference's own function, and as the inverse of compose."""
+    k = np.load(os.path.join(G, "world_kat.npz"))
+    got = oracle.transform_compute_local(k["cl_parent"], k["cl_child"])
+    assert np.array_equal(got[:, :52], k["cl_out"][:, :52])
+    # compose(parent, computeLocal(parent, child)) comes back to child within rounding (fp64 position, fp32 rotation / scale)
+    dt = np.dtype({"names": ["pos", "rot", "scale"], "formats": [(np.float64, 3), (np.float32, 4), (np.float32, 3)], "offsets": [0, 24, 40], "itemsize": 56})
+    back = oracle.transform_compose(k["cl_parent"], got).view(dt).reshape(-1)
+    child = k["cl_child"].view(dt).reshape(-1)
+    assert np.allclose(back["pos"], child["pos"], rtol=0, atol=2e-3 * (1 + np.abs(child["pos"]).max() * 1e-6))
+    assert np.allclose(back["scale"], child["scale"], rtol=1e-5)
+    assert np.allclose(np.abs((back["rot"] * child["rot"]).sum(1)), 1.0, atol=1e-5)
