@@ -317,6 +317,14 @@ LB200_API int lb200_animation_skin(lb200_animation* a);
 LB200_API int lb200_animation_get_dual_quats(lb200_animation* a, uint32_t first, uint32_t count, float* out8);
 LB200_API int lb200_animation_get_matrices(lb200_animation* a, uint32_t first, uint32_t count, float* out16);
 LB200_API int lb200_animation_get_pose(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3, float* out_rot4);
+/* Pose::computeRelative (src/renderer/pose.cpp:136-146) of every instance's absolute pose (needs an update with LB200_PALETTE_POSE):
+ * the parent-relative poses IK / ragdoll consumers start from (controller.cpp).  Kept in HBM next to the absolute ones. */
+LB200_API int lb200_animation_compute_relative(lb200_animation* a);
+LB200_API int lb200_animation_get_relative_pose(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3, float* out_rot4);
+/* Pose::blend (pose.cpp:30-41), instance by instance: a's poses move towards b's by `weight` (<= 0.001: untouched; clamped to [0,1]);
+ * positions a*(1-w) + b*w, rotations scalar nlerp.  relative != 0 blends the parent-relative buffers of compute_relative, else the
+ * absolute ones.  Both systems: same context, skeleton size and instance count. */
+LB200_API int lb200_animation_blend_pose(lb200_animation* a, const lb200_animation* b, float weight, int relative);
 LB200_API int lb200_animation_get_times(lb200_animation* a, uint32_t first, uint32_t count, uint32_t* out_ticks);
 LB200_API int lb200_animation_get_skinned(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3);
 /* Checksum of the skinned vertex buffer computed on the device (sum of the raw u32 bit patterns, mod 2^64) —

@@ -276,6 +276,21 @@ class AnimationSystem:
         check(self.L.lb200_animation_get_pose(self.h, C.c_uint32(first), C.c_uint32(count), ptr(pos), ptr(rot)), self.ctx.h)
         return pos, rot
 
+    def computeRelative(self):
+        """Pose::computeRelative (pose.cpp:136-146) of every instance's absolute pose (update with PALETTE_POSE first)."""
+        check(self.L.lb200_animation_compute_relative(self.h), self.ctx.h)
+
+    def getRelativePose(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        pos = np.empty((count, self.skeleton.bone_count, 3), np.float32)
+        rot = np.empty((count, self.skeleton.bone_count, 4), np.float32)
+        check(self.L.lb200_animation_get_relative_pose(self.h, C.c_uint32(first), C.c_uint32(count), ptr(pos), ptr(rot)), self.ctx.h)
+        return pos, rot
+
+    def blendPose(self, other, weight, relative=False):
+        """Pose::blend (pose.cpp:30-41) per instance: this system's poses move towards `other`'s by weight."""
+        check(self.L.lb200_animation_blend_pose(self.h, other.h, C.c_float(weight), C.c_int(1 if relative else 0)), self.ctx.h)
+
     def getTimes(self, first=0, count=None):
         count = self.n - first if count is None else count
         out = np.empty(count, np.uint32)

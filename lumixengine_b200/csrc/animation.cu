@@ -409,6 +409,51 @@ __global__ void __launch_bounds__(256) checksum_kernel(const uint32_t* __restric
 	if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// Pose::computeRelative (pose.cpp:136-146) for every instance: the reference walks the bones from the last one down, so a bone's
+// parent (index < bone) is still absolute when the bone is converted — every bone only needs the ABSOLUTE pose of itself and of its
+// parent, and all (instance, bone) pairs are independent.  Bones below first_nonroot keep their pose.
+__global__ void __launch_bounds__(256) pose_relative_kernel(const float* __restrict__ abs_pos, const float* __restrict__ abs_rot,
+	const short* __restrict__ parents, uint32_t bone_count, uint32_t first_nonroot, size_t n_bones_total, float* __restrict__ rel_pos, float* __restrict__ rel_rot)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_bones_total) return;
+	const uint32_t bone = (uint32_t)(i % bone_count);
+	const size_t base = i - bone;
+	V3 p = v3(abs_pos[3 * i], abs_pos[3 * i + 1], abs_pos[3 * i + 2]);
+	Q4 r = q4(abs_rot[4 * i], abs_rot[4 * i + 1], abs_rot[4 * i + 2], abs_rot[4 * i + 3]);
+	if (bone >= first_nonroot) {
+		const size_t pi = base + (uint32_t)parents[bone];
+		const Q4 c = q4(abs_rot[4 * pi], abs_rot[4 * pi + 1], abs_rot[4 * pi + 2], -abs_rot[4 * pi + 3]); // conjugated() = (x, y, z, -w), math.cpp:664-667
+		const V3 pp = v3(abs_pos[3 * pi], abs_pos[3 * pi + 1], abs_pos[3 * pi + 2]);
+		p = rotate(c, sub(p, pp));
+		r = qmul(c, r);
+	}
+	rel_pos[3 * i] = p.x; rel_pos[3 * i + 1] = p.y; rel_pos[3 * i + 2] = p.z;
+	rel_rot[4 * i] = r.x; rel_rot[4 * i + 1] = r.y; rel_rot[4 * i + 2] = r.z; rel_rot[4 * i + 3] = r.w;
+}
+
+// Pose::blend (pose.cpp:30-41) for every bone of every instance: positions a*inv + b*w, rotations scalar nlerp (math.cpp:677-692:
+// dot summed ((x+y)+z)+w, sign flip of t, normalise with 1/sqrt).  weight is already clamped; the caller skips weight <= 0.001.
+__global__ void __launch_bounds__(256) pose_blend_kernel(float* __restrict__ pos_a, float* __restrict__ rot_a, const float* __restrict__ pos_b,
+	const float* __restrict__ rot_b, size_t n_bones_total, float weight)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_bones_total) return;
+	const float inv = LB_FSUB(1.0f, weight);
+#pragma unroll
+	for (int k = 0; k < 3; ++k) pos_a[3 * i + k] = LB_FADD(LB_FMUL(pos_a[3 * i + k], inv), LB_FMUL(pos_b[3 * i + k], weight));
+	const Q4 q1 = q4(rot_a[4 * i], rot_a[4 * i + 1], rot_a[4 * i + 2], rot_a[4 * i + 3]);
+	const Q4 q2 = q4(rot_b[4 * i], rot_b[4 * i + 1], rot_b[4 * i + 2], rot_b[4 * i + 3]);
+	float t = weight;
+	const float d = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(q1.x, q2.x), LB_FMUL(q1.y, q2.y)), LB_FMUL(q1.z, q2.z)), LB_FMUL(q1.w, q2.w));
+	if (d < 0) t = -t;
+	Q4 q = q4(LB_FADD(LB_FMUL(q1.x, inv), LB_FMUL(q2.x, t)), LB_FADD(LB_FMUL(q1.y, inv), LB_FMUL(q2.y, t)),
+		LB_FADD(LB_FMUL(q1.z, inv), LB_FMUL(q2.z, t)), LB_FADD(LB_FMUL(q1.w, inv), LB_FMUL(q2.w, t)));
+	const float len2 = LB_FADD(LB_FADD(LB_FADD(LB_FMUL(q.x, q.x), LB_FMUL(q.y, q.y)), LB_FMUL(q.z, q.z)), LB_FMUL(q.w, q.w));
+	const float l = LB_FDIV(1.0f, LB_FSQRT(len2));
+	rot_a[4 * i] = LB_FMUL(q.x, l); rot_a[4 * i + 1] = LB_FMUL(q.y, l); rot_a[4 * i + 2] = LB_FMUL(q.z, l); rot_a[4 * i + 3] = LB_FMUL(q.w, l);
+}
+
 } // namespace
 
 struct lb200_animation {
@@ -426,6 +471,8 @@ struct lb200_animation {
 	int lanes_per_instance = 8;
 	uint32_t* d_clip_index = nullptr; uint32_t* d_time = nullptr;
 	float* d_dq = nullptr; float* d_mtx = nullptr; float* d_pos = nullptr; float* d_rot = nullptr;
+	float* d_rel_pos = nullptr; float* d_rel_rot = nullptr; // Pose::computeRelative of d_pos / d_rot
+	uint32_t first_nonroot = 0;
 	float* d_mesh_pos = nullptr; float4* d_mesh_w = nullptr; short* d_mesh_idx = nullptr;
 	float* d_skinned = nullptr;
 	unsigned long long* d_checksum = nullptr;
@@ -531,6 +578,7 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	lb200_animation* a = new (std::nothrow) lb200_animation;
 	if (!a) return LB200_ERR_CUDA;
 	a->ctx = ctx; a->bone_count = B; a->max_level = max_level; a->n_clips = n_clips; a->max_instances = max_instances;
+	a->first_nonroot = first;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	ANIM_MALLOC(a->d_clips, sizeof(DevClip) * n_clips);
 	ANIM_MALLOC(a->d_tracks, sizeof(DevTrack) * tracks.size());
@@ -615,7 +663,7 @@ void lb200_animation_destroy(lb200_animation* a) {
 	cudaStreamSynchronize(a->ctx->stream);
 	cudaFree(a->d_clips); cudaFree(a->d_tracks); cudaFree(a->d_const_t); cudaFree(a->d_const_r_value); cudaFree(a->d_const_r_bone); cudaFree(a->d_stream);
 	cudaFree(a->d_bind); cudaFree(a->d_key_pos); cudaFree(a->d_key_rot); cudaFree(a->d_key_flags); cudaFree(a->d_parents); cudaFree(a->d_level_bones); cudaFree(a->d_level_start);
-	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot);
+	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot); cudaFree(a->d_rel_pos); cudaFree(a->d_rel_rot);
 	cudaFree(a->d_mesh_pos); cudaFree(a->d_mesh_w); cudaFree(a->d_mesh_idx); cudaFree(a->d_skinned); cudaFree(a->d_checksum);
 	delete a;
 }
@@ -709,6 +757,41 @@ int lb200_animation_get_pose(lb200_animation* a, uint32_t first, uint32_t count,
 	if (rc) return rc;
 	return readBack(a, a->d_rot, sizeof(float) * 4 * a->bone_count, first, count, out_rot4);
 }
+int lb200_animation_compute_relative(lb200_animation* a) {
+	if (!a) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	if (!a->d_pos || !a->n_instances) { lb200_set_error(ctx, "compute_relative needs absolute poses (update with LB200_PALETTE_POSE)"); return LB200_ERR_STATE; }
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t nb = (size_t)a->max_instances * a->bone_count;
+	if (!a->d_rel_pos) { ANIM_MALLOC(a->d_rel_pos, sizeof(float) * 3 * nb); ANIM_MALLOC(a->d_rel_rot, sizeof(float) * 4 * nb); }
+	const size_t n = (size_t)a->n_instances * a->bone_count;
+	pose_relative_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a->d_pos, a->d_rot, a->d_parents, a->bone_count, a->first_nonroot, n, a->d_rel_pos, a->d_rel_rot);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
+int lb200_animation_get_relative_pose(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3, float* out_rot4) {
+	int rc = readBack(a, a ? a->d_rel_pos : nullptr, sizeof(float) * 3 * (a ? a->bone_count : 0), first, count, out_pos3);
+	if (rc) return rc;
+	return readBack(a, a->d_rel_rot, sizeof(float) * 4 * a->bone_count, first, count, out_rot4);
+}
+
+int lb200_animation_blend_pose(lb200_animation* a, const lb200_animation* b, float weight, int relative) {
+	if (!a || !b) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	if (b->ctx != ctx || a->bone_count != b->bone_count || a->n_instances != b->n_instances) { lb200_set_error(ctx, "blend_pose: the two systems differ in context, bone count or instance count"); return LB200_ERR_INVALID; }
+	float* pa = relative ? a->d_rel_pos : a->d_pos; float* ra = relative ? a->d_rel_rot : a->d_rot;
+	const float* pb = relative ? b->d_rel_pos : b->d_pos; const float* rb = relative ? b->d_rel_rot : b->d_rot;
+	if (!pa || !pb || !a->n_instances) { lb200_set_error(ctx, "blend_pose: a pose buffer was never produced"); return LB200_ERR_STATE; }
+	if (weight <= 0.001f) return LB200_OK;                           // pose.cpp:33
+	weight = weight < 0.0f ? 0.0f : (weight > 1.0f ? 1.0f : weight); // pose.cpp:34
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t n = (size_t)a->n_instances * a->bone_count;
+	pose_blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pa, ra, pb, rb, n, weight);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
 int lb200_animation_get_times(lb200_animation* a, uint32_t first, uint32_t count, uint32_t* out_ticks) {
 	return readBack(a, a ? a->d_time : nullptr, sizeof(uint32_t), first, count, out_ticks);
 }

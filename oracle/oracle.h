@@ -100,6 +100,10 @@ void oracle_pose_evaluate(const OracleSkeleton* sk, const OracleClip* clip, uint
 /* Animation::getRelativePose with weight < 0.9999 blending onto an existing relative pose */
 void oracle_pose_sample_weighted(const OracleClip* clip, uint32_t bone_count, uint32_t time_ticks, float weight, OVec3* pos, OQuat* rot);
 void oracle_pose_compute_absolute(const OracleSkeleton* sk, OVec3* pos, OQuat* rot);
+/* pose.cpp:136-146 Pose::computeRelative: absolute -> parent-relative, in place (bones visited from the last one down) */
+void oracle_pose_compute_relative(const OracleSkeleton* sk, OVec3* pos, OQuat* rot);
+/* pose.cpp:30-41 Pose::blend: a = a * (1 - w) + b * w positions, scalar nlerp rotations; w <= 0.001 leaves a untouched, w clamped to [0,1] */
+void oracle_pose_blend(uint32_t bone_count, OVec3* pos_a, OQuat* rot_a, const OVec3* pos_b, const OQuat* rot_b, float weight);
 /* pipeline.cpp:2680-2745 */
 void oracle_palette_dual_quats(const OracleSkeleton* sk, const OVec3* pos, const OQuat* rot, ODualQuat* out);
 /* model.cpp:132-137 */

@@ -128,6 +128,27 @@ void oracle_pose_compute_absolute(const OracleSkeleton* sk, OVec3* pos, OQuat* r
 	}
 }
 
+/* pose.cpp:136-146: i runs from the last bone down, so the parent (index < i) is still absolute when bone i is converted */
+void oracle_pose_compute_relative(const OracleSkeleton* sk, OVec3* pos, OQuat* rot) {
+	for (int32_t i = (int32_t)sk->bone_count - 1; i >= sk->first_nonroot_bone_index; --i) {
+		const int32_t parent = sk->parents[i];
+		const OQuat c = oquat_conjugated(rot[parent]);
+		pos[i] = oquat_rotate(c, ov3_sub(pos[i], pos[parent]));
+		rot[i] = oquat_mul(c, rot[i]);
+	}
+}
+
+/* pose.cpp:30-41 */
+void oracle_pose_blend(uint32_t bone_count, OVec3* pos_a, OQuat* rot_a, const OVec3* pos_b, const OQuat* rot_b, float weight) {
+	if (weight <= 0.001f) return;
+	weight = weight < 0.0f ? 0.0f : (weight > 1.0f ? 1.0f : weight); /* clamp, math.h */
+	const float inv = 1.0f - weight;
+	for (uint32_t i = 0; i < bone_count; ++i) {
+		pos_a[i] = ov3_add(ov3_muls(pos_a[i], inv), ov3_muls(pos_b[i], weight)); /* Vec3 * float + Vec3 * float */
+		rot_a[i] = oquat_nlerp(rot_a[i], rot_b[i], weight);                      /* scalar nlerp, math.cpp:677-692 */
+	}
+}
+
 /* animation_module.cpp:439-456 */
 void oracle_pose_evaluate(const OracleSkeleton* sk, const OracleClip* clip, uint32_t time_ticks, OVec3* pos, OQuat* rot) {
 	for (uint32_t i = 0; i < sk->bone_count; ++i) { /* model.cpp:226-237 */

@@ -433,6 +433,30 @@ def pose_evaluate(skeleton, clip, time_ticks, weight=1.0, start_from_bind=True, 
     return p, r
 
 
+def pose_compute_relative(skeleton, pos, rot, use_ref=False):
+    """Pose::computeRelative (pose.cpp:136-146) on one absolute pose -> (pos, rot) relative to the parents."""
+    p = np.array(pos, np.float32, copy=True)
+    r = np.array(rot, np.float32, copy=True)
+    if use_ref:
+        sk = _skeleton_struct(skeleton, RefSkeleton)
+        ref().ref_pose_compute_relative(C.byref(sk), _ptr(p), _ptr(r))
+    else:
+        sk = _skeleton_struct(skeleton, Skeleton)
+        lib().oracle_pose_compute_relative(C.byref(sk), _ptr(p), _ptr(r))
+    return p, r
+
+
+def pose_blend(pos_a, rot_a, pos_b, rot_b, weight, use_ref=False):
+    """Pose::blend (pose.cpp:30-41): a blended towards b by weight -> (pos, rot)."""
+    p = np.array(pos_a, np.float32, copy=True)
+    r = np.array(rot_a, np.float32, copy=True)
+    pb = np.ascontiguousarray(pos_b, np.float32)
+    rb = np.ascontiguousarray(rot_b, np.float32)
+    f = ref().ref_pose_blend if use_ref else lib().oracle_pose_blend
+    f(C.c_uint32(len(p)), _ptr(p), _ptr(r), _ptr(pb), _ptr(rb), C.c_float(weight))
+    return p, r
+
+
 def palettes(skeleton, pos, rot):
     sk = _skeleton_struct(skeleton, Skeleton)
     p = np.ascontiguousarray(pos, np.float32)

@@ -144,6 +144,48 @@ REF_API void ref_pose_evaluate(const RefSkeleton* sk, const RefClip* clip, uint3
 	model->m_parents.~Array();
 }
 
+static void fillPose(Pose& pose, uint32_t n, const float* pos3, const float* rot4) {
+	pose.resize((int)n);
+	for (uint32_t i = 0; i < n; ++i) {
+		pose.positions[i] = Vec3(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2]);
+		pose.rotations[i] = Quat(rot4[4 * i], rot4[4 * i + 1], rot4[4 * i + 2], rot4[4 * i + 3]);
+	}
+}
+static void readPose(const Pose& pose, uint32_t n, float* pos3, float* rot4) {
+	for (uint32_t i = 0; i < n; ++i) {
+		pos3[3 * i] = pose.positions[i].x; pos3[3 * i + 1] = pose.positions[i].y; pos3[3 * i + 2] = pose.positions[i].z;
+		rot4[4 * i] = pose.rotations[i].x; rot4[4 * i + 1] = pose.rotations[i].y; rot4[4 * i + 2] = pose.rotations[i].z; rot4[4 * i + 3] = pose.rotations[i].w;
+	}
+}
+
+// Pose::blend (pose.cpp:30-41): a = a.blend(b, weight), in place in pos_a / rot_a
+REF_API void ref_pose_blend(uint32_t bone_count, float* pos_a, float* rot_a, const float* pos_b, const float* rot_b, float weight) {
+	static DefaultAllocator allocator;
+	Pose a(allocator), b(allocator);
+	fillPose(a, bone_count, pos_a, rot_a);
+	fillPose(b, bone_count, pos_b, rot_b);
+	a.blend(b, weight);
+	readPose(a, bone_count, pos_a, rot_a);
+}
+
+// Pose::computeRelative (pose.cpp:136-146) on an absolute pose, in place
+REF_API void ref_pose_compute_relative(const RefSkeleton* sk, float* pos3, float* rot4) {
+	static DefaultAllocator allocator;
+	RawStorage<Model> model_mem;
+	Model* model = model_mem.get();
+	new (&model->m_parents) Array<i16>(allocator);
+	for (uint32_t i = 0; i < sk->bone_count; ++i) model->m_parents.push(sk->parents[i]);
+	model->m_first_nonroot_bone_index = sk->first_nonroot;
+	{
+		Pose pose(allocator);
+		fillPose(pose, sk->bone_count, pos3, rot4);
+		pose.is_absolute = true;
+		pose.computeRelative(*model);
+		readPose(pose, sk->bone_count, pos3, rot4);
+	}
+	model->m_parents.~Array();
+}
+
 REF_API uint32_t ref_clip_length_ticks(float fps, uint32_t frame_count) {
 	// Animation::getLength, animation.h:128
 	return Time::fromSeconds(frame_count / fps).raw();

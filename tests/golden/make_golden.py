@@ -154,6 +154,20 @@ def pose_kat():
         d[f"c{k}_times"] = times
         d[f"c{k}_rel"], d[f"c{k}_abs"], d[f"c{k}_blend"] = np.array(rel), np.array(abs_), np.array(blend)
         d[f"c{k}_length"] = np.array([po.ref().ref_clip_length_ticks(C.c_float(clip.fps), C.c_uint32(clip.frame_count))], np.uint32)
+    # Pose::computeRelative and Pose::blend on the poses above (reference's own pose.cpp)
+    abs0 = d["c0_abs"]
+    sk = scenes.skeleton(cfgs[0][0], seed=40)  # the skeleton of config 0
+    rel_back, blends = [], []
+    for i in range(len(abs0)):
+        p, r = po.pose_compute_relative(sk, abs0[i][:, :3], abs0[i][:, 3:], use_ref=True)
+        rel_back.append(np.concatenate([p, r], axis=1))
+    d["c0_abs_to_rel"] = np.array(rel_back)
+    rel0 = d["c0_rel"]
+    d["blend_weights"] = np.array([0.0005, 0.001, 0.0011, 0.25, 0.5, 0.9999, 1.0, 1.7, -0.3], np.float32)
+    for w in d["blend_weights"]:
+        p, r = po.pose_blend(rel0[0][:, :3], rel0[0][:, 3:], rel0[-1][:, :3], -rel0[-1][:, 3:] if w == 0.5 else rel0[-1][:, 3:], float(w), use_ref=True)
+        blends.append(np.concatenate([p, r], axis=1))
+    d["pose_blend"] = np.array(blends)
     d["time_from_seconds_in"] = np.array([0.0, 1 / 60, 1 / 30, 0.5, 3.7, 100.25], np.float32)
     d["time_from_seconds_out"] = np.array([po.ref().ref_time_from_seconds(C.c_float(float(x))) for x in d["time_from_seconds_in"]], np.uint32)
     np.savez_compressed(os.path.join(OUT, "pose_kat.npz"), **d)

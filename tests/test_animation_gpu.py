@@ -122,3 +122,35 @@ def test_c4_size_properties(ctx):
     dq = anim.getDualQuats(0, 100)
     assert np.allclose(np.linalg.norm(dq[..., :4], axis=-1), 1.0, atol=1e-4)
     assert np.all(np.abs((dq[..., :4] * dq[..., 4:]).sum(axis=-1)) < 1e-3)
+
+
+def test_compute_relative_and_blend_match_oracle(ctx, oracle):
+    """Pose::computeRelative (pose.cpp:136-146) and Pose::blend (pose.cpp:30-41) batched over instances, against the oracle."""
+    n_inst = 700
+    sk, clips, _, a, ci, tt = _setup(ctx, 48, 3, n_inst, seed=21)
+    b = lb.AnimationSystem(ctx, sk, clips, None, max_instances=n_inst)
+    ci_b, tt_b = scenes.instance_times(n_inst, clips, seed=99)
+    b.setInstances(ci_b, tt_b)
+    for s in (a, b):
+        s.update(0.0, lb.PALETTE_POSE)
+        s.computeRelative()
+    abs_a, abs_b = a.getPose(), b.getPose()
+    rel_a, rel_b = a.getRelativePose(), b.getRelativePose()
+    exact = []
+    for i in (0, 1, 17, n_inst - 1):
+        ep, er = oracle.pose_compute_relative(sk, abs_a[0][i], abs_a[1][i])
+        exact += [_close(rel_a[0][i], ep, "relative pos"), _close(rel_a[1][i], er, "relative rot")]
+    # blend in both spaces, several weights (0.0005 must leave the pose untouched; 1.7 clamps to 1)
+    for w, relative in ((0.0005, False), (0.3, False), (0.5, True), (1.7, True)):
+        a.blendPose(b, w, relative=relative)
+        cur = a.getRelativePose() if relative else a.getPose()
+        src_a, src_b = (rel_a, rel_b) if relative else (abs_a, abs_b)
+        for i in (0, 5, n_inst - 1):
+            ep, er = oracle.pose_blend(src_a[0][i], src_a[1][i], src_b[0][i], src_b[1][i], w)
+            exact += [_close(cur[0][i], ep, f"blend pos w={w}"), _close(cur[1][i], er, f"blend rot w={w}")]
+        if relative:
+            rel_a = cur
+        else:
+            abs_a = cur
+    print("bit-exact:", exact)
+    a.close(); b.close()

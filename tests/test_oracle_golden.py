@@ -149,3 +149,20 @@ def test_compute_local(oracle):
     assert np.allclose(back["pos"], child["pos"], rtol=0, atol=2e-3 * (1 + np.abs(child["pos"]).max() * 1e-6))
     assert np.allclose(back["scale"], child["scale"], rtol=1e-5)
     assert np.allclose(np.abs((back["rot"] * child["rot"]).sum(1)), 1.0, atol=1e-5)
+
+
+def test_pose_compute_relative_and_blend(oracle):
+    """Pose::computeRelative (pose.cpp:136-146) and Pose::blend (pose.cpp:30-41) against outputs of the reference's own pose.cpp."""
+    from lumixengine_b200 import scenes
+    k = np.load(os.path.join(G, "pose_kat.npz"))
+    sk = scenes.skeleton(24, seed=40)
+    for i in range(len(k["c0_abs"])):
+        p, r = oracle.pose_compute_relative(sk, k["c0_abs"][i][:, :3], k["c0_abs"][i][:, 3:])
+        assert np.array_equal(np.concatenate([p, r], 1).view(np.uint32), k["c0_abs_to_rel"][i].view(np.uint32))
+    rel = k["c0_rel"]
+    for j, w in enumerate(k["blend_weights"]):
+        rb = -rel[-1][:, 3:] if w == 0.5 else rel[-1][:, 3:]  # the negative-dot branch of nlerp
+        p, r = oracle.pose_blend(rel[0][:, :3], rel[0][:, 3:], rel[-1][:, :3], rb, float(w))
+        assert np.array_equal(np.concatenate([p, r], 1).view(np.uint32), k["pose_blend"][j].view(np.uint32)), float(w)
+    # weights at or below 0.001 leave the pose untouched (pose.cpp:33)
+    assert np.array_equal(k["pose_blend"][0], rel[0]) and np.array_equal(k["pose_blend"][1], rel[0])
