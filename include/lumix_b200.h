@@ -317,6 +317,13 @@ LB200_API int lb200_animation_skin(lb200_animation* a);
 LB200_API int lb200_animation_get_dual_quats(lb200_animation* a, uint32_t first, uint32_t count, float* out8);
 LB200_API int lb200_animation_get_matrices(lb200_animation* a, uint32_t first, uint32_t count, float* out16);
 LB200_API int lb200_animation_get_pose(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3, float* out_rot4);
+/* Blend layers: the animator's stack of weighted samples (src/animation/controller.cpp:267-292, nodes.cpp) in a flat per-instance
+ * form.  After the base clip of set_instances (sampled with weight 1 onto the bind pose) every instance applies n_layers further
+ * samples in order, entry [instance * n_layers + k] = (clip, time in ticks, weight): Animation::getRelativePose with ctx.weight
+ * (animation.cpp:117-204, 294-311) — bones the layer's clip tracks move towards its sample by lerp / simd_nlerp when weight < 0.9999,
+ * are replaced otherwise; other bones keep their pose.  Layer times are the caller's (not advanced by update).  n_layers = 0 removes
+ * the layers; lb200_animation_set_instances also does.  Up to 16 layers. */
+LB200_API int lb200_animation_set_layers(lb200_animation* a, uint32_t n_layers, const uint32_t* clip_index, const uint32_t* time_ticks, const float* weight);
 /* Pose::computeRelative (src/renderer/pose.cpp:136-146) of every instance's absolute pose (needs an update with LB200_PALETTE_POSE):
  * the parent-relative poses IK / ragdoll consumers start from (controller.cpp).  Kept in HBM next to the absolute ones. */
 LB200_API int lb200_animation_compute_relative(lb200_animation* a);

@@ -276,6 +276,18 @@ class AnimationSystem:
         check(self.L.lb200_animation_get_pose(self.h, C.c_uint32(first), C.c_uint32(count), ptr(pos), ptr(rot)), self.ctx.h)
         return pos, rot
 
+    def setLayers(self, clip_index, time_ticks, weight):
+        """Blend layers per instance, arrays [n_instances, n_layers] (None / empty removes them): weighted samples applied in order
+        on top of the base clip, Animation::getRelativePose with ctx.weight (animation.cpp:117-204)."""
+        if clip_index is None or np.size(clip_index) == 0:
+            check(self.L.lb200_animation_set_layers(self.h, C.c_uint32(0), None, None, None), self.ctx.h)
+            return
+        ci = np.ascontiguousarray(clip_index, np.uint32).reshape(self.n, -1)
+        tt = np.ascontiguousarray(time_ticks, np.uint32).reshape(self.n, -1)
+        w = np.ascontiguousarray(weight, np.float32).reshape(self.n, -1)
+        assert ci.shape == tt.shape == w.shape
+        check(self.L.lb200_animation_set_layers(self.h, C.c_uint32(ci.shape[1]), ptr(ci), ptr(tt), ptr(w)), self.ctx.h)
+
     def computeRelative(self):
         """Pose::computeRelative (pose.cpp:136-146) of every instance's absolute pose (update with PALETTE_POSE first)."""
         check(self.L.lb200_animation_compute_relative(self.h), self.ctx.h)

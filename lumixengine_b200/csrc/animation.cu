@@ -64,7 +64,7 @@ struct AnimParams {
 	const uint32_t* const_r_bone;
 	const uint32_t* stream; // all bit streams, word-addressed
 	const float4* key_pos; const float4* key_rot; // decoded keyframes (decode_clips_kernel)
-	const unsigned char* key_flags;               // per (clip, bone): bit0 translation animated, bit1 rotation animated
+	const unsigned char* key_flags;               // per (clip, bone): bit0 / bit1 translation / rotation animated, bit2 / bit3 constant track
 	const float4* bind_pos; const float4* bind_rot;         // Bone::relative_transform
 	const float4* inv_bind_pos; const float4* inv_bind_rot; // inverse bind transforms
 	const short* parents;
@@ -82,6 +82,11 @@ struct AnimParams {
 	uint32_t dt_ticks;   // |time_delta| in ticks
 	int dt_negative;
 	int advance;
+	// blend layers on top of the base clip (lb200_animation_set_layers): [instance][n_layers]
+	uint32_t n_layers;
+	const uint32_t* layer_clip;
+	const uint32_t* layer_time;
+	const float* layer_weight;
 };
 
 // unaligned little-endian u64 at byte address `byte` of a word-addressed stream (the reference memcpy's 8 bytes, animation.cpp:44)
@@ -193,9 +198,15 @@ __global__ void __launch_bounds__(256) decode_clips_kernel(const __grid_constant
 	__syncthreads();
 	for (uint32_t i = threadIdx.x; i < clip.n_ct; i += blockDim.x) {
 		const float4 ct = P.const_t[clip.ct_off + i];
-		kp[__float_as_uint(ct.w)] = make_float4(ct.x, ct.y, ct.z, 0.f);
+		const uint32_t bone = __float_as_uint(ct.w);
+		kp[bone] = make_float4(ct.x, ct.y, ct.z, 0.f);
+		if (frame == 0) atomicOr(reinterpret_cast<unsigned int*>(kf + (bone & ~3u)), 4u << (8u * (bone & 3u)));
 	}
-	for (uint32_t i = threadIdx.x; i < clip.n_cr; i += blockDim.x) kr[P.const_r_bone[clip.cr_off + i]] = P.const_r_value[clip.cr_off + i];
+	for (uint32_t i = threadIdx.x; i < clip.n_cr; i += blockDim.x) {
+		const uint32_t bone = P.const_r_bone[clip.cr_off + i];
+		kr[bone] = P.const_r_value[clip.cr_off + i];
+		if (frame == 0) atomicOr(reinterpret_cast<unsigned int*>(kf + (bone & ~3u)), 8u << (8u * (bone & 3u)));
+	}
 	__syncthreads();
 	const uint32_t* t_stream = P.stream + (clip.t_stream >> 2);
 	for (uint32_t i = threadIdx.x; i < clip.n_t; i += blockDim.x) {
@@ -289,6 +300,56 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 			}
 			s_pos[b] = p;
 			s_rot[b] = r;
+		}
+		__syncwarp(gmask);
+
+		// Blend layers (the animator's stack of weighted samples, controller.cpp:267-292 -> Animation::getRelativePose with
+		// ctx.weight): every bone the layer's clip has a track for — constant or animated — moves towards the layer's sample,
+		// lerp (math.cpp:194-201) for positions and simd_nlerp for rotations when weight < 0.9999 (animation.cpp:294-311), plain
+		// replacement otherwise; bones without a track are left alone (animation.cpp:136-203).  Bones are independent: no sync inside.
+		for (uint32_t layer = 0; layer < P.n_layers; ++layer) {
+			const size_t li = (size_t)inst * P.n_layers + layer;
+			const DevClip lclip = P.clips[P.layer_clip[li]];
+			const float w = P.layer_weight[li];
+			const bool use_weight = w < 0.9999f;
+			const float lframe = __double2float_rn(LB_DMUL(__uint2double_rn(P.layer_time[li]) / 32768.0, (double)lclip.fps));
+			const float lhi = LB_FSUB(__uint2float_rn(lclip.frame_count), 0.00001f);
+			float ls = lframe > 0.f ? lframe : 0.f;
+			ls = ls < lhi ? ls : lhi;
+			const uint32_t lidx = (uint32_t)ls;
+			const float lt = LB_FSUB(ls, __uint2float_rn(lidx));
+			const float4* l0p = P.key_pos + lclip.key_off + (size_t)lidx * Bp;
+			const float4* l0r = P.key_rot + lclip.key_off + (size_t)lidx * Bp;
+			const unsigned char* lf = P.key_flags + lclip.flag_off;
+			for (uint32_t b = sub; b < B; b += G) {
+				const uint32_t fl = lf[b];
+				if (fl & 5u) {
+					const float4 p0 = __ldg(l0p + b);
+					V3 v = v3(p0.x, p0.y, p0.z);
+					if (fl & 1u) {
+						const float4 p1 = __ldg(l0p + Bp + b);
+						v = lerp(v, v3(p1.x, p1.y, p1.z), lt);
+					}
+					if (use_weight) {
+						const float4 cur = s_pos[b];
+						v = lerp(v3(cur.x, cur.y, cur.z), v, w);
+					}
+					s_pos[b] = make_float4(v.x, v.y, v.z, 0.f);
+				}
+				if (fl & 10u) {
+					const float4 r0 = __ldg(l0r + b);
+					Q4 q = q4(r0.x, r0.y, r0.z, r0.w);
+					if (fl & 2u) {
+						const float4 r1 = __ldg(l0r + Bp + b);
+						q = simd_nlerp(q, q4(r1.x, r1.y, r1.z, r1.w), lt);
+					}
+					if (use_weight) {
+						const float4 cur = s_rot[b];
+						q = simd_nlerp(q4(cur.x, cur.y, cur.z, cur.w), q, w);
+					}
+					s_rot[b] = make_float4(q.x, q.y, q.z, q.w);
+				}
+			}
 		}
 		__syncwarp(gmask);
 
@@ -470,6 +531,7 @@ struct lb200_animation {
 	short* d_parents = nullptr; unsigned char* d_level_bones = nullptr; uint32_t* d_level_start = nullptr;
 	int lanes_per_instance = 8;
 	uint32_t* d_clip_index = nullptr; uint32_t* d_time = nullptr;
+	uint32_t n_layers = 0; uint32_t* d_layer_clip = nullptr; uint32_t* d_layer_time = nullptr; float* d_layer_weight = nullptr;
 	float* d_dq = nullptr; float* d_mtx = nullptr; float* d_pos = nullptr; float* d_rot = nullptr;
 	float* d_rel_pos = nullptr; float* d_rel_rot = nullptr; // Pose::computeRelative of d_pos / d_rot
 	uint32_t first_nonroot = 0;
@@ -663,7 +725,7 @@ void lb200_animation_destroy(lb200_animation* a) {
 	cudaStreamSynchronize(a->ctx->stream);
 	cudaFree(a->d_clips); cudaFree(a->d_tracks); cudaFree(a->d_const_t); cudaFree(a->d_const_r_value); cudaFree(a->d_const_r_bone); cudaFree(a->d_stream);
 	cudaFree(a->d_bind); cudaFree(a->d_key_pos); cudaFree(a->d_key_rot); cudaFree(a->d_key_flags); cudaFree(a->d_parents); cudaFree(a->d_level_bones); cudaFree(a->d_level_start);
-	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot); cudaFree(a->d_rel_pos); cudaFree(a->d_rel_rot);
+	cudaFree(a->d_clip_index); cudaFree(a->d_time); cudaFree(a->d_layer_clip); cudaFree(a->d_layer_time); cudaFree(a->d_layer_weight); cudaFree(a->d_dq); cudaFree(a->d_mtx); cudaFree(a->d_pos); cudaFree(a->d_rot); cudaFree(a->d_rel_pos); cudaFree(a->d_rel_rot);
 	cudaFree(a->d_mesh_pos); cudaFree(a->d_mesh_w); cudaFree(a->d_mesh_idx); cudaFree(a->d_skinned); cudaFree(a->d_checksum);
 	delete a;
 }
@@ -677,6 +739,7 @@ int lb200_animation_set_instances(lb200_animation* a, const uint32_t* clip_index
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_time, time_ticks, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	a->n_instances = n;
+	a->n_layers = 0; // layer tables are per instance: set them again after changing the instances
 	return LB200_OK;
 }
 
@@ -695,6 +758,7 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	P.bind_pos = a->d_bind; P.bind_rot = a->d_bind + a->bone_count; P.inv_bind_pos = a->d_bind + 2 * a->bone_count; P.inv_bind_rot = a->d_bind + 3 * a->bone_count; P.parents = a->d_parents; P.level_bones = a->d_level_bones; P.level_start = a->d_level_start;
 	P.bone_count = a->bone_count; P.max_level = a->max_level; P.n_instances = a->n_instances;
 	P.clip_index = a->d_clip_index; P.time_ticks = a->d_time;
+	P.n_layers = a->n_layers; P.layer_clip = a->d_layer_clip; P.layer_time = a->d_layer_time; P.layer_weight = a->d_layer_weight;
 	P.out_dq = (flags & LB200_PALETTE_DUAL_QUAT) ? a->d_dq : nullptr;
 	P.out_mtx = (flags & LB200_PALETTE_MATRIX) ? a->d_mtx : nullptr;
 	P.out_pos = (flags & LB200_PALETTE_POSE) ? a->d_pos : nullptr;
@@ -757,6 +821,26 @@ int lb200_animation_get_pose(lb200_animation* a, uint32_t first, uint32_t count,
 	if (rc) return rc;
 	return readBack(a, a->d_rot, sizeof(float) * 4 * a->bone_count, first, count, out_rot4);
 }
+int lb200_animation_set_layers(lb200_animation* a, uint32_t n_layers, const uint32_t* clip_index, const uint32_t* time_ticks, const float* weight) {
+	if (!a || n_layers > 16) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (n_layers == 0) { a->n_layers = 0; return LB200_OK; }
+	if (!clip_index || !time_ticks || !weight || !a->n_instances) return LB200_ERR_INVALID;
+	const size_t n = (size_t)a->n_instances * n_layers;
+	for (size_t i = 0; i < n; ++i) if (clip_index[i] >= a->n_clips) { lb200_set_error(ctx, "layer entry %zu: clip %u out of range", i, clip_index[i]); return LB200_ERR_INVALID; }
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(a->d_layer_clip); cudaFree(a->d_layer_time); cudaFree(a->d_layer_weight);
+	a->d_layer_clip = nullptr; a->d_layer_time = nullptr; a->d_layer_weight = nullptr; a->n_layers = 0;
+	ANIM_MALLOC(a->d_layer_clip, sizeof(uint32_t) * n); ANIM_MALLOC(a->d_layer_time, sizeof(uint32_t) * n); ANIM_MALLOC(a->d_layer_weight, sizeof(float) * n);
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_layer_clip, clip_index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_layer_time, time_ticks, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_layer_weight, weight, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	a->n_layers = n_layers;
+	return LB200_OK;
+}
+
 int lb200_animation_compute_relative(lb200_animation* a) {
 	if (!a) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = a->ctx;

@@ -433,6 +433,15 @@ def pose_evaluate(skeleton, clip, time_ticks, weight=1.0, start_from_bind=True, 
     return p, r
 
 
+def pose_compute_absolute(skeleton, pos, rot):
+    """Pose::computeAbsolute (pose.cpp:66-133) on one relative pose -> (pos, rot)."""
+    sk = _skeleton_struct(skeleton, Skeleton)
+    p = np.array(pos, np.float32, copy=True)
+    r = np.array(rot, np.float32, copy=True)
+    lib().oracle_pose_compute_absolute(C.byref(sk), _ptr(p), _ptr(r))
+    return p, r
+
+
 def pose_compute_relative(skeleton, pos, rot, use_ref=False):
     """Pose::computeRelative (pose.cpp:136-146) on one absolute pose -> (pos, rot) relative to the parents."""
     p = np.array(pos, np.float32, copy=True)

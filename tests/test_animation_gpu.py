@@ -154,3 +154,36 @@ def test_compute_relative_and_blend_match_oracle(ctx, oracle):
             abs_a = cur
     print("bit-exact:", exact)
     a.close(); b.close()
+
+
+def test_blend_layers_match_oracle(ctx, oracle):
+    """Weighted sample stack per instance (Animation::getRelativePose with ctx.weight, animation.cpp:117-204, 294-311): base clip, then
+    layers with weights below and above the 0.9999 switch, clips with constant tracks (which blend) and untracked bones (which do not)."""
+    n_inst, n_layers = 300, 3
+    sk, clips, _, anim, ci, tt = _setup(ctx, 40, 4, n_inst, seed=33, const_fraction=0.3)
+    rng = np.random.default_rng(8)
+    lci = rng.integers(0, len(clips), (n_inst, n_layers)).astype(np.uint32)
+    ltt = np.stack([rng.integers(0, clips[c].length_ticks, n_inst) for c in range(n_layers)], axis=1).astype(np.uint32)
+    lw = rng.random((n_inst, n_layers)).astype(np.float32)
+    lw[::7, 1] = 1.0       # replacement instead of blending
+    lw[::11, 0] = 0.99995  # just above the switch
+    lw[::13, 2] = 0.0
+    anim.setLayers(lci, ltt, lw)
+    anim.update(0.0, lb.PALETTE_DUAL_QUAT | lb.PALETTE_MATRIX | lb.PALETTE_POSE)
+    pos, rot = anim.getPose()
+    dq, mtx = anim.getDualQuats(), anim.getMatrices()
+    exact = []
+    for i in list(range(0, n_inst, 7)) + [1, 2, n_inst - 1]:
+        p, r = oracle.pose_evaluate(sk, clips[ci[i]], tt[i], compute_absolute=False)
+        for k in range(n_layers):
+            p, r = oracle.pose_evaluate(sk, clips[lci[i, k]], ltt[i, k], weight=float(lw[i, k]), start_from_bind=False, compute_absolute=False, pos=p, rot=r)
+        p, r = oracle.pose_compute_absolute(sk, p, r)
+        edq, emtx = oracle.palettes(sk, p, r)
+        exact += [_close(pos[i], p, "layered pose.pos"), _close(rot[i], r, "layered pose.rot"), _close(dq[i], edq, "layered dq"), _close(mtx[i], emtx, "layered mtx")]
+    print("bit-exact:", all(exact))
+    # removing the layers gives the plain single-clip result again
+    anim.setLayers(None, None, None)
+    anim.update(0.0, lb.PALETTE_POSE)
+    exp = oracle.animate_instances(sk, clips, ci, tt)
+    _close(anim.getPose()[0], exp["pos"], "pose.pos after removing layers")
+    anim.close()
