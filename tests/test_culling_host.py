@@ -82,3 +82,41 @@ def test_type_0xff_is_reserved():
         assert e.code == lb._lib.ERR_INVALID
     else:
         raise AssertionError("type 0xff must be rejected (culling_system.cpp:312)")
+
+
+def test_page_churn_in_crowded_cells(oracle):
+    """Two crowded cells (several chained pages each): random removals empty and free pages in the middle of a chain, re-adds
+    prepend fresh pages (culling_system.cpp:103-128, 160-197), radius edits flip entities between the normal and the is_big
+    chain.  After every batch the page list must equal the oracle's, page for page in m_cells order, and freed device page ids
+    must be reused without ever exceeding the high-water mark of the busiest moment."""
+    rng = np.random.default_rng(77)
+    n = 2400
+    ents = np.arange(n, dtype=np.int32)
+    pos = np.stack([rng.uniform(10.0, 590.0, n), rng.uniform(5.0, 295.0, n), rng.uniform(10.0, 290.0, n)], axis=1)  # cells (0,0,0) and (1,0,0)
+    rad = rng.uniform(0.5, 5.0, n).astype(np.float32)
+    types = (rng.random(n) < 0.3).astype(np.uint8)
+    cs, oc = lb.CullingSystem(None), oracle.OracleCulling()
+    cs.add(ents, types, pos, rad); oc.add(ents, types, pos, rad)
+    _same_state(cs, oc)
+    peak_pages = cs.page_count()
+    alive = np.ones(n, bool)
+    for step in range(25):
+        live = np.nonzero(alive)[0]
+        kill = rng.choice(live, min(len(live), int(rng.integers(50, 700))), replace=False).astype(np.int32)
+        cs.remove(kill); oc.remove(kill)
+        alive[kill] = False
+        _same_state(cs, oc)
+        dead = np.nonzero(~alive)[0]
+        back = rng.choice(dead, int(rng.integers(1, len(dead) + 1)), replace=False).astype(np.int32)
+        cs.add(back, types[back], pos[back], rad[back]); oc.add(back, types[back], pos[back], rad[back])
+        alive[back] = True
+        live = np.nonzero(alive)[0]
+        flip = rng.choice(live, min(len(live), 60), replace=False).astype(np.int32)
+        newr = np.where(rng.random(len(flip)) < 0.5, 450.0, 2.0).astype(np.float32)  # > cell size = is_big chain (culling_system.cpp:139)
+        cs.setRadius(flip, newr); oc.set_radius(flip, newr)
+        rad[flip] = newr
+        _same_state(cs, oc)
+        assert cs.entity_count() == int(alive.sum())
+        peak_pages = max(peak_pages, cs.page_count())
+    ids = cs.page_ids()
+    assert len(set(ids.tolist())) == len(ids) and ids.max() < peak_pages + 8  # freed ids come back instead of growing the device arrays
