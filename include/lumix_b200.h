@@ -147,7 +147,9 @@ LB200_API int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum*
 	lb200_cull_result* result);
 
 /* Device-resident form: the same cull, result left in HBM (no D2H of ids).  *out_dev_ids receives the device pointer of the
- * id buffer (valid until the next cull on this object); counts land in `result` (a 2 KB D2H).  With want_counts = 0 nothing is
+ * id buffer: per-type segments, ids of type t at [type_offset[t], type_offset[t] + type_count[t]).  The buffer belongs to one of the
+ * object's output lanes (3 by default, LB200_CULL_LANES): it stays valid through the next lanes - 1 culls, the cull after that reuses
+ * it.  Counts land in `result` (a 2 KB D2H).  With want_counts = 0 nothing is
  * read back and the call is fully asynchronous on the context stream (result may be NULL). */
 LB200_API int lb200_culling_cull_device(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
 	lb200_cull_result* result, int want_counts);
