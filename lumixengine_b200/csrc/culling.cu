@@ -492,7 +492,7 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), out, cur, nxt,
 		xchg ? (uint32_t*)nullptr : mask));
 	LB200_CHECK_LAUNCH(ctx);
-	cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask;
+	cs->last_counters = cur; cs->last_out = out; cs->last_mask = xchg ? nullptr : mask; // exchange culls keep their rows in the slabs
 	cs->lane_parity[lane] ^= 1u;
 	if (!xchg) ++cs->seq;
 	cs->last_pages = h.high_water;
@@ -782,6 +782,7 @@ int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t 
 	const size_t n = h.cells.size();
 	if (capacity_words < n * 8) return LB200_ERR_CAPACITY;
 	if (!cs->last_blocks) { lb200_set_error(cs->ctx, "read_bitmask needs a preceding cull"); return LB200_ERR_STATE; }
+	if (!cs->last_mask) { lb200_set_error(cs->ctx, "the last cull was an exchange step: its visibility rows are in the exchanged slabs"); return LB200_ERR_STATE; }
 	std::vector<uint32_t> tmp((size_t)cs->last_blocks * cs->last_rows_per_block * 8);
 	LB200_CUDA(cs->ctx, cudaMemcpyAsync(tmp.data(), cs->last_mask, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, cs->ctx->stream));
 	LB200_CUDA(cs->ctx, cudaStreamSynchronize(cs->ctx->stream));
