@@ -91,6 +91,19 @@ $CXX $FL -c "$HERE/ref/ref_stubs.cpp" -o "$TMP/obj/ref_stubs.o" &
 $CXX $FL -c "$HERE/ref/ref_harness.cpp" -o "$TMP/obj/ref_harness.o" &
 $CXX $FL -c "$HERE/ref/ref_anim_harness.cpp" -o "$TMP/obj/ref_anim_harness.o" &
 wait
-$CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" "$TMP/obj/ref_anim_harness.o" -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL
+# (5) PipelineImpl::computeSkeletonDualQuats lives in the DX12-bound pipeline.cpp: cut that one member function out of the reference
+#     file into the overlay (never into this repository) and compile it inside oracle/ref/ref_palette_harness.cpp.  Optional: if the
+#     reference moves the function, the library is built without ref_skeleton_dual_quats and the tests that need it skip.
+EXTRA=""
+awk '/void computeSkeletonDualQuats\(const ModelInstance\* mi\) \{/{p=1} /void createCommands\(View& view\)/{p=0} p' \
+	"$REF/src/renderer/pipeline.cpp" > "$S/renderer/extracted_compute_skeleton_dual_quats.inl"
+if [ -s "$S/renderer/extracted_compute_skeleton_dual_quats.inl" ] \
+	&& $CXX $FL -c "$HERE/ref/ref_palette_harness.cpp" -o "$TMP/obj/ref_palette_harness.o" 2> "$TMP/palette.log"; then
+	EXTRA="$TMP/obj/ref_palette_harness.o"
+else
+	echo "build_ref.sh: palette harness not built (see below); continuing without ref_skeleton_dual_quats" >&2
+	tail -5 "$TMP/palette.log" >&2 || true
+fi
+$CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" "$TMP/obj/ref_anim_harness.o" $EXTRA -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL
 ( cd "$REF" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$OUT/REFERENCE_COMMIT"
 echo "built $OUT/libref_lumix.so"

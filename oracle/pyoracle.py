@@ -433,6 +433,21 @@ def pose_evaluate(skeleton, clip, time_ticks, weight=1.0, start_from_bind=True, 
     return p, r
 
 
+def ref_skeleton_dual_quats(skeleton, pos, rot):
+    """The reference's own PipelineImpl::computeSkeletonDualQuats (pipeline.cpp:2680-2745, SIMD batches + scalar tail) on one absolute
+    pose -> float32[bone_count, 8]; None when oracle/_ref was built without the palette harness."""
+    L = ref()
+    if not hasattr(L, "ref_skeleton_dual_quats"):
+        return None
+    sk = _skeleton_struct(skeleton, RefSkeleton)
+    p = np.ascontiguousarray(pos, np.float32)
+    r = np.ascontiguousarray(rot, np.float32)
+    out = np.zeros((skeleton.bone_count, 8), np.float32)
+    rc = L.ref_skeleton_dual_quats(C.byref(sk), _ptr(p), _ptr(r), _ptr(out))
+    assert rc == 0
+    return out
+
+
 def pose_compute_absolute(skeleton, pos, rot):
     """Pose::computeAbsolute (pose.cpp:66-133) on one relative pose -> (pos, rot)."""
     sk = _skeleton_struct(skeleton, Skeleton)

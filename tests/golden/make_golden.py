@@ -153,6 +153,8 @@ def pose_kat():
                                                               compute_absolute=False, pos=p0, rot=r0), axis=1))
         d[f"c{k}_times"] = times
         d[f"c{k}_rel"], d[f"c{k}_abs"], d[f"c{k}_blend"] = np.array(rel), np.array(abs_), np.array(blend)
+        # PipelineImpl::computeSkeletonDualQuats (the reference's own SIMD + scalar-tail code) on the absolute poses
+        d[f"c{k}_dq"] = np.array([po.ref_skeleton_dual_quats(sk, a[:, :3], a[:, 3:]) for a in abs_])
         d[f"c{k}_length"] = np.array([po.ref().ref_clip_length_ticks(C.c_float(clip.fps), C.c_uint32(clip.frame_count))], np.uint32)
     # Pose::computeRelative and Pose::blend on the poses above (reference's own pose.cpp)
     abs0 = d["c0_abs"]

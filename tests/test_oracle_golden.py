@@ -122,6 +122,10 @@ def test_pose_sampling_and_absolute(oracle):
             assert np.array_equal(bits(rel), bits(g[f"c{k}_rel"][j])), (k, t)
             ab = np.concatenate(oracle.pose_evaluate(sk, clip, t, compute_absolute=True), axis=1)
             assert np.array_equal(bits(ab), bits(g[f"c{k}_abs"][j])), (k, t)
+            # dual-quaternion palette of that pose: the reference's own PipelineImpl::computeSkeletonDualQuats (4-wide SIMD batches +
+            # scalar tail, pipeline.cpp:2680-2745), cut out of pipeline.cpp at build time by oracle/build_ref.sh
+            dq, _ = oracle.palettes(sk, ab[:, :3], ab[:, 3:])
+            assert np.array_equal(bits(dq), bits(g[f"c{k}_dq"][j])), (k, t)
             bl = np.concatenate(oracle.pose_evaluate(sk, clip, (int(t) * 7 + 11) % max(L, 1), weight=0.37, start_from_bind=False, compute_absolute=False,
                                                      pos=rel[:, :3], rot=rel[:, 3:]), axis=1)
             assert np.array_equal(bits(bl), bits(g[f"c{k}_blend"][j])), (k, t)
