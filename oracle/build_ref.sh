@@ -97,7 +97,10 @@ wait
 EXTRA=""
 awk '/void computeSkeletonDualQuats\(const ModelInstance\* mi\) \{/{p=1} /void createCommands\(View& view\)/{p=0} p' \
 	"$REF/src/renderer/pipeline.cpp" > "$S/renderer/extracted_compute_skeleton_dual_quats.inl"
-if [ -s "$S/renderer/extracted_compute_skeleton_dual_quats.inl" ] \
+# the two file-static helpers of model.cpp (model.cpp itself needs the whole renderer to link): evaluateSkin :103-109, computeSkinMatrices :132-137
+awk '/^static Vec3 evaluateSkin\(/{p=1} /^Vec3 Model::evalVertexPose\(/{p=0} p' "$REF/src/renderer/model.cpp" > "$S/renderer/extracted_model_statics.inl"
+awk '/^static void computeSkinMatrices\(/{p=1} /^RayCastModelHit Model::castRay\(/{p=0} p' "$REF/src/renderer/model.cpp" >> "$S/renderer/extracted_model_statics.inl"
+if [ -s "$S/renderer/extracted_compute_skeleton_dual_quats.inl" ] && grep -q computeSkinMatrices "$S/renderer/extracted_model_statics.inl" \
 	&& $CXX $FL -c "$HERE/ref/ref_palette_harness.cpp" -o "$TMP/obj/ref_palette_harness.o" 2> "$TMP/palette.log"; then
 	EXTRA="$TMP/obj/ref_palette_harness.o"
 else

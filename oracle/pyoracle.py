@@ -448,6 +448,33 @@ def ref_skeleton_dual_quats(skeleton, pos, rot):
     return out
 
 
+def ref_skin_matrices(skeleton, pos, rot):
+    """The reference's own computeSkinMatrices (model.cpp:132-137) on one absolute pose -> float32[bone_count, 16] or None."""
+    L = ref()
+    if not hasattr(L, "ref_skin_matrices"):
+        return None
+    sk = _skeleton_struct(skeleton, RefSkeleton)
+    p = np.ascontiguousarray(pos, np.float32)
+    r = np.ascontiguousarray(rot, np.float32)
+    out = np.zeros((skeleton.bone_count, 16), np.float32)
+    assert L.ref_skin_matrices(C.byref(sk), _ptr(p), _ptr(r), _ptr(out)) == 0
+    return out
+
+
+def ref_evaluate_skin(matrices, vertices, weights, indices):
+    """The reference's own evaluateSkin (model.cpp:103-109) per vertex -> float32[n, 3] or None."""
+    L = ref()
+    if not hasattr(L, "ref_evaluate_skin"):
+        return None
+    m = np.ascontiguousarray(matrices, np.float32)
+    v = np.ascontiguousarray(vertices, np.float32)
+    w = np.ascontiguousarray(weights, np.float32)
+    i = np.ascontiguousarray(indices, np.int16)
+    out = np.zeros((len(v), 3), np.float32)
+    L.ref_evaluate_skin(_ptr(m), _ptr(v), _ptr(w), _ptr(i), _ptr(out), C.c_uint32(len(v)))
+    return out
+
+
 def pose_compute_absolute(skeleton, pos, rot):
     """Pose::computeAbsolute (pose.cpp:66-133) on one relative pose -> (pos, rot)."""
     sk = _skeleton_struct(skeleton, Skeleton)

@@ -32,6 +32,11 @@ struct ExtractedPipeline {
 #include "renderer/extracted_compute_skeleton_dual_quats.inl"
 };
 
+// file-static helpers of model.cpp, cut out the same way: evaluateSkin (model.cpp:103-109), computeSkinMatrices (model.cpp:132-137)
+namespace extracted_model {
+#include "renderer/extracted_model_statics.inl"
+}
+
 // model.cpp is not part of this library (it pulls in the whole renderer); the extracted function calls this accessor for the
 // scalar tail.  It only gathers bone `i` out of the SoA inverse bind arrays.
 LocalRigidTransform Model::getInverseBindTransform(i32 i) const {
@@ -92,4 +97,45 @@ REF_API int ref_skeleton_dual_quats(const RefSkeletonP* sk, const float* pos3, c
 	free(soa);
 	free(out);
 	return 0;
+}
+
+// computeSkinMatrices (model.cpp:132-137) on one absolute pose: out16 = bone_count column-major matrices
+REF_API int ref_skin_matrices(const RefSkeletonP* sk, const float* pos3, const float* rot4, float* out16) {
+	static DefaultAllocator allocator;
+	const uint32_t n = sk->bone_count;
+	float* soa = (float*)malloc(sizeof(float) * 7 * (n ? n : 1));
+	if (!soa) return -1;
+	RawStorageP<Model> model_mem;
+	Model* model = model_mem.get();
+	float** lanes[7] = {&model->m_inverse_bind.px, &model->m_inverse_bind.py, &model->m_inverse_bind.pz,
+		&model->m_inverse_bind.rx, &model->m_inverse_bind.ry, &model->m_inverse_bind.rz, &model->m_inverse_bind.rw};
+	for (int k = 0; k < 7; ++k) {
+		*lanes[k] = soa + (size_t)k * n;
+		for (uint32_t i = 0; i < n; ++i) (*lanes[k])[i] = sk->inverse_bind7[7 * i + k];
+	}
+	{
+		Pose pose(allocator);
+		pose.resize((int)n);
+		for (uint32_t i = 0; i < n; ++i) {
+			pose.positions[i] = Vec3(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2]);
+			pose.rotations[i] = Quat(rot4[4 * i], rot4[4 * i + 1], rot4[4 * i + 2], rot4[4 * i + 3]);
+		}
+		static_assert(sizeof(Matrix) == 64, "");
+		extracted_model::computeSkinMatrices(pose, *model, (Matrix*)out16);
+	}
+	free(soa);
+	return 0;
+}
+
+// evaluateSkin (model.cpp:103-109) for n vertices against one matrix palette
+REF_API void ref_evaluate_skin(const float* matrices16, const float* pos3, const float* weights4, const int16_t* indices4, float* out3, uint32_t n) {
+	const Matrix* m = (const Matrix*)matrices16;
+	for (uint32_t i = 0; i < n; ++i) {
+		Mesh::Skin s;
+		s.weights = Vec4(weights4[4 * i], weights4[4 * i + 1], weights4[4 * i + 2], weights4[4 * i + 3]);
+		for (int k = 0; k < 4; ++k) s.indices[k] = indices4[4 * i + k];
+		Vec3 p(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2]);
+		const Vec3 r = extracted_model::evaluateSkin(p, s, m);
+		out3[3 * i] = r.x; out3[3 * i + 1] = r.y; out3[3 * i + 2] = r.z;
+	}
 }

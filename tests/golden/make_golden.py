@@ -155,6 +155,10 @@ def pose_kat():
         d[f"c{k}_rel"], d[f"c{k}_abs"], d[f"c{k}_blend"] = np.array(rel), np.array(abs_), np.array(blend)
         # PipelineImpl::computeSkeletonDualQuats (the reference's own SIMD + scalar-tail code) on the absolute poses
         d[f"c{k}_dq"] = np.array([po.ref_skeleton_dual_quats(sk, a[:, :3], a[:, 3:]) for a in abs_])
+        # the reference's own computeSkinMatrices / evaluateSkin (file statics of model.cpp, cut out at build time) on the same poses
+        d[f"c{k}_mtx"] = np.array([po.ref_skin_matrices(sk, a[:, :3], a[:, 3:]) for a in abs_[:12]])
+        mesh = scenes.mesh(sk, 300, seed=60 + k)
+        d[f"c{k}_skinned"] = np.array([po.ref_evaluate_skin(m, mesh.positions, mesh.weights, mesh.indices) for m in d[f"c{k}_mtx"][:4]])
         d[f"c{k}_length"] = np.array([po.ref().ref_clip_length_ticks(C.c_float(clip.fps), C.c_uint32(clip.frame_count))], np.uint32)
     # Pose::computeRelative and Pose::blend on the poses above (reference's own pose.cpp)
     abs0 = d["c0_abs"]

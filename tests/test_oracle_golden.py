@@ -124,8 +124,14 @@ def test_pose_sampling_and_absolute(oracle):
             assert np.array_equal(bits(ab), bits(g[f"c{k}_abs"][j])), (k, t)
             # dual-quaternion palette of that pose: the reference's own PipelineImpl::computeSkeletonDualQuats (4-wide SIMD batches +
             # scalar tail, pipeline.cpp:2680-2745), cut out of pipeline.cpp at build time by oracle/build_ref.sh
-            dq, _ = oracle.palettes(sk, ab[:, :3], ab[:, 3:])
+            dq, mtx = oracle.palettes(sk, ab[:, :3], ab[:, 3:])
             assert np.array_equal(bits(dq), bits(g[f"c{k}_dq"][j])), (k, t)
+            if j < len(g[f"c{k}_mtx"]):  # computeSkinMatrices (model.cpp:132-137), and evaluateSkin (model.cpp:103-109) on a 300-vertex mesh
+                assert np.array_equal(bits(mtx), bits(g[f"c{k}_mtx"][j])), (k, t)
+                if j < len(g[f"c{k}_skinned"]):
+                    mesh = scenes.mesh(sk, 300, seed=60 + k)
+                    v = oracle.skin_vertices(mtx, mesh.positions, mesh.weights, mesh.indices)
+                    assert np.array_equal(bits(v), bits(g[f"c{k}_skinned"][j])), (k, t)
             bl = np.concatenate(oracle.pose_evaluate(sk, clip, (int(t) * 7 + 11) % max(L, 1), weight=0.37, start_from_bind=False, compute_absolute=False,
                                                      pos=rel[:, :3], rot=rel[:, 3:]), axis=1)
             assert np.array_equal(bits(bl), bits(g[f"c{k}_blend"][j])), (k, t)
