@@ -192,10 +192,16 @@ void oracle_skin_vertices(const OMatrix* matrices, const OVec3* vertices, const 
 }
 
 /* animation_module.cpp:458-461; animation.h:21-24,128 */
+/* animation_module.cpp:458-469 with Time's operators (animation.h:17-43): fromSeconds = u32(time * 32768), +, -, % on u32 ticks;
+ * getLength() = Time::fromSeconds(frame_count / fps) (animation.h:128) */
 uint32_t oracle_time_advance(uint32_t time_ticks, float time_delta, float fps, uint32_t frame_count) {
-	const uint32_t dt = (uint32_t)(time_delta * (1 << 15));                /* Time::fromSeconds */
-	const uint32_t l = (uint32_t)(((float)frame_count / fps) * (1 << 15)); /* getLength() */
-	return (time_ticks + dt) % l;
+	const uint32_t l = (uint32_t)(((float)frame_count / fps) * (1 << 15));
+	if (time_delta > 0) {
+		const uint32_t dt = (uint32_t)(time_delta * (1 << 15));
+		return (time_ticks + dt) % l;
+	}
+	const uint32_t dt = (uint32_t)(-time_delta * (1 << 15)) % l;
+	return (time_ticks + l - dt) % l;
 }
 
 void oracle_animate_instances(const OracleSkeleton* sk, const OracleClip* clips, const uint32_t* clip_index, const uint32_t* time_ticks,

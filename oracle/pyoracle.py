@@ -374,8 +374,12 @@ def skin_vertices(matrices, positions, weights, indices):
     return out
 
 
-def time_advance(time_ticks, time_delta, fps, frame_count):
-    return int(lib().oracle_time_advance(C.c_uint32(int(time_ticks)), C.c_float(time_delta), C.c_float(fps), C.c_uint32(frame_count)))
+def time_advance(time_ticks, time_delta, fps, frame_count, use_ref=False):
+    """Animable time after one update (animation_module.cpp:458-469), either sign of time_delta."""
+    L = ref() if use_ref else lib()
+    f = L.ref_time_advance if use_ref else L.oracle_time_advance
+    f.restype = C.c_uint32
+    return int(f(C.c_uint32(int(time_ticks)), C.c_float(time_delta), C.c_float(fps), C.c_uint32(frame_count)))
 
 
 # ---------------------------------------------------------------------------------------------------

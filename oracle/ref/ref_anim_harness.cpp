@@ -191,4 +191,14 @@ REF_API uint32_t ref_clip_length_ticks(float fps, uint32_t frame_count) {
 	return Time::fromSeconds(frame_count / fps).raw();
 }
 
+// The time step of AnimationModuleImpl::updateAnimable (animation_module.cpp:458-469) through the reference's own Time operators
+// (animation.h:17-43) and Animation::getLength's expression (animation.h:128)
+REF_API uint32_t ref_time_advance(uint32_t time_ticks, float time_delta, float fps, uint32_t frame_count) {
+	const Time now(time_ticks);
+	const Time l = Time::fromSeconds(frame_count / fps);
+	if (time_delta > 0) return ((now + Time::fromSeconds(time_delta)) % l).raw();
+	const Time dt = Time::fromSeconds(-time_delta) % l;
+	return ((now + l - dt) % l).raw();
+}
+
 REF_API uint32_t ref_time_from_seconds(float s) { return Time::fromSeconds(s).raw(); }

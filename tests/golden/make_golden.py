@@ -174,6 +174,15 @@ def pose_kat():
         p, r = po.pose_blend(rel0[0][:, :3], rel0[0][:, 3:], rel0[-1][:, :3], -rel0[-1][:, 3:] if w == 0.5 else rel0[-1][:, 3:], float(w), use_ref=True)
         blends.append(np.concatenate([p, r], axis=1))
     d["pose_blend"] = np.array(blends)
+    # time step of updateAnimable through the reference's Time operators: (ticks, time_delta, fps, frame_count) -> ticks
+    rng = np.random.default_rng(77)
+    rows = []
+    for fps, fc in ((30.0, 60), (24.0, 37), (1.0, 3), (29.97, 1000)):
+        l = po.ref().ref_clip_length_ticks(C.c_float(fps), C.c_uint32(fc))
+        for dt in (1 / 60, 0.5, 3.7, -0.25, -1 / 60, -100.3, 0.0, 1e-6, -1e-6, 250.0):
+            for t in rng.integers(0, l, 6):
+                rows.append((float(t), dt, fps, float(fc), float(po.time_advance(t, dt, fps, fc, use_ref=True))))
+    d["time_advance"] = np.array(rows, np.float64)
     d["time_from_seconds_in"] = np.array([0.0, 1 / 60, 1 / 30, 0.5, 3.7, 100.25], np.float32)
     d["time_from_seconds_out"] = np.array([po.ref().ref_time_from_seconds(C.c_float(float(x))) for x in d["time_from_seconds_in"]], np.uint32)
     np.savez_compressed(os.path.join(OUT, "pose_kat.npz"), **d)

@@ -135,6 +135,8 @@ def test_pose_sampling_and_absolute(oracle):
             bl = np.concatenate(oracle.pose_evaluate(sk, clip, (int(t) * 7 + 11) % max(L, 1), weight=0.37, start_from_bind=False, compute_absolute=False,
                                                      pos=rel[:, :3], rot=rel[:, 3:]), axis=1)
             assert np.array_equal(bits(bl), bits(g[f"c{k}_blend"][j])), (k, t)
+    for t, dt, fps, fc, exp in g["time_advance"]:  # animation_module.cpp:458-469 through the reference's own Time operators
+        assert oracle.time_advance(int(t), float(dt), float(fps), int(fc)) == int(exp), (t, dt, fps, fc)
     for s, exp in zip(g["time_from_seconds_in"], g["time_from_seconds_out"]):
         assert int(np.uint32(np.float32(s) * np.float32(32768))) == int(exp)  # Time::fromSeconds, animation.h:21-24
 
