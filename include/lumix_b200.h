@@ -81,6 +81,10 @@ LB200_API void lb200_frustum_perspective(lb200_shifted_frustum* out, const doubl
 	float fov, float ratio, float near_distance, float far_distance);
 LB200_API void lb200_frustum_ortho(lb200_shifted_frustum* out, const double position[3], const float direction[3], const float up[3],
 	float width, float height, float near_distance, float far_distance);
+/* Viewport::getFrustum() (src/core/geometry.cpp:793-818): camera position + rotation quaternion (xyzw), vertical fov or ortho size,
+ * viewport size in pixels (ratio = h > 0 ? w / (float)h : 1). */
+LB200_API void lb200_frustum_from_viewport(lb200_shifted_frustum* out, int is_ortho, float fov, float ortho_size, int w, int h,
+                                           const double pos[3], const float rot[4], float near_distance, float far_distance);
 
 /* ------------------------------------------------------------------------------------------------------------
  * CullingSystem — replaces struct CullingSystem, src/renderer/culling_system.h:58-77 (one C function per virtual,

@@ -8,6 +8,6 @@ Everything computes in liblumix_b200.so (hand-written sm_100a CUDA behind the C-
 There is no CPU fallback: importing works anywhere, creating a Context without a GPU raises NoDeviceError.
 """
 from ._lib import (Context, LumixB200Error, NoDeviceError, PALETTE_DUAL_QUAT, PALETTE_MATRIX, PALETTE_POSE, TYPE_ALL, device_count)  # noqa: F401
-from .culling import CullingSystem, CullResult, frustum_ortho, frustum_perspective  # noqa: F401
+from .culling import CullingSystem, CullResult, frustum_from_viewport, frustum_ortho, frustum_perspective  # noqa: F401
 from .hierarchy import Hierarchy, TRANSFORM_DTYPE  # noqa: F401
 from .animation import AnimationClip, AnimationSystem, SkinnedMesh, Skeleton  # noqa: F401

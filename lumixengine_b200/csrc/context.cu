@@ -211,4 +211,24 @@ void lb200_frustum_ortho(lb200_shifted_frustum* f, const double position[3], con
 	setPoints(f, near_center, far_center, x, y, x, y);
 }
 
+// Viewport::getFrustum(), geometry.cpp:793-818: direction / up from the camera rotation (Quat * Vec3 = rotate, math.cpp:721-724),
+// ratio = h > 0 ? w / (float)h : 1; the reference builds at the origin and then stores pos, which gives the same bytes.
+void lb200_frustum_from_viewport(lb200_shifted_frustum* f, int is_ortho, float fov, float ortho_size, int w, int h, const double pos[3],
+	const float rot[4], float near_distance, float far_distance)
+{
+	const Q4 q = q4(rot[0], rot[1], rot[2], rot[3]);
+	const float ratio = h > 0 ? w / (float)h : 1;
+	const V3 up = rotate(q, v3(0, 1, 0));
+	const float up3[3] = {up.x, up.y, up.z};
+	if (is_ortho) {
+		const V3 d = rotate(q, v3(0, 0, 1));
+		const float d3_[3] = {d.x, d.y, d.z};
+		lb200_frustum_ortho(f, pos, d3_, up3, ortho_size * ratio, ortho_size, near_distance, far_distance);
+		return;
+	}
+	const V3 d = rotate(q, v3(0, 0, -1));
+	const float d3_[3] = {d.x, d.y, d.z};
+	lb200_frustum_perspective(f, pos, d3_, up3, fov, ratio, near_distance, far_distance);
+}
+
 } // extern "C"

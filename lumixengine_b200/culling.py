@@ -30,6 +30,14 @@ def frustum_ortho(position, direction, up, width, height, near, far):
     return f
 
 
+def frustum_from_viewport(pos, rot, fov, w, h, near, far, is_ortho=False, ortho_size=100.0):
+    """Viewport::getFrustum() (src/core/geometry.cpp:793-818): camera position, rotation quaternion (xyzw), viewport size in pixels."""
+    f = ShiftedFrustum()
+    _lib.lib().lb200_frustum_from_viewport(C.byref(f), C.c_int(1 if is_ortho else 0), C.c_float(fov), C.c_float(ortho_size), C.c_int(w), C.c_int(h),
+                                           (C.c_double * 3)(*pos), (C.c_float * 4)(*rot), C.c_float(near), C.c_float(far))
+    return f
+
+
 def frustum_bytes(f):
     return np.frombuffer(bytes(f), np.uint8).copy()
 

@@ -21,6 +21,8 @@ void oracle_frustum_perspective(OShiftedFrustum* f, const double* position, cons
 	float fov, float ratio, float near_distance, float far_distance);
 void oracle_frustum_ortho(OShiftedFrustum* f, const double* position, const float* direction, const float* up,
 	float width, float height, float near_distance, float far_distance);
+void oracle_frustum_from_viewport(OShiftedFrustum* f, int is_ortho, float fov, float ortho_size, int w, int h, const double* pos,
+	const float* rot4, float near_distance, float far_distance);
 int oracle_frustum_contains_aabb(const OShiftedFrustum* f, ODVec3 pos, OVec3 size);
 int oracle_frustum_intersects_aabb(const OShiftedFrustum* f, ODVec3 pos, OVec3 size);
 void oracle_frustum_get_relative(const OShiftedFrustum* f, ODVec3 origin, OFrustum* res);

@@ -100,6 +100,24 @@ void oracle_frustum_ortho(OShiftedFrustum* f, const double* position, const floa
 	sf_set_points(f, near_center, far_center, x, y, x, y, -1, -1, 1, 1);
 }
 
+/* geometry.cpp:793-818 Viewport::getFrustum(): the frustum is built at the origin from the camera rotation (Quat * Vec3 = rotate,
+ * math.cpp:721-724), ratio = h > 0 ? w / (float)h : 1, and then ret.origin = pos.  The builders never read `position` except to store
+ * it, so building at `pos` directly gives the same bytes. */
+void oracle_frustum_from_viewport(OShiftedFrustum* f, int is_ortho, float fov, float ortho_size, int w, int h, const double* pos,
+	const float* rot4, float near_distance, float far_distance)
+{
+	const OQuat rot = oquat(rot4[0], rot4[1], rot4[2], rot4[3]);
+	const float ratio = h > 0 ? w / (float)h : 1;
+	const OVec3 up = oquat_rotate(rot, ov3(0, 1, 0));
+	if (is_ortho) {
+		const OVec3 dir = oquat_rotate(rot, ov3(0, 0, 1));
+		oracle_frustum_ortho(f, pos, &dir.x, &up.x, ortho_size * ratio, ortho_size, near_distance, far_distance);
+		return;
+	}
+	const OVec3 dir = oquat_rotate(rot, ov3(0, 0, -1));
+	oracle_frustum_perspective(f, pos, &dir.x, &up.x, fov, ratio, near_distance, far_distance);
+}
+
 /* geometry.cpp:99-118 ShiftedFrustum::containsAABB */
 int oracle_frustum_contains_aabb(const OShiftedFrustum* f, ODVec3 pos, OVec3 size) {
 	const OVec3 rel_pos = ov3_from_d(odv3_sub(pos, f->origin));

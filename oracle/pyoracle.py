@@ -278,6 +278,18 @@ def ref():
     return _ref
 
 
+def frustum_from_viewport(pos, rot, fov, w, h, near, far, is_ortho=False, ortho_size=100.0, use_ref=False):
+    """Viewport::getFrustum() (geometry.cpp:793-818) -> 256-byte ShiftedFrustum image; use_ref=True runs the reference's own."""
+    out = np.zeros(256, np.uint8)
+    args = (C.c_int(1 if is_ortho else 0), C.c_float(fov), C.c_float(ortho_size), C.c_int(w), C.c_int(h), (C.c_double * 3)(*pos), (C.c_float * 4)(*rot),
+            C.c_float(near), C.c_float(far))
+    if use_ref:
+        ref().ref_viewport_frustum(*args, _ptr(out))
+    else:
+        lib().oracle_frustum_from_viewport(_ptr(out), *args)
+    return out
+
+
 def ref_frustum_perspective(pos, direction, up, fov, ratio, near, far):
     out = np.zeros(256, np.uint8)
     ref().ref_frustum_perspective((C.c_double * 3)(*pos), (C.c_float * 3)(*direction), (C.c_float * 3)(*up),

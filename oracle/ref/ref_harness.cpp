@@ -87,6 +87,18 @@ REF_API void ref_frustum_ortho(const double* pos, const float* dir, const float*
 	memcpy(out256, &f, sizeof(f));
 }
 
+REF_API void ref_viewport_frustum(int is_ortho, float fov, float ortho_size, int w, int h, const double* pos, const float* rot4, float near_d, float far_d, void* out256) {
+	Viewport vp;
+	vp.is_ortho = is_ortho != 0; vp.fov = fov; vp.ortho_size = ortho_size; vp.w = w; vp.h = h;
+	vp.pos = DVec3(pos[0], pos[1], pos[2]);
+	vp.rot = Quat(rot4[0], rot4[1], rot4[2], rot4[3]);
+	vp.near = near_d; vp.far = far_d;
+	ShiftedFrustum f;
+	memset(&f, 0, sizeof(f));
+	f = vp.getFrustum();
+	memcpy(out256, &f, sizeof(f));
+}
+
 REF_API void ref_frustum_get_relative(const void* sf256, const double* origin, void* out224) {
 	const ShiftedFrustum& f = *(const ShiftedFrustum*)sf256;
 	Frustum r = f.getRelative(DVec3(origin[0], origin[1], origin[2]));

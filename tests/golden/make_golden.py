@@ -213,6 +213,17 @@ def world_kat():
     d["cl_parent"] = par.view(np.uint8).reshape(n, 56)
     d["cl_child"] = chi.view(np.uint8).reshape(n, 56)
     d["cl_out"] = po.transform_compute_local(d["cl_parent"], d["cl_child"], use_ref=True)
+    # Viewport::getFrustum() (geometry.cpp:793-818): args = is_ortho, fov, ortho_size, w, h, pos[3], rot[4], near, far
+    vp_args, vp_out = [], []
+    for k in range(120):
+        q = rng.normal(size=4).astype(np.float32); q /= np.linalg.norm(q)
+        pos = rng.normal(size=3) * (1e3 if k % 2 else 1e6)
+        w, h = int(rng.integers(1, 4000)), (int(rng.integers(1, 3000)) if k % 17 else 0)
+        fov, near, far = np.float32(0.2 + rng.random() * 2), np.float32(0.05 + rng.random()), np.float32(100 + rng.random() * 5000)
+        ortho, osz = (k % 3 == 0), np.float32(10 + rng.random() * 500)
+        vp_args.append(np.concatenate([[float(ortho), float(fov), float(osz), w, h], pos, q.astype(np.float64), [float(near), float(far)]]))
+        vp_out.append(po.frustum_from_viewport(pos, q, float(fov), w, h, float(near), float(far), ortho, float(osz), use_ref=True))
+    d["vp_args"], d["vp_out"] = np.array(vp_args), np.array(vp_out)
     np.savez_compressed(os.path.join(OUT, "world_kat.npz"), **d)
     print("world_kat.npz", sum(v.nbytes for v in d.values()))
 

@@ -178,3 +178,17 @@ def test_pose_compute_relative_and_blend(oracle):
         assert np.array_equal(np.concatenate([p, r], 1).view(np.uint32), k["pose_blend"][j].view(np.uint32)), float(w)
     # weights at or below 0.001 leave the pose untouched (pose.cpp:33)
     assert np.array_equal(k["pose_blend"][0], rel[0]) and np.array_equal(k["pose_blend"][1], rel[0])
+
+
+def test_viewport_frustum(oracle):
+    """Viewport::getFrustum() (geometry.cpp:793-818) from the reference build: the restatement and the product's host builder
+    (lb200_frustum_from_viewport needs no GPU) both reproduce its bytes (the last 8 of the 256 are padding)."""
+    import lumixengine_b200 as lb
+    k = np.load(os.path.join(G, "world_kat.npz"))
+    for a, exp in zip(k["vp_args"], k["vp_out"]):
+        is_ortho, fov, osz, w, h = bool(a[0]), float(np.float32(a[1])), float(np.float32(a[2])), int(a[3]), int(a[4])
+        pos, rot, near, far = a[5:8], a[8:12].astype(np.float32), float(np.float32(a[12])), float(np.float32(a[13]))
+        got = oracle.frustum_from_viewport(pos, rot, fov, w, h, near, far, is_ortho, osz)
+        assert np.array_equal(got[:248], exp[:248])
+        prod = lb.culling.frustum_bytes(lb.frustum_from_viewport(pos, rot, fov, w, h, near, far, is_ortho, osz))
+        assert np.array_equal(prod[:248], exp[:248])
