@@ -249,11 +249,12 @@ def ref_relative_matrices(globals56, base_pos):
     return out
 
 
-def sphere_radius(globals56, bounding_radius):
+def sphere_radius(globals56, bounding_radius, use_ref=False):
+    """render_module.cpp:1554: bounding_radius * maximum(scale.x, scale.y, scale.z); use_ref=True uses the reference's own maximum."""
     g = np.ascontiguousarray(globals56, np.uint8)
     b = np.ascontiguousarray(bounding_radius, np.float32)
     out = np.empty(len(b), np.float32)
-    lib().oracle_sphere_radius(_ptr(g), _ptr(b), _ptr(out), C.c_uint32(len(b)))
+    (ref().ref_sphere_radius if use_ref else lib().oracle_sphere_radius)(_ptr(g), _ptr(b), _ptr(out), C.c_uint32(len(b)))
     return out
 
 

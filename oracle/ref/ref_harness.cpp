@@ -144,6 +144,13 @@ REF_API void ref_relative_matrix(const void* tr56, const double* base_pos, float
 	}
 }
 
+// the radius RenderModuleImpl::onModelInstanceMoved hands to CullingSystem::set (render_module.cpp:1554), with the reference's own
+// variadic maximum (math.h:468-475)
+REF_API void ref_sphere_radius(const void* tr56, const float* bounding_radius, float* out, uint32_t n) {
+	const Transform* t = (const Transform*)tr56;
+	for (uint32_t i = 0; i < n; ++i) out[i] = bounding_radius[i] * maximum(t[i].scale.x, t[i].scale.y, t[i].scale.z);
+}
+
 REF_API void ref_transform_compute_local(const void* parent56, const void* child56, void* out56, uint32_t n) {
 	const Transform* p = (const Transform*)parent56;
 	const Transform* c = (const Transform*)child56;

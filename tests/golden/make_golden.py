@@ -213,6 +213,13 @@ def world_kat():
     d["cl_parent"] = par.view(np.uint8).reshape(n, 56)
     d["cl_child"] = chi.view(np.uint8).reshape(n, 56)
     d["cl_out"] = po.transform_compute_local(d["cl_parent"], d["cl_child"], use_ref=True)
+    # sphere refresh of onModelInstanceMoved (render_module.cpp:1554) incl. NaN / negative / equal scales
+    sr = np.zeros(400, tr_dtype)
+    sr["scale"] = (rng.normal(size=(400, 3)) * 2).astype(np.float32)
+    sr["scale"][::13, 1] = np.nan; sr["scale"][::17, 0] = np.nan; sr["scale"][::19] = 1.5; sr["scale"][::23, 2] = np.inf; sr["scale"][::29, 2] = np.nan
+    d["sr_tr"] = sr.view(np.uint8).reshape(400, 56)
+    d["sr_bound"] = (rng.random(400) * 10).astype(np.float32)
+    d["sr_out"] = po.sphere_radius(d["sr_tr"], d["sr_bound"], use_ref=True)
     # Viewport::getFrustum() (geometry.cpp:793-818): args = is_ortho, fov, ortho_size, w, h, pos[3], rot[4], near, far
     vp_args, vp_out = [], []
     for k in range(120):

@@ -192,3 +192,14 @@ def test_viewport_frustum(oracle):
         assert np.array_equal(got[:248], exp[:248])
         prod = lb.culling.frustum_bytes(lb.frustum_from_viewport(pos, rot, fov, w, h, near, far, is_ortho, osz))
         assert np.array_equal(prod[:248], exp[:248])
+
+
+def test_sphere_refresh_radius(oracle):
+    """render_module.cpp:1554 bounding_radius * maximum(scale.x, scale.y, scale.z) with the reference's variadic maximum (math.h:468-475),
+    including NaN scales (a NaN in z propagates, a NaN in x or y is dropped by the comparisons)."""
+    k = np.load(os.path.join(G, "world_kat.npz"))
+    got = oracle.sphere_radius(k["sr_tr"], k["sr_bound"])
+    exp = k["sr_out"]
+    assert np.isnan(exp).sum() > 0
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    assert np.array_equal(got[~np.isnan(exp)].view(np.uint32), exp[~np.isnan(exp)].view(np.uint32))
