@@ -14,6 +14,7 @@
 // HBM-bound: 16 B per tested sphere + 4 B read + 4 B write per visible id.  No tensor cores: there is no
 // contraction here.
 #include "cull_kernel.cuh"
+#include "cull_kernel_lean.cuh"
 #include "culling_host.hpp"
 #include "lb200_math.cuh"
 
@@ -488,7 +489,9 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = pdl ? 1 : 0;
-	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cull_pages_kernel<256>, P, (const lb200_page_desc*)(cs->d_desc + off),
+	// LB200_CULL_LEAN=1 selects the instruction-lean variant (cull_kernel_lean.cuh): same results, not yet validated on a GPU
+	static const bool lean = getenv("LB200_CULL_LEAN") != nullptr && atoi(getenv("LB200_CULL_LEAN")) != 0;
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, lean ? cull_pages_lean_kernel<256> : cull_pages_kernel<256>, P, (const lb200_page_desc*)(cs->d_desc + off),
 		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), out, cur, nxt,
 		xchg ? (uint32_t*)nullptr : mask));
 	LB200_CHECK_LAUNCH(ctx);
