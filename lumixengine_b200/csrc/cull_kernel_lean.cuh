@@ -10,6 +10,10 @@
 //   B  plane-outer / row-inner: warp-uniform loop over the planes of the mask, seven rows unrolled inside, no branch per sphere; lanes past
 //      `count` load a clamped slot and are masked at the ballot.
 //   D  full rows take the lane index as rank, rows without a visible sphere are skipped.
+//
+//   Static SASS (cuobjdump, sm_100a): 64 registers, no spills, 1928 instructions in all (default kernel: 2200); the plane loop of B is
+//   67 instructions per plane for the seven rows of a page (56 FMUL / FADD / LOP3 + 11 of loop overhead, plane load and shuffle), i.e.
+//   about 45 + 67 x planes + 40 per tested page against the 353 executed per tested page by the default kernel on the C2 view.
 #pragma once
 
 #include "cull_kernel.cuh"
