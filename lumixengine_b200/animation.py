@@ -124,6 +124,77 @@ class AnimationClip:
             CR[i] = (b, 0, v)
         return AnimationClip(fps, frame_count, T, CT, R, CR, t_stream, r_stream, t_frame_bits, r_frame_bits)
 
+    # ---- compiled .ani image (the file Animation::load reads, src/animation/animation.cpp:397-493) ----
+    ANI_MAGIC = 0x5F4C4146  # '_LAF', animation.h:56
+    ANI_VERSION = 7         # Version::SKELETON: no skeleton path string in the file (animation.h:64-69)
+
+    def to_ani_bytes(self, bone_hashes, flags=0):
+        """Serialise the clip the way the asset compiler does: header, fps, frame count, flags, translation track descriptors
+        (BoneNameHash u64, TrackType u8, then value or min / to_range / bitsizes / offset_bits), the translation bit stream, rotation
+        descriptors (+ skipped_channel) and the rotation bit stream.  bone_hashes[bone_index] = the bone's name hash."""
+        import struct
+        out = [struct.pack("<II", self.ANI_MAGIC, self.ANI_VERSION), struct.pack("<fII", self.fps, self.frame_count, flags)]
+        out.append(struct.pack("<I", len(self.translations) + len(self.const_translations)))
+        tracks = [(int(t["bone_index"]), 0, t) for t in self.const_translations] + [(int(t["bone_index"]), 1, t) for t in self.translations]
+        for bone, kind, t in sorted(tracks, key=lambda x: (x[0], x[1])):
+            out.append(struct.pack("<QB", int(bone_hashes[bone]), kind))
+            if kind == 0:
+                out.append(struct.pack("<3f", *t["value"]))
+            else:
+                out.append(struct.pack("<3f3f3BH", *t["min"], *t["to_range"], *[int(x) for x in t["bitsizes"]], int(t["offset_bits"])))
+        n = (self.translations_frame_size_bits * (self.frame_count + 1) + 7) // 8  # animation.cpp:461
+        out.append(bytes(self.translation_stream[:n]))
+        out.append(struct.pack("<I", len(self.rotations) + len(self.const_rotations)))
+        tracks = [(int(t["bone_index"]), 0, t) for t in self.const_rotations] + [(int(t["bone_index"]), 1, t) for t in self.rotations]
+        for bone, kind, t in sorted(tracks, key=lambda x: (x[0], x[1])):
+            out.append(struct.pack("<QB", int(bone_hashes[bone]), kind))
+            if kind == 0:
+                out.append(struct.pack("<4f", *t["value"]))
+            else:
+                out.append(struct.pack("<3f3f3BHB", *t["min"], *t["to_range"], *[int(x) for x in t["bitsizes"]], int(t["offset_bits"]), int(t["skipped_channel"])))
+        n = (self.rotations_frame_size_bits * (self.frame_count + 1) + 7) // 8
+        out.append(bytes(self.rotation_stream[:n]))
+        return b"".join(out)
+
+    @staticmethod
+    def from_ani_bytes(data, hash_to_bone):
+        """Animation::load (animation.cpp:397-493) + the bone index resolution of Animation::onBeforeReady (:366-395): compiled .ani
+        image -> AnimationClip.  hash_to_bone maps a BoneNameHash value to the bone index of the skeleton (Model::getBoneIndex)."""
+        import struct
+        magic, version = struct.unpack_from("<II", data, 0)
+        if magic != AnimationClip.ANI_MAGIC:
+            raise ValueError("not a compiled animation ('_LAF' magic missing)")
+        if version <= 6 or version > 7:
+            raise ValueError(f"animation version {version} not supported (7 = SKELETON without an embedded path)")
+        pos = 8
+        fps, frame_count, _flags = struct.unpack_from("<fII", data, pos); pos += 12
+        (n_tr,) = struct.unpack_from("<I", data, pos); pos += 4
+        T, CT, t_bits = [], [], 0
+        for _ in range(n_tr):
+            h, kind = struct.unpack_from("<QB", data, pos); pos += 9
+            if kind == 0:
+                CT.append((hash_to_bone[h], 0, struct.unpack_from("<3f", data, pos))); pos += 12
+            else:
+                v = struct.unpack_from("<3f3f3BH", data, pos); pos += 29
+                T.append((hash_to_bone[h], v[9], v[6:9], 0, v[0:3], v[3:6]))
+                t_bits += sum(v[6:9])
+        n = (t_bits * (frame_count + 1) + 7) // 8
+        t_stream = np.zeros(n + 8, np.uint8); t_stream[:n] = np.frombuffer(data, np.uint8, n, pos); pos += n
+        (n_rot,) = struct.unpack_from("<I", data, pos); pos += 4
+        R, CR, r_bits = [], [], 0
+        for _ in range(n_rot):
+            h, kind = struct.unpack_from("<QB", data, pos); pos += 9
+            if kind == 0:
+                CR.append((hash_to_bone[h], 0, struct.unpack_from("<4f", data, pos))); pos += 16
+            else:
+                v = struct.unpack_from("<3f3f3BHB", data, pos); pos += 30
+                R.append((hash_to_bone[h], v[9], v[6:9], v[10], v[0:3], v[3:6]))
+                r_bits += sum(v[6:9]) + 1  # + sign bit, animation.cpp:484
+        n = (r_bits * (frame_count + 1) + 7) // 8
+        r_stream = np.zeros(n + 8, np.uint8); r_stream[:n] = np.frombuffer(data, np.uint8, min(n, len(data) - pos), pos)[:n]
+        return AnimationClip(fps, frame_count, np.array(T, TRACK_DTYPE), np.array(CT, CONST_T_DTYPE), np.array(R, TRACK_DTYPE), np.array(CR, CONST_R_DTYPE),
+                             t_stream, r_stream, t_bits, r_bits)
+
     def as_struct(self, struct_cls):
         """Fill a ctypes clip struct (lumix_b200 `Clip` or any struct with the same field names); keeps the arrays alive through self."""
         s = struct_cls()

@@ -492,6 +492,28 @@ def ref_evaluate_skin(matrices, vertices, weights, indices):
     return out
 
 
+class RefLoaded(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("fps", C.c_float), ("frame_count", C.c_uint32), ("flags", C.c_uint32), ("t_bits", C.c_uint32), ("r_bits", C.c_uint32),
+                ("n_t", C.c_uint32), ("n_ct", C.c_uint32), ("n_r", C.c_uint32), ("n_cr", C.c_uint32), ("t_stream_offset", C.c_uint32),
+                ("r_stream_offset", C.c_uint32), ("mem_size", C.c_uint32)]
+
+
+def ref_animation_load(image, cap=256):
+    """The reference's own Animation::load (animation.cpp:397-493) on a compiled .ani image -> dict of everything it parsed."""
+    from lumixengine_b200.animation import TRACK_DTYPE
+    img = np.frombuffer(bytes(image), np.uint8).copy()
+    out = RefLoaded()
+    th, cth, rh, crh = (np.zeros(cap, np.uint64) for _ in range(4))
+    t, r = np.zeros(cap, TRACK_DTYPE), np.zeros(cap, TRACK_DTYPE)
+    ctv, crv = np.zeros((cap, 3), np.float32), np.zeros((cap, 4), np.float32)
+    ref().ref_animation_load(_ptr(img), C.c_uint32(len(img)), C.byref(out), _ptr(th), _ptr(t), _ptr(cth), _ptr(ctv), _ptr(rh), _ptr(r), _ptr(crh), _ptr(crv),
+                             C.c_uint32(cap))
+    d = {k: getattr(out, k) for k, _ in RefLoaded._fields_}
+    d.update(t_hash=th[:out.n_t], t=t[:out.n_t], ct_hash=cth[:out.n_ct], ct_value=ctv[:out.n_ct], r_hash=rh[:out.n_r], r=r[:out.n_r],
+             cr_hash=crh[:out.n_cr], cr_value=crv[:out.n_cr])
+    return d
+
+
 def pose_compute_absolute(skeleton, pos, rot):
     """Pose::computeAbsolute (pose.cpp:66-133) on one relative pose -> (pos, rot)."""
     sk = _skeleton_struct(skeleton, Skeleton)

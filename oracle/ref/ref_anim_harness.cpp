@@ -191,6 +191,73 @@ REF_API uint32_t ref_clip_length_ticks(float fps, uint32_t frame_count) {
 	return Time::fromSeconds(frame_count / fps).raw();
 }
 
+// Animation::load (animation.cpp:397-493) on a caller-supplied compiled .ani image, version SKELETON (7: no skeleton path in the file; the
+// harness pre-sets m_skeleton so the loader does not go to the resource system).  Reports what the loader parsed: scalar fields, the
+// four track arrays (name hash instead of the bone index, which onBeforeReady resolves later against the model) and where the two
+// bit streams start inside its copy of the file body.
+struct RefLoaded {
+	int32_t ok;
+	float fps;
+	uint32_t frame_count, flags, t_bits, r_bits, n_t, n_ct, n_r, n_cr, t_stream_offset, r_stream_offset, mem_size;
+};
+REF_API void ref_animation_load(const uint8_t* image, uint32_t size, RefLoaded* out, uint64_t* t_hash, RefTrack* t, uint64_t* ct_hash, float* ct_value3,
+	uint64_t* r_hash, RefTrack* r, uint64_t* cr_hash, float* cr_value4, uint32_t cap)
+{
+	static DefaultAllocator allocator;
+	memset(out, 0, sizeof(*out));
+	RawStorage<Animation> anim_mem;
+	Animation* anim = anim_mem.get();
+	new (&anim->m_translations) Array<Animation::TranslationTrack>(allocator);
+	new (&anim->m_const_translations) Array<Animation::ConstTranslationTrack>(allocator);
+	new (&anim->m_rotations) Array<Animation::RotationTrack>(allocator);
+	new (&anim->m_const_rotations) Array<Animation::ConstRotationTrack>(allocator);
+	new (&anim->m_mem) Array<u8>(allocator);
+	RawStorage<Model> model_mem;
+	anim->m_skeleton = model_mem.get(); // only tested for null by load()
+	out->ok = anim->load(Span<const u8>(image, size)) ? 1 : 0;
+	if (out->ok && anim->m_translations.size() <= (int)cap && anim->m_const_translations.size() <= (int)cap && anim->m_rotations.size() <= (int)cap
+		&& anim->m_const_rotations.size() <= (int)cap)
+	{
+		out->fps = anim->m_fps; out->frame_count = anim->m_frame_count; out->flags = (uint32_t)anim->m_flags;
+		out->t_bits = anim->m_translations_frame_size_bits; out->r_bits = anim->m_rotations_frame_size_bits;
+		out->n_t = anim->m_translations.size(); out->n_ct = anim->m_const_translations.size();
+		out->n_r = anim->m_rotations.size(); out->n_cr = anim->m_const_rotations.size();
+		out->mem_size = anim->m_mem.size();
+		out->t_stream_offset = (uint32_t)(anim->m_translation_stream - anim->m_mem.begin());
+		out->r_stream_offset = (uint32_t)(anim->m_rotation_stream - anim->m_mem.begin());
+		for (uint32_t i = 0; i < out->n_t; ++i) {
+			const Animation::TranslationTrack& k = anim->m_translations[i];
+			t_hash[i] = k.bone_name.getHashValue();
+			t[i].bone_index = 0; t[i].offset_bits = k.offset_bits; memcpy(t[i].bitsizes, k.bitsizes, 3); t[i].skipped_channel = 0;
+			t[i].min[0] = k.min.x; t[i].min[1] = k.min.y; t[i].min[2] = k.min.z;
+			t[i].to_range[0] = k.to_range.x; t[i].to_range[1] = k.to_range.y; t[i].to_range[2] = k.to_range.z;
+		}
+		for (uint32_t i = 0; i < out->n_ct; ++i) {
+			const Animation::ConstTranslationTrack& k = anim->m_const_translations[i];
+			ct_hash[i] = k.bone_name.getHashValue();
+			ct_value3[3 * i] = k.value.x; ct_value3[3 * i + 1] = k.value.y; ct_value3[3 * i + 2] = k.value.z;
+		}
+		for (uint32_t i = 0; i < out->n_r; ++i) {
+			const Animation::RotationTrack& k = anim->m_rotations[i];
+			r_hash[i] = k.bone_name.getHashValue();
+			r[i].bone_index = 0; r[i].offset_bits = k.offset_bits; memcpy(r[i].bitsizes, k.bitsizes, 3); r[i].skipped_channel = k.skipped_channel;
+			r[i].min[0] = k.min.x; r[i].min[1] = k.min.y; r[i].min[2] = k.min.z;
+			r[i].to_range[0] = k.to_range.x; r[i].to_range[1] = k.to_range.y; r[i].to_range[2] = k.to_range.z;
+		}
+		for (uint32_t i = 0; i < out->n_cr; ++i) {
+			const Animation::ConstRotationTrack& k = anim->m_const_rotations[i];
+			cr_hash[i] = k.bone_name.getHashValue();
+			cr_value4[4 * i] = k.value.x; cr_value4[4 * i + 1] = k.value.y; cr_value4[4 * i + 2] = k.value.z; cr_value4[4 * i + 3] = k.value.w;
+		}
+	}
+	else out->ok = out->ok ? -1 : 0; // -1: parsed but over the caller's capacity
+	anim->m_translations.~Array();
+	anim->m_const_translations.~Array();
+	anim->m_rotations.~Array();
+	anim->m_const_rotations.~Array();
+	anim->m_mem.~Array();
+}
+
 // The time step of AnimationModuleImpl::updateAnimable (animation_module.cpp:458-469) through the reference's own Time operators
 // (animation.h:17-43) and Animation::getLength's expression (animation.h:128)
 REF_API uint32_t ref_time_advance(uint32_t time_ticks, float time_delta, float fps, uint32_t frame_count) {

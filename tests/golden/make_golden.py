@@ -235,6 +235,31 @@ def world_kat():
     print("world_kat.npz", sum(v.nbytes for v in d.values()))
 
 
+def ani_kat():
+    """Compiled .ani images written by AnimationClip.to_ani_bytes and what the reference's own Animation::load (animation.cpp:397-493)
+    parsed out of them."""
+    d = {}
+    cfgs = [(24, 17, 0.25, (11, 13, 16), (12, 14, 16)), (64, 60, 0.25, (16, 16, 16), (15, 15, 15)), (7, 3, 0.0, (5, 3, 7), (9, 9, 9)), (5, 9, 1.0, (16, 16, 16), (15, 15, 15))]
+    for k, (bones, frames, cf, pb, rb) in enumerate(cfgs):
+        sk = scenes.skeleton(bones, seed=bones)
+        clip = scenes.clip(sk, frames=frames, seed=bones + 3, pos_bits=pb, rot_bits=rb, const_fraction=cf)
+        hashes = np.array([(0x9E3779B97F4A7C15 * (i + 1)) & 0xFFFFFFFFFFFFFFFF for i in range(bones)], np.uint64)
+        img = clip.to_ani_bytes(hashes)
+        L = po.ref_animation_load(img)
+        assert L["ok"] == 1
+        d[f"a{k}_image"] = np.frombuffer(img, np.uint8).copy()
+        d[f"a{k}_hashes"] = hashes
+        d[f"a{k}_scalars"] = np.array([L["frame_count"], L["t_bits"], L["r_bits"], L["n_t"], L["n_ct"], L["n_r"], L["n_cr"], L["t_stream_offset"], L["r_stream_offset"],
+                                       L["mem_size"]], np.int64)
+        d[f"a{k}_fps"] = np.array([L["fps"]], np.float32)
+        for key in ("t_hash", "ct_hash", "r_hash", "cr_hash", "ct_value", "cr_value"):
+            d[f"a{k}_{key}"] = L[key]
+        d[f"a{k}_t"] = L["t"].view(np.uint8).reshape(-1, 32)
+        d[f"a{k}_r"] = L["r"].view(np.uint8).reshape(-1, 32)
+    np.savez_compressed(os.path.join(OUT, "ani_kat.npz"), **d)
+    print("ani_kat.npz", sum(v.nbytes for v in d.values()))
+
+
 if __name__ == "__main__":
     po.build()
     po.ref().ref_clip_length_ticks.restype = C.c_uint32
@@ -243,5 +268,6 @@ if __name__ == "__main__":
     pose_kat()
     cull_kat()
     world_kat()
+    ani_kat()
     sys.stdout.flush()
     os._exit(0)

@@ -203,3 +203,38 @@ def test_sphere_refresh_radius(oracle):
     assert np.isnan(exp).sum() > 0
     assert np.array_equal(np.isnan(got), np.isnan(exp))
     assert np.array_equal(got[~np.isnan(exp)].view(np.uint32), exp[~np.isnan(exp)].view(np.uint32))
+
+
+def test_ani_image_loader():
+    """AnimationClip.from_ani_bytes against what the reference's own Animation::load (animation.cpp:397-493) parsed out of the same
+    compiled .ani images (tests/golden/ani_kat.npz), and to_ani_bytes reproduces the images byte for byte."""
+    from lumixengine_b200.animation import AnimationClip, TRACK_DTYPE
+    k = np.load(os.path.join(G, "ani_kat.npz"))
+    cfgs = [(24, 17, 0.25, (11, 13, 16), (12, 14, 16)), (64, 60, 0.25, (16, 16, 16), (15, 15, 15)), (7, 3, 0.0, (5, 3, 7), (9, 9, 9)), (5, 9, 1.0, (16, 16, 16), (15, 15, 15))]
+    for i, (bones, frames, cf, pb, rb) in enumerate(cfgs):
+        img, hashes = k[f"a{i}_image"].tobytes(), k[f"a{i}_hashes"]
+        h2b = {int(h): b for b, h in enumerate(hashes)}
+        clip = AnimationClip.from_ani_bytes(img, h2b)
+        fc, t_bits, r_bits, n_t, n_ct, n_r, n_cr, t_off, r_off, mem = (int(v) for v in k[f"a{i}_scalars"])
+        assert (clip.frame_count, clip.translations_frame_size_bits, clip.rotations_frame_size_bits) == (fc, t_bits, r_bits)
+        assert np.float32(clip.fps) == k[f"a{i}_fps"][0]
+        assert (len(clip.translations), len(clip.const_translations), len(clip.rotations), len(clip.const_rotations)) == (n_t, n_ct, n_r, n_cr)
+        for mine, ref, hs in ((clip.translations, k[f"a{i}_t"], k[f"a{i}_t_hash"]), (clip.rotations, k[f"a{i}_r"], k[f"a{i}_r_hash"])):
+            ref = ref.reshape(-1).view(TRACK_DTYPE) if len(ref) else np.zeros(0, TRACK_DTYPE)
+            assert np.array_equal([h2b[int(h)] for h in hs], mine["bone_index"])  # onBeforeReady's resolution (animation.cpp:366-395)
+            for f in ("offset_bits", "bitsizes", "skipped_channel", "min", "to_range"):
+                assert np.ascontiguousarray(ref[f]).tobytes() == np.ascontiguousarray(mine[f]).tobytes(), f
+        assert np.array_equal([h2b[int(h)] for h in k[f"a{i}_ct_hash"]], clip.const_translations["bone_index"])
+        assert k[f"a{i}_ct_value"].tobytes() == np.ascontiguousarray(clip.const_translations["value"]).tobytes()
+        assert np.array_equal([h2b[int(h)] for h in k[f"a{i}_cr_hash"]], clip.const_rotations["bone_index"])
+        assert k[f"a{i}_cr_value"].tobytes() == np.ascontiguousarray(clip.const_rotations["value"]).tobytes()
+        body = img[24:]
+        n_t_bytes, n_r_bytes = (t_bits * (fc + 1) + 7) // 8, (r_bits * (fc + 1) + 7) // 8
+        assert body[t_off:t_off + n_t_bytes] == bytes(clip.translation_stream[:n_t_bytes])
+        assert body[r_off:r_off + n_r_bytes] == bytes(clip.rotation_stream[:n_r_bytes])
+        assert mem == len(body) + 8  # the loader's 8-byte unpacker padding, animation.cpp:439
+        # and the writer is the inverse of the loader
+        sk = scenes.skeleton(bones, seed=bones)
+        orig = scenes.clip(sk, frames=frames, seed=bones + 3, pos_bits=pb, rot_bits=rb, const_fraction=cf)
+        assert orig.to_ani_bytes(hashes) == img
+        assert clip.to_ani_bytes(hashes) == img
