@@ -238,3 +238,22 @@ def test_ani_image_loader():
         orig = scenes.clip(sk, frames=frames, seed=bones + 3, pos_bits=pb, rot_bits=rb, const_fraction=cf)
         assert orig.to_ani_bytes(hashes) == img
         assert clip.to_ani_bytes(hashes) == img
+
+
+def test_skeleton_derivation_follows_parse_bones(oracle):
+    """Skeleton derives the inverse bind pose and the relative bind transforms the way Model::parseBones does (model.cpp:389-421:
+    invert(transform) = LocalRigidTransform::inverted's formula, relative = inverse_bind(parent) * transform).  Both primitives are pinned
+    against the reference build (math_kat: lrt_inverted, lrt_mul); here the numpy derivation must equal them bit for bit."""
+    L = oracle.lib()
+    for bones in (1, 5, 24, 64, 196):
+        sk = scenes.skeleton(bones, seed=100 + bones)
+        abs7 = np.ascontiguousarray(sk.bind_abs7, np.float32)
+        inv = np.zeros_like(abs7)
+        L.oracle_lrt_inverted(P(abs7), P(inv), C.c_uint32(bones))
+        assert np.array_equal(bits(inv), bits(sk.inverse_bind7))
+        par = np.maximum(sk.parents, 0)
+        rel = np.zeros_like(abs7)
+        L.oracle_lrt_mul(P(np.ascontiguousarray(inv[par])), P(abs7), P(rel), C.c_uint32(bones))
+        rel[sk.parents < 0] = abs7[sk.parents < 0]  # roots keep their transform (model.cpp:416-419)
+        assert np.array_equal(bits(rel), bits(sk.bind_relative7))
+        assert all(int(p) < i for i, p in enumerate(sk.parents))  # parent < child, model.cpp:381-384
