@@ -59,6 +59,22 @@ def test_world_patch_compiles_inside_world_cpp():
             assert f in syms  # unresolved here, provided by liblumix_b200.so
 
 
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "engine")), reason="reference tree not present")
+def test_plugin_entry_compiles_against_engine_headers():
+    """host/b200_system.cpp: the ISystem + LUMIX_PLUGIN_ENTRY the engine's SystemManager loads (plugin.h:64-96), static-plugin flavour."""
+    with tempfile.TemporaryDirectory() as tmp:
+        _copy_headers(tmp, ("core", "engine"))
+        obj = os.path.join(tmp, "b200_system.o")
+        cmd = GXX + ["-I", os.path.join(tmp, "src"), "-I", os.path.join(REF, "external"), "-I", os.path.join(ROOT, "include"),
+                     os.path.join(ROOT, "lumixengine_b200", "host", "b200_system.cpp"), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+        assert "createPlugin_b200" in syms  # -DSTATIC_PLUGINS: the name plugins.inl references
+        for f in ("lb200_init", "lb200_shutdown", "lb200_synchronize"):
+            assert f in syms
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "renderer")), reason="reference tree not present")
 def test_shim_compiles_against_engine_headers():
     # the Linux port of the reference lacks an SRWLock body (src/core/sync.h:22-24, SURVEY F8): give the preprocessor the one-line
