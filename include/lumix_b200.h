@@ -150,6 +150,17 @@ typedef struct {
 LB200_API int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity,
 	lb200_cull_result* result);
 
+/* The same delivery without blocking the calling thread — the engine calls cull from job-system fibers, possibly for several views
+ * (src/renderer/pipeline.cpp:1036-1041), and a fiber must not sit in an OS wait (docs/job_system.md):
+ *   lb200_culling_cull_begin  uploads pending edits, enqueues the cull and the device-side write of ids + counts into `out_ids`
+ *                             (page-locked memory only: lb200_host_alloc) and returns at once;
+ *   lb200_culling_cull_poll   1 = finished, 0 = still running (jobs::yield() and ask again), < 0 = error;
+ *   lb200_culling_cull_end    waits if it still has to, fills `result` like lb200_culling_cull (LB200_ERR_CAPACITY as there).
+ * One begin may be outstanding per culling system. */
+LB200_API int lb200_culling_cull_begin(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity);
+LB200_API int lb200_culling_cull_poll(lb200_culling* cs);
+LB200_API int lb200_culling_cull_end(lb200_culling* cs, lb200_cull_result* result);
+
 /* Device-resident form: the same cull, result left in HBM (no D2H of ids).  *out_dev_ids receives the device pointer of the
  * id buffer: per-type segments, ids of type t at [type_offset[t], type_offset[t] + type_count[t]).  The buffer belongs to one of the
  * object's output lanes (3 by default, LB200_CULL_LANES): it stays valid through the next lanes - 1 culls, the cull after that reuses

@@ -270,6 +270,10 @@ struct lb200_culling {
 	uint32_t* d_mask = nullptr;     // lanes * mask_words
 	size_t mask_words = 0;
 	uint32_t* d_counters = nullptr; // lanes * 2 * COUNTER_WORDS: [lane][parity]
+	// asynchronous host delivery (lb200_culling_cull_begin / _poll / _end)
+	cudaEvent_t done_event = nullptr;
+	bool pending = false;
+	uint32_t pending_capacity = 0;
 	// the cull issued last
 	uint32_t* last_counters = nullptr;
 	uint32_t* last_out = nullptr;
@@ -582,6 +586,7 @@ void lb200_culling_destroy(lb200_culling* cs) {
 			if (cs->lane_event[l]) cudaEventDestroy(cs->lane_event[l]);
 		}
 		if (cs->fork_event) cudaEventDestroy(cs->fork_event);
+		if (cs->done_event) cudaEventDestroy(cs->done_event);
 		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_out_ids); cudaFree(cs->d_mask);
 		cudaFree(cs->d_counters); cudaFree(cs->d_stage); cudaFree(cs->d_gather_ids); cudaFree(cs->d_gather_counts); cudaFree(cs->d_slab);
 		if (cs->h_counters) cudaFreeHost(cs->h_counters);
@@ -724,6 +729,60 @@ int lb200_culling_cull_device_n(lb200_culling* cs, const lb200_shifted_frustum* 
 		if (rc) return rc;
 	}
 	return joinLanes(cs);
+}
+
+// ---- asynchronous form of lb200_culling_cull for callers that must not block their thread (the engine calls cull from job-system
+// fibers, src/renderer/pipeline.cpp:1036-1041: begin, then jobs::yield() while poll says "running", then end) ----
+int lb200_culling_cull_begin(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t* out_ids, uint32_t capacity) {
+	if (!cs || !frustum || !out_ids || !capacity) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	lb200_ctx* ctx = cs->ctx;
+	if (cs->pending) { lb200_set_error(ctx, "cull_begin: the previous cull_begin has not been ended"); return LB200_ERR_STATE; }
+	if (cs->host.cells.empty()) { lb200_set_error(ctx, "cull_begin on an empty culling system (cull() handles that case)"); return LB200_ERR_STATE; }
+	int rc = ensureDevice(cs);
+	if (rc) return rc;
+	cudaPointerAttributes attr = {};
+	if (!cs->h_counters_dev || cudaPointerGetAttributes(&attr, out_ids) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+		cudaGetLastError();
+		lb200_set_error(ctx, "cull_begin needs a page-locked destination (lb200_host_alloc)");
+		return LB200_ERR_INVALID;
+	}
+	if (!cs->done_event) LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->done_event, cudaEventDisableTiming));
+	rc = launchCull(cs, frustum, type);
+	if (rc) return rc;
+	PackParams PP;
+	memcpy(PP.type_base, cs->last_type_base, sizeof(PP.type_base));
+	PP.slab_ids = capacity;
+	pack_host_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(PP, cs->last_counters, cs->last_out, (uint32_t*)attr.devicePointer, cs->h_counters_dev);
+	LB200_CHECK_LAUNCH(ctx);
+	LB200_CUDA(ctx, cudaEventRecord(cs->done_event, ctx->stream));
+	cs->pending = true;
+	cs->pending_capacity = capacity;
+	cs->has_last = false;
+	return LB200_OK;
+}
+
+int lb200_culling_cull_poll(lb200_culling* cs) {
+	if (!cs || !cs->ctx) return LB200_ERR_INVALID;
+	if (!cs->pending) return 1;
+	const cudaError_t e = cudaEventQuery(cs->done_event);
+	if (e == cudaSuccess) return 1;
+	if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+	lb200_set_error(cs->ctx, "cudaEventQuery failed: %s", cudaGetErrorString(e));
+	return LB200_ERR_CUDA;
+}
+
+int lb200_culling_cull_end(lb200_culling* cs, lb200_cull_result* result) {
+	if (!cs || !result) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	lb200_ctx* ctx = cs->ctx;
+	if (!cs->pending) { lb200_set_error(ctx, "cull_end without cull_begin"); return LB200_ERR_STATE; }
+	cs->pending = false;
+	LB200_CUDA(ctx, cudaEventSynchronize(cs->done_event));
+	parseCounts(cs, result);
+	uint32_t off = 0;
+	for (int t = 0; t < 256; ++t) { result->type_offset[t] = off; off += result->type_count[t]; }
+	return result->total > cs->pending_capacity ? LB200_ERR_CAPACITY : LB200_OK;
 }
 
 int lb200_culling_last_result(lb200_culling* cs, const uint32_t** out_dev_ids, lb200_cull_result* result) {

@@ -186,6 +186,24 @@ class CullingSystem:
         # a view of the page-locked result buffer, valid until the next cull on this object (the engine shim copies it into CullResult pages)
         return CullResult(out[:res.total], res)
 
+    def cull_begin(self, frustum, type=TYPE_ALL):
+        """Non-blocking form of cull(): enqueue the cull and the device-side write of the result into the page-locked buffer."""
+        out = self._out_buffer(self.entity_count())
+        self._err(self.L.lb200_culling_cull_begin(self.h, C.byref(frustum), C.c_uint8(type), ptr(out), C.c_uint32(len(out))))
+
+    def cull_poll(self):
+        """True once the cull started by cull_begin has finished (a job would yield and ask again)."""
+        rc = self.L.lb200_culling_cull_poll(self.h)
+        if rc < 0:
+            self._err(rc)
+        return rc == 1
+
+    def cull_end(self):
+        """Result of the cull started by cull_begin (waits if it still has to): the same CullResult view cull() returns."""
+        res = _lib.CullResult()
+        self._err(self.L.lb200_culling_cull_end(self.h, C.byref(res)))
+        return CullResult(self._out[:res.total], res)
+
     def cull_device(self, frustum, type=TYPE_ALL, want_counts=True):
         """Same cull, ids stay in HBM: returns (device pointer int, lb200_cull_result or None)."""
         dev = vp()

@@ -83,7 +83,14 @@ struct CullingSystemB200 final : CullingSystem {
 		jobs::MutexGuard guard(m_mutex);
 		if (!ensureCapacity(lb200_culling_entity_count(m_cs))) return nullptr;
 		lb200_cull_result res;
-		const int rc = lb200_culling_cull(m_cs, (const lb200_shifted_frustum*)&frustum, type, m_ids, m_capacity, &res);
+		int rc;
+		if (lb200_culling_page_count(m_cs) == 0) return nullptr; // culling_system.cpp:322
+		// no OS wait inside a job (docs/job_system.md): enqueue, then give the worker back to the job system until the GPU is done
+		rc = lb200_culling_cull_begin(m_cs, (const lb200_shifted_frustum*)&frustum, type, m_ids, m_capacity);
+		if (rc == LB200_OK) {
+			while (lb200_culling_cull_poll(m_cs) == 0) jobs::yield();
+			rc = lb200_culling_cull_end(m_cs, &res);
+		}
 		if (rc != LB200_OK) { // no CPU fallback: report and return "nothing visible" (the reference's own empty result, :322)
 			logError("lumix_b200 cull failed: ", lb200_last_error(m_ctx));
 			return nullptr;

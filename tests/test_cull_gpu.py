@@ -262,3 +262,22 @@ def test_pinned_and_pageable_destinations_agree(ctx, oracle):
     rc = cs.L.lb200_culling_cull(cs.h, C.byref(f), C.c_uint8(0xFF), small.ctypes.data_as(C.c_void_p), C.c_uint32(16), C.byref(res))
     assert rc == _lib.ERR_CAPACITY and res.total == pinned.total
     cs.close()
+
+
+def test_begin_poll_end_equals_cull(ctx, oracle):
+    """The non-blocking delivery (what the engine shim uses from job fibers: begin, yield while poll is false, end) hands back exactly
+    what cull() does, for a full cull and for one renderable type."""
+    scene = scenes.cull_scene(200_000, (3000.0, 300.0, 3000.0), seed=51, big_fraction=0.004, type_probs=(0.6, 0.3, 0.1))
+    cs, oc = _both(ctx, oracle, scene)
+    f = lb.frustum_perspective(**dict(scenes.c1_frustum_args(), far=2400.0))
+    for t in (lb.culling.TYPE_ALL, 1):
+        oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f), -1 if t == lb.culling.TYPE_ALL else t)
+        cs.cull_begin(f, t)
+        spins = 0
+        while not cs.cull_poll():
+            spins += 1
+            assert spins < 10_000_000
+        res = cs.cull_end()
+        _assert_same(res, oids, otys)
+        _assert_same(cs.cull(f, t), oids, otys)
+    cs.close()
