@@ -39,3 +39,50 @@ def test_cull_sets_equal_reference_job_system(ref, workers):
         o, ro = np.argsort(ids), np.argsort(rids)
         assert np.array_equal(ids[o], rids[ro]) and np.array_equal(tys[o], rtys[ro])
         assert info["pages"] == st["pages_total"] - st["pages_filtered"]  # one result page per processed cell page (:337)
+
+
+def test_random_views_and_edits_equal_reference(ref):
+    """Randomised cross-check: small worlds with crowded and sparse cells, random perspective / ortho views (inside, outside, tangent
+    to cell borders, huge and tiny far planes, types filtered or not), with batches of moves / radius changes / removals in between.
+    The restatement must return exactly the reference's visible set every time."""
+    rng = np.random.default_rng(2024)
+    for world in range(3):
+        n = int(rng.integers(2_000, 30_000))
+        half = (float(rng.choice([250.0, 900.0, 4000.0])), float(rng.choice([50.0, 400.0])), float(rng.choice([250.0, 900.0, 4000.0])))
+        scene = scenes.cull_scene(n, half, seed=300 + world, big_fraction=float(rng.choice([0.0, 0.02, 0.3])), type_probs=(0.5, 0.25, 0.25))
+        rc, oc = ref.RefCulling(workers=1), ref.OracleCulling()
+        rc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+        oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+        alive = np.ones(n, bool)
+        pos, rad = scene["pos"].copy(), scene["radius"].copy()
+        for step in range(12):
+            p = rng.normal(size=3) * np.array(half) * 1.5
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            up = np.cross(np.cross(d, rng.normal(size=3)), d); up /= np.linalg.norm(up)
+            if step % 5 == 0:  # snapped to a cell corner, axis-aligned: planes coincide with cell faces
+                p = np.round(p / 300.0) * 300.0
+                d, up = np.array([0.0, 0.0, -1.0]), np.array([0.0, 1.0, 0.0])
+            far = float(rng.choice([30.0, 700.0, 5000.0, 60000.0]))
+            if step % 3 == 2:
+                args = (p, d.astype(np.float32), up.astype(np.float32), float(rng.uniform(10, 3000)), float(rng.uniform(10, 3000)), 0.0, far)
+                f, fr = ref.frustum_ortho(*args), ref.ref_frustum_ortho(*args)
+            else:
+                args = (p, d.astype(np.float32), up.astype(np.float32), float(rng.uniform(0.2, 2.4)), float(rng.uniform(0.5, 2.5)), float(rng.uniform(0.01, 2.0)), far)
+                f, fr = ref.frustum_perspective(*args), ref.ref_frustum_perspective(*args)
+            assert np.array_equal(f[:248], fr[:248])
+            t = int(rng.choice([-1, -1, 0, 1, 2]))
+            ids, tys, _ = oc.cull(f, t)
+            rids, rtys, info = rc.cull(fr, type=t, cap=n, iters=1)
+            assert info["count"] == len(ids), (world, step)
+            o, ro = np.argsort(ids), np.argsort(rids)
+            assert np.array_equal(ids[o], rids[ro]) and np.array_equal(tys[o], rtys[ro]), (world, step)
+            # edits between views
+            live = np.nonzero(alive)[0]
+            mv = rng.choice(live, min(len(live), 400), replace=False).astype(np.int32)
+            a, b, c = np.array_split(mv, 3)
+            pos[a] = pos[a] + rng.normal(size=(len(a), 3)) * 200.0
+            rc.set_position(a, pos[a]); oc.set_position(a, pos[a])
+            rad[b] = (rng.random(len(b)) * 500.0).astype(np.float32)
+            rc.set_radius(b, rad[b]); oc.set_radius(b, rad[b])
+            rc.remove(c); oc.remove(c)
+            alive[c] = False
