@@ -281,3 +281,45 @@ def test_begin_poll_end_equals_cull(ctx, oracle):
         _assert_same(res, oids, otys)
         _assert_same(cs.cull(f, t), oids, otys)
     cs.close()
+
+
+def test_random_views_and_edits(ctx, oracle):
+    """Randomised parity run (the same generator the oracle itself is checked with against the reference build in
+    tests/test_oracle_ref.py): worlds with crowded and sparse cells, perspective / ortho views incl. axis-aligned ones snapped to cell
+    corners, tiny and huge far planes, type filters, and batches of moves / radius changes / removals between the views."""
+    rng = np.random.default_rng(2024)
+    for world in range(3):
+        n = int(rng.integers(2_000, 30_000))
+        half = (float(rng.choice([250.0, 900.0, 4000.0])), float(rng.choice([50.0, 400.0])), float(rng.choice([250.0, 900.0, 4000.0])))
+        scene = scenes.cull_scene(n, half, seed=300 + world, big_fraction=float(rng.choice([0.0, 0.02, 0.3])), type_probs=(0.5, 0.25, 0.25))
+        cs, oc = _both(ctx, oracle, scene)
+        alive = np.ones(n, bool)
+        pos, rad = scene["pos"].copy(), scene["radius"].copy()
+        for step in range(12):
+            p = rng.normal(size=3) * np.array(half) * 1.5
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            up = np.cross(np.cross(d, rng.normal(size=3)), d); up /= np.linalg.norm(up)
+            if step % 5 == 0:
+                p = np.round(p / 300.0) * 300.0
+                d, up = np.array([0.0, 0.0, -1.0]), np.array([0.0, 1.0, 0.0])
+            far = float(rng.choice([30.0, 700.0, 5000.0, 60000.0]))
+            if step % 3 == 2:
+                f = lb.frustum_ortho(p, d.astype(np.float32), up.astype(np.float32), float(rng.uniform(10, 3000)), float(rng.uniform(10, 3000)), 0.0, far)
+            else:
+                f = lb.frustum_perspective(p, d.astype(np.float32), up.astype(np.float32), float(rng.uniform(0.2, 2.4)), float(rng.uniform(0.5, 2.5)),
+                                           float(rng.uniform(0.01, 2.0)), far)
+            t = int(rng.choice([-1, -1, 0, 1, 2]))
+            oids, otys, st = oc.cull(lb.culling.frustum_bytes(f), t)
+            res = cs.cull(f) if t < 0 else cs.cull(f, t)
+            _assert_same(res, oids, otys)
+            assert res.stats["pages_tested"] == st["pages_tested"] and res.stats["pages_inside"] == st["pages_inside"], (world, step)
+            live = np.nonzero(alive)[0]
+            mv = rng.choice(live, min(len(live), 400), replace=False).astype(np.int32)
+            a, b, c = np.array_split(mv, 3)
+            pos[a] = pos[a] + rng.normal(size=(len(a), 3)) * 200.0
+            cs.setPosition(a, pos[a]); oc.set_position(a, pos[a])
+            rad[b] = (rng.random(len(b)) * 500.0).astype(np.float32)
+            cs.setRadius(b, rad[b]); oc.set_radius(b, rad[b])
+            cs.remove(c); oc.remove(c)
+            alive[c] = False
+        cs.close()
