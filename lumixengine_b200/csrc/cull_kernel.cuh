@@ -208,7 +208,6 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 		for (uint32_t w = warp; w < n_work; w += CULL_WARPS) {
 			const WorkItem it = s_item[w];
 			const uint32_t count = it.meta & 0xffu;
-			const uint32_t type = (it.meta >> 8) & 0xffu;
 			const int cls = (int)((it.meta >> 16) & 3u);
 			const uint32_t as_test = (it.meta >> 18) & 1u;
 			const uint32_t need = it.meta >> 24;

@@ -709,7 +709,6 @@ int lb200_culling_cull_device_n(lb200_culling* cs, const lb200_shifted_frustum* 
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
 	if (cs->host.cells.empty()) return LB200_OK;
 	cs->has_last = false;
-	lb200_ctx* ctx = cs->ctx;
 	int rc = flushPages(cs); // uploads (if any) go to the context stream before the lanes fork from it
 	if (rc) return rc;
 	const uint32_t L = std::min(cs->lanes, n);
