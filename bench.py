@@ -29,6 +29,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_ENTITIES = 10_000_000
+WORKLOAD = "C2: 10M static entities, 1 camera frustum cull (BASELINE.json configs[1]); per GPU at N>1"
 REPLICAS = 8  # scene copies rotated through by successive culls: 8 x ~200 MB > 126 MB L2
 
 
@@ -140,7 +141,7 @@ def reference_arm(a, rank):
     line = {
         "impl": "reference", "metric": "M entities culled/s", "value": r["value"], "unit": "M entities/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 10M static entities, 1 camera frustum cull", "entities_per_step": N_ENTITIES, "visible": r["visible"],
+        "config": {"workload": WORKLOAD, "entities_per_step": N_ENTITIES, "visible": r["visible"],
                    "note": "one 10M shard culled on the host whatever --gpus is (bounded sample of the N-shard job)"},
         "cpu_baseline": {"value": r["value"], "unit": "M entities/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "impl": r["impl"]},
         "e2e": {"value": r["value"], "unit": "M entities/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -349,7 +350,7 @@ def ours(a, rank, world):
     line = {
         "metric": "M entities culled/s", "value": total_entities / ms_step / 1e3, "unit": "M entities/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 10M static entities, 1 camera frustum cull (BASELINE.json configs[1]); per GPU at N>1", "entities_per_gpu": N_ENTITIES,
+        "config": {"workload": WORKLOAD, "entities_per_gpu": N_ENTITIES,
                    "visible_per_gpu": int(visible), "pages": cs.page_count(), "frustum": "perspective fov 60deg 16:9 near 0.1 far 4500 at origin looking -z",
                    "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{cs.page_count() * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
                    "parallelism": f"dp{world}: whole cell pages per rank" + (("; exchanged each step: " + exchange_desc) if world > 1 else ""),
