@@ -86,3 +86,31 @@ def test_random_views_and_edits_equal_reference(ref):
             rc.set_radius(b, rad[b]); oc.set_radius(b, rad[b])
             rc.remove(c); oc.remove(c)
             alive[c] = False
+
+
+def test_random_clips_equal_reference(ref):
+    """Randomised pose pin: skeletons of 1..196 bones, clips of 1..90 frames with 3..19-bit channels (tracks up to 58 bits wide, which
+    exercises the 64-bit unpack path), any share of constant tracks; plain, weighted and chained samples, relative and absolute, against
+    the reference's own Animation::getRelativePose + Pose::computeAbsolute."""
+    rng = np.random.default_rng(99)
+    for trial in range(25):
+        bones = int(rng.choice([1, 2, 3, 4, 5, 7, 16, 33, 64, 100, 196]))
+        frames = int(rng.integers(1, 91))
+        pb = tuple(int(x) for x in rng.integers(3, 20, 3))
+        rb = tuple(int(x) for x in rng.integers(3, 20, 3))
+        sk = scenes.skeleton(bones, seed=500 + trial)
+        clip = scenes.clip(sk, frames=frames, fps=float(rng.choice([1.0, 24.0, 30.0, 59.94])), seed=600 + trial, pos_bits=pb, rot_bits=rb,
+                           const_fraction=float(rng.choice([0.0, 0.25, 1.0])))
+        other = scenes.clip(sk, frames=int(rng.integers(1, 40)), seed=700 + trial, const_fraction=0.5)
+        L = clip.length_ticks
+        for t in [0, 1, max(L - 1, 0), L, L + 5000] + [int(x) for x in rng.integers(0, max(L, 1), 6)]:
+            for absolute in (False, True):
+                a = np.concatenate(ref.pose_evaluate(sk, clip, t, compute_absolute=absolute), axis=1)
+                b = np.concatenate(ref.ref_pose_evaluate(sk, clip, t, compute_absolute=absolute), axis=1)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (trial, t, absolute)
+            rel = ref.pose_evaluate(sk, clip, t, compute_absolute=False)
+            w = float(rng.choice([0.0, 0.3, 0.9998, 0.9999, 1.0]))
+            t2 = int(rng.integers(0, max(other.length_ticks, 1)))
+            a = np.concatenate(ref.pose_evaluate(sk, other, t2, weight=w, start_from_bind=False, compute_absolute=True, pos=rel[0], rot=rel[1]), axis=1)
+            b = np.concatenate(ref.ref_pose_evaluate(sk, other, t2, weight=w, start_from_bind=False, compute_absolute=True, pos=rel[0], rot=rel[1]), axis=1)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (trial, t, w)
