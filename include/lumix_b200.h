@@ -326,7 +326,8 @@ LB200_API void lb200_animation_destroy(lb200_animation* a);
 /* Per-instance state: Animable{time, animation}, animation_module.h:17-21.  time in Time ticks (1 s = 32768, animation.h:17-43). */
 LB200_API int lb200_animation_set_instances(lb200_animation* a, const uint32_t* clip_index, const uint32_t* time_ticks, uint32_t n);
 /* One updateAnimables pass (animation_module.cpp:737-749) for all instances: evaluate at the current time, build the requested
- * palettes in HBM, then advance time by time_delta seconds (time = (time + dt) % length, :458-461). */
+ * palettes in HBM, then step the time as :458-469 do: time_delta > 0: (time + dt) % length; otherwise (rewind, and zero):
+ * (time + length - (-dt % length)) % length — a time already below the clip length is left alone by a zero step. */
 LB200_API int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t palette_flags);
 /* evaluateSkin (model.cpp:103-109) for every vertex of every instance from the matrix palette; output stays in HBM. */
 LB200_API int lb200_animation_skin(lb200_animation* a);

@@ -764,9 +764,11 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	P.out_pos = (flags & LB200_PALETTE_POSE) ? a->d_pos : nullptr;
 	P.out_rot = (flags & LB200_PALETTE_POSE) ? a->d_rot : nullptr;
 	// Time::fromSeconds: u32(time * ONE_SECOND), animation.h:21-24 (:462 uses -time_delta for rewinds)
-	P.dt_negative = time_delta < 0;
+	// animation_module.cpp:458 `if (time_delta > 0) ... else ...`: zero takes the rewind branch too, which leaves a time below the clip
+	// length alone and wraps one at or beyond it (time % length), exactly as the reference does on every update
+	P.dt_negative = !(time_delta > 0);
 	P.dt_ticks = (uint32_t)((P.dt_negative ? -time_delta : time_delta) * (float)(1 << 15));
-	P.advance = time_delta != 0;
+	P.advance = 1;
 	static const int g_env = [] { const char* e = getenv("LB200_POSE_LANES"); const int v = e ? atoi(e) : 0; return (v == 8 || v == 16 || v == 32) ? v : 0; }();
 	const int G = g_env ? g_env : a->lanes_per_instance;
 	const unsigned per_block = POSE_THREADS / G;

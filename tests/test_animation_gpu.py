@@ -180,3 +180,34 @@ def test_blend_layers_match_oracle(ctx, oracle):
     exp = oracle.animate_instances(sk, clips, ci, tt)
     _close(anim.getPose()[0], exp["pos"], "pose.pos after removing layers")
     anim.close()
+
+
+def test_random_skeletons_and_clips(ctx, oracle):
+    """Randomised parity run: 1..196 bones, 1..90 frames, 5..18-bit channels, any share of constant tracks, several clips per system,
+    times inside / at / beyond the clip end; pose, both palettes and the advanced time against the oracle."""
+    rng = np.random.default_rng(123)
+    for trial in range(10):
+        bones = int(rng.choice([1, 2, 3, 5, 16, 33, 64, 100, 196]))
+        sk = scenes.skeleton(bones, seed=800 + trial)
+        clips = []
+        for c in range(int(rng.integers(1, 4))):
+            pb = tuple(int(x) for x in rng.integers(5, 19, 3))
+            rb = tuple(int(x) for x in rng.integers(5, 19, 3))
+            clips.append(scenes.clip(sk, frames=int(rng.integers(1, 91)), fps=float(rng.choice([1.0, 24.0, 30.0, 59.94])), seed=900 + 10 * trial + c,
+                                     pos_bits=pb, rot_bits=rb, const_fraction=float(rng.choice([0.0, 0.25, 1.0]))))
+        n_inst = int(rng.integers(1, 400))
+        ci = rng.integers(0, len(clips), n_inst).astype(np.uint32)
+        lengths = np.array([c.length_ticks for c in clips], np.int64)
+        tt = (rng.random(n_inst) * (lengths[ci] + 3)).astype(np.uint32)  # a few at or past the end: clamped by frame_count - 1e-5
+        tt[:3] = [0, 1, int(lengths[ci[2 % n_inst]])][:min(3, n_inst)] if n_inst >= 3 else tt[:3]
+        anim = lb.AnimationSystem(ctx, sk, clips, None, max_instances=n_inst)
+        anim.setInstances(ci, tt)
+        dt = float(rng.choice([0.0, 1.0 / 60.0, 0.75]))
+        anim.update(dt, lb.PALETTE_DUAL_QUAT | lb.PALETTE_MATRIX | lb.PALETTE_POSE)
+        exp = oracle.animate_instances(sk, clips, ci, tt)
+        pos, rot = anim.getPose()
+        _close(pos, exp["pos"], f"trial {trial} pose.pos"); _close(rot, exp["rot"], f"trial {trial} pose.rot")
+        _close(anim.getDualQuats(), exp["dq"], f"trial {trial} dual quats"); _close(anim.getMatrices(), exp["mtx"], f"trial {trial} matrices")
+        want = np.array([oracle.time_advance(t, dt, clips[c].fps, clips[c].frame_count) for c, t in zip(ci, tt)], np.uint32)
+        assert np.array_equal(anim.getTimes(), want), trial
+        anim.close()
