@@ -744,6 +744,7 @@ int lb200_animation_set_instances(lb200_animation* a, const uint32_t* clip_index
 }
 
 int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags) {
+	lb200_range range("update animables"); // animation_module.cpp:743
 	if (!a) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = a->ctx;
 	if (!a->n_instances) return LB200_OK;
@@ -785,6 +786,7 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 }
 
 int lb200_animation_skin(lb200_animation* a) {
+	lb200_range range("skin");
 	if (!a) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = a->ctx;
 	if (!a->n_vertices || !a->d_mtx) { lb200_set_error(ctx, "skin needs a mesh and a matrix palette (update with LB200_PALETTE_MATRIX first)"); return LB200_ERR_STATE; }

@@ -434,6 +434,7 @@ void cullGeometry(const lb200_culling* cs, uint32_t grid, uint32_t n_pages, uint
 struct Exchange { uint32_t epoch; }; // non-null: store mask rows + counts into every rank's slab (peer memory); lane = epoch % lanes
 
 int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, const Exchange* xchg = nullptr, cudaStream_t stream = nullptr) {
+	lb200_range range("culling"); // culling_system.cpp:330
 	lb200_ctx* ctx = cs->ctx;
 	lb::CullingHost& h = cs->host;
 	const bool had_dirty = h.all_dirty || !h.dirty_list.empty() || !cs->d_counters;

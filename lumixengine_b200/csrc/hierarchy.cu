@@ -307,6 +307,7 @@ int lb200_hierarchy_set_root_globals(lb200_hierarchy* h, const lb200_transform* 
 
 int lb200_hierarchy_propagate(lb200_hierarchy* h) {
 	if (!h) return LB200_ERR_INVALID;
+	lb200_range range("transform hierarchy"); // World::transformEntity, world.cpp:255
 	lb200_ctx* ctx = h->ctx;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	const size_t n_levels = h->level_start.size() - 1;

@@ -4,6 +4,7 @@
 #include "../../include/lumix_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only; a no-op unless a tool (ncu, nsys) injects itself
 
 #include <atomic>
 #include <stdarg.h>
@@ -43,6 +44,15 @@ struct lb200_ctx {
 };
 
 void lb200_set_error(lb200_ctx* ctx, const char* fmt, ...);
+
+// NVTX range named like the reference's PROFILE_BLOCK / PROFILE_FUNCTION scopes (culling_system.cpp:330 "culling",
+// animation_module.cpp:743 "update animables"), so that a timeline of the engine with this library reads like the reference's own.
+struct lb200_range {
+	explicit lb200_range(const char* name) { nvtxRangePushA(name); }
+	~lb200_range() { nvtxRangePop(); }
+	lb200_range(const lb200_range&) = delete;
+	lb200_range& operator=(const lb200_range&) = delete;
+};
 uint32_t lb200_cull_lanes(); // LB200_CULL_LANES, default 3, 1..LB200_MAX_LANES (context.cu)
 
 #define LB200_CUDA(ctx, expr)                                                                        \
