@@ -115,6 +115,10 @@ LB200_API int lb200_culling_is_added(const lb200_culling* cs, int32_t entity);
 /* batch forms of the same calls (one FFI crossing for n entities) */
 LB200_API int lb200_culling_add_many(lb200_culling* cs, const int32_t* entities, const uint8_t* types, const double* pos3, const float* radius, uint32_t n);
 LB200_API int lb200_culling_set_many(lb200_culling* cs, const int32_t* entities, const double* pos3, const float* radius, uint32_t n);
+/* set() for n DISTINCT entities, e.g. the sphere refresh after a hierarchy propagate (render_module.cpp:1544-1554): movers that stay in
+ * their cell are overwritten in place on all host cores, the others go through set() one by one in the given order.  Same final state
+ * as lb200_culling_set_many; an entity listed twice is undefined behaviour here. */
+LB200_API int lb200_culling_set_many_unique(lb200_culling* cs, const int32_t* entities, const double* pos3, const float* radius, uint32_t n);
 LB200_API int lb200_culling_set_position_many(lb200_culling* cs, const int32_t* entities, const double* pos3, uint32_t n);
 LB200_API int lb200_culling_set_radius_many(lb200_culling* cs, const int32_t* entities, const float* radius, uint32_t n);
 LB200_API int lb200_culling_remove_many(lb200_culling* cs, const int32_t* entities, uint32_t n);

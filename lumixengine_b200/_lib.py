@@ -90,7 +90,7 @@ SYMBOLS = [
     "lb200_frustum_perspective", "lb200_frustum_ortho", "lb200_frustum_from_viewport",
     "lb200_culling_create", "lb200_culling_destroy", "lb200_culling_add", "lb200_culling_remove", "lb200_culling_set_position",
     "lb200_culling_set_radius", "lb200_culling_set", "lb200_culling_get_radius", "lb200_culling_is_added",
-    "lb200_culling_add_many", "lb200_culling_set_many", "lb200_culling_set_position_many", "lb200_culling_set_radius_many", "lb200_culling_remove_many",
+    "lb200_culling_add_many", "lb200_culling_set_many", "lb200_culling_set_many_unique", "lb200_culling_set_position_many", "lb200_culling_set_radius_many", "lb200_culling_remove_many",
     "lb200_culling_page_count", "lb200_culling_entity_count", "lb200_culling_get_page",
     "lb200_culling_cull", "lb200_culling_cull_begin", "lb200_culling_cull_poll", "lb200_culling_cull_end", "lb200_culling_cull_device", "lb200_culling_cull_device_n", "lb200_culling_last_result", "lb200_culling_flush", "lb200_culling_read_bitmask", "lb200_culling_set_replicas",
     "lb200_culling_last_algorithmic_bytes",

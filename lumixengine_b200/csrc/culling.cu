@@ -624,6 +624,11 @@ int lb200_culling_set_many(lb200_culling* cs, const int32_t* entities, const dou
 	}
 	return LB200_OK;
 }
+int lb200_culling_set_many_unique(lb200_culling* cs, const int32_t* entities, const double* pos3, const float* radius, uint32_t n) {
+	if (!cs || (n && (!entities || !pos3 || !radius))) return LB200_ERR_INVALID;
+	return cs->host.setManyUnique(entities, pos3, radius, n);
+}
+
 int lb200_culling_set_position_many(lb200_culling* cs, const int32_t* entities, const double* pos3, uint32_t n) {
 	if (!cs || (n && (!entities || !pos3))) return LB200_ERR_INVALID;
 	for (uint32_t i = 0; i < n; ++i) {

@@ -9,6 +9,7 @@
 #include "lb200_internal.h"
 
 #include <stdlib.h>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -291,6 +292,58 @@ struct CullingHost {
 		const uint8_t type = desc[cell].type;
 		remove(entity);
 		return add(entity, type, pos, radius);
+	}
+
+	// Batch form of set() for DISTINCT entities (the sphere refresh after a hierarchy propagate, render_module.cpp:1544-1554, touches every
+	// moved entity once).  Most movers stay inside their cell and on the same side of the is_big threshold: those are plain overwrites of
+	// their own slot, independent of each other, and run on all host cores; the rest — cell or chain changes, which rewire pages — then
+	// run one by one in their original order through set().  In-cell overwrites do not touch the page structure and carry their data
+	// along when a later swap-with-last moves them, so the final state is the one the sequential loop produces (tests/test_culling_host.py).
+	int setManyUnique(const int32_t* ents, const double* pos3, const float* radius, uint32_t n) {
+		for (uint32_t i = 0; i < n; ++i) if (!isAdded(ents[i])) return LB200_ERR_INVALID;
+		unsigned workers = std::thread::hardware_concurrency();
+		workers = workers > 32 ? 32 : (workers < 1 ? 1 : workers);
+		if (n < 32768) workers = 1;
+		std::vector<std::vector<uint32_t>> dirty(workers), slow(workers);
+		std::vector<long long> bad_delta(workers, 0);
+		auto run = [&](unsigned w) {
+			const uint32_t begin = (uint32_t)((uint64_t)n * w / workers), end = (uint32_t)((uint64_t)n * (w + 1) / workers);
+			for (uint32_t i = begin; i < end; ++i) {
+				const uint32_t slot = entity_to_slot[ents[i]];
+				const uint32_t cell = slot / PAGE_SLOTS;
+				const double* pos = pos3 + 3 * (size_t)i;
+				const CellKey nk = makeKey(pos, 0, false);
+				const bool was_big = desc[cell].is_big != 0;
+				const bool is_big = radius[i] > LB200_CELL_SIZE;
+				if (was_big != is_big || !sameCell(nk, keys[cell])) { slow[w].push_back(i); continue; }
+				float* s = spheres + 4 * (size_t)slot;
+				bad_delta[w] += (badRadius(radius[i]) ? 1 : 0) - (badRadius(s[3]) ? 1 : 0);
+				s[3] = radius[i];
+				s[0] = (float)(pos[0] - desc[cell].origin[0]);
+				s[1] = (float)(pos[1] - desc[cell].origin[1]);
+				s[2] = (float)(pos[2] - desc[cell].origin[2]);
+				// read first: once a page is flagged its line stays shared between the cores instead of bouncing on every mover
+				if (!__atomic_load_n(&dirty_flag[cell], __ATOMIC_RELAXED) && !__atomic_exchange_n(&dirty_flag[cell], (uint8_t)1, __ATOMIC_RELAXED)) dirty[w].push_back(cell);
+			}
+		};
+		if (workers == 1) run(0);
+		else {
+			std::vector<std::thread> pool;
+			for (unsigned w = 1; w < workers; ++w) pool.emplace_back(run, w);
+			run(0);
+			for (std::thread& t : pool) t.join();
+		}
+		for (unsigned w = 0; w < workers; ++w) {
+			dirty_list.insert(dirty_list.end(), dirty[w].begin(), dirty[w].end());
+			n_bad_radius = (uint32_t)((long long)n_bad_radius + bad_delta[w]);
+		}
+		for (unsigned w = 0; w < workers; ++w) {
+			for (uint32_t i : slow[w]) {
+				const int rc = set(ents[i], pos3 + 3 * (size_t)i, radius[i]);
+				if (rc) return rc;
+			}
+		}
+		return LB200_OK;
 	}
 
 	// culling_system.cpp:242-258

@@ -136,11 +136,14 @@ class CullingSystem:
         r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), e.shape))
         self._err(self.L.lb200_culling_set_radius_many(self.h, ptr(e), ptr(r), C.c_uint32(len(e))))
 
-    def set(self, entity, pos, radius):
+    def set(self, entity, pos, radius, unique=False):
+        """CullingSystem::set for one entity or a batch.  unique=True promises that no entity is listed twice (the sphere refresh after a
+        propagate): in-cell movers are then overwritten in place on all host cores (lb200_culling_set_many_unique)."""
         e = np.atleast_1d(np.asarray(entity, np.int32))
         p = np.ascontiguousarray(np.asarray(pos, np.float64).reshape(-1, 3))
         r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), e.shape))
-        self._err(self.L.lb200_culling_set_many(self.h, ptr(e), ptr(p), ptr(r), C.c_uint32(len(e))))
+        f = self.L.lb200_culling_set_many_unique if unique else self.L.lb200_culling_set_many
+        self._err(f(self.h, ptr(e), ptr(p), ptr(r), C.c_uint32(len(e))))
 
     def getRadius(self, entity):
         return float(self.L.lb200_culling_get_radius(self.h, C.c_int32(entity)))

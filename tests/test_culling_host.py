@@ -120,3 +120,33 @@ def test_page_churn_in_crowded_cells(oracle):
         peak_pages = max(peak_pages, cs.page_count())
     ids = cs.page_ids()
     assert len(set(ids.tolist())) == len(ids) and ids.max() < peak_pages + 8  # freed ids come back instead of growing the device arrays
+
+
+def test_parallel_set_of_distinct_entities_equals_sequential(oracle):
+    """lb200_culling_set_many_unique: in-cell movers are overwritten on all host cores, the rest re-bin sequentially; the state after it
+    must be the one the one-by-one loop (and the oracle) produces — including entities that a later swap-with-last relocates."""
+    import time
+    rng = np.random.default_rng(5)
+    n = 400_000
+    scene = scenes.cull_scene(n, (3000.0, 300.0, 3000.0), seed=9, big_fraction=0.002, type_probs=(0.6, 0.4))
+    a, b, oc = lb.CullingSystem(None), lb.CullingSystem(None), oracle.OracleCulling()
+    for c in (a, b, oc):
+        c.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    pos, rad = scene["pos"].copy(), scene["radius"].copy()
+    for step in range(3):
+        ids = rng.permutation(n)[: 300_000].astype(np.int32)  # distinct
+        step_len = np.where(rng.random(len(ids)) < 0.9, 2.0, 250.0)[:, None]  # 10 % are likely to leave their cell
+        pos[ids] = pos[ids] + rng.normal(size=(len(ids), 3)) * step_len
+        flip = rng.random(len(ids)) < 0.01
+        rad[ids[flip]] = np.where(rad[ids[flip]] > 300.0, 3.0, 450.0).astype(np.float32)  # crosses the is_big threshold
+        t0 = time.perf_counter(); a.set(ids, pos[ids], rad[ids], unique=True); t_par = time.perf_counter() - t0
+        t0 = time.perf_counter(); b.set(ids, pos[ids], rad[ids]); t_seq = time.perf_counter() - t0
+        oc.set(ids, pos[ids], rad[ids])
+        _same_state(a, oc)
+        _same_state(b, oc)
+        print(f"set of {len(ids)} movers: parallel {t_par * 1e3:.1f} ms, sequential {t_seq * 1e3:.1f} ms")
+    # small batches take the sequential path inside the same entry point
+    ids = rng.permutation(n)[:1000].astype(np.int32)
+    pos[ids] += 50.0
+    a.set(ids, pos[ids], rad[ids], unique=True); oc.set(ids, pos[ids], rad[ids])
+    _same_state(a, oc)
