@@ -132,6 +132,20 @@ def run_cpu_worker(args, timeout=900):
     raise RuntimeError("cpu baseline worker failed: " + out.stderr[-2000:])
 
 
+def attach_path_baselines(paths):
+    """CPU figures for the secondary stages, timed on the host next to the GPU ones: the serial restatements of
+    World::transformEntity, updateAnimable + palettes and evaluateSkin (kind "port": the reference itself is serial on these paths or
+    cannot be linked here), on bounded samples.  Never fatal."""
+    try:
+        pr = run_cpu_worker(["--workload", "propagate", "--n", "1000000", "--steps", "5"], timeout=300)
+        paths["propagate_1m_depth8"]["cpu_baseline"] = {"value": pr["value"], "unit": pr["unit"], "cores": pr["cores"], "kind": pr["kind"], "sample": pr["sample"]}
+        an = run_cpu_worker(["--workload", "anim", "--n", "10000"], timeout=300)
+        for key, part in (("pose_palette_100k_x64", "pose"), ("skin_100k_x5k", "skin")):
+            paths[key]["cpu_baseline"] = {"value": an[part]["value"], "unit": an[part]["unit"], "cores": an["cores"], "kind": an["kind"], "sample": an[part]["sample"]}
+    except Exception as e:  # the GPU numbers stand on their own
+        paths["cpu_baseline_error"] = repr(e)
+
+
 def reference_arm(a, rank):
     """The reference's own CPU implementation (oracle/_ref) on the host cores; rank 0 only."""
     if rank != 0:
@@ -372,6 +386,7 @@ def ours(a, rank, world):
             line["paths"] = secondary_paths(ctx, lb, scenes, peak, a.steps, a.warmup)
             sk = line["paths"]["skin_100k_x5k"]
             line["secondary"] = {"metric": "M skinned verts/s", "value": sk["value"], "unit": sk["unit"], "roofline_frac": sk["roofline"]["frac"]}
+            attach_path_baselines(line["paths"])
         except Exception as e:  # the headline number stands on its own
             line["paths_error"] = repr(e)
         try:
