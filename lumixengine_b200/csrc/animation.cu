@@ -639,6 +639,8 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 
 	lb200_animation* a = new (std::nothrow) lb200_animation;
 	if (!a) return LB200_ERR_CUDA;
+	// any early return below (allocation or copy failure) releases what has been allocated so far
+	struct Guard { lb200_animation* a; ~Guard() { if (a) lb200_animation_destroy(a); } } guard{a};
 	a->ctx = ctx; a->bone_count = B; a->max_level = max_level; a->n_clips = n_clips; a->max_instances = max_instances;
 	a->first_nonroot = first;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -678,7 +680,7 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_level_start, level_start.data(), sizeof(uint32_t) * level_start.size(), cudaMemcpyHostToDevice, st));
 	if (mesh && mesh->n_vertices) {
 		a->n_vertices = mesh->n_vertices;
-		for (uint32_t v = 0; v < mesh->n_vertices * 4; ++v) if (mesh->indices4[v] < 0 || (uint32_t)mesh->indices4[v] >= B) { lb200_animation_destroy(a); return LB200_ERR_INVALID; }
+		for (uint32_t v = 0; v < mesh->n_vertices * 4; ++v) if (mesh->indices4[v] < 0 || (uint32_t)mesh->indices4[v] >= B) return LB200_ERR_INVALID;
 		ANIM_MALLOC(a->d_mesh_pos, sizeof(float) * 3 * mesh->n_vertices);
 		ANIM_MALLOC(a->d_mesh_w, sizeof(float4) * mesh->n_vertices);
 		ANIM_MALLOC(a->d_mesh_idx, sizeof(short) * 4 * mesh->n_vertices);
@@ -715,6 +717,7 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 196 * 3 * sizeof(float4))));
 	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 196 * 3 * sizeof(float4))));
 	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * 196 * 3 * sizeof(float4))));
+	guard.a = nullptr;
 	*out = a;
 	return LB200_OK;
 }
