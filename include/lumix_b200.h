@@ -354,6 +354,12 @@ LB200_API int lb200_animation_get_relative_pose(lb200_animation* a, uint32_t fir
  * positions a*(1-w) + b*w, rotations scalar nlerp.  relative != 0 blends the parent-relative buffers of compute_relative, else the
  * absolute ones.  Both systems: same context, skeleton size and instance count. */
 LB200_API int lb200_animation_blend_pose(lb200_animation* a, const lb200_animation* b, float weight, int relative);
+/* RenderModuleImpl::updateBoneAttachment (src/renderer/render_module.cpp:377-405) for n attachments at once: entity i
+ * follows bone bone[i] of instance instance[i] (absolute poses of the last update with LB200_PALETTE_POSE):
+ * out[i] = parent_transforms[i].compose(bone_transform * relative7[i]) (math.cpp:763, 859-861) with scale = original_scale3[i].
+ * Host arrays in, host transforms out (the engine then feeds them to World::setTransform / the batched propagate). */
+LB200_API int lb200_animation_bone_attachments(lb200_animation* a, uint32_t n, const uint32_t* instance, const uint32_t* bone, const float* relative7,
+                                               const lb200_transform* parent_transforms, const float* original_scale3, lb200_transform* out_transforms);
 LB200_API int lb200_animation_get_times(lb200_animation* a, uint32_t first, uint32_t count, uint32_t* out_ticks);
 LB200_API int lb200_animation_get_skinned(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3);
 /* Checksum of the skinned vertex buffer computed on the device (sum of the raw u32 bit patterns, mod 2^64) —

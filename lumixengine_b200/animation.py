@@ -359,6 +359,19 @@ class AnimationSystem:
         assert ci.shape == tt.shape == w.shape
         check(self.L.lb200_animation_set_layers(self.h, C.c_uint32(ci.shape[1]), ptr(ci), ptr(tt), ptr(w)), self.ctx.h)
 
+    def boneAttachments(self, instance, bone, relative7, parent_transforms, original_scale3):
+        """updateBoneAttachment (render_module.cpp:377-405) for a batch: world Transforms of entities attached to posed bones."""
+        from .hierarchy import TRANSFORM_DTYPE
+        inst = np.ascontiguousarray(instance, np.uint32)
+        bn = np.ascontiguousarray(bone, np.uint32)
+        rel = np.ascontiguousarray(relative7, np.float32).reshape(-1, 7)
+        par = np.ascontiguousarray(parent_transforms, TRANSFORM_DTYPE)
+        sc = np.ascontiguousarray(original_scale3, np.float32).reshape(-1, 3)
+        assert len(inst) == len(bn) == len(rel) == len(par) == len(sc)
+        out = np.empty(len(inst), TRANSFORM_DTYPE)
+        check(self.L.lb200_animation_bone_attachments(self.h, C.c_uint32(len(inst)), ptr(inst), ptr(bn), ptr(rel), ptr(par), ptr(sc), ptr(out)), self.ctx.h)
+        return out
+
     def computeRelative(self):
         """Pose::computeRelative (pose.cpp:136-146) of every instance's absolute pose (update with PALETTE_POSE first)."""
         check(self.L.lb200_animation_compute_relative(self.h), self.ctx.h)

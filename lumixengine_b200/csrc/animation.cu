@@ -515,6 +515,36 @@ __global__ void __launch_bounds__(256) pose_blend_kernel(float* __restrict__ pos
 	rot_a[4 * i] = LB_FMUL(q.x, l); rot_a[4 * i + 1] = LB_FMUL(q.y, l); rot_a[4 * i + 2] = LB_FMUL(q.z, l); rot_a[4 * i + 3] = LB_FMUL(q.w, l);
 }
 
+// RenderModuleImpl::updateBoneAttachment (render_module.cpp:377-405) for a batch of attachments: the attached entity follows a bone of a
+// posed model instance — world transform = parent_entity_transform.compose(bone_transform * relative_transform) (math.cpp:763, 859-861),
+// scale replaced by the entity's own.  One thread per attachment; the bone comes from the absolute pose this system keeps in HBM.
+__global__ void __launch_bounds__(256) bone_attachments_kernel(const float* __restrict__ abs_pos, const float* __restrict__ abs_rot, uint32_t bone_count,
+	const uint32_t* __restrict__ instance, const uint32_t* __restrict__ bone, const float* __restrict__ relative7,
+	const lb200_transform* __restrict__ parent_tr, const float* __restrict__ original_scale3, uint32_t n, lb200_transform* __restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const size_t bi = (size_t)instance[i] * bone_count + bone[i];
+	Rigid b;
+	b.pos = v3(abs_pos[3 * bi], abs_pos[3 * bi + 1], abs_pos[3 * bi + 2]);
+	b.rot = q4(abs_rot[4 * bi], abs_rot[4 * bi + 1], abs_rot[4 * bi + 2], abs_rot[4 * bi + 3]);
+	const float* r = relative7 + 7 * (size_t)i;
+	Rigid rel;
+	rel.pos = v3(r[0], r[1], r[2]);
+	rel.rot = q4(r[3], r[4], r[5], r[6]);
+	const Rigid local = rmul(b, rel); // LocalRigidTransform::operator*, math.cpp:859-861
+	const lb200_transform p = parent_tr[i];
+	const Q4 prot = q4(p.rot[0], p.rot[1], p.rot[2], p.rot[3]);
+	// Transform::compose(const LocalRigidTransform&), math.cpp:763: pos + rot.rotate(rhs.pos * scale) in fp32, added to the fp64 position
+	const V3 rotated = rotate(prot, mul(local.pos, v3(p.scale[0], p.scale[1], p.scale[2])));
+	const Q4 rot = qmul(prot, local.rot);
+	lb200_transform o;
+	o.pos[0] = LB_DADD(p.pos[0], (double)rotated.x); o.pos[1] = LB_DADD(p.pos[1], (double)rotated.y); o.pos[2] = LB_DADD(p.pos[2], (double)rotated.z);
+	o.rot[0] = rot.x; o.rot[1] = rot.y; o.rot[2] = rot.z; o.rot[3] = rot.w;
+	o.scale[0] = original_scale3[3 * (size_t)i]; o.scale[1] = original_scale3[3 * (size_t)i + 1]; o.scale[2] = original_scale3[3 * (size_t)i + 2];
+	out[i] = o;
+}
+
 } // namespace
 
 struct lb200_animation {
@@ -845,6 +875,40 @@ int lb200_animation_set_layers(lb200_animation* a, uint32_t n_layers, const uint
 	LB200_CUDA(ctx, cudaMemcpyAsync(a->d_layer_weight, weight, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	a->n_layers = n_layers;
+	return LB200_OK;
+}
+
+int lb200_animation_bone_attachments(lb200_animation* a, uint32_t n, const uint32_t* instance, const uint32_t* bone, const float* relative7,
+	const lb200_transform* parent_transforms, const float* original_scale3, lb200_transform* out_transforms)
+{
+	if (!a || !n || !instance || !bone || !relative7 || !parent_transforms || !original_scale3 || !out_transforms) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = a->ctx;
+	if (!a->d_pos || !a->n_instances) { lb200_set_error(ctx, "bone_attachments needs absolute poses (update with LB200_PALETTE_POSE)"); return LB200_ERR_STATE; }
+	for (uint32_t i = 0; i < n; ++i) {
+		if (instance[i] >= a->n_instances || bone[i] >= a->bone_count) { lb200_set_error(ctx, "attachment %u: instance %u / bone %u out of range", i, instance[i], bone[i]); return LB200_ERR_INVALID; }
+	}
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	// one staging allocation per call: [instance n][bone n][relative 7n][scale 3n] u32/f32, [parent n][out n] transforms
+	const size_t words = (size_t)n * (1 + 1 + 7 + 3);
+	uint32_t* d_words = nullptr;
+	lb200_transform* d_tr = nullptr;
+	LB200_CUDA(ctx, cudaMalloc(&d_words, sizeof(uint32_t) * words));
+	if (cudaMalloc(&d_tr, sizeof(lb200_transform) * 2 * (size_t)n) != cudaSuccess) { cudaGetLastError(); cudaFree(d_words); lb200_set_error(ctx, "bone_attachments: out of device memory"); return LB200_ERR_CUDA; }
+	cudaError_t e = cudaMemcpyAsync(d_words, instance, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_words + n, bone, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_words + 2 * (size_t)n, relative7, sizeof(float) * 7 * n, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_words + 9 * (size_t)n, original_scale3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_tr, parent_transforms, sizeof(lb200_transform) * n, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) {
+		bone_attachments_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a->d_pos, a->d_rot, a->bone_count, d_words, d_words + n,
+			reinterpret_cast<const float*>(d_words + 2 * (size_t)n), d_tr, reinterpret_cast<const float*>(d_words + 9 * (size_t)n), n, d_tr + n);
+		ctx->launches.fetch_add(1, std::memory_order_relaxed);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out_transforms, d_tr + n, sizeof(lb200_transform) * n, cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d_words); cudaFree(d_tr);
+	if (e != cudaSuccess) { lb200_set_error(ctx, "bone_attachments failed: %s", cudaGetErrorString(e)); return LB200_ERR_CUDA; }
 	return LB200_OK;
 }
 

@@ -58,6 +58,11 @@ void oracle_sphere_radius(const OTransform* globals, const float* bounding_radiu
  * locals[i] = Transform::computeLocal(globals[parents[i]], globals[i]) (math.cpp:809-816); roots keep locals[i] untouched. */
 void oracle_compute_locals(const int32_t* parents, const OTransform* globals, OTransform* locals, uint32_t n);
 void oracle_transform_compute_local(const OTransform* parent, const OTransform* child, OTransform* out, uint32_t n);
+/* RenderModuleImpl::updateBoneAttachment (render_module.cpp:377-405): world transform of an entity attached to a bone of a posed model
+ * instance = parent_entity_transform.compose(bone_transform * relative_transform), scale replaced by the entity's own.
+ * bone7 / relative7: pos xyz + rot xyzw per attachment. */
+void oracle_bone_attachments(const OTransform* parent_transforms, const float* bone7, const float* relative7, const float* original_scale3,
+	OTransform* out, uint32_t n);
 /* world.cpp:370-377 World::getRelativeMatrix: rot.toMatrix(), translation = Vec3(pos - base_pos), multiply3x3(scale) */
 void oracle_relative_matrices(const OTransform* globals, const double* base_pos3, OMatrix* out, uint32_t n);
 

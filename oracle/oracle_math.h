@@ -161,6 +161,16 @@ static inline OTransform otransform_compute_local(const OTransform* parent, cons
 	return r;
 }
 
+/* math.cpp:763 Transform::compose(const LocalRigidTransform&): { pos + rot.rotate(rhs.pos * scale), rot * rhs.rot, scale } —
+ * Vec3 * Vec3 (math.cpp:459) and Quat::rotate(Vec3) in fp32, then DVec3 + Vec3 (math.cpp:512) */
+static inline OTransform otransform_compose_rigid(const OTransform* a, OVec3 rhs_pos, OQuat rhs_rot) {
+	OTransform r;
+	r.pos = odv3_addf(a->pos, oquat_rotate(a->rot, ov3_mul(rhs_pos, a->scale)));
+	r.rot = oquat_mul(a->rot, rhs_rot);
+	r.scale = a->scale;
+	return r;
+}
+
 /* math.cpp:859-861 LocalRigidTransform::operator* */
 static inline OLocalRigidTransform olrt_mul(OLocalRigidTransform a, OLocalRigidTransform b) {
 	OLocalRigidTransform r;

@@ -79,3 +79,19 @@ void oracle_compute_locals(const int32_t* parents, const OTransform* globals, OT
 void oracle_transform_compute_local(const OTransform* parent, const OTransform* child, OTransform* out, uint32_t n) {
 	for (uint32_t i = 0; i < n; ++i) out[i] = otransform_compute_local(&parent[i], &child[i]);
 }
+
+/* render_module.cpp:399-403 */
+void oracle_bone_attachments(const OTransform* parent_transforms, const float* bone7, const float* relative7, const float* original_scale3,
+	OTransform* out, uint32_t n)
+{
+	for (uint32_t i = 0; i < n; ++i) {
+		const float* b = bone7 + 7 * (size_t)i;
+		const float* r = relative7 + 7 * (size_t)i;
+		const OLocalRigidTransform bone = {ov3(b[0], b[1], b[2]), oquat(b[3], b[4], b[5], b[6])};
+		const OLocalRigidTransform rel = {ov3(r[0], r[1], r[2]), oquat(r[3], r[4], r[5], r[6])};
+		const OLocalRigidTransform local = olrt_mul(bone, rel);
+		OTransform res = otransform_compose_rigid(&parent_transforms[i], local.pos, local.rot);
+		res.scale = ov3(original_scale3[3 * i], original_scale3[3 * i + 1], original_scale3[3 * i + 2]);
+		out[i] = res;
+	}
+}

@@ -231,6 +231,18 @@ def transform_compute_local(parent56, child56, use_ref=False):
     return out
 
 
+def bone_attachments(parent56, bone7, relative7, original_scale3, use_ref=False):
+    """RenderModuleImpl::updateBoneAttachment (render_module.cpp:399-403) per attachment -> uint8[n,56] Transforms."""
+    p = np.ascontiguousarray(parent56, np.uint8)
+    b = np.ascontiguousarray(bone7, np.float32)
+    r = np.ascontiguousarray(relative7, np.float32)
+    sc = np.ascontiguousarray(original_scale3, np.float32)
+    out = np.zeros_like(p)
+    f = ref().ref_bone_attachments if use_ref else lib().oracle_bone_attachments
+    f(_ptr(p), _ptr(b), _ptr(r), _ptr(sc), _ptr(out), C.c_uint32(len(p)))
+    return out
+
+
 def relative_matrices(globals56, base_pos):
     """World::getRelativeMatrix (world.cpp:370-377) for every transform: float32[n,16], column-major like Matrix."""
     g = np.ascontiguousarray(globals56, np.uint8)

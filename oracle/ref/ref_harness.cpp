@@ -151,6 +151,21 @@ REF_API void ref_sphere_radius(const void* tr56, const float* bounding_radius, f
 	for (uint32_t i = 0; i < n; ++i) out[i] = bounding_radius[i] * maximum(t[i].scale.x, t[i].scale.y, t[i].scale.z);
 }
 
+// the three reference calls of RenderModuleImpl::updateBoneAttachment (render_module.cpp:399-403) on caller-supplied data
+REF_API void ref_bone_attachments(const void* parent56, const float* bone7, const float* relative7, const float* original_scale3, void* out56, uint32_t n) {
+	const Transform* parent = (const Transform*)parent56;
+	Transform* out = (Transform*)out56;
+	for (uint32_t i = 0; i < n; ++i) {
+		const float* b = bone7 + 7 * (size_t)i;
+		const float* r = relative7 + 7 * (size_t)i;
+		const LocalRigidTransform bone_transform = {Vec3(b[0], b[1], b[2]), Quat(b[3], b[4], b[5], b[6])};
+		const LocalRigidTransform relative_transform = {Vec3(r[0], r[1], r[2]), Quat(r[3], r[4], r[5], r[6])};
+		Transform result = parent[i].compose(bone_transform * relative_transform);
+		result.scale = Vec3(original_scale3[3 * i], original_scale3[3 * i + 1], original_scale3[3 * i + 2]);
+		out[i] = result;
+	}
+}
+
 REF_API void ref_transform_compute_local(const void* parent56, const void* child56, void* out56, uint32_t n) {
 	const Transform* p = (const Transform*)parent56;
 	const Transform* c = (const Transform*)child56;

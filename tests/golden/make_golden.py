@@ -220,6 +220,17 @@ def world_kat():
     d["sr_tr"] = sr.view(np.uint8).reshape(400, 56)
     d["sr_bound"] = (rng.random(400) * 10).astype(np.float32)
     d["sr_out"] = po.sphere_radius(d["sr_tr"], d["sr_bound"], use_ref=True)
+    # updateBoneAttachment (render_module.cpp:399-403): parents far from / near the origin, non-uniform scales
+    nb = 600
+    bp = np.zeros(nb, tr_dtype)
+    bp["pos"] = rng.normal(size=(nb, 3)) * np.where(rng.random((nb, 1)) < 0.5, 1e3, 1e6)
+    bp["rot"] = unit_quats(rng, nb)
+    bp["scale"] = (0.25 + 2 * rng.random((nb, 3))).astype(np.float32)
+    d["ba_parent"] = bp.view(np.uint8).reshape(nb, 56)
+    d["ba_bone"] = np.concatenate([(rng.normal(size=(nb, 3)) * 2).astype(np.float32), unit_quats(rng, nb)], axis=1)
+    d["ba_rel"] = np.concatenate([(rng.normal(size=(nb, 3)) * 0.5).astype(np.float32), unit_quats(rng, nb)], axis=1)
+    d["ba_scale"] = (0.5 + rng.random((nb, 3))).astype(np.float32)
+    d["ba_out"] = po.bone_attachments(d["ba_parent"], d["ba_bone"], d["ba_rel"], d["ba_scale"], use_ref=True)
     # Viewport::getFrustum() (geometry.cpp:793-818): args = is_ortho, fov, ortho_size, w, h, pos[3], rot[4], near, far
     vp_args, vp_out = [], []
     for k in range(120):

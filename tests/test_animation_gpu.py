@@ -3,6 +3,8 @@
 north_star tolerance: 1e-5 relative for skin matrices.  The kernels keep the reference's op order without FMA, so the
 tests first try bit-exactness and otherwise enforce the 1e-5 bound (relative to the largest magnitude of the row).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -211,3 +213,29 @@ def test_random_skeletons_and_clips(ctx, oracle):
         want = np.array([oracle.time_advance(t, dt, clips[c].fps, clips[c].frame_count) for c, t in zip(ci, tt)], np.uint32)
         assert np.array_equal(anim.getTimes(), want), trial
         anim.close()
+
+
+@pytest.mark.skipif(os.environ.get("LB200_RUN_UNVALIDATED", "0") in ("", "0"),
+                    reason="bone_attachments_kernel was written after the round's GPU budget was spent: set LB200_RUN_UNVALIDATED=1 to run it")
+def test_bone_attachments_match_oracle(ctx, oracle):
+    """updateBoneAttachment batched (render_module.cpp:377-405): entities following bones of posed instances."""
+    n_inst = 200
+    sk, clips, _, anim, ci, tt = _setup(ctx, 40, 2, n_inst, seed=61)
+    anim.update(0.0, lb.PALETTE_POSE)
+    pos, rot = anim.getPose()
+    rng = np.random.default_rng(4)
+    n = 1500
+    inst = rng.integers(0, n_inst, n).astype(np.uint32)
+    bone = rng.integers(0, 40, n).astype(np.uint32)
+    rel = np.concatenate([(rng.normal(size=(n, 3)) * 0.5).astype(np.float32), scenes.random_unit_quats(rng, n)], axis=1).astype(np.float32)
+    par = np.zeros(n, lb.TRANSFORM_DTYPE)
+    par["pos"] = rng.normal(size=(n, 3)) * 5000.0
+    par["rot"] = scenes.random_unit_quats(rng, n)
+    par["scale"] = (0.5 + rng.random((n, 3))).astype(np.float32)
+    scale = (0.5 + rng.random((n, 3))).astype(np.float32)
+    got = anim.boneAttachments(inst, bone, rel, par, scale)
+    bone7 = np.concatenate([pos[inst, bone], rot[inst, bone]], axis=1).astype(np.float32)
+    exp = oracle.bone_attachments(np.ascontiguousarray(par).view(np.uint8).reshape(n, 56), bone7, rel, scale).view(lb.TRANSFORM_DTYPE).reshape(-1)
+    assert np.array_equal(got["pos"], exp["pos"]) and np.array_equal(got["rot"].view(np.uint32), exp["rot"].view(np.uint32))
+    assert np.array_equal(got["scale"], exp["scale"])
+    anim.close()

@@ -257,3 +257,11 @@ def test_skeleton_derivation_follows_parse_bones(oracle):
         rel[sk.parents < 0] = abs7[sk.parents < 0]  # roots keep their transform (model.cpp:416-419)
         assert np.array_equal(bits(rel), bits(sk.bind_relative7))
         assert all(int(p) < i for i, p in enumerate(sk.parents))  # parent < child, model.cpp:381-384
+
+
+def test_bone_attachments(oracle):
+    """RenderModuleImpl::updateBoneAttachment (render_module.cpp:399-403) against the reference's own Transform::compose(LocalRigidTransform)
+    and LocalRigidTransform::operator*."""
+    k = np.load(os.path.join(G, "world_kat.npz"))
+    got = oracle.bone_attachments(k["ba_parent"], k["ba_bone"], k["ba_rel"], k["ba_scale"])
+    assert np.array_equal(got[:, :52], k["ba_out"][:, :52])
