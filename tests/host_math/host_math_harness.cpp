@@ -75,4 +75,19 @@ void hm_transform_compose(const Tr* parent, const Tr* local, Tr* out, unsigned n
 	}
 }
 
+// the body of bone_attachments_kernel (csrc/animation.cu), expression for expression: updateBoneAttachment, render_module.cpp:399-403
+void hm_bone_attachments(const Tr* parent, const float* bone7, const float* relative7, const float* scale3, Tr* out, unsigned n) {
+	for (unsigned i = 0; i < n; ++i) {
+		const Rigid local = rmul(rigid7(bone7 + 7 * i), rigid7(relative7 + 7 * i));
+		const Tr& p = parent[i];
+		const Q4 prot = q4(p.rot[0], p.rot[1], p.rot[2], p.rot[3]);
+		const V3 rotated = rotate(prot, mul(local.pos, v3(p.scale[0], p.scale[1], p.scale[2])));
+		const Q4 rot = qmul(prot, local.rot);
+		Tr& o = out[i];
+		o.pos[0] = LB_DADD(p.pos[0], (double)rotated.x); o.pos[1] = LB_DADD(p.pos[1], (double)rotated.y); o.pos[2] = LB_DADD(p.pos[2], (double)rotated.z);
+		o.rot[0] = rot.x; o.rot[1] = rot.y; o.rot[2] = rot.z; o.rot[3] = rot.w;
+		o.scale[0] = scale3[3 * i]; o.scale[1] = scale3[3 * i + 1]; o.scale[2] = scale3[3 * i + 2]; o.pad = 0;
+	}
+}
+
 } // extern "C"

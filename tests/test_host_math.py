@@ -52,3 +52,13 @@ def test_device_math_header_reproduces_reference_bits(hm):
     out = np.zeros((n, 56), np.uint8)
     hm.hm_transform_compose(P(c(k["tr_a"])), P(c(k["tr_b"])), P(out), C.c_uint(n))
     assert np.array_equal(out[:, :52], k["compose"][:, :52])
+
+
+def test_bone_attachment_expression(hm):
+    """The expression bone_attachments_kernel evaluates, on the host, against the reference-run vectors of updateBoneAttachment."""
+    k = np.load(os.path.join(G, "world_kat.npz"))
+    n = len(k["ba_parent"])
+    out = np.zeros((n, 56), np.uint8)
+    c = np.ascontiguousarray
+    hm.hm_bone_attachments(P(c(k["ba_parent"])), P(c(k["ba_bone"])), P(c(k["ba_rel"])), P(c(k["ba_scale"])), P(out), C.c_uint(n))
+    assert np.array_equal(out[:, :52], k["ba_out"][:, :52])
