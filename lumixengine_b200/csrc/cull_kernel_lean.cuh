@@ -9,11 +9,13 @@
 //      containsAABB box); A2 runs the exact classification + plane mask on the compacted candidates only.
 //   B  plane-outer / row-inner: warp-uniform loop over the planes of the mask, seven rows unrolled inside, no branch per sphere; lanes past
 //      `count` load a clamped slot and are masked at the ballot.
-//   D  full rows take the lane index as rank, rows without a visible sphere are skipped.
+//   D  pages whose ids are all visible (the reference's "fully inside" pages and pages with an empty plane mask) are copied with one base
+//      address per lane and immediate row offsets; only tested pages go through ballots and ranks.
 //
-//   Static SASS (cuobjdump, sm_100a): 64 registers, no spills, 1928 instructions in all (default kernel: 2200); the plane loop of B is
+//   Static SASS (cuobjdump, sm_100a): 64 registers, 28 B of spills, 1888 instructions in all (default kernel: 2200).  The plane loop of B is
 //   67 instructions per plane for the seven rows of a page (56 FMUL / FADD / LOP3 + 11 of loop overhead, plane load and shuffle), i.e.
-//   about 45 + 67 x planes + 40 per tested page against the 353 executed per tested page by the default kernel on the C2 view.
+//   about 45 + 67 x planes + 40 per tested page against the 353 the default kernel executes per tested page on the C2 view; a copied
+//   page costs about 40 instructions in D against 131.  Estimate for the C2 view: 4.2 M warp instructions per cull against 7.2 M.
 #pragma once
 
 #include "cull_kernel.cuh"
@@ -292,26 +294,34 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 		// or four pages per warp iteration was tried twice and lost to register spills under the 64-register cap of 4 blocks/SM.
 		for (uint32_t w = warp; w < n_work; w += CULL_WARPS) {
 			const uint32_t page = s_item[w].page;
-			const uint32_t type = (s_item[w].meta >> 8) & 0xffu;
+			const uint32_t meta = s_item[w].meta;
+			const uint32_t type = (meta >> 8) & 0xffu;
+			uint32_t* dst = out_ids + P.type_base[type] + s_bal[w][ROWS];
+			const int* ep = entities + (size_t)page * LB200_PAGE_SLOTS;
+			if (((meta >> 16) & 3u) == CLS_COPY) {
+				// every id of the page is visible (culling_system.cpp:345-360, or an empty plane mask): a straight copy, one base address per
+				// lane and immediate offsets per row — no ballots, no ranks
+				const uint32_t count = meta & 0xffu;
+				const int* src = ep + lane;
+				uint32_t* d = dst + lane;
+				int id[ROWS];
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) if ((uint32_t)(k * 32 + lane) < count) id[k] = ldg_stream_i32(src + k * 32);
+#pragma unroll
+				for (int k = 0; k < ROWS; ++k) if ((uint32_t)(k * 32 + lane) < count) d[k * 32] = (uint32_t)id[k];
+				continue;
+			}
 			uint32_t bal[ROWS];
 #pragma unroll
 			for (int k = 0; k < ROWS; ++k) bal[k] = s_bal[w][k];
-			uint32_t* dst = out_ids + P.type_base[type] + s_bal[w][ROWS];
-			const int* ep = entities + (size_t)page * LB200_PAGE_SLOTS;
 			int id[ROWS];
 #pragma unroll
-			for (int k = 0; k < ROWS; ++k) if (bal[k] && ((bal[k] >> lane) & 1u)) id[k] = ldg_stream_i32(ep + k * 32 + lane);
+			for (int k = 0; k < ROWS; ++k) if ((bal[k] >> lane) & 1u) id[k] = ldg_stream_i32(ep + k * 32 + lane);
 			uint32_t prefix = 0;
 #pragma unroll
 			for (int k = 0; k < ROWS; ++k) {
-				if (bal[k] == 0xffffffffu) { // full row (every row of a copied page but the last): the lane index is the rank
-					dst[prefix + lane] = (uint32_t)id[k];
-					prefix += 32u;
-				}
-				else if (bal[k]) { // rows without a visible sphere cost one uniform test
-					if ((bal[k] >> lane) & 1u) dst[prefix + __popc(bal[k] & lt_mask)] = (uint32_t)id[k];
-					prefix += __popc(bal[k]);
-				}
+				if ((bal[k] >> lane) & 1u) dst[prefix + __popc(bal[k] & lt_mask)] = (uint32_t)id[k];
+				prefix += __popc(bal[k]);
 			}
 		}
 		__syncthreads(); // every warp is done with s_item / s_bal
