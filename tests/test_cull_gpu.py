@@ -1,4 +1,6 @@
 """GPU parity of CullingSystem::cull against the oracle (bit-exact visible sets per renderable type)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -264,6 +266,8 @@ def test_pinned_and_pageable_destinations_agree(ctx, oracle):
     cs.close()
 
 
+@pytest.mark.skipif(os.environ.get("LB200_RUN_UNVALIDATED", "0") in ("", "0"),
+                    reason="written after the round's GPU budget was spent (DESIGN.md section 11): set LB200_RUN_UNVALIDATED=1 to run it")
 def test_begin_poll_end_equals_cull(ctx, oracle):
     """The non-blocking delivery (what the engine shim uses from job fibers: begin, yield while poll is false, end) hands back exactly
     what cull() does, for a full cull and for one renderable type."""
@@ -283,6 +287,8 @@ def test_begin_poll_end_equals_cull(ctx, oracle):
     cs.close()
 
 
+@pytest.mark.skipif(os.environ.get("LB200_RUN_UNVALIDATED", "0") in ("", "0"),
+                    reason="written after the round's GPU budget was spent (DESIGN.md section 11): set LB200_RUN_UNVALIDATED=1 to run it")
 def test_random_views_and_edits(ctx, oracle):
     """Randomised parity run (the same generator the oracle itself is checked with against the reference build in
     tests/test_oracle_ref.py): worlds with crowded and sparse cells, perspective / ortho views incl. axis-aligned ones snapped to cell
