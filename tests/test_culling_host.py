@@ -150,3 +150,25 @@ def test_parallel_set_of_distinct_entities_equals_sequential(oracle):
     pos[ids] += 50.0
     a.set(ids, pos[ids], rad[ids], unique=True); oc.set(ids, pos[ids], rad[ids])
     _same_state(a, oc)
+
+
+def test_threshold_values_bin_like_the_oracle(oracle):
+    """radius == 300 is not big, the next float is (culling_system.cpp:139); positions on cell borders, +-0.0 and within 1e-8 of a border
+    land in the oracle's cells (the oracle itself is checked against the reference build with the same values, test_oracle_ref.py)."""
+    r_edge = np.float32(300.0)
+    radii = np.array([r_edge, np.nextafter(r_edge, np.float32(1e9)), np.nextafter(r_edge, np.float32(0)), 0.0, 1e-30], np.float32)
+    coords = [0.0, -0.0, 300.0, -300.0, 299.99999999, -299.99999999, 300.00000001, 600.0, -600.0, 899.9999, 1e-300, -1e-300]
+    pos = np.array([[x, y, 10.0] for x in coords for y in (0.0, -300.0, 299.99999999)], np.float64)
+    P = np.repeat(pos, len(radii), axis=0)
+    R = np.tile(radii, len(pos))
+    E = np.arange(len(P), dtype=np.int32)
+    T = (E % 3).astype(np.uint8)
+    cs, oc = lb.CullingSystem(None), oracle.OracleCulling()
+    cs.add(E, T, P, R); oc.add(E, T, P, R)
+    _same_state(cs, oc)
+    big = E[R > r_edge]
+    cs.setRadius(big, np.full(len(big), r_edge, np.float32)); oc.set_radius(big, np.full(len(big), r_edge, np.float32))
+    edge = E[R == r_edge]
+    up = np.full(len(edge), np.nextafter(r_edge, np.float32(1e9)), np.float32)
+    cs.setRadius(edge, up); oc.set_radius(edge, up)
+    _same_state(cs, oc)

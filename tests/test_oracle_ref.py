@@ -114,3 +114,39 @@ def test_random_clips_equal_reference(ref):
             a = np.concatenate(ref.pose_evaluate(sk, other, t2, weight=w, start_from_bind=False, compute_absolute=True, pos=rel[0], rot=rel[1]), axis=1)
             b = np.concatenate(ref.ref_pose_evaluate(sk, other, t2, weight=w, start_from_bind=False, compute_absolute=True, pos=rel[0], rot=rel[1]), axis=1)
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (trial, t, w)
+
+
+def test_threshold_values_equal_reference(ref):
+    """Exact thresholds: radius == cell size (not big: `radius > m_cell_size`, culling_system.cpp:139) and the next float above it; positions
+    exactly on cell borders, +-0.0 and just inside them (cell index = int(pos * (1 / 300.f)), truncation toward zero)."""
+    r_edge = np.float32(300.0)
+    radii = np.array([r_edge, np.nextafter(r_edge, np.float32(1e9)), np.nextafter(r_edge, np.float32(0)), 0.0, 1e-30], np.float32)
+    coords = [0.0, -0.0, 300.0, -300.0, 299.99999999, -299.99999999, 300.00000001, 600.0, -600.0, 899.9999, 1e-300, -1e-300]
+    pos = np.array([[x, y, 10.0] for x in coords for y in (0.0, -300.0, 299.99999999)], np.float64)
+    n = len(pos) * len(radii)
+    P = np.repeat(pos, len(radii), axis=0)
+    R = np.tile(radii, len(pos))
+    E = np.arange(n, dtype=np.int32)
+    T = (E % 3).astype(np.uint8)
+    rc, oc = ref.RefCulling(workers=1), ref.OracleCulling()
+    rc.add(E, T, P, R); oc.add(E, T, P, R)
+    a = scenes.c1_frustum_args()
+    for args in (dict(a, position=(0.0, 0.0, 500.0)), dict(a, position=(300.0, 0.0, 300.0), direction=(-1.0, 0.0, 0.0)), dict(a, position=(-1000.0, 100.0, 0.0), direction=(1.0, 0.0, 0.0), far=5000.0)):
+        f = ref.frustum_perspective(args["position"], args["direction"], args["up"], args["fov"], args["ratio"], args["near"], args["far"])
+        ids, tys, st = oc.cull(f)
+        rids, rtys, info = rc.cull(f, cap=n, iters=1)
+        assert info["count"] == len(ids) > 0
+        o, ro = np.argsort(ids), np.argsort(rids)
+        assert np.array_equal(ids[o], rids[ro]) and np.array_equal(tys[o], rtys[ro])
+        assert info["pages"] == st["pages_total"] - st["pages_filtered"]
+    # the same edits on both: shrink the big ones to exactly the threshold, grow the exact ones past it
+    big = E[R > r_edge]
+    rc.set_radius(big, np.full(len(big), r_edge, np.float32)); oc.set_radius(big, np.full(len(big), r_edge, np.float32))
+    edge = E[R == r_edge]
+    up = np.full(len(edge), np.nextafter(r_edge, np.float32(1e9)), np.float32)
+    rc.set_radius(edge, up); oc.set_radius(edge, up)
+    f = ref.frustum_perspective(a["position"], a["direction"], a["up"], a["fov"], a["ratio"], a["near"], 5000.0)
+    ids, tys, _ = oc.cull(f)
+    rids, rtys, info = rc.cull(f, cap=n, iters=1)
+    o, ro = np.argsort(ids), np.argsort(rids)
+    assert info["count"] == len(ids) and np.array_equal(ids[o], rids[ro]) and np.array_equal(tys[o], rtys[ro])
