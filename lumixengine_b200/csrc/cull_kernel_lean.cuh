@@ -234,6 +234,11 @@ __global__ void __launch_bounds__(CULL_THREADS, 1024 / CULL_THREADS) cull_pages_
 				}
 #pragma unroll
 				for (int k = 0; k < ROWS; ++k) {
+					// A NaN radius: on the reference's SSE path t - (-radius) hands the NaN through with the sign of -radius, and that sign is
+					// what movemask reads (+NaN radius: culled by every plane; -NaN radius: passes every plane).  The GPU's subtraction returns
+					// the canonical positive NaN instead, so the sign is taken from the radius directly.  (tests/golden/cull_kat.npz: special_*)
+					const uint32_t rbits = __float_as_uint(s[k].w);
+					if ((rbits & 0x7fffffffu) > 0x7f800000u && need) acc[k] = ~rbits & 0x80000000u;
 					const bool visible = (acc[k] >> 31) == 0 && (uint32_t)(k * 32 + lane) < count;
 					bal[k] = __ballot_sync(0xffffffffu, visible);
 					page_visible += __popc(bal[k]);

@@ -473,7 +473,11 @@ static uint32_t do_culling(const CellPage* cell, const OFrustum* fr, uint32_t* o
 	for (int i = 0; i < cell->header.count; ++i) {
 		const OSphere* s = &cell->spheres[i];
 		const float cx = s->position.x, cy = s->position.y, cz = s->position.z;
-		const float r = -s->radius;
+		/* :282 f4Splat(-sphere->radius) and :291 t - r are two separate SSE operations in the reference (xorps, subps).  They must stay
+		 * separate here: folded into t + radius the value is the same, but a NaN radius would come out with the other sign, and the sign
+		 * bit is what movemask reads (a +NaN radius culls the sphere on every plane, a -NaN radius makes it pass).  volatile keeps gcc from
+		 * folding. */
+		volatile float r = -s->radius;
 		int culled = 0;
 		for (int g = 0; g < 2 && !culled; ++g) {
 			int mask = 0;

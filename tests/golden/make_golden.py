@@ -131,6 +131,19 @@ def cull_kat():
         ids, tys, _ = rc.cull(f, cap=30_000)
         o = np.argsort(ids)
         d[f"edited{i}_ids"], d[f"edited{i}_types"] = ids[o], tys[o]
+    # special radii: +NaN / -NaN / +-inf / -0.0 / negative.  movemask reads sign bits, and t - (-radius) hands a NaN radius through with its
+    # sign flipped: a +NaN radius is culled by every plane, a -NaN radius passes every plane (even outside the frustum)
+    rs = np.random.default_rng(3)
+    ns = 2000
+    spos = np.stack([rs.uniform(-250, 250, ns), rs.uniform(-100, 100, ns), rs.uniform(-900, -100, ns)], 1)
+    srad = np.full(ns, 2.0, np.float32)
+    srad[:100] = np.nan
+    srad[100:200] = np.array([0xFFC00000], np.uint32).view(np.float32)[0]
+    srad[200:300] = np.inf; srad[300:400] = -np.inf; srad[400:500] = -0.0; srad[500:600] = -3.5
+    rs2 = po.RefCulling(workers=4)
+    rs2.add(np.arange(ns, dtype=np.int32), np.zeros(ns, np.uint8), spos, srad)
+    sids, _, _ = rs2.cull(fb[0], cap=ns)
+    d.update(special_pos=spos, special_radius_bits=srad.view(np.uint32), special_visible=np.sort(sids))
     np.savez_compressed(os.path.join(OUT, "cull_kat.npz"), **d)
     print("cull_kat.npz", sum(v.nbytes for v in d.values()))
 

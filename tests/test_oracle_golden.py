@@ -106,6 +106,16 @@ def test_cull_visible_sets(oracle):
     check("vis")
     oc.set_position(g["edit_a"], g["edit_pa"]); oc.set_radius(g["edit_b"], g["edit_rb"]); oc.set(g["edit_c"], g["edit_pc"], g["edit_rc"]); oc.remove(g["edit_e"])
     check("edited")
+    # special radii (NaN of either sign, infinities, -0.0, negative): the sign bit movemask sees is the reference's
+    rad = g["special_radius_bits"].view(np.float32)
+    n = len(rad)
+    os_ = oracle.OracleCulling()
+    os_.add(np.arange(n, dtype=np.int32), np.zeros(n, np.uint8), g["special_pos"], rad)
+    ids, _, _ = os_.cull(g["frusta"][0])
+    assert np.array_equal(np.sort(ids), g["special_visible"])
+    vis = set(int(i) for i in ids)
+    assert not any(i in vis for i in range(100))          # +NaN radius: culled by every plane
+    assert all(i in vis for i in range(100, 200))          # -NaN radius: passes every plane, wherever the sphere is
 
 
 def test_pose_sampling_and_absolute(oracle):
