@@ -33,6 +33,15 @@ for seed, n, box, kw in ((1, 100_000, (2000.0, 200.0, 2000.0), {}), (11, 300_000
             bad += not ok
             print(f"CHECK {tag} scene {seed} view {vi} filter {type_filter:#x}: visible {res.total:7d} {'ok' if ok else 'MISMATCH'}", flush=True)
     cs.close()
+# special radii (tests/golden/cull_kat.npz: special_*): the lean kernel follows the reference for NaN radii, the default kernel is known not to
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cull_kat.npz"))
+rad = g["special_radius_bits"].view(np.float32)
+cs = lb.CullingSystem(ctx); cs.add(np.arange(len(rad), dtype=np.int32), np.zeros(len(rad), np.uint8), g["special_pos"], rad)
+f0 = culling_frustum = lb.culling.frustum_from_bytes(g["frusta"][0]) if hasattr(lb.culling, "frustum_from_bytes") else lb.frustum_perspective(**scenes.c1_frustum_args())
+res = cs.cull(f0)
+same = np.array_equal(np.sort(res.ids), g["special_visible"])
+print(f"CHECK {tag} special radii (NaN / inf / -0.0 / negative): {'ok' if same else 'differs from the reference (expected for the default kernel)'}")
+cs.close()
 print(f"CHECK {tag} mismatches: {bad}")
 # timing on the 10 M scene (the five views of time_cull_variants.py)
 scene = scenes.c2_scene(10_000_000)
