@@ -370,7 +370,6 @@ def ours(a, rank, world):
                    "parallelism": f"dp{world}: whole cell pages per rank" + (("; exchanged each step: " + exchange_desc) if world > 1 else ""),
                    "submission": "K culls = one lb200_culling_cull_device_n call: consecutive (independent) culls on 3 streams / output lanes, half-occupancy grids, programmatic dependent launch" if world == 1 else "K exchange steps = one lb200_culling_cull_exchange_n call (steps on 3 streams, 6 exchange buffers per rank)",
                    "lone_cull_ms": ms_lone,
-                   "kernel_variant": "lean (LB200_CULL_LEAN)" if os.environ.get("LB200_CULL_LEAN", "0") not in ("", "0") else "default",
                    "scene_build_s": build_s, "page_stats": stats},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -187,6 +187,12 @@ LB200_API int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words,
  * back-to-back timed culls never re-read an L2-resident scene (B200_PROFILING.md "Timing hygiene"). */
 LB200_API int lb200_culling_set_replicas(lb200_culling* cs, uint32_t replicas);
 /* Algorithmic HBM bytes of the last cull: page descriptors + 16 B per tested sphere + 4 B per id read + 4 B per id written + mask. */
+/* Measurement helper: device time (ms) of `iters` single culls, each with the device to itself and its launches already queued when the
+ * device reaches them (no host launch latency inside the interval, nothing overlapping the cull). */
+LB200_API int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t iters, float* out_ms);
+/* Profiling aid: %globaltimer stamps (ns) of the phase boundaries of the last cull issued while LB200_CULL_TRACE=1 was set:
+ * out[2 kernels][2048 blocks][8 points] (cull_kernel.cuh trace_point). */
+LB200_API int lb200_culling_read_trace(lb200_culling* cs, uint64_t* out);
 LB200_API uint64_t lb200_culling_last_algorithmic_bytes(const lb200_culling* cs);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -200,6 +206,8 @@ LB200_API void lb200_comm_destroy(lb200_ctx* ctx);
  * (CUDA IPC).  After it lb200_culling_cull_gather pushes each rank's slab straight into its peers' memory from one fused kernel
  * and synchronises with per-epoch flags instead of calling NCCL on the per-frame path.  Up to 8 ranks (one NVSwitch box). */
 LB200_API int lb200_comm_enable_p2p(lb200_ctx* ctx, uint32_t max_slab_ids);
+/* LB200_OK, or LB200_ERR_NCCL (once; the condition is reset) if a device-side wait for a peer's slab gave up since the last check. */
+LB200_API int lb200_comm_status(lb200_ctx* ctx);
 /* Slab layout of the exchange: every rank contributes `256 + slab_ids` u32 words = [256 per-type counts][its visible ids packed type after
  * type]; the gathered buffer holds n_ranks such slabs back to back (rank r at word r * (256 + slab_ids)).
  *
@@ -213,16 +221,20 @@ LB200_API int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, cons
  * (256 + slab_ids on the NCCL path, the fixed peer-buffer stride after lb200_comm_enable_p2p). */
 LB200_API uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, uint32_t slab_ids);
 
-/* Bitmask exchange (the fixed-size product): the cull kernel itself stores each page's 32-byte visibility row and, at its
- * end, the per-type visible counts straight into EVERY rank's memory over NVLink (no separate pack / collective launch); the visible
- * ids stay sharded on the rank that owns the entities (*out_dev_ids, per-type segments as in lb200_culling_cull_device).
+/* Bitmask exchange: the cull's work kernel itself stores the 32-byte visibility row of every page it worked on — together
+ * with the page id — straight into EVERY rank's memory over NVLink (no separate pack / collective launch; rows of pages outside the
+ * frustum are all zero and never cross the links); a one-block kernel behind it sends the per-type counts and raises the epoch flags.
+ * The visible ids stay sharded on the rank that owns the entities (*out_dev_ids, per-type segments as in lb200_culling_cull_device).
  * Needs lb200_comm_enable_p2p(ctx, max over ranks of lb200_culling_exchange_slab_words(cs) - 256).  Asynchronous on the context
  * stream; when the stream reaches the end of this call every rank's slab of this step is complete in *out_dev_slabs.
  * Slab of rank r = words [r * stride, (r + 1) * stride):
- *   [0,256)   visible count per renderable type
- *   [256,264) n_pages, blocks, rows_per_block, chunk, 0, 0, 0, 0
- *   [264, ..) 8 words per mask row; the row of page p (page id on rank r) is (p % blocks) * rows_per_block + p / blocks;
- *             bit s of the 256-bit row = slot s of the page is visible (slots >= 200 are 0) */
+ *   [0,256)            visible count per renderable type
+ *   [256,264)          n_pages, n_test, n_copy, cap, 0, 0, 0, 0
+ *   [264, 264 + cap)   page id of record i (page ids of rank r)
+ *   [264 + cap, ..)    8 words per record: bit s of the 256-bit row = slot s of the page is visible (slots >= 200 are 0)
+ *   valid records: [0, n_test) (pages that went through sphere tests) and (cap - 1 - j) for j in [0, n_copy) (pages copied whole);
+ *   every page without a record has an all-zero row.
+ * A peer that does not publish within ~4 s makes the next lb200_synchronize / exchange call return LB200_ERR_NCCL (lb200_comm_status). */
 LB200_API int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,
                                           const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words);
 /* n independent exchange steps issued from one call: step (epoch) e runs on internal stream e % lanes on every rank, so the remote

@@ -66,7 +66,17 @@ int lb200_comm_allgather_u32(lb200_ctx* ctx, const uint32_t* send, uint32_t* rec
 	return LB200_OK;
 }
 
+int lb200_comm_check(lb200_ctx* ctx) {
+	lb200_ctx::Peer& P = ctx->peer;
+	if (!P.h_timeout || !*(volatile uint32_t*)P.h_timeout) return LB200_OK;
+	*(volatile uint32_t*)P.h_timeout = 0;
+	lb200_set_error(ctx, "multi-GPU exchange: a peer's slab did not arrive within the wait limit (~4 s); the exchanged slabs of that step are incomplete");
+	return LB200_ERR_NCCL;
+}
+
 extern "C" {
+
+int lb200_comm_status(lb200_ctx* ctx) { return ctx ? lb200_comm_check(ctx) : LB200_ERR_INVALID; }
 
 int lb200_comm_get_unique_id(lb200_ctx* ctx, uint8_t out_id[128]) {
 	if (!ctx || !out_id) return LB200_ERR_INVALID;
@@ -104,16 +114,19 @@ int lb200_comm_enable_p2p(lb200_ctx* ctx, uint32_t max_slab_ids) {
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	lb200_ctx::Peer& P = ctx->peer;
 	P.slab_words = (256 + (size_t)max_slab_ids + 63) & ~(size_t)63;
-	const size_t flag_bytes = 256;
+	const size_t flag_bytes = 512;
 	const size_t buf_bytes = sizeof(uint32_t) * P.slab_words * (size_t)R;
 	P.lanes = lb200_cull_lanes(); // the same on every rank (same environment)
 	P.n_buffers = 2 * P.lanes;
-	static_assert(2 * LB200_MAX_LANES * LB200_MAX_RANKS * sizeof(uint32_t) <= 256, "flag block");
+	static_assert(2 * LB200_MAX_LANES * LB200_MAX_RANKS * sizeof(uint32_t) <= 512, "flag block");
 	const size_t total = flag_bytes + P.n_buffers * buf_bytes;
 	LB200_CUDA(ctx, cudaMalloc(&P.local_block, total));
 	LB200_CUDA(ctx, cudaMemsetAsync(P.local_block, 0, flag_bytes, ctx->stream));
 	LB200_CUDA(ctx, cudaMalloc(&P.done_counter, sizeof(uint32_t) * LB200_MAX_LANES));
 	LB200_CUDA(ctx, cudaMemsetAsync(P.done_counter, 0, sizeof(uint32_t) * LB200_MAX_LANES, ctx->stream));
+	LB200_CUDA(ctx, cudaHostAlloc(&P.h_timeout, sizeof(uint32_t), cudaHostAllocMapped));
+	*P.h_timeout = 0;
+	LB200_CUDA(ctx, cudaHostGetDevicePointer((void**)&P.d_timeout, P.h_timeout, 0));
 	cudaIpcMemHandle_t mine;
 	LB200_CUDA(ctx, cudaIpcGetMemHandle(&mine, P.local_block));
 	// exchange the 64-byte handles with NCCL
@@ -157,6 +170,7 @@ void lb200_comm_destroy(lb200_ctx* ctx) {
 		for (int r = 0; r < LB200_MAX_RANKS; ++r) if (ctx->peer.opened[r]) cudaIpcCloseMemHandle(ctx->peer.opened[r]);
 		cudaFree(ctx->peer.local_block);
 		cudaFree(ctx->peer.done_counter);
+		if (ctx->peer.h_timeout) cudaFreeHost(ctx->peer.h_timeout);
 		ctx->peer = lb200_ctx::Peer();
 	}
 	p_ncclCommDestroy((ncclComm_t)ctx->nccl_comm);

@@ -75,7 +75,7 @@ const char* lb200_last_error(const lb200_ctx* ctx) { return ctx ? ctx->error : g
 int lb200_synchronize(lb200_ctx* ctx) {
 	if (!ctx) return LB200_ERR_INVALID;
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	return LB200_OK;
+	return lb200_comm_check(ctx);
 }
 
 void* lb200_host_alloc(lb200_ctx* ctx, size_t bytes) {

@@ -14,7 +14,6 @@
 // HBM-bound: 16 B per tested sphere + 4 B read + 4 B write per visible id.  No tensor cores: there is no
 // contraction here.
 #include "cull_kernel.cuh"
-#include "cull_kernel_lean.cuh"
 #include "culling_host.hpp"
 #include "lb200_math.cuh"
 
@@ -197,7 +196,7 @@ __global__ void wait_peers_kernel(const uint32_t* flags, uint32_t n_ranks, uint3
 // the stream runs its read-only prologue meanwhile.
 struct PublishParams {
 	uint32_t n_ranks, rank, epoch, n_buffers;
-	uint32_t n_pages, blocks, rows_per_block, chunk;
+	uint32_t n_pages, item_cap;
 	uint32_t* dst[LB200_MAX_RANKS];   // rank r's exchange buffer of this epoch, already offset to MY slab inside it
 	uint32_t* flags[LB200_MAX_RANKS]; // rank r's flag block: [n_buffers][LB200_MAX_RANKS]
 };
@@ -210,16 +209,18 @@ __global__ void __launch_bounds__(288) publish_wait_kernel(const __grid_constant
 		uint32_t v = 0;
 		if (i < 256) v = __ldcg(counters + i);
 		else if (i == 256) v = P.n_pages;
-		else if (i == 257) v = P.blocks;
-		else if (i == 258) v = P.rows_per_block;
-		else if (i == 259) v = P.chunk;
+		else if (i == 257) v = __ldcg(counters + CNT_N_TEST);
+		else if (i == 258) v = __ldcg(counters + CNT_N_COPY);
+		else if (i == 259) v = P.item_cap;
 		for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][i] = v;
 	}
-	// release: everything that happened before this fence — the cull grid's rows (ordered before us by the grid dependency) and the
-	// header just written — is visible to whoever observes the flag
+	// release: everything that happened before the flag store — the work grid's records (ordered before us by the grid dependency) and
+	// the header just written by all threads of this block (barrier, then a system-scope fence by the storing threads) — is visible to
+	// whoever observes the flag
 	__threadfence_system();
 	__syncthreads();
 	if (i < P.n_ranks) {
+		__threadfence_system();
 		volatile uint32_t* f = P.flags[i] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + P.rank;
 		*f = P.epoch;
 		const volatile uint32_t* mine = P.flags[P.rank] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + i;
@@ -229,6 +230,12 @@ __global__ void __launch_bounds__(288) publish_wait_kernel(const __grid_constant
 		}
 	}
 	__threadfence_system();
+}
+
+// holds the stream for a while, so that whatever the host enqueues behind it is already queued when the device gets there
+__global__ void delay_kernel(long long cycles) {
+	const long long t0 = clock64();
+	while (clock64() - t0 < cycles) {}
 }
 
 void* pinnedAlloc(size_t n) {
@@ -267,8 +274,12 @@ struct lb200_culling {
 	uint64_t seq = 0;
 	uint32_t* d_out_ids = nullptr;  // lanes * out_cap
 	uint32_t out_cap = 0;
-	uint32_t* d_mask = nullptr;     // lanes * mask_words
+	uint32_t* d_mask = nullptr;     // lanes * mask_words; row of page p = words [8p, 8p + 8)
 	size_t mask_words = 0;
+	lbcull::TestItem* d_test_items = nullptr; // lanes * item_cap: work lists of the classify kernel
+	lbcull::CopyItem* d_copy_items = nullptr; // lanes * item_cap
+	uint32_t item_cap = 0;
+	bool uploaded_since_last_cull = true; // the next cull's kernels are launched plain (no programmatic overlap with the upload)
 	uint32_t* d_counters = nullptr; // lanes * 2 * COUNTER_WORDS: [lane][parity]
 	// asynchronous host delivery (lb200_culling_cull_begin / _poll / _end)
 	cudaEvent_t done_event = nullptr;
@@ -289,13 +300,11 @@ struct lb200_culling {
 	size_t stage_pages = 0;
 	// multi-GPU gather buffers
 	uint32_t* d_gather_ids = nullptr;
-	uint32_t* d_gather_counts = nullptr;
 	size_t gather_ids_cap = 0;
 	uint32_t* d_slab = nullptr;
 	size_t slab_cap = 0;
 
 	uint32_t last_type_base[256];
-	uint32_t last_blocks = 0, last_rows_per_block = 0, last_chunk = 0; // mask row of page p = (p % blocks) * rows_per_block + p / blocks
 	lb200_cull_result last = {};
 	bool has_last = false;
 	uint64_t last_bytes = 0;
@@ -314,9 +323,10 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS, ctx->stream));
 		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocMapped));
 		if (cudaHostGetDevicePointer((void**)&cs->h_counters_dev, cs->h_counters, 0) != cudaSuccess) { cudaGetLastError(); cs->h_counters_dev = nullptr; }
-		cs->threads = 256; // 512-thread blocks measured no better (profiles/)
+		cs->threads = WORK_THREADS;
 		int per_sm = 0;
-		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_pages_kernel<256>, 256, 0));
+		LB200_CUDA(ctx, cudaFuncSetAttribute(cull_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORK_SMEM));
+		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_work_kernel, WORK_THREADS, WORK_SMEM));
 		if (per_sm < 1) per_sm = 1;
 		cs->grid = ctx->sm_count * per_sm;
 		// cull_device_n runs independent culls concurrently: half-occupancy grids let two of them share every SM, so one cull's
@@ -329,15 +339,17 @@ int ensureDevice(lb200_culling* cs) {
 		uint32_t cap = cs->dev_cap ? cs->dev_cap : 1024;
 		while (cap < h.high_water) cap *= 2;
 		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_mask);
-		cs->d_spheres = nullptr; cs->d_entities = nullptr; cs->d_desc = nullptr; cs->d_mask = nullptr;
+		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_mask); cudaFree(cs->d_test_items); cudaFree(cs->d_copy_items);
+		cs->d_spheres = nullptr; cs->d_entities = nullptr; cs->d_desc = nullptr; cs->d_mask = nullptr; cs->d_test_items = nullptr; cs->d_copy_items = nullptr;
 		const size_t R = cs->replicas;
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_spheres, sizeof(float4) * PAGE_SLOTS * (size_t)cap * R));
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_entities, sizeof(int) * PAGE_SLOTS * (size_t)cap * R));
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_desc, sizeof(lb200_page_desc) * (size_t)cap * R));
-		// block-transposed rows (cull_kernel.cuh phase E): at most one chunk of padding rows per block
-		cs->mask_words = 8 * ((size_t)cap + 256 * (size_t)cs->grid);
+		cs->mask_words = 8 * (size_t)cap;
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_mask, sizeof(uint32_t) * cs->mask_words * cs->lanes));
+		cs->item_cap = cap; // every page can end up in one of the two lists
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_test_items, sizeof(TestItem) * (size_t)cap * cs->lanes));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_copy_items, sizeof(CopyItem) * (size_t)cap * cs->lanes));
 		// free / never-used pages must read count == 0
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_desc, 0, sizeof(lb200_page_desc) * (size_t)cap * R, ctx->stream));
 		cs->dev_cap = cap;
@@ -405,7 +417,12 @@ int flushPages(lb200_culling* cs) {
 			st_d[i] = h.desc[p];
 			st_i[i] = p;
 		}
-		LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_stage, cs->h_stage, per_page * cap, cudaMemcpyHostToDevice, ctx->stream));
+		// only the m used entries of each of the four sections travel
+		const size_t sec[5] = {0, sizeof(float4) * PAGE_SLOTS * cap, (sizeof(float4) + sizeof(int)) * PAGE_SLOTS * cap,
+			(sizeof(float4) + sizeof(int)) * PAGE_SLOTS * cap + sizeof(lb200_page_desc) * cap, 0};
+		const size_t used[4] = {sizeof(float4) * PAGE_SLOTS * m, sizeof(int) * PAGE_SLOTS * m, sizeof(lb200_page_desc) * m, sizeof(uint32_t) * m};
+		for (int k = 0; k < 4; ++k)
+			LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_stage + sec[k], cs->h_stage + sec[k], used[k], cudaMemcpyHostToDevice, ctx->stream));
 		const float4* d_s = reinterpret_cast<const float4*>(cs->d_stage);
 		const int* d_e = reinterpret_cast<const int*>(cs->d_stage + sizeof(float4) * PAGE_SLOTS * cap);
 		const lb200_page_desc* d_d = reinterpret_cast<const lb200_page_desc*>(cs->d_stage + (sizeof(float4) + sizeof(int)) * PAGE_SLOTS * cap);
@@ -417,27 +434,19 @@ int flushPages(lb200_culling* cs) {
 		}
 	}
 	h.clearDirty();
+	cs->uploaded_since_last_cull = true;
 	return LB200_OK;
 }
 
-// rounds / rows per block of a cull over n_pages (the kernel's dealing: page = j * blocks + block)
-void cullGeometry(const lb200_culling* cs, uint32_t grid, uint32_t n_pages, uint32_t* chunk_out, uint32_t* blocks_out, uint32_t* rpb_out) {
-	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
-	uint32_t chunk = (n_pages + grid - 1) / grid;
-	chunk = std::max(32u, std::min((uint32_t)cs->threads, chunk));
-	const uint32_t blocks = std::max(1u, std::min(grid, (n_pages + chunk - 1) / chunk));
-	const uint32_t per_round = chunk * blocks;
-	const uint32_t rounds = std::max(1u, (n_pages + per_round - 1) / per_round);
-	*chunk_out = chunk; *blocks_out = blocks; *rpb_out = rounds * chunk;
-}
+struct Exchange { uint32_t epoch; }; // non-null: store {page, row} records + counts into every rank's slab (peer memory); lane = epoch % lanes
 
-struct Exchange { uint32_t epoch; }; // non-null: store mask rows + counts into every rank's slab (peer memory); lane = epoch % lanes
+// words one rank contributes to a bitmask exchange step: header + page ids + rows (cull_kernel.cuh)
+size_t exchangeSlabWords(const lb200_culling* cs) { return XHEADER_WORDS + 9 * (size_t)cs->item_cap; }
 
 int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, const Exchange* xchg = nullptr, cudaStream_t stream = nullptr) {
 	lb200_range range("culling"); // culling_system.cpp:330
 	lb200_ctx* ctx = cs->ctx;
 	lb::CullingHost& h = cs->host;
-	const bool had_dirty = h.all_dirty || !h.dirty_list.empty() || !cs->d_counters;
 	int rc = flushPages(cs);
 	if (rc) return rc;
 
@@ -452,6 +461,9 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	P.ox = f->origin[0]; P.oy = f->origin[1]; P.oz = f->origin[2];
 	P.n_pages = h.high_water;
 	P.type_filter = type;
+	P.item_cap = cs->item_cap;
+	static const bool trace = getenv("LB200_CULL_TRACE") != nullptr;
+	P.trace = trace ? 1u : 0u;
 	uint32_t acc = 0;
 	for (int t = 0; t < 256; ++t) { P.type_base[t] = acc; acc += h.type_counts[t]; }
 	memcpy(cs->last_type_base, P.type_base, sizeof(P.type_base));
@@ -464,10 +476,8 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	uint32_t* nxt = cs->d_counters + ((size_t)lane * 2 + (cs->lane_parity[lane] ^ 1u)) * COUNTER_WORDS;
 	uint32_t* out = cs->d_out_ids + (size_t)lane * cs->out_cap;
 	uint32_t* mask = cs->d_mask + (size_t)lane * cs->mask_words;
-	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid), h.high_water, &chunk, &blocks, &rpb);
-	P.chunk = chunk;
-	P.rows_per_block = rpb;
+	TestItem* test_items = cs->d_test_items + (size_t)lane * cs->item_cap;
+	CopyItem* copy_items = cs->d_copy_items + (size_t)lane * cs->item_cap;
 	P.n_ranks = 0;
 	for (int r = 0; r < LB200_MAX_RANKS; ++r) P.xdst[r] = nullptr;
 	if (xchg) {
@@ -477,36 +487,44 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	}
 	static const bool no_mask = getenv("LB200_NO_PLANE_MASKING") != nullptr;
 	P.plane_masking = (h.n_bad_radius == 0 && !no_mask) ? 1u : 0u;
-	static const bool pf_ids = getenv("LB200_PREFETCH_TEST_IDS") ? atoi(getenv("LB200_PREFETCH_TEST_IDS")) != 0 : false;
-	P.prefetch_test_ids = pf_ids ? 1u : 0u;
-	// Programmatic stream serialization: the kernel's prologue (up to cudaGridDependencySynchronize) reads only the page descriptors
-	// and issues L2 prefetches of page data.  Those arrays are written by flushPages alone, so unless this call uploaded something the
-	// prologue may overlap the tail of whatever kernel precedes it on the stream — for back-to-back views (main, shadow cascades,
-	// lights) that is the previous cull, which releases its dependents at its first instruction.
+	// Programmatic stream serialization.  The classify kernel only READS scene data (descriptors; L2 prefetches of page rows) before its
+	// cudaGridDependencySynchronize(): unless something was uploaded since the last cull it may overlap the tail of whatever kernel
+	// precedes it on the stream — for back-to-back views (main, shadow cascades, lights) that is the previous cull's work kernel, which
+	// releases its dependents at its first instruction.  The flag is sticky: whichever call uploaded (flush, set_many, ...), the first
+	// cull after it is launched plain.  The work kernel always follows its own classify kernel and is always launched this way.
 	static const bool no_pdl = getenv("LB200_NO_PDL") != nullptr;
-	const bool pdl = !no_pdl && !had_dirty;
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(blocks);
-	cfg.blockDim = dim3(256);
-	cfg.stream = stream ? stream : ctx->stream;
+	const bool pdl = !no_pdl && !cs->uploaded_since_last_cull;
+	cs->uploaded_since_last_cull = false;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cudaLaunchConfig_t cfg = {};
+	cfg.stream = stream ? stream : ctx->stream;
 	cfg.attrs = attr;
+	uint32_t* mask_arg = xchg ? (uint32_t*)nullptr : mask;
+	// classify: one thread per page
+	cfg.gridDim = dim3((h.high_water + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS);
+	cfg.blockDim = dim3(CLASSIFY_THREADS);
 	cfg.numAttrs = pdl ? 1 : 0;
-	// LB200_CULL_LEAN=1 selects the instruction-lean variant (cull_kernel_lean.cuh): same results, not yet validated on a GPU
-	static const bool lean = getenv("LB200_CULL_LEAN") != nullptr && atoi(getenv("LB200_CULL_LEAN")) != 0;
-	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, lean ? cull_pages_lean_kernel<256> : cull_pages_kernel<256>, P, (const lb200_page_desc*)(cs->d_desc + off),
-		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), out, cur, nxt,
-		xchg ? (uint32_t*)nullptr : mask));
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cull_classify_kernel, P, (const lb200_page_desc*)(cs->d_desc + off),
+		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), cur, test_items, copy_items, mask_arg));
 	LB200_CHECK_LAUNCH(ctx);
-	cs->last_counters = cur; cs->last_out = out; cs->last_mask = xchg ? nullptr : mask; // exchange culls keep their rows in the slabs
+	static const bool skip_work = getenv("LB200_DEBUG_SKIP_WORK") != nullptr; // profiling only: results are not produced
+	if (skip_work) { cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask_arg; cs->last_pages = h.high_water; if (!xchg) ++cs->seq; return LB200_OK; }
+	// work: persistent grid, one warp per listed page; never more warps than pages
+	const uint32_t resident = (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid);
+	const uint32_t blocks = std::max(1u, std::min(resident, (h.high_water + WORK_WARPS - 1) / WORK_WARPS));
+	cfg.gridDim = dim3(blocks);
+	cfg.blockDim = dim3(WORK_THREADS);
+	cfg.dynamicSmemBytes = WORK_SMEM;
+	cfg.numAttrs = no_pdl ? 0 : 1;
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cull_work_kernel, P, (const float4*)(cs->d_spheres + off * PAGE_SLOTS),
+		(const int*)(cs->d_entities + off * PAGE_SLOTS), (const TestItem*)test_items, (const CopyItem*)copy_items, out, cur, nxt, mask_arg));
+	LB200_CHECK_LAUNCH(ctx);
+	cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask_arg; // exchange culls keep their rows in the slabs
 	cs->lane_parity[lane] ^= 1u;
 	if (!xchg) ++cs->seq;
 	cs->last_pages = h.high_water;
-	cs->last_blocks = blocks;
-	cs->last_chunk = chunk;
-	cs->last_rows_per_block = rpb;
 	return LB200_OK;
 }
 
@@ -589,7 +607,8 @@ void lb200_culling_destroy(lb200_culling* cs) {
 		if (cs->fork_event) cudaEventDestroy(cs->fork_event);
 		if (cs->done_event) cudaEventDestroy(cs->done_event);
 		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_out_ids); cudaFree(cs->d_mask);
-		cudaFree(cs->d_counters); cudaFree(cs->d_stage); cudaFree(cs->d_gather_ids); cudaFree(cs->d_gather_counts); cudaFree(cs->d_slab);
+		cudaFree(cs->d_counters); cudaFree(cs->d_stage); cudaFree(cs->d_gather_ids); cudaFree(cs->d_slab);
+		cudaFree(cs->d_test_items); cudaFree(cs->d_copy_items);
 		if (cs->h_counters) cudaFreeHost(cs->h_counters);
 		if (cs->h_stage) cudaFreeHost(cs->h_stage);
 	}
@@ -848,17 +867,54 @@ int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t 
 	const lb::CullingHost& h = cs->host;
 	const size_t n = h.cells.size();
 	if (capacity_words < n * 8) return LB200_ERR_CAPACITY;
-	if (!cs->last_blocks) { lb200_set_error(cs->ctx, "read_bitmask needs a preceding cull"); return LB200_ERR_STATE; }
+	if (!cs->last_pages) { lb200_set_error(cs->ctx, "read_bitmask needs a preceding cull"); return LB200_ERR_STATE; }
 	if (!cs->last_mask) { lb200_set_error(cs->ctx, "the last cull was an exchange step: its visibility rows are in the exchanged slabs"); return LB200_ERR_STATE; }
-	std::vector<uint32_t> tmp((size_t)cs->last_blocks * cs->last_rows_per_block * 8);
+	std::vector<uint32_t> tmp((size_t)cs->last_pages * 8);
 	LB200_CUDA(cs->ctx, cudaMemcpyAsync(tmp.data(), cs->last_mask, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, cs->ctx->stream));
 	LB200_CUDA(cs->ctx, cudaStreamSynchronize(cs->ctx->stream));
 	for (size_t i = 0; i < n; ++i) {
 		const uint32_t p = h.cells[i];
 		if (p >= cs->last_pages) { memset(out_words + 8 * i, 0, sizeof(uint32_t) * 8); continue; } // page created after the last cull
-		const size_t row = (size_t)(p % cs->last_blocks) * cs->last_rows_per_block + p / cs->last_blocks;
-		memcpy(out_words + 8 * i, tmp.data() + 8 * row, sizeof(uint32_t) * 8);
+		memcpy(out_words + 8 * i, tmp.data() + 8 * (size_t)p, sizeof(uint32_t) * 8);
 	}
+	return LB200_OK;
+}
+
+// Device time of ONE cull that has the device to itself (the latency of a lone view): per iteration a short delay kernel, then
+// event / cull / event enqueued while it runs, so the interval holds no host launch latency and nothing overlaps the cull.
+int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t iters, float* out_ms) {
+	if (!cs || !frustum || !out_ms || !iters) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	lb200_ctx* ctx = cs->ctx;
+	if (cs->host.cells.empty()) return LB200_ERR_STATE;
+	int rc = flushPages(cs);
+	if (rc) return rc;
+	cudaEvent_t e0, e1;
+	LB200_CUDA(ctx, cudaEventCreate(&e0));
+	LB200_CUDA(ctx, cudaEventCreate(&e1));
+	for (uint32_t i = 0; i < iters; ++i) {
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		delay_kernel<<<1, 32, 0, ctx->stream>>>(200000); // ~100 us
+		LB200_CHECK_LAUNCH(ctx);
+		LB200_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+		static const int mode = getenv("LB200_LONE_MODE") ? atoi(getenv("LB200_LONE_MODE")) : 0; // profiling: 2 = nothing, 3 = two empty kernels
+		if (mode == 3) { delay_kernel<<<148, 128, 0, ctx->stream>>>(0); delay_kernel<<<592, 256, 0, ctx->stream>>>(0); }
+		else if (mode != 2) rc = launchCull(cs, frustum, type);
+		if (rc) break;
+		LB200_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+		LB200_CUDA(ctx, cudaEventSynchronize(e1));
+		LB200_CUDA(ctx, cudaEventElapsedTime(&out_ms[i], e0, e1));
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	cs->has_last = false;
+	return rc;
+}
+
+// Profiling aid: the %globaltimer stamps of the last cull launched with LB200_CULL_TRACE=1 — out[kernel 0..1][block 0..2047][point 0..7] (ns).
+int lb200_culling_read_trace(lb200_culling* cs, uint64_t* out) {
+	if (!cs || !cs->ctx || !out) return LB200_ERR_INVALID;
+	LB200_CUDA(cs->ctx, cudaStreamSynchronize(cs->ctx->stream));
+	LB200_CUDA(cs->ctx, cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)));
 	return LB200_OK;
 }
 
@@ -919,7 +975,9 @@ int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* fr
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
 	lb200_ctx* ctx = cs->ctx;
 	if (cs->host.cells.empty()) { lb200_set_error(ctx, "cull_gather on an empty culling system"); return LB200_ERR_STATE; }
-	int rc = launchCull(cs, frustum, type);
+	int rc = lb200_comm_check(ctx);
+	if (rc) return rc;
+	rc = launchCull(cs, frustum, type);
 	if (rc) return rc;
 	const uint32_t* cur = cs->last_counters;
 	cs->has_last = false;
@@ -938,12 +996,8 @@ int lb200_culling_cull_gather(lb200_culling* cs, const lb200_shifted_frustum* fr
 		}
 		pack_push_kernel<<<ctx->sm_count * pushGridMul(), 256, 0, ctx->stream>>>(PP, cur, cs->last_out, peer.done_counter);
 		LB200_CHECK_LAUNCH(ctx);
-		if (!cs->d_gather_counts) {
-			LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
-			LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
-		}
 		if (!(dbg & 1u)) {
-			wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, epoch, peer.n_buffers, cs->d_gather_counts);
+			wait_peers_kernel<<<1, 32, 0, ctx->stream>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, epoch, peer.n_buffers, peer.d_timeout);
 			LB200_CHECK_LAUNCH(ctx);
 		}
 		if (out_dev_slabs) *out_dev_slabs = peer.gather[epoch % peer.n_buffers][ctx->rank];
@@ -971,17 +1025,11 @@ static int prepareExchange(lb200_culling* cs, const lb200_shifted_frustum* frust
 	int rc = flushPages(cs); // uploads (if any) go to the context stream, before any lane forks from it
 	if (rc) return rc;
 	if (peer.lanes != cs->lanes) { lb200_set_error(ctx, "exchange lanes (%u) differ from cull lanes (%u)", peer.lanes, cs->lanes); return LB200_ERR_STATE; }
-	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, (uint32_t)cs->grid_lanes, cs->host.high_water, &chunk, &blocks, &rpb);
-	if (XHEADER_WORDS + 8 * (size_t)blocks * rpb > peer.slab_words) {
-		lb200_set_error(ctx, "exchange slab too small: %zu words needed, %zu mapped", XHEADER_WORDS + 8 * (size_t)blocks * rpb, peer.slab_words);
+	if (exchangeSlabWords(cs) > peer.slab_words) {
+		lb200_set_error(ctx, "exchange slab too small: %zu words needed, %zu mapped", exchangeSlabWords(cs), peer.slab_words);
 		return LB200_ERR_CAPACITY;
 	}
-	if (!cs->d_gather_counts) {
-		LB200_CUDA(ctx, cudaMalloc(&cs->d_gather_counts, sizeof(uint32_t)));
-		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_gather_counts, 0, sizeof(uint32_t), ctx->stream));
-	}
-	return LB200_OK;
+	return lb200_comm_check(ctx);
 }
 
 // one exchange step on `stream` (nullptr = the context stream): the cull kernel stores rows + counts into every rank and raises this
@@ -995,7 +1043,7 @@ static int exchangeStep(lb200_culling* cs, const lb200_shifted_frustum* frustum,
 	if (rc) return rc;
 	PublishParams PP;
 	PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = x.epoch; PP.n_buffers = peer.n_buffers;
-	PP.n_pages = cs->last_pages; PP.blocks = cs->last_blocks; PP.rows_per_block = cs->last_rows_per_block; PP.chunk = cs->last_chunk;
+	PP.n_pages = cs->last_pages; PP.item_cap = cs->item_cap;
 	for (int r = 0; r < LB200_MAX_RANKS; ++r) {
 		PP.dst[r] = r < ctx->n_ranks ? peer.gather[x.epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
 		PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
@@ -1009,7 +1057,7 @@ static int exchangeStep(lb200_culling* cs, const lb200_shifted_frustum* frustum,
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, publish_wait_kernel, PP, (const uint32_t*)cs->last_counters, cs->d_gather_counts));
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, publish_wait_kernel, PP, (const uint32_t*)cs->last_counters, peer.d_timeout));
 	LB200_CHECK_LAUNCH(ctx);
 	if (epoch_out) *epoch_out = x.epoch;
 	return LB200_OK;
@@ -1068,9 +1116,7 @@ int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum
 
 uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs) {
 	if (!cs || !cs->ctx || ensureDevice(cs) != LB200_OK) return 0;
-	uint32_t chunk, blocks, rpb;
-	cullGeometry(cs, (uint32_t)cs->grid_lanes, cs->host.high_water, &chunk, &blocks, &rpb);
-	return XHEADER_WORDS + 8u * blocks * rpb;
+	return (uint32_t)exchangeSlabWords(cs);
 }
 
 int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t** out_dev_ids, uint32_t* out_counts) {

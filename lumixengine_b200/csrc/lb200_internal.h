@@ -12,7 +12,7 @@
 #include <string.h>
 
 #define LB200_MAX_RANKS 8
-#define LB200_MAX_LANES 4  // concurrent culls (streams / output lanes); exchange buffers = 2 x lanes
+#define LB200_MAX_LANES 8  // concurrent culls (streams / output lanes); exchange buffers = 2 x lanes
 
 struct lb200_ctx {
 	int device = -1;
@@ -34,12 +34,16 @@ struct lb200_ctx {
 		// issued on stream e % lanes.  A rank overwrites buffer b for epoch e only after its wait for epoch e - lanes on the same
 		// stream, i.e. after every rank published e - lanes, which every rank issues behind whatever consumed e - 2 x lanes there.
 		uint32_t lanes = 1, n_buffers = 2;
-		void* local_block = nullptr;      // this rank's allocation: [flags n_buffers x 8 x u32 in 256 B][gather 0] .. [gather n_buffers-1]
+		void* local_block = nullptr;      // this rank's allocation: [flags n_buffers x 8 x u32 in 512 B][gather 0] .. [gather n_buffers-1]
 		uint32_t* gather[2 * LB200_MAX_LANES][LB200_MAX_RANKS] = {}; // gather[b][r] = rank r's buffer b as seen from this process
 		uint32_t* flags[LB200_MAX_RANKS] = {};     // flags[r] = rank r's flag block
 		void* opened[LB200_MAX_RANKS] = {};        // cudaIpcOpenMemHandle results to close
 		uint32_t* done_counter = nullptr; // local, one per lane, for the last-block election
 		uint32_t epoch = 0;
+		// a wait kernel that gave up on a peer (~4 s) raises this word; page-locked + mapped so the host sees it without a copy.
+		// lb200_comm_check() turns it into LB200_ERR_NCCL and resets it (called by lb200_synchronize and every exchange entry point)
+		uint32_t* h_timeout = nullptr;
+		uint32_t* d_timeout = nullptr;
 	} peer;
 };
 
@@ -53,6 +57,7 @@ struct lb200_range {
 	lb200_range(const lb200_range&) = delete;
 	lb200_range& operator=(const lb200_range&) = delete;
 };
+int lb200_comm_check(lb200_ctx* ctx); // comm.cu: LB200_ERR_NCCL (and reset) if a peer wait timed out since the last check
 uint32_t lb200_cull_lanes(); // LB200_CULL_LANES, default 3, 1..LB200_MAX_LANES (context.cu)
 
 #define LB200_CUDA(ctx, expr)                                                                        \

@@ -239,6 +239,12 @@ class CullingSystem:
         self._err(self.L.lb200_culling_read_bitmask(self.h, ptr(out), C.c_uint32(len(out))))
         return out[:n * 8].reshape(n, 8)
 
+    def time_lone_cull(self, frustum, iters=20, type=TYPE_ALL):
+        """Device time (ms, per iteration) of single culls that have the device to themselves, launches pre-queued (no host latency)."""
+        out = np.zeros(iters, np.float32)
+        self._err(self.L.lb200_culling_time_lone_cull(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(iters), ptr(out)))
+        return out
+
     def last_algorithmic_bytes(self):
         return int(self.L.lb200_culling_last_algorithmic_bytes(self.h))
 
@@ -277,15 +283,19 @@ class CullingSystem:
         return (ids.value or 0), (slabs.value or 0), int(stride.value)
 
     def read_exchanged(self, slabs_ptr, stride, n_ranks):
-        """Host copy of the exchanged slabs -> per rank dict(counts[256], n_pages, blocks, rows_per_block, mask[n_pages, 8] by page id)."""
+        """Host copy of the exchanged slabs -> per rank dict(counts[256], n_pages, n_test, n_copy, mask[n_pages, 8] by page id).
+        A slab holds {page id, visibility row} records of the pages the rank worked on (cull_kernel.cuh): tested pages from the front of the
+        record area, copied pages from its back; every other page's row is zero."""
         host = self.ctx.copy_to_host(slabs_ptr, stride * n_ranks, np.uint32).reshape(n_ranks, stride)
         out = []
         for r in range(n_ranks):
-            n_pages, blocks, rpb, chunk = (int(v) for v in host[r, 256:260])
-            rows = host[r, 264:264 + 8 * blocks * rpb].reshape(blocks * rpb, 8)
-            p = np.arange(n_pages)
-            out.append(dict(counts=host[r, :256].copy(), n_pages=n_pages, blocks=blocks, rows_per_block=rpb, chunk=chunk,
-                            mask=rows[(p % max(blocks, 1)) * rpb + p // max(blocks, 1)].copy()))
+            n_pages, n_test, n_copy, cap = (int(v) for v in host[r, 256:260])
+            pages = host[r, 264:264 + cap]
+            rows = host[r, 264 + cap:264 + 9 * cap].reshape(cap, 8)
+            rec = np.concatenate([np.arange(n_test), cap - 1 - np.arange(n_copy)]).astype(np.int64)
+            mask = np.zeros((n_pages, 8), np.uint32)
+            mask[pages[rec]] = rows[rec]
+            out.append(dict(counts=host[r, :256].copy(), n_pages=n_pages, n_test=n_test, n_copy=n_copy, mask=mask))
         return out
 
     def read_gathered(self, dev_ptr, slab_ids, n_ranks, stride=None):

@@ -22,7 +22,9 @@ for name, f in cases.items():
     for _ in range(n): cs.cull_device(f, want_counts=False)
     ctx.record(e1); ms_py = ctx.elapsed_ms(e0, e1) / n
     ctx.synchronize(); ctx.record(e0); cs.cull_device_n(f, n); ctx.record(e1); ms = ctx.elapsed_ms(e0, e1) / n
+    lone = cs.time_lone_cull(f, 40)  # one cull on an idle device, launches pre-queued behind a delay kernel
+    lone_us = float(sorted(lone)[len(lone) // 2]) * 1e3
     _, res = cs.cull_device(f, want_counts=True)
     b = cs.last_algorithmic_bytes()
-    print(f"CULLVAR {name:12s} {ms*1e3:7.2f} us (python loop {ms_py*1e3:6.2f})  visible {res.total:9d} tested_pages {res.pages_tested:6d} inside {res.pages_inside:6d} ent_tested {res.entities_tested:9d} bytes {b/1e6:7.1f} MB  {b/ms/1e6:7.0f} GB/s")
+    print(f"CULLVAR {name:12s} {ms*1e3:7.2f} us (python loop {ms_py*1e3:6.2f})  visible {res.total:9d} tested_pages {res.pages_tested:6d} inside {res.pages_inside:6d} ent_tested {res.entities_tested:9d} bytes {b/1e6:7.1f} MB  {b/ms/1e6:7.0f} GB/s  lone {lone_us:6.2f} us = {b/lone_us/1e3:6.0f} GB/s")
 cs.close(); ctx.close()

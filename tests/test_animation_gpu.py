@@ -184,8 +184,6 @@ def test_blend_layers_match_oracle(ctx, oracle):
     anim.close()
 
 
-@pytest.mark.skipif(os.environ.get("LB200_RUN_UNVALIDATED", "0") in ("", "0"),
-                    reason="written after the round's GPU budget was spent (DESIGN.md section 11): set LB200_RUN_UNVALIDATED=1 to run it")
 def test_random_skeletons_and_clips(ctx, oracle):
     """Randomised parity run: 1..196 bones, 1..90 frames, 5..18-bit channels, any share of constant tracks, several clips per system,
     times inside / at / beyond the clip end; pose, both palettes and the advanced time against the oracle."""
@@ -217,8 +215,6 @@ def test_random_skeletons_and_clips(ctx, oracle):
         anim.close()
 
 
-@pytest.mark.skipif(os.environ.get("LB200_RUN_UNVALIDATED", "0") in ("", "0"),
-                    reason="written after the round's GPU budget was spent (DESIGN.md section 11): set LB200_RUN_UNVALIDATED=1 to run it")
 def test_bone_attachments_match_oracle(ctx, oracle):
     """updateBoneAttachment batched (render_module.cpp:377-405): entities following bones of posed instances."""
     n_inst = 200
