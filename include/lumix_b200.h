@@ -221,7 +221,7 @@ LB200_API int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, cons
  * (256 + slab_ids on the NCCL path, the fixed peer-buffer stride after lb200_comm_enable_p2p). */
 LB200_API uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, uint32_t slab_ids);
 
-/* Bitmask exchange: the cull's work kernel itself stores the 32-byte visibility row of every page it worked on — together
+/* Bitmask exchange: the cull kernel itself stores the 32-byte visibility row of every page it worked on — together
  * with the page id — straight into EVERY rank's memory over NVLink (no separate pack / collective launch; rows of pages outside the
  * frustum are all zero and never cross the links); a one-block kernel behind it sends the per-type counts and raises the epoch flags.
  * The visible ids stay sharded on the rank that owns the entities (*out_dev_ids, per-type segments as in lb200_culling_cull_device).
@@ -229,10 +229,9 @@ LB200_API uint32_t lb200_culling_gather_stride_words(const lb200_culling* cs, ui
  * stream; when the stream reaches the end of this call every rank's slab of this step is complete in *out_dev_slabs.
  * Slab of rank r = words [r * stride, (r + 1) * stride):
  *   [0,256)            visible count per renderable type
- *   [256,264)          n_pages, n_test, n_copy, cap, 0, 0, 0, 0
- *   [264, 264 + cap)   page id of record i (page ids of rank r)
+ *   [256,264)          n_pages, n_records, 0, cap, 0, 0, 0, 0
+ *   [264, 264 + cap)   page id of record i < n_records (page ids of rank r)
  *   [264 + cap, ..)    8 words per record: bit s of the 256-bit row = slot s of the page is visible (slots >= 200 are 0)
- *   valid records: [0, n_test) (pages that went through sphere tests) and (cap - 1 - j) for j in [0, n_copy) (pages copied whole);
  *   every page without a record has an all-zero row.
  * A peer that does not publish within ~4 s makes the next lb200_synchronize / exchange call return LB200_ERR_NCCL (lb200_comm_status). */
 LB200_API int lb200_culling_cull_exchange(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, const uint32_t** out_dev_ids,

@@ -209,8 +209,7 @@ __global__ void __launch_bounds__(288) publish_wait_kernel(const __grid_constant
 		uint32_t v = 0;
 		if (i < 256) v = __ldcg(counters + i);
 		else if (i == 256) v = P.n_pages;
-		else if (i == 257) v = __ldcg(counters + CNT_N_TEST);
-		else if (i == 258) v = __ldcg(counters + CNT_N_COPY);
+		else if (i == 257) v = __ldcg(counters + CNT_N_REC);
 		else if (i == 259) v = P.item_cap;
 		for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][i] = v;
 	}
@@ -276,9 +275,7 @@ struct lb200_culling {
 	uint32_t out_cap = 0;
 	uint32_t* d_mask = nullptr;     // lanes * mask_words; row of page p = words [8p, 8p + 8)
 	size_t mask_words = 0;
-	lbcull::TestItem* d_test_items = nullptr; // lanes * item_cap: work lists of the classify kernel
-	lbcull::CopyItem* d_copy_items = nullptr; // lanes * item_cap
-	uint32_t item_cap = 0;
+	uint32_t item_cap = 0; // record capacity of an exchange slab
 	bool uploaded_since_last_cull = true; // the next cull's kernels are launched plain (no programmatic overlap with the upload)
 	uint32_t* d_counters = nullptr; // lanes * 2 * COUNTER_WORDS: [lane][parity]
 	// asynchronous host delivery (lb200_culling_cull_begin / _poll / _end)
@@ -294,6 +291,9 @@ struct lb200_culling {
 	int grid = 0;       // resident blocks of a cull that has the device to itself
 	int grid_lanes = 0; // resident blocks of a cull issued by cull_device_n (runs next to its neighbours)
 	int threads = 256;
+	int stage_depth = 0;   // pages in flight per warp through the bulk-copy engine (0: straight loads), LB200_CULL_STAGE
+	size_t smem = 0;
+	void (*kernel)(const lbcull::CullParams, const lb200_page_desc*, const float4*, const int*, uint32_t*, uint32_t*, uint32_t*, uint32_t*) = nullptr;
 	// staging for sparse dirty uploads
 	uint8_t* h_stage = nullptr;
 	uint8_t* d_stage = nullptr;
@@ -323,10 +323,13 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS, ctx->stream));
 		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocMapped));
 		if (cudaHostGetDevicePointer((void**)&cs->h_counters_dev, cs->h_counters, 0) != cudaSuccess) { cudaGetLastError(); cs->h_counters_dev = nullptr; }
-		cs->threads = WORK_THREADS;
+		cs->threads = CULL_THREADS;
 		int per_sm = 0;
-		LB200_CUDA(ctx, cudaFuncSetAttribute(cull_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORK_SMEM));
-		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cull_work_kernel, WORK_THREADS, WORK_SMEM));
+		cs->stage_depth = getenv("LB200_CULL_STAGE") ? std::max(0, std::min(2, atoi(getenv("LB200_CULL_STAGE")))) : LB200_CULL_STAGE_DEFAULT;
+		cs->kernel = cs->stage_depth == 0 ? cull_pages_kernel<0> : (cs->stage_depth == 1 ? cull_pages_kernel<1> : cull_pages_kernel<2>);
+		cs->smem = cull_smem_bytes(cs->stage_depth);
+		LB200_CUDA(ctx, cudaFuncSetAttribute(cs->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs->smem));
+		LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cs->kernel, CULL_THREADS, cs->smem));
 		if (per_sm < 1) per_sm = 1;
 		cs->grid = ctx->sm_count * per_sm;
 		// cull_device_n runs independent culls concurrently: half-occupancy grids let two of them share every SM, so one cull's
@@ -339,17 +342,15 @@ int ensureDevice(lb200_culling* cs) {
 		uint32_t cap = cs->dev_cap ? cs->dev_cap : 1024;
 		while (cap < h.high_water) cap *= 2;
 		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_mask); cudaFree(cs->d_test_items); cudaFree(cs->d_copy_items);
-		cs->d_spheres = nullptr; cs->d_entities = nullptr; cs->d_desc = nullptr; cs->d_mask = nullptr; cs->d_test_items = nullptr; cs->d_copy_items = nullptr;
+		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_mask);
+		cs->d_spheres = nullptr; cs->d_entities = nullptr; cs->d_desc = nullptr; cs->d_mask = nullptr;
 		const size_t R = cs->replicas;
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_spheres, sizeof(float4) * PAGE_SLOTS * (size_t)cap * R));
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_entities, sizeof(int) * PAGE_SLOTS * (size_t)cap * R));
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_desc, sizeof(lb200_page_desc) * (size_t)cap * R));
 		cs->mask_words = 8 * (size_t)cap;
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_mask, sizeof(uint32_t) * cs->mask_words * cs->lanes));
-		cs->item_cap = cap; // every page can end up in one of the two lists
-		LB200_CUDA(ctx, cudaMalloc(&cs->d_test_items, sizeof(TestItem) * (size_t)cap * cs->lanes));
-		LB200_CUDA(ctx, cudaMalloc(&cs->d_copy_items, sizeof(CopyItem) * (size_t)cap * cs->lanes));
+		cs->item_cap = cap; // every page can end up with a record
 		// free / never-used pages must read count == 0
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_desc, 0, sizeof(lb200_page_desc) * (size_t)cap * R, ctx->stream));
 		cs->dev_cap = cap;
@@ -476,8 +477,6 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	uint32_t* nxt = cs->d_counters + ((size_t)lane * 2 + (cs->lane_parity[lane] ^ 1u)) * COUNTER_WORDS;
 	uint32_t* out = cs->d_out_ids + (size_t)lane * cs->out_cap;
 	uint32_t* mask = cs->d_mask + (size_t)lane * cs->mask_words;
-	TestItem* test_items = cs->d_test_items + (size_t)lane * cs->item_cap;
-	CopyItem* copy_items = cs->d_copy_items + (size_t)lane * cs->item_cap;
 	P.n_ranks = 0;
 	for (int r = 0; r < LB200_MAX_RANKS; ++r) P.xdst[r] = nullptr;
 	if (xchg) {
@@ -487,39 +486,33 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	}
 	static const bool no_mask = getenv("LB200_NO_PLANE_MASKING") != nullptr;
 	P.plane_masking = (h.n_bad_radius == 0 && !no_mask) ? 1u : 0u;
-	// Programmatic stream serialization.  The classify kernel only READS scene data (descriptors; L2 prefetches of page rows) before its
-	// cudaGridDependencySynchronize(): unless something was uploaded since the last cull it may overlap the tail of whatever kernel
-	// precedes it on the stream — for back-to-back views (main, shadow cascades, lights) that is the previous cull's work kernel, which
-	// releases its dependents at its first instruction.  The flag is sticky: whichever call uploaded (flush, set_many, ...), the first
-	// cull after it is launched plain.  The work kernel always follows its own classify kernel and is always launched this way.
+	// Programmatic stream serialization: the kernel's prologue (up to cudaGridDependencySynchronize: descriptor reads, classification, the
+	// sphere tests of round 0, whose results sit in shared memory) only READS scene data.  Those arrays are written by flushPages alone, so
+	// unless something was uploaded since the last cull the prologue may overlap the tail of whatever kernel precedes it on the stream —
+	// for back-to-back views (main, shadow cascades, lights) that is the previous cull, which releases its dependents at its first
+	// instruction.  The flag is sticky: whichever call uploaded (flush, set_many, ...), the first cull after it is launched plain.
 	static const bool no_pdl = getenv("LB200_NO_PDL") != nullptr;
 	const bool pdl = !no_pdl && !cs->uploaded_since_last_cull;
 	cs->uploaded_since_last_cull = false;
+	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
+	const uint32_t resident = (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid);
+	uint32_t chunk = (h.high_water + resident - 1) / resident;
+	chunk = std::max(32u, std::min((uint32_t)MAX_CHUNK, chunk));
+	const uint32_t blocks = std::max(1u, std::min(resident, (h.high_water + chunk - 1) / chunk));
+	P.chunk = chunk;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(blocks);
+	cfg.blockDim = dim3(CULL_THREADS);
+	cfg.dynamicSmemBytes = cs->smem;
 	cfg.stream = stream ? stream : ctx->stream;
 	cfg.attrs = attr;
-	uint32_t* mask_arg = xchg ? (uint32_t*)nullptr : mask;
-	// classify: one thread per page
-	cfg.gridDim = dim3((h.high_water + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS);
-	cfg.blockDim = dim3(CLASSIFY_THREADS);
 	cfg.numAttrs = pdl ? 1 : 0;
-	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cull_classify_kernel, P, (const lb200_page_desc*)(cs->d_desc + off),
-		(const float4*)(cs->d_spheres + off * PAGE_SLOTS), (const int*)(cs->d_entities + off * PAGE_SLOTS), cur, test_items, copy_items, mask_arg));
-	LB200_CHECK_LAUNCH(ctx);
-	static const bool skip_work = getenv("LB200_DEBUG_SKIP_WORK") != nullptr; // profiling only: results are not produced
-	if (skip_work) { cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask_arg; cs->last_pages = h.high_water; if (!xchg) ++cs->seq; return LB200_OK; }
-	// work: persistent grid, one warp per listed page; never more warps than pages
-	const uint32_t resident = (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid);
-	const uint32_t blocks = std::max(1u, std::min(resident, (h.high_water + WORK_WARPS - 1) / WORK_WARPS));
-	cfg.gridDim = dim3(blocks);
-	cfg.blockDim = dim3(WORK_THREADS);
-	cfg.dynamicSmemBytes = WORK_SMEM;
-	cfg.numAttrs = no_pdl ? 0 : 1;
-	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cull_work_kernel, P, (const float4*)(cs->d_spheres + off * PAGE_SLOTS),
-		(const int*)(cs->d_entities + off * PAGE_SLOTS), (const TestItem*)test_items, (const CopyItem*)copy_items, out, cur, nxt, mask_arg));
+	uint32_t* mask_arg = xchg ? (uint32_t*)nullptr : mask;
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, cs->kernel, P, (const lb200_page_desc*)(cs->d_desc + off), (const float4*)(cs->d_spheres + off * PAGE_SLOTS),
+		(const int*)(cs->d_entities + off * PAGE_SLOTS), out, cur, nxt, mask_arg));
 	LB200_CHECK_LAUNCH(ctx);
 	cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask_arg; // exchange culls keep their rows in the slabs
 	cs->lane_parity[lane] ^= 1u;
@@ -608,7 +601,6 @@ void lb200_culling_destroy(lb200_culling* cs) {
 		if (cs->done_event) cudaEventDestroy(cs->done_event);
 		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_out_ids); cudaFree(cs->d_mask);
 		cudaFree(cs->d_counters); cudaFree(cs->d_stage); cudaFree(cs->d_gather_ids); cudaFree(cs->d_slab);
-		cudaFree(cs->d_test_items); cudaFree(cs->d_copy_items);
 		if (cs->h_counters) cudaFreeHost(cs->h_counters);
 		if (cs->h_stage) cudaFreeHost(cs->h_stage);
 	}
@@ -898,7 +890,7 @@ int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum*
 		LB200_CHECK_LAUNCH(ctx);
 		LB200_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
 		static const int mode = getenv("LB200_LONE_MODE") ? atoi(getenv("LB200_LONE_MODE")) : 0; // profiling: 2 = nothing, 3 = two empty kernels
-		if (mode == 3) { delay_kernel<<<148, 128, 0, ctx->stream>>>(0); delay_kernel<<<592, 256, 0, ctx->stream>>>(0); }
+		if (mode == 3) delay_kernel<<<592, 256, 0, ctx->stream>>>(0);
 		else if (mode != 2) rc = launchCull(cs, frustum, type);
 		if (rc) break;
 		LB200_CUDA(ctx, cudaEventRecord(e1, ctx->stream));

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #define LB200_MAX_RANKS 8
+#define LB200_CULL_STAGE_DEFAULT 0 // pages in flight per warp through the bulk-copy engine (cull_kernel.cuh); LB200_CULL_STAGE overrides
 #define LB200_MAX_LANES 8  // concurrent culls (streams / output lanes); exchange buffers = 2 x lanes
 
 struct lb200_ctx {

@@ -283,19 +283,17 @@ class CullingSystem:
         return (ids.value or 0), (slabs.value or 0), int(stride.value)
 
     def read_exchanged(self, slabs_ptr, stride, n_ranks):
-        """Host copy of the exchanged slabs -> per rank dict(counts[256], n_pages, n_test, n_copy, mask[n_pages, 8] by page id).
-        A slab holds {page id, visibility row} records of the pages the rank worked on (cull_kernel.cuh): tested pages from the front of the
-        record area, copied pages from its back; every other page's row is zero."""
+        """Host copy of the exchanged slabs -> per rank dict(counts[256], n_pages, n_records, mask[n_pages, 8] by page id).
+        A slab holds one {page id, visibility row} record per page the rank worked on (cull_kernel.cuh); every other page's row is zero."""
         host = self.ctx.copy_to_host(slabs_ptr, stride * n_ranks, np.uint32).reshape(n_ranks, stride)
         out = []
         for r in range(n_ranks):
-            n_pages, n_test, n_copy, cap = (int(v) for v in host[r, 256:260])
-            pages = host[r, 264:264 + cap]
-            rows = host[r, 264 + cap:264 + 9 * cap].reshape(cap, 8)
-            rec = np.concatenate([np.arange(n_test), cap - 1 - np.arange(n_copy)]).astype(np.int64)
+            n_pages, n_rec, _, cap = (int(v) for v in host[r, 256:260])
+            pages = host[r, 264:264 + n_rec]
+            rows = host[r, 264 + cap:264 + cap + 8 * n_rec].reshape(n_rec, 8)
             mask = np.zeros((n_pages, 8), np.uint32)
-            mask[pages[rec]] = rows[rec]
-            out.append(dict(counts=host[r, :256].copy(), n_pages=n_pages, n_test=n_test, n_copy=n_copy, mask=mask))
+            mask[pages] = rows
+            out.append(dict(counts=host[r, :256].copy(), n_pages=n_pages, n_records=n_rec, mask=mask))
         return out
 
     def read_gathered(self, dev_ptr, slab_ids, n_ranks, stride=None):

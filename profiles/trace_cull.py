@@ -13,8 +13,7 @@ cs = lb.CullingSystem(ctx); cs.set_replicas(8)
 cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"]); cs.flush()
 A = scenes.c2_frustum_args()
 views = {"c2_default": lb.frustum_perspective(**A), "nothing": lb.frustum_perspective(**dict(A, position=(1e6, 0.0, 1e6), far=100.0))}
-names = [["start", "A1 done", "A2 done", "prefetch issued", "grid dep", "claims done", "items written"],
-         ["start", "grid dep", "T done", "C done", "claims visible", "W done"]]
+names = [["start", "A1 done", "A2 done", "B done", "grid dep", "all rounds done"], []]
 for name, f in views.items():
     cs.time_lone_cull(f, 5)
     for rep in range(2):
@@ -24,7 +23,7 @@ for name, f in views.items():
         grids = [(cs.ctx and (10_000_000 // 180)), 0]
         k0 = out[0]; nb0 = int((k0[:, 0] > 0).sum()); k1 = out[1]; nb1 = int((k1[:, 0] > 0).sum())
         t0 = int(k0[:nb0, 0].min())
-        print(f"TRACE {name} rep {rep}: lone {t:.2f} us; classify blocks {nb0}, work blocks {nb1}")
+        print(f"TRACE {name} rep {rep}: lone {t:.2f} us; classify blocks {nb0}, second kernel blocks {nb1}")
         for k, (arr, nb) in enumerate(((k0, nb0), (k1, nb1))):
             for p, label in enumerate(names[k]):
                 v = (arr[:nb, p].astype(np.int64) - t0) / 1e3
