@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 {
 	extern __shared__ __align__(128) unsigned char s_dyn[];
 	__shared__ WorkItem s_item[MAX_CHUNK];
-	__shared__ __align__(16) uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // [ROWS] = visible count, then offset of the page inside its type's output segment
+	__shared__ __align__(16) uint32_t s_bal[MAX_CHUNK][ROWS + 1]; // the 256-bit visibility row of a tested page ([ROWS] = 0)
+	__shared__ uint32_t s_off[MAX_CHUNK];                         // visible ids of the page, then its offset inside out_ids
 	__shared__ uint16_t s_cand[MAX_CHUNK]; // classify threads whose page survived the cheap pass
 	__shared__ uint32_t s_stats[N_STATS];
 	__shared__ uint32_t s_zpage[MAX_CHUNK]; // page whose mask row is zero (ends without work), or ~0
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 				uint4* it = reinterpret_cast<uint4*>(&s_item[slot]);
 				it[0] = make_uint4(page, count | (type << 8) | ((uint32_t)cls << 16) | (need << 24), __float_as_uint(rd[0]), __float_as_uint(rd[1]));
 				it[1] = make_uint4(__float_as_uint(rd[2]), __float_as_uint(rd[3]), __float_as_uint(rd[4]), __float_as_uint(rd[5]));
+				if (cls == CLS_COPY) s_off[slot] = count; // culling_system.cpp:345-360: every entity of the page is visible
 			}
 			else s_zpage[t0] = page;
 		}
@@ -311,38 +313,29 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 		// listed page w: s_item[item_index(w)] — the COPY pages sit at the back of the array
 #define LB_ITEM(w) ((w) < n_test ? (w) : (uint32_t)MAX_CHUNK - 1u - ((w) - n_test))
 
-		// ---------------- B. sphere tests: one warp per listed page, rows staged in shared memory by the bulk-copy engine ----------------
-		// The warp's pages are w = warp, warp + CULL_WARPS, ...; the loads of up to STAGE_DEPTH TEST pages are in flight while one is tested.
+		// ---------------- B. sphere tests: one warp per listed TEST page (w = warp, warp + CULL_WARPS, ... < n_test) ----------------
+		// STAGE_DEPTH > 0: the rows are staged in shared memory by the bulk-copy engine, up to STAGE_DEPTH pages in flight per warp.
 		{
 			uint32_t next_load = warp; // next listed page whose spheres have not been requested
 			uint32_t in_flight = 0, head = 0, tail = 0; // ring of stage buffers: tail = next to fill, head = next to consume
 			auto issue = [&]() {
 				if (STAGE_DEPTH == 0) return;
-				while (in_flight < (uint32_t)STAGE_DEPTH && next_load < n_work) {
-					const uint32_t meta = s_item[LB_ITEM(next_load)].meta;
-					if (((meta >> 16) & 3u) == CLS_TEST) {
-						if (lane == 0) {
-							const uint32_t bar = smem_u32(&s_bar[warp][tail]);
-							const uint32_t bytes = (meta & 0xffu) * 16u;
-							mbar_expect_tx(bar, bytes);
-							bulk_load(smem_u32(stage + (size_t)tail * LB200_PAGE_SLOTS), spheres + (size_t)s_item[LB_ITEM(next_load)].page * LB200_PAGE_SLOTS, bytes, bar);
-						}
-						tail = tail + 1 == (uint32_t)STAGE_DEPTH ? 0 : tail + 1;
-						++in_flight;
+				while (in_flight < (uint32_t)STAGE_DEPTH && next_load < n_test) {
+					if (lane == 0) {
+						const uint32_t bar = smem_u32(&s_bar[warp][tail]);
+						const uint32_t bytes = (s_item[next_load].meta & 0xffu) * 16u;
+						mbar_expect_tx(bar, bytes);
+						bulk_load(smem_u32(stage + (size_t)tail * LB200_PAGE_SLOTS), spheres + (size_t)s_item[next_load].page * LB200_PAGE_SLOTS, bytes, bar);
 					}
+					tail = tail + 1 == (uint32_t)STAGE_DEPTH ? 0 : tail + 1;
+					++in_flight;
 					next_load += CULL_WARPS;
 				}
 			};
 			issue();
-			for (uint32_t w = warp; w < n_work; w += CULL_WARPS) {
-				const uint32_t iw = LB_ITEM(w);
+			for (uint32_t iw = warp; iw < n_test; iw += CULL_WARPS) {
 				const uint4 ia = *reinterpret_cast<const uint4*>(&s_item[iw]);
 				const uint32_t count = ia.y & 0xffu;
-				const int cls = (int)((ia.y >> 16) & 3u);
-				if (cls != CLS_TEST) { // CLS_COPY, culling_system.cpp:345-360: every entity of the page is visible
-					if (lane == 0) s_bal[iw][ROWS] = count;
-					continue;
-				}
 				const uint4 ib = *(reinterpret_cast<const uint4*>(&s_item[iw]) + 1);
 				const uint32_t need = ia.y >> 24;
 				const bool upper = count > 128u; // rows 4-6 exist (warp-uniform): half of the tested pages of a typical scene stop before
@@ -437,7 +430,8 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 				}
 				if (lane == 0) {
 					*reinterpret_cast<uint4*>(&s_bal[iw][0]) = make_uint4(bal[0], bal[1], bal[2], bal[3]);
-					*reinterpret_cast<uint4*>(&s_bal[iw][4]) = make_uint4(bal[4], bal[5], bal[6], page_visible);
+					*reinterpret_cast<uint4*>(&s_bal[iw][4]) = make_uint4(bal[4], bal[5], bal[6], 0u);
+					s_off[iw] = page_visible;
 				}
 			}
 		}
@@ -459,7 +453,7 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 			const bool has = wi < n_work;
 			const uint32_t iwi = LB_ITEM(wi);
 			const uint32_t my_type = has ? ((s_item[iwi].meta >> 8) & 0xffu) : 0xffffu;
-			const uint32_t my_count = has ? s_bal[iwi][ROWS] : 0u;
+			const uint32_t my_count = has ? s_off[iwi] : 0u;
 			const uint32_t n_mine = (n_work + CULL_WARPS - 1 - warp) / CULL_WARPS; // pages of this warp (warp-uniform)
 			const uint32_t packed = (my_type << 16) | my_count; // count <= 200
 			uint32_t prefix = 0, total = 0;
@@ -475,7 +469,7 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 			if (P.n_ranks && lane == 31 && n_mine) rec_base = atomicAdd(&counters[CNT_N_REC], n_mine);
 			base = __shfl_sync(0xffffffffu, base, leader);
 			rec_base = __shfl_sync(0xffffffffu, rec_base, 31);
-			if (has) s_bal[iwi][ROWS] = base + prefix; // offset of the page inside its type's output segment
+			if (has) s_off[iwi] = P.type_base[my_type] + base + prefix; // where the page's ids go in out_ids
 		}
 		__syncwarp();
 
@@ -487,8 +481,7 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 				const uint32_t page = s_item[iw].page;
 				const uint32_t meta = s_item[iw].meta;
 				const uint32_t count = meta & 0xffu;
-				const uint32_t type = (meta >> 8) & 0xffu;
-				uint32_t* dst = out_ids + P.type_base[type] + s_bal[iw][ROWS];
+				uint32_t* dst = out_ids + s_off[iw];
 				const int* ep = entities + (size_t)page * LB200_PAGE_SLOTS;
 				uint32_t row_word; // lane k < 8 (and its images in the other 8-lane groups): word k of the page's visibility row
 				if (((meta >> 16) & 3u) == CLS_COPY) {
@@ -517,7 +510,7 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 						if ((bal[k] >> lane) & 1u) dst[prefix + __popc(bal[k] & lt_mask)] = (uint32_t)id[k];
 						prefix += __popc(bal[k]);
 					}
-					row_word = (lane & 7) < ROWS ? s_bal[iw][lane & 7] : 0u;
+					row_word = s_bal[iw][lane & 7];
 				}
 				if (mask_out && lane < 8) mask_out[(size_t)page * 8 + lane] = row_word;
 				if (P.n_ranks) {
