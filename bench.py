@@ -123,6 +123,36 @@ class ClockSampler:
                 "sampled": "50 ms nvidia-smi samples over the timed regions plus a ~1.5 s probe loop of the same cull kernel"}
 
 
+def shared_config(visible, pages=None):
+    """The keys both arms (--impl ours / reference) put into `config`: same workload, same scene, same frustum."""
+    return {"workload": WORKLOAD, "entities_per_gpu": N_ENTITIES, "visible_per_gpu": int(visible),
+            "frustum": "perspective fov 60deg 16:9 near 0.1 far 4500 at origin looking -z",
+            "scene_rng": "numpy default_rng(seed 2 + rank) in lumixengine_b200/scenes.py::c2_scene, shared by both arms (SURVEY 8d names the reference's "
+                         "RandomGenerator(521288629, 362436069); the distribution is the one 8d gives, the generator is not)"}
+
+
+def build_info():
+    """Source hash recorded by build() next to the .so against the hash of the sources as they lie here: a stale prebuilt library shows."""
+    try:
+        from lumixengine_b200 import _lib
+        cur = _lib.source_hash()
+        rec = _lib.recorded_source_hash()
+        return {"source_hash": cur, "library_built_from": rec, "fresh": cur == rec}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def cull_cpu_baseline(steps, warmup):
+    """The reference's CullingSystemImpl::cull on its own job system with W = min(cores, 64) workers AND with one worker (BASELINE.md
+    section 3: its job system anti-scales on this path); the faster of the two is the baseline value."""
+    runs = []
+    for workers in (0, 1):
+        r = run_cpu_worker(["--workload", "cull", "--n", str(N_ENTITIES), "--scene", "c2", "--steps", str(steps), "--warmup", str(warmup), "--workers", str(workers)])
+        runs.append(r)
+    best = max(runs, key=lambda r: r["value"])
+    return best, runs
+
+
 def run_cpu_worker(args, timeout=900):
     cmd = [sys.executable, "-m", "oracle.cpu_baseline"] + args
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
@@ -150,14 +180,17 @@ def reference_arm(a, rank):
     """The reference's own CPU implementation (oracle/_ref) on the host cores; rank 0 only."""
     if rank != 0:
         return
-    r = run_cpu_worker(["--workload", "cull", "--n", str(N_ENTITIES), "--scene", "c2", "--steps", str(a.steps), "--warmup", str(a.warmup)])
+    r, runs = cull_cpu_baseline(a.steps, a.warmup)
     ms = r["median_s"] * 1e3
+    cfg = shared_config(r["visible"])
+    cfg["note"] = "one 10M shard culled on the host whatever --gpus is (bounded sample of the N-shard job)"
     line = {
         "impl": "reference", "metric": "M entities culled/s", "value": r["value"], "unit": "M entities/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "entities_per_step": N_ENTITIES, "visible": r["visible"],
-                   "note": "one 10M shard culled on the host whatever --gpus is (bounded sample of the N-shard job)"},
-        "cpu_baseline": {"value": r["value"], "unit": "M entities/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "impl": r["impl"]},
+        "config": cfg,
+        "cpu_baseline": {"value": r["value"], "unit": "M entities/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "impl": r["impl"],
+                         "by_workers": [{"workers": x["cores"], "value": x["value"], "median_ms": x["median_s"] * 1e3} for x in runs],
+                         "note": "value = the faster of W = min(cores, 64) and W = 1"},
         "e2e": {"value": r["value"], "unit": "M entities/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,17 +213,26 @@ def secondary_paths(ctx, lb, scenes, peak, steps, warmup):
     out = {}
     # --- propagate ---
     parents, locals_, roots = scenes.hierarchy_forest(1_000_000, 8, 7, seed=3)
-    h = lb.Hierarchy(ctx, parents)
-    h.setLocalTransforms(locals_)
-    h.setRootTransforms(roots)
-    for _ in range(max(warmup, 3)):
-        h.propagate()
-    ms = time_region(ctx, h.propagate, steps) / steps
-    b = h.algorithmic_bytes()
+    hs = []
+    for _ in range(5):  # 5 x 112 MB of locals + globals > 4 x the 126 MB L2: successive steps never find their hierarchy in L2
+        h = lb.Hierarchy(ctx, parents)
+        h.setLocalTransforms(locals_)
+        h.setRootTransforms(roots)
+        hs.append(h)
+    turn = [0]
+
+    def prop():
+        hs[turn[0] % len(hs)].propagate()
+        turn[0] += 1
+    for _ in range(max(warmup, 3) + len(hs)):
+        prop()
+    ms = time_region(ctx, prop, steps) / steps
+    b = hs[0].algorithmic_bytes()
     out["propagate_1m_depth8"] = {"value": len(parents) / ms / 1e3, "unit": "M nodes/s", "ms_per_step": ms,
                                   "roofline": {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": b / ms / 1e6 / peak, "algorithmic_bytes": b},
-                                  "note": "narrow levels fused into one block + one launch per wide level; the 112 MB working set is not flushed between steps (locals stay partly L2-resident)"}
-    h.close()
+                                  "note": "narrow levels fused into one block + one launch per wide level; 5 hierarchies (560 MB) rotated, so every step reads its locals from HBM"}
+    for h in hs:
+        h.close()
     # --- pose + palette, skin ---
     sk = scenes.skeleton(64)
     clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
@@ -323,11 +365,13 @@ def ours(a, rank, world):
 
     # kernel-only timing for the roofline (N>1 steps also contain the gather): K launches of the cull kernel alone
     ms_kernel = time_region(ctx, lambda: cs.cull_device_n(f, a.steps), 1) / a.steps
-    # one cull on an idle device, nothing to overlap with (host synchronisation between launches): the latency of a lone view
-    lone = []
-    for _ in range(20):
-        lone.append(time_region(ctx, lambda: cs.cull_device(f, want_counts=False), 1))
-    ms_lone = statistics.median(lone)
+    # one cull on an idle device, nothing to overlap with, its launch queued behind a delay kernel (no host latency in the interval):
+    # the latency of a lone view — beside what the interval costs when it holds nothing, and when it holds one empty kernel
+    lone = {what: float(np.mean(cs.time_lone_cull(f, 50, mode=mode))) for mode, what in ((0, "cull"), (1, "empty_interval"), (2, "empty_kernel"))}
+    ms_lone = lone["cull"]
+    # parity at full size: the digest of the visible set (per type: count, sum, xor of ids) against the reference's own build below
+    full = cs.cull(f)
+    gpu_digest = lb.culling.digest_ids(full.ids, full.types())
 
     # ---- e2e: the public host API, frustum in host memory -> visible ids in pinned host memory, every step ----
     for _ in range(3):
@@ -364,12 +408,11 @@ def ours(a, rank, world):
     line = {
         "metric": "M entities culled/s", "value": total_entities / ms_step / 1e3, "unit": "M entities/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "entities_per_gpu": N_ENTITIES,
-                   "visible_per_gpu": int(visible), "pages": cs.page_count(), "frustum": "perspective fov 60deg 16:9 near 0.1 far 4500 at origin looking -z",
+        "config": {**shared_config(visible), "pages": cs.page_count(),
                    "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{cs.page_count() * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
                    "parallelism": f"dp{world}: whole cell pages per rank" + (("; exchanged each step: " + exchange_desc) if world > 1 else ""),
                    "submission": "K culls = one lb200_culling_cull_device_n call: consecutive (independent) culls on 3 streams / output lanes, half-occupancy grids, programmatic dependent launch" if world == 1 else "K exchange steps = one lb200_culling_cull_exchange_n call (steps on 3 streams, 6 exchange buffers per rank)",
-                   "lone_cull_ms": ms_lone,
+                   "lone_cull_ms": ms_lone, "lone_empty_interval_ms": lone["empty_interval"], "lone_empty_kernel_ms": lone["empty_kernel"],
                    "scene_build_s": build_s, "page_stats": stats},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -378,7 +421,11 @@ def ours(a, rank, world):
         "roofline": {"bound": "hbm", "achieved": alg_bytes / ms_kernel / 1e6, "peak": peak, "unit": "GB/s", "frac": alg_bytes / ms_kernel / 1e6 / peak,
                      "traffic": traffic_from_profile("cull_pages_kernel"), "kernel": "cull_pages_kernel", "kernel_ms": ms_kernel, "algorithmic_bytes": int(alg_bytes),
                      "peak_source": peak_src,
+                     "lone_frac": alg_bytes / ms_lone / 1e6 / peak, "lone_ms": ms_lone,
+                     "lone_note": "one cull, device to itself, CUDA events (1 us ticks) around it; the interval costs lone_empty_interval_ms with nothing in it and lone_empty_kernel_ms with one empty kernel",
                      "scan_all_equivalent_gbs": (16 * N_ENTITIES + 8 * visible + N_ENTITIES / 8) / ms_kernel / 1e6},
+        "build": build_info(),
+        "parity": {"gpu_digest": gpu_digest, "digest": "per renderable type [count, sum of ids, xor of ids] of the visible set of one C2 cull"},
     }
     if world == 1 and not a.only_cull:
         try:
@@ -389,10 +436,16 @@ def ours(a, rank, world):
         except Exception as e:  # the headline number stands on its own
             line["paths_error"] = repr(e)
         try:
-            cb = run_cpu_worker(["--workload", "cull", "--n", str(N_ENTITIES), "--scene", "c2", "--steps", "20", "--warmup", "2"])
+            cb, runs = cull_cpu_baseline(20, 2)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "M entities/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
-                                    "impl": cb["impl"], "median_ms": cb["median_s"] * 1e3, "visible": cb["visible"]}
+                                    "impl": cb["impl"], "median_ms": cb["median_s"] * 1e3, "visible": cb["visible"],
+                                    "by_workers": [{"workers": x["cores"], "value": x["value"], "median_ms": x["median_s"] * 1e3} for x in runs],
+                                    "note": "value = the faster of W = min(cores, 64) and W = 1 (the reference's job system anti-scales on this path)"}
             assert cb["visible"] == visible, "CPU reference and GPU disagree on the visible count"
+            if "digest" in cb:
+                line["parity"]["reference_digest"] = cb["digest"]
+                line["parity"]["equal"] = cb["digest"] == gpu_digest
+                assert cb["digest"] == gpu_digest, "the visible set of the 10M C2 cull differs from the reference's own CullingSystemImpl"
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": "M entities/s", "cores": 0, "kind": "reference", "sample": "failed: " + repr(e)}
     emit(line)

@@ -187,9 +187,10 @@ LB200_API int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words,
  * back-to-back timed culls never re-read an L2-resident scene (B200_PROFILING.md "Timing hygiene"). */
 LB200_API int lb200_culling_set_replicas(lb200_culling* cs, uint32_t replicas);
 /* Algorithmic HBM bytes of the last cull: page descriptors + 16 B per tested sphere + 4 B per id read + 4 B per id written + mask. */
-/* Measurement helper: device time (ms) of `iters` single culls, each with the device to itself and its launches already queued when the
- * device reaches them (no host launch latency inside the interval, nothing overlapping the cull). */
-LB200_API int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t iters, float* out_ms);
+/* Measurement helper: device time (ms) of `iters` single culls, each with the device to itself and its launch already queued when the
+ * device reaches it (no host launch latency inside the interval, nothing overlapping the cull).  mode 0 = the cull, 1 = nothing between
+ * the two event records, 2 = one empty kernel of the cull's grid (the fixed costs the first number contains). */
+LB200_API int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t iters, int mode, float* out_ms);
 /* Profiling aid: %globaltimer stamps (ns) of the phase boundaries of the last cull issued while LB200_CULL_TRACE=1 was set:
  * out[2 kernels][2048 blocks][8 points] (cull_kernel.cuh trace_point). */
 LB200_API int lb200_culling_read_trace(lb200_culling* cs, uint64_t* out);

@@ -106,9 +106,29 @@ SYMBOLS = [
 _lib = None
 
 
+def source_hash():
+    """sha256 over the sources liblumix_b200.so is built from (csrc/*, include/lumix_b200.h), in name order."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "csrc", "*.h"))
+                   + glob.glob(os.path.join(HERE, "csrc", "*.hpp")) + [os.path.join(HERE, "csrc", "Makefile"), os.path.join(os.path.dirname(HERE), "include", "lumix_b200.h")])
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def recorded_source_hash():
+    p = SO_PATH + ".srchash"
+    return open(p).read().strip() if os.path.exists(p) else None
+
+
 def build():
-    """Compile liblumix_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile liblumix_b200.so for sm_100a (nvcc cross-compiles without a GPU) and record the hash of the sources next to it."""
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc"), "-j8"])
+    with open(SO_PATH + ".srchash", "w") as f:
+        f.write(source_hash() + "\n")
 
 
 def lib():

@@ -874,8 +874,10 @@ int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t 
 
 // Device time of ONE cull that has the device to itself (the latency of a lone view): per iteration a short delay kernel, then
 // event / cull / event enqueued while it runs, so the interval holds no host launch latency and nothing overlaps the cull.
-int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t iters, float* out_ms) {
-	if (!cs || !frustum || !out_ms || !iters) return LB200_ERR_INVALID;
+// mode 0: the cull; 1: nothing between the events (what the two event records cost by themselves); 2: one empty kernel of the cull's
+// grid (the fixed cost of any kernel launch).  CUDA events tick in ~1 us steps.
+int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type, uint32_t iters, int mode, float* out_ms) {
+	if (!cs || !frustum || !out_ms || !iters || mode < 0 || mode > 2) return LB200_ERR_INVALID;
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
 	lb200_ctx* ctx = cs->ctx;
 	if (cs->host.cells.empty()) return LB200_ERR_STATE;
@@ -889,9 +891,8 @@ int lb200_culling_time_lone_cull(lb200_culling* cs, const lb200_shifted_frustum*
 		delay_kernel<<<1, 32, 0, ctx->stream>>>(200000); // ~100 us
 		LB200_CHECK_LAUNCH(ctx);
 		LB200_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-		static const int mode = getenv("LB200_LONE_MODE") ? atoi(getenv("LB200_LONE_MODE")) : 0; // profiling: 2 = nothing, 3 = two empty kernels
-		if (mode == 3) delay_kernel<<<592, 256, 0, ctx->stream>>>(0);
-		else if (mode != 2) rc = launchCull(cs, frustum, type);
+		if (mode == 2) delay_kernel<<<cs->grid, CULL_THREADS, 0, ctx->stream>>>(0);
+		else if (mode == 0) rc = launchCull(cs, frustum, type);
 		if (rc) break;
 		LB200_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
 		LB200_CUDA(ctx, cudaEventSynchronize(e1));

@@ -38,6 +38,17 @@ def frustum_from_viewport(pos, rot, fov, w, h, near, far, is_ortho=False, ortho_
     return f
 
 
+def digest_ids(ids, types, n_types=4):
+    """Order-independent digest of a visible set: per renderable type (count, sum of ids, xor of ids)."""
+    ids = np.asarray(ids).astype(np.uint64)
+    types = np.asarray(types)
+    out = []
+    for t in range(n_types):
+        sel = ids[types == t]
+        out.append([int(len(sel)), int(sel.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(sel)) if len(sel) else 0])
+    return out
+
+
 def frustum_bytes(f):
     return np.frombuffer(bytes(f), np.uint8).copy()
 
@@ -239,10 +250,11 @@ class CullingSystem:
         self._err(self.L.lb200_culling_read_bitmask(self.h, ptr(out), C.c_uint32(len(out))))
         return out[:n * 8].reshape(n, 8)
 
-    def time_lone_cull(self, frustum, iters=20, type=TYPE_ALL):
-        """Device time (ms, per iteration) of single culls that have the device to themselves, launches pre-queued (no host latency)."""
+    def time_lone_cull(self, frustum, iters=20, type=TYPE_ALL, mode=0):
+        """Device time (ms, per iteration) of single culls that have the device to themselves, launch pre-queued (no host latency).
+        mode 1 / 2: nothing / one empty kernel of the same grid between the events (the fixed costs inside the number)."""
         out = np.zeros(iters, np.float32)
-        self._err(self.L.lb200_culling_time_lone_cull(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(iters), ptr(out)))
+        self._err(self.L.lb200_culling_time_lone_cull(self.h, C.byref(frustum), C.c_uint8(type), C.c_uint32(iters), C.c_int(mode), ptr(out)))
         return out
 
     def last_algorithmic_bytes(self):

@@ -44,6 +44,9 @@ def bench_cull(n, steps, warmup, workers, scene_name):
         t0 = time.time()
         rc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
         build_s = time.time() - t0
+        ids, tys, _ = rc.cull(f, cap=n)  # one cull with the ids kept: the digest bench.py compares with the GPU's
+        ids = ids.astype(np.uint64)
+        out["digest"] = [[int((tys == t).sum()), int(ids[tys == t].sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(ids[tys == t])) if (tys == t).any() else 0] for t in range(4)]
         if warmup:
             rc.cull(f, cap=0, iters=warmup)
         times = []

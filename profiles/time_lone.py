@@ -1,4 +1,4 @@
-"""Device latency of one lone C2 cull (LB200_LONE_MODE / LB200_DEBUG_SKIP_WORK select what sits between the events; see culling.cu)."""
+"""Device latency of one lone C2 cull and of the fixed costs inside it (nothing / one empty kernel between the events)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -11,7 +11,8 @@ cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"]); cs.flu
 A = scenes.c2_frustum_args()
 views = {"c2_default": lb.frustum_perspective(**A), "nothing": lb.frustum_perspective(**dict(A, position=(1e6, 0.0, 1e6), far=100.0))}
 for name, f in views.items():
-    cs.time_lone_cull(f, 10)
-    t = np.sort(cs.time_lone_cull(f, 60)) * 1e3
-    print(f"LONE mode={os.environ.get('LB200_LONE_MODE', '0')} skip_work={os.environ.get('LB200_DEBUG_SKIP_WORK', '0')} {name:11s} median {t[len(t)//2]:6.2f} us  min {t[0]:6.2f}  p90 {t[int(len(t)*0.9)]:6.2f}")
+    for mode, what in ((0, "cull"), (1, "empty interval"), (2, "empty kernel")):
+        cs.time_lone_cull(f, 10, mode=mode)
+        t = np.sort(cs.time_lone_cull(f, 100, mode=mode)) * 1e3
+        print(f"LONE {name:11s} {what:15s} mean {t.mean():6.2f} us  median {t[len(t)//2]:6.2f}  min {t[0]:6.2f}  p90 {t[int(len(t)*0.9)]:6.2f}")
 cs.close(); ctx.close()
