@@ -197,6 +197,70 @@ LB200_API int lb200_culling_read_trace(lb200_culling* cs, uint64_t* out);
 LB200_API uint64_t lb200_culling_last_algorithmic_bytes(const lb200_culling* cs);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Sort keys — the consumer of the visible list: PipelineImpl::createSortKeys (src/renderer/pipeline.cpp:3789-4018:
+ * LOD selection + smoothing, sort keys / values :53-143, auto-instancing :452-523 and its instance data :3958-4016) and
+ * PipelineImpl::radixSort (:4020-4144), on the device.  It reads the ids of the last cull where they lie in HBM; sorted keys / values
+ * and the per-group instance data stay in HBM for the draw-command stage; the host reads back four counters.
+ * One-instancer form of the reference (it runs one AutoInstancer per job worker and splits a mesh's instances over them): instancer
+ * index 0 in the group values, every mesh's instances in one group.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lb200_sortkeys lb200_sortkeys;
+typedef struct lb200_sk_model {   /* per Model (src/renderer/model.h) */
+	float lod_distances[4];       /* m_lod_distances (squared), model.h:234 */
+	int32_t lod_from[5];          /* m_lod_indices[].from / .to, model.h:129-133,233 */
+	int32_t lod_to[5];
+	uint32_t mesh_base;           /* first entry of this model in the mesh table */
+	uint32_t mesh_count;
+} lb200_sk_model;
+typedef struct lb200_sk_mesh {    /* per (model, mesh): MeshMaterial + Mesh + Material fields createSortKeys reads */
+	uint32_t sort_key;            /* MeshMaterial::sort_key (model.h:65, RenderModule::computeSortKey): also the auto-instancer group */
+	uint32_t material_index;      /* MeshMaterial::material_index */
+	float lod;                    /* Mesh::lod (model.h:120) */
+	uint8_t layer;                /* Material::getLayer() */
+	uint8_t skinned;              /* Mesh::type == SKINNED */
+	uint16_t pad;
+} lb200_sk_mesh;
+typedef struct lb200_sk_view {
+	double camera_pos[3];         /* view.cp.pos */
+	double lod_ref_point[3];      /* m_viewport.pos */
+	float time_delta;             /* Engine::getLastTimeDelta() */
+	float lod_multiplier;         /* Renderer::getLODMultiplier() */
+	uint32_t frame_number;        /* Renderer::frameNumber() % 0xffffffff */
+	uint32_t is_shadow;           /* view.cp.is_shadow */
+	uint32_t max_sort_key;        /* Renderer::getMaxSortKey(); needs < max_groups */
+	uint32_t pad;
+	uint32_t bucket_map[256];     /* as built at pipeline.cpp:3803-3812: bucket | 0x100 if depth-sorted, 0xffffffff if the layer is not in the view */
+	uint8_t layer_to_bucket[256]; /* View::layer_to_bucket */
+} lb200_sk_view;
+typedef struct lb200_sk_result { uint32_t n_keys, n_instances, n_pose, n_dirty, n_groups; } lb200_sk_result;
+typedef struct lb200_sk_outputs { /* device pointers, valid until the next create_keys */
+	const uint64_t* keys;              /* n_keys sort keys (sorted if asked), pipeline.cpp:62-71 layout */
+	const uint64_t* values;            /* their sort values */
+	const uint32_t* group_count;       /* per mesh sort key g in [0, n_groups): instances of the group */
+	const uint32_t* group_offset;      /* ... and where they start in group_renderables / instance_data */
+	const uint64_t* group_renderables; /* entity | mesh_idx << 40 */
+	const void* instance_data;         /* 48 B per instance: rot (16), camera-relative pos (12), lod - mesh.lod (4), scale (12), material index (4) */
+	const uint32_t* pose_list;         /* n_pose skinned instances whose palette is due this frame */
+	const uint32_t* dirty_list;        /* n_dirty instances with ModelInstance::dirty set (material override refresh) */
+	const float* lod;                  /* ModelInstance::lod per entity, updated by the pass */
+	const uint32_t* pose_frame;        /* Pose::frame per entity */
+} lb200_sk_outputs;
+#define LB200_SK_MOVED 1u /* ModelInstance::MOVED */
+#define LB200_SK_DIRTY 2u /* ModelInstance::dirty */
+LB200_API int lb200_sortkeys_create(lb200_ctx* ctx, uint32_t max_entities, uint32_t max_groups, uint32_t max_keys, uint32_t max_instances, lb200_sortkeys** out);
+LB200_API void lb200_sortkeys_destroy(lb200_sortkeys* sk);
+LB200_API int lb200_sortkeys_set_models(lb200_sortkeys* sk, const lb200_sk_model* models, uint32_t n_models, const lb200_sk_mesh* meshes, uint32_t n_meshes);
+/* Per-entity state, arrays indexed by entity id; a null pointer leaves that array as it is. */
+LB200_API int lb200_sortkeys_set_instances(lb200_sortkeys* sk, uint32_t n, const uint32_t* model_of, const float* lod, const uint8_t* flags, const uint32_t* pose_frame,
+                                           const uint32_t* decal_sort_key, const uint8_t* decal_layer);
+/* World::getTransforms() (world.h:65), indexed by entity id: uploaded from the host, or a device array the caller keeps alive. */
+LB200_API int lb200_sortkeys_set_transforms(lb200_sortkeys* sk, const lb200_transform* transforms, uint32_t n);
+LB200_API int lb200_sortkeys_set_transforms_device(lb200_sortkeys* sk, const lb200_transform* dev_transforms);
+/* createSortKeys (+ radixSort if `sort`) for the last cull of `cs` on the context stream.  Asynchronous unless `want_counts`. */
+LB200_API int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb200_sk_view* view, int sort, int want_counts, lb200_sk_result* result);
+LB200_API int lb200_sortkeys_device_outputs(lb200_sortkeys* sk, lb200_sk_outputs* out);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  NCCL is dlopen()ed; the unique id travels through the caller
  * (torch.distributed store / any out-of-band channel).
  * ---------------------------------------------------------------------------------------------------------- */

@@ -96,6 +96,8 @@ SYMBOLS = [
     "lb200_culling_last_algorithmic_bytes", "lb200_culling_time_lone_cull", "lb200_culling_read_trace",
     "lb200_comm_get_unique_id", "lb200_comm_init", "lb200_comm_destroy", "lb200_comm_enable_p2p", "lb200_comm_status", "lb200_culling_gather_stride_words", "lb200_culling_allgather", "lb200_culling_cull_gather",
     "lb200_culling_cull_exchange", "lb200_culling_cull_exchange_n", "lb200_culling_exchange_slab_words", "lb200_culling_page_id",
+    "lb200_sortkeys_create", "lb200_sortkeys_destroy", "lb200_sortkeys_set_models", "lb200_sortkeys_set_instances", "lb200_sortkeys_set_transforms",
+    "lb200_sortkeys_set_transforms_device", "lb200_sortkeys_create_keys", "lb200_sortkeys_device_outputs",
     "lb200_hierarchy_create", "lb200_hierarchy_destroy", "lb200_hierarchy_depth", "lb200_hierarchy_set_locals", "lb200_hierarchy_set_root_globals",
     "lb200_hierarchy_propagate", "lb200_hierarchy_get_globals", "lb200_hierarchy_get_spheres", "lb200_hierarchy_get_relative_matrices", "lb200_hierarchy_set_globals", "lb200_hierarchy_compute_locals", "lb200_hierarchy_get_locals", "lb200_hierarchy_algorithmic_bytes",
     "lb200_animation_create", "lb200_animation_destroy", "lb200_animation_set_instances", "lb200_animation_update", "lb200_animation_skin",
@@ -155,6 +157,7 @@ def lib():
     L.lb200_hierarchy_algorithmic_bytes.restype = C.c_uint64
     L.lb200_animation_algorithmic_bytes.restype = C.c_uint64
     L.lb200_shutdown.restype = None
+    L.lb200_sortkeys_destroy.restype = None
     L.lb200_host_alloc.restype = vp
     L.lb200_host_alloc.argtypes = [vp, C.c_size_t]
     L.lb200_host_free.restype = None

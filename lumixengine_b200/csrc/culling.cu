@@ -579,6 +579,13 @@ void parseCounts(lb200_culling* cs, lb200_cull_result* result) {
 
 } // namespace
 
+int lb200_culling_internal_last(lb200_culling* cs, const uint32_t** out_ids, const uint32_t** counters, const uint32_t** type_base, const uint32_t** type_counts) {
+	if (!cs || !cs->ctx) return LB200_ERR_INVALID;
+	if (!cs->last_counters) { lb200_set_error(cs->ctx, "no cull has been issued on this culling system yet"); return LB200_ERR_STATE; }
+	*out_ids = cs->last_out; *counters = cs->last_counters; *type_base = cs->last_type_base; *type_counts = cs->host.type_counts;
+	return LB200_OK;
+}
+
 extern "C" {
 
 int lb200_culling_create(lb200_ctx* ctx, lb200_culling** out) {

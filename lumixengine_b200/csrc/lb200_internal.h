@@ -58,6 +58,8 @@ struct lb200_range {
 	lb200_range(const lb200_range&) = delete;
 	lb200_range& operator=(const lb200_range&) = delete;
 };
+// culling.cu: where the last cull left its result (device: ids, counters; host: per-type segment bases and entity counts, 256 each)
+int lb200_culling_internal_last(lb200_culling* cs, const uint32_t** out_ids, const uint32_t** counters, const uint32_t** type_base, const uint32_t** type_counts);
 int lb200_comm_check(lb200_ctx* ctx); // comm.cu: LB200_ERR_NCCL (and reset) if a peer wait timed out since the last check
 uint32_t lb200_cull_lanes(); // LB200_CULL_LANES, default 3, 1..LB200_MAX_LANES (context.cu)
 
@@ -92,3 +94,4 @@ static_assert(sizeof(lb200_page_desc) == 32, "page descriptor is one 32-byte sec
 static_assert(sizeof(lb200_shifted_frustum) == 256, "ShiftedFrustum image, geometry.h:99-149");
 static_assert(sizeof(lb200_transform) == 56, "Transform image, math.h:306-327");
 static_assert(sizeof(lb200_track) == 32, "track descriptor");
+static_assert(sizeof(lb200_sk_model) == 64 && sizeof(lb200_sk_mesh) == 16 && sizeof(lb200_sk_view) == 1352, "sort-key tables");

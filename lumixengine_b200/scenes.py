@@ -151,3 +151,50 @@ def instance_times(n, clips, seed=7):
     lengths = np.array([c.length_ticks for c in clips], np.uint32)
     tt = (rng.random(n) * lengths[ci]).astype(np.uint32)
     return ci, tt
+
+
+def sortkey_setup(n_entities, types, pos, n_models=48, seed=7, skinned_fraction=0.1, moved_fraction=0.02, dirty_fraction=0.002, finite_draw_distance=0.25):
+    """Synthetic inputs of PipelineImpl::createSortKeys (pipeline.cpp:3789-4018) for a culling scene: models with 1-4 LODs of 1-3 meshes
+    (sort keys allocated one per mesh like Renderer::allocSortKey), four material layers (0 default bucket, 1 depth-sorted bucket, 2 not
+    in the view, 3 a second default bucket), per-entity model / lod state / MOVED / dirty flags, decal materials for the DECAL and
+    CURVE_DECAL renderables (RenderableTypes 1 and 3), random rotations and scales.  Pure numpy.
+    -> dict(models, meshes, model_of, lod, flags, pose_frame, decal_sort_key, decal_layer, transforms, layer_to_bucket, depth_sorted_buckets, max_sort_key)"""
+    from .sortkeys import SK_MESH_DTYPE, SK_MODEL_DTYPE
+    from .hierarchy import TRANSFORM_DTYPE
+    rng = np.random.default_rng(seed)
+    models = np.zeros(n_models, SK_MODEL_DTYPE)
+    meshes = []
+    n_skinned_models = max(1, int(round(n_models * skinned_fraction)))
+    for m in range(n_models):
+        n_lods = int(rng.integers(1, 5))
+        d = np.sort(rng.uniform(80.0, 1500.0, 4)) ** 2  # squared LOD distances (model.h:234)
+        dist = np.full(4, np.finfo(np.float32).max, np.float32)
+        dist[:n_lods - 1] = d[:n_lods - 1]
+        if rng.random() < finite_draw_distance:
+            dist[n_lods - 1] = d[3] * 4.0  # beyond it getLODMeshIndices returns an empty LOD: the model is not drawn
+        models[m]["lod_distances"] = dist
+        models[m]["lod_from"], models[m]["lod_to"] = 0, -1
+        models[m]["mesh_base"] = len(meshes)
+        skinned = m < n_skinned_models
+        at = 0
+        for l in range(n_lods):
+            k = int(rng.integers(1, 4))
+            models[m]["lod_from"][l], models[m]["lod_to"][l] = at, at + k - 1
+            for _ in range(k):
+                meshes.append((len(meshes), int(rng.integers(1, 5000)), float(l), int(rng.choice([0, 0, 0, 1, 2, 3])), 1 if skinned else 0, 0))
+            at += k
+        models[m]["mesh_count"] = at
+    meshes = np.array(meshes, SK_MESH_DTYPE)
+    model_of = rng.integers(0, n_models, n_entities).astype(np.uint32)
+    lod = rng.choice(np.array([0.0, 1.0, 2.0, 3.0, 4.0, 0.5, 1.25, 2.9, 3.5], np.float32), n_entities).astype(np.float32)
+    flags = np.zeros(n_entities, np.uint8)
+    flags[rng.random(n_entities) < moved_fraction] |= 1
+    flags[rng.random(n_entities) < dirty_fraction] |= 2
+    tr = np.zeros(n_entities, TRANSFORM_DTYPE)
+    tr["pos"] = pos
+    q = rng.normal(size=(n_entities, 4)).astype(np.float32)
+    tr["rot"] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    tr["scale"] = rng.uniform(0.5, 2.0, (n_entities, 3)).astype(np.float32)
+    return dict(models=models, meshes=meshes, model_of=model_of, lod=lod, flags=flags, pose_frame=np.full(n_entities, 0xffffffff, np.uint32),
+                decal_sort_key=rng.integers(0, 2000, n_entities).astype(np.uint32), decal_layer=rng.choice(np.array([0, 1, 2, 3], np.uint8), n_entities).astype(np.uint8),
+                transforms=tr, layer_to_bucket=[0, 1, 0xff, 2], depth_sorted_buckets=(1,), max_sort_key=len(meshes) - 1)

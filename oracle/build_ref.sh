@@ -9,7 +9,7 @@
 #   overlay    : SURVEY.md §8(c) — src/core/sync.h (SRWLock body), src/core/linux/sync.cpp (stale
 #                Semaphore::signal signature + SRWLock methods), src/core/simd.h (take the SSE branch
 #                on GCC), src/core/job_system.cpp (noinline on getWorker(): the reference's TLS guard
-#                is MSVC/clang pragmas only)
+#                is MSVC/clang pragmas only; 1 MB fiber stacks as on Windows)
 #   stubs      : oracle/ref/ref_stubs.cpp (os::mem*, profiler no-ops, atomics missing on Linux)
 #
 # Flags mirror the reference's Linux config (scripts/genie.lua:339-342: -msse2, no FMA, no fast-math)
@@ -75,6 +75,9 @@ open(p, 'w').write('\n'.join(out))
 EOF
 # (4) job_system.cpp: keep getWorker() out of line so &g_worker is recomputed after a fiber switch
 sed -i 's|^WorkerTask\* getWorker()|__attribute__((noinline)) WorkerTask* getWorker()|' "$S/core/job_system.cpp"
+#     and give fibers 1 MB of stack: Windows fibers reserve 1 MB whatever CreateFiber is asked to commit, the Linux port mallocs exactly the
+#     64 KB it is asked for, which PipelineImpl::radixSort's two 48 KB histograms overflow (ref_sortkeys_harness.cpp runs it in a job)
+sed -i 's|Fiber::create(64 \* 1024, manage, new_fiber)|Fiber::create(1024 * 1024, manage, new_fiber)|' "$S/core/job_system.cpp"
 
 CXX=${LUMIX_REF_CXX:-/usr/bin/g++} # not $CXX: a wrapper there may link libstdc++ statically, which clashes with other C++ libs at exit
 FL="-std=c++20 -O2 -DSTATIC_PLUGINS -DNDEBUG -fno-exceptions -fno-rtti -msse2 -msse3 -ffp-contract=off -fPIC -w -fvisibility=hidden -I$S -I$REF/external"
@@ -106,6 +109,17 @@ if [ -s "$S/renderer/extracted_compute_skeleton_dual_quats.inl" ] && grep -q com
 else
 	echo "build_ref.sh: palette harness not built (see below); continuing without ref_skeleton_dual_quats" >&2
 	tail -5 "$TMP/palette.log" >&2 || true
+fi
+# (6) the sort-key packers (pipeline.cpp:41-143) and Histogram + radixSort (:4020-4144), cut out the same way for oracle/ref/ref_sortkeys_harness.cpp
+awk '/^enum class DrawCommandTypes : u8/{p=1} /^struct Indirect \{/{p=0} p' "$REF/src/renderer/pipeline.cpp" > "$S/renderer/extracted_sort_key_packers.inl"
+awk '/^\tstruct Histogram \{/{p=1} /^\tvoid viewport\(int x, int y, int w, int h\) override/{p=0} p' "$REF/src/renderer/pipeline.cpp" > "$S/renderer/extracted_radix_sort.inl"
+cp "$REF/src/renderer/material.h" "$S/renderer/" 2>/dev/null || true
+if grep -q makeAutoInstancedSortValue "$S/renderer/extracted_sort_key_packers.inl" && grep -q "void radixSort" "$S/renderer/extracted_radix_sort.inl" \
+	&& $CXX $FL -c "$HERE/ref/ref_sortkeys_harness.cpp" -o "$TMP/obj/ref_sortkeys_harness.o" 2> "$TMP/sortkeys.log"; then
+	EXTRA="$EXTRA $TMP/obj/ref_sortkeys_harness.o"
+else
+	echo "build_ref.sh: sort-key harness not built (see below); continuing without ref_radix_sort / ref_make_*" >&2
+	tail -8 "$TMP/sortkeys.log" >&2 || true
 fi
 $CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" "$TMP/obj/ref_anim_harness.o" $EXTRA -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL
 ( cd "$REF" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$OUT/REFERENCE_COMMIT"

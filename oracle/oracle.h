@@ -123,6 +123,55 @@ uint32_t oracle_time_advance(uint32_t time_ticks, float time_delta, float fps, u
 void oracle_animate_instances(const OracleSkeleton* sk, const OracleClip* clips, const uint32_t* clip_index, const uint32_t* time_ticks,
 	uint32_t n, OVec3* out_pos, OQuat* out_rot, ODualQuat* out_dq, OMatrix* out_mtx);
 
+/* ---- sort keys, LOD selection, auto-instancing, radix sort (oracle_sortkeys.c; pipeline.cpp:53-143, 452-523, 3789-4144) ---- */
+typedef struct {
+	float lod_distances[4];  /* Model::m_lod_distances (squared), model.h:234 */
+	int32_t lod_from[5];     /* Model::m_lod_indices[].from / .to, model.h:129-133,233 */
+	int32_t lod_to[5];
+	uint32_t mesh_base;      /* first entry of this model in the mesh table */
+	uint32_t mesh_count;
+} OracleSkModel; /* 64 B */
+typedef struct {
+	uint32_t sort_key;       /* MeshMaterial::sort_key (model.h:65; RenderModule::computeSortKey) */
+	uint32_t material_index; /* MeshMaterial::material_index */
+	float lod;               /* Mesh::lod (model.h:120) */
+	uint8_t layer;           /* Material::getLayer() */
+	uint8_t skinned;         /* Mesh::type == SKINNED */
+	uint16_t pad;
+} OracleSkMesh; /* 16 B */
+typedef struct {
+	double camera_pos[3];    /* view.cp.pos */
+	double lod_ref_point[3]; /* m_viewport.pos */
+	float time_delta;
+	float lod_multiplier;    /* Renderer::getLODMultiplier() */
+	uint32_t frame_number;
+	uint32_t is_shadow;
+	uint32_t max_sort_key;   /* Renderer::getMaxSortKey() */
+	uint32_t pad;
+	uint32_t bucket_map[256];     /* pipeline.cpp:3803-3812 ([255] unused) */
+	uint8_t layer_to_bucket[256]; /* View::layer_to_bucket */
+} OracleSkView;
+
+uint32_t oracle_float_flip(uint32_t float_bits_value);
+uint64_t oracle_make_mesh_sort_key(uint32_t mesh_sort_key, uint8_t bucket);
+uint64_t oracle_make_depth_sort_key(float depth_squared, uint8_t bucket);
+uint64_t oracle_make_autoinstanced_sort_key(int32_t instancer_index, uint8_t bucket);
+uint64_t oracle_make_decal_sort_key(uint32_t material_sort_key, uint8_t bucket);
+uint64_t oracle_make_decal_sort_value(int32_t entity);
+uint64_t oracle_make_curve_decal_sort_value(int32_t entity);
+uint64_t oracle_make_skinned_sort_value(int32_t entity, uint32_t mesh_idx);
+uint64_t oracle_make_mesh_sort_value(int32_t entity, uint32_t mesh_idx);
+uint64_t oracle_make_autoinstanced_sort_value(uint32_t batch_idx, uint32_t instancer_idx);
+uint32_t oracle_lod_mesh_indices(const float* lod_distances4, float squared_distance);
+void oracle_radix_sort(uint64_t* keys_io, uint64_t* values_io, uint32_t size);
+void oracle_radix_sort_ex(uint64_t* keys_io, uint64_t* values_io, uint32_t size, int reference_copy_back);
+int oracle_create_sort_keys(const uint32_t* visible_ids, const uint8_t* visible_types, uint32_t n_visible, const OTransform* transforms,
+	const uint32_t* model_of, float* lod, const uint8_t* flags, uint32_t* pose_frame, const uint32_t* decal_sort_key, const uint8_t* decal_layer,
+	const OracleSkModel* models, const OracleSkMesh* meshes, const OracleSkView* view,
+	uint64_t* keys, uint64_t* values, uint32_t cap_keys, uint32_t* n_keys,
+	uint32_t* group_count, uint32_t* group_offset, uint64_t* group_renderables, uint8_t* instance_data48, uint32_t cap_instances, uint32_t* n_instances,
+	uint32_t* pose_list, uint32_t cap_pose, uint32_t* n_pose, uint32_t* dirty_list, uint32_t cap_dirty, uint32_t* n_dirty);
+
 #ifdef __cplusplus
 }
 #endif

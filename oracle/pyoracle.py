@@ -22,12 +22,12 @@ def build(force=False):
     """Compile the C restatement (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(ORACLE_SO) or any(
         os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(ORACLE_SO)
-        for f in ("oracle_cull.c", "oracle_propagate.c", "oracle_anim.c", "oracle.h", "oracle_math.h")
+        for f in ("oracle_cull.c", "oracle_propagate.c", "oracle_anim.c", "oracle_sortkeys.c", "oracle.h", "oracle_math.h")
     ):
         subprocess.check_call(["make", "-s", "-C", HERE])
     ref_root = os.environ.get("LUMIX_REFERENCE", "/root/reference")
     if os.path.isdir(os.path.join(ref_root, "src", "core")):
-        srcs = [os.path.join(HERE, "build_ref.sh"), os.path.join(HERE, "ref", "ref_harness.cpp"), os.path.join(HERE, "ref", "ref_stubs.cpp")]
+        srcs = [os.path.join(HERE, "build_ref.sh")] + [os.path.join(HERE, "ref", f) for f in ("ref_harness.cpp", "ref_stubs.cpp", "ref_sortkeys_harness.cpp")]
         if force or not os.path.exists(REF_SO) or any(os.path.getmtime(s) > os.path.getmtime(REF_SO) for s in srcs):
             subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
 
@@ -568,3 +568,84 @@ def palettes(skeleton, pos, rot):
     lib().oracle_palette_dual_quats(C.byref(sk), _ptr(p), _ptr(r), _ptr(dq))
     lib().oracle_palette_matrices(C.byref(sk), _ptr(p), _ptr(r), _ptr(mtx))
     return dq, mtx
+
+
+# ---- sort keys / LOD / auto-instancing / radix sort (oracle_sortkeys.c; pipeline.cpp:53-143, 452-523, 3789-4144) ----
+SK_MODEL_DTYPE = np.dtype([("lod_distances", np.float32, 4), ("lod_from", np.int32, 5), ("lod_to", np.int32, 5), ("mesh_base", np.uint32), ("mesh_count", np.uint32)])
+SK_MESH_DTYPE = np.dtype([("sort_key", np.uint32), ("material_index", np.uint32), ("lod", np.float32), ("layer", np.uint8), ("skinned", np.uint8), ("pad", np.uint16)])
+SK_VIEW_DTYPE = np.dtype([("camera_pos", np.float64, 3), ("lod_ref_point", np.float64, 3), ("time_delta", np.float32), ("lod_multiplier", np.float32),
+                          ("frame_number", np.uint32), ("is_shadow", np.uint32), ("max_sort_key", np.uint32), ("pad", np.uint32),
+                          ("bucket_map", np.uint32, 256), ("layer_to_bucket", np.uint8, 256)])
+assert SK_MODEL_DTYPE.itemsize == 64 and SK_MESH_DTYPE.itemsize == 16 and SK_VIEW_DTYPE.itemsize == 48 + 24 + 1024 + 256
+
+
+def create_sort_keys(visible_ids, visible_types, transforms56, model_of, lod, flags, pose_frame, decal_sort_key, decal_layer, models, meshes, view,
+                     sort=True):
+    """PipelineImpl::createSortKeys (one worker) + radixSort on flat inputs.  `lod` and `pose_frame` are updated in place like the
+    reference's ModelInstance::lod / Pose::frame.  -> dict(keys, values (sorted if `sort`), group_count, group_offset, group_renderables,
+    instance_data[n, 48] bytes, pose_list, dirty_list)."""
+    L = lib()
+    ids = np.ascontiguousarray(visible_ids, np.uint32)
+    tys = np.ascontiguousarray(visible_types, np.uint8)
+    n = len(ids)
+    view = np.ascontiguousarray(view, SK_VIEW_DTYPE).reshape(1)
+    n_groups = int(view["max_sort_key"][0]) + 1
+    cap_keys = 8 * n + n_groups + 16
+    cap_inst = 8 * n + 16
+    keys, values = np.zeros(cap_keys, np.uint64), np.zeros(cap_keys, np.uint64)
+    gcount, goff = np.zeros(n_groups, np.uint32), np.zeros(n_groups, np.uint32)
+    grend, idata = np.zeros(cap_inst, np.uint64), np.zeros((cap_inst, 48), np.uint8)
+    pose_list, dirty_list = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.uint32)
+    cnt = (C.c_uint32 * 4)()
+    tr = np.ascontiguousarray(transforms56)
+    assert tr.dtype.itemsize * (tr.shape[-1] if tr.ndim > 1 else 1) == 56 or tr.dtype.itemsize == 56
+    models = np.ascontiguousarray(models, SK_MODEL_DTYPE)
+    meshes = np.ascontiguousarray(meshes, SK_MESH_DTYPE)
+    assert lod.dtype == np.float32 and lod.flags.c_contiguous and pose_frame.dtype == np.uint32 and pose_frame.flags.c_contiguous
+    rc = L.oracle_create_sort_keys(_ptr(ids), _ptr(tys), C.c_uint32(n), _ptr(tr), _ptr(np.ascontiguousarray(model_of, np.uint32)), _ptr(lod),
+                                   _ptr(np.ascontiguousarray(flags, np.uint8)), _ptr(pose_frame),
+                                   _ptr(np.ascontiguousarray(decal_sort_key, np.uint32)), _ptr(np.ascontiguousarray(decal_layer, np.uint8)),
+                                   _ptr(models), _ptr(meshes), _ptr(view), _ptr(keys), _ptr(values), C.c_uint32(cap_keys), C.byref(cnt, 0),
+                                   _ptr(gcount), _ptr(goff), _ptr(grend), _ptr(idata), C.c_uint32(cap_inst), C.byref(cnt, 4),
+                                   _ptr(pose_list), C.c_uint32(n + 1), C.byref(cnt, 8), _ptr(dirty_list), C.c_uint32(n + 1), C.byref(cnt, 12))
+    assert rc == 0, "oracle_create_sort_keys: capacity"
+    nk, ni, npose, nd = (int(c) for c in cnt)
+    keys, values = keys[:nk].copy(), values[:nk].copy()
+    if sort and nk:
+        L.oracle_radix_sort(_ptr(keys), _ptr(values), C.c_uint32(nk))
+    return dict(keys=keys, values=values, group_count=gcount, group_offset=goff, group_renderables=grend[:ni].copy(), instance_data=idata[:ni].copy(),
+                pose_list=pose_list[:npose].copy(), dirty_list=dirty_list[:nd].copy())
+
+
+def radix_sort(keys, values, reference_copy_back=False):
+    """PipelineImpl::radixSort restated; reference_copy_back=True keeps the reference's literal last lines (see oracle_sortkeys.c)."""
+    k, v = np.ascontiguousarray(keys, np.uint64).copy(), np.ascontiguousarray(values, np.uint64).copy()
+    lib().oracle_radix_sort_ex(_ptr(k), _ptr(v), C.c_uint32(len(k)), C.c_int(1 if reference_copy_back else 0))
+    return k, v
+
+
+def sortkey_packers(which):
+    """The oracle's ('oracle') or the reference's own ('ref') packers as a dict of callables with identical signatures."""
+    L = lib() if which == "oracle" else ref()
+    pre = "oracle_" if which == "oracle" else "ref_"
+    sig = {"float_flip": (C.c_uint32, [C.c_uint32]), "make_mesh_sort_key": (C.c_uint64, [C.c_uint32, C.c_uint8]),
+           "make_depth_sort_key": (C.c_uint64, [C.c_float, C.c_uint8]), "make_autoinstanced_sort_key": (C.c_uint64, [C.c_int32, C.c_uint8]),
+           "make_decal_sort_key": (C.c_uint64, [C.c_uint32, C.c_uint8]), "make_decal_sort_value": (C.c_uint64, [C.c_int32]),
+           "make_curve_decal_sort_value": (C.c_uint64, [C.c_int32]), "make_skinned_sort_value": (C.c_uint64, [C.c_int32, C.c_uint32]),
+           "make_mesh_sort_value": (C.c_uint64, [C.c_int32, C.c_uint32]), "make_autoinstanced_sort_value": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+           "lod_mesh_indices": (C.c_uint32, [vp, C.c_float])}
+    out = {}
+    for name, (res, args) in sig.items():
+        f = getattr(L, pre + name)
+        f.restype, f.argtypes = res, args
+        out[name] = f
+    return out
+
+
+def ref_radix_sort(keys, values, workers=2):
+    """The reference's own PipelineImpl::radixSort (on its job system)."""
+    R = ref()
+    assert R.ref_jobs_init(C.c_int(workers))
+    k, v = np.ascontiguousarray(keys, np.uint64).copy(), np.ascontiguousarray(values, np.uint64).copy()
+    R.ref_radix_sort(_ptr(k), _ptr(v), C.c_int(len(k)))
+    return k, v

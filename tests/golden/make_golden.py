@@ -284,6 +284,51 @@ def ani_kat():
     print("ani_kat.npz", sum(v.nbytes for v in d.values()))
 
 
+def sortkeys_kat():
+    """The reference's own sort-key packers, Model::getLODMeshIndices and PipelineImpl::radixSort (pipeline.cpp:53-143, 4020-4144; model.h:173-179),
+    compiled from the reference file by oracle/build_ref.sh."""
+    rng = np.random.default_rng(2024)
+    R = po.sortkey_packers("ref")
+    n = 600
+    d = {}
+    u32 = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    u32[:8] = [0, 1, 0x7fffffff, 0x80000000, 0xffffffff, 0x3f800000, 0xbf800000, 0x7f800000]
+    buckets = rng.integers(0, 256, n).astype(np.uint8)
+    ents = rng.integers(-3, 2**24, n).astype(np.int32)
+    mesh_idx = rng.integers(0, 64, n).astype(np.uint32)
+    depths = (rng.random(n) * 1e7).astype(np.float32)
+    depths[:4] = [0.0, 1e-30, 3.4e38, 1.0]
+    d.update(u32=u32, buckets=buckets, ents=ents, mesh_idx=mesh_idx, depths=depths)
+    d["float_flip"] = np.array([R["float_flip"](int(x)) for x in u32], np.uint32)
+    d["mesh_key"] = np.array([R["make_mesh_sort_key"](int(k), int(b)) for k, b in zip(u32, buckets)], np.uint64)
+    d["depth_key"] = np.array([R["make_depth_sort_key"](float(x), int(b)) for x, b in zip(depths, buckets)], np.uint64)
+    d["inst_key"] = np.array([R["make_autoinstanced_sort_key"](int(k & 0xffff), int(b)) for k, b in zip(u32, buckets)], np.uint64)
+    d["decal_key"] = np.array([R["make_decal_sort_key"](int(k), int(b)) for k, b in zip(u32, buckets)], np.uint64)
+    d["decal_value"] = np.array([R["make_decal_sort_value"](int(e)) for e in ents], np.uint64)
+    d["curve_decal_value"] = np.array([R["make_curve_decal_sort_value"](int(e)) for e in ents], np.uint64)
+    d["skinned_value"] = np.array([R["make_skinned_sort_value"](int(e), int(m)) for e, m in zip(ents, mesh_idx)], np.uint64)
+    d["mesh_value"] = np.array([R["make_mesh_sort_value"](int(e), int(m)) for e, m in zip(ents, mesh_idx)], np.uint64)
+    d["inst_value"] = np.array([R["make_autoinstanced_sort_value"](int(k & 0xffff), int(m)) for k, m in zip(u32, mesh_idx)], np.uint64)
+    lodd = np.sort(rng.uniform(10.0, 1e6, (n, 4)).astype(np.float32), axis=1)
+    lodd[::7, 2:] = np.finfo(np.float32).max
+    sq = (rng.random(n) * 1.2e6).astype(np.float32)
+    sq[:5] = [lodd[0, 0], lodd[1, 1], lodd[2, 2], lodd[3, 3], 0.0]
+    d.update(lod_distances=lodd, squared=sq)
+    d["lod_index"] = np.array([R["lod_mesh_indices"](lodd[i].ctypes.data_as(C.c_void_p), float(sq[i])) for i in range(n)], np.uint32)
+    # radix sort: realistic key layouts (bucket byte, instanced flag, 32 low bits; runs of equal keys: the sort is stable)
+    for name, size in (("tiny", 5), ("below_step", 511), ("above_step", 513), ("big", 20000)):
+        keys = (rng.integers(0, 6, size).astype(np.uint64) << np.uint64(56)) | (rng.integers(0, 2, size).astype(np.uint64) << np.uint64(55)) | rng.integers(0, 3000, size).astype(np.uint64)
+        vals = np.arange(size, dtype=np.uint64) | (rng.integers(0, 5, size).astype(np.uint64) << np.uint64(32))
+        k, v = po.ref_radix_sort(keys, vals, workers=4)
+        d[f"rs_{name}_keys"], d[f"rs_{name}_values"], d[f"rs_{name}_sorted_keys"], d[f"rs_{name}_sorted_values"] = keys, vals, k, v
+    keys = rng.integers(0, 2**63, 3000, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, 3000).astype(np.uint64)  # all 64 bits in play
+    vals = np.arange(3000, dtype=np.uint64)
+    k, v = po.ref_radix_sort(keys, vals, workers=4)
+    d["rs_full_keys"], d["rs_full_values"], d["rs_full_sorted_keys"], d["rs_full_sorted_values"] = keys, vals, k, v
+    np.savez_compressed(os.path.join(OUT, "sortkeys_kat.npz"), **d)
+    print("sortkeys_kat.npz", sum(v.nbytes for v in d.values()))
+
+
 if __name__ == "__main__":
     po.build()
     po.ref().ref_clip_length_ticks.restype = C.c_uint32
@@ -293,5 +338,6 @@ if __name__ == "__main__":
     cull_kat()
     world_kat()
     ani_kat()
+    sortkeys_kat()
     sys.stdout.flush()
     os._exit(0)
