@@ -50,106 +50,191 @@ struct EmitParams {
 __device__ __forceinline__ uint32_t float_flip(uint32_t bits) { return bits ^ ((uint32_t)(-(int32_t)(bits >> 31)) | 0x80000000u); }
 __device__ __forceinline__ uint64_t sext(int32_t e) { return (uint64_t)(int64_t)e; } // EntityPtr::index is an i32: `entity.index | u64` sign-extends
 
-__device__ __forceinline__ void push_key(uint64_t* keys, uint64_t* values, uint32_t* counts, uint32_t cap, uint64_t key, uint64_t value) {
-	const uint32_t slot = atomicAdd(&counts[CNT_KEYS], 1u);
-	if (slot < cap) { keys[slot] = key; values[slot] = value; }
+// The same counter for lanes of a warp that add to the same auto-instancer group: one atomic per (warp, group).
+__device__ __forceinline__ uint32_t warp_claim_keyed(uint32_t* counters, uint32_t key) {
+	const uint32_t active = __activemask();
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t peers = __match_any_sync(active, key);
+	const int leader = __ffs((int)peers) - 1;
+	uint32_t base = 0;
+	if ((int)lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+	base = __shfl_sync(peers, base, leader);
+	return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
 
-__global__ void __launch_bounds__(SK_THREADS) emit_kernel(const __grid_constant__ EmitParams P, const uint32_t* __restrict__ visible,
-	const uint32_t* __restrict__ cull_counters, const lb200_transform* __restrict__ transforms, const uint32_t* __restrict__ model_of,
-	float* __restrict__ lod, const uint8_t* __restrict__ flags, uint32_t* __restrict__ pose_frame, const uint32_t* __restrict__ decal_sort_key,
-	const uint8_t* __restrict__ decal_layer, const lb200_sk_model* __restrict__ models, const lb200_sk_mesh* __restrict__ meshes,
-	uint64_t* __restrict__ keys, uint64_t* __restrict__ values, uint32_t* __restrict__ counts, uint32_t* __restrict__ group_count,
-	uint8_t* __restrict__ group_layer, uint64_t* __restrict__ rec_value, uint2* __restrict__ rec_group_rank, uint32_t* __restrict__ pose_list,
-	uint32_t* __restrict__ dirty_list)
-{
-	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+// Where one renderable's outputs go.  The per-renderable logic runs twice: first with a counting sink (how many keys / instancer records /
+// pose-list entries it emits), then — after ONE block-wide scan and ONE global atomic per counter and block — with a writing sink whose
+// slots are already known.  A single hot counter bumped once per key serialises at the L2 (~1 M claims per view otherwise).
+struct Sink {
+	bool write;
+	uint32_t k, r, p; // next key / record / pose slot (write) or running counts (count)
+	uint32_t* s_grp;  // per block and group, in shared memory: instances counted (count), then the block's cursor inside the group (write);
+	                  // null when the view has more groups than fit: ranks then come from the global counters directly
+};
+
+struct EmitArgs {
+	const lb200_transform* transforms; const uint32_t* model_of; float* lod; const uint8_t* flags; uint32_t* pose_frame;
+	const uint32_t* decal_sort_key; const uint8_t* decal_layer; const lb200_sk_model* models; const lb200_sk_mesh* meshes;
+	uint64_t* keys; uint64_t* values; uint32_t* counts; uint32_t* group_count; uint8_t* group_layer; uint64_t* rec_value; uint2* rec_group_rank;
+	uint32_t* pose_list; uint32_t* dirty_list;
+};
+
+__device__ __forceinline__ void push_key(const EmitParams& P, const EmitArgs& A, Sink& s, uint64_t key, uint64_t value) {
+	if (s.write && s.k < P.cap_keys) { A.keys[s.k] = key; A.values[s.k] = value; }
+	++s.k;
+}
+
+// DECAL / CURVE_DECAL renderable (:3840-3867)
+__device__ __forceinline__ void decal_entity(const EmitParams& P, const EmitArgs& A, Sink& s, int32_t e, int type) {
+	const uint8_t bucket = (uint8_t)P.view.bucket_map[A.decal_layer[e]];
+	if (bucket < 0xff) {
+		push_key(P, A, s, A.decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
+			sext(e) | ((uint64_t)(type == RT_DECAL ? DRAW_DECAL : DRAW_CURVE_DECAL) << SORT_VALUE_TYPE_SHIFT));
+	}
+}
+
+// MESH renderable (:3868-3956)
+__device__ __forceinline__ void mesh_entity(const EmitParams& P, const EmitArgs& A, Sink& s, int32_t e) {
 	const float global_lod_multiplier_rcp = LB_FDIV(1.0f, P.view.lod_multiplier); // :3798-3799
 	const float time_delta = P.view.time_delta;
 	const bool is_shadow = P.view.is_shadow != 0;
-	// ---- decals (:3840-3867) ----
-#pragma unroll 1
-	for (int t = RT_DECAL; t <= RT_CURVE_DECAL; t += 2) {
-		const uint32_t n = __ldg(cull_counters + t);
-		for (uint32_t i = gtid; i < n; i += gsize) {
-			const int32_t e = (int32_t)visible[P.type_base[t] + i];
-			const uint8_t bucket = (uint8_t)P.view.bucket_map[decal_layer[e]];
-			if (bucket < 0xff) {
-				const uint64_t key = decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT);
-				const uint64_t value = sext(e) | ((uint64_t)(t == RT_DECAL ? DRAW_DECAL : DRAW_CURVE_DECAL) << SORT_VALUE_TYPE_SHIFT);
-				push_key(keys, values, counts, P.cap_keys, key, value);
+	const lb200_sk_model& model = A.models[A.model_of[e]];
+	const double px = A.transforms[e].pos[0], py = A.transforms[e].pos[1], pz = A.transforms[e].pos[2];
+	const double dx = LB_DSUB(px, P.view.lod_ref_point[0]), dy = LB_DSUB(py, P.view.lod_ref_point[1]), dz = LB_DSUB(pz, P.view.lod_ref_point[2]);
+	const float squared_length = (float)LB_DADD(LB_DADD(LB_DMUL(dx, dx), LB_DMUL(dy, dy)), LB_DMUL(dz, dz)); // squaredLength(DVec3), math.cpp:397
+	const float sd = LB_FMUL(squared_length, global_lod_multiplier_rcp);
+	const uint32_t lod_idx = sd < model.lod_distances[0] ? 0u : sd < model.lod_distances[1] ? 1u : sd < model.lod_distances[2] ? 2u : sd < model.lod_distances[3] ? 3u : 4u;
+	const uint8_t fl = A.flags[e];
+	if (fl & LB200_SK_DIRTY) { // mi.dirty, :3878-3881: queueMaterialOverrideRefresh (rare: its own atomic)
+		if (s.write) {
+			const uint32_t slot = atomicAdd(&A.counts[CNT_DIRTY], 1u);
+			if (slot < P.cap_dirty) A.dirty_list[slot] = (uint32_t)e;
+		}
+		return;
+	}
+	int lods[2], n_lods = 0;
+	float cur = A.lod[e];
+	if (cur != (float)lod_idx) { // :3926-3941
+		const float d = LB_FSUB((float)lod_idx, cur);
+		const float ad = fabsf(d);
+		if (ad <= time_delta) {
+			cur = (float)lod_idx;
+			lods[n_lods++] = (int)lod_idx;
+		}
+		else {
+			if (!is_shadow) cur = LB_FADD(cur, LB_FMUL(LB_FDIV(d, ad), time_delta));
+			const uint32_t cur_lod_idx = (uint32_t)cur;
+			lods[n_lods++] = (int)cur_lod_idx;
+			if (cur_lod_idx < 3) lods[n_lods++] = (int)cur_lod_idx + 1;
+		}
+		if (s.write) A.lod[e] = cur;
+	}
+	else lods[n_lods++] = (int)lod_idx;
+	bool pose_done = A.pose_frame[e] == P.view.frame_number;
+	for (int li = 0; li < n_lods; ++li) { // create_key, :3883-3924
+		const int from = model.lod_from[lods[li]], to = model.lod_to[lods[li]];
+		for (int mesh_idx = from; mesh_idx <= to; ++mesh_idx) {
+			const lb200_sk_mesh mm = A.meshes[model.mesh_base + (uint32_t)mesh_idx];
+			const uint32_t bucket = P.view.bucket_map[mm.layer];
+			if (mm.skinned) {
+				// once per instance and frame: the instance's palette has to be built (PoseProcessor::push; the compare-exchange on
+				// Pose::frame of :3890-3897 — one thread owns the instance within a view)
+				if (!pose_done) {
+					pose_done = true;
+					if (s.write) {
+						A.pose_frame[e] = P.view.frame_number;
+						if (s.p < P.cap_pose) A.pose_list[s.p] = (uint32_t)e;
+					}
+					++s.p;
+				}
+				push_key(P, A, s, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
+					sext(e) | ((uint64_t)DRAW_SKINNED << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
+			}
+			else if ((fl & LB200_SK_MOVED) && !is_shadow) {
+				push_key(P, A, s, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
+					sext(e) | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
+			}
+			else if (bucket < 0xff) { // AutoInstancer::add(mesh_sort_key, e.index | mesh_idx << 40), :3913-3914
+				if (!s.write) { if (s.s_grp) atomicAdd(&s.s_grp[mm.sort_key], 1u); }
+				else {
+					const uint32_t rank = s.s_grp ? atomicAdd(&s.s_grp[mm.sort_key], 1u) : warp_claim_keyed(A.group_count, mm.sort_key);
+					if (s.r < P.cap_recs) {
+						A.rec_value[s.r] = sext(e) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT);
+						A.rec_group_rank[s.r] = make_uint2(mm.sort_key, rank);
+					}
+					if (rank == 0) A.group_layer[mm.sort_key] = mm.layer; // the same for every instance of the mesh: written once (a store per instance to a handful of bytes serialises at the L2)
+				}
+				++s.r;
+			}
+			else if (bucket < 0xffff) { // depth sorted, :3915-3922
+				const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
+				const float sq = (float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz));
+				push_key(P, A, s, float_flip(__float_as_uint(sq)) | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
+					sext(e) | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
 			}
 		}
 	}
-	// ---- meshes (:3868-3956) ----
-	const uint32_t n_mesh = __ldg(cull_counters + RT_MESH);
-	for (uint32_t i = gtid; i < n_mesh; i += gsize) {
-		const int32_t e = (int32_t)visible[P.type_base[RT_MESH] + i];
-		const lb200_sk_model& model = models[model_of[e]];
-		const double px = transforms[e].pos[0], py = transforms[e].pos[1], pz = transforms[e].pos[2];
-		const double dx = LB_DSUB(px, P.view.lod_ref_point[0]), dy = LB_DSUB(py, P.view.lod_ref_point[1]), dz = LB_DSUB(pz, P.view.lod_ref_point[2]);
-		const float squared_length = (float)LB_DADD(LB_DADD(LB_DMUL(dx, dx), LB_DMUL(dy, dy)), LB_DMUL(dz, dz)); // squaredLength(DVec3), math.cpp:397
-		const float sd = LB_FMUL(squared_length, global_lod_multiplier_rcp);
-		const uint32_t lod_idx = sd < model.lod_distances[0] ? 0u : sd < model.lod_distances[1] ? 1u : sd < model.lod_distances[2] ? 2u : sd < model.lod_distances[3] ? 3u : 4u;
-		const uint8_t fl = flags[e];
-		if (fl & LB200_SK_DIRTY) { // mi.dirty, :3878-3881: queueMaterialOverrideRefresh
-			const uint32_t slot = atomicAdd(&counts[CNT_DIRTY], 1u);
-			if (slot < P.cap_dirty) dirty_list[slot] = (uint32_t)e;
-			continue;
+}
+
+// block-wide exclusive scan of one value per thread (SK_THREADS threads); returns the thread's prefix, *total = the block's sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /* SK_THREADS / 32 + 1 */, uint32_t* total) {
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t x = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+		if (lane >= (uint32_t)d) x += y;
+	}
+	if (lane == 31) s_warp[warp] = x;
+	__syncthreads();
+	uint32_t before = 0, sum = 0;
+#pragma unroll
+	for (int w = 0; w < SK_THREADS / 32; ++w) { if ((uint32_t)w < warp) before += s_warp[w]; sum += s_warp[w]; }
+	__syncthreads();
+	*total = sum;
+	return before + x - v;
+}
+
+constexpr uint32_t SK_SMEM_GROUPS = 8192; // group counters a block keeps in shared memory (32 KB)
+
+// Every block walks its share of the visible renderables twice.  Pass 1 counts: keys / records / pose entries per thread, instances per
+// auto-instancer group per block (shared-memory atomics).  Then ONE block-wide scan and one global atomic per counter claim the block's
+// output ranges, and one global atomic per group the block touched claims its slice of the group.  Pass 2 repeats the logic and writes.
+__global__ void __launch_bounds__(SK_THREADS) emit_kernel(const __grid_constant__ EmitParams P, const uint32_t* __restrict__ visible,
+	const uint32_t* __restrict__ cull_counters, const EmitArgs A, uint32_t n_groups)
+{
+	extern __shared__ uint32_t s_grp_mem[];
+	__shared__ uint32_t s_warp[SK_THREADS / 32];
+	__shared__ uint32_t s_base[3];
+	uint32_t* s_grp = n_groups <= SK_SMEM_GROUPS ? s_grp_mem : nullptr;
+	if (s_grp) for (uint32_t g = threadIdx.x; g < n_groups; g += SK_THREADS) s_grp[g] = 0;
+	__syncthreads();
+	// the three segments as one index space: [MESH | DECAL | CURVE_DECAL]
+	const uint32_t n_mesh = __ldg(cull_counters + RT_MESH), n_decal = __ldg(cull_counters + RT_DECAL), n_curve = __ldg(cull_counters + RT_CURVE_DECAL);
+	const uint32_t n_all = n_mesh + n_decal + n_curve;
+	Sink sink = {false, 0u, 0u, 0u, s_grp};
+#pragma unroll 1
+	for (int pass = 0; pass < 2; ++pass) {
+		for (uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x; i < n_all; i += gridDim.x * SK_THREADS) {
+			if (i < n_mesh) mesh_entity(P, A, sink, (int32_t)visible[P.type_base[RT_MESH] + i]);
+			else if (i < n_mesh + n_decal) decal_entity(P, A, sink, (int32_t)visible[P.type_base[RT_DECAL] + (i - n_mesh)], RT_DECAL);
+			else decal_entity(P, A, sink, (int32_t)visible[P.type_base[RT_CURVE_DECAL] + (i - n_mesh - n_decal)], RT_CURVE_DECAL);
 		}
-		int lods[2], n_lods = 0;
-		float cur = lod[e];
-		if (cur != (float)lod_idx) { // :3926-3941
-			const float d = LB_FSUB((float)lod_idx, cur);
-			const float ad = fabsf(d);
-			if (ad <= time_delta) {
-				cur = (float)lod_idx;
-				lods[n_lods++] = (int)lod_idx;
-			}
-			else {
-				if (!is_shadow) cur = LB_FADD(cur, LB_FMUL(LB_FDIV(d, ad), time_delta));
-				const uint32_t cur_lod_idx = (uint32_t)cur;
-				lods[n_lods++] = (int)cur_lod_idx;
-				if (cur_lod_idx < 3) lods[n_lods++] = (int)cur_lod_idx + 1;
-			}
-			lod[e] = cur;
+		if (pass == 1) break;
+		uint32_t tk, tr, tp;
+		const uint32_t pk = block_exclusive_scan(sink.k, s_warp, &tk);
+		const uint32_t pr = block_exclusive_scan(sink.r, s_warp, &tr);
+		const uint32_t pp = block_exclusive_scan(sink.p, s_warp, &tp);
+		if (threadIdx.x == 0) {
+			s_base[0] = tk ? atomicAdd(&A.counts[CNT_KEYS], tk) : 0u;
+			s_base[1] = tr ? atomicAdd(&A.counts[CNT_RECS], tr) : 0u;
+			s_base[2] = tp ? atomicAdd(&A.counts[CNT_POSE], tp) : 0u;
 		}
-		else lods[n_lods++] = (int)lod_idx;
-		for (int li = 0; li < n_lods; ++li) { // create_key, :3883-3924
-			const int from = model.lod_from[lods[li]], to = model.lod_to[lods[li]];
-			for (int mesh_idx = from; mesh_idx <= to; ++mesh_idx) {
-				const lb200_sk_mesh mm = meshes[model.mesh_base + (uint32_t)mesh_idx];
-				const uint32_t bucket = P.view.bucket_map[mm.layer];
-				if (mm.skinned) {
-					// once per instance and frame: the instance's palette has to be built (PoseProcessor::push)
-					if (atomicExch(&pose_frame[e], P.view.frame_number) != P.view.frame_number) {
-						const uint32_t slot = atomicAdd(&counts[CNT_POSE], 1u);
-						if (slot < P.cap_pose) pose_list[slot] = (uint32_t)e;
-					}
-					push_key(keys, values, counts, P.cap_keys, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
-						sext(e) | ((uint64_t)DRAW_SKINNED << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
-				}
-				else if ((fl & LB200_SK_MOVED) && !is_shadow) {
-					push_key(keys, values, counts, P.cap_keys, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
-						sext(e) | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
-				}
-				else if (bucket < 0xff) { // AutoInstancer::add(mesh_sort_key, e.index | mesh_idx << 40), :3913-3914
-					const uint32_t rank = atomicAdd(&group_count[mm.sort_key], 1u);
-					const uint32_t rec = atomicAdd(&counts[CNT_RECS], 1u);
-					if (rec < P.cap_recs) {
-						rec_value[rec] = sext(e) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT);
-						rec_group_rank[rec] = make_uint2(mm.sort_key, rank);
-					}
-					group_layer[mm.sort_key] = mm.layer; // the same for every instance of the mesh
-				}
-				else if (bucket < 0xffff) { // depth sorted, :3915-3922
-					const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
-					const float sq = (float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz));
-					push_key(keys, values, counts, P.cap_keys, float_flip(__float_as_uint(sq)) | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
-						sext(e) | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
-				}
-			}
-		}
+		// the block's slice of every group it has instances of: count -> cursor
+		if (s_grp) for (uint32_t g = threadIdx.x; g < n_groups; g += SK_THREADS) if (s_grp[g]) s_grp[g] = atomicAdd(&A.group_count[g], s_grp[g]);
+		__syncthreads();
+		sink.write = true;
+		sink.k = s_base[0] + pk; sink.r = s_base[1] + pr; sink.p = s_base[2] + pp;
 	}
 }
 
@@ -269,22 +354,28 @@ __global__ void __launch_bounds__(RS_THREADS) rs_block_hist_kernel(int pass, con
 	block_hist[threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// exclusive scan over block_hist in (digit, block) order: one block, thread d owns digit d
-__global__ void __launch_bounds__(256) rs_scan_kernel(int pass, const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st, uint32_t* __restrict__ block_hist, uint32_t n_blocks) {
-	__shared__ uint32_t s_tot[256];
+// exclusive scan over block_hist in (digit, block) order.  Block d of the grid owns digit d: its base is the number of keys with a
+// smaller digit (the pass's global histogram), then one warp scans the digit's per-block counts 32 at a time.
+__global__ void __launch_bounds__(32) rs_scan_kernel(int pass, const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st, uint32_t* __restrict__ block_hist, uint32_t n_blocks) {
 	const uint32_t n = min(counts[CNT_KEYS], cap);
 	if (pass_is_trivial(st, pass, n)) return;
-	const uint32_t d = threadIdx.x;
-	uint32_t sum = 0;
-	for (uint32_t b = 0; b < n_blocks; ++b) sum += block_hist[d * n_blocks + b];
-	s_tot[d] = sum;
-	__syncthreads();
+	const uint32_t d = blockIdx.x, lane = threadIdx.x;
 	uint32_t base = 0;
-	for (uint32_t k = 0; k < d; ++k) base += s_tot[k];
-	for (uint32_t b = 0; b < n_blocks; ++b) {
-		const uint32_t c = block_hist[d * n_blocks + b];
-		block_hist[d * n_blocks + b] = base;
-		base += c;
+	for (uint32_t k = lane; k < d; k += 32) base += st->global_hist[pass][k];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+	uint32_t* row = block_hist + (size_t)d * n_blocks;
+	for (uint32_t b0 = 0; b0 < n_blocks; b0 += 32) {
+		const uint32_t b = b0 + lane;
+		const uint32_t c = b < n_blocks ? row[b] : 0u;
+		uint32_t x = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= (uint32_t)o) x += y;
+		}
+		if (b < n_blocks) row[b] = base + x - c;
+		base += __shfl_sync(0xffffffffu, x, 31);
 	}
 }
 
@@ -497,10 +588,10 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 	for (int t = 0; t < 4; ++t) EP.type_base[t] = type_base[t];
 	EP.cap_keys = sk->cap_keys; EP.cap_recs = sk->cap_recs; EP.cap_pose = sk->max_entities; EP.cap_dirty = sk->max_entities;
 	const uint32_t work = type_counts[RT_MESH] + type_counts[RT_DECAL] + type_counts[RT_CURVE_DECAL]; // upper bound of visible renderables
-	const uint32_t grid = std::max(1u, std::min((uint32_t)ctx->sm_count * 8u, (work + SK_THREADS - 1) / SK_THREADS));
-	emit_kernel<<<grid, SK_THREADS, 0, s>>>(EP, visible, cull_counters, sk->transforms, sk->d_model_of, sk->d_lod, sk->d_flags, sk->d_pose_frame,
-		sk->d_decal_sort_key, sk->d_decal_layer, sk->d_models, sk->d_meshes, sk->d_keys[0], sk->d_values[0], sk->d_counts, sk->d_group_count,
-		sk->d_group_layer, sk->d_rec_value, sk->d_rec_group_rank, sk->d_pose_list, sk->d_dirty_list);
+	const uint32_t grid = std::max(1u, std::min((uint32_t)ctx->sm_count * 4u, (work + SK_THREADS - 1) / SK_THREADS));
+	EmitArgs EA = {sk->transforms, sk->d_model_of, sk->d_lod, sk->d_flags, sk->d_pose_frame, sk->d_decal_sort_key, sk->d_decal_layer, sk->d_models, sk->d_meshes,
+		sk->d_keys[0], sk->d_values[0], sk->d_counts, sk->d_group_count, sk->d_group_layer, sk->d_rec_value, sk->d_rec_group_rank, sk->d_pose_list, sk->d_dirty_list};
+	emit_kernel<<<grid, SK_THREADS, n_groups <= SK_SMEM_GROUPS ? sizeof(uint32_t) * n_groups : 0, s>>>(EP, visible, cull_counters, EA, n_groups);
 	LB200_CHECK_LAUNCH(ctx);
 	GroupParams GP;
 	memcpy(GP.layer_to_bucket, view->layer_to_bucket, 256);
@@ -518,7 +609,7 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 		for (int pass = 0; pass < RS_PASSES; ++pass) {
 			rs_block_hist_kernel<<<sk->sort_blocks, RS_THREADS, 0, s>>>(pass, sk->d_keys[0], sk->d_keys[1], sk->d_counts, sk->cap_keys, sk->d_sort_state, sk->d_block_hist);
 			LB200_CHECK_LAUNCH(ctx);
-			rs_scan_kernel<<<1, 256, 0, s>>>(pass, sk->d_counts, sk->cap_keys, sk->d_sort_state, sk->d_block_hist, sk->sort_blocks);
+			rs_scan_kernel<<<256, 32, 0, s>>>(pass, sk->d_counts, sk->cap_keys, sk->d_sort_state, sk->d_block_hist, sk->sort_blocks);
 			LB200_CHECK_LAUNCH(ctx);
 			rs_scatter_kernel<<<sk->sort_blocks, RS_THREADS, 0, s>>>(pass, sk->d_keys[0], sk->d_keys[1], sk->d_values[0], sk->d_values[1], sk->d_counts, sk->cap_keys,
 				sk->d_sort_state, sk->d_block_hist);
