@@ -40,6 +40,10 @@ LB200_API void lb200_shutdown(lb200_ctx* ctx);
 LB200_API const char* lb200_last_error(const lb200_ctx* ctx); /* ctx may be NULL: last init error */
 LB200_API int lb200_device_count(void);
 LB200_API int lb200_synchronize(lb200_ctx* ctx);
+/* Calls fn(user) from a driver thread once everything enqueued on the context stream so far has finished (cudaLaunchHostFunc).  For callers
+ * that must not block their thread — the engine calls cull from job-system fibers (pipeline.cpp:1036-1041): fn schedules a job that turns a
+ * jobs::Signal green and the fiber parks on that signal meanwhile.  fn must not call into this library. */
+LB200_API int lb200_host_callback(lb200_ctx* ctx, void (*fn)(void*), void* user);
 /* Kernels this library launched on ctx since init (bench.py's gpu_launches). */
 LB200_API uint64_t lb200_launch_count(const lb200_ctx* ctx);
 /* cudaStream_t of the context as an integer (for CUDA-event timing on the launching stream). */

@@ -78,6 +78,12 @@ int lb200_synchronize(lb200_ctx* ctx) {
 	return lb200_comm_check(ctx);
 }
 
+int lb200_host_callback(lb200_ctx* ctx, void (*fn)(void*), void* user) {
+	if (!ctx || !fn) return LB200_ERR_INVALID;
+	LB200_CUDA(ctx, cudaLaunchHostFunc(ctx->stream, fn, user));
+	return LB200_OK;
+}
+
 void* lb200_host_alloc(lb200_ctx* ctx, size_t bytes) {
 	if (!ctx) return nullptr;
 	void* p = nullptr;

@@ -322,7 +322,16 @@ int ensureDevice(lb200_culling* cs) {
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_counters, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS));
 		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_counters, 0, sizeof(uint32_t) * 2 * cs->lanes * COUNTER_WORDS, ctx->stream));
 		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_counters, sizeof(uint32_t) * COUNTER_WORDS, cudaHostAllocMapped));
-		if (cudaHostGetDevicePointer((void**)&cs->h_counters_dev, cs->h_counters, 0) != cudaSuccess) { cudaGetLastError(); cs->h_counters_dev = nullptr; }
+		{
+			const cudaError_t me = cudaHostGetDevicePointer((void**)&cs->h_counters_dev, cs->h_counters, 0);
+			if (me != cudaSuccess) {
+				cudaGetLastError();
+				cs->h_counters_dev = nullptr;
+				cudaPointerAttributes pa = {}; // unified addressing: page-locked memory has a device address whether or not it was asked to be "mapped"
+				if (cudaPointerGetAttributes(&pa, cs->h_counters) == cudaSuccess && pa.devicePointer) cs->h_counters_dev = (uint32_t*)pa.devicePointer;
+				else { cudaGetLastError(); lb200_set_error(ctx, "page-locked counters have no device address: %s", cudaGetErrorString(me)); }
+			}
+		}
 		cs->threads = CULL_THREADS;
 		int per_sm = 0;
 		cs->stage_depth = getenv("LB200_CULL_STAGE") ? std::max(0, std::min(2, atoi(getenv("LB200_CULL_STAGE")))) : LB200_CULL_STAGE_DEFAULT;
@@ -765,9 +774,11 @@ int lb200_culling_cull_begin(lb200_culling* cs, const lb200_shifted_frustum* fru
 	int rc = ensureDevice(cs);
 	if (rc) return rc;
 	cudaPointerAttributes attr = {};
-	if (!cs->h_counters_dev || cudaPointerGetAttributes(&attr, out_ids) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+	const cudaError_t pe = cudaPointerGetAttributes(&attr, out_ids);
+	if (!cs->h_counters_dev || pe != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
 		cudaGetLastError();
-		lb200_set_error(ctx, "cull_begin needs a page-locked destination (lb200_host_alloc)");
+		lb200_set_error(ctx, "cull_begin needs a page-locked destination (lb200_host_alloc): cudaPointerGetAttributes -> %s, memory type %d, device pointer %p, counters mapped %d",
+			cudaGetErrorString(pe), (int)attr.type, attr.devicePointer, cs->h_counters_dev ? 1 : 0);
 		return LB200_ERR_INVALID;
 	}
 	if (!cs->done_event) LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->done_event, cudaEventDisableTiming));

@@ -85,14 +85,21 @@ struct CullingSystemB200 final : CullingSystem {
 		lb200_cull_result res;
 		int rc;
 		if (lb200_culling_page_count(m_cs) == 0) return nullptr; // culling_system.cpp:322
-		// no OS wait inside a job (docs/job_system.md): enqueue, then give the worker back to the job system until the GPU is done
+		// No OS wait inside a job (docs/job_system.md) and no spinning on jobs::yield() (its own TODO: a yielding fiber can be popped while it
+		// is still switching out, job_system.cpp:763): enqueue the cull, let the driver call back when the stream has reached the end of it,
+		// and park this fiber on a jobs::Signal meanwhile.  The callback runs on a driver thread, which is not a job worker, so it only
+		// schedules a job (jobs::run is legal from any thread) and that job turns the signal green.
+		jobs::Signal done;
+		jobs::turnRed(&done);
 		rc = lb200_culling_cull_begin(m_cs, (const lb200_shifted_frustum*)&frustum, type, m_ids, m_capacity);
 		if (rc == LB200_OK) {
-			while (lb200_culling_cull_poll(m_cs) == 0) jobs::yield();
+			rc = lb200_host_callback(m_ctx, [](void* signal) { jobs::run(signal, [](void* s) { jobs::turnGreen((jobs::Signal*)s); }, nullptr); }, &done);
+			if (rc == LB200_OK) jobs::wait(&done);
+			else while (lb200_culling_cull_poll(m_cs) == 0) {} // could not register the callback: the cull itself is short
 			rc = lb200_culling_cull_end(m_cs, &res);
 		}
 		if (rc != LB200_OK) { // no CPU fallback: report and return "nothing visible" (the reference's own empty result, :322)
-			logError("lumix_b200 cull failed: ", lb200_last_error(m_ctx));
+			logError("lumix_b200 cull failed (code ", rc, "): ", lb200_last_error(m_ctx));
 			return nullptr;
 		}
 		CullResult* head = nullptr;

@@ -122,5 +122,22 @@ else
 	tail -8 "$TMP/sortkeys.log" >&2 || true
 fi
 $CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/ref_harness.o" "$TMP/obj/ref_anim_harness.o" $EXTRA -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL
+# (7) the executed drop-in boundary: the SAME reference objects minus its CullingSystemImpl, plus lumixengine_b200/host/culling_system_b200.cpp
+#     (CullingSystem::create / CullResult::free over liblumix_b200.so) and a harness that drives it through the abstract CullingSystem from
+#     job-system fibers (oracle/ref/ref_engine_shim_harness.cpp).  Needs the product library to link against; skipped if it is not built yet.
+PRODUCT_DIR="$(cd "$HERE/../lumixengine_b200" && pwd)"
+if [ -f "$PRODUCT_DIR/liblumix_b200.so" ]; then
+	SHIM_OBJS=""
+	for o in $OBJS; do case "$o" in */core_*.o) SHIM_OBJS="$SHIM_OBJS $o";; esac; done # job system, allocators, PageAllocator, math, geometry, log ...
+	if $CXX $FL -I"$HERE/../include" -c "$PRODUCT_DIR/host/culling_system_b200.cpp" -o "$TMP/obj/shim.o" 2> "$TMP/shim.log" \
+		&& $CXX $FL -c "$HERE/ref/ref_engine_shim_harness.cpp" -o "$TMP/obj/shim_harness.o" 2>> "$TMP/shim.log" \
+		&& $CXX -shared -o "$OUT/libengine_shim_b200.so" $SHIM_OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/shim.o" "$TMP/obj/shim_harness.o" \
+			-L"$PRODUCT_DIR" -llumix_b200 -Wl,-rpath,'$ORIGIN/../../lumixengine_b200' -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL 2>> "$TMP/shim.log"; then
+		echo "built $OUT/libengine_shim_b200.so"
+	else
+		echo "build_ref.sh: engine shim library not built (see below)" >&2
+		tail -8 "$TMP/shim.log" >&2 || true
+	fi
+fi
 ( cd "$REF" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$OUT/REFERENCE_COMMIT"
 echo "built $OUT/libref_lumix.so"

@@ -56,7 +56,7 @@ i64 AtomicI64::setBits(i64 v) { return __atomic_fetch_or(&value, v, __ATOMIC_ACQ
 i64 AtomicI64::clearBits(i64 v) { return __atomic_fetch_and(&value, ~v, __ATOMIC_ACQ_REL); }
 bool AtomicI64::bitTestAndSet(u32 bit_position) {
 	const i64 mask = i64(1) << bit_position;
-	return (__atomic_fetch_or(&value, mask, __ATOMIC_ACQ_REL) & mask) != 0;
+	return (__atomic_fetch_or(&value, mask, __ATOMIC_ACQ_REL) & mask) == 0; // true = the bit was clear and is now ours (win/atomic.cpp:47: !_interlockedbittestandset64)
 }
 void* exchangePtr(void* volatile* value, void* exchange) { return __atomic_exchange_n(value, exchange, __ATOMIC_ACQ_REL); }
 bool compareExchangePtr(void* volatile* value, void* exchange, void* comperand) {

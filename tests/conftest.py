@@ -42,7 +42,7 @@ def pytest_sessionfinish(session, exitstatus):
 @pytest.hookimpl(trylast=True)
 def pytest_unconfigure(config):
     mod = sys.modules.get("oracle.pyoracle")
-    if mod is not None and getattr(mod, "_ref", None) is not None:
+    if (mod is not None and getattr(mod, "_ref", None) is not None) or os.environ.get("LB200_ENGINE_SHIM_LOADED") == "1":
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(_exit_status[0])

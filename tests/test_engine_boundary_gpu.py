@@ -1,0 +1,87 @@
+"""The drop-in boundary, executed: lumixengine_b200/host/culling_system_b200.cpp linked with the reference's own job system, allocators and
+PageAllocator (oracle/_ref/libengine_shim_b200.so, built by oracle/build_ref.sh from /root/reference + this repository's shim).  The GPU is
+driven through the engine's abstract CullingSystem (culling_system.h:58-77): CullingSystem::create(allocator, page_allocator), add / set /
+remove, cull() from job-system fibers for several views at once (pipeline.cpp:1036-1041), the CullResult page chain (one renderable
+type per 4 KB page, <= 1020 ids, pages from the engine's PageAllocator) walked and freed by the caller (pipeline.cpp:1045)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import lumixengine_b200 as lb
+from lumixengine_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+SO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libengine_shim_b200.so")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def shim():
+    if not os.path.exists(SO):
+        pytest.skip("oracle/_ref/libengine_shim_b200.so not built (needs /root/reference at build time)")
+    L = C.CDLL(SO)
+    os.environ["LB200_ENGINE_SHIM_LOADED"] = "1"  # the engine's job system cannot be shut down on Linux: tests/conftest.py leaves with os._exit
+    L.shim_create.restype = C.c_void_p
+    L.shim_get_radius.restype = C.c_float
+    assert L.shim_jobs_init(C.c_int(4)) == 4
+    return L
+
+
+def _cull_views(L, h, frusta, type, cap):
+    fb = np.ascontiguousarray(np.stack([lb.culling.frustum_bytes(f) for f in frusta]))
+    ids = np.zeros((len(frusta), cap), np.uint32)
+    tys = np.zeros((len(frusta), cap), np.uint8)
+    info = np.zeros((len(frusta), 4), np.uint32)
+    L.shim_cull_views(C.c_void_p(h), _p(fb), C.c_uint32(len(frusta)), C.c_int(type), _p(ids), _p(tys), C.c_uint32(cap), _p(info))
+    return [(ids[v, :info[v, 0]].copy(), tys[v, :info[v, 0]].copy(), info[v]) for v in range(len(frusta))]
+
+
+def test_cull_through_the_engine_vtable_from_job_fibers(shim, oracle):
+    L = shim
+    n = 120_000
+    scene = scenes.cull_scene(n, (3000.0, 300.0, 3000.0), seed=77, big_fraction=0.004, type_probs=(0.7, 0.15, 0.1, 0.05))
+    h = L.shim_create()
+    e, t, p, r = (np.ascontiguousarray(scene[k], d) for k, d in (("entities", np.int32), ("types", np.uint8), ("pos", np.float64), ("radius", np.float32)))
+    L.shim_add(C.c_void_p(h), _p(e), _p(t), _p(p), _p(r), C.c_uint32(n))
+    oc = oracle.OracleCulling()
+    oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    assert L.shim_is_added(C.c_void_p(h), C.c_int32(5)) == 1 and L.shim_get_radius(C.c_void_p(h), C.c_int32(5)) == np.float32(scene["radius"][5])
+    a = scenes.c1_frustum_args()
+    frusta = [lb.frustum_perspective(**dict(a, far=3500.0)),
+              lb.frustum_perspective(**dict(a, position=(500.0, 30.0, 400.0), direction=(-0.6, -0.1, -0.8), far=2500.0)),
+              lb.frustum_ortho((0.0, 1000.0, 0.0), (0.0, -1.0, 0.0), (0.0, 0.0, -1.0), 900.0, 900.0, 0.0, 2000.0),
+              lb.frustum_perspective(**dict(a, position=(1e6, 0.0, 1e6), far=50.0))]  # sees nothing
+    base_pages = L.shim_allocated_pages(C.c_void_p(h))
+
+    def check(type_filter):
+        views = _cull_views(L, h, frusta, type_filter, n)  # four views, four jobs at once
+        for f, (ids, tys, info) in zip(frusta, views):
+            oi, ot, _ = oc.cull(lb.culling.frustum_bytes(f), type_filter)
+            assert info[2] == 0, "a result page broke the CullResult contract (count > 1020 or not 4 KB aligned)"
+            assert len(ids) == len(oi)
+            assert np.array_equal(np.sort(ids.astype(np.int64) * 256 + tys), np.sort(oi.astype(np.int64) * 256 + ot))
+            if len(oi):
+                assert info[1] >= -(-len(oi) // 1020) and info[3] == 0
+        assert sum(len(v[0]) for v in views) > 20_000 or type_filter > 0
+        assert L.shim_allocated_pages(C.c_void_p(h)) == base_pages, "CullResult::free left pages allocated"
+    check(-1)
+    check(1)
+    # edits through the same interface (setPosition / setRadius / remove paths of culling_system.cpp:160-258), then again
+    rng = np.random.default_rng(4)
+    mv = rng.choice(n, 6000, replace=False).astype(np.int32)
+    newp = scene["pos"][mv] + rng.normal(size=(len(mv), 3)) * np.array([400.0, 30.0, 400.0])
+    newr = (rng.random(len(mv)) * 500).astype(np.float32)
+    L.shim_set(C.c_void_p(h), _p(mv), _p(np.ascontiguousarray(newp)), _p(newr), C.c_uint32(len(mv)))
+    oc.set(mv, newp, newr)
+    gone = rng.choice(np.setdiff1d(np.arange(n, dtype=np.int32), mv), 3000, replace=False).astype(np.int32)
+    L.shim_remove(C.c_void_p(h), _p(gone), C.c_uint32(len(gone)))
+    oc.remove(gone)
+    base_pages = L.shim_allocated_pages(C.c_void_p(h))
+    check(-1)
+    os.write(2, b"[test] all views checked\n")
+    L.shim_destroy(C.c_void_p(h))
