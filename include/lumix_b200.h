@@ -52,6 +52,10 @@ LB200_API uint64_t lb200_stream_handle(const lb200_ctx* ctx);
 LB200_API void* lb200_host_alloc(lb200_ctx* ctx, size_t bytes);
 LB200_API void lb200_host_free(lb200_ctx* ctx, void* p);
 /* Copy `bytes` from a device pointer handed out by this library (e.g. *out_dev_ids) to host memory, ordered after the context stream. */
+/* Device buffers for the entry points that take device pointers (lb200_culling_set_many_device, lb200_sortkeys_set_transforms_device). */
+LB200_API void* lb200_device_alloc(lb200_ctx* ctx, size_t bytes);
+LB200_API void lb200_device_free(lb200_ctx* ctx, void* device_ptr);
+LB200_API int lb200_copy_to_device(lb200_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
 LB200_API int lb200_copy_to_host(lb200_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
 /* Device-time helpers: record a timestamp on the context stream / milliseconds between two of them (CUDA events). */
 LB200_API int lb200_event_create(lb200_ctx* ctx, void** out_event);
@@ -191,6 +195,17 @@ LB200_API int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words,
  * back-to-back timed culls never re-read an L2-resident scene (B200_PROFILING.md "Timing hygiene"). */
 LB200_API int lb200_culling_set_replicas(lb200_culling* cs, uint32_t replicas);
 /* Algorithmic HBM bytes of the last cull: page descriptors + 16 B per tested sphere + 4 B per id read + 4 B per id written + mask. */
+/* Device-side re-binning: CullingSystem::set (culling_system.cpp:222-240) for n DISTINCT entities whose new world spheres lie
+ * in device memory — the sphere refresh behind a hierarchy propagate (render_module.cpp:1544-1554; lb200_hierarchy_refresh_spheres) — without
+ * the host's cell map in the loop: in-cell movers are overwritten in place, cell / big-ness changers leave their pages (tombstone + per-page
+ * compaction, empty pages to a free list) and are re-inserted sorted by target chain (open page first, new pages from the free list).
+ * dev_entities: n entity ids in device memory, or NULL for the identity (mover i = entity i); max_entity: largest entity id that can appear.
+ * The host mirror is refreshed lazily: the next host-side accessor / mutator (add, remove, set*, get_page, ...) pulls the device state back
+ * first (or call lb200_culling_sync_host).  Visible sets of later culls are the reference's; slots / pages inside a chain may differ from
+ * a sequential replay of the same edits (as they do between two edit orders).  Needs set_replicas(1). */
+LB200_API int lb200_culling_set_many_device(lb200_culling* cs, const int32_t* dev_entities, const double* dev_pos3, const float* dev_radius, uint32_t n, uint32_t max_entity);
+LB200_API int lb200_culling_sync_host(lb200_culling* cs);
+LB200_API uint32_t lb200_culling_last_rebin_changers(const lb200_culling* cs);
 /* Measurement helper: device time (ms) of `iters` single culls, each with the device to itself and its launch already queued when the
  * device reaches it (no host launch latency inside the interval, nothing overlapping the cull).  mode 0 = the cull, 1 = nothing between
  * the two event records, 2 = one empty kernel of the cull's grid (the fixed costs the first number contains). */
@@ -333,6 +348,9 @@ LB200_API int lb200_hierarchy_get_globals(lb200_hierarchy* h, lb200_transform* o
 /* RenderModuleImpl::onModelInstanceMoved, render_module.cpp:1544-1554: world sphere per node =
  * (global.pos, bounding_radius * max(scale)); out_pos3 n*3 doubles, out_radius n floats (host). */
 LB200_API int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius, double* out_pos3, float* out_radius);
+/* The same refresh left in device memory (bounding_radius may be NULL after the first call: the radii uploaded last are kept): *dev_pos3 = n x 3
+ * doubles, *dev_radius = n floats, both indexed like `parents`; input of lb200_culling_set_many_device when node index = entity id. */
+LB200_API int lb200_hierarchy_refresh_spheres(lb200_hierarchy* h, const float* bounding_radius, const double** dev_pos3, const float** dev_radius);
 /* The other direction, World::transformEntity(entity, update_local = true) (world.cpp:267-270) / World::setParent (world.cpp:619-701):
  * world transforms are authoritative (physics, editor gizmo, re-parenting) and the local transforms follow:
  * local = Transform::computeLocal(parent global, own global) (math.cpp:809-816) for every non-root node, one launch.

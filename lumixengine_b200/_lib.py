@@ -86,20 +86,20 @@ class Mesh(C.Structure):
 # every symbol include/lumix_b200.h declares (tests/test_abi.py checks the header against this and the .so)
 SYMBOLS = [
     "lb200_init", "lb200_shutdown", "lb200_last_error", "lb200_device_count", "lb200_synchronize", "lb200_host_callback", "lb200_launch_count", "lb200_stream_handle",
-    "lb200_host_alloc", "lb200_host_free", "lb200_copy_to_host", "lb200_event_create", "lb200_event_record", "lb200_event_elapsed_ms", "lb200_event_destroy",
+    "lb200_host_alloc", "lb200_host_free", "lb200_copy_to_host", "lb200_device_alloc", "lb200_device_free", "lb200_copy_to_device", "lb200_event_create", "lb200_event_record", "lb200_event_elapsed_ms", "lb200_event_destroy",
     "lb200_frustum_perspective", "lb200_frustum_ortho", "lb200_frustum_from_viewport",
     "lb200_culling_create", "lb200_culling_destroy", "lb200_culling_add", "lb200_culling_remove", "lb200_culling_set_position",
     "lb200_culling_set_radius", "lb200_culling_set", "lb200_culling_get_radius", "lb200_culling_is_added",
     "lb200_culling_add_many", "lb200_culling_set_many", "lb200_culling_set_many_unique", "lb200_culling_set_position_many", "lb200_culling_set_radius_many", "lb200_culling_remove_many",
     "lb200_culling_page_count", "lb200_culling_entity_count", "lb200_culling_get_page",
     "lb200_culling_cull", "lb200_culling_cull_begin", "lb200_culling_cull_poll", "lb200_culling_cull_end", "lb200_culling_cull_device", "lb200_culling_cull_device_n", "lb200_culling_last_result", "lb200_culling_flush", "lb200_culling_read_bitmask", "lb200_culling_set_replicas",
-    "lb200_culling_last_algorithmic_bytes", "lb200_culling_time_lone_cull", "lb200_culling_read_trace",
+    "lb200_culling_last_algorithmic_bytes", "lb200_culling_time_lone_cull", "lb200_culling_set_many_device", "lb200_culling_sync_host", "lb200_culling_last_rebin_changers", "lb200_culling_read_trace",
     "lb200_comm_get_unique_id", "lb200_comm_init", "lb200_comm_destroy", "lb200_comm_enable_p2p", "lb200_comm_status", "lb200_culling_gather_stride_words", "lb200_culling_allgather", "lb200_culling_cull_gather",
     "lb200_culling_cull_exchange", "lb200_culling_cull_exchange_n", "lb200_culling_exchange_slab_words", "lb200_culling_page_id",
     "lb200_sortkeys_create", "lb200_sortkeys_destroy", "lb200_sortkeys_set_models", "lb200_sortkeys_set_instances", "lb200_sortkeys_set_transforms",
     "lb200_sortkeys_set_transforms_device", "lb200_sortkeys_create_keys", "lb200_sortkeys_device_outputs",
     "lb200_hierarchy_create", "lb200_hierarchy_destroy", "lb200_hierarchy_depth", "lb200_hierarchy_set_locals", "lb200_hierarchy_set_root_globals",
-    "lb200_hierarchy_propagate", "lb200_hierarchy_get_globals", "lb200_hierarchy_get_spheres", "lb200_hierarchy_get_relative_matrices", "lb200_hierarchy_set_globals", "lb200_hierarchy_compute_locals", "lb200_hierarchy_get_locals", "lb200_hierarchy_algorithmic_bytes",
+    "lb200_hierarchy_propagate", "lb200_hierarchy_get_globals", "lb200_hierarchy_get_spheres", "lb200_hierarchy_refresh_spheres", "lb200_hierarchy_get_relative_matrices", "lb200_hierarchy_set_globals", "lb200_hierarchy_compute_locals", "lb200_hierarchy_get_locals", "lb200_hierarchy_algorithmic_bytes",
     "lb200_animation_create", "lb200_animation_destroy", "lb200_animation_set_instances", "lb200_animation_update", "lb200_animation_skin",
     "lb200_animation_get_dual_quats", "lb200_animation_get_matrices", "lb200_animation_get_pose", "lb200_animation_get_times", "lb200_animation_set_layers", "lb200_animation_bone_attachments", "lb200_animation_compute_relative", "lb200_animation_get_relative_pose", "lb200_animation_blend_pose",
     "lb200_animation_get_skinned", "lb200_animation_skinned_checksum", "lb200_animation_algorithmic_bytes",
@@ -148,6 +148,7 @@ def lib():
     L.lb200_stream_handle.argtypes = [vp]
     L.lb200_culling_get_radius.restype = C.c_float
     L.lb200_culling_page_count.restype = C.c_uint32
+    L.lb200_culling_last_rebin_changers.restype = C.c_uint32
     L.lb200_culling_entity_count.restype = C.c_uint32
     L.lb200_culling_gather_stride_words.restype = C.c_uint32
     L.lb200_culling_exchange_slab_words.restype = C.c_uint32
@@ -161,6 +162,10 @@ def lib():
     L.lb200_host_alloc.restype = vp
     L.lb200_host_alloc.argtypes = [vp, C.c_size_t]
     L.lb200_host_free.restype = None
+    L.lb200_device_alloc.restype = vp
+    L.lb200_device_alloc.argtypes = [vp, C.c_size_t]
+    L.lb200_device_free.restype = None
+    L.lb200_device_free.argtypes = [vp, vp]
     L.lb200_host_free.argtypes = [vp, vp]
     L.lb200_event_destroy.restype = None
     L.lb200_event_destroy.argtypes = [vp, vp]
@@ -189,6 +194,9 @@ def check(rc, ctx_handle=None):
 
 def ptr(a):
     return None if a is None else a.ctypes.data_as(vp)
+
+
+LB200_ERR_CUDA_CODE = -2
 
 
 class Context:
@@ -232,6 +240,19 @@ class Context:
             check(ERR_CUDA, self.h)
         buf = (C.c_uint8 * (max(n, 1) * dt.itemsize)).from_address(p)
         return np.frombuffer(buf, dtype=dt, count=n)
+
+    def to_device(self, array):
+        """Device copy of a numpy array -> device pointer (int); free it with free_device."""
+        import numpy as np
+        a = np.ascontiguousarray(array)
+        p = self.L.lb200_device_alloc(self.h, C.c_size_t(max(a.nbytes, 1)))
+        if not p:
+            check(LB200_ERR_CUDA_CODE, self.h)
+        check(self.L.lb200_copy_to_device(self.h, vp(p), ptr(a), C.c_size_t(a.nbytes)), self.h)
+        return p
+
+    def free_device(self, dev_ptr):
+        self.L.lb200_device_free(self.h, vp(dev_ptr))
 
     def copy_to_host(self, dev_ptr, n, dtype):
         """numpy array of n elements read from a device pointer this library handed out."""

@@ -100,6 +100,32 @@ void lb200_host_free(lb200_ctx* ctx, void* p) {
 	if (p) cudaFreeHost(p);
 }
 
+void* lb200_device_alloc(lb200_ctx* ctx, size_t bytes) {
+	if (!ctx) return nullptr;
+	void* p = nullptr;
+	cudaSetDevice(ctx->device);
+	if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+		lb200_set_error(ctx, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return p;
+}
+
+void lb200_device_free(lb200_ctx* ctx, void* p) {
+	if (!ctx || !p) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(p);
+}
+
+int lb200_copy_to_device(lb200_ctx* ctx, void* dst_device, const void* src_host, size_t bytes) {
+	if (!ctx || (bytes && (!dst_device || !src_host))) return LB200_ERR_INVALID;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	LB200_CUDA(ctx, cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
 int lb200_copy_to_host(lb200_ctx* ctx, void* dst_host, const void* src_device, size_t bytes) {
 	if (!ctx || (bytes && (!dst_host || !src_device))) return LB200_ERR_INVALID;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));

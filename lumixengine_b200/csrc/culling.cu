@@ -304,6 +304,22 @@ struct lb200_culling {
 	uint32_t* d_slab = nullptr;
 	size_t slab_cap = 0;
 
+	// ---- device-side re-binning (lb200_culling_set_many_device) ----
+	// While `device_authoritative`, the page arrays in HBM are ahead of the host mirror (entities were re-binned by kernels); any host-side
+	// accessor or mutator first pulls the device state back (syncHostFromDevice).
+	bool device_authoritative = false;
+	uint64_t rebin_built_gen = ~0ull;   // host.edit_gen the device-side tables were built from
+	uint32_t* d_entity_to_slot = nullptr; uint32_t entity_cap = 0;
+	int4* d_page_cell = nullptr;        // per page: cell indices x, y, z, type | is_big << 8
+	unsigned long long* d_hash_keys = nullptr; uint32_t* d_hash_vals = nullptr; uint32_t hash_cap = 0; // packed cell key -> open page of its chain
+	uint32_t* d_free_pages = nullptr;   // stack of free page ids
+	uint32_t* d_rebin_counters = nullptr; uint32_t* h_rebin_counters = nullptr; // RB_* below; pinned mirror
+	uint32_t* d_changers = nullptr; uint32_t changers_cap = 0; // mover indices that change cell / chain
+	uint32_t* d_page_dirty = nullptr; uint32_t* d_dirty_pages = nullptr;
+	uint64_t* d_rb_keys[2] = {}; uint64_t* d_rb_vals[2] = {}; void* d_rb_sort_state = nullptr; uint32_t* d_rb_block_hist = nullptr; uint32_t rb_sort_blocks = 0;
+	uint32_t dev_high_water = 0;        // pages [0, dev_high_water) may be in use on the device
+	uint32_t rebin_page_cap = 0;        // size of the per-page side arrays (follows dev_cap)
+
 	uint32_t last_type_base[256];
 	lb200_cull_result last = {};
 	bool has_last = false;
@@ -312,6 +328,17 @@ struct lb200_culling {
 };
 
 namespace {
+
+int syncHostFromDevice(lb200_culling* cs);
+// pages the kernels have to look at: the host's high-water mark, or the device's own while it is ahead of the host mirror
+inline uint32_t livePages(const lb200_culling* cs) { return cs->device_authoritative ? cs->dev_high_water : cs->host.high_water; }
+#define LB200_HOST_VIEW(cs)                                               \
+	do {                                                                  \
+		if ((cs) && (cs)->device_authoritative) {                         \
+			const int rc__ = syncHostFromDevice(cs);                      \
+			if (rc__) return rc__;                                        \
+		}                                                                 \
+	} while (0)
 
 int ensureDevice(lb200_culling* cs) {
 	lb200_ctx* ctx = cs->ctx;
@@ -469,7 +496,8 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 		P.pz[i] = f->points[point_of_plane[i]][2];
 	}
 	P.ox = f->origin[0]; P.oy = f->origin[1]; P.oz = f->origin[2];
-	P.n_pages = h.high_water;
+	const uint32_t n_pages = livePages(cs);
+	P.n_pages = n_pages;
 	P.type_filter = type;
 	P.item_cap = cs->item_cap;
 	static const bool trace = getenv("LB200_CULL_TRACE") != nullptr;
@@ -505,9 +533,9 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	cs->uploaded_since_last_cull = false;
 	// chunk = pages per block per round: spread the pages over every resident block, at most one classify thread per page
 	const uint32_t resident = (uint32_t)(stream || xchg ? cs->grid_lanes : cs->grid);
-	uint32_t chunk = (h.high_water + resident - 1) / resident;
+	uint32_t chunk = (n_pages + resident - 1) / resident;
 	chunk = std::max(32u, std::min((uint32_t)MAX_CHUNK, chunk));
-	const uint32_t blocks = std::max(1u, std::min(resident, (h.high_water + chunk - 1) / chunk));
+	const uint32_t blocks = std::max(1u, std::min(resident, (n_pages + chunk - 1) / chunk));
 	P.chunk = chunk;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -526,7 +554,7 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	cs->last_counters = cur; cs->last_out = out; cs->last_mask = mask_arg; // exchange culls keep their rows in the slabs
 	cs->lane_parity[lane] ^= 1u;
 	if (!xchg) ++cs->seq;
-	cs->last_pages = h.high_water;
+	cs->last_pages = n_pages;
 	return LB200_OK;
 }
 
@@ -617,6 +645,11 @@ void lb200_culling_destroy(lb200_culling* cs) {
 		if (cs->done_event) cudaEventDestroy(cs->done_event);
 		cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_out_ids); cudaFree(cs->d_mask);
 		cudaFree(cs->d_counters); cudaFree(cs->d_stage); cudaFree(cs->d_gather_ids); cudaFree(cs->d_slab);
+		cudaFree(cs->d_entity_to_slot); cudaFree(cs->d_page_cell); cudaFree(cs->d_hash_keys); cudaFree(cs->d_hash_vals); cudaFree(cs->d_free_pages);
+		cudaFree(cs->d_rebin_counters); cudaFree(cs->d_changers); cudaFree(cs->d_page_dirty); cudaFree(cs->d_dirty_pages);
+		for (int b = 0; b < 2; ++b) { cudaFree(cs->d_rb_keys[b]); cudaFree(cs->d_rb_vals[b]); }
+		cudaFree(cs->d_rb_sort_state); cudaFree(cs->d_rb_block_hist);
+		if (cs->h_rebin_counters) cudaFreeHost(cs->h_rebin_counters);
 		if (cs->h_counters) cudaFreeHost(cs->h_counters);
 		if (cs->h_stage) cudaFreeHost(cs->h_stage);
 	}
@@ -624,17 +657,22 @@ void lb200_culling_destroy(lb200_culling* cs) {
 }
 
 int lb200_culling_add(lb200_culling* cs, int32_t entity, uint8_t type, const double pos[3], float radius) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || !pos || type == LB200_TYPE_ALL) return LB200_ERR_INVALID;
 	return cs->host.add(entity, type, pos, radius);
 }
-int lb200_culling_remove(lb200_culling* cs, int32_t entity) { return cs ? cs->host.remove(entity) : LB200_ERR_INVALID; }
-int lb200_culling_set_position(lb200_culling* cs, int32_t entity, const double pos[3]) { return cs && pos ? cs->host.setPosition(entity, pos) : LB200_ERR_INVALID; }
-int lb200_culling_set_radius(lb200_culling* cs, int32_t entity, float radius) { return cs ? cs->host.setRadius(entity, radius) : LB200_ERR_INVALID; }
-int lb200_culling_set(lb200_culling* cs, int32_t entity, const double pos[3], float radius) { return cs && pos ? cs->host.set(entity, pos, radius) : LB200_ERR_INVALID; }
-float lb200_culling_get_radius(const lb200_culling* cs, int32_t entity) { return cs && cs->host.isAdded(entity) ? cs->host.getRadius(entity) : 0.0f; }
-int lb200_culling_is_added(const lb200_culling* cs, int32_t entity) { return cs && cs->host.isAdded(entity) ? 1 : 0; }
+int lb200_culling_remove(lb200_culling* cs, int32_t entity) { LB200_HOST_VIEW(cs); return cs ? cs->host.remove(entity) : LB200_ERR_INVALID; }
+int lb200_culling_set_position(lb200_culling* cs, int32_t entity, const double pos[3]) { LB200_HOST_VIEW(cs); return cs && pos ? cs->host.setPosition(entity, pos) : LB200_ERR_INVALID; }
+int lb200_culling_set_radius(lb200_culling* cs, int32_t entity, float radius) { LB200_HOST_VIEW(cs); return cs ? cs->host.setRadius(entity, radius) : LB200_ERR_INVALID; }
+int lb200_culling_set(lb200_culling* cs, int32_t entity, const double pos[3], float radius) { LB200_HOST_VIEW(cs); return cs && pos ? cs->host.set(entity, pos, radius) : LB200_ERR_INVALID; }
+float lb200_culling_get_radius(const lb200_culling* cs, int32_t entity) {
+	if (cs && cs->device_authoritative && syncHostFromDevice(const_cast<lb200_culling*>(cs))) return 0.0f;
+	return cs && cs->host.isAdded(entity) ? cs->host.getRadius(entity) : 0.0f;
+}
+int lb200_culling_is_added(const lb200_culling* cs, int32_t entity) { return cs && cs->host.isAdded(entity) ? 1 : 0; } // re-binning never adds or removes entities
 
 int lb200_culling_add_many(lb200_culling* cs, const int32_t* entities, const uint8_t* types, const double* pos3, const float* radius, uint32_t n) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || (n && (!entities || !types || !pos3 || !radius))) return LB200_ERR_INVALID;
 	for (uint32_t i = 0; i < n; ++i) {
 		if (types[i] == LB200_TYPE_ALL) return LB200_ERR_INVALID;
@@ -644,6 +682,7 @@ int lb200_culling_add_many(lb200_culling* cs, const int32_t* entities, const uin
 	return LB200_OK;
 }
 int lb200_culling_set_many(lb200_culling* cs, const int32_t* entities, const double* pos3, const float* radius, uint32_t n) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || (n && (!entities || !pos3 || !radius))) return LB200_ERR_INVALID;
 	for (uint32_t i = 0; i < n; ++i) {
 		const int rc = cs->host.set(entities[i], pos3 + 3 * (size_t)i, radius[i]);
@@ -652,11 +691,13 @@ int lb200_culling_set_many(lb200_culling* cs, const int32_t* entities, const dou
 	return LB200_OK;
 }
 int lb200_culling_set_many_unique(lb200_culling* cs, const int32_t* entities, const double* pos3, const float* radius, uint32_t n) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || (n && (!entities || !pos3 || !radius))) return LB200_ERR_INVALID;
 	return cs->host.setManyUnique(entities, pos3, radius, n);
 }
 
 int lb200_culling_set_position_many(lb200_culling* cs, const int32_t* entities, const double* pos3, uint32_t n) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || (n && (!entities || !pos3))) return LB200_ERR_INVALID;
 	for (uint32_t i = 0; i < n; ++i) {
 		const int rc = cs->host.setPosition(entities[i], pos3 + 3 * (size_t)i);
@@ -665,6 +706,7 @@ int lb200_culling_set_position_many(lb200_culling* cs, const int32_t* entities, 
 	return LB200_OK;
 }
 int lb200_culling_set_radius_many(lb200_culling* cs, const int32_t* entities, const float* radius, uint32_t n) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || (n && (!entities || !radius))) return LB200_ERR_INVALID;
 	for (uint32_t i = 0; i < n; ++i) {
 		const int rc = cs->host.setRadius(entities[i], radius[i]);
@@ -673,17 +715,22 @@ int lb200_culling_set_radius_many(lb200_culling* cs, const int32_t* entities, co
 	return LB200_OK;
 }
 int lb200_culling_remove_many(lb200_culling* cs, const int32_t* entities, uint32_t n) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || (n && !entities)) return LB200_ERR_INVALID;
 	for (uint32_t i = 0; i < n; ++i) cs->host.remove(entities[i]);
 	return LB200_OK;
 }
 
-uint32_t lb200_culling_page_count(const lb200_culling* cs) { return cs ? (uint32_t)cs->host.cells.size() : 0; }
+uint32_t lb200_culling_page_count(const lb200_culling* cs) {
+	if (cs && cs->device_authoritative && syncHostFromDevice(const_cast<lb200_culling*>(cs))) return 0;
+	return cs ? (uint32_t)cs->host.cells.size() : 0;
+}
 uint32_t lb200_culling_entity_count(const lb200_culling* cs) { return cs ? cs->host.n_entities : 0; }
 
 int lb200_culling_get_page(const lb200_culling* cs, uint32_t page, double origin[3], int32_t indices[3], uint8_t* type, uint8_t* is_big,
 	uint32_t* count, float* spheres4, int32_t* entities)
 {
+	if (cs && cs->device_authoritative) { const int rc = syncHostFromDevice(const_cast<lb200_culling*>(cs)); if (rc) return rc; }
 	if (!cs || page >= cs->host.cells.size()) return LB200_ERR_INVALID;
 	const lb::CullingHost& h = cs->host;
 	const uint32_t p = h.cells[page];
@@ -698,16 +745,19 @@ int lb200_culling_get_page(const lb200_culling* cs, uint32_t page, double origin
 }
 
 int32_t lb200_culling_page_id(const lb200_culling* cs, uint32_t page) {
+	if (cs && cs->device_authoritative && syncHostFromDevice(const_cast<lb200_culling*>(cs))) return -1;
 	return cs && page < cs->host.cells.size() ? (int32_t)cs->host.cells[page] : -1;
 }
 
 int lb200_culling_flush(lb200_culling* cs) {
+	LB200_HOST_VIEW(cs);
 	if (!cs) return LB200_ERR_INVALID;
 	if (!cs->ctx) { return LB200_ERR_NO_DEVICE; }
 	return flushPages(cs);
 }
 
 int lb200_culling_set_replicas(lb200_culling* cs, uint32_t replicas) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || replicas < 1 || replicas > 64) return LB200_ERR_INVALID;
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
 	if (replicas == cs->replicas) return LB200_OK;
@@ -871,6 +921,7 @@ int lb200_culling_cull(lb200_culling* cs, const lb200_shifted_frustum* frustum, 
 }
 
 int lb200_culling_read_bitmask(lb200_culling* cs, uint32_t* out_words, uint32_t capacity_words) {
+	LB200_HOST_VIEW(cs);
 	if (!cs || !out_words) return LB200_ERR_INVALID;
 	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
 	// bitmask is indexed by page id; report it in m_cells order like lb200_culling_get_page
@@ -1147,5 +1198,452 @@ int lb200_culling_allgather(lb200_culling* cs, uint32_t slab_ids, const uint32_t
 	if (out_dev_ids) *out_dev_ids = cs->d_gather_ids;
 	return LB200_OK;
 }
+
+} // extern "C"
+
+// =====================================================================================================================================
+// Device-side re-binning: CullingSystem::set (src/renderer/culling_system.cpp:222-240) for a batch of DISTINCT entities
+// whose new world spheres already lie in HBM (the sphere refresh behind a hierarchy propagate, render_module.cpp:1544-1554), without the
+// host hash map in the loop:
+//   1. classify   one thread per mover: new cell = IVec3(pos * (1 / 300.f)) (culling_system.cpp:25-31), is_big = radius > 300; same cell
+//                 and same big-ness -> the sphere is overwritten in its slot (:228-233); otherwise the mover joins the changer list;
+//   2. remove     changers leave their pages (:160-187): the slot is tombstoned, the page marked dirty; one warp per dirty page then
+//                 compacts the survivors (the reference swaps the last sphere into the hole: same set, slots differ), pages that run empty
+//                 go to the free list (:169-176);
+//   3. add        changers sorted by target chain (cell, type, is_big) with the device radix sort; the head of every run fills the chain's
+//                 open page (the reference's map head, :110-127) and opens new pages from the free list as it overflows (:143-156).
+// Results of a cull afterwards are the reference's: every entity sits in the chain of its cell with the sphere relative to the cell
+// origin computed exactly as culling_system.cpp:100 does, pages hold <= 200 spheres, empty pages are skipped.  Which slot / which page of
+// its chain an entity occupies differs from the sequential host order (as it does between two edit orders on the host); the per-page
+// statistics of a cull can therefore differ from a host-side replay, visible sets cannot.
+// =====================================================================================================================================
+namespace {
+
+enum { RB_HIGH_WATER = 0, RB_N_FREE, RB_N_CHANGERS, RB_N_DIRTY, RB_OVERFLOW, RB_BAD_RADIUS, RB_WORDS = 8 };
+constexpr unsigned long long HASH_EMPTY = ~0ull;
+constexpr uint32_t NO_OPEN_PAGE = 0xffffffffu;
+
+__host__ __device__ __forceinline__ unsigned long long packCellKey(int x, int y, int z, uint32_t type, uint32_t is_big) {
+	// 18 bits per axis (+-131 071 cells of 300 m), 8 bits type, 1 bit is_big
+	return ((unsigned long long)((uint32_t)x & 0x3ffffu)) | ((unsigned long long)((uint32_t)y & 0x3ffffu) << 18) | ((unsigned long long)((uint32_t)z & 0x3ffffu) << 36)
+		| ((unsigned long long)(type & 0xffu) << 54) | ((unsigned long long)(is_big & 1u) << 62);
+}
+__host__ __device__ __forceinline__ uint32_t hashCellKey(unsigned long long k) {
+	k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+	return (uint32_t)k;
+}
+
+__device__ __forceinline__ uint32_t hashFind(const unsigned long long* keys, const uint32_t* vals, uint32_t cap, unsigned long long key, uint32_t* slot_out) {
+	uint32_t i = hashCellKey(key) & (cap - 1);
+	for (;;) {
+		const unsigned long long k = keys[i];
+		if (k == key) { *slot_out = i; return vals[i]; }
+		if (k == HASH_EMPTY) { *slot_out = i; return NO_OPEN_PAGE; }
+		i = (i + 1) & (cap - 1);
+	}
+}
+
+// 1. classify + in-place overwrite
+__global__ void __launch_bounds__(256) rebin_classify_kernel(uint32_t n, const int32_t* __restrict__ ents, const double* __restrict__ pos3, const float* __restrict__ radius,
+	const uint32_t* __restrict__ entity_to_slot, uint32_t entity_cap, const lb200_page_desc* __restrict__ desc, const int4* __restrict__ page_cell,
+	float4* __restrict__ spheres, uint32_t* __restrict__ changers, uint32_t* __restrict__ counters)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool changer = false;
+	if (i < n) {
+		const int32_t e = ents ? ents[i] : (int32_t)i;
+		const uint32_t slot = (uint32_t)e < entity_cap ? entity_to_slot[e] : NO_SLOT;
+		if (slot != NO_SLOT) {
+			const uint32_t page = slot / PAGE_SLOTS;
+			const double px = pos3[3 * (size_t)i], py = pos3[3 * (size_t)i + 1], pz = pos3[3 * (size_t)i + 2];
+			const float r = radius[i];
+			const double inv = (double)(1 / LB200_CELL_SIZE); // culling_system.cpp:25-31: IVec3(pos * (1 / cell_size)), DVec3 * float
+			const int ix = (int)__dmul_rn(px, inv), iy = (int)__dmul_rn(py, inv), iz = (int)__dmul_rn(pz, inv);
+			const int4 c = page_cell[page];
+			const bool was_big = ((uint32_t)c.w >> 8) != 0, is_big = r > LB200_CELL_SIZE;
+			if (was_big == is_big && ix == c.x && iy == c.y && iz == c.z) { // :228-233
+				const lb200_page_desc d = desc[page];
+				const float old_r = spheres[slot].w;
+				spheres[slot] = make_float4((float)__dsub_rn(px, d.origin[0]), (float)__dsub_rn(py, d.origin[1]), (float)__dsub_rn(pz, d.origin[2]), r);
+				const int delta = (!(r >= 0.0f) ? 1 : 0) - (!(old_r >= 0.0f) ? 1 : 0);
+				if (delta) atomicAdd(&counters[RB_BAD_RADIUS], (uint32_t)delta);
+			}
+			else changer = true;
+		}
+	}
+	const uint32_t bal = __ballot_sync(0xffffffffu, changer);
+	if (bal) {
+		const uint32_t lane = threadIdx.x & 31u;
+		uint32_t base = 0;
+		if (lane == 0) base = atomicAdd(&counters[RB_N_CHANGERS], (uint32_t)__popc(bal));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (changer) changers[base + __popc(bal & ((1u << lane) - 1u))] = i;
+	}
+}
+
+// 2a. changers leave their slots; the sort keys of step 3 are built on the way
+__global__ void __launch_bounds__(256) rebin_remove_kernel(const uint32_t* __restrict__ changers, const int32_t* __restrict__ ents,
+	const double* __restrict__ pos3, const float* __restrict__ radius, uint32_t* __restrict__ entity_to_slot, const int4* __restrict__ page_cell, float4* __restrict__ spheres,
+	int* __restrict__ entities, uint32_t* __restrict__ page_dirty, uint32_t* __restrict__ dirty_pages, uint32_t* wcounters, uint64_t* __restrict__ keys, uint64_t* __restrict__ vals)
+{
+	const uint32_t n = wcounters[RB_N_CHANGERS];
+	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		const uint32_t i = changers[k];
+		const int32_t e = ents ? ents[i] : (int32_t)i;
+		const uint32_t slot = entity_to_slot[e];
+		const uint32_t page = slot / PAGE_SLOTS;
+		const float old_r = spheres[slot].w;
+		if (!(old_r >= 0.0f)) atomicAdd(&wcounters[RB_BAD_RADIUS], 0xffffffffu);
+		entities[slot] = -1 - e; // tombstone
+		if (atomicExch(&page_dirty[page], 1u) == 0u) dirty_pages[atomicAdd(&wcounters[RB_N_DIRTY], 1u)] = page;
+		const double inv = (double)(1 / LB200_CELL_SIZE);
+		const int ix = (int)__dmul_rn(pos3[3 * (size_t)i], inv), iy = (int)__dmul_rn(pos3[3 * (size_t)i + 1], inv), iz = (int)__dmul_rn(pos3[3 * (size_t)i + 2], inv);
+		const uint32_t type = (uint32_t)page_cell[page].w & 0xffu; // set() keeps the renderable type (:236-239)
+		keys[k] = packCellKey(ix, iy, iz, type, radius[i] > LB200_CELL_SIZE ? 1u : 0u);
+		vals[k] = ((uint64_t)(uint32_t)ix) | ((uint64_t)i << 32); // mover index; the cell indices are recomputed by the add kernel
+		if (!(radius[i] >= 0.0f)) atomicAdd(&wcounters[RB_BAD_RADIUS], 1u);
+	}
+}
+
+// 2b. one warp per dirty page: survivors move up, the count drops, empty pages are freed
+__global__ void __launch_bounds__(256) rebin_compact_kernel(const uint32_t* __restrict__ dirty_pages, uint32_t* __restrict__ counters, lb200_page_desc* __restrict__ desc,
+	const int4* __restrict__ page_cell, float4* __restrict__ spheres, int* __restrict__ entities, uint32_t* __restrict__ entity_to_slot, uint32_t* __restrict__ page_dirty,
+	uint32_t* __restrict__ free_pages, unsigned long long* __restrict__ hash_keys, uint32_t* __restrict__ hash_vals, uint32_t hash_cap)
+{
+	const uint32_t n = counters[RB_N_DIRTY];
+	const uint32_t lane = threadIdx.x & 31u;
+	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += (gridDim.x * blockDim.x) >> 5) {
+		const uint32_t page = dirty_pages[w];
+		const uint32_t count = desc[page].count;
+		const size_t base = (size_t)page * PAGE_SLOTS;
+		float4 sp[7]; int en[7]; uint32_t bal[7];
+#pragma unroll
+		for (int k = 0; k < 7; ++k) {
+			const uint32_t s = k * 32 + lane;
+			const bool in = s < count;
+			if (in) { sp[k] = spheres[base + s]; en[k] = entities[base + s]; }
+			bal[k] = __ballot_sync(0xffffffffu, in && en[k] >= 0);
+		}
+		__syncwarp();
+		uint32_t at = 0;
+#pragma unroll
+		for (int k = 0; k < 7; ++k) {
+			if ((bal[k] >> lane) & 1u) {
+				const uint32_t dst = at + __popc(bal[k] & ((1u << lane) - 1u));
+				spheres[base + dst] = sp[k];
+				entities[base + dst] = en[k];
+				entity_to_slot[en[k]] = (uint32_t)(base + dst);
+			}
+			at += __popc(bal[k]);
+		}
+		if (lane == 0) {
+			desc[page].count = at;
+			page_dirty[page] = 0;
+			if (at == 0) { // culling_system.cpp:169-176: the page leaves its chain; if it was the chain's open page the chain has none now
+				free_pages[atomicAdd(&counters[RB_N_FREE], 1u)] = page;
+				const int4 c = page_cell[page];
+				uint32_t slot;
+				const uint32_t open = hashFind(hash_keys, hash_vals, hash_cap, packCellKey(c.x, c.y, c.z, (uint32_t)c.w & 0xffu, (uint32_t)c.w >> 8), &slot);
+				if (open == page) hash_vals[slot] = NO_OPEN_PAGE;
+			}
+		}
+	}
+}
+
+// 3. adds, sorted by chain: the head of every run of equal keys places the whole run
+__global__ void __launch_bounds__(128) rebin_add_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, uint32_t* __restrict__ counters,
+	const int32_t* __restrict__ ents, const double* __restrict__ pos3, const float* __restrict__ radius, uint32_t* __restrict__ entity_to_slot,
+	lb200_page_desc* __restrict__ desc, int4* __restrict__ page_cell, float4* __restrict__ spheres, int* __restrict__ entities, uint32_t* __restrict__ free_pages,
+	unsigned long long* __restrict__ hash_keys, uint32_t* __restrict__ hash_vals, uint32_t hash_cap, uint32_t page_cap)
+{
+	const uint32_t n = counters[RB_N_CHANGERS];
+	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		const uint64_t key = keys[k];
+		if (k != 0 && keys[k - 1] == key) continue; // not the head of its run
+		// chain of this key: its open page, if any
+		uint32_t hslot = hashCellKey(key) & (hash_cap - 1);
+		uint32_t page = NO_OPEN_PAGE;
+		for (;;) { // find or claim the key's hash slot (runs have distinct keys: no two threads insert the same one)
+			const unsigned long long prev = atomicCAS(&hash_keys[hslot], HASH_EMPTY, (unsigned long long)key);
+			if (prev == HASH_EMPTY) { hash_vals[hslot] = NO_OPEN_PAGE; break; }
+			if (prev == key) { page = hash_vals[hslot]; break; }
+			hslot = (hslot + 1) & (hash_cap - 1);
+		}
+		uint32_t cnt = page != NO_OPEN_PAGE ? desc[page].count : PAGE_SLOTS;
+		double ox = 0, oy = 0, oz = 0;
+		if (page != NO_OPEN_PAGE) { ox = desc[page].origin[0]; oy = desc[page].origin[1]; oz = desc[page].origin[2]; }
+		for (uint32_t j = k; j < n && keys[j] == key; ++j) {
+			const uint32_t i = (uint32_t)(vals[j] >> 32);
+			const int32_t e = ents ? ents[i] : (int32_t)i;
+			const double px = pos3[3 * (size_t)i], py = pos3[3 * (size_t)i + 1], pz = pos3[3 * (size_t)i + 2];
+			if (cnt >= PAGE_SLOTS) { // culling_system.cpp:110-127 / :143-156: a new page in front of the chain
+				if (page != NO_OPEN_PAGE) desc[page].count = cnt;
+				uint32_t np;
+				const uint32_t nf = atomicSub(&counters[RB_N_FREE], 1u);
+				if (nf != 0u && nf < 0x80000000u) np = free_pages[nf - 1];
+				else { atomicAdd(&counters[RB_N_FREE], 1u); np = atomicAdd(&counters[RB_HIGH_WATER], 1u); }
+				if (np >= page_cap) { atomicExch(&counters[RB_OVERFLOW], 1u); page = NO_OPEN_PAGE; break; }
+				const double inv = (double)(1 / LB200_CELL_SIZE);
+				const int ix = (int)__dmul_rn(px, inv), iy = (int)__dmul_rn(py, inv), iz = (int)__dmul_rn(pz, inv);
+				const uint32_t type = (uint32_t)(key >> 54) & 0xffu, is_big = (uint32_t)(key >> 62) & 1u;
+				ox = __dmul_rn((double)LB200_CELL_SIZE, (double)ix); oy = __dmul_rn((double)LB200_CELL_SIZE, (double)iy); oz = __dmul_rn((double)LB200_CELL_SIZE, (double)iz); // :146
+				lb200_page_desc d;
+				d.origin[0] = ox; d.origin[1] = oy; d.origin[2] = oz; d.count = 0; d.type = (uint8_t)type; d.is_big = (uint8_t)is_big; d.pad = 0;
+				desc[np] = d;
+				page_cell[np] = make_int4(ix, iy, iz, (int)(type | (is_big << 8)));
+				page = np;
+				cnt = 0;
+			}
+			const uint32_t slot = page * PAGE_SLOTS + cnt;
+			spheres[slot] = make_float4((float)__dsub_rn(px, ox), (float)__dsub_rn(py, oy), (float)__dsub_rn(pz, oz), radius[i]); // :100
+			entities[slot] = e;
+			entity_to_slot[e] = slot;
+			++cnt;
+		}
+		if (page != NO_OPEN_PAGE) { desc[page].count = cnt; hash_vals[hslot] = page; }
+	}
+}
+
+int growDevicePages(lb200_culling* cs, uint32_t min_cap) {
+	lb200_ctx* ctx = cs->ctx;
+	if (min_cap <= cs->dev_cap) return LB200_OK;
+	uint32_t cap = cs->dev_cap ? cs->dev_cap : 1024;
+	while (cap < min_cap) cap *= 2;
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	float4* ns = nullptr; int* ne = nullptr; lb200_page_desc* nd = nullptr; uint32_t* nm = nullptr; int4* nc = nullptr; uint32_t* nf = nullptr; uint32_t* npd = nullptr; uint32_t* ndp = nullptr;
+	LB200_CUDA(ctx, cudaMalloc(&ns, sizeof(float4) * PAGE_SLOTS * (size_t)cap));
+	LB200_CUDA(ctx, cudaMalloc(&ne, sizeof(int) * PAGE_SLOTS * (size_t)cap));
+	LB200_CUDA(ctx, cudaMalloc(&nd, sizeof(lb200_page_desc) * (size_t)cap));
+	LB200_CUDA(ctx, cudaMalloc(&nm, sizeof(uint32_t) * 8 * (size_t)cap * cs->lanes));
+	LB200_CUDA(ctx, cudaMalloc(&nc, sizeof(int4) * (size_t)cap));
+	LB200_CUDA(ctx, cudaMalloc(&nf, sizeof(uint32_t) * (size_t)cap));
+	LB200_CUDA(ctx, cudaMalloc(&npd, sizeof(uint32_t) * (size_t)cap));
+	LB200_CUDA(ctx, cudaMalloc(&ndp, sizeof(uint32_t) * (size_t)cap));
+	LB200_CUDA(ctx, cudaMemsetAsync(nd, 0, sizeof(lb200_page_desc) * (size_t)cap, ctx->stream));
+	LB200_CUDA(ctx, cudaMemsetAsync(npd, 0, sizeof(uint32_t) * (size_t)cap, ctx->stream));
+	const size_t old = cs->dev_cap;
+	if (old) {
+		LB200_CUDA(ctx, cudaMemcpyAsync(ns, cs->d_spheres, sizeof(float4) * PAGE_SLOTS * old, cudaMemcpyDeviceToDevice, ctx->stream));
+		LB200_CUDA(ctx, cudaMemcpyAsync(ne, cs->d_entities, sizeof(int) * PAGE_SLOTS * old, cudaMemcpyDeviceToDevice, ctx->stream));
+		LB200_CUDA(ctx, cudaMemcpyAsync(nd, cs->d_desc, sizeof(lb200_page_desc) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+		if (cs->d_page_cell) LB200_CUDA(ctx, cudaMemcpyAsync(nc, cs->d_page_cell, sizeof(int4) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+		if (cs->d_free_pages) LB200_CUDA(ctx, cudaMemcpyAsync(nf, cs->d_free_pages, sizeof(uint32_t) * old, cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(cs->d_spheres); cudaFree(cs->d_entities); cudaFree(cs->d_desc); cudaFree(cs->d_mask); cudaFree(cs->d_page_cell); cudaFree(cs->d_free_pages);
+	cudaFree(cs->d_page_dirty); cudaFree(cs->d_dirty_pages);
+	cs->d_spheres = ns; cs->d_entities = ne; cs->d_desc = nd; cs->d_mask = nm; cs->d_page_cell = nc; cs->d_free_pages = nf; cs->d_page_dirty = npd; cs->d_dirty_pages = ndp;
+	cs->mask_words = 8 * (size_t)cap;
+	cs->item_cap = cap;
+	cs->dev_cap = cap;
+	cs->rebin_page_cap = cap;
+	return LB200_OK;
+}
+
+// device-side tables for the re-binning, (re)built from the host mirror whenever it was edited since
+int ensureRebinState(lb200_culling* cs, uint32_t max_entity) {
+	lb200_ctx* ctx = cs->ctx;
+	lb::CullingHost& h = cs->host;
+	if (cs->replicas != 1) { lb200_set_error(ctx, "device re-binning works on the live page arrays: set_replicas(1)"); return LB200_ERR_STATE; }
+	int rc = flushPages(cs);
+	if (rc) return rc;
+	if (!cs->d_rebin_counters) {
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_rebin_counters, sizeof(uint32_t) * RB_WORDS));
+		LB200_CUDA(ctx, cudaHostAlloc(&cs->h_rebin_counters, sizeof(uint32_t) * RB_WORDS, cudaHostAllocDefault));
+		cs->rb_sort_blocks = (uint32_t)ctx->sm_count * 2;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_rb_sort_state, lb200_radix_sort_state_bytes()));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_rb_block_hist, sizeof(uint32_t) * 256 * cs->rb_sort_blocks));
+	}
+	if (!cs->d_page_cell || cs->rebin_page_cap != cs->dev_cap) { // the per-page side arrays follow dev_cap
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(cs->d_page_cell); cudaFree(cs->d_free_pages); cudaFree(cs->d_page_dirty); cudaFree(cs->d_dirty_pages);
+		cs->d_page_cell = nullptr; cs->d_free_pages = nullptr; cs->d_page_dirty = nullptr; cs->d_dirty_pages = nullptr;
+		const uint32_t cap = cs->dev_cap;
+		cs->rebin_page_cap = cap;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_page_cell, sizeof(int4) * (size_t)cap));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_free_pages, sizeof(uint32_t) * (size_t)cap));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_page_dirty, sizeof(uint32_t) * (size_t)cap));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_dirty_pages, sizeof(uint32_t) * (size_t)cap));
+		LB200_CUDA(ctx, cudaMemsetAsync(cs->d_page_dirty, 0, sizeof(uint32_t) * (size_t)cap, ctx->stream));
+		cs->rebin_built_gen = ~0ull;
+	}
+	const uint32_t need_entities = std::max((uint32_t)h.entity_to_slot.size(), max_entity + 1);
+	if (cs->entity_cap < need_entities) {
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(cs->d_entity_to_slot);
+		cs->d_entity_to_slot = nullptr;
+		uint32_t cap = cs->entity_cap ? cs->entity_cap : 4096;
+		while (cap < need_entities) cap *= 2;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_entity_to_slot, sizeof(uint32_t) * (size_t)cap));
+		cs->entity_cap = cap;
+		cs->rebin_built_gen = ~0ull;
+	}
+	if (cs->rebin_built_gen == h.edit_gen && !cs->device_authoritative) return LB200_OK;
+	if (cs->device_authoritative) return LB200_OK; // the tables are live on the device
+	// ---- build from the host mirror ----
+	const uint32_t n_pages = h.high_water;
+	std::vector<int4> cells(n_pages);
+	for (uint32_t p = 0; p < n_pages; ++p) cells[p] = make_int4(h.keys[p].x, h.keys[p].y, h.keys[p].z, (int)(h.keys[p].type | ((uint32_t)h.keys[p].is_big << 8)));
+	uint32_t hcap = 1024;
+	while (hcap < 4 * std::max<uint32_t>(n_pages, 256)) hcap *= 2;
+	if (cs->hash_cap < hcap) {
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(cs->d_hash_keys); cudaFree(cs->d_hash_vals);
+		cs->d_hash_keys = nullptr; cs->d_hash_vals = nullptr;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_hash_keys, sizeof(unsigned long long) * (size_t)hcap));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_hash_vals, sizeof(uint32_t) * (size_t)hcap));
+		cs->hash_cap = hcap;
+	}
+	hcap = cs->hash_cap;
+	std::vector<unsigned long long> hk(hcap, HASH_EMPTY);
+	std::vector<uint32_t> hv(hcap, NO_OPEN_PAGE);
+	for (const auto& kv : h.cell_map) { // key -> head page of the chain (the page adds go to, culling_system.cpp:110-127)
+		const unsigned long long key = packCellKey(kv.first.x, kv.first.y, kv.first.z, kv.first.type, kv.first.is_big);
+		uint32_t i = hashCellKey(key) & (hcap - 1);
+		while (hk[i] != HASH_EMPTY) i = (i + 1) & (hcap - 1);
+		hk[i] = key; hv[i] = kv.second;
+	}
+	std::vector<uint32_t> e2s(cs->entity_cap, NO_SLOT);
+	std::copy(h.entity_to_slot.begin(), h.entity_to_slot.end(), e2s.begin());
+	uint32_t counters[RB_WORDS] = {};
+	counters[RB_HIGH_WATER] = n_pages;
+	counters[RB_N_FREE] = (uint32_t)h.free_pages.size();
+	counters[RB_BAD_RADIUS] = h.n_bad_radius;
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_page_cell, cells.data(), sizeof(int4) * n_pages, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_hash_keys, hk.data(), sizeof(unsigned long long) * hcap, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_hash_vals, hv.data(), sizeof(uint32_t) * hcap, cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_entity_to_slot, e2s.data(), sizeof(uint32_t) * cs->entity_cap, cudaMemcpyHostToDevice, ctx->stream));
+	if (!h.free_pages.empty()) LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_free_pages, h.free_pages.data(), sizeof(uint32_t) * h.free_pages.size(), cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->d_rebin_counters, counters, sizeof(counters), cudaMemcpyHostToDevice, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the staging vectors go out of scope
+	cs->dev_high_water = n_pages;
+	cs->rebin_built_gen = h.edit_gen;
+	return LB200_OK;
+}
+
+// pull the device state back into the host mirror (page arrays, counts, entity -> slot, chains regrouped by key with the open page as head)
+int syncHostFromDevice(lb200_culling* cs) {
+	if (!cs->device_authoritative) return LB200_OK;
+	lb200_ctx* ctx = cs->ctx;
+	lb::CullingHost& h = cs->host;
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->h_rebin_counters, cs->d_rebin_counters, sizeof(uint32_t) * RB_WORDS, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const uint32_t n_pages = cs->h_rebin_counters[RB_HIGH_WATER];
+	if (h.cap < n_pages && !h.grow(n_pages)) return LB200_ERR_CUDA;
+	std::vector<int4> cells(n_pages);
+	std::vector<unsigned long long> hk(cs->hash_cap);
+	std::vector<uint32_t> hv(cs->hash_cap);
+	LB200_CUDA(ctx, cudaMemcpyAsync(h.spheres, cs->d_spheres, sizeof(float4) * PAGE_SLOTS * (size_t)n_pages, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(h.entities, cs->d_entities, sizeof(int) * PAGE_SLOTS * (size_t)n_pages, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(h.desc, cs->d_desc, sizeof(lb200_page_desc) * (size_t)n_pages, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(cells.data(), cs->d_page_cell, sizeof(int4) * (size_t)n_pages, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(hk.data(), cs->d_hash_keys, sizeof(unsigned long long) * cs->hash_cap, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(hv.data(), cs->d_hash_vals, sizeof(uint32_t) * cs->hash_cap, cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaMemcpyAsync(h.entity_to_slot.data(), cs->d_entity_to_slot, sizeof(uint32_t) * h.entity_to_slot.size(), cudaMemcpyDeviceToHost, ctx->stream));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	h.high_water = n_pages;
+	h.cells.clear(); h.cell_map.clear(); h.free_pages.clear();
+	h.n_bad_radius = 0;
+	std::unordered_map<lb::CellKey, uint32_t, lb::CellKeyHasher> tail; // last page linked so far of each chain
+	for (uint32_t i = 0; i < cs->hash_cap; ++i) { // the open page of every chain is its head (culling_system.cpp:110-127)
+		if (hk[i] == HASH_EMPTY || hv[i] == NO_OPEN_PAGE || hv[i] >= n_pages || h.desc[hv[i]].count == 0) continue;
+		const uint32_t p = hv[i];
+		lb::CellKey k; k.x = cells[p].x; k.y = cells[p].y; k.z = cells[p].z; k.type = (uint8_t)(cells[p].w & 0xff); k.is_big = (uint8_t)((uint32_t)cells[p].w >> 8);
+		h.cell_map[k] = p;
+	}
+	for (uint32_t p = 0; p < n_pages; ++p) {
+		h.next[p] = h.prev[p] = lb::NO_PAGE;
+		if (h.desc[p].count == 0) { h.free_pages.push_back(p); continue; }
+		lb::CellKey k; k.x = cells[p].x; k.y = cells[p].y; k.z = cells[p].z; k.type = (uint8_t)(cells[p].w & 0xff); k.is_big = (uint8_t)((uint32_t)cells[p].w >> 8);
+		h.keys[p] = k;
+		h.cellsPush(p);
+		for (uint32_t s = 0; s < h.desc[p].count; ++s) if (lb::CullingHost::badRadius(h.spheres[4 * ((size_t)p * PAGE_SLOTS + s) + 3])) ++h.n_bad_radius;
+		if (h.cell_map.find(k) == h.cell_map.end()) h.cell_map[k] = p; // a chain whose open page ran empty: any of its pages heads it
+	}
+	for (uint32_t p = 0; p < n_pages; ++p) { // link the other pages of every chain behind its head
+		if (h.desc[p].count == 0) continue;
+		const uint32_t head = h.cell_map[h.keys[p]];
+		if (p == head) continue;
+		auto it = tail.find(h.keys[p]);
+		const uint32_t last = it == tail.end() ? head : it->second;
+		h.next[last] = (int32_t)p; h.prev[p] = (int32_t)last;
+		tail[h.keys[p]] = p;
+	}
+	h.clearDirty();
+	++h.edit_gen;
+	cs->device_authoritative = false;
+	cs->rebin_built_gen = ~0ull;
+	return LB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int lb200_culling_set_many_device(lb200_culling* cs, const int32_t* dev_entities, const double* dev_pos3, const float* dev_radius, uint32_t n, uint32_t max_entity) {
+	if (!cs || !dev_pos3 || !dev_radius) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_ERR_NO_DEVICE;
+	if (n == 0) return LB200_OK;
+	lb200_ctx* ctx = cs->ctx;
+	lb200_range range("culling set many");
+	int rc = ensureRebinState(cs, max_entity);
+	if (rc) return rc;
+	cudaStream_t s = ctx->stream;
+	if (cs->changers_cap < n) {
+		LB200_CUDA(ctx, cudaStreamSynchronize(s));
+		cudaFree(cs->d_changers);
+		for (int b = 0; b < 2; ++b) { cudaFree(cs->d_rb_keys[b]); cudaFree(cs->d_rb_vals[b]); cs->d_rb_keys[b] = nullptr; cs->d_rb_vals[b] = nullptr; }
+		cs->d_changers = nullptr;
+		uint32_t cap = cs->changers_cap ? cs->changers_cap : 4096;
+		while (cap < n) cap *= 2;
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_changers, sizeof(uint32_t) * (size_t)cap));
+		for (int b = 0; b < 2; ++b) {
+			LB200_CUDA(ctx, cudaMalloc(&cs->d_rb_keys[b], sizeof(uint64_t) * (size_t)cap));
+			LB200_CUDA(ctx, cudaMalloc(&cs->d_rb_vals[b], sizeof(uint64_t) * (size_t)cap));
+		}
+		cs->changers_cap = cap;
+	}
+	uint32_t* C = cs->d_rebin_counters;
+	LB200_CUDA(ctx, cudaMemsetAsync(C + RB_N_CHANGERS, 0, sizeof(uint32_t) * 2, s)); // changers, dirty pages
+	rebin_classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, dev_entities, dev_pos3, dev_radius, cs->d_entity_to_slot, cs->entity_cap, cs->d_desc, cs->d_page_cell, cs->d_spheres, cs->d_changers, C);
+	LB200_CHECK_LAUNCH(ctx);
+	// how many entities change their chain decides how many new pages the adds may need: one small read-back
+	LB200_CUDA(ctx, cudaMemcpyAsync(cs->h_rebin_counters, C, sizeof(uint32_t) * RB_WORDS, cudaMemcpyDeviceToHost, s));
+	LB200_CUDA(ctx, cudaStreamSynchronize(s));
+	const uint32_t n_changers = cs->h_rebin_counters[RB_N_CHANGERS];
+	cs->device_authoritative = true;
+	cs->uploaded_since_last_cull = true; // the page arrays changed: the next cull must not overlap these kernels
+	if (n_changers) {
+		rc = growDevicePages(cs, cs->h_rebin_counters[RB_HIGH_WATER] + n_changers); // worst case: every changer opens a page
+		if (rc) return rc;
+		const uint32_t grid = std::max(1u, std::min((uint32_t)ctx->sm_count * 4u, (n_changers + 255) / 256));
+		rebin_remove_kernel<<<grid, 256, 0, s>>>(cs->d_changers, dev_entities, dev_pos3, dev_radius, cs->d_entity_to_slot, cs->d_page_cell, cs->d_spheres, cs->d_entities,
+			cs->d_page_dirty, cs->d_dirty_pages, C, cs->d_rb_keys[0], cs->d_rb_vals[0]);
+		LB200_CHECK_LAUNCH(ctx);
+		rebin_compact_kernel<<<grid, 256, 0, s>>>(cs->d_dirty_pages, C, cs->d_desc, cs->d_page_cell, cs->d_spheres, cs->d_entities, cs->d_entity_to_slot, cs->d_page_dirty,
+			cs->d_free_pages, cs->d_hash_keys, cs->d_hash_vals, cs->hash_cap);
+		LB200_CHECK_LAUNCH(ctx);
+		rc = lb200_radix_sort_pairs(ctx, s, cs->d_rb_keys[0], cs->d_rb_keys[1], cs->d_rb_vals[0], cs->d_rb_vals[1], C + RB_N_CHANGERS, cs->changers_cap, cs->d_rb_sort_state,
+			cs->d_rb_block_hist, cs->rb_sort_blocks);
+		if (rc) return rc;
+		rebin_add_kernel<<<std::max(1u, std::min((uint32_t)ctx->sm_count * 8u, (n_changers + 127) / 128)), 128, 0, s>>>(cs->d_rb_keys[0], cs->d_rb_vals[0], C, dev_entities, dev_pos3, dev_radius,
+			cs->d_entity_to_slot, cs->d_desc, cs->d_page_cell, cs->d_spheres, cs->d_entities, cs->d_free_pages, cs->d_hash_keys, cs->d_hash_vals, cs->hash_cap, cs->dev_cap);
+		LB200_CHECK_LAUNCH(ctx);
+		LB200_CUDA(ctx, cudaMemcpyAsync(cs->h_rebin_counters, C, sizeof(uint32_t) * RB_WORDS, cudaMemcpyDeviceToHost, s));
+		LB200_CUDA(ctx, cudaStreamSynchronize(s));
+		if (cs->h_rebin_counters[RB_OVERFLOW]) { lb200_set_error(ctx, "device re-binning ran out of pages (capacity %u)", cs->dev_cap); return LB200_ERR_CAPACITY; }
+	}
+	cs->dev_high_water = cs->h_rebin_counters[RB_HIGH_WATER];
+	cs->host.n_bad_radius = cs->h_rebin_counters[RB_BAD_RADIUS]; // plane masking of the cull kernel needs radius >= 0 everywhere
+	return LB200_OK;
+}
+
+int lb200_culling_sync_host(lb200_culling* cs) {
+	if (!cs) return LB200_ERR_INVALID;
+	if (!cs->ctx) return LB200_OK;
+	return syncHostFromDevice(cs);
+}
+
+uint32_t lb200_culling_last_rebin_changers(const lb200_culling* cs) { return cs && cs->h_rebin_counters ? cs->h_rebin_counters[RB_N_CHANGERS] : 0; }
 
 } // extern "C"

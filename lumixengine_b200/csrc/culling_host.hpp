@@ -71,7 +71,10 @@ struct CullingHost {
 	AllocFn alloc_fn;
 	FreeFn free_fn;
 
+	uint64_t edit_gen = 0; // bumped by every edit: the device-side re-binning tables (culling.cu) are rebuilt when it moved
+
 	void markDirty(uint32_t page) {
+		++edit_gen;
 		if (!dirty_flag[page]) { dirty_flag[page] = 1; dirty_list.push_back(page); }
 	}
 
@@ -333,6 +336,7 @@ struct CullingHost {
 			run(0);
 			for (std::thread& t : pool) t.join();
 		}
+		++edit_gen;
 		for (unsigned w = 0; w < workers; ++w) {
 			dirty_list.insert(dirty_list.end(), dirty[w].begin(), dirty[w].end());
 			n_bad_radius = (uint32_t)((long long)n_bad_radius + bad_delta[w]);

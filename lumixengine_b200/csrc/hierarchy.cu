@@ -375,6 +375,24 @@ int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius
 	return LB200_OK;
 }
 
+int lb200_hierarchy_refresh_spheres(lb200_hierarchy* h, const float* bounding_radius, const double** dev_pos3, const float** dev_radius) {
+	if (!h || !dev_pos3 || !dev_radius) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!h->d_radius_in) {
+		if (!bounding_radius) { lb200_set_error(ctx, "refresh_spheres: the first call needs the bounding radii"); return LB200_ERR_INVALID; }
+		LB200_CUDA(ctx, cudaMalloc(&h->d_radius_in, sizeof(float) * h->n));
+		LB200_CUDA(ctx, cudaMalloc(&h->d_sphere_pos, sizeof(double) * 3 * (size_t)h->n));
+		LB200_CUDA(ctx, cudaMalloc(&h->d_sphere_radius, sizeof(float) * h->n));
+	}
+	if (bounding_radius) LB200_CUDA(ctx, cudaMemcpyAsync(h->d_radius_in, bounding_radius, sizeof(float) * h->n, cudaMemcpyHostToDevice, ctx->stream));
+	spheres_kernel<<<(h->n + HT - 1) / HT, HT, 0, ctx->stream>>>(h->G, h->d_order, h->d_radius_in, h->n, h->d_sphere_pos, h->d_sphere_radius);
+	LB200_CHECK_LAUNCH(ctx);
+	*dev_pos3 = h->d_sphere_pos;
+	*dev_radius = h->d_sphere_radius;
+	return LB200_OK;
+}
+
 int lb200_hierarchy_set_globals(lb200_hierarchy* h, const lb200_transform* globals) {
 	if (!h || !globals) return LB200_ERR_INVALID;
 	return upload(h, globals, h->G, h->n);

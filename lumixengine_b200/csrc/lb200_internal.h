@@ -60,6 +60,10 @@ struct lb200_range {
 };
 // culling.cu: where the last cull left its result (device: ids, counters; host: per-type segment bases and entity counts, 256 each)
 int lb200_culling_internal_last(lb200_culling* cs, const uint32_t** out_ids, const uint32_t** counters, const uint32_t** type_base, const uint32_t** type_counts);
+// sortkeys.cu: stable LSD radix sort of (u64 key, u64 value) pairs, count read on the device; the result ends in buffer 0
+size_t lb200_radix_sort_state_bytes();
+int lb200_radix_sort_pairs(lb200_ctx* ctx, cudaStream_t stream, uint64_t* keys0, uint64_t* keys1, uint64_t* values0, uint64_t* values1, const uint32_t* count_dev, uint32_t cap,
+	void* state, uint32_t* block_hist, uint32_t blocks);
 int lb200_comm_check(lb200_ctx* ctx); // comm.cu: LB200_ERR_NCCL (and reset) if a peer wait timed out since the last check
 uint32_t lb200_cull_lanes(); // LB200_CULL_LANES, default 3, 1..LB200_MAX_LANES (context.cu)
 

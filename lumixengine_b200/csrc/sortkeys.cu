@@ -73,11 +73,27 @@ struct Sink {
 };
 
 struct EmitArgs {
-	const lb200_transform* transforms; const uint32_t* model_of; float* lod; const uint8_t* flags; uint32_t* pose_frame;
-	const uint32_t* decal_sort_key; const uint8_t* decal_layer; const lb200_sk_model* models; const lb200_sk_mesh* meshes;
-	uint64_t* keys; uint64_t* values; uint32_t* counts; uint32_t* group_count; uint8_t* group_layer; uint64_t* rec_value; uint2* rec_group_rank;
-	uint32_t* pose_list; uint32_t* dirty_list;
+	const lb200_transform* __restrict__ transforms; const uint32_t* __restrict__ model_of; float* __restrict__ lod; const uint8_t* __restrict__ flags;
+	uint32_t* __restrict__ pose_frame; const uint32_t* __restrict__ decal_sort_key; const uint8_t* __restrict__ decal_layer;
+	const lb200_sk_model* __restrict__ models; const lb200_sk_mesh* __restrict__ meshes;
+	uint64_t* __restrict__ keys; uint64_t* __restrict__ values; uint32_t* __restrict__ counts; uint32_t* __restrict__ group_count;
+	uint8_t* __restrict__ group_layer; uint64_t* __restrict__ rec_value; uint2* __restrict__ rec_group_rank;
+	uint32_t* __restrict__ pose_list; uint32_t* __restrict__ dirty_list;
+	const uint32_t* s_bucket_map; // the view's bucket map in shared memory: every lane looks up its own layer
 };
+
+// the 64-byte model record / 16-byte mesh record through the read-only path, into registers
+__device__ __forceinline__ lb200_sk_model load_model(const lb200_sk_model* p) {
+	union { lb200_sk_model m; int4 q[4]; } u;
+	const int4* s = reinterpret_cast<const int4*>(p);
+	u.q[0] = __ldg(s); u.q[1] = __ldg(s + 1); u.q[2] = __ldg(s + 2); u.q[3] = __ldg(s + 3);
+	return u.m;
+}
+__device__ __forceinline__ lb200_sk_mesh load_mesh(const lb200_sk_mesh* p) {
+	union { lb200_sk_mesh m; int4 q; } u;
+	u.q = __ldg(reinterpret_cast<const int4*>(p));
+	return u.m;
+}
 
 __device__ __forceinline__ void push_key(const EmitParams& P, const EmitArgs& A, Sink& s, uint64_t key, uint64_t value) {
 	if (s.write && s.k < P.cap_keys) { A.keys[s.k] = key; A.values[s.k] = value; }
@@ -86,7 +102,7 @@ __device__ __forceinline__ void push_key(const EmitParams& P, const EmitArgs& A,
 
 // DECAL / CURVE_DECAL renderable (:3840-3867)
 __device__ __forceinline__ void decal_entity(const EmitParams& P, const EmitArgs& A, Sink& s, int32_t e, int type) {
-	const uint8_t bucket = (uint8_t)P.view.bucket_map[A.decal_layer[e]];
+	const uint8_t bucket = (uint8_t)A.s_bucket_map[A.decal_layer[e]];
 	if (bucket < 0xff) {
 		push_key(P, A, s, A.decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
 			sext(e) | ((uint64_t)(type == RT_DECAL ? DRAW_DECAL : DRAW_CURVE_DECAL) << SORT_VALUE_TYPE_SHIFT));
@@ -98,7 +114,7 @@ __device__ __forceinline__ void mesh_entity(const EmitParams& P, const EmitArgs&
 	const float global_lod_multiplier_rcp = LB_FDIV(1.0f, P.view.lod_multiplier); // :3798-3799
 	const float time_delta = P.view.time_delta;
 	const bool is_shadow = P.view.is_shadow != 0;
-	const lb200_sk_model& model = A.models[A.model_of[e]];
+	const lb200_sk_model model = load_model(A.models + A.model_of[e]);
 	const double px = A.transforms[e].pos[0], py = A.transforms[e].pos[1], pz = A.transforms[e].pos[2];
 	const double dx = LB_DSUB(px, P.view.lod_ref_point[0]), dy = LB_DSUB(py, P.view.lod_ref_point[1]), dz = LB_DSUB(pz, P.view.lod_ref_point[2]);
 	const float squared_length = (float)LB_DADD(LB_DADD(LB_DMUL(dx, dx), LB_DMUL(dy, dy)), LB_DMUL(dz, dz)); // squaredLength(DVec3), math.cpp:397
@@ -132,10 +148,12 @@ __device__ __forceinline__ void mesh_entity(const EmitParams& P, const EmitArgs&
 	else lods[n_lods++] = (int)lod_idx;
 	bool pose_done = A.pose_frame[e] == P.view.frame_number;
 	for (int li = 0; li < n_lods; ++li) { // create_key, :3883-3924
-		const int from = model.lod_from[lods[li]], to = model.lod_to[lods[li]];
+		const int l = lods[li]; // no dynamic indexing of the register copy
+		const int from = l == 0 ? model.lod_from[0] : l == 1 ? model.lod_from[1] : l == 2 ? model.lod_from[2] : l == 3 ? model.lod_from[3] : model.lod_from[4];
+		const int to = l == 0 ? model.lod_to[0] : l == 1 ? model.lod_to[1] : l == 2 ? model.lod_to[2] : l == 3 ? model.lod_to[3] : model.lod_to[4];
 		for (int mesh_idx = from; mesh_idx <= to; ++mesh_idx) {
-			const lb200_sk_mesh mm = A.meshes[model.mesh_base + (uint32_t)mesh_idx];
-			const uint32_t bucket = P.view.bucket_map[mm.layer];
+			const lb200_sk_mesh mm = load_mesh(A.meshes + model.mesh_base + (uint32_t)mesh_idx);
+			const uint32_t bucket = A.s_bucket_map[mm.layer];
 			if (mm.skinned) {
 				// once per instance and frame: the instance's palette has to be built (PoseProcessor::push; the compare-exchange on
 				// Pose::frame of :3890-3897 — one thread owns the instance within a view)
@@ -201,11 +219,14 @@ constexpr uint32_t SK_SMEM_GROUPS = 8192; // group counters a block keeps in sha
 // auto-instancer group per block (shared-memory atomics).  Then ONE block-wide scan and one global atomic per counter claim the block's
 // output ranges, and one global atomic per group the block touched claims its slice of the group.  Pass 2 repeats the logic and writes.
 __global__ void __launch_bounds__(SK_THREADS) emit_kernel(const __grid_constant__ EmitParams P, const uint32_t* __restrict__ visible,
-	const uint32_t* __restrict__ cull_counters, const EmitArgs A, uint32_t n_groups)
+	const uint32_t* __restrict__ cull_counters, EmitArgs A, uint32_t n_groups)
 {
 	extern __shared__ uint32_t s_grp_mem[];
 	__shared__ uint32_t s_warp[SK_THREADS / 32];
 	__shared__ uint32_t s_base[3];
+	__shared__ uint32_t s_bucket_map[256];
+	s_bucket_map[threadIdx.x] = P.view.bucket_map[threadIdx.x]; // SK_THREADS == 256
+	A.s_bucket_map = s_bucket_map;
 	uint32_t* s_grp = n_groups <= SK_SMEM_GROUPS ? s_grp_mem : nullptr;
 	if (s_grp) for (uint32_t g = threadIdx.x; g < n_groups; g += SK_THREADS) s_grp[g] = 0;
 	__syncthreads();
@@ -293,7 +314,7 @@ __global__ void __launch_bounds__(SK_THREADS) fill_kernel(const double cx, const
 		const uint32_t at = group_offset[gr.x] + gr.y;
 		const int32_t e = (int32_t)(uint32_t)v;
 		const uint32_t mesh_idx = (uint32_t)(v >> SORT_VALUE_MESH_IDX_SHIFT);
-		const lb200_sk_mesh mm = meshes[models[model_of[e]].mesh_base + mesh_idx];
+		const lb200_sk_mesh mm = meshes[__ldg(&models[model_of[e]].mesh_base) + mesh_idx];
 		const lb200_transform& tr = transforms[e];
 		const float lx = (float)LB_DSUB(tr.pos[0], cx), ly = (float)LB_DSUB(tr.pos[1], cy), lz = (float)LB_DSUB(tr.pos[2], cz); // Vec3(tr.pos - camera_pos)
 		const float lod_d = LB_FSUB(lod[e], mm.lod);
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_global_hist_kernel(const uint64
 	__shared__ uint32_t s_h[RS_PASSES][256];
 	for (int i = threadIdx.x; i < RS_PASSES * 256; i += RS_THREADS) (&s_h[0][0])[i] = 0;
 	__syncthreads();
-	const uint32_t n = min(counts[CNT_KEYS], cap);
+	const uint32_t n = min(counts[0], cap);
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint64_t k = keys[i];
 #pragma unroll
@@ -342,7 +363,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_block_hist_kernel(int pass, con
 	const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st, uint32_t* __restrict__ block_hist /* [256][gridDim] */)
 {
 	__shared__ uint32_t s_h[256];
-	const uint32_t n = min(counts[CNT_KEYS], cap);
+	const uint32_t n = min(counts[0], cap);
 	if (pass_is_trivial(st, pass, n)) return;
 	const uint64_t* keys = st->cur ? buf1 : buf0;
 	s_h[threadIdx.x] = 0;
@@ -357,7 +378,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_block_hist_kernel(int pass, con
 // exclusive scan over block_hist in (digit, block) order.  Block d of the grid owns digit d: its base is the number of keys with a
 // smaller digit (the pass's global histogram), then one warp scans the digit's per-block counts 32 at a time.
 __global__ void __launch_bounds__(32) rs_scan_kernel(int pass, const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st, uint32_t* __restrict__ block_hist, uint32_t n_blocks) {
-	const uint32_t n = min(counts[CNT_KEYS], cap);
+	const uint32_t n = min(counts[0], cap);
 	if (pass_is_trivial(st, pass, n)) return;
 	const uint32_t d = blockIdx.x, lane = threadIdx.x;
 	uint32_t base = 0;
@@ -384,7 +405,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int pass, uint64
 {
 	__shared__ uint32_t s_digit_base[256];        // where this block's next key of digit d goes
 	__shared__ uint16_t s_warp_cnt[RS_WARPS][256]; // keys of digit d in warp w of the current tile
-	const uint32_t n = min(counts[CNT_KEYS], cap);
+	const uint32_t n = min(counts[0], cap);
 	if (pass_is_trivial(st, pass, n)) return;
 	const uint32_t cur = st->cur;
 	const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
@@ -436,11 +457,36 @@ __global__ void __launch_bounds__(RS_THREADS) rs_finish_kernel(uint64_t* __restr
 	const uint64_t* __restrict__ vbuf1, const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st)
 {
 	if (!st->cur) return;
-	const uint32_t n = min(counts[CNT_KEYS], cap);
+	const uint32_t n = min(counts[0], cap);
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { kbuf0[i] = kbuf1[i]; vbuf0[i] = vbuf1[i]; }
 }
 
 } // namespace
+
+// Stable LSD radix sort of n = min(*count_dev, cap) (key, value) pairs of 64 bits, all launches on `stream`, n read on the device.  The
+// sorted pairs end in buffer 0.  state: lb200_radix_sort_state_bytes() bytes, block_hist: 256 x blocks words.  (Also used by the device
+// re-binning of the culling structure, culling.cu.)
+size_t lb200_radix_sort_state_bytes() { return sizeof(SortState); }
+
+int lb200_radix_sort_pairs(lb200_ctx* ctx, cudaStream_t s, uint64_t* keys0, uint64_t* keys1, uint64_t* values0, uint64_t* values1, const uint32_t* count_dev, uint32_t cap,
+	void* state, uint32_t* block_hist, uint32_t blocks)
+{
+	SortState* st = (SortState*)state;
+	LB200_CUDA(ctx, cudaMemsetAsync(st, 0, sizeof(SortState), s));
+	rs_global_hist_kernel<<<blocks, RS_THREADS, 0, s>>>(keys0, count_dev, cap, st);
+	LB200_CHECK_LAUNCH(ctx);
+	for (int pass = 0; pass < RS_PASSES; ++pass) {
+		rs_block_hist_kernel<<<blocks, RS_THREADS, 0, s>>>(pass, keys0, keys1, count_dev, cap, st, block_hist);
+		LB200_CHECK_LAUNCH(ctx);
+		rs_scan_kernel<<<256, 32, 0, s>>>(pass, count_dev, cap, st, block_hist, blocks);
+		LB200_CHECK_LAUNCH(ctx);
+		rs_scatter_kernel<<<blocks, RS_THREADS, 0, s>>>(pass, keys0, keys1, values0, values1, count_dev, cap, st, block_hist);
+		LB200_CHECK_LAUNCH(ctx);
+	}
+	rs_finish_kernel<<<blocks, RS_THREADS, 0, s>>>(keys0, keys1, values0, values1, count_dev, cap, st);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
 
 struct lb200_sortkeys {
 	lb200_ctx* ctx = nullptr;
@@ -590,7 +636,7 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 	const uint32_t work = type_counts[RT_MESH] + type_counts[RT_DECAL] + type_counts[RT_CURVE_DECAL]; // upper bound of visible renderables
 	const uint32_t grid = std::max(1u, std::min((uint32_t)ctx->sm_count * 4u, (work + SK_THREADS - 1) / SK_THREADS));
 	EmitArgs EA = {sk->transforms, sk->d_model_of, sk->d_lod, sk->d_flags, sk->d_pose_frame, sk->d_decal_sort_key, sk->d_decal_layer, sk->d_models, sk->d_meshes,
-		sk->d_keys[0], sk->d_values[0], sk->d_counts, sk->d_group_count, sk->d_group_layer, sk->d_rec_value, sk->d_rec_group_rank, sk->d_pose_list, sk->d_dirty_list};
+		sk->d_keys[0], sk->d_values[0], sk->d_counts, sk->d_group_count, sk->d_group_layer, sk->d_rec_value, sk->d_rec_group_rank, sk->d_pose_list, sk->d_dirty_list, nullptr};
 	emit_kernel<<<grid, SK_THREADS, n_groups <= SK_SMEM_GROUPS ? sizeof(uint32_t) * n_groups : 0, s>>>(EP, visible, cull_counters, EA, n_groups);
 	LB200_CHECK_LAUNCH(ctx);
 	GroupParams GP;
@@ -603,20 +649,8 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 	LB200_CHECK_LAUNCH(ctx);
 	if (sort) {
 		lb200_range r2("radixSort"); // pipeline.cpp:4101
-		LB200_CUDA(ctx, cudaMemsetAsync(sk->d_sort_state, 0, sizeof(SortState), s));
-		rs_global_hist_kernel<<<sk->sort_blocks, RS_THREADS, 0, s>>>(sk->d_keys[0], sk->d_counts, sk->cap_keys, sk->d_sort_state);
-		LB200_CHECK_LAUNCH(ctx);
-		for (int pass = 0; pass < RS_PASSES; ++pass) {
-			rs_block_hist_kernel<<<sk->sort_blocks, RS_THREADS, 0, s>>>(pass, sk->d_keys[0], sk->d_keys[1], sk->d_counts, sk->cap_keys, sk->d_sort_state, sk->d_block_hist);
-			LB200_CHECK_LAUNCH(ctx);
-			rs_scan_kernel<<<256, 32, 0, s>>>(pass, sk->d_counts, sk->cap_keys, sk->d_sort_state, sk->d_block_hist, sk->sort_blocks);
-			LB200_CHECK_LAUNCH(ctx);
-			rs_scatter_kernel<<<sk->sort_blocks, RS_THREADS, 0, s>>>(pass, sk->d_keys[0], sk->d_keys[1], sk->d_values[0], sk->d_values[1], sk->d_counts, sk->cap_keys,
-				sk->d_sort_state, sk->d_block_hist);
-			LB200_CHECK_LAUNCH(ctx);
-		}
-		rs_finish_kernel<<<sk->sort_blocks, RS_THREADS, 0, s>>>(sk->d_keys[0], sk->d_keys[1], sk->d_values[0], sk->d_values[1], sk->d_counts, sk->cap_keys, sk->d_sort_state);
-		LB200_CHECK_LAUNCH(ctx);
+		rc = lb200_radix_sort_pairs(ctx, s, sk->d_keys[0], sk->d_keys[1], sk->d_values[0], sk->d_values[1], sk->d_counts + CNT_KEYS, sk->cap_keys, sk->d_sort_state, sk->d_block_hist, sk->sort_blocks);
+		if (rc) return rc;
 	}
 	if (want_counts) {
 		if (!result) return LB200_ERR_INVALID;

@@ -250,6 +250,15 @@ class CullingSystem:
         self._err(self.L.lb200_culling_read_bitmask(self.h, ptr(out), C.c_uint32(len(out))))
         return out[:n * 8].reshape(n, 8)
 
+    def set_many_device(self, dev_pos3, dev_radius, n, dev_entities=None, max_entity=None):
+        """CullingSystem::set for n distinct entities whose new spheres lie in device memory (pointers as ints); the host mirror follows lazily."""
+        self._err(self.L.lb200_culling_set_many_device(self.h, vp(dev_entities) if dev_entities else None, vp(dev_pos3), vp(dev_radius), C.c_uint32(n),
+                                                        C.c_uint32(n - 1 if max_entity is None else max_entity)))
+        return int(self.L.lb200_culling_last_rebin_changers(self.h))
+
+    def sync_host(self):
+        self._err(self.L.lb200_culling_sync_host(self.h))
+
     def time_lone_cull(self, frustum, iters=20, type=TYPE_ALL, mode=0):
         """Device time (ms, per iteration) of single culls that have the device to themselves, launch pre-queued (no host latency).
         mode 1 / 2: nothing / one empty kernel of the same grid between the events (the fixed costs inside the number)."""

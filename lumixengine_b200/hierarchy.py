@@ -87,6 +87,15 @@ class Hierarchy:
         check(self.L.lb200_hierarchy_get_spheres(self.h, ptr(b), ptr(pos), ptr(rad)), self.ctx.h)
         return pos, rad
 
+    def refreshSpheres(self, bounding_radius=None):
+        """The same refresh left in HBM -> (device pointer of pos f64[n,3], device pointer of radius f32[n]); CullingSystem.set_many_device
+        takes them when node index = entity id.  bounding_radius may be omitted after the first call."""
+        import ctypes as C
+        b = None if bounding_radius is None else np.ascontiguousarray(bounding_radius, np.float32)
+        p, r = C.c_void_p(), C.c_void_p()
+        check(self.L.lb200_hierarchy_refresh_spheres(self.h, ptr(b) if b is not None else None, C.byref(p), C.byref(r)), self.ctx.h)
+        return p.value, r.value
+
     def getRelativeMatrices(self, base_pos):
         """World::getRelativeMatrix(entity, base_pos) (world.cpp:370-377) for every node: float32[n,16], column-major."""
         b = np.ascontiguousarray(base_pos, np.float64)

@@ -358,3 +358,63 @@ def test_random_views_and_edits(ctx, oracle):
             cs.remove(c); oc.remove(c)
             alive[c] = False
         cs.close()
+
+
+def _canon(res):
+    return np.sort(res.ids.astype(np.int64) * 256 + res.types())
+
+
+def test_device_rebinning_equals_host_set(ctx, oracle):
+    """SURVEY 8f N3: CullingSystem::set for a batch of movers on the device (in-cell overwrites, cell / big-ness changers through tombstones,
+    page compaction, the sorted re-insertion) against the oracle's sequential set(): same visible sets for several views, frame after frame,
+    and the host mirror pulled back from the device agrees entity by entity."""
+    rng = np.random.default_rng(21)
+    n = 150_000
+    scene = scenes.cull_scene(n, (3000.0, 300.0, 3000.0), seed=5, big_fraction=0.01, type_probs=(0.7, 0.2, 0.1))
+    cs, oc = _both(ctx, oracle, scene)
+    a = scenes.c1_frustum_args()
+    views = [lb.frustum_perspective(**dict(a, far=3000.0)), lb.frustum_perspective(**dict(a, position=(700.0, 20.0, -400.0), direction=(-0.7, -0.05, 0.7), far=2500.0)),
+             lb.frustum_ortho((0.0, 0.0, 5000.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0), 5000.0, 5000.0, 0.0, 10000.0)]
+    pos, rad = scene["pos"].copy(), scene["radius"].copy()
+    for frame in range(4):
+        if frame < 3:  # every entity moves: most stay in their cell, some cross borders, some change big-ness, a crowd teleports into one cell
+            pos = pos + rng.normal(size=pos.shape) * np.array([25.0, 3.0, 25.0])
+            rad = np.where(rng.random(n) < 0.02, (rng.random(n) * 650).astype(np.float32), rad).astype(np.float32)
+            if frame == 1:
+                crowd = rng.choice(n, 4000, replace=False)
+                pos[crowd] = np.array([1234.0, 10.0, -777.0]) + rng.random((4000, 3)) * 40.0
+            ents = np.arange(n, dtype=np.int32)
+            d_pos, d_rad = ctx.to_device(pos), ctx.to_device(rad)
+            changers = cs.set_many_device(d_pos, d_rad, n)
+            ctx.free_device(d_pos); ctx.free_device(d_rad)
+            assert changers > 100
+        else:  # a subset given by an id list, after host-side edits in between (the host mirror is pulled back, edited, pushed again)
+            gone = rng.choice(n, 500, replace=False).astype(np.int32)
+            cs.remove(gone); oc.remove(gone)
+            ents = np.setdiff1d(rng.choice(n, 30_000, replace=False), gone).astype(np.int32)
+            pos[ents] += rng.normal(size=(len(ents), 3)) * np.array([200.0, 10.0, 200.0])
+            d_ents, d_pos, d_rad = ctx.to_device(ents), ctx.to_device(pos[ents]), ctx.to_device(rad[ents])
+            cs.set_many_device(d_pos, d_rad, len(ents), dev_entities=d_ents, max_entity=n - 1)
+            for p in (d_ents, d_pos, d_rad):
+                ctx.free_device(p)
+        oc.set(ents, pos[ents], rad[ents])
+        for f in views:
+            res = cs.cull(f)
+            oi, ot, _ = oc.cull(lb.culling.frustum_bytes(f))
+            assert res.total == len(oi) and np.array_equal(_canon(res), np.sort(oi.astype(np.int64) * 256 + ot)), f"frame {frame}"
+        if frame in (1, 3):  # host mirror after the pull-back: every entity in the cell of its position, sphere relative to the page origin
+            cs.sync_host()
+            assert cs.page_count() > 0
+            seen = np.zeros(n, bool)
+            for pg in cs.pages():
+                e = pg["entities"]
+                assert pg["count"] == len(e) <= 200 and not seen[e].any()
+                seen[e] = True
+                key = (pos[e] * np.float32(1 / 300.0)).astype(np.int64)  # trunc toward zero like IVec3(DVec3)
+                assert np.all(key == np.asarray(pg["indices"])[None, :]) and np.all((rad[e] > 300.0) == bool(pg["is_big"]))
+                assert np.array_equal(pg["spheres"][:, :3], (pos[e] - np.asarray(pg["origin"])).astype(np.float32)) and np.array_equal(pg["spheres"][:, 3], rad[e])
+            alive = np.ones(n, bool)
+            if frame == 3:
+                alive[gone] = False
+            assert np.array_equal(seen, alive)
+    cs.close()
