@@ -169,6 +169,10 @@ def attach_path_baselines(paths):
     try:
         pr = run_cpu_worker(["--workload", "propagate", "--n", "1000000", "--steps", "5"], timeout=300)
         paths["propagate_1m_depth8"]["cpu_baseline"] = {"value": pr["value"], "unit": pr["unit"], "cores": pr["cores"], "kind": pr["kind"], "sample": pr["sample"]}
+        if "c3_update_and_cull" in paths:
+            c3 = run_cpu_worker(["--workload", "c3chain", "--n", "1000000", "--steps", "3"], timeout=600)
+            paths["c3_update_and_cull"]["cpu_baseline"] = {"value": c3["value"], "unit": c3["unit"], "cores": c3["cores"], "kind": c3["kind"], "sample": c3["sample"], "ms_per_step": c3["median_s"] * 1e3,
+                                                          "parts_ms": c3["parts_ms"]}
         an = run_cpu_worker(["--workload", "anim", "--n", "10000"], timeout=300)
         for key, part in (("pose_palette_100k_x64", "pose"), ("skin_100k_x5k", "skin")):
             paths[key]["cpu_baseline"] = {"value": an[part]["value"], "unit": an[part]["unit"], "cores": an["cores"], "kind": an["kind"], "sample": an[part]["sample"]}
@@ -233,6 +237,41 @@ def secondary_paths(ctx, lb, scenes, peak, steps, warmup):
                                   "note": "narrow levels fused into one block + one launch per wide level; 5 hierarchies (560 MB) rotated, so every step reads its locals from HBM"}
     for h in hs:
         h.close()
+    # --- config 3 as a chain: 1M-node propagate -> sphere refresh -> re-binning of the culling structure -> cull, all on the device ---
+    bounding = np.full(len(parents), 1.0, np.float32)  # radius = 1.0 * max(scale)
+    h = lb.Hierarchy(ctx, parents)
+    h.setLocalTransforms(locals_)
+    h.setRootTransforms(roots)
+    h.propagate()
+    pos0, rad0 = h.getSpheres(bounding)
+    c3 = lb.CullingSystem(ctx)
+    c3.add(np.arange(len(parents), dtype=np.int32), np.zeros(len(parents), np.uint8), pos0, rad0)
+    c3.flush()
+    root_ids = np.nonzero(parents < 0)[0].astype(np.uint32)
+    root_sets = [roots[root_ids].copy(), roots[root_ids].copy()]
+    root_sets[1]["pos"] += np.array([37.0, 4.0, -29.0])  # every tree drifts back and forth: ~4 % of the nodes cross a cell border per step
+    f3 = lb.frustum_perspective(**scenes.c2_frustum_args())
+    state = {"k": 0, "changers": 0}
+
+    def chain():
+        state["k"] += 1
+        h.setSubset(root_ids, root_sets[state["k"] & 1], globals_=True)  # World::setTransform for the roots: 3906 x 60 B over PCIe
+        h.propagate()
+        d_pos, d_rad = h.refreshSpheres(bounding if state["k"] == 1 else None)
+        state["changers"] = c3.set_many_device(d_pos, d_rad, len(parents))
+        c3.cull_device(f3, want_counts=False)
+    for _ in range(max(warmup, 3)):
+        chain()
+    c_steps = max(3, min(steps, 20))
+    ms = time_region(ctx, chain, c_steps) / c_steps
+    _, r3 = c3.cull_device(f3, want_counts=True)
+    out["c3_update_and_cull"] = {"value": len(parents) / ms / 1e3, "unit": "M nodes/s", "ms_per_step": ms, "nodes": len(parents), "cell_changers_per_step": int(state["changers"]),
+                                 "visible": int(r3.total),
+                                 "note": "BASELINE configs[2] as one chain on one stream: root transforms uploaded (3906 x 60 B), propagate, sphere refresh (render_module.cpp:1544-1554) left "
+                                         "in HBM, CullingSystem::set for all 1M nodes on the device (lb200_culling_set_many_device: two 32-byte counter read-backs inside), cull. "
+                                         "The 1M-entity culling structure (22 MB) is L2-resident: a latency number, not an HBM one"}
+    h.close()
+    c3.close()
     # --- pose + palette, skin ---
     sk = scenes.skeleton(64)
     clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
@@ -260,6 +299,97 @@ def secondary_paths(ctx, lb, scenes, peak, steps, warmup):
                             "note": "evaluateSkin (model.cpp:103-109), 6 GB written per step"}
     anim.close()
     return out
+
+
+C5_ENTITIES = 50_000_000
+C5_INSTANCES = 1_000_000
+
+
+def c5_mixed(ctx, lb, scenes, rank, world, dist, steps, warmup):
+    """BASELINE configs[4]: 50M-entity cull + 1M skinned instances, STRONG scaling over the ranks.  Entities shard by index range (every rank
+    owns whole cell pages of its 50M / N entities), instances by index range (pose + dual-quaternion palette of 1M / N instances, no
+    exchange).  The one collective of the path (north_star): every step all-gathers the compacted visible id lists — fused pack + NVLink peer
+    push + epoch flags (LB200_C5_EXCHANGE=nccl: pack + ncclAllGather).  One exchanged step is verified: every rank's view of the gathered
+    slabs has the digest of the ranks' own id lists."""
+    import numpy as np
+    n_ent = C5_ENTITIES // world
+    n_inst = C5_INSTANCES // world
+    scene = scenes.c2_scene(n_ent, seed=500 + rank)
+    cs = lb.CullingSystem(ctx)
+    t0 = time.time()
+    cs.add(np.arange(n_ent, dtype=np.int32), scene["types"], scene["pos"], scene["radius"])  # local ids; the global id is rank * n_ent + local
+    build_s = time.time() - t0
+    cs.flush()
+    f = lb.frustum_perspective(**scenes.c2_frustum_args())
+    sk = scenes.skeleton(64)
+    clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
+    anim = lb.AnimationSystem(ctx, sk, clips, scenes.mesh(sk, 64), max_instances=n_inst)
+    ci, tt = scenes.instance_times(n_inst, clips, seed=9 + rank)
+    anim.setInstances(ci, tt)
+    first = cs.cull(f)
+    visible = int(first.total)
+    own = lb.culling.digest_ids(first.ids, first.types())
+    slab = visible + 1024
+    mode = "single GPU: no exchange"
+    if world > 1:
+        import torch
+        t = torch.tensor([slab], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        slab = int(t.item())
+        if os.environ.get("LB200_C5_EXCHANGE", "p2p") == "p2p":
+            ctx.comm_enable_p2p(slab)  # no-op if the headline run already mapped buffers at least this large
+            mode = "visible id lists: fused pack + NVLink peer push + epoch flags (lb200_culling_cull_gather)"
+        else:
+            mode = "visible id lists: pack + ncclAllGather (lb200_culling_cull_gather without peer mapping)"
+
+    def step():
+        if world > 1:
+            cs.cull_gather(f, slab)
+        else:
+            cs.cull_device(f, want_counts=False)
+        anim.update(1.0 / 60.0, lb.PALETTE_DUAL_QUAT)
+    for _ in range(max(warmup, 3)):
+        step()
+    ctx.synchronize()
+    verified = None
+    if world > 1:
+        import torch
+        dev = cs.cull_gather(f, slab)
+        ctx.synchronize()
+        slabs, counts = cs.read_gathered(dev, slab, world)
+        seen = []
+        for r in range(world):
+            off = np.concatenate([[0], np.cumsum(counts[r])])
+            seen.append([[int(counts[r][t]), int(slabs[r][off[t]:off[t + 1]].astype(np.uint64).sum(dtype=np.uint64)),
+                          int(np.bitwise_xor.reduce(slabs[r][off[t]:off[t + 1]].astype(np.uint64))) if counts[r][t] else 0] for t in range(4)])
+        mine = torch.tensor(own, dtype=torch.int64, device="cuda")
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+        verified = all(seen[r] == everyone[r].cpu().tolist() for r in range(world))
+        flag = torch.tensor([1 if verified else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verified = bool(flag.item())
+        dist.barrier()
+    ms = time_region(ctx, lambda: [step() for _ in range(steps)], 1) / steps
+    ms_cull = time_region(ctx, lambda: [cs.cull_gather(f, slab) if world > 1 else cs.cull_device(f, want_counts=False) for _ in range(steps)], 1) / steps
+    ms_pose = time_region(ctx, lambda: [anim.update(1.0 / 60.0, lb.PALETTE_DUAL_QUAT) for _ in range(steps)], 1) / steps
+    vis_total = visible
+    if world > 1:
+        import torch
+        t = torch.tensor([ms, ms_cull, ms_pose], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_cull, ms_pose = (float(x) for x in t.tolist())
+        v = torch.tensor([visible], dtype=torch.int64, device="cuda")
+        dist.all_reduce(v)
+        vis_total = int(v.item())
+    anim.close()
+    cs.close()
+    return {"value": C5_ENTITIES / ms / 1e3, "unit": "M entities/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world,
+            "entities_total": C5_ENTITIES, "skinned_instances_total": C5_INSTANCES, "entities_per_gpu": n_ent, "instances_per_gpu": n_inst,
+            "visible_total": vis_total, "parts_ms": {"cull_and_gather": ms_cull, "pose_palette": ms_pose}, "exchange": mode, "exchange_verified": verified,
+            "gather_bytes_received_per_gpu": int(vis_total - visible) * 4, "scene_build_s": build_s,
+            "note": "a step = cull of the rank's shard + all-gather of the visible ids + pose / dual-quaternion palette of the rank's instances, on one stream; "
+                    "device time, max over ranks; value = 50M entities / step time at every N"}
 
 
 def ours(a, rank, world):
@@ -427,6 +557,18 @@ def ours(a, rank, world):
         ctx.synchronize()
     clocks = sampler.stop(t_load0, time.time())
 
+    n_pages_c2 = cs.page_count()
+    c5_result = None
+    if not a.only_cull and not a.no_c5:
+        SK.close()
+        cs.close()  # free the C2 scene's HBM and pinned host memory before the 50M scene
+        cs = None
+        del scene, sk_in
+        try:
+            c5_result = c5_mixed(ctx, lb, scenes, rank, world, dist, max(5, min(a.steps, 50)), a.warmup)
+        except Exception as e:
+            c5_result = {"error": repr(e)}
+
     if rank != 0:
         ctx.close()
         if dist:
@@ -437,8 +579,8 @@ def ours(a, rank, world):
     line = {
         "metric": "M entities culled/s", "value": total_entities / ms_step / 1e3, "unit": "M entities/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {**shared_config(visible), "pages": cs.page_count(),
-                   "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{cs.page_count() * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
+        "config": {**shared_config(visible), "pages": n_pages_c2,
+                   "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{n_pages_c2 * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
                    "parallelism": f"dp{world}: whole cell pages per rank" + (("; exchanged each step: " + exchange_desc) if world > 1 else ""),
                    "submission": "K culls = one lb200_culling_cull_device_n call: consecutive (independent) culls on 3 streams / output lanes, half-occupancy grids, programmatic dependent launch" if world == 1 else "K exchange steps = one lb200_culling_cull_exchange_n call (steps on 3 streams, 6 exchange buffers per rank)",
                    "lone_cull_ms": ms_lone, "lone_empty_interval_ms": lone["empty_interval"], "lone_empty_kernel_ms": lone["empty_kernel"],
@@ -461,9 +603,16 @@ def ours(a, rank, world):
         "build": build_info(),
         "parity": {"gpu_digest": gpu_digest, "digest": "per renderable type [count, sum of ids, xor of ids] of the visible set of one C2 cull"},
     }
+    if not a.only_cull and not a.no_c5:
+        try:
+            c5 = c5_result
+            if rank == 0 and c5 is not None:
+                line.setdefault("paths", {})["c5_mixed_50m_plus_1m_skinned"] = c5
+        except Exception as e:
+            line["c5_error"] = repr(e)
     if world == 1 and not a.only_cull:
         try:
-            line["paths"] = secondary_paths(ctx, lb, scenes, peak, a.steps, a.warmup)
+            line.setdefault("paths", {}).update(secondary_paths(ctx, lb, scenes, peak, a.steps, a.warmup))
             sk = line["paths"]["skin_100k_x5k"]
             line["secondary"] = {"metric": "M skinned verts/s", "value": sk["value"], "unit": sk["unit"], "roofline_frac": sk["roofline"]["frac"]}
             attach_path_baselines(line["paths"])
@@ -495,6 +644,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--only-cull", action="store_true", help="skip the secondary paths and the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the 50M + 1M mixed scene (BASELINE configs[4])")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     claim_stdout()

@@ -341,6 +341,9 @@ LB200_API uint32_t lb200_hierarchy_depth(const lb200_hierarchy* h);
 LB200_API int lb200_hierarchy_set_locals(lb200_hierarchy* h, const lb200_transform* locals);
 /* Root world transforms (entries of non-root nodes are ignored). */
 LB200_API int lb200_hierarchy_set_root_globals(lb200_hierarchy* h, const lb200_transform* globals);
+/* World::setLocalTransform / World::setTransform for SOME nodes (world.h:98-123): `count` node indices with their new local transforms
+ * (globals = 0) or world transforms (globals = 1; meaningful for roots).  Only count x 60 bytes cross PCIe. */
+LB200_API int lb200_hierarchy_set_subset(lb200_hierarchy* h, const uint32_t* nodes, const lb200_transform* values, uint32_t count, int globals);
 /* Run the propagation on the GPU; globals stay in HBM. */
 LB200_API int lb200_hierarchy_propagate(lb200_hierarchy* h);
 /* World::getTransforms (world.h:65): copy globals back in the caller's node order. */

@@ -316,6 +316,7 @@ struct lb200_culling {
 	uint32_t* d_rebin_counters = nullptr; uint32_t* h_rebin_counters = nullptr; // RB_* below; pinned mirror
 	uint32_t* d_changers = nullptr; uint32_t changers_cap = 0; // mover indices that change cell / chain
 	uint32_t* d_page_dirty = nullptr; uint32_t* d_dirty_pages = nullptr;
+	void* d_rb_plans = nullptr;         // one RunPlan per changer slot (used at the first index of every run)
 	uint64_t* d_rb_keys[2] = {}; uint64_t* d_rb_vals[2] = {}; void* d_rb_sort_state = nullptr; uint32_t* d_rb_block_hist = nullptr; uint32_t rb_sort_blocks = 0;
 	uint32_t dev_high_water = 0;        // pages [0, dev_high_water) may be in use on the device
 	uint32_t rebin_page_cap = 0;        // size of the per-page side arrays (follows dev_cap)
@@ -648,7 +649,7 @@ void lb200_culling_destroy(lb200_culling* cs) {
 		cudaFree(cs->d_entity_to_slot); cudaFree(cs->d_page_cell); cudaFree(cs->d_hash_keys); cudaFree(cs->d_hash_vals); cudaFree(cs->d_free_pages);
 		cudaFree(cs->d_rebin_counters); cudaFree(cs->d_changers); cudaFree(cs->d_page_dirty); cudaFree(cs->d_dirty_pages);
 		for (int b = 0; b < 2; ++b) { cudaFree(cs->d_rb_keys[b]); cudaFree(cs->d_rb_vals[b]); }
-		cudaFree(cs->d_rb_sort_state); cudaFree(cs->d_rb_block_hist);
+		cudaFree(cs->d_rb_sort_state); cudaFree(cs->d_rb_block_hist); cudaFree(cs->d_rb_plans);
 		if (cs->h_rebin_counters) cudaFreeHost(cs->h_rebin_counters);
 		if (cs->h_counters) cudaFreeHost(cs->h_counters);
 		if (cs->h_stage) cudaFreeHost(cs->h_stage);
@@ -1350,17 +1351,22 @@ __global__ void __launch_bounds__(256) rebin_compact_kernel(const uint32_t* __re
 	}
 }
 
-// 3. adds, sorted by chain: the head of every run of equal keys places the whole run
-__global__ void __launch_bounds__(128) rebin_add_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, uint32_t* __restrict__ counters,
-	const int32_t* __restrict__ ents, const double* __restrict__ pos3, const float* __restrict__ radius, uint32_t* __restrict__ entity_to_slot,
-	lb200_page_desc* __restrict__ desc, int4* __restrict__ page_cell, float4* __restrict__ spheres, int* __restrict__ entities, uint32_t* __restrict__ free_pages,
-	unsigned long long* __restrict__ hash_keys, uint32_t* __restrict__ hash_vals, uint32_t hash_cap, uint32_t page_cap)
+// 3a. adds, sorted by chain: the head of every run of equal keys plans the run — how many go into the chain's open page, how many new
+// pages the rest needs (taken from the free list / the high-water mark), the pages' descriptors and final counts, the chain's new open
+// page.  Work per run is proportional to its PAGES, not its entities: a crowd that moves into one cell is placed in parallel by 3b.
+struct RunPlan { uint32_t open_page, open_count, free_in_open, new_base; }; // stored at the run's first index
+__global__ void __launch_bounds__(128) rebin_plan_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, uint32_t* counters,
+	const double* __restrict__ pos3, lb200_page_desc* __restrict__ desc, int4* __restrict__ page_cell, const uint32_t* __restrict__ free_pages,
+	unsigned long long* __restrict__ hash_keys, uint32_t* __restrict__ hash_vals, uint32_t hash_cap, uint32_t page_cap, RunPlan* __restrict__ plans,
+	uint32_t* __restrict__ new_pages, uint32_t* __restrict__ n_new_pages)
 {
 	const uint32_t n = counters[RB_N_CHANGERS];
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
 		const uint64_t key = keys[k];
 		if (k != 0 && keys[k - 1] == key) continue; // not the head of its run
-		// chain of this key: its open page, if any
+		uint32_t lo = k, hi = n; // end of the run: first index whose key differs (the keys are sorted)
+		while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (keys[mid] == key) lo = mid; else hi = mid; }
+		const uint32_t run = hi - k;
 		uint32_t hslot = hashCellKey(key) & (hash_cap - 1);
 		uint32_t page = NO_OPEN_PAGE;
 		for (;;) { // find or claim the key's hash slot (runs have distinct keys: no two threads insert the same one)
@@ -1369,38 +1375,66 @@ __global__ void __launch_bounds__(128) rebin_add_kernel(const uint64_t* __restri
 			if (prev == key) { page = hash_vals[hslot]; break; }
 			hslot = (hslot + 1) & (hash_cap - 1);
 		}
-		uint32_t cnt = page != NO_OPEN_PAGE ? desc[page].count : PAGE_SLOTS;
-		double ox = 0, oy = 0, oz = 0;
-		if (page != NO_OPEN_PAGE) { ox = desc[page].origin[0]; oy = desc[page].origin[1]; oz = desc[page].origin[2]; }
-		for (uint32_t j = k; j < n && keys[j] == key; ++j) {
-			const uint32_t i = (uint32_t)(vals[j] >> 32);
-			const int32_t e = ents ? ents[i] : (int32_t)i;
-			const double px = pos3[3 * (size_t)i], py = pos3[3 * (size_t)i + 1], pz = pos3[3 * (size_t)i + 2];
-			if (cnt >= PAGE_SLOTS) { // culling_system.cpp:110-127 / :143-156: a new page in front of the chain
-				if (page != NO_OPEN_PAGE) desc[page].count = cnt;
+		RunPlan plan;
+		plan.open_page = page;
+		plan.open_count = page != NO_OPEN_PAGE ? desc[page].count : PAGE_SLOTS;
+		plan.free_in_open = PAGE_SLOTS - plan.open_count;
+		const uint32_t into_open = run < plan.free_in_open ? run : plan.free_in_open;
+		const uint32_t rest = run - into_open;
+		const uint32_t m = (rest + PAGE_SLOTS - 1) / PAGE_SLOTS; // culling_system.cpp:110-127 / :143-156: new pages in front of the chain
+		plan.new_base = m ? atomicAdd(n_new_pages, m) : 0u;
+		if (page != NO_OPEN_PAGE) desc[page].count = plan.open_count + into_open;
+		if (m) {
+			const uint32_t i0 = (uint32_t)(vals[k] >> 32); // any member of the run gives the cell
+			const double inv = (double)(1 / LB200_CELL_SIZE);
+			const int ix = (int)__dmul_rn(pos3[3 * (size_t)i0], inv), iy = (int)__dmul_rn(pos3[3 * (size_t)i0 + 1], inv), iz = (int)__dmul_rn(pos3[3 * (size_t)i0 + 2], inv);
+			const uint32_t type = (uint32_t)(key >> 54) & 0xffu, is_big = (uint32_t)(key >> 62) & 1u;
+			lb200_page_desc d;
+			d.origin[0] = __dmul_rn((double)LB200_CELL_SIZE, (double)ix); // :146
+			d.origin[1] = __dmul_rn((double)LB200_CELL_SIZE, (double)iy);
+			d.origin[2] = __dmul_rn((double)LB200_CELL_SIZE, (double)iz);
+			d.type = (uint8_t)type; d.is_big = (uint8_t)is_big; d.pad = 0;
+			for (uint32_t q = 0; q < m; ++q) {
 				uint32_t np;
 				const uint32_t nf = atomicSub(&counters[RB_N_FREE], 1u);
 				if (nf != 0u && nf < 0x80000000u) np = free_pages[nf - 1];
 				else { atomicAdd(&counters[RB_N_FREE], 1u); np = atomicAdd(&counters[RB_HIGH_WATER], 1u); }
-				if (np >= page_cap) { atomicExch(&counters[RB_OVERFLOW], 1u); page = NO_OPEN_PAGE; break; }
-				const double inv = (double)(1 / LB200_CELL_SIZE);
-				const int ix = (int)__dmul_rn(px, inv), iy = (int)__dmul_rn(py, inv), iz = (int)__dmul_rn(pz, inv);
-				const uint32_t type = (uint32_t)(key >> 54) & 0xffu, is_big = (uint32_t)(key >> 62) & 1u;
-				ox = __dmul_rn((double)LB200_CELL_SIZE, (double)ix); oy = __dmul_rn((double)LB200_CELL_SIZE, (double)iy); oz = __dmul_rn((double)LB200_CELL_SIZE, (double)iz); // :146
-				lb200_page_desc d;
-				d.origin[0] = ox; d.origin[1] = oy; d.origin[2] = oz; d.count = 0; d.type = (uint8_t)type; d.is_big = (uint8_t)is_big; d.pad = 0;
+				if (np >= page_cap) { atomicExch(&counters[RB_OVERFLOW], 1u); np = 0; }
+				d.count = q + 1 < m ? PAGE_SLOTS : rest - q * PAGE_SLOTS;
 				desc[np] = d;
 				page_cell[np] = make_int4(ix, iy, iz, (int)(type | (is_big << 8)));
+				new_pages[plan.new_base + q] = np;
 				page = np;
-				cnt = 0;
 			}
-			const uint32_t slot = page * PAGE_SLOTS + cnt;
-			spheres[slot] = make_float4((float)__dsub_rn(px, ox), (float)__dsub_rn(py, oy), (float)__dsub_rn(pz, oz), radius[i]); // :100
-			entities[slot] = e;
-			entity_to_slot[e] = slot;
-			++cnt;
 		}
-		if (page != NO_OPEN_PAGE) { desc[page].count = cnt; hash_vals[hslot] = page; }
+		plans[k] = plan;
+		if (page != NO_OPEN_PAGE) hash_vals[hslot] = page; // the last page opened (or the old open page) takes the chain's next adds
+	}
+}
+
+// 3b. every changer finds its run (binary search on the sorted keys), its rank in it, and from the run's plan its page and slot
+__global__ void __launch_bounds__(256) rebin_place_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, const uint32_t* __restrict__ counters,
+	const int32_t* __restrict__ ents, const double* __restrict__ pos3, const float* __restrict__ radius, uint32_t* __restrict__ entity_to_slot,
+	const lb200_page_desc* __restrict__ desc, float4* __restrict__ spheres, int* __restrict__ entities, const RunPlan* __restrict__ plans, const uint32_t* __restrict__ new_pages)
+{
+	const uint32_t n = counters[RB_N_CHANGERS];
+	for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+		const uint64_t key = keys[j];
+		uint32_t lo = 0, hi = j; // first index of the run: smallest index with this key
+		while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+		const RunPlan plan = plans[lo];
+		const uint32_t r = j - lo;
+		uint32_t page, idx;
+		if (r < plan.free_in_open) { page = plan.open_page; idx = plan.open_count + r; }
+		else { const uint32_t q = r - plan.free_in_open; page = new_pages[plan.new_base + q / PAGE_SLOTS]; idx = q % PAGE_SLOTS; }
+		const uint32_t i = (uint32_t)(vals[j] >> 32);
+		const int32_t e = ents ? ents[i] : (int32_t)i;
+		const lb200_page_desc d = desc[page];
+		const uint32_t slot = page * PAGE_SLOTS + idx;
+		spheres[slot] = make_float4((float)__dsub_rn(pos3[3 * (size_t)i], d.origin[0]), (float)__dsub_rn(pos3[3 * (size_t)i + 1], d.origin[1]),
+			(float)__dsub_rn(pos3[3 * (size_t)i + 2], d.origin[2]), radius[i]); // :100
+		entities[slot] = e;
+		entity_to_slot[e] = slot;
 	}
 }
 
@@ -1591,12 +1625,14 @@ int lb200_culling_set_many_device(lb200_culling* cs, const int32_t* dev_entities
 	cudaStream_t s = ctx->stream;
 	if (cs->changers_cap < n) {
 		LB200_CUDA(ctx, cudaStreamSynchronize(s));
-		cudaFree(cs->d_changers);
+		cudaFree(cs->d_changers); cudaFree(cs->d_rb_plans);
+		cs->d_rb_plans = nullptr;
 		for (int b = 0; b < 2; ++b) { cudaFree(cs->d_rb_keys[b]); cudaFree(cs->d_rb_vals[b]); cs->d_rb_keys[b] = nullptr; cs->d_rb_vals[b] = nullptr; }
 		cs->d_changers = nullptr;
 		uint32_t cap = cs->changers_cap ? cs->changers_cap : 4096;
 		while (cap < n) cap *= 2;
 		LB200_CUDA(ctx, cudaMalloc(&cs->d_changers, sizeof(uint32_t) * (size_t)cap));
+		LB200_CUDA(ctx, cudaMalloc(&cs->d_rb_plans, 16 * (size_t)cap));
 		for (int b = 0; b < 2; ++b) {
 			LB200_CUDA(ctx, cudaMalloc(&cs->d_rb_keys[b], sizeof(uint64_t) * (size_t)cap));
 			LB200_CUDA(ctx, cudaMalloc(&cs->d_rb_vals[b], sizeof(uint64_t) * (size_t)cap));
@@ -1626,8 +1662,12 @@ int lb200_culling_set_many_device(lb200_culling* cs, const int32_t* dev_entities
 		rc = lb200_radix_sort_pairs(ctx, s, cs->d_rb_keys[0], cs->d_rb_keys[1], cs->d_rb_vals[0], cs->d_rb_vals[1], C + RB_N_CHANGERS, cs->changers_cap, cs->d_rb_sort_state,
 			cs->d_rb_block_hist, cs->rb_sort_blocks);
 		if (rc) return rc;
-		rebin_add_kernel<<<std::max(1u, std::min((uint32_t)ctx->sm_count * 8u, (n_changers + 127) / 128)), 128, 0, s>>>(cs->d_rb_keys[0], cs->d_rb_vals[0], C, dev_entities, dev_pos3, dev_radius,
-			cs->d_entity_to_slot, cs->d_desc, cs->d_page_cell, cs->d_spheres, cs->d_entities, cs->d_free_pages, cs->d_hash_keys, cs->d_hash_vals, cs->hash_cap, cs->dev_cap);
+		LB200_CUDA(ctx, cudaMemsetAsync(C + RB_WORDS - 1, 0, sizeof(uint32_t), s)); // the new-page cursor of this batch
+		rebin_plan_kernel<<<std::max(1u, std::min((uint32_t)ctx->sm_count * 8u, (n_changers + 127) / 128)), 128, 0, s>>>(cs->d_rb_keys[0], cs->d_rb_vals[0], C, dev_pos3, cs->d_desc,
+			cs->d_page_cell, cs->d_free_pages, cs->d_hash_keys, cs->d_hash_vals, cs->hash_cap, cs->dev_cap, (RunPlan*)cs->d_rb_plans, (uint32_t*)cs->d_rb_vals[1], C + RB_WORDS - 1);
+		LB200_CHECK_LAUNCH(ctx);
+		rebin_place_kernel<<<grid, 256, 0, s>>>(cs->d_rb_keys[0], cs->d_rb_vals[0], C, dev_entities, dev_pos3, dev_radius, cs->d_entity_to_slot, cs->d_desc, cs->d_spheres,
+			cs->d_entities, (const RunPlan*)cs->d_rb_plans, (const uint32_t*)cs->d_rb_vals[1]);
 		LB200_CHECK_LAUNCH(ctx);
 		LB200_CUDA(ctx, cudaMemcpyAsync(cs->h_rebin_counters, C, sizeof(uint32_t) * RB_WORDS, cudaMemcpyDeviceToHost, s));
 		LB200_CUDA(ctx, cudaStreamSynchronize(s));

@@ -38,6 +38,19 @@ __global__ void __launch_bounds__(HT) aos_to_soa_kernel(const lb200_transform* _
 	out.sx[i] = t.scale[0]; out.sy[i] = t.scale[1]; out.sz[i] = t.scale[2];
 }
 
+// a few transforms (World::setTransform / setLocalTransform for some entities): node ids + values -> their level positions
+__global__ void __launch_bounds__(HT) scatter_transforms_kernel(const uint32_t* __restrict__ nodes, const lb200_transform* __restrict__ values, uint32_t count,
+	const uint32_t* __restrict__ pos_of_node, SoaTransforms out)
+{
+	const uint32_t k = blockIdx.x * HT + threadIdx.x;
+	if (k >= count) return;
+	const uint32_t i = pos_of_node[nodes[k]];
+	const lb200_transform t = values[k];
+	out.px[i] = t.pos[0]; out.py[i] = t.pos[1]; out.pz[i] = t.pos[2];
+	out.rot[i] = make_float4(t.rot[0], t.rot[1], t.rot[2], t.rot[3]);
+	out.sx[i] = t.scale[0]; out.sy[i] = t.scale[1]; out.sz[i] = t.scale[2];
+}
+
 __global__ void __launch_bounds__(HT) soa_to_aos_kernel(SoaTransforms in, const uint32_t* __restrict__ order, uint32_t n, lb200_transform* __restrict__ out) {
 	const uint32_t i = blockIdx.x * HT + threadIdx.x;
 	if (i >= n) return;
@@ -185,6 +198,8 @@ struct lb200_hierarchy {
 	uint32_t n = 0;
 	std::vector<uint32_t> level_start; // size depth + 1
 	uint32_t* d_order = nullptr;       // level position -> caller node index
+	uint32_t* d_pos_of_node = nullptr; // caller node index -> level position
+	uint8_t* d_subset = nullptr; uint8_t* h_subset = nullptr; size_t subset_cap = 0; // staging of set_subset: [node ids][transforms], pinned + device
 	int* d_parent = nullptr;           // level position -> parent's level position
 	SoaTransforms L, G;
 	lb200_transform* d_stage = nullptr; // n Transforms (API boundary)
@@ -278,6 +293,10 @@ int lb200_hierarchy_create(lb200_ctx* ctx, const int32_t* parents, uint32_t n, l
 	if (!rc) rc = allocSoa(ctx, h->G, n);
 	if (rc) { lb200_hierarchy_destroy(h); return rc; }
 	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_order, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	std::vector<uint32_t> pos_of_node(n);
+	for (uint32_t i = 0; i < n; ++i) pos_of_node[order[i]] = i;
+	LB200_CUDA(ctx, cudaMalloc(&h->d_pos_of_node, sizeof(uint32_t) * n));
+	LB200_CUDA(ctx, cudaMemcpy(h->d_pos_of_node, pos_of_node.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
 	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_parent, parent_pos.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	*out = h;
@@ -288,6 +307,7 @@ void lb200_hierarchy_destroy(lb200_hierarchy* h) {
 	if (!h) return;
 	cudaSetDevice(h->ctx->device);
 	cudaStreamSynchronize(h->ctx->stream);
+	cudaFree(h->d_pos_of_node); cudaFree(h->d_subset); if (h->h_subset) cudaFreeHost(h->h_subset);
 	cudaFree(h->d_order); cudaFree(h->d_parent); cudaFree(h->d_stage); cudaFree(h->d_matrices); cudaFree(h->d_radius_in); cudaFree(h->d_sphere_pos); cudaFree(h->d_sphere_radius);
 	freeSoa(h->L); freeSoa(h->G);
 	delete h;
@@ -372,6 +392,32 @@ int lb200_hierarchy_get_spheres(lb200_hierarchy* h, const float* bounding_radius
 	LB200_CUDA(ctx, cudaMemcpyAsync(out_pos3, h->d_sphere_pos, sizeof(double) * 3 * (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaMemcpyAsync(out_radius, h->d_sphere_radius, sizeof(float) * h->n, cudaMemcpyDeviceToHost, ctx->stream));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LB200_OK;
+}
+
+int lb200_hierarchy_set_subset(lb200_hierarchy* h, const uint32_t* nodes, const lb200_transform* values, uint32_t count, int globals) {
+	if (!h || (count && (!nodes || !values))) return LB200_ERR_INVALID;
+	if (!count) return LB200_OK;
+	lb200_ctx* ctx = h->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t bytes = (sizeof(uint32_t) + sizeof(lb200_transform)) * (size_t)count + 16;
+	if (h->subset_cap < bytes) {
+		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(h->d_subset); if (h->h_subset) cudaFreeHost(h->h_subset);
+		h->d_subset = nullptr; h->h_subset = nullptr;
+		size_t cap = h->subset_cap ? h->subset_cap : 4096;
+		while (cap < bytes) cap *= 2;
+		LB200_CUDA(ctx, cudaMalloc(&h->d_subset, cap));
+		LB200_CUDA(ctx, cudaHostAlloc(&h->h_subset, cap, cudaHostAllocDefault));
+		h->subset_cap = cap;
+	}
+	else LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the previous upload may still read the pinned staging
+	const size_t tr_off = (sizeof(uint32_t) * (size_t)count + 15) & ~(size_t)15;
+	memcpy(h->h_subset, nodes, sizeof(uint32_t) * (size_t)count);
+	memcpy(h->h_subset + tr_off, values, sizeof(lb200_transform) * (size_t)count);
+	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_subset, h->h_subset, tr_off + sizeof(lb200_transform) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+	scatter_transforms_kernel<<<(count + HT - 1) / HT, HT, 0, ctx->stream>>>((const uint32_t*)h->d_subset, (const lb200_transform*)(h->d_subset + tr_off), count, h->d_pos_of_node, globals ? h->G : h->L);
+	LB200_CHECK_LAUNCH(ctx);
 	return LB200_OK;
 }
 

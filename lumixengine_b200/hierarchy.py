@@ -87,6 +87,14 @@ class Hierarchy:
         check(self.L.lb200_hierarchy_get_spheres(self.h, ptr(b), ptr(pos), ptr(rad)), self.ctx.h)
         return pos, rad
 
+    def setSubset(self, nodes, transforms, globals_=False):
+        """World::setLocalTransform (or setTransform with globals_=True, for roots) for some nodes: only those transforms are uploaded."""
+        import ctypes as C
+        nd = np.ascontiguousarray(nodes, np.uint32)
+        tr = np.ascontiguousarray(transforms, TRANSFORM_DTYPE)
+        assert len(nd) == len(tr)
+        check(self.L.lb200_hierarchy_set_subset(self.h, ptr(nd), ptr(tr), C.c_uint32(len(nd)), C.c_int(1 if globals_ else 0)), self.ctx.h)
+
     def refreshSpheres(self, bounding_radius=None):
         """The same refresh left in HBM -> (device pointer of pos f64[n,3], device pointer of radius f32[n]); CullingSystem.set_many_device
         takes them when node index = entity id.  bounding_radius may be omitted after the first call."""

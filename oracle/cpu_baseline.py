@@ -95,6 +95,49 @@ def bench_propagate(n, steps):
                 sample=f"{steps} x serial DFS over {len(parents)} nodes (depth 8), includes the 56 MB globals copy")
 
 
+def bench_c3chain(n, steps):
+    """BASELINE configs[2] on the host: serial DFS propagate (port; the reference is serial), RenderModule::onModelInstanceMoved's sphere refresh,
+    the reference's own CullingSystemImpl::set for every node and its cull (oracle/_ref when present, else the C restatement)."""
+    from lumixengine_b200 import scenes
+    from oracle import pyoracle as po
+    po.build()
+    parents, locals_, roots = scenes.hierarchy_forest(n, 8, 7, seed=3)
+    lb_ = np.ascontiguousarray(locals_).view(np.uint8).reshape(len(parents), 56)
+    root_sets = [roots, roots.copy()]
+    root_sets[1]["pos"] += np.array([37.0, 4.0, -29.0])
+    fa = scenes.c2_frustum_args()
+    f = po.frustum_perspective(fa["position"], fa["direction"], fa["up"], fa["fov"], fa["ratio"], fa["near"], fa["far"])
+    use_ref = po.ref_available()
+    cs = po.RefCulling(workers=1) if use_ref else po.OracleCulling()
+    ents = np.arange(len(parents), dtype=np.int32)
+
+    def globals_of(k):
+        gb = np.ascontiguousarray(root_sets[k & 1]).view(np.uint8).reshape(len(parents), 56)
+        return po.propagate(parents, lb_, gb)
+    g = globals_of(0).view(scenes.TRANSFORM_DTYPE).reshape(-1)
+    cs.add(ents, np.zeros(len(parents), np.uint8), np.ascontiguousarray(g["pos"]), np.max(g["scale"], axis=1).astype(np.float32))
+    times, parts = [], []
+    for k in range(1, steps + 1):
+        t0 = time.perf_counter()
+        g = globals_of(k).view(scenes.TRANSFORM_DTYPE).reshape(-1)
+        t1 = time.perf_counter()
+        pos, rad = np.ascontiguousarray(g["pos"]), np.max(g["scale"], axis=1).astype(np.float32)
+        t2 = time.perf_counter()
+        cs.set(ents, pos, rad)
+        t3 = time.perf_counter()
+        if use_ref:
+            cs.cull(f, cap=0, iters=1)
+        else:
+            cs.cull(f, want_ids=False)
+        t4 = time.perf_counter()
+        times.append(t4 - t0)
+        parts.append([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3])
+    m = float(np.median(times))
+    return dict(kind="reference" if use_ref else "port", cores=1, n=len(parents), median_s=m, value=len(parents) / m / 1e6, unit="M nodes/s",
+                parts_ms=dict(zip(("propagate", "sphere_refresh", "culling_set", "cull"), [float(x) for x in np.median(np.array(parts), axis=0)])),
+                sample=f"{steps} x (serial DFS over {len(parents)} nodes + sphere refresh + CullingSystem::set x {len(parents)} + cull), one host core")
+
+
 def bench_anim(n_inst, n_verts, skin_instances):
     from lumixengine_b200 import scenes
     from oracle import pyoracle as po
@@ -128,6 +171,8 @@ def main():
         res = bench_cull(a.n, a.steps, a.warmup, a.workers, a.scene)
     elif a.workload == "propagate":
         res = bench_propagate(a.n, a.steps)
+    elif a.workload == "c3chain":
+        res = bench_c3chain(a.n, a.steps)
     elif a.workload == "anim":
         res = bench_anim(a.n, 5000, 200)
     else:
