@@ -195,9 +195,21 @@ def reference_arm(a, rank):
         "cpu_baseline": {"value": r["value"], "unit": "M entities/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "impl": r["impl"],
                          "by_workers": [{"workers": x["cores"], "value": x["value"], "median_ms": x["median_s"] * 1e3} for x in runs],
                          "note": "value = the faster of W = min(cores, 64) and W = 1"},
-        "e2e": {"value": r["value"], "unit": "M entities/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": r["value"], "unit": "M entities/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_step": ms,
+                "stages": "CullingSystemImpl::cull only (the sort-key stage could not be timed: see e2e.error)"},
         "gpu_launches": 0,
     }
+    # the same end-to-end step as the GPU arm's e2e: cull -> createSortKeys -> radixSort (pipeline.cpp:3789-4144), on the host
+    try:
+        sk = run_cpu_worker(["--workload", "sortkeys", "--n", str(N_ENTITIES), "--steps", "3"], timeout=600)
+        total_ms = ms + sk["median_s"] * 1e3
+        line["e2e"] = {"value": N_ENTITIES / total_ms / 1e3, "unit": "M entities/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_step": total_ms,
+                       "stages": "CullingSystemImpl::cull (reference build, the faster worker count) + PipelineImpl::createSortKeys over its visible list (C restatement, one worker: "
+                                 "pipeline.cpp does not compile here) + PipelineImpl::radixSort (" + sk["radix_sort"] + ")",
+                       "parts_ms": {"cull": ms, "create_sort_keys": sk["create_keys_median_s"] * 1e3, "radix_sort": sk["sort_median_s"] * 1e3},
+                       "sort_keys": {"n_keys": sk["n_keys"], "n_instances": sk["n_instances"], "sample": sk["sample"]}}
+    except Exception as e:
+        line["e2e"]["error"] = repr(e)
     emit(line)
 
 

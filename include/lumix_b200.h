@@ -261,7 +261,7 @@ typedef struct lb200_sk_outputs { /* device pointers, valid until the next creat
 	const void* instance_data;         /* 48 B per instance: rot (16), camera-relative pos (12), lod - mesh.lod (4), scale (12), material index (4) */
 	const uint32_t* pose_list;         /* n_pose skinned instances whose palette is due this frame */
 	const uint32_t* dirty_list;        /* n_dirty instances with ModelInstance::dirty set (material override refresh) */
-	const float* lod;                  /* ModelInstance::lod per entity, updated by the pass */
+	const float* lod;                  /* ModelInstance::lod per entity, updated by the pass (unpacked from the entity records by device_outputs) */
 	const uint32_t* pose_frame;        /* Pose::frame per entity */
 } lb200_sk_outputs;
 #define LB200_SK_MOVED 1u /* ModelInstance::MOVED */
@@ -272,9 +272,10 @@ LB200_API int lb200_sortkeys_set_models(lb200_sortkeys* sk, const lb200_sk_model
 /* Per-entity state, arrays indexed by entity id; a null pointer leaves that array as it is. */
 LB200_API int lb200_sortkeys_set_instances(lb200_sortkeys* sk, uint32_t n, const uint32_t* model_of, const float* lod, const uint8_t* flags, const uint32_t* pose_frame,
                                            const uint32_t* decal_sort_key, const uint8_t* decal_layer);
-/* World::getTransforms() (world.h:65), indexed by entity id: uploaded from the host, or a device array the caller keeps alive. */
+/* World::getTransforms() (world.h:65), indexed by entity id: from the host, or from a device array (e.g. the hierarchy's globals).  Both
+ * pack the transforms into the library's per-entity records when called (on the context stream): call again after the transforms changed. */
 LB200_API int lb200_sortkeys_set_transforms(lb200_sortkeys* sk, const lb200_transform* transforms, uint32_t n);
-LB200_API int lb200_sortkeys_set_transforms_device(lb200_sortkeys* sk, const lb200_transform* dev_transforms);
+LB200_API int lb200_sortkeys_set_transforms_device(lb200_sortkeys* sk, const lb200_transform* dev_transforms, uint32_t n);
 /* createSortKeys (+ radixSort if `sort`) for the last cull of `cs` on the context stream.  Asynchronous unless `want_counts`. */
 LB200_API int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb200_sk_view* view, int sort, int want_counts, lb200_sk_result* result);
 LB200_API int lb200_sortkeys_device_outputs(lb200_sortkeys* sk, lb200_sk_outputs* out);

@@ -418,10 +418,22 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_palette_kernel(const __grid
 constexpr int SKIN_THREADS = 256;
 // SKIN_GROUP = instances per block (template parameter): vertex data stays in registers across them
 
-template <int SKIN_GROUP>
+// Packed fp32 pairs (Blackwell FFMA2: two IEEE fp32 FMAs per issue slot).  The reference rounds every product and every sum on its own
+// (no FMA), so a pair-wise product is issued as fma(a, b, -0) and a pair-wise sum as fma(a, 1, b): each rounds exactly once,
+// to the same bits as mul.rn / add.rn (x*y + (-0) keeps the sign of a zero product; a*1 is exact).  The constants -0 and 1 reach the
+// kernel as ARGUMENTS: with literal constants ptxas 12.9 folds fma(a, 1, fma(b, c, -0)) into fma(b, c, a) — one rounding, other bits.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+	unsigned long long r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+	return r;
+}
+
+template <int SKIN_GROUP, bool PACKED>
 __global__ void __launch_bounds__(SKIN_THREADS) skin_kernel(const float* __restrict__ palette_mtx, const float* __restrict__ positions3,
 	const float4* __restrict__ weights4, const short* __restrict__ indices4, uint32_t n_vertices, uint32_t bone_count, uint32_t n_instances,
-	float* __restrict__ out)
+	float* __restrict__ out, const float one_arg, const float neg_zero_arg)
 {
 	extern __shared__ float4 s_rows[]; // [group][bone][3] rows of the 3x4 upper part
 	const uint32_t v = blockIdx.x * SKIN_THREADS + threadIdx.x;
@@ -443,6 +455,31 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_kernel(const float* __restr
 	const float px = positions3[3 * (size_t)v], py = positions3[3 * (size_t)v + 1], pz = positions3[3 * (size_t)v + 2];
 	const float4 w = weights4[v];
 	const short4 idx = reinterpret_cast<const short4*>(indices4)[v];
+
+	if constexpr (PACKED) {
+		const unsigned long long one = f2_pack(one_arg, one_arg), nz = f2_pack(neg_zero_arg, neg_zero_arg);
+		const unsigned long long wx = f2_pack(w.x, w.x), wy = f2_pack(w.y, w.y), wz = f2_pack(w.z, w.z), ww = f2_pack(w.w, w.w);
+		const unsigned long long pxy = f2_pack(px, py);
+		for (uint32_t g = 0; g < n_inst; ++g) {
+			const ulonglong2* rows = reinterpret_cast<const ulonglong2*>(s_rows + (size_t)g * bone_count * 3);
+			float o[3];
+#pragma unroll
+			for (int r = 0; r < 3; ++r) {
+				const ulonglong2 a = rows[idx.x * 3 + r], b = rows[idx.y * 3 + r], c = rows[idx.z * 3 + r], d = rows[idx.w * 3 + r]; // .x = elements (0, 1), .y = (2, 3)
+				// model.cpp:105-106: m = m0*w.x + m1*w.y + m2*w.z + m3*w.w, elementwise, left to right (math.cpp:1022-1071), two elements per instruction
+				const unsigned long long m01 = f2_fma(f2_fma(f2_fma(f2_fma(a.x, wx, nz), one, f2_fma(b.x, wy, nz)), one, f2_fma(c.x, wz, nz)), one, f2_fma(d.x, ww, nz));
+				const unsigned long long m23 = f2_fma(f2_fma(f2_fma(f2_fma(a.y, wx, nz), one, f2_fma(b.y, wy, nz)), one, f2_fma(c.y, wz, nz)), one, f2_fma(d.y, ww, nz));
+				// math.cpp:1231-1235 transformPoint: ((m0*x + m1*y) + m2*z) + m3
+				float t0, t1, m2, m3;
+				f2_unpack(f2_fma(m01, pxy, nz), t0, t1);
+				f2_unpack(m23, m2, m3);
+				o[r] = LB_FADD(LB_FADD(LB_FADD(t0, t1), LB_FMUL(m2, pz)), m3);
+			}
+			float* dst = out + ((size_t)(inst0 + g) * n_vertices + v) * 3;
+			dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+		}
+		return;
+	}
 
 	for (uint32_t g = 0; g < n_inst; ++g) {
 		const float4* rows = s_rows + (size_t)g * bone_count * 3;
@@ -744,9 +781,12 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 	}
-	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 196 * 3 * sizeof(float4))));
-	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 196 * 3 * sizeof(float4))));
-	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 196 * 3 * sizeof(float4))));
+	LB200_CUDA(ctx, cudaFuncSetAttribute(skin_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * 196 * 3 * sizeof(float4))));
 	guard.a = nullptr;
 	*out = a;
 	return LB200_OK;
@@ -830,9 +870,13 @@ int lb200_animation_skin(lb200_animation* a) {
 	const dim3 grid((a->n_vertices + SKIN_THREADS - 1) / SKIN_THREADS, (a->n_instances + group - 1) / group);
 	if (grid.y > 65535) { lb200_set_error(ctx, "too many instances for one skin launch"); return LB200_ERR_INVALID; }
 	const size_t smem = sizeof(float4) * 3 * a->bone_count * group;
-	if (group == 4) skin_kernel<4><<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
-	else if (group == 16) skin_kernel<16><<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
-	else skin_kernel<8><<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned);
+	// LB200_SKIN_SCALAR=1: one fp32 operation per instruction (the round-1 kernel) instead of packed pairs; the results are the same bits
+	static const bool scalar = [] { const char* e = getenv("LB200_SKIN_SCALAR"); return e && atoi(e) != 0; }();
+	volatile float one = 1.0f, neg_zero = -0.0f; // run-time arguments of the packed kernel (see f2_fma)
+#define LB200_SKIN_LAUNCH(G, P) skin_kernel<G, P><<<grid, SKIN_THREADS, smem, ctx->stream>>>(a->d_mtx, a->d_mesh_pos, a->d_mesh_w, a->d_mesh_idx, a->n_vertices, a->bone_count, a->n_instances, a->d_skinned, one, neg_zero)
+	if (scalar) { if (group == 4) LB200_SKIN_LAUNCH(4, false); else if (group == 16) LB200_SKIN_LAUNCH(16, false); else LB200_SKIN_LAUNCH(8, false); }
+	else { if (group == 4) LB200_SKIN_LAUNCH(4, true); else if (group == 16) LB200_SKIN_LAUNCH(16, true); else LB200_SKIN_LAUNCH(8, true); }
+#undef LB200_SKIN_LAUNCH
 	LB200_CHECK_LAUNCH(ctx);
 	return LB200_OK;
 }

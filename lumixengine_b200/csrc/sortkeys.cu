@@ -2,21 +2,28 @@
 // LOD selection with its smoothing state, sort keys / sort values (:53-143), auto-instancing groups + their instance data (:452-523,
 // :3958-4016) — and PipelineImpl::radixSort (:4020-4144).  The ids the cull kernel compacted never leave HBM: this stage reads them
 // where they lie (lb200_culling's per-type segments + counters) and leaves sorted keys / values and per-group instance data in HBM; the
-// host reads back four counters.
+// host reads back a handful of counters.
 //
-//   emit_kernel        one thread per visible renderable (grid-stride over the MESH, DECAL and CURVE_DECAL segments):
-//                      MESH  — squared distance to the LOD reference point in fp64 -> float, Model::getLODMeshIndices (model.h:173-179),
-//                              the lod smoothing of :3926-3941 (ModelInstance::lod is updated in place), then per mesh of the LOD range(s)
-//                              one of: skinned -> key/value + the instance joins the pose list once per frame (the compare-exchange on
-//                              Pose::frame, :3890-3897); moved -> key/value; bucket < 0xff -> a record for the auto-instancer (its rank
-//                              inside the group comes from an atomic on the group's counter); depth-sorted -> depth key/value;
-//                      DECAL / CURVE_DECAL — key/value from the material's sort key and layer.
-//   groups_kernel      exclusive scan of the group counters (one block), one key/value per non-empty group (:3958-3969).
-//   fill_kernel        one thread per record: 48 bytes of instance data (rot, camera-relative position, lod - mesh.lod, scale, material
-//                      index) at group_offset + rank (:3990-4008).
-//   radix sort         LSD, 8 passes of 8 bits over the 64-bit keys, stable, hand-written: one global histogram kernel decides which
-//                      passes move anything (the reference skips passes whose keys share one bin too, :4120), then per pass
-//                      block histograms -> scan -> stable scatter (warp match + per-warp counts).  No library sort.
+// Data layout: the walk over the visible list is a random gather by entity id, so everything createSortKeys reads per renderable lives in
+// ONE 64-byte record per entity (one DRAM burst): sector 0 = position (fp64) + model index / flags + ModelInstance::lod — all a static
+// mesh needs for its LOD and its keys; sector 1 = rotation, scale, Pose::frame — what the instance data adds.  (Round-2 profile of the
+// SoA form: 1.33 GB of DRAM reads per 1.5 M visible meshes, six 32-byte sectors per renderable and pass; profiles/r2_B_sortkeys_ncu.txt.)
+//
+//   create_keys_kernel one cooperative launch (grid = what is co-resident), one thread per visible renderable, grid-stride:
+//     pass 1  MESH: sector 0 -> squared distance to the LOD reference point in fp64 -> float, Model::getLODMeshIndices (model.h:173-179),
+//             the lod smoothing of :3926-3941 (ModelInstance::lod updated in place), the pose claim (the compare-exchange on Pose::frame,
+//             :3890-3897); what the renderable will emit is COUNTED (keys, pose entries per thread; instances per auto-instancer group
+//             per block in shared memory) and its decision is stashed as one word.  One block-wide scan + one global atomic per counter
+//             and block, one global atomic per (block, group) claim the block's output ranges.
+//     -- grid barrier --
+//             exclusive scan of the group totals (every block for itself, <= 8192 groups; one block + a second barrier beyond that);
+//             block 0 also writes group_offset and one key/value per non-empty group (:3958-3969).
+//     pass 2  the stashed decisions are replayed: keys / values (:53-143) at the claimed slots, pose / dirty lists, and for every
+//             auto-instanced mesh the 48 bytes of instance data (:3990-4008) straight at group_offset + the block's slice + rank.
+//   radix_sort_kernel  LSD, 8 bits per pass over the 64-bit keys, stable, hand-written, ONE cooperative launch for all passes: passes in
+//             which every key has the same digit are skipped (OR / AND of all keys; the reference skips the all-in-bin-0 case, :4120);
+//             per pass block histograms -> grid barrier -> every block sums the histograms of the blocks before it -> stable scatter
+//             (warp match + per-warp digit counters) -> grid barrier.  No library sort.
 // The reference runs createSortKeys on every job worker with one AutoInstancer per worker; this is the one-instancer form (instancer
 // index 0 in the group values), every mesh's instances in one group.  Order inside a group and among equal keys is unspecified in the
 // reference too (it depends on the workers' race for result pages).
@@ -40,6 +47,42 @@ enum { DRAW_MESH = 0, DRAW_AUTOINSTANCED = 1, DRAW_SKINNED = 2, DRAW_DECAL = 3, 
 enum { RT_MESH = 0, RT_DECAL = 1, RT_LOCAL_LIGHT = 2, RT_CURVE_DECAL = 3 };                                // render_module.h:293-301
 enum { CNT_KEYS = 0, CNT_RECS, CNT_INST, CNT_POSE, CNT_DIRTY, CNT_WORDS = 8 };
 
+// One entity = one 64-byte DRAM burst.  Sector 0 is all a static mesh needs for LOD selection and keys, sector 1 is what instance data adds.
+struct alignas(64) SkEntity {
+	double pos[3];        // Transform::pos
+	uint32_t model_flags; // model index (24 bits) | LB200_SK_* flags << 24
+	float lod;            // ModelInstance::lod (smoothing state, updated by the pass)
+	float rot[4];         // Transform::rot
+	float scale[3];       // Transform::scale
+	uint32_t pose_frame;  // Pose::frame (0xffffffff = never)
+};
+static_assert(sizeof(SkEntity) == 64, "one burst per entity");
+
+// ---- grid-wide barrier of a cooperative launch (every block of the grid is resident) ----
+struct GridBar { uint32_t count, gen; };
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void grid_barrier(GridBar* b) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const uint32_t gen = ld_acquire_gpu(&b->gen); // cannot advance before this block has arrived
+		__threadfence();                              // this block's writes before the arrival
+		if (atomicAdd(&b->count, 1u) == gridDim.x - 1) {
+			b->count = 0;
+			__threadfence();
+			atomicAdd(&b->gen, 1u);
+		}
+		else {
+			while (ld_acquire_gpu(&b->gen) == gen) {}
+		}
+		__threadfence(); // gpu-scope fence: also drops this SM's L1 lines, the block's plain loads behind the barrier see the other blocks' writes
+	}
+	__syncthreads();
+}
+
 struct EmitParams {
 	lb200_sk_view view;
 	uint32_t type_base[4]; // offsets of the MESH / DECAL / LOCAL_LIGHT / CURVE_DECAL segments inside out_ids
@@ -62,24 +105,14 @@ __device__ __forceinline__ uint32_t warp_claim_keyed(uint32_t* counters, uint32_
 	return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
 
-// Where one renderable's outputs go.  The per-renderable logic runs twice: first with a counting sink (how many keys / instancer records /
-// pose-list entries it emits), then — after ONE block-wide scan and ONE global atomic per counter and block — with a writing sink whose
-// slots are already known.  A single hot counter bumped once per key serialises at the L2 (~1 M claims per view otherwise).
-struct Sink {
-	bool write;
-	uint32_t k, r, p; // next key / record / pose slot (write) or running counts (count)
-	uint32_t* s_grp;  // per block and group, in shared memory: instances counted (count), then the block's cursor inside the group (write);
-	                  // null when the view has more groups than fit: ranks then come from the global counters directly
-};
-
 struct EmitArgs {
-	const lb200_transform* __restrict__ transforms; const uint32_t* __restrict__ model_of; float* __restrict__ lod; const uint8_t* __restrict__ flags;
-	uint32_t* __restrict__ pose_frame; const uint32_t* __restrict__ decal_sort_key; const uint8_t* __restrict__ decal_layer;
+	SkEntity* ent; const uint32_t* __restrict__ decal_sort_key; const uint8_t* __restrict__ decal_layer;
 	const lb200_sk_model* __restrict__ models; const lb200_sk_mesh* __restrict__ meshes;
-	uint64_t* __restrict__ keys; uint64_t* __restrict__ values; uint32_t* __restrict__ counts; uint32_t* __restrict__ group_count;
-	uint8_t* __restrict__ group_layer; uint64_t* __restrict__ rec_value; uint2* __restrict__ rec_group_rank;
-	uint32_t* __restrict__ pose_list; uint32_t* __restrict__ dirty_list;
-	const uint32_t* s_bucket_map; // the view's bucket map in shared memory: every lane looks up its own layer
+	uint64_t* __restrict__ keys; uint64_t* __restrict__ values; uint32_t* counts;
+	uint32_t* group_count; uint32_t* group_offset; uint32_t* group_cursor; const uint8_t* __restrict__ group_layer;
+	uint64_t* __restrict__ group_renderables; float4* __restrict__ instance_data;
+	uint32_t* __restrict__ pose_list; uint32_t* __restrict__ dirty_list; uint32_t* __restrict__ stash;
+	GridBar* bar;
 };
 
 // the 64-byte model record / 16-byte mesh record through the read-only path, into registers
@@ -94,108 +127,135 @@ __device__ __forceinline__ lb200_sk_mesh load_mesh(const lb200_sk_mesh* p) {
 	u.q = __ldg(reinterpret_cast<const int4*>(p));
 	return u.m;
 }
+__device__ __forceinline__ int lod_from(const lb200_sk_model& m, int l) { return l == 0 ? m.lod_from[0] : l == 1 ? m.lod_from[1] : l == 2 ? m.lod_from[2] : l == 3 ? m.lod_from[3] : m.lod_from[4]; }
+__device__ __forceinline__ int lod_to(const lb200_sk_model& m, int l) { return l == 0 ? m.lod_to[0] : l == 1 ? m.lod_to[1] : l == 2 ? m.lod_to[2] : l == 3 ? m.lod_to[3] : m.lod_to[4]; }
 
-__device__ __forceinline__ void push_key(const EmitParams& P, const EmitArgs& A, Sink& s, uint64_t key, uint64_t value) {
-	if (s.write && s.k < P.cap_keys) { A.keys[s.k] = key; A.values[s.k] = value; }
-	++s.k;
-}
+// what pass 1 decided for a MESH renderable, one word: model (24) | first lod (3) | second lod too (1) | MOVED (1) | pose claimed here (1) | dirty (1)
+constexpr uint32_t CODE_MODEL_MASK = 0xffffffu;
+constexpr int CODE_LOD_SHIFT = 24;
+constexpr uint32_t CODE_TWO = 1u << 27, CODE_MOVED = 1u << 28, CODE_POSE = 1u << 29, CODE_DIRTY = 1u << 30;
 
-// DECAL / CURVE_DECAL renderable (:3840-3867)
-__device__ __forceinline__ void decal_entity(const EmitParams& P, const EmitArgs& A, Sink& s, int32_t e, int type) {
-	const uint8_t bucket = (uint8_t)A.s_bucket_map[A.decal_layer[e]];
-	if (bucket < 0xff) {
-		push_key(P, A, s, A.decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
-			sext(e) | ((uint64_t)(type == RT_DECAL ? DRAW_DECAL : DRAW_CURVE_DECAL) << SORT_VALUE_TYPE_SHIFT));
-	}
-}
+struct Counts { uint32_t k, r, p; };
 
-// MESH renderable (:3868-3956)
-__device__ __forceinline__ void mesh_entity(const EmitParams& P, const EmitArgs& A, Sink& s, int32_t e) {
-	const float global_lod_multiplier_rcp = LB_FDIV(1.0f, P.view.lod_multiplier); // :3798-3799
-	const float time_delta = P.view.time_delta;
-	const bool is_shadow = P.view.is_shadow != 0;
-	const lb200_sk_model model = load_model(A.models + A.model_of[e]);
-	const double px = A.transforms[e].pos[0], py = A.transforms[e].pos[1], pz = A.transforms[e].pos[2];
+// MESH renderable, pass 1 (:3868-3956): LOD selection + smoothing state + pose claim; counts what pass 2 will write
+__device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, float lod_multiplier_rcp, int32_t e, Counts& c) {
+	SkEntity* rec = A.ent + e;
+	const int4 q0 = *reinterpret_cast<const int4*>(rec), q1 = *(reinterpret_cast<const int4*>(rec) + 1); // sector 0 (plain loads: this kernel writes lod)
+	const double px = __hiloint2double(q0.y, q0.x), py = __hiloint2double(q0.w, q0.z), pz = __hiloint2double(q1.y, q1.x);
+	const uint32_t model_flags = (uint32_t)q1.z;
+	float cur = __int_as_float(q1.w);
+	const uint32_t model_idx = model_flags & CODE_MODEL_MASK, fl = model_flags >> 24;
+	if (fl & LB200_SK_DIRTY) return CODE_DIRTY | model_idx; // mi.dirty, :3878-3881
+	const lb200_sk_model model = load_model(A.models + model_idx);
 	const double dx = LB_DSUB(px, P.view.lod_ref_point[0]), dy = LB_DSUB(py, P.view.lod_ref_point[1]), dz = LB_DSUB(pz, P.view.lod_ref_point[2]);
 	const float squared_length = (float)LB_DADD(LB_DADD(LB_DMUL(dx, dx), LB_DMUL(dy, dy)), LB_DMUL(dz, dz)); // squaredLength(DVec3), math.cpp:397
-	const float sd = LB_FMUL(squared_length, global_lod_multiplier_rcp);
+	const float sd = LB_FMUL(squared_length, lod_multiplier_rcp);
 	const uint32_t lod_idx = sd < model.lod_distances[0] ? 0u : sd < model.lod_distances[1] ? 1u : sd < model.lod_distances[2] ? 2u : sd < model.lod_distances[3] ? 3u : 4u;
-	const uint8_t fl = A.flags[e];
-	if (fl & LB200_SK_DIRTY) { // mi.dirty, :3878-3881: queueMaterialOverrideRefresh (rare: its own atomic)
-		if (s.write) {
-			const uint32_t slot = atomicAdd(&A.counts[CNT_DIRTY], 1u);
-			if (slot < P.cap_dirty) A.dirty_list[slot] = (uint32_t)e;
-		}
-		return;
-	}
-	int lods[2], n_lods = 0;
-	float cur = A.lod[e];
+	const bool is_shadow = P.view.is_shadow != 0;
+	uint32_t lod0 = lod_idx;
+	bool two = false;
 	if (cur != (float)lod_idx) { // :3926-3941
 		const float d = LB_FSUB((float)lod_idx, cur);
 		const float ad = fabsf(d);
-		if (ad <= time_delta) {
-			cur = (float)lod_idx;
-			lods[n_lods++] = (int)lod_idx;
-		}
+		if (ad <= P.view.time_delta) cur = (float)lod_idx;
 		else {
-			if (!is_shadow) cur = LB_FADD(cur, LB_FMUL(LB_FDIV(d, ad), time_delta));
-			const uint32_t cur_lod_idx = (uint32_t)cur;
-			lods[n_lods++] = (int)cur_lod_idx;
-			if (cur_lod_idx < 3) lods[n_lods++] = (int)cur_lod_idx + 1;
+			if (!is_shadow) cur = LB_FADD(cur, LB_FMUL(LB_FDIV(d, ad), P.view.time_delta));
+			lod0 = (uint32_t)cur;
+			two = lod0 < 3;
 		}
-		if (s.write) A.lod[e] = cur;
+		rec->lod = cur;
 	}
-	else lods[n_lods++] = (int)lod_idx;
-	bool pose_done = A.pose_frame[e] == P.view.frame_number;
+	uint32_t code = model_idx | (lod0 << CODE_LOD_SHIFT) | (two ? CODE_TWO : 0u) | ((fl & LB200_SK_MOVED) ? CODE_MOVED : 0u);
+	bool pose_checked = false;
+	const int n_lods = two ? 2 : 1;
 	for (int li = 0; li < n_lods; ++li) { // create_key, :3883-3924
-		const int l = lods[li]; // no dynamic indexing of the register copy
-		const int from = l == 0 ? model.lod_from[0] : l == 1 ? model.lod_from[1] : l == 2 ? model.lod_from[2] : l == 3 ? model.lod_from[3] : model.lod_from[4];
-		const int to = l == 0 ? model.lod_to[0] : l == 1 ? model.lod_to[1] : l == 2 ? model.lod_to[2] : l == 3 ? model.lod_to[3] : model.lod_to[4];
-		for (int mesh_idx = from; mesh_idx <= to; ++mesh_idx) {
+		const int l = (int)lod0 + li;
+		const int to = lod_to(model, l);
+		for (int mesh_idx = lod_from(model, l); mesh_idx <= to; ++mesh_idx) {
 			const lb200_sk_mesh mm = load_mesh(A.meshes + model.mesh_base + (uint32_t)mesh_idx);
-			const uint32_t bucket = A.s_bucket_map[mm.layer];
+			const uint32_t bucket = s_bucket_map[mm.layer];
 			if (mm.skinned) {
-				// once per instance and frame: the instance's palette has to be built (PoseProcessor::push; the compare-exchange on
-				// Pose::frame of :3890-3897 — one thread owns the instance within a view)
-				if (!pose_done) {
-					pose_done = true;
-					if (s.write) {
-						A.pose_frame[e] = P.view.frame_number;
-						if (s.p < P.cap_pose) A.pose_list[s.p] = (uint32_t)e;
-					}
-					++s.p;
+				// once per instance and frame the palette has to be built (PoseProcessor::push; the compare-exchange on Pose::frame of
+				// :3890-3897 — one thread owns the instance within a view)
+				if (!pose_checked) {
+					pose_checked = true;
+					if (rec->pose_frame != P.view.frame_number) { rec->pose_frame = P.view.frame_number; code |= CODE_POSE; ++c.p; }
 				}
-				push_key(P, A, s, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
-					sext(e) | ((uint64_t)DRAW_SKINNED << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
+				++c.k;
 			}
-			else if ((fl & LB200_SK_MOVED) && !is_shadow) {
-				push_key(P, A, s, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
-					sext(e) | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
+			else if ((fl & LB200_SK_MOVED) && !is_shadow) ++c.k;
+			else if (bucket < 0xff) { // AutoInstancer::add, :3913-3914
+				++c.r;
+				if (s_grp) atomicAdd(&s_grp[mm.sort_key], 1u);
+				else warp_claim_keyed(A.group_count, mm.sort_key);
 			}
-			else if (bucket < 0xff) { // AutoInstancer::add(mesh_sort_key, e.index | mesh_idx << 40), :3913-3914
-				if (!s.write) { if (s.s_grp) atomicAdd(&s.s_grp[mm.sort_key], 1u); }
-				else {
-					const uint32_t rank = s.s_grp ? atomicAdd(&s.s_grp[mm.sort_key], 1u) : warp_claim_keyed(A.group_count, mm.sort_key);
-					if (s.r < P.cap_recs) {
-						A.rec_value[s.r] = sext(e) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT);
-						A.rec_group_rank[s.r] = make_uint2(mm.sort_key, rank);
-					}
-					if (rank == 0) A.group_layer[mm.sort_key] = mm.layer; // the same for every instance of the mesh: written once (a store per instance to a handful of bytes serialises at the L2)
+			else if (bucket < 0xffff) ++c.k; // depth sorted, :3915-3922
+		}
+	}
+	return code;
+}
+
+__device__ __forceinline__ void push_key(const EmitParams& P, const EmitArgs& A, uint32_t& slot, uint64_t key, uint64_t value) {
+	if (slot < P.cap_keys) { A.keys[slot] = key; A.values[slot] = value; }
+	++slot;
+}
+
+// MESH renderable, pass 2: replay of the stashed decision, writes
+__device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, int32_t e, uint32_t code, uint32_t& k, uint32_t& p) {
+	if (code & CODE_DIRTY) { // queueMaterialOverrideRefresh (rare: its own atomic)
+		const uint32_t slot = atomicAdd(&A.counts[CNT_DIRTY], 1u);
+		if (slot < P.cap_dirty) A.dirty_list[slot] = (uint32_t)e;
+		return;
+	}
+	const lb200_sk_model model = load_model(A.models + (code & CODE_MODEL_MASK));
+	const bool is_shadow = P.view.is_shadow != 0;
+	const uint32_t lod0 = (code >> CODE_LOD_SHIFT) & 7u;
+	const int n_lods = (code & CODE_TWO) ? 2 : 1;
+	if (code & CODE_POSE) {
+		if (p < P.cap_pose) A.pose_list[p] = (uint32_t)e;
+		++p;
+	}
+	bool have = false;
+	int4 q0, q1, q2, q3; // the entity's record, fetched once and only if an instance or a depth key needs it
+	q0 = q1 = q2 = q3 = make_int4(0, 0, 0, 0);
+	for (int li = 0; li < n_lods; ++li) {
+		const int l = (int)lod0 + li;
+		const int to = lod_to(model, l);
+		for (int mesh_idx = lod_from(model, l); mesh_idx <= to; ++mesh_idx) {
+			const lb200_sk_mesh mm = load_mesh(A.meshes + model.mesh_base + (uint32_t)mesh_idx);
+			const uint32_t bucket = s_bucket_map[mm.layer];
+			const uint64_t mesh_value = sext(e) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT);
+			if (mm.skinned) push_key(P, A, k, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)DRAW_SKINNED << SORT_VALUE_TYPE_SHIFT));
+			else if ((code & CODE_MOVED) && !is_shadow) push_key(P, A, k, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT));
+			else if (bucket < 0xffff) {
+				if (!have) {
+					have = true;
+					const int4* r = reinterpret_cast<const int4*>(A.ent + e);
+					q0 = r[0]; q1 = r[1]; q2 = r[2]; q3 = r[3];
 				}
-				++s.r;
-			}
-			else if (bucket < 0xffff) { // depth sorted, :3915-3922
+				const double px = __hiloint2double(q0.y, q0.x), py = __hiloint2double(q0.w, q0.z), pz = __hiloint2double(q1.y, q1.x);
 				const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
-				const float sq = (float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz));
-				push_key(P, A, s, float_flip(__float_as_uint(sq)) | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT),
-					sext(e) | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT));
+				if (bucket < 0xff) { // instance data of the auto-instanced mesh, :3990-4008, at the group's offset + this block's slice + rank
+					const uint32_t at = s_grp ? atomicAdd(&s_grp[mm.sort_key], 1u) : warp_claim_keyed(A.group_cursor, mm.sort_key);
+					if (at < P.cap_recs) {
+						A.group_renderables[at] = mesh_value;
+						float4* dst = A.instance_data + (size_t)at * 3;
+						dst[0] = make_float4(__int_as_float(q2.x), __int_as_float(q2.y), __int_as_float(q2.z), __int_as_float(q2.w)); // rot
+						dst[1] = make_float4((float)rx, (float)ry, (float)rz, LB_FSUB(__int_as_float(q1.w), mm.lod)); // Vec3(tr.pos - camera_pos), lod - mesh.lod
+						dst[2] = make_float4(__int_as_float(q3.x), __int_as_float(q3.y), __int_as_float(q3.z), __uint_as_float(mm.material_index)); // scale, material
+					}
+				}
+				else { // depth sorted, :3915-3922
+					const float sq = (float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz));
+					push_key(P, A, k, float_flip(__float_as_uint(sq)) | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT));
+				}
 			}
 		}
 	}
 }
 
 // block-wide exclusive scan of one value per thread (SK_THREADS threads); returns the thread's prefix, *total = the block's sum
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /* SK_THREADS / 32 + 1 */, uint32_t* total) {
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /* SK_THREADS / 32 */, uint32_t* total) {
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	uint32_t x = v;
 #pragma unroll
@@ -215,275 +275,291 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 
 constexpr uint32_t SK_SMEM_GROUPS = 8192; // group counters a block keeps in shared memory (32 KB)
 
-// Every block walks its share of the visible renderables twice.  Pass 1 counts: keys / records / pose entries per thread, instances per
-// auto-instancer group per block (shared-memory atomics).  Then ONE block-wide scan and one global atomic per counter claim the block's
-// output ranges, and one global atomic per group the block touched claims its slice of the group.  Pass 2 repeats the logic and writes.
-__global__ void __launch_bounds__(SK_THREADS) emit_kernel(const __grid_constant__ EmitParams P, const uint32_t* __restrict__ visible,
+__global__ void __launch_bounds__(SK_THREADS, 3) create_keys_kernel(const __grid_constant__ EmitParams P, const uint32_t* __restrict__ visible,
 	const uint32_t* __restrict__ cull_counters, EmitArgs A, uint32_t n_groups)
 {
 	extern __shared__ uint32_t s_grp_mem[];
 	__shared__ uint32_t s_warp[SK_THREADS / 32];
-	__shared__ uint32_t s_base[3];
+	__shared__ uint32_t s_base[2];
+	__shared__ uint32_t s_carry;
 	__shared__ uint32_t s_bucket_map[256];
 	s_bucket_map[threadIdx.x] = P.view.bucket_map[threadIdx.x]; // SK_THREADS == 256
-	A.s_bucket_map = s_bucket_map;
 	uint32_t* s_grp = n_groups <= SK_SMEM_GROUPS ? s_grp_mem : nullptr;
 	if (s_grp) for (uint32_t g = threadIdx.x; g < n_groups; g += SK_THREADS) s_grp[g] = 0;
 	__syncthreads();
 	// the three segments as one index space: [MESH | DECAL | CURVE_DECAL]
 	const uint32_t n_mesh = __ldg(cull_counters + RT_MESH), n_decal = __ldg(cull_counters + RT_DECAL), n_curve = __ldg(cull_counters + RT_CURVE_DECAL);
 	const uint32_t n_all = n_mesh + n_decal + n_curve;
-	Sink sink = {false, 0u, 0u, 0u, s_grp};
-#pragma unroll 1
-	for (int pass = 0; pass < 2; ++pass) {
-		for (uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x; i < n_all; i += gridDim.x * SK_THREADS) {
-			if (i < n_mesh) mesh_entity(P, A, sink, (int32_t)visible[P.type_base[RT_MESH] + i]);
-			else if (i < n_mesh + n_decal) decal_entity(P, A, sink, (int32_t)visible[P.type_base[RT_DECAL] + (i - n_mesh)], RT_DECAL);
-			else decal_entity(P, A, sink, (int32_t)visible[P.type_base[RT_CURVE_DECAL] + (i - n_mesh - n_decal)], RT_CURVE_DECAL);
+	const float lod_multiplier_rcp = LB_FDIV(1.0f, P.view.lod_multiplier); // :3798-3799
+	const uint32_t stride = gridDim.x * SK_THREADS;
+
+	// ---- pass 1: decide + count ----
+	Counts c = {0u, 0u, 0u};
+	for (uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x; i < n_all; i += stride) {
+		if (i < n_mesh) A.stash[i] = mesh_count(P, A, s_bucket_map, s_grp, lod_multiplier_rcp, (int32_t)visible[P.type_base[RT_MESH] + i], c);
+		else { // DECAL / CURVE_DECAL renderable (:3840-3867): one key if its layer is in the view
+			const bool curve = i >= n_mesh + n_decal;
+			const int32_t e = (int32_t)visible[curve ? P.type_base[RT_CURVE_DECAL] + (i - n_mesh - n_decal) : P.type_base[RT_DECAL] + (i - n_mesh)];
+			if ((uint8_t)s_bucket_map[A.decal_layer[e]] < 0xff) ++c.k;
 		}
-		if (pass == 1) break;
-		uint32_t tk, tr, tp;
-		const uint32_t pk = block_exclusive_scan(sink.k, s_warp, &tk);
-		const uint32_t pr = block_exclusive_scan(sink.r, s_warp, &tr);
-		const uint32_t pp = block_exclusive_scan(sink.p, s_warp, &tp);
-		if (threadIdx.x == 0) {
-			s_base[0] = tk ? atomicAdd(&A.counts[CNT_KEYS], tk) : 0u;
-			s_base[1] = tr ? atomicAdd(&A.counts[CNT_RECS], tr) : 0u;
-			s_base[2] = tp ? atomicAdd(&A.counts[CNT_POSE], tp) : 0u;
-		}
-		// the block's slice of every group it has instances of: count -> cursor
-		if (s_grp) for (uint32_t g = threadIdx.x; g < n_groups; g += SK_THREADS) if (s_grp[g]) s_grp[g] = atomicAdd(&A.group_count[g], s_grp[g]);
-		__syncthreads();
-		sink.write = true;
-		sink.k = s_base[0] + pk; sink.r = s_base[1] + pr; sink.p = s_base[2] + pp;
 	}
-}
+	uint32_t tk, tp;
+	const uint32_t pk = block_exclusive_scan(c.k, s_warp, &tk);
+	const uint32_t pp = block_exclusive_scan(c.p, s_warp, &tp);
+	if (threadIdx.x == 0) {
+		s_base[0] = tk ? atomicAdd(&A.counts[CNT_KEYS], tk) : 0u;
+		s_base[1] = tp ? atomicAdd(&A.counts[CNT_POSE], tp) : 0u;
+	}
+	// the block's slice of every group it has instances of: count -> start inside the group
+	if (s_grp) for (uint32_t g = threadIdx.x; g < n_groups; g += SK_THREADS) if (s_grp[g]) s_grp[g] = atomicAdd(&A.group_count[g], s_grp[g]);
+	grid_barrier(A.bar); // every block's counts are in: group totals are final
 
-// one block: exclusive scan of the group counters, then one key/value per non-empty group (:3958-3969)
-struct GroupParams { uint8_t layer_to_bucket[256]; uint32_t n_groups, cap_keys; };
-
-__global__ void __launch_bounds__(1024) groups_kernel(const __grid_constant__ GroupParams P, const uint32_t* __restrict__ group_count,
-	uint32_t* __restrict__ group_offset, const uint8_t* __restrict__ group_layer, uint64_t* __restrict__ keys, uint64_t* __restrict__ values,
-	uint32_t* __restrict__ counts)
-{
-	__shared__ uint32_t s_warp[32];
-	__shared__ uint32_t s_carry;
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	if (tid == 0) s_carry = 0;
-	__syncthreads();
-	for (uint32_t base = 0; base < P.n_groups; base += 1024) {
-		const uint32_t g = base + tid;
-		const uint32_t c = g < P.n_groups ? group_count[g] : 0u;
-		uint32_t x = c;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-			if (lane >= (uint32_t)d) x += y;
-		}
-		if (lane == 31) s_warp[warp] = x;
+	// ---- group offsets = exclusive scan of the group totals; block 0 publishes them and one key/value per non-empty group (:3958-3969) ----
+	if (s_grp || blockIdx.x == 0) {
+		if (threadIdx.x == 0) s_carry = 0;
 		__syncthreads();
-		uint32_t before = s_carry;
-		for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
-		if (g < P.n_groups) {
-			group_offset[g] = before + x - c;
-			if (c) {
-				const uint32_t slot = atomicAdd(&counts[CNT_KEYS], 1u);
-				if (slot < P.cap_keys) {
-					keys[slot] = (uint64_t)g | SORT_KEY_INSTANCED_FLAG | ((uint64_t)P.layer_to_bucket[group_layer[g]] << SORT_KEY_BUCKET_SHIFT); // :100-102
-					values[slot] = (uint64_t)g | ((uint64_t)0 << SORT_VALUE_INSTANCER_SHIFT) | ((uint64_t)DRAW_AUTOINSTANCED << SORT_VALUE_TYPE_SHIFT); // :141-143
+		for (uint32_t base = 0; base < n_groups; base += SK_THREADS) {
+			const uint32_t g = base + threadIdx.x;
+			const uint32_t cnt = g < n_groups ? __ldcg(A.group_count + g) : 0u;
+			uint32_t total;
+			const uint32_t carry = s_carry; // read before the scan's barriers: thread 0 moves it on behind them
+			const uint32_t off = carry + block_exclusive_scan(cnt, s_warp, &total);
+			if (g < n_groups) {
+				if (s_grp) s_grp[g] += off; // cursor of this block inside the group, absolute
+				if (blockIdx.x == 0) {
+					A.group_offset[g] = off;
+					if (!s_grp) A.group_cursor[g] = off;
+					if (cnt) {
+						const uint32_t slot = atomicAdd(&A.counts[CNT_KEYS], 1u);
+						if (slot < P.cap_keys) {
+							A.keys[slot] = (uint64_t)g | SORT_KEY_INSTANCED_FLAG | ((uint64_t)P.view.layer_to_bucket[A.group_layer[g]] << SORT_KEY_BUCKET_SHIFT); // :100-102
+							A.values[slot] = (uint64_t)g | ((uint64_t)0 << SORT_VALUE_INSTANCER_SHIFT) | ((uint64_t)DRAW_AUTOINSTANCED << SORT_VALUE_TYPE_SHIFT); // :141-143
+						}
+					}
 				}
 			}
+			if (threadIdx.x == 0) s_carry += total;
+			__syncthreads();
 		}
-		__syncthreads();
-		if (tid == 1023) s_carry = before + x;
-		__syncthreads();
+		if (blockIdx.x == 0 && threadIdx.x == 0) { A.counts[CNT_INST] = s_carry; A.counts[CNT_RECS] = s_carry; }
 	}
-	if (tid == 0) counts[CNT_INST] = s_carry;
+	if (!s_grp) grid_barrier(A.bar); // more groups than fit in shared memory: everybody waits for block 0's cursors in HBM
+
+	// ---- pass 2: write ----
+	uint32_t k = s_base[0] + pk, p = s_base[1] + pp;
+	for (uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x; i < n_all; i += stride) {
+		if (i < n_mesh) mesh_write(P, A, s_bucket_map, s_grp, (int32_t)visible[P.type_base[RT_MESH] + i], A.stash[i], k, p);
+		else {
+			const bool curve = i >= n_mesh + n_decal;
+			const int32_t e = (int32_t)visible[curve ? P.type_base[RT_CURVE_DECAL] + (i - n_mesh - n_decal) : P.type_base[RT_DECAL] + (i - n_mesh)];
+			const uint8_t bucket = (uint8_t)s_bucket_map[A.decal_layer[e]];
+			if (bucket < 0xff) push_key(P, A, k, A.decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
+				sext(e) | ((uint64_t)(curve ? DRAW_CURVE_DECAL : DRAW_DECAL) << SORT_VALUE_TYPE_SHIFT));
+		}
+	}
 }
 
-// instance data of the auto-instanced meshes, :3990-4008
-__global__ void __launch_bounds__(SK_THREADS) fill_kernel(const double cx, const double cy, const double cz, uint32_t cap_recs, const uint32_t* __restrict__ counts,
-	const uint64_t* __restrict__ rec_value, const uint2* __restrict__ rec_group_rank, const uint32_t* __restrict__ group_offset,
-	const lb200_transform* __restrict__ transforms, const uint32_t* __restrict__ model_of, const float* __restrict__ lod,
-	const lb200_sk_model* __restrict__ models, const lb200_sk_mesh* __restrict__ meshes, uint64_t* __restrict__ group_renderables, float4* __restrict__ instance_data)
+// ---- per-entity records: packing what the caller hands over as arrays, unpacking the state the pass keeps ----
+__global__ void __launch_bounds__(256) ent_init_kernel(SkEntity* ent, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int4* r = reinterpret_cast<int4*>(ent + i);
+	r[0] = r[1] = r[2] = make_int4(0, 0, 0, 0);
+	r[3] = make_int4(0, 0, 0, (int)0xffffffffu); // Pose::frame = 0xffffffff: "never" (pipeline.cpp:3814)
+}
+__global__ void __launch_bounds__(256) ent_pack_transforms_kernel(SkEntity* ent, const lb200_transform* __restrict__ tr, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const lb200_transform t = tr[i];
+	SkEntity& r = ent[i];
+	r.pos[0] = t.pos[0]; r.pos[1] = t.pos[1]; r.pos[2] = t.pos[2];
+	r.rot[0] = t.rot[0]; r.rot[1] = t.rot[1]; r.rot[2] = t.rot[2]; r.rot[3] = t.rot[3];
+	r.scale[0] = t.scale[0]; r.scale[1] = t.scale[1]; r.scale[2] = t.scale[2];
+}
+__global__ void __launch_bounds__(256) ent_pack_fields_kernel(SkEntity* ent, uint32_t n, const uint32_t* __restrict__ model_of, const float* __restrict__ lod,
+	const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pose_frame)
 {
-	const uint32_t n = min(counts[CNT_RECS], cap_recs);
-	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-		const uint64_t v = rec_value[r];
-		const uint2 gr = rec_group_rank[r];
-		const uint32_t at = group_offset[gr.x] + gr.y;
-		const int32_t e = (int32_t)(uint32_t)v;
-		const uint32_t mesh_idx = (uint32_t)(v >> SORT_VALUE_MESH_IDX_SHIFT);
-		const lb200_sk_mesh mm = meshes[__ldg(&models[model_of[e]].mesh_base) + mesh_idx];
-		const lb200_transform& tr = transforms[e];
-		const float lx = (float)LB_DSUB(tr.pos[0], cx), ly = (float)LB_DSUB(tr.pos[1], cy), lz = (float)LB_DSUB(tr.pos[2], cz); // Vec3(tr.pos - camera_pos)
-		const float lod_d = LB_FSUB(lod[e], mm.lod);
-		group_renderables[at] = v;
-		float4* dst = instance_data + (size_t)at * 3;
-		dst[0] = make_float4(tr.rot[0], tr.rot[1], tr.rot[2], tr.rot[3]);
-		dst[1] = make_float4(lx, ly, lz, lod_d);
-		dst[2] = make_float4(tr.scale[0], tr.scale[1], tr.scale[2], __uint_as_float(mm.material_index));
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	SkEntity& r = ent[i];
+	if (model_of || flags) {
+		uint32_t mf = r.model_flags;
+		if (model_of) mf = (mf & ~CODE_MODEL_MASK) | (model_of[i] & CODE_MODEL_MASK);
+		if (flags) mf = (mf & CODE_MODEL_MASK) | ((uint32_t)flags[i] << 24);
+		r.model_flags = mf;
 	}
+	if (lod) r.lod = lod[i];
+	if (pose_frame) r.pose_frame = pose_frame[i];
+}
+__global__ void __launch_bounds__(256) ent_unpack_state_kernel(const SkEntity* __restrict__ ent, uint32_t n, float* __restrict__ lod, uint32_t* __restrict__ pose_frame) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	lod[i] = ent[i].lod;
+	pose_frame[i] = ent[i].pose_frame;
 }
 
 // ---------------------------------------------------------------- radix sort ----------------------------------------------------------------
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 4;                         // keys per thread and tile
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 2048 keys
 constexpr int RS_PASSES = 8;
-struct SortState { uint32_t cur; uint32_t done_blocks; uint32_t pad[2]; uint32_t global_hist[RS_PASSES][256]; };
+struct SortState { GridBar bar; uint32_t pad[2]; unsigned long long key_or, key_or_not; }; // zero-initialised: OR of all keys, OR of all complements
 
-__global__ void __launch_bounds__(RS_THREADS) rs_global_hist_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint32_t cap, SortState* st) {
-	__shared__ uint32_t s_h[RS_PASSES][256];
-	for (int i = threadIdx.x; i < RS_PASSES * 256; i += RS_THREADS) (&s_h[0][0])[i] = 0;
-	__syncthreads();
-	const uint32_t n = min(counts[0], cap);
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const uint64_t k = keys[i];
-#pragma unroll
-		for (int p = 0; p < RS_PASSES; ++p) atomicAdd(&s_h[p][(k >> (8 * p)) & 0xffu], 1u);
-	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < RS_PASSES * 256; i += RS_THREADS) if ((&s_h[0][0])[i]) atomicAdd(&(&st->global_hist[0][0])[i], (&s_h[0][0])[i]);
-}
-
-// a pass moves nothing when every key has the same digit there (the reference's skip at pipeline.cpp:4120 is the bin-0 case of this)
-__device__ __forceinline__ bool pass_is_trivial(const SortState* st, int pass, uint32_t n) {
-	return st->global_hist[pass][0] == n;
-}
-
-// keys of block b: [b * per, min(n, (b + 1) * per)), per = ceil(n / blocks) rounded up to RS_THREADS
-__device__ __forceinline__ void block_range(uint32_t n, uint32_t& begin, uint32_t& end) {
-	uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-	per = (per + RS_THREADS - 1) / RS_THREADS * RS_THREADS;
-	begin = min(n, blockIdx.x * per);
-	end = min(n, begin + per);
-}
-
-__global__ void __launch_bounds__(RS_THREADS) rs_block_hist_kernel(int pass, const uint64_t* __restrict__ buf0, const uint64_t* __restrict__ buf1,
-	const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st, uint32_t* __restrict__ block_hist /* [256][gridDim] */)
+// All passes in one cooperative launch.  Tiles of RS_TILE keys are dealt to the blocks in contiguous runs (block b: tiles [b*T/G, (b+1)*T/G)),
+// so "block order, then tile order, then position" is the key order and the scatter is stable.
+__global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbuf0, uint64_t* kbuf1, uint64_t* vbuf0, uint64_t* vbuf1, const uint32_t* __restrict__ counts, uint32_t cap,
+	SortState* st, uint32_t* block_hist /* [gridDim][256] */)
 {
-	__shared__ uint32_t s_h[256];
+	__shared__ uint32_t s_hist[256];              // count phase: this block's digit histogram; scatter phase: the block's running digit cursors
+	__shared__ uint32_t s_part[2][256], s_bef[2][256], s_wsum[8];
+	__shared__ uint32_t s_wcnt[RS_WARPS][256];    // per warp: keys of digit d in the warp's part of the tile, then the warp's first destination of digit d
+	__shared__ unsigned long long s_red[2][RS_WARPS];
 	const uint32_t n = min(counts[0], cap);
-	if (pass_is_trivial(st, pass, n)) return;
-	const uint64_t* keys = st->cur ? buf1 : buf0;
-	s_h[threadIdx.x] = 0;
-	__syncthreads();
-	uint32_t begin, end;
-	block_range(n, begin, end);
-	for (uint32_t i = begin + threadIdx.x; i < end; i += RS_THREADS) atomicAdd(&s_h[(keys[i] >> (8 * pass)) & 0xffu], 1u);
-	__syncthreads();
-	block_hist[threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
-}
-
-// exclusive scan over block_hist in (digit, block) order.  Block d of the grid owns digit d: its base is the number of keys with a
-// smaller digit (the pass's global histogram), then one warp scans the digit's per-block counts 32 at a time.
-__global__ void __launch_bounds__(32) rs_scan_kernel(int pass, const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st, uint32_t* __restrict__ block_hist, uint32_t n_blocks) {
-	const uint32_t n = min(counts[0], cap);
-	if (pass_is_trivial(st, pass, n)) return;
-	const uint32_t d = blockIdx.x, lane = threadIdx.x;
-	uint32_t base = 0;
-	for (uint32_t k = lane; k < d; k += 32) base += st->global_hist[pass][k];
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
-	uint32_t* row = block_hist + (size_t)d * n_blocks;
-	for (uint32_t b0 = 0; b0 < n_blocks; b0 += 32) {
-		const uint32_t b = b0 + lane;
-		const uint32_t c = b < n_blocks ? row[b] : 0u;
-		uint32_t x = c;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-			if (lane >= (uint32_t)o) x += y;
-		}
-		if (b < n_blocks) row[b] = base + x - c;
-		base += __shfl_sync(0xffffffffu, x, 31);
-	}
-}
-
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int pass, uint64_t* __restrict__ kbuf0, uint64_t* __restrict__ kbuf1, uint64_t* __restrict__ vbuf0,
-	uint64_t* __restrict__ vbuf1, const uint32_t* __restrict__ counts, uint32_t cap, SortState* st, const uint32_t* __restrict__ block_hist)
-{
-	__shared__ uint32_t s_digit_base[256];        // where this block's next key of digit d goes
-	__shared__ uint16_t s_warp_cnt[RS_WARPS][256]; // keys of digit d in warp w of the current tile
-	const uint32_t n = min(counts[0], cap);
-	if (pass_is_trivial(st, pass, n)) return;
-	const uint32_t cur = st->cur;
-	const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
-	const uint64_t* vsrc = cur ? vbuf1 : vbuf0;
-	uint64_t* kdst = cur ? kbuf0 : kbuf1;
-	uint64_t* vdst = cur ? vbuf0 : vbuf1;
+	if (n < 2) return; // uniform over the grid: nothing to sort (buffer 0 already holds the result)
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	s_digit_base[tid] = block_hist[tid * gridDim.x + blockIdx.x];
-	for (int w = 0; w < RS_WARPS; ++w) s_warp_cnt[w][tid] = 0;
-	__syncthreads();
-	uint32_t begin, end;
-	block_range(n, begin, end);
-	for (uint32_t tile = begin; tile < end; tile += RS_THREADS) {
-		const uint32_t i = tile + tid;
-		const bool has = i < end;
-		const uint64_t k = has ? ksrc[i] : 0;
-		const uint64_t v = has ? vsrc[i] : 0;
-		const uint32_t d = has ? (uint32_t)((k >> (8 * pass)) & 0xffu) : 0x100u; // inactive threads match only each other
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
-		const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-		if (has && rank_in_warp == 0) s_warp_cnt[warp][d] = (uint16_t)__popc(peers);
-		__syncthreads();
-		if (has) {
-			uint32_t before = s_digit_base[d];
-			for (uint32_t w = 0; w < warp; ++w) before += s_warp_cnt[w][d];
-			const uint32_t dest = before + rank_in_warp;
-			kdst[dest] = k;
-			vdst[dest] = v;
-		}
-		__syncthreads();
-		{ // thread d: advance the block's cursor of digit d past this tile, clear the per-warp counts
-			uint32_t tot = 0;
+	const uint32_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+	const uint32_t tile_begin = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+	const uint32_t tile_end = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+	const uint32_t key_begin = tile_begin * RS_TILE, key_end = min(n, tile_end * RS_TILE);
+
+	// which digits differ at all: OR and AND over every key
+	{
+		unsigned long long o = 0ull, a = 0ull;
+		for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) { const unsigned long long k = kbuf0[i]; o |= k; a |= ~k; }
 #pragma unroll
-			for (int w = 0; w < RS_WARPS; ++w) { tot += s_warp_cnt[w][tid]; s_warp_cnt[w][tid] = 0; }
-			s_digit_base[tid] += tot;
-		}
+		for (int d = 16; d > 0; d >>= 1) { o |= __shfl_xor_sync(0xffffffffu, o, d); a |= __shfl_xor_sync(0xffffffffu, a, d); }
+		if (lane == 0) { s_red[0][warp] = o; s_red[1][warp] = a; }
 		__syncthreads();
+		if (tid == 0) {
+			for (int w = 1; w < RS_WARPS; ++w) { o |= s_red[0][w]; a |= s_red[1][w]; }
+			if (key_begin < key_end) { atomicOr(&st->key_or, o); atomicOr(&st->key_or_not, a); }
+		}
 	}
-	// the last block to finish flips the buffers
-	__shared__ bool s_last;
-	__threadfence();
-	if (tid == 0) s_last = atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1;
-	__syncthreads();
-	if (s_last && tid == 0) { st->cur = cur ^ 1u; st->done_blocks = 0; }
+	grid_barrier(&st->bar);
+	const unsigned long long varying = __ldcg(&st->key_or) & __ldcg(&st->key_or_not); // bits that are 1 in some key and 0 in another
+
+	uint32_t cur = 0;
+#pragma unroll 1
+	for (int pass = 0; pass < RS_PASSES; ++pass) {
+		const int shift = 8 * pass;
+		if (((varying >> shift) & 0xffull) == 0ull) continue; // every key has the same digit here: the pass would move nothing
+		const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
+		const uint64_t* vsrc = cur ? vbuf1 : vbuf0;
+		uint64_t* kdst = cur ? kbuf0 : kbuf1;
+		uint64_t* vdst = cur ? vbuf0 : vbuf1;
+		// count
+		if (tid < 256) s_hist[tid] = 0;
+		__syncthreads();
+		for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) atomicAdd(&s_hist[(uint32_t)(__ldcg(ksrc + i) >> shift) & 0xffu], 1u);
+		__syncthreads();
+		if (tid < 256) block_hist[blockIdx.x * 256 + tid] = s_hist[tid];
+		grid_barrier(&st->bar);
+		// where this block's keys of digit d start: all keys of smaller digits + the keys of digit d in the blocks before this one
+		{
+			const uint32_t d = tid & 255u, part = tid >> 8;
+			uint32_t before = 0, total = 0;
+			for (uint32_t b = part; b < gridDim.x; b += RS_THREADS / 256) {
+				const uint32_t c = __ldcg(block_hist + b * 256 + d);
+				total += c;
+				if (b < blockIdx.x) before += c;
+			}
+			s_part[part][d] = total;
+			s_bef[part][d] = before;
+			__syncthreads();
+			uint32_t x = 0, mine = 0;
+			if (tid < 256) { // exclusive scan of the 256 digit totals by the first 8 warps
+				mine = s_part[0][tid] + s_part[1][tid];
+				x = mine;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+				if (lane == 31) s_wsum[warp] = x;
+			}
+			__syncthreads();
+			if (tid < 256) {
+				uint32_t start = x - mine;
+				for (uint32_t w = 0; w < warp; ++w) start += s_wsum[w];
+				s_hist[tid] = start + s_bef[0][tid] + s_bef[1][tid];
+			}
+			__syncthreads();
+		}
+		// stable scatter, tile by tile
+		for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+			const uint32_t wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
+			uint64_t k[RS_ITEMS], v[RS_ITEMS];
+			uint32_t dg[RS_ITEMS], rk[RS_ITEMS];
+#pragma unroll
+			for (int j = 0; j < RS_ITEMS; ++j) {
+				const uint32_t i = wbase + j * 32 + lane;
+				const bool has = i < n;
+				k[j] = has ? __ldcg(ksrc + i) : 0;
+				v[j] = has ? __ldcg(vsrc + i) : 0;
+				dg[j] = has ? (uint32_t)(k[j] >> shift) & 0xffu : 0x100u; // keys past the end match only each other
+			}
+			for (int d = lane; d < 256; d += 32) s_wcnt[warp][d] = 0;
+			__syncwarp();
+#pragma unroll
+			for (int j = 0; j < RS_ITEMS; ++j) {
+				const uint32_t peers = __match_any_sync(0xffffffffu, dg[j]);
+				const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+				uint32_t seen = 0;
+				if (dg[j] < 256) seen = s_wcnt[warp][dg[j]];
+				__syncwarp();
+				if (dg[j] < 256 && below == 0) s_wcnt[warp][dg[j]] = seen + __popc(peers);
+				__syncwarp();
+				rk[j] = seen + below;
+			}
+			__syncthreads();
+			if (tid < 256) { // digit tid: the warps' slices in warp order, then advance the block's cursor past the tile
+				uint32_t acc = s_hist[tid];
+#pragma unroll
+				for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = s_wcnt[w][tid]; s_wcnt[w][tid] = acc; acc += t; }
+				s_hist[tid] = acc;
+			}
+			__syncthreads();
+#pragma unroll
+			for (int j = 0; j < RS_ITEMS; ++j) {
+				if (dg[j] < 256) {
+					const uint32_t dest = s_wcnt[warp][dg[j]] + rk[j];
+					kdst[dest] = k[j];
+					vdst[dest] = v[j];
+				}
+			}
+			__syncthreads();
+		}
+		grid_barrier(&st->bar);
+		cur ^= 1u;
+	}
+	if (cur) { // sorted data to buffer 0 if it ended up in buffer 1
+		for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) { kbuf0[i] = __ldcg(kbuf1 + i); vbuf0[i] = __ldcg(vbuf1 + i); }
+	}
 }
 
-// sorted data to buffer 0 if it ended up in buffer 1
-__global__ void __launch_bounds__(RS_THREADS) rs_finish_kernel(uint64_t* __restrict__ kbuf0, const uint64_t* __restrict__ kbuf1, uint64_t* __restrict__ vbuf0,
-	const uint64_t* __restrict__ vbuf1, const uint32_t* __restrict__ counts, uint32_t cap, const SortState* __restrict__ st)
-{
-	if (!st->cur) return;
-	const uint32_t n = min(counts[0], cap);
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { kbuf0[i] = kbuf1[i]; vbuf0[i] = vbuf1[i]; }
+int coop_grid_limit(lb200_ctx* ctx, const void* kernel, int threads, size_t smem, uint32_t* out) {
+	int per_sm = 0;
+	LB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+	if (per_sm < 1) { lb200_set_error(ctx, "cooperative kernel does not fit on an SM (%zu B of shared memory)", smem); return LB200_ERR_CUDA; }
+	*out = (uint32_t)per_sm * (uint32_t)ctx->sm_count;
+	return LB200_OK;
 }
 
 } // namespace
 
-// Stable LSD radix sort of n = min(*count_dev, cap) (key, value) pairs of 64 bits, all launches on `stream`, n read on the device.  The
-// sorted pairs end in buffer 0.  state: lb200_radix_sort_state_bytes() bytes, block_hist: 256 x blocks words.  (Also used by the device
-// re-binning of the culling structure, culling.cu.)
+// Stable LSD radix sort of n = min(*count_dev, cap) (key, value) pairs of 64 bits, one cooperative launch on `stream`, n read on the device.
+// The sorted pairs end in buffer 0.  state: lb200_radix_sort_state_bytes() bytes, block_hist: 256 x blocks words; at most `blocks` blocks
+// are launched.  (Also used by the device re-binning of the culling structure, culling.cu.)
 size_t lb200_radix_sort_state_bytes() { return sizeof(SortState); }
 
 int lb200_radix_sort_pairs(lb200_ctx* ctx, cudaStream_t s, uint64_t* keys0, uint64_t* keys1, uint64_t* values0, uint64_t* values1, const uint32_t* count_dev, uint32_t cap,
 	void* state, uint32_t* block_hist, uint32_t blocks)
 {
+	static uint32_t limit = 0; // blocks of radix_sort_kernel that are co-resident (one device kind per process)
+	if (!limit) { const int rc = coop_grid_limit(ctx, (const void*)radix_sort_kernel, RS_THREADS, 0, &limit); if (rc) return rc; }
 	SortState* st = (SortState*)state;
 	LB200_CUDA(ctx, cudaMemsetAsync(st, 0, sizeof(SortState), s));
-	rs_global_hist_kernel<<<blocks, RS_THREADS, 0, s>>>(keys0, count_dev, cap, st);
-	LB200_CHECK_LAUNCH(ctx);
-	for (int pass = 0; pass < RS_PASSES; ++pass) {
-		rs_block_hist_kernel<<<blocks, RS_THREADS, 0, s>>>(pass, keys0, keys1, count_dev, cap, st, block_hist);
-		LB200_CHECK_LAUNCH(ctx);
-		rs_scan_kernel<<<256, 32, 0, s>>>(pass, count_dev, cap, st, block_hist, blocks);
-		LB200_CHECK_LAUNCH(ctx);
-		rs_scatter_kernel<<<blocks, RS_THREADS, 0, s>>>(pass, keys0, keys1, values0, values1, count_dev, cap, st, block_hist);
-		LB200_CHECK_LAUNCH(ctx);
-	}
-	rs_finish_kernel<<<blocks, RS_THREADS, 0, s>>>(keys0, keys1, values0, values1, count_dev, cap, st);
+	uint32_t grid = std::max(1u, std::min(std::min(limit, blocks), (cap + RS_TILE - 1) / RS_TILE));
+	void* args[] = {&keys0, &keys1, &values0, &values1, &count_dev, &cap, &st, &block_hist};
+	LB200_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)radix_sort_kernel, dim3(grid), dim3(RS_THREADS), args, 0, s));
 	LB200_CHECK_LAUNCH(ctx);
 	return LB200_OK;
 }
@@ -493,22 +569,35 @@ struct lb200_sortkeys {
 	uint32_t max_entities = 0, max_groups = 0;
 	uint32_t cap_keys = 0, cap_recs = 0;
 	// inputs
-	lb200_transform* d_transforms = nullptr; // owned copy (set_transforms) ...
-	const lb200_transform* transforms = nullptr; // ... or the caller's device array
-	uint32_t* d_model_of = nullptr; float* d_lod = nullptr; uint8_t* d_flags = nullptr; uint32_t* d_pose_frame = nullptr;
+	SkEntity* d_ent = nullptr;         // one 64-byte record per entity (transform, model / flags, lod and pose-frame state)
+	bool have_transforms = false;
 	uint32_t* d_decal_sort_key = nullptr; uint8_t* d_decal_layer = nullptr;
 	lb200_sk_model* d_models = nullptr; lb200_sk_mesh* d_meshes = nullptr; uint32_t n_models = 0, n_meshes = 0;
+	uint8_t* d_group_layer = nullptr;  // layer of the mesh material a sort key (= auto-instancer group) belongs to
 	// outputs
 	uint64_t *d_keys[2] = {}, *d_values[2] = {};
 	uint32_t* d_counts = nullptr; uint32_t* h_counts = nullptr; // pinned
-	uint32_t *d_group_count = nullptr, *d_group_offset = nullptr; uint8_t* d_group_layer = nullptr;
-	uint64_t* d_rec_value = nullptr; uint2* d_rec_group_rank = nullptr;
+	uint32_t *d_group_count = nullptr, *d_group_offset = nullptr, *d_group_cursor = nullptr;
 	uint64_t* d_group_renderables = nullptr; float4* d_instance_data = nullptr;
-	uint32_t *d_pose_list = nullptr, *d_dirty_list = nullptr;
+	uint32_t *d_pose_list = nullptr, *d_dirty_list = nullptr, *d_stash = nullptr;
+	float* d_lod = nullptr; uint32_t* d_pose_frame = nullptr; // unpacked on request (lb200_sortkeys_device_outputs)
+	GridBar* d_bar = nullptr;
 	SortState* d_sort_state = nullptr; uint32_t* d_block_hist = nullptr;
 	uint32_t sort_blocks = 0;
 	uint32_t last_groups = 0;
+	uint32_t keys_grid_limit[2] = {0, 0}; // co-resident blocks of create_keys_kernel: group counters in shared memory / in HBM
 };
+
+namespace {
+// host array -> temporary device buffer on the context stream (setters are not on the per-frame path)
+template <typename T> int upload_temp(lb200_ctx* ctx, const T* host, size_t n, T** dev) {
+	*dev = nullptr;
+	if (!host) return LB200_OK;
+	LB200_CUDA(ctx, cudaMalloc(dev, sizeof(T) * n));
+	LB200_CUDA(ctx, cudaMemcpyAsync(*dev, host, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+	return LB200_OK;
+}
+} // namespace
 
 extern "C" {
 
@@ -520,15 +609,11 @@ int lb200_sortkeys_create(lb200_ctx* ctx, uint32_t max_entities, uint32_t max_gr
 	sk->ctx = ctx; sk->max_entities = max_entities; sk->max_groups = max_groups;
 	sk->cap_keys = max_keys ? max_keys : max_entities; sk->cap_recs = max_instances ? max_instances : max_entities;
 	const size_t E = max_entities;
-	LB200_CUDA(ctx, cudaMalloc(&sk->d_model_of, sizeof(uint32_t) * E));
-	LB200_CUDA(ctx, cudaMalloc(&sk->d_lod, sizeof(float) * E));
-	LB200_CUDA(ctx, cudaMalloc(&sk->d_flags, E));
-	LB200_CUDA(ctx, cudaMalloc(&sk->d_pose_frame, sizeof(uint32_t) * E));
+	LB200_CUDA(ctx, cudaMalloc(&sk->d_ent, sizeof(SkEntity) * E));
+	ent_init_kernel<<<(uint32_t)((E + 255) / 256), 256, 0, ctx->stream>>>(sk->d_ent, max_entities);
+	LB200_CHECK_LAUNCH(ctx);
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_decal_sort_key, sizeof(uint32_t) * E));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_decal_layer, E));
-	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_model_of, 0, sizeof(uint32_t) * E, ctx->stream));
-	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_flags, 0, E, ctx->stream));
-	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_pose_frame, 0xff, sizeof(uint32_t) * E, ctx->stream)); // 0xffffffff marks "never" (pipeline.cpp:3814)
 	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_decal_sort_key, 0, sizeof(uint32_t) * E, ctx->stream));
 	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_decal_layer, 0, E, ctx->stream));
 	for (int b = 0; b < 2; ++b) {
@@ -539,16 +624,20 @@ int lb200_sortkeys_create(lb200_ctx* ctx, uint32_t max_entities, uint32_t max_gr
 	LB200_CUDA(ctx, cudaHostAlloc(&sk->h_counts, sizeof(uint32_t) * CNT_WORDS, cudaHostAllocDefault));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_group_count, sizeof(uint32_t) * max_groups));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_group_offset, sizeof(uint32_t) * max_groups));
+	LB200_CUDA(ctx, cudaMalloc(&sk->d_group_cursor, sizeof(uint32_t) * max_groups));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_group_layer, max_groups));
-	LB200_CUDA(ctx, cudaMalloc(&sk->d_rec_value, sizeof(uint64_t) * sk->cap_recs));
-	LB200_CUDA(ctx, cudaMalloc(&sk->d_rec_group_rank, sizeof(uint2) * sk->cap_recs));
+	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_group_layer, 0, max_groups, ctx->stream));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_group_renderables, sizeof(uint64_t) * sk->cap_recs));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_instance_data, 48 * (size_t)sk->cap_recs));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_pose_list, sizeof(uint32_t) * E));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_dirty_list, sizeof(uint32_t) * E));
+	LB200_CUDA(ctx, cudaMalloc(&sk->d_stash, sizeof(uint32_t) * E));
+	LB200_CUDA(ctx, cudaMalloc(&sk->d_bar, sizeof(GridBar)));
+	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_bar, 0, sizeof(GridBar), ctx->stream));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_sort_state, sizeof(SortState)));
-	sk->sort_blocks = (uint32_t)ctx->sm_count * 4;
+	sk->sort_blocks = (uint32_t)ctx->sm_count * 2;
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_block_hist, sizeof(uint32_t) * 256 * sk->sort_blocks));
+	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	*out = sk;
 	return LB200_OK;
 }
@@ -557,12 +646,12 @@ void lb200_sortkeys_destroy(lb200_sortkeys* sk) {
 	if (!sk) return;
 	cudaSetDevice(sk->ctx->device);
 	cudaStreamSynchronize(sk->ctx->stream);
-	cudaFree(sk->d_transforms); cudaFree(sk->d_model_of); cudaFree(sk->d_lod); cudaFree(sk->d_flags); cudaFree(sk->d_pose_frame);
-	cudaFree(sk->d_decal_sort_key); cudaFree(sk->d_decal_layer); cudaFree(sk->d_models); cudaFree(sk->d_meshes);
+	cudaFree(sk->d_ent); cudaFree(sk->d_decal_sort_key); cudaFree(sk->d_decal_layer); cudaFree(sk->d_models); cudaFree(sk->d_meshes); cudaFree(sk->d_group_layer);
 	for (int b = 0; b < 2; ++b) { cudaFree(sk->d_keys[b]); cudaFree(sk->d_values[b]); }
 	cudaFree(sk->d_counts); if (sk->h_counts) cudaFreeHost(sk->h_counts);
-	cudaFree(sk->d_group_count); cudaFree(sk->d_group_offset); cudaFree(sk->d_group_layer); cudaFree(sk->d_rec_value); cudaFree(sk->d_rec_group_rank);
-	cudaFree(sk->d_group_renderables); cudaFree(sk->d_instance_data); cudaFree(sk->d_pose_list); cudaFree(sk->d_dirty_list);
+	cudaFree(sk->d_group_count); cudaFree(sk->d_group_offset); cudaFree(sk->d_group_cursor);
+	cudaFree(sk->d_group_renderables); cudaFree(sk->d_instance_data); cudaFree(sk->d_pose_list); cudaFree(sk->d_dirty_list); cudaFree(sk->d_stash);
+	cudaFree(sk->d_lod); cudaFree(sk->d_pose_frame); cudaFree(sk->d_bar);
 	cudaFree(sk->d_sort_state); cudaFree(sk->d_block_hist);
 	delete sk;
 }
@@ -570,6 +659,7 @@ void lb200_sortkeys_destroy(lb200_sortkeys* sk) {
 int lb200_sortkeys_set_models(lb200_sortkeys* sk, const lb200_sk_model* models, uint32_t n_models, const lb200_sk_mesh* meshes, uint32_t n_meshes) {
 	if (!sk || !models || !meshes || !n_models || !n_meshes) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = sk->ctx;
+	if (n_models > CODE_MODEL_MASK + 1u) { lb200_set_error(ctx, "%u models: the entity record keeps 24 bits of model index", n_models); return LB200_ERR_INVALID; }
 	for (uint32_t i = 0; i < n_meshes; ++i) if (meshes[i].sort_key >= sk->max_groups) { lb200_set_error(ctx, "mesh %u: sort key %u >= max_groups %u", i, meshes[i].sort_key, sk->max_groups); return LB200_ERR_INVALID; }
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	cudaFree(sk->d_models); cudaFree(sk->d_meshes);
@@ -578,40 +668,76 @@ int lb200_sortkeys_set_models(lb200_sortkeys* sk, const lb200_sk_model* models, 
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_meshes, sizeof(lb200_sk_mesh) * n_meshes));
 	LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_models, models, sizeof(lb200_sk_model) * n_models, cudaMemcpyHostToDevice, ctx->stream));
 	LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_meshes, meshes, sizeof(lb200_sk_mesh) * n_meshes, cudaMemcpyHostToDevice, ctx->stream));
-	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	// a sort key stands for one (mesh, material) pair (RenderModule::computeSortKey): the layer a group's key is bucketed by (:3958-3969)
+	// is that material's, the same for every instance of the group
+	uint8_t* layer = new (std::nothrow) uint8_t[sk->max_groups];
+	if (!layer) return LB200_ERR_CUDA;
+	memset(layer, 0, sk->max_groups);
+	for (uint32_t i = 0; i < n_meshes; ++i) layer[meshes[i].sort_key] = meshes[i].layer;
+	const cudaError_t e = cudaMemcpyAsync(sk->d_group_layer, layer, sk->max_groups, cudaMemcpyHostToDevice, ctx->stream);
+	cudaStreamSynchronize(ctx->stream);
+	delete[] layer;
+	LB200_CUDA(ctx, e);
 	sk->n_models = n_models; sk->n_meshes = n_meshes;
 	return LB200_OK;
 }
 
-// per-entity state, arrays indexed by entity id (n <= max_entities); null pointers leave that array as it is
+// per-entity state, arrays indexed by entity id (n <= max_entities); null pointers leave that field as it is
 int lb200_sortkeys_set_instances(lb200_sortkeys* sk, uint32_t n, const uint32_t* model_of, const float* lod, const uint8_t* flags, const uint32_t* pose_frame,
 	const uint32_t* decal_sort_key, const uint8_t* decal_layer)
 {
 	if (!sk || n > sk->max_entities) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = sk->ctx;
-	if (model_of) LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_model_of, model_of, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-	if (lod) LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_lod, lod, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
-	if (flags) LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_flags, flags, n, cudaMemcpyHostToDevice, ctx->stream));
-	if (pose_frame) LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_pose_frame, pose_frame, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-	if (decal_sort_key) LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_decal_sort_key, decal_sort_key, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-	if (decal_layer) LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_decal_layer, decal_layer, n, cudaMemcpyHostToDevice, ctx->stream));
-	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (!n) return LB200_OK;
+	uint32_t *t_model = nullptr, *t_pose = nullptr; float* t_lod = nullptr; uint8_t* t_flags = nullptr;
+	int rc = upload_temp(ctx, model_of, n, &t_model);
+	if (!rc) rc = upload_temp(ctx, lod, n, &t_lod);
+	if (!rc) rc = upload_temp(ctx, flags, n, &t_flags);
+	if (!rc) rc = upload_temp(ctx, pose_frame, n, &t_pose);
+	if (!rc && (t_model || t_lod || t_flags || t_pose)) {
+		ent_pack_fields_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sk->d_ent, n, t_model, t_lod, t_flags, t_pose);
+		ctx->launches.fetch_add(1, std::memory_order_relaxed);
+		if (cudaGetLastError() != cudaSuccess) { lb200_set_error(ctx, "ent_pack_fields_kernel launch failed"); rc = LB200_ERR_CUDA; }
+	}
+	cudaError_t e = cudaSuccess;
+	if (!rc && decal_sort_key) e = cudaMemcpyAsync(sk->d_decal_sort_key, decal_sort_key, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+	if (!rc && e == cudaSuccess && decal_layer) e = cudaMemcpyAsync(sk->d_decal_layer, decal_layer, n, cudaMemcpyHostToDevice, ctx->stream);
+	const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+	cudaFree(t_model); cudaFree(t_lod); cudaFree(t_flags); cudaFree(t_pose);
+	if (rc) return rc;
+	LB200_CUDA(ctx, e);
+	LB200_CUDA(ctx, e2);
 	return LB200_OK;
 }
 
 int lb200_sortkeys_set_transforms(lb200_sortkeys* sk, const lb200_transform* transforms, uint32_t n) {
 	if (!sk || !transforms || n > sk->max_entities) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = sk->ctx;
-	if (!sk->d_transforms) LB200_CUDA(ctx, cudaMalloc(&sk->d_transforms, sizeof(lb200_transform) * (size_t)sk->max_entities));
-	LB200_CUDA(ctx, cudaMemcpyAsync(sk->d_transforms, transforms, sizeof(lb200_transform) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	sk->transforms = sk->d_transforms;
+	lb200_transform* tmp = nullptr;
+	int rc = upload_temp(ctx, transforms, n, &tmp);
+	if (!rc && n) {
+		ent_pack_transforms_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sk->d_ent, tmp, n);
+		ctx->launches.fetch_add(1, std::memory_order_relaxed);
+		if (cudaGetLastError() != cudaSuccess) { lb200_set_error(ctx, "ent_pack_transforms_kernel launch failed"); rc = LB200_ERR_CUDA; }
+	}
+	const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(tmp);
+	if (rc) return rc;
+	LB200_CUDA(ctx, e);
+	sk->have_transforms = true;
 	return LB200_OK;
 }
 
-int lb200_sortkeys_set_transforms_device(lb200_sortkeys* sk, const lb200_transform* dev_transforms) {
-	if (!sk || !dev_transforms) return LB200_ERR_INVALID;
-	sk->transforms = dev_transforms;
+// World::getTransforms() already in HBM (e.g. lb200_hierarchy's globals): packed into the entity records on the context stream, now —
+// call again after the array changed.
+int lb200_sortkeys_set_transforms_device(lb200_sortkeys* sk, const lb200_transform* dev_transforms, uint32_t n) {
+	if (!sk || !dev_transforms || n > sk->max_entities) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = sk->ctx;
+	if (n) {
+		ent_pack_transforms_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sk->d_ent, dev_transforms, n);
+		LB200_CHECK_LAUNCH(ctx);
+	}
+	sk->have_transforms = true;
 	return LB200_OK;
 }
 
@@ -619,33 +745,34 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 	if (!sk || !cs || !view) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = sk->ctx;
 	lb200_range range("create keys"); // pipeline.cpp:3818
-	if (!sk->transforms || !sk->d_models) { lb200_set_error(ctx, "create_keys needs set_models and set_transforms first"); return LB200_ERR_STATE; }
+	if (!sk->have_transforms || !sk->d_models) { lb200_set_error(ctx, "create_keys needs set_models and set_transforms first"); return LB200_ERR_STATE; }
 	if (view->max_sort_key >= sk->max_groups) { lb200_set_error(ctx, "view.max_sort_key %u >= max_groups %u", view->max_sort_key, sk->max_groups); return LB200_ERR_INVALID; }
 	const uint32_t *visible = nullptr, *cull_counters = nullptr, *type_base = nullptr, *type_counts = nullptr;
 	int rc = lb200_culling_internal_last(cs, &visible, &cull_counters, &type_base, &type_counts);
 	if (rc) return rc;
 	cudaStream_t s = ctx->stream;
-	const uint32_t n_groups = view->max_sort_key + 1;
+	uint32_t n_groups = view->max_sort_key + 1;
 	sk->last_groups = n_groups;
 	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_counts, 0, sizeof(uint32_t) * CNT_WORDS, s));
 	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_group_count, 0, sizeof(uint32_t) * n_groups, s));
+	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_bar, 0, sizeof(GridBar), s));
 	EmitParams EP;
 	EP.view = *view;
 	for (int t = 0; t < 4; ++t) EP.type_base[t] = type_base[t];
 	EP.cap_keys = sk->cap_keys; EP.cap_recs = sk->cap_recs; EP.cap_pose = sk->max_entities; EP.cap_dirty = sk->max_entities;
+	const bool in_smem = n_groups <= SK_SMEM_GROUPS;
+	size_t smem = in_smem ? sizeof(uint32_t) * n_groups : 0;
+	uint32_t& limit = sk->keys_grid_limit[in_smem ? 0 : 1];
+	if (!limit) { // co-resident blocks with the largest group table this path can ask for, so that the number holds for every view
+		rc = coop_grid_limit(ctx, (const void*)create_keys_kernel, SK_THREADS, in_smem ? sizeof(uint32_t) * SK_SMEM_GROUPS : 0, &limit);
+		if (rc) return rc;
+	}
 	const uint32_t work = type_counts[RT_MESH] + type_counts[RT_DECAL] + type_counts[RT_CURVE_DECAL]; // upper bound of visible renderables
-	const uint32_t grid = std::max(1u, std::min((uint32_t)ctx->sm_count * 4u, (work + SK_THREADS - 1) / SK_THREADS));
-	EmitArgs EA = {sk->transforms, sk->d_model_of, sk->d_lod, sk->d_flags, sk->d_pose_frame, sk->d_decal_sort_key, sk->d_decal_layer, sk->d_models, sk->d_meshes,
-		sk->d_keys[0], sk->d_values[0], sk->d_counts, sk->d_group_count, sk->d_group_layer, sk->d_rec_value, sk->d_rec_group_rank, sk->d_pose_list, sk->d_dirty_list, nullptr};
-	emit_kernel<<<grid, SK_THREADS, n_groups <= SK_SMEM_GROUPS ? sizeof(uint32_t) * n_groups : 0, s>>>(EP, visible, cull_counters, EA, n_groups);
-	LB200_CHECK_LAUNCH(ctx);
-	GroupParams GP;
-	memcpy(GP.layer_to_bucket, view->layer_to_bucket, 256);
-	GP.n_groups = n_groups; GP.cap_keys = sk->cap_keys;
-	groups_kernel<<<1, 1024, 0, s>>>(GP, sk->d_group_count, sk->d_group_offset, sk->d_group_layer, sk->d_keys[0], sk->d_values[0], sk->d_counts);
-	LB200_CHECK_LAUNCH(ctx);
-	fill_kernel<<<grid, SK_THREADS, 0, s>>>(view->camera_pos[0], view->camera_pos[1], view->camera_pos[2], sk->cap_recs, sk->d_counts, sk->d_rec_value,
-		sk->d_rec_group_rank, sk->d_group_offset, sk->transforms, sk->d_model_of, sk->d_lod, sk->d_models, sk->d_meshes, sk->d_group_renderables, sk->d_instance_data);
+	uint32_t grid = std::max(1u, std::min(limit, (work + SK_THREADS - 1) / SK_THREADS));
+	EmitArgs EA = {sk->d_ent, sk->d_decal_sort_key, sk->d_decal_layer, sk->d_models, sk->d_meshes, sk->d_keys[0], sk->d_values[0], sk->d_counts,
+		sk->d_group_count, sk->d_group_offset, sk->d_group_cursor, sk->d_group_layer, sk->d_group_renderables, sk->d_instance_data, sk->d_pose_list, sk->d_dirty_list, sk->d_stash, sk->d_bar};
+	void* args[] = {&EP, &visible, &cull_counters, &EA, &n_groups};
+	LB200_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)create_keys_kernel, dim3(grid), dim3(SK_THREADS), args, smem, s));
 	LB200_CHECK_LAUNCH(ctx);
 	if (sort) {
 		lb200_range r2("radixSort"); // pipeline.cpp:4101
@@ -663,9 +790,17 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 	return LB200_OK;
 }
 
-// device pointers of the last create_keys (valid until the next one): sorted keys / values, group tables, instance data, lists
+// device pointers of the last create_keys (valid until the next one): sorted keys / values, group tables, instance data, lists; the
+// lod / pose-frame state is unpacked from the entity records into plain arrays for the caller (on the context stream)
 int lb200_sortkeys_device_outputs(lb200_sortkeys* sk, lb200_sk_outputs* out) {
 	if (!sk || !out) return LB200_ERR_INVALID;
+	lb200_ctx* ctx = sk->ctx;
+	if (!sk->d_lod) {
+		LB200_CUDA(ctx, cudaMalloc(&sk->d_lod, sizeof(float) * (size_t)sk->max_entities));
+		LB200_CUDA(ctx, cudaMalloc(&sk->d_pose_frame, sizeof(uint32_t) * (size_t)sk->max_entities));
+	}
+	ent_unpack_state_kernel<<<(sk->max_entities + 255) / 256, 256, 0, ctx->stream>>>(sk->d_ent, sk->max_entities, sk->d_lod, sk->d_pose_frame);
+	LB200_CHECK_LAUNCH(ctx);
 	out->keys = sk->d_keys[0]; out->values = sk->d_values[0]; out->group_count = sk->d_group_count; out->group_offset = sk->d_group_offset;
 	out->group_renderables = sk->d_group_renderables; out->instance_data = sk->d_instance_data; out->pose_list = sk->d_pose_list; out->dirty_list = sk->d_dirty_list;
 	out->lod = sk->d_lod; out->pose_frame = sk->d_pose_frame;

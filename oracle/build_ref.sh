@@ -129,9 +129,29 @@ PRODUCT_DIR="$(cd "$HERE/../lumixengine_b200" && pwd)"
 if [ -f "$PRODUCT_DIR/liblumix_b200.so" ]; then
 	SHIM_OBJS=""
 	for o in $OBJS; do case "$o" in */core_*.o) SHIM_OBJS="$SHIM_OBJS $o";; esac; done # job system, allocators, PageAllocator, math, geometry, log ...
+	# the World patch as INTEGRATION.md section 2 describes it, applied to the overlay copy of the reference's own world.h / world.cpp:
+	# declarations into `struct World`, host/world_b200.inl appended to world.cpp, one line in ~World
+	cp "$REF/src/engine/world.cpp" "$S/engine/world.cpp"
+	python3 - "$S/engine" "$PRODUCT_DIR/host" <<'PYEOF'
+import sys
+eng, host = sys.argv[1], sys.argv[2]
+wh = open(eng + "/world.h").read()
+anchor = "private:\n\tvoid transformEntity(EntityRef entity, bool update_local);"
+assert anchor in wh, "world.h changed: INTEGRATION.md section 2 needs another anchor"
+wh = wh.replace(anchor, open(host + "/world_b200_decl.inl").read() + anchor).replace("namespace Lumix {", "struct lb200_ctx; // include/lumix_b200.h\nnamespace Lumix {", 1)
+open(eng + "/world.h", "w").write(wh)
+wc = open(eng + "/world.cpp").read()
+dtor = "World::~World() {\n"
+assert dtor in wc
+wc = wc.replace(dtor, dtor + "\tdestroyHierarchyB200();\n", 1) + "\n" + open(host + "/world_b200.inl").read()
+open(eng + "/world.cpp", "w").write(wc)
+PYEOF
 	if $CXX $FL -I"$HERE/../include" -c "$PRODUCT_DIR/host/culling_system_b200.cpp" -o "$TMP/obj/shim.o" 2> "$TMP/shim.log" \
 		&& $CXX $FL -c "$HERE/ref/ref_engine_shim_harness.cpp" -o "$TMP/obj/shim_harness.o" 2>> "$TMP/shim.log" \
+		&& $CXX $FL -I"$HERE/../include" -c "$S/engine/world.cpp" -o "$TMP/obj/world_b200.o" 2>> "$TMP/shim.log" \
+		&& $CXX $FL -I"$HERE/../include" -c "$HERE/ref/ref_world_shim_harness.cpp" -o "$TMP/obj/world_harness.o" 2>> "$TMP/shim.log" \
 		&& $CXX -shared -o "$OUT/libengine_shim_b200.so" $SHIM_OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/shim.o" "$TMP/obj/shim_harness.o" \
+			"$TMP/obj/world_b200.o" "$TMP/obj/world_harness.o" \
 			-L"$PRODUCT_DIR" -llumix_b200 -Wl,-rpath,'$ORIGIN/../../lumixengine_b200' -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL 2>> "$TMP/shim.log"; then
 		echo "built $OUT/libengine_shim_b200.so"
 	else

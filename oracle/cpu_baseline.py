@@ -78,6 +78,48 @@ def bench_cull(n, steps, warmup, workers, scene_name):
     return out
 
 
+def bench_sortkeys(n, steps, seed_offset=40):
+    """The stage behind the cull on the host: PipelineImpl::createSortKeys on the visible list of the C2 cull (C restatement, one worker:
+    pipeline.cpp cannot be compiled here — kind "port") and PipelineImpl::radixSort (the reference's own function cut out of pipeline.cpp at
+    build time when oracle/_ref exists, on its job system; else the restatement).  Same inputs as bench.py's e2e step."""
+    from lumixengine_b200 import scenes
+    from oracle import pyoracle as po
+    po.build()
+    scene = scenes.c2_scene(n)
+    fa = scenes.c2_frustum_args()
+    f = po.frustum_perspective(fa["position"], fa["direction"], fa["up"], fa["fov"], fa["ratio"], fa["near"], fa["far"])
+    if po.ref_available():
+        rc = po.RefCulling(workers=1)
+        rc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+        ids, tys, _ = rc.cull(f, cap=n)
+    else:
+        oc = po.OracleCulling()
+        oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+        ids, tys, _ = oc.cull(f)
+    sk = scenes.sortkey_setup(n, scene["types"], scene["pos"], seed=seed_offset)
+    view = np.zeros(1, po.SK_VIEW_DTYPE)
+    from lumixengine_b200 import sortkeys as skm  # host-side view packing only (numpy)
+    keys_s, sort_s, nk, ni = [], [], 0, 0
+    use_ref_sort = po.ref_available() and hasattr(po.ref(), "ref_radix_sort")
+    for k in range(steps):
+        view = skm.make_view(fa["position"], fa["position"], 1.0 / 60.0, 1.0, 100 + k, False, sk["max_sort_key"], sk["layer_to_bucket"], sk["depth_sorted_buckets"])
+        t0 = time.perf_counter()
+        out = po.create_sort_keys(ids, tys, sk["transforms"], sk["model_of"], sk["lod"], sk["flags"], sk["pose_frame"], sk["decal_sort_key"], sk["decal_layer"],
+                                  sk["models"], sk["meshes"], view, sort=False)
+        t1 = time.perf_counter()
+        if use_ref_sort:
+            po.ref_radix_sort(out["keys"], out["values"], workers=2)
+        else:
+            po.radix_sort(out["keys"], out["values"])
+        t2 = time.perf_counter()
+        keys_s.append(t1 - t0)
+        sort_s.append(t2 - t1)
+        nk, ni = len(out["keys"]), len(out["group_renderables"])
+    return dict(kind="port", cores=1, n=n, visible=int(len(ids)), n_keys=nk, n_instances=ni, create_keys_median_s=float(np.median(keys_s)), sort_median_s=float(np.median(sort_s)),
+                median_s=float(np.median(np.array(keys_s) + np.array(sort_s))), radix_sort="reference (pipeline.cpp:4100-4144 cut out at build time)" if use_ref_sort else "port",
+                sample=f"{steps} x (createSortKeys over the {len(ids)} visible renderables of the C2 cull, one worker, + radixSort of the keys); includes the Python-side output allocation")
+
+
 def bench_propagate(n, steps):
     from lumixengine_b200 import scenes
     from oracle import pyoracle as po
@@ -169,6 +211,8 @@ def main():
     a = ap.parse_args()
     if a.workload == "cull":
         res = bench_cull(a.n, a.steps, a.warmup, a.workers, a.scene)
+    elif a.workload == "sortkeys":
+        res = bench_sortkeys(a.n, a.steps)
     elif a.workload == "propagate":
         res = bench_propagate(a.n, a.steps)
     elif a.workload == "c3chain":

@@ -85,3 +85,52 @@ def test_cull_through_the_engine_vtable_from_job_fibers(shim, oracle):
     check(-1)
     os.write(2, b"[test] all views checked\n")
     L.shim_destroy(C.c_void_p(h))
+
+
+def _wshim(L):
+    L.wshim_run.restype = C.c_int
+    return L.wshim_run
+
+
+@pytest.mark.parametrize("n,depth,fanout,reparent", [(20_000, 6, 3, 0), (60_000, 8, 4, 1)])
+def test_world_patch_runs_inside_the_reference_world(shim, oracle, n, depth, fanout, reparent):
+    """host/world_b200.inl inside the reference's own World (world.cpp + the patch, compiled by oracle/build_ref.sh): root moves through
+    World::setTransformsDeferredB200 + World::propagateHierarchyB200 (GPU) against the same moves through World::setTransform — the
+    reference recursion transformEntity (world.cpp:255-282) — in a second World of the same process.  Every Transform bit for bit, and the
+    `transformed` delegates (world.h:139, what RenderModule::onModelInstanceMoved hangs on) fire for the same entities the same number of
+    times."""
+    from lumixengine_b200.hierarchy import TRANSFORM_DTYPE
+    parents, locals_, roots = scenes.hierarchy_forest(n, depth, fanout, seed=21 + depth)
+    rng = np.random.default_rng(5)
+    listens = (rng.random(n) < 0.7).astype(np.uint8)
+    root_ids = np.nonzero(parents < 0)[0].astype(np.uint32)
+    moved = rng.choice(root_ids, max(1, len(root_ids) // 2), replace=False).astype(np.uint32)  # half of the roots move, the other trees must stay put
+    rounds = 3
+    vals = np.zeros((rounds, len(moved)), TRANSFORM_DTYPE)
+    for r in range(rounds):
+        vals[r]["pos"] = roots[moved]["pos"] + rng.normal(size=(len(moved), 3)) * 50.0
+        vals[r]["rot"] = scenes.random_unit_quats(rng, len(moved))
+        vals[r]["scale"] = (0.7 + 0.6 * rng.random((len(moved), 3))).astype(np.float32)
+    out_ref = np.zeros(n, TRANSFORM_DTYPE)
+    out_b = np.zeros(n, TRANSFORM_DTYPE)
+    calls_ref = np.zeros(n, np.uint32)
+    calls_b = np.zeros(n, np.uint32)
+    seconds = np.zeros(2)
+    world_locals = np.zeros(n, TRANSFORM_DTYPE)
+    rc = _wshim(shim)(_p(parents), _p(np.ascontiguousarray(locals_)), _p(np.ascontiguousarray(roots)), C.c_uint32(n), _p(listens),
+                      _p(moved), _p(np.ascontiguousarray(vals)), C.c_uint32(len(moved)), C.c_uint32(rounds), C.c_int(reparent),
+                      _p(out_ref), _p(out_b), _p(calls_ref), _p(calls_b), _p(seconds), _p(world_locals))
+    assert rc == 0
+    for field in ("pos", "rot", "scale"):
+        assert out_ref[field].tobytes() == out_b[field].tobytes(), "World::propagateHierarchyB200 left other transforms than World::transformEntity"
+    assert np.array_equal(calls_ref, calls_b), "the `transformed` delegates fired for other entities than under the reference recursion"
+    assert calls_ref.sum() > 0 and (calls_ref[listens == 0] == 0).all()
+    if not reparent:  # the reference World against the C restatement as well: same forest, last round's roots, and the local transforms as the
+        # World holds them (World::setLocalTransform recomputes the local from the composed global, world.cpp:704-712 + 267-270)
+        g = roots.copy()
+        g[moved] = vals[-1]
+        as_bytes = lambda a: np.ascontiguousarray(a).view(np.uint8).reshape(len(a), 56)
+        want = oracle.propagate(parents, as_bytes(world_locals), as_bytes(g)).view(TRANSFORM_DTYPE).reshape(-1)
+        for field in ("pos", "rot", "scale"):  # not the 4 padding bytes of the 56-byte Transform
+            assert want[field].tobytes() == out_ref[field].tobytes()
+    os.write(2, f"[test] world patch n={n}: reference recursion {seconds[0] * 1e3:.2f} ms, B200 path {seconds[1] * 1e3:.2f} ms (host time, {rounds} rounds)\n".encode())

@@ -54,6 +54,7 @@ def test_world_patch_compiles_inside_world_cpp():
         assert r.returncode == 0, r.stderr[-3000:]
         syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
         assert "Lumix::World::propagateHierarchyB200(lb200_ctx*, bool)" in syms
+        assert "Lumix::World::setTransformsDeferredB200(Lumix::EntityRef const*, Lumix::Transform const*, unsigned int)" in syms
         assert "Lumix::World::transformEntity(Lumix::EntityRef, bool)" in syms
         for f in ("lb200_hierarchy_create", "lb200_hierarchy_set_locals", "lb200_hierarchy_propagate", "lb200_hierarchy_get_globals"):
             assert f in syms  # unresolved here, provided by liblumix_b200.so

@@ -33,10 +33,14 @@ def _compare(got, exp, lod_exp, pf_exp, n_entities):
     assert np.array_equal(got["pose_frame"][:n_entities], pf_exp)
 
 
-@pytest.mark.parametrize("n,seed,is_shadow", [(60_000, 11, False), (25_000, 12, True)])
-def test_sort_keys_match_oracle_over_frames(ctx, oracle, n, seed, is_shadow):
+@pytest.mark.parametrize("n,seed,is_shadow,key_stride", [(60_000, 11, False, 1), (25_000, 12, True, 1), (40_000, 13, False, 131)])
+def test_sort_keys_match_oracle_over_frames(ctx, oracle, n, seed, is_shadow, key_stride):
     scene = scenes.cull_scene(n, (2500.0, 300.0, 2500.0), seed=seed, type_probs=(0.8, 0.08, 0.04, 0.08), big_fraction=0.002)
     sk = scenes.sortkey_setup(n, scene["types"], scene["pos"], seed=seed + 100)
+    if key_stride > 1:  # sparse sort keys: more auto-instancer groups than a block keeps in shared memory (8192) -> the group cursors live in HBM
+        sk["meshes"]["sort_key"] = sk["meshes"]["sort_key"] * key_stride + 7
+        sk["max_sort_key"] = int(sk["meshes"]["sort_key"].max()) + 3
+        assert sk["max_sort_key"] + 1 > 8192
     cs = lb.CullingSystem(ctx)
     cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
     oc = oracle.OracleCulling()
