@@ -279,6 +279,16 @@ LB200_API int lb200_sortkeys_set_transforms_device(lb200_sortkeys* sk, const lb2
 /* createSortKeys (+ radixSort if `sort`) for the last cull of `cs` on the context stream.  Asynchronous unless `want_counts`. */
 LB200_API int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb200_sk_view* view, int sort, int want_counts, lb200_sk_result* result);
 LB200_API int lb200_sortkeys_device_outputs(lb200_sortkeys* sk, lb200_sk_outputs* out);
+/* RenderModuleImpl::onModelInstanceMoved (src/renderer/render_module.cpp:1544-1554) for n instances whose new transforms lie in device memory:
+ * the transforms go into the entity records, ModelInstance::MOVED is set (createSortKeys then draws the instance as DRAW_MESH, pipeline.cpp
+ * :3904-3909) and the instance joins m_moved_instances once.  With dev_bounding_radius (per moved instance: Model::getOriginBoundingRadius)
+ * the spheres CullingSystem::set needs are written to dev_out_pos3 (3 doubles each) / dev_out_radius for lb200_culling_set_many_device. */
+LB200_API int lb200_sortkeys_move_device(lb200_sortkeys* sk, const int32_t* dev_entities, const lb200_transform* dev_transforms, uint32_t n, const float* dev_bounding_radius,
+                                         double* dev_out_pos3, float* dev_out_radius);
+/* RenderModuleImpl::endFrame (render_module.cpp:526-534): MOVED cleared and ModelInstance::prev_frame_transform taken for every instance moved
+ * since the last call; lb200_sortkeys_prev_transforms hands out the per-entity device array of those transforms. */
+LB200_API int lb200_sortkeys_end_frame(lb200_sortkeys* sk);
+LB200_API int lb200_sortkeys_prev_transforms(lb200_sortkeys* sk, const lb200_transform** dev_prev);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  NCCL is dlopen()ed; the unique id travels through the caller
@@ -462,6 +472,10 @@ LB200_API int lb200_animation_blend_pose(lb200_animation* a, const lb200_animati
  * Host arrays in, host transforms out (the engine then feeds them to World::setTransform / the batched propagate). */
 LB200_API int lb200_animation_bone_attachments(lb200_animation* a, uint32_t n, const uint32_t* instance, const uint32_t* bone, const float* relative7,
                                                const lb200_transform* parent_transforms, const float* original_scale3, lb200_transform* out_transforms);
+/* The same with every table in device memory and the transforms left there: the device-side chain pose -> attached entity transform ->
+ * lb200_sortkeys_move_device -> lb200_culling_set_many_device -> cull.  No index validation. */
+LB200_API int lb200_animation_bone_attachments_device(lb200_animation* a, uint32_t n, const uint32_t* dev_instance, const uint32_t* dev_bone, const float* dev_relative7,
+                                                      const lb200_transform* dev_parent_transforms, const float* dev_original_scale3, lb200_transform* dev_out_transforms);
 LB200_API int lb200_animation_get_times(lb200_animation* a, uint32_t first, uint32_t count, uint32_t* out_ticks);
 LB200_API int lb200_animation_get_skinned(lb200_animation* a, uint32_t first, uint32_t count, float* out_pos3);
 /* Checksum of the skinned vertex buffer computed on the device (sum of the raw u32 bit patterns, mod 2^64) —

@@ -372,6 +372,12 @@ class AnimationSystem:
         check(self.L.lb200_animation_bone_attachments(self.h, C.c_uint32(len(inst)), ptr(inst), ptr(bn), ptr(rel), ptr(par), ptr(sc), ptr(out)), self.ctx.h)
         return out
 
+    def boneAttachmentsDevice(self, n, dev_instance, dev_bone, dev_relative7, dev_parent_transforms, dev_original_scale3, dev_out_transforms):
+        """The same with every table in device memory (pointers as ints) and the transforms left there."""
+        from ._lib import vp
+        check(self.L.lb200_animation_bone_attachments_device(self.h, C.c_uint32(n), vp(dev_instance), vp(dev_bone), vp(dev_relative7), vp(dev_parent_transforms),
+                                                             vp(dev_original_scale3), vp(dev_out_transforms)), self.ctx.h)
+
     def computeRelative(self):
         """Pose::computeRelative (pose.cpp:136-146) of every instance's absolute pose (update with PALETTE_POSE first)."""
         check(self.L.lb200_animation_compute_relative(self.h), self.ctx.h)

@@ -956,6 +956,21 @@ int lb200_animation_bone_attachments(lb200_animation* a, uint32_t n, const uint3
 	return LB200_OK;
 }
 
+// The same with every table already in HBM and the result left there (pose -> entity transform -> re-binning -> cull without the
+// host in between): out feeds lb200_sortkeys_move_device / lb200_culling_set_many_device.  Indices are the caller's responsibility here.
+int lb200_animation_bone_attachments_device(lb200_animation* a, uint32_t n, const uint32_t* dev_instance, const uint32_t* dev_bone, const float* dev_relative7,
+	const lb200_transform* dev_parent_transforms, const float* dev_original_scale3, lb200_transform* dev_out_transforms)
+{
+	if (!a || !dev_instance || !dev_bone || !dev_relative7 || !dev_parent_transforms || !dev_original_scale3 || !dev_out_transforms) return LB200_ERR_INVALID;
+	if (!n) return LB200_OK;
+	lb200_ctx* ctx = a->ctx;
+	if (!a->d_pos || !a->n_instances) { lb200_set_error(ctx, "bone_attachments needs absolute poses (update with LB200_PALETTE_POSE)"); return LB200_ERR_STATE; }
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	bone_attachments_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a->d_pos, a->d_rot, a->bone_count, dev_instance, dev_bone, dev_relative7, dev_parent_transforms, dev_original_scale3, n, dev_out_transforms);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
 int lb200_animation_compute_relative(lb200_animation* a) {
 	if (!a) return LB200_ERR_INVALID;
 	lb200_ctx* ctx = a->ctx;

@@ -199,7 +199,8 @@ struct lb200_hierarchy {
 	std::vector<uint32_t> level_start; // size depth + 1
 	uint32_t* d_order = nullptr;       // level position -> caller node index
 	uint32_t* d_pos_of_node = nullptr; // caller node index -> level position
-	uint8_t* d_subset = nullptr; uint8_t* h_subset = nullptr; size_t subset_cap = 0; // staging of set_subset: [node ids][transforms], pinned + device
+	// staging of set_subset: [node ids][transforms], pinned + device, two of each used in turn: an upload waits only for the upload before last
+	uint8_t* d_subset[2] = {nullptr, nullptr}; uint8_t* h_subset[2] = {nullptr, nullptr}; size_t subset_cap = 0; cudaEvent_t subset_done[2] = {nullptr, nullptr}; uint32_t subset_turn = 0;
 	int* d_parent = nullptr;           // level position -> parent's level position
 	SoaTransforms L, G;
 	lb200_transform* d_stage = nullptr; // n Transforms (API boundary)
@@ -307,7 +308,7 @@ void lb200_hierarchy_destroy(lb200_hierarchy* h) {
 	if (!h) return;
 	cudaSetDevice(h->ctx->device);
 	cudaStreamSynchronize(h->ctx->stream);
-	cudaFree(h->d_pos_of_node); cudaFree(h->d_subset); if (h->h_subset) cudaFreeHost(h->h_subset);
+	cudaFree(h->d_pos_of_node); for (int b = 0; b < 2; ++b) { cudaFree(h->d_subset[b]); if (h->h_subset[b]) cudaFreeHost(h->h_subset[b]); if (h->subset_done[b]) cudaEventDestroy(h->subset_done[b]); }
 	cudaFree(h->d_order); cudaFree(h->d_parent); cudaFree(h->d_stage); cudaFree(h->d_matrices); cudaFree(h->d_radius_in); cudaFree(h->d_sphere_pos); cudaFree(h->d_sphere_radius);
 	freeSoa(h->L); freeSoa(h->G);
 	delete h;
@@ -403,20 +404,28 @@ int lb200_hierarchy_set_subset(lb200_hierarchy* h, const uint32_t* nodes, const 
 	const size_t bytes = (sizeof(uint32_t) + sizeof(lb200_transform)) * (size_t)count + 16;
 	if (h->subset_cap < bytes) {
 		LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(h->d_subset); if (h->h_subset) cudaFreeHost(h->h_subset);
-		h->d_subset = nullptr; h->h_subset = nullptr;
 		size_t cap = h->subset_cap ? h->subset_cap : 4096;
 		while (cap < bytes) cap *= 2;
-		LB200_CUDA(ctx, cudaMalloc(&h->d_subset, cap));
-		LB200_CUDA(ctx, cudaHostAlloc(&h->h_subset, cap, cudaHostAllocDefault));
+		for (int b = 0; b < 2; ++b) {
+			cudaFree(h->d_subset[b]); if (h->h_subset[b]) cudaFreeHost(h->h_subset[b]);
+			h->d_subset[b] = nullptr; h->h_subset[b] = nullptr;
+			LB200_CUDA(ctx, cudaMalloc(&h->d_subset[b], cap));
+			LB200_CUDA(ctx, cudaHostAlloc(&h->h_subset[b], cap, cudaHostAllocDefault));
+			if (!h->subset_done[b]) LB200_CUDA(ctx, cudaEventCreateWithFlags(&h->subset_done[b], cudaEventDisableTiming));
+			LB200_CUDA(ctx, cudaEventRecord(h->subset_done[b], ctx->stream));
+		}
 		h->subset_cap = cap;
 	}
-	else LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the previous upload may still read the pinned staging
+	const uint32_t turn = h->subset_turn++ & 1u;
+	LB200_CUDA(ctx, cudaEventSynchronize(h->subset_done[turn])); // the upload before last has left this pair of buffers (no wait for the frame in flight)
+	uint8_t* hs = h->h_subset[turn];
+	uint8_t* ds = h->d_subset[turn];
 	const size_t tr_off = (sizeof(uint32_t) * (size_t)count + 15) & ~(size_t)15;
-	memcpy(h->h_subset, nodes, sizeof(uint32_t) * (size_t)count);
-	memcpy(h->h_subset + tr_off, values, sizeof(lb200_transform) * (size_t)count);
-	LB200_CUDA(ctx, cudaMemcpyAsync(h->d_subset, h->h_subset, tr_off + sizeof(lb200_transform) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-	scatter_transforms_kernel<<<(count + HT - 1) / HT, HT, 0, ctx->stream>>>((const uint32_t*)h->d_subset, (const lb200_transform*)(h->d_subset + tr_off), count, h->d_pos_of_node, globals ? h->G : h->L);
+	memcpy(hs, nodes, sizeof(uint32_t) * (size_t)count);
+	memcpy(hs + tr_off, values, sizeof(lb200_transform) * (size_t)count);
+	LB200_CUDA(ctx, cudaMemcpyAsync(ds, hs, tr_off + sizeof(lb200_transform) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+	scatter_transforms_kernel<<<(count + HT - 1) / HT, HT, 0, ctx->stream>>>((const uint32_t*)ds, (const lb200_transform*)(ds + tr_off), count, h->d_pos_of_node, globals ? h->G : h->L);
+	LB200_CUDA(ctx, cudaEventRecord(h->subset_done[turn], ctx->stream));
 	LB200_CHECK_LAUNCH(ctx);
 	return LB200_OK;
 }

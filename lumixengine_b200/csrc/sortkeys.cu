@@ -31,6 +31,7 @@
 #include "lb200_math.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <new>
 
 namespace {
@@ -137,6 +138,23 @@ constexpr uint32_t CODE_TWO = 1u << 27, CODE_MOVED = 1u << 28, CODE_POSE = 1u <<
 
 struct Counts { uint32_t k, r, p; };
 
+// What one mesh of a MESH renderable turns into (create_key, :3883-3924), as flags instead of branches: lanes of a warp hold different
+// models, so every branch here used to run with a handful of lanes (round-2 profile: 11.8 active threads per instruction on average).
+//   skinned                     -> key (mesh sort key) + the instance joins the pose list once per frame
+//   MOVED and not a shadow view -> key (mesh sort key)
+//   bucket < 0xff               -> an instance of the mesh's auto-instancer group
+//   bucket < 0xffff             -> depth-sorted key
+struct MeshKind { bool skinned, key, inst, depth; };
+__device__ __forceinline__ MeshKind mesh_kind(const lb200_sk_mesh& mm, uint32_t bucket, bool moved_not_shadow) {
+	MeshKind k;
+	k.skinned = mm.skinned != 0;
+	const bool plain = k.skinned || moved_not_shadow;
+	k.inst = !plain && bucket < 0xffu;
+	k.depth = !plain && bucket >= 0xffu && bucket < 0xffffu;
+	k.key = plain || k.depth;
+	return k;
+}
+
 // MESH renderable, pass 1 (:3868-3956): LOD selection + smoothing state + pose claim; counts what pass 2 will write
 __device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, float lod_multiplier_rcp, int32_t e, Counts& c) {
 	SkEntity* rec = A.ent + e;
@@ -165,33 +183,27 @@ __device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitAr
 		}
 		rec->lod = cur;
 	}
+	const bool moved_not_shadow = (fl & LB200_SK_MOVED) && !is_shadow;
 	uint32_t code = model_idx | (lod0 << CODE_LOD_SHIFT) | (two ? CODE_TWO : 0u) | ((fl & LB200_SK_MOVED) ? CODE_MOVED : 0u);
-	bool pose_checked = false;
-	const int n_lods = two ? 2 : 1;
-	for (int li = 0; li < n_lods; ++li) { // create_key, :3883-3924
-		const int l = (int)lod0 + li;
-		const int to = lod_to(model, l);
-		for (int mesh_idx = lod_from(model, l); mesh_idx <= to; ++mesh_idx) {
-			const lb200_sk_mesh mm = load_mesh(A.meshes + model.mesh_base + (uint32_t)mesh_idx);
-			const uint32_t bucket = s_bucket_map[mm.layer];
-			if (mm.skinned) {
-				// once per instance and frame the palette has to be built (PoseProcessor::push; the compare-exchange on Pose::frame of
-				// :3890-3897 — one thread owns the instance within a view)
-				if (!pose_checked) {
-					pose_checked = true;
-					if (rec->pose_frame != P.view.frame_number) { rec->pose_frame = P.view.frame_number; code |= CODE_POSE; ++c.p; }
-				}
-				++c.k;
-			}
-			else if ((fl & LB200_SK_MOVED) && !is_shadow) ++c.k;
-			else if (bucket < 0xff) { // AutoInstancer::add, :3913-3914
-				++c.r;
-				if (s_grp) atomicAdd(&s_grp[mm.sort_key], 1u);
-				else warp_claim_keyed(A.group_count, mm.sort_key);
-			}
-			else if (bucket < 0xffff) ++c.k; // depth sorted, :3915-3922
+	// the meshes of lod0 and, while the lod blends over, of lod0 + 1: one loop over both ranges
+	const int from0 = lod_from(model, (int)lod0), to0 = lod_to(model, (int)lod0);
+	const int from1 = two ? lod_from(model, (int)lod0 + 1) : 0, to1 = two ? lod_to(model, (int)lod0 + 1) : -1;
+	const int n0 = max(to0 - from0 + 1, 0), n_all = n0 + max(to1 - from1 + 1, 0);
+	bool any_skinned = false;
+	for (int j = 0; j < n_all; ++j) {
+		const int mesh_idx = j < n0 ? from0 + j : from1 + (j - n0);
+		const lb200_sk_mesh mm = load_mesh(A.meshes + model.mesh_base + (uint32_t)mesh_idx);
+		const MeshKind kind = mesh_kind(mm, s_bucket_map[mm.layer], moved_not_shadow);
+		any_skinned |= kind.skinned;
+		c.k += kind.key ? 1u : 0u;
+		if (kind.inst) { // AutoInstancer::add, :3913-3914
+			if (s_grp) atomicAdd(&s_grp[mm.sort_key], 1u);
+			else warp_claim_keyed(A.group_count, mm.sort_key);
 		}
 	}
+	// once per instance and frame the palette has to be built (PoseProcessor::push; the compare-exchange on Pose::frame of :3890-3897 —
+	// one thread owns the instance within a view)
+	if (any_skinned && rec->pose_frame != P.view.frame_number) { rec->pose_frame = P.view.frame_number; code |= CODE_POSE; ++c.p; }
 	return code;
 }
 
@@ -208,47 +220,42 @@ __device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& 
 		return;
 	}
 	const lb200_sk_model model = load_model(A.models + (code & CODE_MODEL_MASK));
-	const bool is_shadow = P.view.is_shadow != 0;
+	const bool moved_not_shadow = (code & CODE_MOVED) && P.view.is_shadow == 0;
 	const uint32_t lod0 = (code >> CODE_LOD_SHIFT) & 7u;
-	const int n_lods = (code & CODE_TWO) ? 2 : 1;
+	const bool two = (code & CODE_TWO) != 0;
 	if (code & CODE_POSE) {
 		if (p < P.cap_pose) A.pose_list[p] = (uint32_t)e;
 		++p;
 	}
-	bool have = false;
-	int4 q0, q1, q2, q3; // the entity's record, fetched once and only if an instance or a depth key needs it
-	q0 = q1 = q2 = q3 = make_int4(0, 0, 0, 0);
-	for (int li = 0; li < n_lods; ++li) {
-		const int l = (int)lod0 + li;
-		const int to = lod_to(model, l);
-		for (int mesh_idx = lod_from(model, l); mesh_idx <= to; ++mesh_idx) {
-			const lb200_sk_mesh mm = load_mesh(A.meshes + model.mesh_base + (uint32_t)mesh_idx);
-			const uint32_t bucket = s_bucket_map[mm.layer];
-			const uint64_t mesh_value = sext(e) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT);
-			if (mm.skinned) push_key(P, A, k, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)DRAW_SKINNED << SORT_VALUE_TYPE_SHIFT));
-			else if ((code & CODE_MOVED) && !is_shadow) push_key(P, A, k, mm.sort_key | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT));
-			else if (bucket < 0xffff) {
-				if (!have) {
-					have = true;
-					const int4* r = reinterpret_cast<const int4*>(A.ent + e);
-					q0 = r[0]; q1 = r[1]; q2 = r[2]; q3 = r[3];
-				}
-				const double px = __hiloint2double(q0.y, q0.x), py = __hiloint2double(q0.w, q0.z), pz = __hiloint2double(q1.y, q1.x);
-				const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
-				if (bucket < 0xff) { // instance data of the auto-instanced mesh, :3990-4008, at the group's offset + this block's slice + rank
-					const uint32_t at = s_grp ? atomicAdd(&s_grp[mm.sort_key], 1u) : warp_claim_keyed(A.group_cursor, mm.sort_key);
-					if (at < P.cap_recs) {
-						A.group_renderables[at] = mesh_value;
-						float4* dst = A.instance_data + (size_t)at * 3;
-						dst[0] = make_float4(__int_as_float(q2.x), __int_as_float(q2.y), __int_as_float(q2.z), __int_as_float(q2.w)); // rot
-						dst[1] = make_float4((float)rx, (float)ry, (float)rz, LB_FSUB(__int_as_float(q1.w), mm.lod)); // Vec3(tr.pos - camera_pos), lod - mesh.lod
-						dst[2] = make_float4(__int_as_float(q3.x), __int_as_float(q3.y), __int_as_float(q3.z), __uint_as_float(mm.material_index)); // scale, material
-					}
-				}
-				else { // depth sorted, :3915-3922
-					const float sq = (float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz));
-					push_key(P, A, k, float_flip(__float_as_uint(sq)) | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)DRAW_MESH << SORT_VALUE_TYPE_SHIFT));
-				}
+	// the entity's record: position for depth keys, everything for instance data (a MOVED or all-skinned renderable would not need it;
+	// both are rare, and one unconditional fetch keeps the warp together)
+	const int4* r = reinterpret_cast<const int4*>(A.ent + e);
+	const int4 q0 = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
+	const double px = __hiloint2double(q0.y, q0.x), py = __hiloint2double(q0.w, q0.z), pz = __hiloint2double(q1.y, q1.x);
+	const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
+	const float fx = (float)rx, fy = (float)ry, fz = (float)rz; // Vec3(tr.pos - camera_pos)
+	const uint32_t depth_bits = float_flip(__float_as_uint((float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz)))); // :3915-3922
+	const int from0 = lod_from(model, (int)lod0), to0 = lod_to(model, (int)lod0);
+	const int from1 = two ? lod_from(model, (int)lod0 + 1) : 0, to1 = two ? lod_to(model, (int)lod0 + 1) : -1;
+	const int n0 = max(to0 - from0 + 1, 0), n_all = n0 + max(to1 - from1 + 1, 0);
+	for (int j = 0; j < n_all; ++j) {
+		const int mesh_idx = j < n0 ? from0 + j : from1 + (j - n0);
+		const lb200_sk_mesh mm = load_mesh(A.meshes + model.mesh_base + (uint32_t)mesh_idx);
+		const uint32_t bucket = s_bucket_map[mm.layer];
+		const MeshKind kind = mesh_kind(mm, bucket, moved_not_shadow);
+		const uint64_t mesh_value = sext(e) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT);
+		if (kind.key) {
+			const uint64_t low = kind.depth ? (uint64_t)depth_bits : (uint64_t)mm.sort_key;
+			push_key(P, A, k, low | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)(kind.skinned ? DRAW_SKINNED : DRAW_MESH) << SORT_VALUE_TYPE_SHIFT));
+		}
+		if (kind.inst) { // instance data of the auto-instanced mesh, :3990-4008, at the group's offset + this block's slice + rank
+			const uint32_t at = s_grp ? atomicAdd(&s_grp[mm.sort_key], 1u) : warp_claim_keyed(A.group_cursor, mm.sort_key);
+			if (at < P.cap_recs) {
+				A.group_renderables[at] = mesh_value;
+				float4* dst = A.instance_data + (size_t)at * 3;
+				dst[0] = make_float4(__int_as_float(q2.x), __int_as_float(q2.y), __int_as_float(q2.z), __int_as_float(q2.w)); // rot
+				dst[1] = make_float4(fx, fy, fz, LB_FSUB(__int_as_float(q1.w), mm.lod));                                     // camera-relative position, lod - mesh.lod
+				dst[2] = make_float4(__int_as_float(q3.x), __int_as_float(q3.y), __int_as_float(q3.z), __uint_as_float(mm.material_index)); // scale, material
 			}
 		}
 	}
@@ -275,7 +282,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 
 constexpr uint32_t SK_SMEM_GROUPS = 8192; // group counters a block keeps in shared memory (32 KB)
 
-__global__ void __launch_bounds__(SK_THREADS, 3) create_keys_kernel(const __grid_constant__ EmitParams P, const uint32_t* __restrict__ visible,
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// entity id at index i of the three segments seen as one index space [MESH | DECAL | CURVE_DECAL]
+__device__ __forceinline__ uint32_t visible_at(const EmitParams& P, const uint32_t* __restrict__ visible, uint32_t i, uint32_t n_mesh, uint32_t n_decal) {
+	return i < n_mesh ? visible[P.type_base[RT_MESH] + i] : i < n_mesh + n_decal ? visible[P.type_base[RT_DECAL] + (i - n_mesh)] : visible[P.type_base[RT_CURVE_DECAL] + (i - n_mesh - n_decal)];
+}
+
+__global__ void __launch_bounds__(SK_THREADS, 4) create_keys_kernel(const __grid_constant__ EmitParams P, const uint32_t* __restrict__ visible,
 	const uint32_t* __restrict__ cull_counters, EmitArgs A, uint32_t n_groups)
 {
 	extern __shared__ uint32_t s_grp_mem[];
@@ -294,13 +307,22 @@ __global__ void __launch_bounds__(SK_THREADS, 3) create_keys_kernel(const __grid
 	const uint32_t stride = gridDim.x * SK_THREADS;
 
 	// ---- pass 1: decide + count ----
+	// The walk is a random gather by entity id: the id of the thread's NEXT renderable is read one iteration ahead and its record is
+	// requested into L2 while the current one is processed (a dependent chain id -> record -> model -> mesh per renderable otherwise).
 	Counts c = {0u, 0u, 0u};
-	for (uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x; i < n_all; i += stride) {
-		if (i < n_mesh) A.stash[i] = mesh_count(P, A, s_bucket_map, s_grp, lod_multiplier_rcp, (int32_t)visible[P.type_base[RT_MESH] + i], c);
-		else { // DECAL / CURVE_DECAL renderable (:3840-3867): one key if its layer is in the view
-			const bool curve = i >= n_mesh + n_decal;
-			const int32_t e = (int32_t)visible[curve ? P.type_base[RT_CURVE_DECAL] + (i - n_mesh - n_decal) : P.type_base[RT_DECAL] + (i - n_mesh)];
-			if ((uint8_t)s_bucket_map[A.decal_layer[e]] < 0xff) ++c.k;
+	{
+		uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x;
+		uint32_t e = i < n_all ? visible_at(P, visible, i, n_mesh, n_decal) : 0u;
+		for (; i < n_all; i += stride) {
+			const uint32_t i_next = i + stride;
+			uint32_t e_next = 0;
+			if (i_next < n_all) {
+				e_next = visible_at(P, visible, i_next, n_mesh, n_decal);
+				if (i_next < n_mesh) prefetch_l2(A.ent + e_next); else prefetch_l2(A.decal_layer + e_next);
+			}
+			if (i < n_mesh) A.stash[i] = mesh_count(P, A, s_bucket_map, s_grp, lod_multiplier_rcp, (int32_t)e, c);
+			else if ((uint8_t)s_bucket_map[A.decal_layer[e]] < 0xff) ++c.k; // DECAL / CURVE_DECAL renderable (:3840-3867): one key if its layer is in the view
+			e = e_next;
 		}
 	}
 	uint32_t tk, tp;
@@ -347,14 +369,25 @@ __global__ void __launch_bounds__(SK_THREADS, 3) create_keys_kernel(const __grid
 
 	// ---- pass 2: write ----
 	uint32_t k = s_base[0] + pk, p = s_base[1] + pp;
-	for (uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x; i < n_all; i += stride) {
-		if (i < n_mesh) mesh_write(P, A, s_bucket_map, s_grp, (int32_t)visible[P.type_base[RT_MESH] + i], A.stash[i], k, p);
-		else {
-			const bool curve = i >= n_mesh + n_decal;
-			const int32_t e = (int32_t)visible[curve ? P.type_base[RT_CURVE_DECAL] + (i - n_mesh - n_decal) : P.type_base[RT_DECAL] + (i - n_mesh)];
-			const uint8_t bucket = (uint8_t)s_bucket_map[A.decal_layer[e]];
-			if (bucket < 0xff) push_key(P, A, k, A.decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
-				sext(e) | ((uint64_t)(curve ? DRAW_CURVE_DECAL : DRAW_DECAL) << SORT_VALUE_TYPE_SHIFT));
+	{
+		uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x;
+		uint32_t e = i < n_all ? visible_at(P, visible, i, n_mesh, n_decal) : 0u;
+		for (; i < n_all; i += stride) {
+			const uint32_t i_next = i + stride;
+			uint32_t e_next = 0;
+			if (i_next < n_all) {
+				e_next = visible_at(P, visible, i_next, n_mesh, n_decal);
+				if (i_next < n_mesh) { prefetch_l2(A.ent + e_next); prefetch_l2(reinterpret_cast<const char*>(A.ent + e_next) + 32); }
+				else prefetch_l2(A.decal_sort_key + e_next);
+			}
+			if (i < n_mesh) mesh_write(P, A, s_bucket_map, s_grp, (int32_t)e, A.stash[i], k, p);
+			else {
+				const bool curve = i >= n_mesh + n_decal;
+				const uint8_t bucket = (uint8_t)s_bucket_map[A.decal_layer[e]];
+				if (bucket < 0xff) push_key(P, A, k, A.decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
+					sext((int32_t)e) | ((uint64_t)(curve ? DRAW_CURVE_DECAL : DRAW_DECAL) << SORT_VALUE_TYPE_SHIFT));
+			}
+			e = e_next;
 		}
 	}
 }
@@ -398,6 +431,43 @@ __global__ void __launch_bounds__(256) ent_unpack_state_kernel(const SkEntity* _
 	pose_frame[i] = ent[i].pose_frame;
 }
 
+// RenderModuleImpl::onModelInstanceMoved (render_module.cpp:1544-1554) for a batch whose new transforms are already in HBM (e.g. bone attachments
+// of this frame's poses): the record takes the transform, the instance gets ModelInstance::MOVED and joins the moved list once, and — if
+// asked — the sphere CullingSystem::set needs (pos, bounding radius * max scale) is written for lb200_culling_set_many_device.
+__global__ void __launch_bounds__(256) ent_move_kernel(SkEntity* ent, uint32_t max_entities, const int32_t* __restrict__ entities, const lb200_transform* __restrict__ tr, uint32_t n,
+	const float* __restrict__ bounding_radius, double* __restrict__ out_pos3, float* __restrict__ out_radius, uint32_t* moved_list, uint32_t* moved_count)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const lb200_transform t = tr[i];
+	if (out_pos3) { out_pos3[3 * (size_t)i] = t.pos[0]; out_pos3[3 * (size_t)i + 1] = t.pos[1]; out_pos3[3 * (size_t)i + 2] = t.pos[2]; }
+	if (out_radius) out_radius[i] = LB_FMUL(bounding_radius[i], fmaxf(fmaxf(t.scale[0], t.scale[1]), t.scale[2])); // maximum(x, y, z), math.h
+	const uint32_t e = (uint32_t)entities[i];
+	if (e >= max_entities) return;
+	SkEntity& r = ent[e];
+	r.pos[0] = t.pos[0]; r.pos[1] = t.pos[1]; r.pos[2] = t.pos[2];
+	r.rot[0] = t.rot[0]; r.rot[1] = t.rot[1]; r.rot[2] = t.rot[2]; r.rot[3] = t.rot[3];
+	r.scale[0] = t.scale[0]; r.scale[1] = t.scale[1]; r.scale[2] = t.scale[2];
+	const uint32_t before = atomicOr(&r.model_flags, (uint32_t)LB200_SK_MOVED << 24);
+	if (!(before & ((uint32_t)LB200_SK_MOVED << 24))) moved_list[atomicAdd(moved_count, 1u)] = e; // m_moved_instances.push(entity), once
+}
+
+// RenderModuleImpl::endFrame (render_module.cpp:526-534): MOVED off, prev_frame_transform = the transform of this frame
+__global__ void __launch_bounds__(256) ent_end_frame_kernel(SkEntity* ent, const uint32_t* __restrict__ moved_list, uint32_t* moved_count, lb200_transform* __restrict__ prev) {
+	const uint32_t n = *moved_count;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t e = moved_list[i];
+		SkEntity& r = ent[e];
+		r.model_flags &= ~((uint32_t)LB200_SK_MOVED << 24);
+		lb200_transform t;
+		t.pos[0] = r.pos[0]; t.pos[1] = r.pos[1]; t.pos[2] = r.pos[2];
+		t.rot[0] = r.rot[0]; t.rot[1] = r.rot[1]; t.rot[2] = r.rot[2]; t.rot[3] = r.rot[3];
+		t.scale[0] = r.scale[0]; t.scale[1] = r.scale[1]; t.scale[2] = r.scale[2];
+		prev[e] = t;
+	}
+}
+__global__ void reset_word_kernel(uint32_t* w) { *w = 0; }
+
 // ---------------------------------------------------------------- radix sort ----------------------------------------------------------------
 constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
@@ -406,10 +476,45 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 2048 keys
 constexpr int RS_PASSES = 8;
 struct SortState { GridBar bar; uint32_t pad[2]; unsigned long long key_or, key_or_not; }; // zero-initialised: OR of all keys, OR of all complements
 
-// All passes in one cooperative launch.  Tiles of RS_TILE keys are dealt to the blocks in contiguous runs (block b: tiles [b*T/G, (b+1)*T/G)),
-// so "block order, then tile order, then position" is the key order and the scatter is stable.
+constexpr int RS_REG_ITEMS = 16;                    // keys a thread can keep in registers over all passes
+
+// Where this block's keys of digit d start: all keys of smaller digits + the keys of digit d in the blocks before this one.
+// In: block_hist[b][d] of every block (behind a grid barrier).  Out: s_hist[d].  All RS_THREADS threads.
+__device__ __forceinline__ void digit_starts(const uint32_t* block_hist, uint32_t* s_hist, uint32_t (*s_part)[256], uint32_t (*s_bef)[256], uint32_t* s_wsum) {
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t d = tid & 255u, part = tid >> 8;
+	uint32_t before = 0, total = 0;
+	for (uint32_t b = part; b < gridDim.x; b += RS_THREADS / 256) {
+		const uint32_t c = __ldcg(block_hist + b * 256 + d);
+		total += c;
+		if (b < blockIdx.x) before += c;
+	}
+	s_part[part][d] = total;
+	s_bef[part][d] = before;
+	__syncthreads();
+	uint32_t x = 0, mine = 0;
+	if (tid < 256) { // exclusive scan of the 256 digit totals by the first 8 warps
+		mine = s_part[0][tid] + s_part[1][tid];
+		x = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+		if (lane == 31) s_wsum[warp] = x;
+	}
+	__syncthreads();
+	if (tid < 256) {
+		uint32_t start = x - mine;
+		for (uint32_t w = 0; w < warp; ++w) start += s_wsum[w];
+		s_hist[tid] = start + s_bef[0][tid] + s_bef[1][tid];
+	}
+	__syncthreads();
+}
+
+// All passes in one cooperative launch, stable: the key order is "block, then position inside the block's contiguous run".
+//   n <= gridDim * RS_THREADS * RS_REG_ITEMS (a frame's worth of draw keys): every block owns ONE run of `items` keys per thread that stays in
+//   registers from the pass's ranking to its scatter — a pass reads every pair once and writes it once;
+//   larger n: tiles of RS_TILE keys, dealt to the blocks in contiguous runs (block b: tiles [b*T/G, (b+1)*T/G)), counted, then re-read and scattered.
 __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbuf0, uint64_t* kbuf1, uint64_t* vbuf0, uint64_t* vbuf1, const uint32_t* __restrict__ counts, uint32_t cap,
-	SortState* st, uint32_t* block_hist /* [gridDim][256] */)
+	SortState* st, uint32_t* block_hist /* [gridDim][256] */, uint32_t reg_items /* RS_REG_ITEMS; 0 forces the tiled path (tests) */)
 {
 	__shared__ uint32_t s_hist[256];              // count phase: this block's digit histogram; scatter phase: the block's running digit cursors
 	__shared__ uint32_t s_part[2][256], s_bef[2][256], s_wsum[8];
@@ -418,12 +523,22 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 	const uint32_t n = min(counts[0], cap);
 	if (n < 2) return; // uniform over the grid: nothing to sort (buffer 0 already holds the result)
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	const uint32_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
-	const uint32_t tile_begin = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
-	const uint32_t tile_end = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
-	const uint32_t key_begin = tile_begin * RS_TILE, key_end = min(n, tile_end * RS_TILE);
+	const bool in_regs = n <= gridDim.x * (uint32_t)RS_THREADS * reg_items;
+	uint32_t key_begin, key_end, tile_begin = 0, tile_end = 0, items = 0;
+	if (in_regs) {
+		items = (n + gridDim.x * RS_THREADS - 1) / (gridDim.x * RS_THREADS); // 1..RS_REG_ITEMS keys per thread
+		key_begin = min(n, blockIdx.x * items * RS_THREADS);
+		key_end = min(n, key_begin + items * RS_THREADS);
+	}
+	else {
+		const uint32_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+		tile_begin = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+		tile_end = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+		key_begin = tile_begin * RS_TILE;
+		key_end = min(n, tile_end * RS_TILE);
+	}
 
-	// which digits differ at all: OR and AND over every key
+	// which bits differ at all: OR of every key and OR of every complement
 	{
 		unsigned long long o = 0ull, a = 0ull;
 		for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) { const unsigned long long k = kbuf0[i]; o |= k; a |= ~k; }
@@ -440,95 +555,129 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 	const unsigned long long varying = __ldcg(&st->key_or) & __ldcg(&st->key_or_not); // bits that are 1 in some key and 0 in another
 
 	uint32_t cur = 0;
+	if (in_regs) {
+		// the warp's run: [key_begin + warp * items * 32, + items * 32); item j of lane l = run + j * 32 + l, so (j, lane) is the key order
+		const uint32_t wbase = key_begin + warp * items * 32u;
+		uint64_t k[RS_REG_ITEMS], v[RS_REG_ITEMS];
+		uint16_t rk[RS_REG_ITEMS];
 #pragma unroll 1
-	for (int pass = 0; pass < RS_PASSES; ++pass) {
-		const int shift = 8 * pass;
-		if (((varying >> shift) & 0xffull) == 0ull) continue; // every key has the same digit here: the pass would move nothing
-		const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
-		const uint64_t* vsrc = cur ? vbuf1 : vbuf0;
-		uint64_t* kdst = cur ? kbuf0 : kbuf1;
-		uint64_t* vdst = cur ? vbuf0 : vbuf1;
-		// count
-		if (tid < 256) s_hist[tid] = 0;
-		__syncthreads();
-		for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) atomicAdd(&s_hist[(uint32_t)(__ldcg(ksrc + i) >> shift) & 0xffu], 1u);
-		__syncthreads();
-		if (tid < 256) block_hist[blockIdx.x * 256 + tid] = s_hist[tid];
-		grid_barrier(&st->bar);
-		// where this block's keys of digit d start: all keys of smaller digits + the keys of digit d in the blocks before this one
-		{
-			const uint32_t d = tid & 255u, part = tid >> 8;
-			uint32_t before = 0, total = 0;
-			for (uint32_t b = part; b < gridDim.x; b += RS_THREADS / 256) {
-				const uint32_t c = __ldcg(block_hist + b * 256 + d);
-				total += c;
-				if (b < blockIdx.x) before += c;
-			}
-			s_part[part][d] = total;
-			s_bef[part][d] = before;
-			__syncthreads();
-			uint32_t x = 0, mine = 0;
-			if (tid < 256) { // exclusive scan of the 256 digit totals by the first 8 warps
-				mine = s_part[0][tid] + s_part[1][tid];
-				x = mine;
+		for (int pass = 0; pass < RS_PASSES; ++pass) {
+			const int shift = 8 * pass;
+			if (((varying >> shift) & 0xffull) == 0ull) continue; // every key has the same digit here: the pass would move nothing
+			const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
+			const uint64_t* vsrc = cur ? vbuf1 : vbuf0;
+			uint64_t* kdst = cur ? kbuf0 : kbuf1;
+			uint64_t* vdst = cur ? vbuf0 : vbuf1;
 #pragma unroll
-				for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
-				if (lane == 31) s_wsum[warp] = x;
-			}
-			__syncthreads();
-			if (tid < 256) {
-				uint32_t start = x - mine;
-				for (uint32_t w = 0; w < warp; ++w) start += s_wsum[w];
-				s_hist[tid] = start + s_bef[0][tid] + s_bef[1][tid];
-			}
-			__syncthreads();
-		}
-		// stable scatter, tile by tile
-		for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
-			const uint32_t wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
-			uint64_t k[RS_ITEMS], v[RS_ITEMS];
-			uint32_t dg[RS_ITEMS], rk[RS_ITEMS];
-#pragma unroll
-			for (int j = 0; j < RS_ITEMS; ++j) {
+			for (int j = 0; j < RS_REG_ITEMS; ++j) {
 				const uint32_t i = wbase + j * 32 + lane;
-				const bool has = i < n;
+				const bool has = (uint32_t)j < items && i < key_end;
 				k[j] = has ? __ldcg(ksrc + i) : 0;
 				v[j] = has ? __ldcg(vsrc + i) : 0;
-				dg[j] = has ? (uint32_t)(k[j] >> shift) & 0xffu : 0x100u; // keys past the end match only each other
 			}
 			for (int d = lane; d < 256; d += 32) s_wcnt[warp][d] = 0;
 			__syncwarp();
 #pragma unroll
-			for (int j = 0; j < RS_ITEMS; ++j) {
-				const uint32_t peers = __match_any_sync(0xffffffffu, dg[j]);
-				const uint32_t below = __popc(peers & ((1u << lane) - 1u));
-				uint32_t seen = 0;
-				if (dg[j] < 256) seen = s_wcnt[warp][dg[j]];
-				__syncwarp();
-				if (dg[j] < 256 && below == 0) s_wcnt[warp][dg[j]] = seen + __popc(peers);
-				__syncwarp();
-				rk[j] = seen + below;
+			for (int j = 0; j < RS_REG_ITEMS; ++j) {
+				if ((uint32_t)j < items) { // uniform
+					const bool has = wbase + j * 32 + lane < key_end;
+					const uint32_t dg = has ? (uint32_t)(k[j] >> shift) & 0xffu : 0x100u; // lanes past the end match only each other
+					const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+					const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+					uint32_t seen = 0;
+					if (has) seen = s_wcnt[warp][dg];
+					__syncwarp();
+					if (has && below == 0) s_wcnt[warp][dg] = seen + __popc(peers);
+					__syncwarp();
+					rk[j] = (uint16_t)(seen + below);
+				}
 			}
 			__syncthreads();
-			if (tid < 256) { // digit tid: the warps' slices in warp order, then advance the block's cursor past the tile
-				uint32_t acc = s_hist[tid];
+			if (tid < 256) { // digit tid: the warps' counts -> each warp's offset inside the block's slice; the sum is the block's histogram entry
+				uint32_t acc = 0;
 #pragma unroll
 				for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = s_wcnt[w][tid]; s_wcnt[w][tid] = acc; acc += t; }
-				s_hist[tid] = acc;
+				block_hist[blockIdx.x * 256 + tid] = acc;
 			}
-			__syncthreads();
+			grid_barrier(&st->bar);
+			digit_starts(block_hist, s_hist, s_part, s_bef, s_wsum);
 #pragma unroll
-			for (int j = 0; j < RS_ITEMS; ++j) {
-				if (dg[j] < 256) {
-					const uint32_t dest = s_wcnt[warp][dg[j]] + rk[j];
+			for (int j = 0; j < RS_REG_ITEMS; ++j) {
+				if ((uint32_t)j < items && wbase + j * 32 + lane < key_end) {
+					const uint32_t dg = (uint32_t)(k[j] >> shift) & 0xffu;
+					const uint32_t dest = s_hist[dg] + s_wcnt[warp][dg] + rk[j];
 					kdst[dest] = k[j];
 					vdst[dest] = v[j];
 				}
 			}
-			__syncthreads();
+			grid_barrier(&st->bar);
+			cur ^= 1u;
 		}
-		grid_barrier(&st->bar);
-		cur ^= 1u;
+	}
+	else {
+#pragma unroll 1
+		for (int pass = 0; pass < RS_PASSES; ++pass) {
+			const int shift = 8 * pass;
+			if (((varying >> shift) & 0xffull) == 0ull) continue;
+			const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
+			const uint64_t* vsrc = cur ? vbuf1 : vbuf0;
+			uint64_t* kdst = cur ? kbuf0 : kbuf1;
+			uint64_t* vdst = cur ? vbuf0 : vbuf1;
+			// count
+			if (tid < 256) s_hist[tid] = 0;
+			__syncthreads();
+			for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) atomicAdd(&s_hist[(uint32_t)(__ldcg(ksrc + i) >> shift) & 0xffu], 1u);
+			__syncthreads();
+			if (tid < 256) block_hist[blockIdx.x * 256 + tid] = s_hist[tid];
+			grid_barrier(&st->bar);
+			digit_starts(block_hist, s_hist, s_part, s_bef, s_wsum);
+			// stable scatter, tile by tile
+			for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+				const uint32_t wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
+				uint64_t k[RS_ITEMS], v[RS_ITEMS];
+				uint32_t dg[RS_ITEMS], rk[RS_ITEMS];
+#pragma unroll
+				for (int j = 0; j < RS_ITEMS; ++j) {
+					const uint32_t i = wbase + j * 32 + lane;
+					const bool has = i < n;
+					k[j] = has ? __ldcg(ksrc + i) : 0;
+					v[j] = has ? __ldcg(vsrc + i) : 0;
+					dg[j] = has ? (uint32_t)(k[j] >> shift) & 0xffu : 0x100u; // keys past the end match only each other
+				}
+				for (int d = lane; d < 256; d += 32) s_wcnt[warp][d] = 0;
+				__syncwarp();
+#pragma unroll
+				for (int j = 0; j < RS_ITEMS; ++j) {
+					const uint32_t peers = __match_any_sync(0xffffffffu, dg[j]);
+					const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+					uint32_t seen = 0;
+					if (dg[j] < 256) seen = s_wcnt[warp][dg[j]];
+					__syncwarp();
+					if (dg[j] < 256 && below == 0) s_wcnt[warp][dg[j]] = seen + __popc(peers);
+					__syncwarp();
+					rk[j] = seen + below;
+				}
+				__syncthreads();
+				if (tid < 256) { // digit tid: the warps' slices in warp order, then advance the block's cursor past the tile
+					uint32_t acc = s_hist[tid];
+#pragma unroll
+					for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = s_wcnt[w][tid]; s_wcnt[w][tid] = acc; acc += t; }
+					s_hist[tid] = acc;
+				}
+				__syncthreads();
+#pragma unroll
+				for (int j = 0; j < RS_ITEMS; ++j) {
+					if (dg[j] < 256) {
+						const uint32_t dest = s_wcnt[warp][dg[j]] + rk[j];
+						kdst[dest] = k[j];
+						vdst[dest] = v[j];
+					}
+				}
+				__syncthreads();
+			}
+			grid_barrier(&st->bar);
+			cur ^= 1u;
+		}
 	}
 	if (cur) { // sorted data to buffer 0 if it ended up in buffer 1
 		for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) { kbuf0[i] = __ldcg(kbuf1 + i); vbuf0[i] = __ldcg(vbuf1 + i); }
@@ -558,7 +707,9 @@ int lb200_radix_sort_pairs(lb200_ctx* ctx, cudaStream_t s, uint64_t* keys0, uint
 	SortState* st = (SortState*)state;
 	LB200_CUDA(ctx, cudaMemsetAsync(st, 0, sizeof(SortState), s));
 	uint32_t grid = std::max(1u, std::min(std::min(limit, blocks), (cap + RS_TILE - 1) / RS_TILE));
-	void* args[] = {&keys0, &keys1, &values0, &values1, &count_dev, &cap, &st, &block_hist};
+	static const uint32_t reg_items = [] { const char* e = getenv("LB200_SORT_TILED"); return (e && atoi(e) != 0) ? 0u : (uint32_t)RS_REG_ITEMS; }(); // LB200_SORT_TILED=1: always the tiled path
+	uint32_t reg_items_arg = reg_items;
+	void* args[] = {&keys0, &keys1, &values0, &values1, &count_dev, &cap, &st, &block_hist, &reg_items_arg};
 	LB200_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)radix_sort_kernel, dim3(grid), dim3(RS_THREADS), args, 0, s));
 	LB200_CHECK_LAUNCH(ctx);
 	return LB200_OK;
@@ -581,6 +732,7 @@ struct lb200_sortkeys {
 	uint64_t* d_group_renderables = nullptr; float4* d_instance_data = nullptr;
 	uint32_t *d_pose_list = nullptr, *d_dirty_list = nullptr, *d_stash = nullptr;
 	float* d_lod = nullptr; uint32_t* d_pose_frame = nullptr; // unpacked on request (lb200_sortkeys_device_outputs)
+	uint32_t* d_moved_list = nullptr; uint32_t* d_moved_count = nullptr; lb200_transform* d_prev = nullptr; // RenderModule::m_moved_instances, ModelInstance::prev_frame_transform (first move onwards)
 	GridBar* d_bar = nullptr;
 	SortState* d_sort_state = nullptr; uint32_t* d_block_hist = nullptr;
 	uint32_t sort_blocks = 0;
@@ -651,7 +803,7 @@ void lb200_sortkeys_destroy(lb200_sortkeys* sk) {
 	cudaFree(sk->d_counts); if (sk->h_counts) cudaFreeHost(sk->h_counts);
 	cudaFree(sk->d_group_count); cudaFree(sk->d_group_offset); cudaFree(sk->d_group_cursor);
 	cudaFree(sk->d_group_renderables); cudaFree(sk->d_instance_data); cudaFree(sk->d_pose_list); cudaFree(sk->d_dirty_list); cudaFree(sk->d_stash);
-	cudaFree(sk->d_lod); cudaFree(sk->d_pose_frame); cudaFree(sk->d_bar);
+	cudaFree(sk->d_lod); cudaFree(sk->d_pose_frame); cudaFree(sk->d_bar); cudaFree(sk->d_moved_list); cudaFree(sk->d_moved_count); cudaFree(sk->d_prev);
 	cudaFree(sk->d_sort_state); cudaFree(sk->d_block_hist);
 	delete sk;
 }
@@ -804,6 +956,49 @@ int lb200_sortkeys_device_outputs(lb200_sortkeys* sk, lb200_sk_outputs* out) {
 	out->keys = sk->d_keys[0]; out->values = sk->d_values[0]; out->group_count = sk->d_group_count; out->group_offset = sk->d_group_offset;
 	out->group_renderables = sk->d_group_renderables; out->instance_data = sk->d_instance_data; out->pose_list = sk->d_pose_list; out->dirty_list = sk->d_dirty_list;
 	out->lod = sk->d_lod; out->pose_frame = sk->d_pose_frame;
+	return LB200_OK;
+}
+
+// RenderModule::onModelInstanceMoved for n instances whose new transforms lie in HBM: transforms into the entity records,
+// ModelInstance::MOVED on, the instances join the moved list (createSortKeys draws them as DRAW_MESH until lb200_sortkeys_end_frame).
+// With dev_bounding_radius: (pos, radius * max scale) per instance into dev_out_pos3 / dev_out_radius, the arguments of
+// lb200_culling_set_many_device (render_module.cpp:1552-1554).
+int lb200_sortkeys_move_device(lb200_sortkeys* sk, const int32_t* dev_entities, const lb200_transform* dev_transforms, uint32_t n, const float* dev_bounding_radius,
+	double* dev_out_pos3, float* dev_out_radius)
+{
+	if (!sk || !dev_entities || !dev_transforms || (dev_out_radius && !dev_bounding_radius)) return LB200_ERR_INVALID;
+	if (!n) return LB200_OK;
+	lb200_ctx* ctx = sk->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!sk->d_moved_list) {
+		LB200_CUDA(ctx, cudaMalloc(&sk->d_moved_list, sizeof(uint32_t) * (size_t)sk->max_entities));
+		LB200_CUDA(ctx, cudaMalloc(&sk->d_moved_count, sizeof(uint32_t)));
+		LB200_CUDA(ctx, cudaMemsetAsync(sk->d_moved_count, 0, sizeof(uint32_t), ctx->stream));
+		LB200_CUDA(ctx, cudaMalloc(&sk->d_prev, sizeof(lb200_transform) * (size_t)sk->max_entities));
+		LB200_CUDA(ctx, cudaMemsetAsync(sk->d_prev, 0, sizeof(lb200_transform) * (size_t)sk->max_entities, ctx->stream));
+	}
+	ent_move_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sk->d_ent, sk->max_entities, dev_entities, dev_transforms, n, dev_bounding_radius, dev_out_pos3, dev_out_radius, sk->d_moved_list, sk->d_moved_count);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
+// RenderModule::endFrame (render_module.cpp:526-534) for the instances moved since the last call
+int lb200_sortkeys_end_frame(lb200_sortkeys* sk) {
+	if (!sk) return LB200_ERR_INVALID;
+	if (!sk->d_moved_list) return LB200_OK; // nothing ever moved through this object
+	lb200_ctx* ctx = sk->ctx;
+	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
+	ent_end_frame_kernel<<<(uint32_t)ctx->sm_count * 2, 256, 0, ctx->stream>>>(sk->d_ent, sk->d_moved_list, sk->d_moved_count, sk->d_prev);
+	LB200_CHECK_LAUNCH(ctx);
+	reset_word_kernel<<<1, 1, 0, ctx->stream>>>(sk->d_moved_count);
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
+// ModelInstance::prev_frame_transform per entity (device array, zero until an instance has been through move + end_frame), valid while sk lives
+int lb200_sortkeys_prev_transforms(lb200_sortkeys* sk, const lb200_transform** dev_prev) {
+	if (!sk || !dev_prev) return LB200_ERR_INVALID;
+	*dev_prev = sk->d_prev;
 	return LB200_OK;
 }
 

@@ -79,6 +79,25 @@ class SortKeys:
         self._err(self.L.lb200_sortkeys_create_keys(self.h, culling.h, ptr(view), C.c_int(1 if sort else 0), C.c_int(1 if want_counts else 0), C.byref(res)))
         return res if want_counts else None
 
+    def moveDevice(self, dev_entities, dev_transforms, n, dev_bounding_radius=None, dev_out_pos3=None, dev_out_radius=None):
+        """RenderModule::onModelInstanceMoved for n instances whose transforms lie in device memory (pointers as ints): records updated, MOVED set;
+        with bounding radii also the spheres for CullingSystem.set_many_device."""
+        self._err(self.L.lb200_sortkeys_move_device(self.h, vp(dev_entities), vp(dev_transforms), C.c_uint32(n), vp(dev_bounding_radius) if dev_bounding_radius else None,
+                                                    vp(dev_out_pos3) if dev_out_pos3 else None, vp(dev_out_radius) if dev_out_radius else None))
+
+    def endFrame(self):
+        """RenderModule::endFrame: MOVED cleared, prev_frame_transform taken for the instances moved since the last call."""
+        self._err(self.L.lb200_sortkeys_end_frame(self.h))
+
+    def prevTransforms(self):
+        """Host copy of ModelInstance::prev_frame_transform per entity (zeros until an instance went through moveDevice + endFrame)."""
+        from .hierarchy import TRANSFORM_DTYPE
+        p = vp()
+        self._err(self.L.lb200_sortkeys_prev_transforms(self.h, C.byref(p)))
+        if not p:
+            return np.zeros(self.max_entities, TRANSFORM_DTYPE)
+        return self.ctx.copy_to_host(p.value, self.max_entities, TRANSFORM_DTYPE)
+
     def read(self, res):
         """Host copies of everything the last createSortKeys left in HBM."""
         o = SkOutputs()

@@ -128,7 +128,7 @@ $CXX -shared -o "$OUT/libref_lumix.so" $OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/re
 PRODUCT_DIR="$(cd "$HERE/../lumixengine_b200" && pwd)"
 if [ -f "$PRODUCT_DIR/liblumix_b200.so" ]; then
 	SHIM_OBJS=""
-	for o in $OBJS; do case "$o" in */core_*.o) SHIM_OBJS="$SHIM_OBJS $o";; esac; done # job system, allocators, PageAllocator, math, geometry, log ...
+	for o in $OBJS; do case "$o" in */core_*.o|*/engine_resource.o|*/renderer_pose.o|*/animation_animation.o) SHIM_OBJS="$SHIM_OBJS $o";; esac; done # job system, allocators, PageAllocator, math, geometry, log ...; Pose, Animation, Resource for the animation binding
 	# the World patch as INTEGRATION.md section 2 describes it, applied to the overlay copy of the reference's own world.h / world.cpp:
 	# declarations into `struct World`, host/world_b200.inl appended to world.cpp, one line in ~World
 	cp "$REF/src/engine/world.cpp" "$S/engine/world.cpp"
@@ -146,12 +146,25 @@ assert dtor in wc
 wc = wc.replace(dtor, dtor + "\tdestroyHierarchyB200();\n", 1) + "\n" + open(host + "/world_b200.inl").read()
 open(eng + "/world.cpp", "w").write(wc)
 PYEOF
+	# the animation binding: the accessors of host/animation_b200_decl.inl go into `struct Animation` of a second copy
+	# of animation.h that only the binding's harness sees (inline getters: the layout of Animation does not change, the reference's own
+	# animation.o above was compiled from the unpatched header)
+	mkdir -p "$TMP/patched/animation"
+	python3 - "$S/animation/animation.h" "$TMP/patched/animation/animation.h" "$PRODUCT_DIR/host/animation_b200_decl.inl" <<'PYEOF'
+import sys
+src, dst, decl = sys.argv[1:4]
+t = open(src).read()
+anchor = "\tconst Array<TranslationTrack>& getTranslations() const { return m_translations; }"
+assert anchor in t, "animation.h changed: INTEGRATION.md section 3 needs another anchor"
+open(dst, "w").write(t.replace(anchor, open(decl).read() + anchor))
+PYEOF
 	if $CXX $FL -I"$HERE/../include" -c "$PRODUCT_DIR/host/culling_system_b200.cpp" -o "$TMP/obj/shim.o" 2> "$TMP/shim.log" \
+		&& $CXX -I"$TMP/patched" $FL -I"$HERE/../include" -I"$PRODUCT_DIR/host" -c "$HERE/ref/ref_anim_shim_harness.cpp" -o "$TMP/obj/anim_harness.o" 2>> "$TMP/shim.log" \
 		&& $CXX $FL -c "$HERE/ref/ref_engine_shim_harness.cpp" -o "$TMP/obj/shim_harness.o" 2>> "$TMP/shim.log" \
 		&& $CXX $FL -I"$HERE/../include" -c "$S/engine/world.cpp" -o "$TMP/obj/world_b200.o" 2>> "$TMP/shim.log" \
 		&& $CXX $FL -I"$HERE/../include" -c "$HERE/ref/ref_world_shim_harness.cpp" -o "$TMP/obj/world_harness.o" 2>> "$TMP/shim.log" \
 		&& $CXX -shared -o "$OUT/libengine_shim_b200.so" $SHIM_OBJS "$TMP/obj/ref_stubs.o" "$TMP/obj/shim.o" "$TMP/obj/shim_harness.o" \
-			"$TMP/obj/world_b200.o" "$TMP/obj/world_harness.o" \
+			"$TMP/obj/world_b200.o" "$TMP/obj/world_harness.o" "$TMP/obj/anim_harness.o" \
 			-L"$PRODUCT_DIR" -llumix_b200 -Wl,-rpath,'$ORIGIN/../../lumixengine_b200' -lpthread -Wl,--no-undefined -Wl,--exclude-libs,ALL 2>> "$TMP/shim.log"; then
 		echo "built $OUT/libengine_shim_b200.so"
 	else

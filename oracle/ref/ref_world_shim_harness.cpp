@@ -31,11 +31,6 @@ namespace Lumix::reflection {
 Span<const RegisteredComponent> getComponents() { return {}; }
 }
 
-namespace Lumix {
-// engine/resource.cpp:16-23 (prefab.h has a static ResourceType; resource.cpp itself needs the resource manager to link)
-ResourceType::ResourceType(const char* type_name) { type = RuntimeHash(type_name); }
-}
-
 namespace {
 
 struct StubSystems final : SystemManager {

@@ -103,3 +103,29 @@ def test_shim_compiles_against_engine_headers():
         syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
         assert "Lumix::CullingSystem::create(Lumix::IAllocator&, Lumix::PageAllocator&)" in syms
         assert "lb200_culling_cull" in syms  # unresolved here, provided by liblumix_b200.so
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "animation")), reason="reference tree not present")
+def test_animation_binding_compiles_against_render_module():
+    """host/animation_b200.inl instantiated with the engine's own RenderModule (render_module.h:402-403 lockPose / unlockPose,
+    getModelInstanceModel), animation.h patched with host/animation_b200_decl.inl as INTEGRATION.md section 3 says."""
+    host = os.path.join(ROOT, "lumixengine_b200", "host")
+    with tempfile.TemporaryDirectory() as tmp:
+        _copy_headers(tmp, ("core", "engine", "renderer", "animation"))
+        ah = os.path.join(tmp, "src", "animation", "animation.h")
+        text = open(ah).read()
+        anchor = "\tconst Array<TranslationTrack>& getTranslations() const { return m_translations; }"
+        assert anchor in text, "animation.h changed: INTEGRATION.md section 3 needs another anchor"
+        open(ah, "w").write(text.replace(anchor, open(os.path.join(host, "animation_b200_decl.inl")).read() + anchor))
+        tu = os.path.join(tmp, "tu.cpp")
+        open(tu, "w").write('#include "animation/animation.h"\n#include "animation/animation_module.h"\n#include "core/log.h"\n#include "renderer/model.h"\n'
+                            '#include "renderer/pose.h"\n#include "renderer/render_module.h"\n#include <string.h>\n#include "animation_b200.inl"\n'
+                            'namespace Lumix { template struct AnimablesB200<RenderModule>; }\n')
+        obj = os.path.join(tmp, "tu.o")
+        cmd = GXX + ["-I", os.path.join(tmp, "src"), "-I", os.path.join(REF, "external"), "-I", os.path.join(ROOT, "include"), "-I", host, tu, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+        assert "Lumix::AnimablesB200<Lumix::RenderModule>::update(lb200_ctx*, Lumix::RenderModule&, Lumix::Span<Lumix::Animable>, float)" in syms
+        for f in ("lb200_animation_create", "lb200_animation_set_instances", "lb200_animation_update", "lb200_animation_get_pose", "lb200_animation_get_times"):
+            assert f in syms

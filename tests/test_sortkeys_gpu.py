@@ -95,3 +95,91 @@ def test_device_radix_sort_alone(ctx, oracle):
     assert len(np.unique(got["keys"])) < 100
     S.close()
     cs.close()
+
+
+def test_pose_to_attachment_to_cull_chain_on_device(ctx, oracle):
+    """SURVEY 8f N4 closed on the device: this frame's poses -> updateBoneAttachment for a batch (render_module.cpp:377-405) -> the attached
+    entities' new transforms stay in HBM -> onModelInstanceMoved's bookkeeping (MOVED flag, moved list, sphere for CullingSystem::set,
+    :1544-1554) -> device re-binning -> cull -> createSortKeys (MOVED instances become DRAW_MESH keys) -> endFrame (:526-534: MOVED off,
+    prev_frame_transform).  Every stage against the oracle fed with the same edits one by one."""
+    n = 30_000
+    scene = scenes.cull_scene(n, (1800.0, 200.0, 1800.0), seed=31, type_probs=(0.9, 0.04, 0.02, 0.04), big_fraction=0.002)
+    sk = scenes.sortkey_setup(n, scene["types"], scene["pos"], seed=77, moved_fraction=0.0)
+    cs = lb.CullingSystem(ctx)
+    cs.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    oc = oracle.OracleCulling()
+    oc.add(scene["entities"], scene["types"], scene["pos"], scene["radius"])
+    S = lb.SortKeys(ctx, n, sk["max_sort_key"] + 1, max_keys=4 * n, max_instances=4 * n)
+    S.setModels(sk["models"], sk["meshes"])
+    S.setInstances(sk["model_of"], sk["lod"], sk["flags"], sk["pose_frame"], sk["decal_sort_key"], sk["decal_layer"])
+    S.setTransforms(sk["transforms"])
+    # posed instances
+    skel = scenes.skeleton(40)
+    clips = [scenes.clip(skel, frames=30, seed=s) for s in (3, 4)]
+    n_inst = 120
+    anim = lb.AnimationSystem(ctx, skel, clips, None, max_instances=n_inst)
+    ci, tt = scenes.instance_times(n_inst, clips, seed=2)
+    anim.setInstances(ci, tt)
+    anim.update(1.0 / 60.0, lb.PALETTE_POSE)
+    pos, rot = anim.getPose()
+    # attachments: m distinct MESH entities follow bones of posed instances whose entity is some other entity of the scene
+    rng = np.random.default_rng(9)
+    mesh_ids = np.nonzero(scene["types"] == 0)[0]
+    m = 2500
+    att = rng.choice(mesh_ids, m, replace=False).astype(np.int32)
+    parent_entity = rng.integers(0, n, m)
+    inst = rng.integers(0, n_inst, m).astype(np.uint32)
+    bone = rng.integers(0, 40, m).astype(np.uint32)
+    rel = np.concatenate([(rng.normal(size=(m, 3)) * 0.5).astype(np.float32), scenes.random_unit_quats(rng, m)], axis=1).astype(np.float32)
+    par = np.ascontiguousarray(sk["transforms"][parent_entity])
+    scale = np.ascontiguousarray(sk["transforms"]["scale"][att])
+    br = (0.5 + 2.0 * rng.random(m)).astype(np.float32)  # Model::getOriginBoundingRadius of the attached entities' models
+    dev = {k: ctx.to_device(v) for k, v in dict(ent=att, inst=inst, bone=bone, rel=rel, par=par, scale=scale, br=br).items()}
+    dev["out_tr"] = ctx.to_device(np.zeros(m, lb.TRANSFORM_DTYPE))
+    dev["pos3"] = ctx.to_device(np.zeros((m, 3), np.float64))
+    dev["rad"] = ctx.to_device(np.zeros(m, np.float32))
+    anim.boneAttachmentsDevice(m, dev["inst"], dev["bone"], dev["rel"], dev["par"], dev["scale"], dev["out_tr"])
+    S.moveDevice(dev["ent"], dev["out_tr"], m, dev["br"], dev["pos3"], dev["rad"])
+    cs.set_replicas(1)
+    cs.set_many_device(dev["pos3"], dev["rad"], m, dev_entities=dev["ent"], max_entity=n - 1)
+    # the oracle's side of the same frame
+    bone7 = np.concatenate([pos[inst, bone], rot[inst, bone]], axis=1).astype(np.float32)
+    exp_tr = oracle.bone_attachments(np.ascontiguousarray(par).view(np.uint8).reshape(m, 56), bone7, rel, scale).view(lb.TRANSFORM_DTYPE).reshape(-1)
+    got_tr = ctx.copy_to_host(dev["out_tr"], m, lb.TRANSFORM_DTYPE)
+    for field in ("pos", "rot", "scale"):
+        assert got_tr[field].tobytes() == exp_tr[field].tobytes()
+    exp_rad = (br * np.max(exp_tr["scale"], axis=1)).astype(np.float32)
+    assert np.array_equal(ctx.copy_to_host(dev["rad"], m, np.float32), exp_rad)
+    oc.set(att, np.ascontiguousarray(exp_tr["pos"]), exp_rad)
+    transforms2 = sk["transforms"].copy()
+    transforms2[att] = exp_tr
+    flags2 = sk["flags"].copy()
+    flags2[att] |= sortkeys.MOVED
+    lod, pf = sk["lod"].copy(), sk["pose_frame"].copy()
+    a = scenes.c1_frustum_args()
+    cam = dict(a, far=2500.0)
+    f = lb.frustum_perspective(**cam)
+    for frame, flags in ((0, flags2), (1, sk["flags"])):  # frame 1 comes after endFrame: MOVED is off again, the transforms stay
+        view = sortkeys.make_view(cam["position"], cam["position"], 1.0 / 30.0, 1.0, 60 + frame, False, sk["max_sort_key"], sk["layer_to_bucket"], sk["depth_sorted_buckets"])
+        cs.cull_device(f, want_counts=False)
+        res = S.createSortKeys(cs, view)
+        got = S.read(res)
+        oids, otys, _ = oc.cull(lb.culling.frustum_bytes(f))
+        exp = oracle.create_sort_keys(oids, otys, transforms2, sk["model_of"], lod, flags, pf, sk["decal_sort_key"], sk["decal_layer"], sk["models"], sk["meshes"], view)
+        assert res.n_keys == len(exp["keys"]) > 100
+        _compare(got, exp, lod, pf, n)
+        if frame == 0:
+            moved_visible = np.isin(att, oids).sum()
+            assert moved_visible > 50, "the scene should have attached entities in view"
+            S.endFrame()
+            prev = S.prevTransforms()
+            for field in ("pos", "rot", "scale"):
+                assert prev[field][att].tobytes() == exp_tr[field].tobytes()
+            rest = np.ones(n, bool)
+            rest[att] = False
+            assert not prev["pos"][rest].any()
+    for p in dev.values():
+        ctx.free_device(p)
+    anim.close()
+    S.close()
+    cs.close()
