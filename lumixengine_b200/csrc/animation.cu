@@ -777,6 +777,8 @@ int lb200_animation_create(lb200_ctx* ctx, const lb200_skeleton* sk, const lb200
 	LB200_CUDA(ctx, cudaStreamSynchronize(st));
 	{
 		const int smem_max = (int)(sizeof(float4) * (2 * 196 * (POSE_THREADS / 8) + 2 * 196 + 128));
+		const int smem_max4 = (int)std::min<size_t>(220 * 1024, sizeof(float4) * (2 * 196 * (POSE_THREADS / 4) + 2 * 196 + 128));
+		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max4));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 		LB200_CUDA(ctx, cudaFuncSetAttribute(pose_palette_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -843,15 +845,20 @@ int lb200_animation_update(lb200_animation* a, float time_delta, uint32_t flags)
 	P.dt_negative = !(time_delta > 0);
 	P.dt_ticks = (uint32_t)((P.dt_negative ? -time_delta : time_delta) * (float)(1 << 15));
 	P.advance = 1;
-	static const int g_env = [] { const char* e = getenv("LB200_POSE_LANES"); const int v = e ? atoi(e) : 0; return (v == 8 || v == 16 || v == 32) ? v : 0; }();
-	const int G = g_env ? g_env : a->lanes_per_instance;
+	static const int g_env = [] { const char* e = getenv("LB200_POSE_LANES"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 8 || v == 16 || v == 32) ? v : 0; }();
+	int G = g_env ? g_env : a->lanes_per_instance;
+	if (G == 4) { // 32 instances per block: only while their poses fit in shared memory
+		const uint32_t bp = (a->bone_count + 3u) & ~3u;
+		if (sizeof(float4) * (2 * (size_t)bp * (POSE_THREADS / 4) + 2 * bp + 128) > 200 * 1024) G = 8;
+	}
 	const unsigned per_block = POSE_THREADS / G;
 	const unsigned blocks = (a->n_instances + per_block - 1) / per_block;
 	const uint32_t Bp_ = (a->bone_count + 3u) & ~3u;
 	const uint32_t n_ls_ = (a->max_level + 2u + 3u) & ~3u;
 	const size_t shared_words16 = 2 * Bp_ + (n_ls_ * 4 + Bp_ * 2 + Bp_ + 15) / 16; // inverse bind + topology, in float4 units
 	const size_t smem = sizeof(float4) * (shared_words16 + 2 * (size_t)Bp_ * per_block);
-	if (G == 8) pose_palette_kernel<8><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
+	if (G == 4) pose_palette_kernel<4><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
+	else if (G == 8) pose_palette_kernel<8><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
 	else if (G == 16) pose_palette_kernel<16><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
 	else pose_palette_kernel<32><<<blocks, POSE_THREADS, smem, ctx->stream>>>(P);
 	LB200_CHECK_LAUNCH(ctx);

@@ -20,8 +20,8 @@
 //             block 0 also writes group_offset and one key/value per non-empty group (:3958-3969).
 //     pass 2  the stashed decisions are replayed: keys / values (:53-143) at the claimed slots, pose / dirty lists, and for every
 //             auto-instanced mesh the 48 bytes of instance data (:3990-4008) straight at group_offset + the block's slice + rank.
-//   radix_sort_kernel  LSD, 8 bits per pass over the 64-bit keys, stable, hand-written, ONE cooperative launch for all passes: passes in
-//             which every key has the same digit are skipped (OR / AND of all keys; the reference skips the all-in-bin-0 case, :4120);
+//   radix_sort_kernel  LSD, 8 bits per pass over the 64-bit keys, stable, hand-written, ONE cooperative launch for all passes: only bits that
+//             differ between keys are sorted on (OR of all keys / of all complements; the reference skips the all-in-bin-0 case, :4120);
 //             per pass block histograms -> grid barrier -> every block sums the histograms of the blocks before it -> stable scatter
 //             (warp match + per-warp digit counters) -> grid barrier.  No library sort.
 // The reference runs createSortKeys on every job worker with one AutoInstancer per worker; this is the one-instancer form (instancer
@@ -112,7 +112,7 @@ struct EmitArgs {
 	uint64_t* __restrict__ keys; uint64_t* __restrict__ values; uint32_t* counts;
 	uint32_t* group_count; uint32_t* group_offset; uint32_t* group_cursor; const uint8_t* __restrict__ group_layer;
 	uint64_t* __restrict__ group_renderables; float4* __restrict__ instance_data;
-	uint32_t* __restrict__ pose_list; uint32_t* __restrict__ dirty_list; uint32_t* __restrict__ stash;
+	uint32_t* __restrict__ pose_list; uint32_t* __restrict__ dirty_list; uint32_t* __restrict__ stash; float4* __restrict__ stash4; uint32_t stash_stride;
 	GridBar* bar;
 };
 
@@ -156,9 +156,11 @@ __device__ __forceinline__ MeshKind mesh_kind(const lb200_sk_mesh& mm, uint32_t 
 }
 
 // MESH renderable, pass 1 (:3868-3956): LOD selection + smoothing state + pose claim; counts what pass 2 will write
-__device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, float lod_multiplier_rcp, int32_t e, Counts& c) {
+__device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, float lod_multiplier_rcp, int32_t e, uint32_t i, Counts& c) {
 	SkEntity* rec = A.ent + e;
-	const int4 q0 = *reinterpret_cast<const int4*>(rec), q1 = *(reinterpret_cast<const int4*>(rec) + 1); // sector 0 (plain loads: this kernel writes lod)
+	// the whole record, one 64-byte burst (plain loads: this kernel writes lod / pose_frame)
+	const int4* rp = reinterpret_cast<const int4*>(rec);
+	const int4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
 	const double px = __hiloint2double(q0.y, q0.x), py = __hiloint2double(q0.w, q0.z), pz = __hiloint2double(q1.y, q1.x);
 	const uint32_t model_flags = (uint32_t)q1.z;
 	float cur = __int_as_float(q1.w);
@@ -183,6 +185,13 @@ __device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitAr
 		}
 		rec->lod = cur;
 	}
+	// what pass 2 writes per auto-instanced mesh (:3990-4008) or depth-sorted key (:3915-3922), stashed next to the decision in arrays indexed
+	// like the visible list: pass 2 reads them coalesced and never touches the record again
+	const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
+	const uint32_t depth_bits = float_flip(__float_as_uint((float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz))));
+	A.stash4[i] = make_float4(__int_as_float(q2.x), __int_as_float(q2.y), __int_as_float(q2.z), __int_as_float(q2.w));                 // rot
+	A.stash4[A.stash_stride + i] = make_float4((float)rx, (float)ry, (float)rz, __uint_as_float(depth_bits));                            // Vec3(tr.pos - camera_pos), depth key
+	A.stash4[2 * (size_t)A.stash_stride + i] = make_float4(__int_as_float(q3.x), __int_as_float(q3.y), __int_as_float(q3.z), cur);    // scale, lod after the update
 	const bool moved_not_shadow = (fl & LB200_SK_MOVED) && !is_shadow;
 	uint32_t code = model_idx | (lod0 << CODE_LOD_SHIFT) | (two ? CODE_TWO : 0u) | ((fl & LB200_SK_MOVED) ? CODE_MOVED : 0u);
 	// the meshes of lod0 and, while the lod blends over, of lod0 + 1: one loop over both ranges
@@ -203,7 +212,7 @@ __device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitAr
 	}
 	// once per instance and frame the palette has to be built (PoseProcessor::push; the compare-exchange on Pose::frame of :3890-3897 —
 	// one thread owns the instance within a view)
-	if (any_skinned && rec->pose_frame != P.view.frame_number) { rec->pose_frame = P.view.frame_number; code |= CODE_POSE; ++c.p; }
+	if (any_skinned && (uint32_t)q3.w != P.view.frame_number) { rec->pose_frame = P.view.frame_number; code |= CODE_POSE; ++c.p; }
 	return code;
 }
 
@@ -213,7 +222,7 @@ __device__ __forceinline__ void push_key(const EmitParams& P, const EmitArgs& A,
 }
 
 // MESH renderable, pass 2: replay of the stashed decision, writes
-__device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, int32_t e, uint32_t code, uint32_t& k, uint32_t& p) {
+__device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, int32_t e, uint32_t i, uint32_t code, uint32_t& k, uint32_t& p) {
 	if (code & CODE_DIRTY) { // queueMaterialOverrideRefresh (rare: its own atomic)
 		const uint32_t slot = atomicAdd(&A.counts[CNT_DIRTY], 1u);
 		if (slot < P.cap_dirty) A.dirty_list[slot] = (uint32_t)e;
@@ -227,14 +236,7 @@ __device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& 
 		if (p < P.cap_pose) A.pose_list[p] = (uint32_t)e;
 		++p;
 	}
-	// the entity's record: position for depth keys, everything for instance data (a MOVED or all-skinned renderable would not need it;
-	// both are rare, and one unconditional fetch keeps the warp together)
-	const int4* r = reinterpret_cast<const int4*>(A.ent + e);
-	const int4 q0 = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
-	const double px = __hiloint2double(q0.y, q0.x), py = __hiloint2double(q0.w, q0.z), pz = __hiloint2double(q1.y, q1.x);
-	const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
-	const float fx = (float)rx, fy = (float)ry, fz = (float)rz; // Vec3(tr.pos - camera_pos)
-	const uint32_t depth_bits = float_flip(__float_as_uint((float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz)))); // :3915-3922
+	const float4 s_rot = A.stash4[i], s_pos = A.stash4[A.stash_stride + i], s_scl = A.stash4[2 * (size_t)A.stash_stride + i]; // coalesced
 	const int from0 = lod_from(model, (int)lod0), to0 = lod_to(model, (int)lod0);
 	const int from1 = two ? lod_from(model, (int)lod0 + 1) : 0, to1 = two ? lod_to(model, (int)lod0 + 1) : -1;
 	const int n0 = max(to0 - from0 + 1, 0), n_all = n0 + max(to1 - from1 + 1, 0);
@@ -245,7 +247,7 @@ __device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& 
 		const MeshKind kind = mesh_kind(mm, bucket, moved_not_shadow);
 		const uint64_t mesh_value = sext(e) | ((uint64_t)mesh_idx << SORT_VALUE_MESH_IDX_SHIFT);
 		if (kind.key) {
-			const uint64_t low = kind.depth ? (uint64_t)depth_bits : (uint64_t)mm.sort_key;
+			const uint64_t low = kind.depth ? (uint64_t)__float_as_uint(s_pos.w) : (uint64_t)mm.sort_key;
 			push_key(P, A, k, low | ((uint64_t)(uint8_t)bucket << SORT_KEY_BUCKET_SHIFT), mesh_value | ((uint64_t)(kind.skinned ? DRAW_SKINNED : DRAW_MESH) << SORT_VALUE_TYPE_SHIFT));
 		}
 		if (kind.inst) { // instance data of the auto-instanced mesh, :3990-4008, at the group's offset + this block's slice + rank
@@ -253,9 +255,9 @@ __device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& 
 			if (at < P.cap_recs) {
 				A.group_renderables[at] = mesh_value;
 				float4* dst = A.instance_data + (size_t)at * 3;
-				dst[0] = make_float4(__int_as_float(q2.x), __int_as_float(q2.y), __int_as_float(q2.z), __int_as_float(q2.w)); // rot
-				dst[1] = make_float4(fx, fy, fz, LB_FSUB(__int_as_float(q1.w), mm.lod));                                     // camera-relative position, lod - mesh.lod
-				dst[2] = make_float4(__int_as_float(q3.x), __int_as_float(q3.y), __int_as_float(q3.z), __uint_as_float(mm.material_index)); // scale, material
+				dst[0] = s_rot;
+				dst[1] = make_float4(s_pos.x, s_pos.y, s_pos.z, LB_FSUB(s_scl.w, mm.lod)); // camera-relative position, lod - mesh.lod
+				dst[2] = make_float4(s_scl.x, s_scl.y, s_scl.z, __uint_as_float(mm.material_index));
 			}
 		}
 	}
@@ -318,10 +320,17 @@ __global__ void __launch_bounds__(SK_THREADS, 4) create_keys_kernel(const __grid
 			uint32_t e_next = 0;
 			if (i_next < n_all) {
 				e_next = visible_at(P, visible, i_next, n_mesh, n_decal);
-				if (i_next < n_mesh) prefetch_l2(A.ent + e_next); else prefetch_l2(A.decal_layer + e_next);
+				if (i_next < n_mesh) { prefetch_l2(A.ent + e_next); prefetch_l2(reinterpret_cast<const char*>(A.ent + e_next) + 32); }
+				else { prefetch_l2(A.decal_layer + e_next); prefetch_l2(A.decal_sort_key + e_next); }
 			}
-			if (i < n_mesh) A.stash[i] = mesh_count(P, A, s_bucket_map, s_grp, lod_multiplier_rcp, (int32_t)e, c);
-			else if ((uint8_t)s_bucket_map[A.decal_layer[e]] < 0xff) ++c.k; // DECAL / CURVE_DECAL renderable (:3840-3867): one key if its layer is in the view
+			if (i < n_mesh) A.stash[i] = mesh_count(P, A, s_bucket_map, s_grp, lod_multiplier_rcp, (int32_t)e, i, c);
+			else { // DECAL / CURVE_DECAL renderable (:3840-3867): one key if its layer is in the view; bucket and material sort key stashed for pass 2
+				const uint32_t bucket = (uint8_t)s_bucket_map[A.decal_layer[e]];
+				uint32_t key = 0;
+				if (bucket < 0xff) { key = A.decal_sort_key[e]; ++c.k; }
+				A.stash[i] = bucket;
+				A.stash4[i].x = __uint_as_float(key);
+			}
 			e = e_next;
 		}
 	}
@@ -375,16 +384,12 @@ __global__ void __launch_bounds__(SK_THREADS, 4) create_keys_kernel(const __grid
 		for (; i < n_all; i += stride) {
 			const uint32_t i_next = i + stride;
 			uint32_t e_next = 0;
-			if (i_next < n_all) {
-				e_next = visible_at(P, visible, i_next, n_mesh, n_decal);
-				if (i_next < n_mesh) { prefetch_l2(A.ent + e_next); prefetch_l2(reinterpret_cast<const char*>(A.ent + e_next) + 32); }
-				else prefetch_l2(A.decal_sort_key + e_next);
-			}
-			if (i < n_mesh) mesh_write(P, A, s_bucket_map, s_grp, (int32_t)e, A.stash[i], k, p);
+			if (i_next < n_all) e_next = visible_at(P, visible, i_next, n_mesh, n_decal);
+			if (i < n_mesh) mesh_write(P, A, s_bucket_map, s_grp, (int32_t)e, i, A.stash[i], k, p);
 			else {
 				const bool curve = i >= n_mesh + n_decal;
-				const uint8_t bucket = (uint8_t)s_bucket_map[A.decal_layer[e]];
-				if (bucket < 0xff) push_key(P, A, k, A.decal_sort_key[e] | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
+				const uint32_t bucket = A.stash[i];
+				if (bucket < 0xff) push_key(P, A, k, (uint64_t)__float_as_uint(A.stash4[i].x) | ((uint64_t)bucket << SORT_KEY_BUCKET_SHIFT),
 					sext((int32_t)e) | ((uint64_t)(curve ? DRAW_CURVE_DECAL : DRAW_DECAL) << SORT_VALUE_TYPE_SHIFT));
 			}
 			e = e_next;
@@ -484,10 +489,20 @@ __device__ __forceinline__ void digit_starts(const uint32_t* block_hist, uint32_
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t d = tid & 255u, part = tid >> 8;
 	uint32_t before = 0, total = 0;
-	for (uint32_t b = part; b < gridDim.x; b += RS_THREADS / 256) {
-		const uint32_t c = __ldcg(block_hist + b * 256 + d);
-		total += c;
-		if (b < blockIdx.x) before += c;
+	// 8 rows in flight per thread: the rows come from L2 and a row-at-a-time loop would pay one L2 round trip per row
+	for (uint32_t b0 = part; b0 < gridDim.x; b0 += 8 * (RS_THREADS / 256)) {
+		uint32_t c[8];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) {
+			const uint32_t b = b0 + u * (RS_THREADS / 256);
+			c[u] = b < gridDim.x ? __ldcg(block_hist + b * 256 + d) : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < 8; ++u) {
+			const uint32_t b = b0 + u * (RS_THREADS / 256);
+			total += c[u];
+			if (b < blockIdx.x) before += c[u];
+		}
 	}
 	s_part[part][d] = total;
 	s_bef[part][d] = before;
@@ -560,10 +575,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 		const uint32_t wbase = key_begin + warp * items * 32u;
 		uint64_t k[RS_REG_ITEMS], v[RS_REG_ITEMS];
 		uint16_t rk[RS_REG_ITEMS];
+		// digit windows: 8 bits from the lowest bit that still differs between keys, then from the next such bit above the window, ...
+		// (bytes in which every key agrees cost nothing, and a group of differing bits that straddles a byte border is one pass, not two)
 #pragma unroll 1
-		for (int pass = 0; pass < RS_PASSES; ++pass) {
-			const int shift = 8 * pass;
-			if (((varying >> shift) & 0xffull) == 0ull) continue; // every key has the same digit here: the pass would move nothing
+		for (unsigned long long left = varying; left != 0ull;) {
+			const int shift = __ffsll((long long)left) - 1;
+			left &= ~(0xffull << shift);
 			const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
 			const uint64_t* vsrc = cur ? vbuf1 : vbuf0;
 			uint64_t* kdst = cur ? kbuf0 : kbuf1;
@@ -616,9 +633,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 	}
 	else {
 #pragma unroll 1
-		for (int pass = 0; pass < RS_PASSES; ++pass) {
-			const int shift = 8 * pass;
-			if (((varying >> shift) & 0xffull) == 0ull) continue;
+		for (unsigned long long left = varying; left != 0ull;) {
+			const int shift = __ffsll((long long)left) - 1;
+			left &= ~(0xffull << shift);
 			const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
 			const uint64_t* vsrc = cur ? vbuf1 : vbuf0;
 			uint64_t* kdst = cur ? kbuf0 : kbuf1;
@@ -730,7 +747,7 @@ struct lb200_sortkeys {
 	uint32_t* d_counts = nullptr; uint32_t* h_counts = nullptr; // pinned
 	uint32_t *d_group_count = nullptr, *d_group_offset = nullptr, *d_group_cursor = nullptr;
 	uint64_t* d_group_renderables = nullptr; float4* d_instance_data = nullptr;
-	uint32_t *d_pose_list = nullptr, *d_dirty_list = nullptr, *d_stash = nullptr;
+	uint32_t *d_pose_list = nullptr, *d_dirty_list = nullptr, *d_stash = nullptr; float4* d_stash4 = nullptr; // the two passes' hand-over: one word + 3 x float4 per visible renderable
 	float* d_lod = nullptr; uint32_t* d_pose_frame = nullptr; // unpacked on request (lb200_sortkeys_device_outputs)
 	uint32_t* d_moved_list = nullptr; uint32_t* d_moved_count = nullptr; lb200_transform* d_prev = nullptr; // RenderModule::m_moved_instances, ModelInstance::prev_frame_transform (first move onwards)
 	GridBar* d_bar = nullptr;
@@ -784,6 +801,7 @@ int lb200_sortkeys_create(lb200_ctx* ctx, uint32_t max_entities, uint32_t max_gr
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_pose_list, sizeof(uint32_t) * E));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_dirty_list, sizeof(uint32_t) * E));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_stash, sizeof(uint32_t) * E));
+	LB200_CUDA(ctx, cudaMalloc(&sk->d_stash4, sizeof(float4) * 3 * E));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_bar, sizeof(GridBar)));
 	LB200_CUDA(ctx, cudaMemsetAsync(sk->d_bar, 0, sizeof(GridBar), ctx->stream));
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_sort_state, sizeof(SortState)));
@@ -802,7 +820,7 @@ void lb200_sortkeys_destroy(lb200_sortkeys* sk) {
 	for (int b = 0; b < 2; ++b) { cudaFree(sk->d_keys[b]); cudaFree(sk->d_values[b]); }
 	cudaFree(sk->d_counts); if (sk->h_counts) cudaFreeHost(sk->h_counts);
 	cudaFree(sk->d_group_count); cudaFree(sk->d_group_offset); cudaFree(sk->d_group_cursor);
-	cudaFree(sk->d_group_renderables); cudaFree(sk->d_instance_data); cudaFree(sk->d_pose_list); cudaFree(sk->d_dirty_list); cudaFree(sk->d_stash);
+	cudaFree(sk->d_group_renderables); cudaFree(sk->d_instance_data); cudaFree(sk->d_pose_list); cudaFree(sk->d_dirty_list); cudaFree(sk->d_stash); cudaFree(sk->d_stash4);
 	cudaFree(sk->d_lod); cudaFree(sk->d_pose_frame); cudaFree(sk->d_bar); cudaFree(sk->d_moved_list); cudaFree(sk->d_moved_count); cudaFree(sk->d_prev);
 	cudaFree(sk->d_sort_state); cudaFree(sk->d_block_hist);
 	delete sk;
@@ -922,7 +940,7 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 	const uint32_t work = type_counts[RT_MESH] + type_counts[RT_DECAL] + type_counts[RT_CURVE_DECAL]; // upper bound of visible renderables
 	uint32_t grid = std::max(1u, std::min(limit, (work + SK_THREADS - 1) / SK_THREADS));
 	EmitArgs EA = {sk->d_ent, sk->d_decal_sort_key, sk->d_decal_layer, sk->d_models, sk->d_meshes, sk->d_keys[0], sk->d_values[0], sk->d_counts,
-		sk->d_group_count, sk->d_group_offset, sk->d_group_cursor, sk->d_group_layer, sk->d_group_renderables, sk->d_instance_data, sk->d_pose_list, sk->d_dirty_list, sk->d_stash, sk->d_bar};
+		sk->d_group_count, sk->d_group_offset, sk->d_group_cursor, sk->d_group_layer, sk->d_group_renderables, sk->d_instance_data, sk->d_pose_list, sk->d_dirty_list, sk->d_stash, sk->d_stash4, sk->max_entities, sk->d_bar};
 	void* args[] = {&EP, &visible, &cull_counters, &EA, &n_groups};
 	LB200_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)create_keys_kernel, dim3(grid), dim3(SK_THREADS), args, smem, s));
 	LB200_CHECK_LAUNCH(ctx);
