@@ -369,7 +369,11 @@ def c5_mixed(ctx, lb, scenes, rank, world, dist, steps, warmup):
     f = lb.frustum_perspective(**scenes.c2_frustum_args())
     sk = scenes.skeleton(64)
     clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
-    anim = lb.AnimationSystem(ctx, sk, clips, scenes.mesh(sk, 64), max_instances=n_inst)
+    # culling and the animation update are independent jobs of a frame (the engine runs them concurrently on its job system): here they are
+    # two streams — the animation system lives on a second context of the same device — so the NVLink-bound id gather and the arithmetic-
+    # bound pose pass overlap
+    ctx_anim = lb.Context(ctx.device)
+    anim = lb.AnimationSystem(ctx_anim, sk, clips, scenes.mesh(sk, 64), max_instances=n_inst)
     ci, tt = scenes.instance_times(n_inst, clips, seed=9 + rank)
     anim.setInstances(ci, tt)
     first = cs.cull(f)
@@ -405,7 +409,7 @@ def c5_mixed(ctx, lb, scenes, rank, world, dist, steps, warmup):
         slabs, counts = cs.read_gathered(dev, slab, world)
         seen = []
         for r in range(world):
-            off = np.concatenate([[0], np.cumsum(counts[r])])
+            off = np.concatenate([[0], np.cumsum(counts[r].astype(np.int64))])  # int64: cumsum of uint32 is uint64, which numpy promotes to float next to an int
             seen.append([[int(counts[r][t]), int(slabs[r][off[t]:off[t + 1]].astype(np.uint64).sum(dtype=np.uint64)),
                           int(np.bitwise_xor.reduce(slabs[r][off[t]:off[t + 1]].astype(np.uint64))) if counts[r][t] else 0] for t in range(4)])
         mine = torch.tensor(own, dtype=torch.int64, device="cuda")
@@ -416,9 +420,26 @@ def c5_mixed(ctx, lb, scenes, rank, world, dist, steps, warmup):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         verified = bool(flag.item())
         dist.barrier()
-    ms = time_region(ctx, lambda: [step() for _ in range(steps)], 1) / steps
-    ms_cull = time_region(ctx, lambda: [cs.cull_gather(f, slab) if world > 1 else cs.cull_device(f, want_counts=False) for _ in range(steps)], 1) / steps
-    ms_pose = time_region(ctx, lambda: [anim.update(1.0 / 60.0, lb.PALETTE_DUAL_QUAT) for _ in range(steps)], 1) / steps
+    def region(fn):  # K steps between two events on the culling stream; the closing event is recorded once the animation stream has drained too
+        ctx_anim.synchronize()
+        e0, e1 = ctx.event(), ctx.event()
+        ctx.synchronize()
+        ctx.record(e0)
+        fn()
+        ctx_anim.synchronize()
+        ctx.record(e1)
+        return ctx.elapsed_ms(e0, e1)
+    if world > 1:
+        dist.barrier()
+    ms = region(lambda: [step() for _ in range(steps)]) / steps
+    ms_cull = region(lambda: [cs.cull_gather(f, slab) if world > 1 else cs.cull_device(f, want_counts=False) for _ in range(steps)]) / steps
+    ea, eb = ctx_anim.event(), ctx_anim.event()
+    ctx_anim.synchronize()
+    ctx_anim.record(ea)
+    for _ in range(steps):
+        anim.update(1.0 / 60.0, lb.PALETTE_DUAL_QUAT)
+    ctx_anim.record(eb)
+    ms_pose = ctx_anim.elapsed_ms(ea, eb) / steps
     vis_total = visible
     if world > 1:
         import torch
@@ -429,13 +450,14 @@ def c5_mixed(ctx, lb, scenes, rank, world, dist, steps, warmup):
         dist.all_reduce(v)
         vis_total = int(v.item())
     anim.close()
+    ctx_anim.close()
     cs.close()
     return {"value": C5_ENTITIES / ms / 1e3, "unit": "M entities/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world,
             "entities_total": C5_ENTITIES, "skinned_instances_total": C5_INSTANCES, "entities_per_gpu": n_ent, "instances_per_gpu": n_inst,
             "visible_total": vis_total, "parts_ms": {"cull_and_gather": ms_cull, "pose_palette": ms_pose}, "exchange": mode, "exchange_verified": verified,
             "gather_bytes_received_per_gpu": int(vis_total - visible) * 4, "scene_build_s": build_s,
-            "note": "a step = cull of the rank's shard + all-gather of the visible ids + pose / dual-quaternion palette of the rank's instances, on one stream; "
-                    "device time, max over ranks; value = 50M entities / step time at every N"}
+            "note": "a step = [cull of the rank's shard + all-gather of the visible ids] on one stream and [pose / dual-quaternion palette of the rank's instances] on a second "
+                    "one (independent jobs of a frame); device time of K steps until both streams have drained, max over ranks; value = 50M entities / step time at every N"}
 
 
 def ours(a, rank, world):
@@ -444,6 +466,9 @@ def ours(a, rank, world):
 
     dist = None
     if world > 1:
+        # exchange steps of a lane wait for the peers' flags: more lanes in flight hide more of that (N=2: 14.5 us per step with 3 lanes, 11.1 with 6;
+        # profiles/r2_N2_time_exchange.log).  Read once by the library when the first culling system is created.
+        os.environ.setdefault("LB200_CULL_LANES", "6")
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         import torch
         import torch.distributed as dist
@@ -638,7 +663,7 @@ def ours(a, rank, world):
         "config": {**shared_config(visible), "pages": n_pages_c2,
                    "l2": f"{REPLICAS} rotating copies of the page arrays ({REPLICAS} x ~{n_pages_c2 * 4064 // 1_000_000} MB): successive culls never re-read an L2-resident scene",
                    "parallelism": f"dp{world}: whole cell pages per rank" + (("; exchanged each step: " + exchange_desc) if world > 1 else ""),
-                   "submission": "K culls = one lb200_culling_cull_device_n call: consecutive (independent) culls on 3 streams / output lanes, half-occupancy grids, programmatic dependent launch" if world == 1 else "K exchange steps = one lb200_culling_cull_exchange_n call (steps on 3 streams, 6 exchange buffers per rank)",
+                   "submission": "K culls = one lb200_culling_cull_device_n call: consecutive (independent) culls on 3 streams / output lanes, half-occupancy grids, programmatic dependent launch" if world == 1 else f"K exchange steps = one lb200_culling_cull_exchange_n call (steps on {os.environ.get('LB200_CULL_LANES', '3')} streams / output lanes, 3 x lanes exchange buffers per rank)",
                    "lone_cull_ms": ms_lone, "lone_empty_interval_ms": lone["empty_interval"], "lone_empty_kernel_ms": lone["empty_kernel"],
                    "scene_build_s": build_s, "page_stats": stats},
         "gpu_launches": int(launches),

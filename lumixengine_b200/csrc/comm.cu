@@ -114,11 +114,11 @@ int lb200_comm_enable_p2p(lb200_ctx* ctx, uint32_t max_slab_ids) {
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	lb200_ctx::Peer& P = ctx->peer;
 	P.slab_words = (256 + (size_t)max_slab_ids + 63) & ~(size_t)63;
-	const size_t flag_bytes = 512;
+	const size_t flag_bytes = 1024;
 	const size_t buf_bytes = sizeof(uint32_t) * P.slab_words * (size_t)R;
 	P.lanes = lb200_cull_lanes(); // the same on every rank (same environment)
-	P.n_buffers = 2 * P.lanes;
-	static_assert(2 * LB200_MAX_LANES * LB200_MAX_RANKS * sizeof(uint32_t) <= 512, "flag block");
+	P.n_buffers = 3 * P.lanes;
+	static_assert(3 * LB200_MAX_LANES * LB200_MAX_RANKS * sizeof(uint32_t) <= 1024, "flag block");
 	const size_t total = flag_bytes + P.n_buffers * buf_bytes;
 	LB200_CUDA(ctx, cudaMalloc(&P.local_block, total));
 	LB200_CUDA(ctx, cudaMemsetAsync(P.local_block, 0, flag_bytes, ctx->stream));

@@ -231,6 +231,27 @@ __global__ void __launch_bounds__(288) publish_wait_kernel(const __grid_constant
 	__threadfence_system();
 }
 
+// The two halves as kernels of their own for the pipelined form (lb200_culling_cull_exchange_n): publish stays on the lane's stream behind the
+// cull, the wait (wait_peers_kernel) goes to the lane's second stream, so the lane's next cull does not sit behind a peer's flag round trip.
+__global__ void __launch_bounds__(288) publish_kernel(const __grid_constant__ PublishParams P, const uint32_t* counters) {
+	const uint32_t i = threadIdx.x;
+	if (i < XHEADER_WORDS) {
+		uint32_t v = 0;
+		if (i < 256) v = __ldcg(counters + i);
+		else if (i == 256) v = P.n_pages;
+		else if (i == 257) v = __ldcg(counters + CNT_N_REC);
+		else if (i == 259) v = P.item_cap;
+		for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][i] = v;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (i < P.n_ranks) {
+		__threadfence_system();
+		volatile uint32_t* f = P.flags[i] + (P.epoch % P.n_buffers) * LB200_MAX_RANKS + P.rank;
+		*f = P.epoch;
+	}
+}
+
 // holds the stream for a while, so that whatever the host enqueues behind it is already queued when the device gets there
 __global__ void delay_kernel(long long cycles) {
 	const long long t0 = clock64();
@@ -270,6 +291,10 @@ struct lb200_culling {
 	cudaStream_t lane_stream[MAX_LANES] = {};
 	cudaEvent_t lane_event[MAX_LANES] = {};
 	cudaEvent_t fork_event = nullptr;
+	// pipelined exchange (lb200_culling_cull_exchange_n): the wait of an epoch runs on a second stream of its lane
+	cudaStream_t wait_stream[MAX_LANES] = {};
+	cudaEvent_t ev_published[MAX_LANES][4] = {}, ev_waited[MAX_LANES][4] = {};
+	uint64_t lane_cycle[MAX_LANES] = {}; // exchange steps this lane has issued
 	uint64_t seq = 0;
 	uint32_t* d_out_ids = nullptr;  // lanes * out_cap
 	uint32_t out_cap = 0;
@@ -641,6 +666,8 @@ void lb200_culling_destroy(lb200_culling* cs) {
 		for (uint32_t l = 0; l < lb200_culling::MAX_LANES; ++l) {
 			if (cs->lane_stream[l]) { cudaStreamSynchronize(cs->lane_stream[l]); cudaStreamDestroy(cs->lane_stream[l]); }
 			if (cs->lane_event[l]) cudaEventDestroy(cs->lane_event[l]);
+			if (cs->wait_stream[l]) { cudaStreamSynchronize(cs->wait_stream[l]); cudaStreamDestroy(cs->wait_stream[l]); }
+			for (int k = 0; k < 4; ++k) { if (cs->ev_published[l][k]) cudaEventDestroy(cs->ev_published[l][k]); if (cs->ev_waited[l][k]) cudaEventDestroy(cs->ev_waited[l][k]); }
 		}
 		if (cs->fork_event) cudaEventDestroy(cs->fork_event);
 		if (cs->done_event) cudaEventDestroy(cs->done_event);
@@ -1126,6 +1153,38 @@ static int exchangeStep(lb200_culling* cs, const lb200_shifted_frustum* frustum,
 	return LB200_OK;
 }
 
+// One step of the pipelined form on lane l = epoch % lanes (see lb200_ctx::Peer): cull and publish on the lane's stream, the wait on the
+// lane's second stream; cull(e) behind wait(e - 2 x lanes), publish(e) behind wait(e - lanes).
+static int exchangeStepPipelined(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type) {
+	lb200_ctx* ctx = cs->ctx;
+	lb200_ctx::Peer& peer = ctx->peer;
+	Exchange x;
+	x.epoch = ++peer.epoch;
+	const uint32_t l = x.epoch % cs->lanes;
+	const uint64_t k = cs->lane_cycle[l]++;
+	cudaStream_t lane = cs->lane_stream[l], side = cs->wait_stream[l];
+	// events never recorded yet make these waits no-ops (the lane's first two steps)
+	LB200_CUDA(ctx, cudaStreamWaitEvent(lane, cs->ev_waited[l][(k + 2) % 4], 0)); // = cycle k - 2
+	int rc = launchCull(cs, frustum, type, &x, lane);
+	if (rc) return rc;
+	LB200_CUDA(ctx, cudaStreamWaitEvent(lane, cs->ev_waited[l][(k + 3) % 4], 0)); // = cycle k - 1
+	PublishParams PP;
+	PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = x.epoch; PP.n_buffers = peer.n_buffers;
+	PP.n_pages = cs->last_pages; PP.item_cap = cs->item_cap;
+	for (int r = 0; r < LB200_MAX_RANKS; ++r) {
+		PP.dst[r] = r < ctx->n_ranks ? peer.gather[x.epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+		PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
+	}
+	publish_kernel<<<1, 288, 0, lane>>>(PP, (const uint32_t*)cs->last_counters);
+	LB200_CHECK_LAUNCH(ctx);
+	LB200_CUDA(ctx, cudaEventRecord(cs->ev_published[l][k % 4], lane));
+	LB200_CUDA(ctx, cudaStreamWaitEvent(side, cs->ev_published[l][k % 4], 0));
+	wait_peers_kernel<<<1, 32, 0, side>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, x.epoch, peer.n_buffers, peer.d_timeout);
+	LB200_CHECK_LAUNCH(ctx);
+	LB200_CUDA(ctx, cudaEventRecord(cs->ev_waited[l][k % 4], side));
+	return LB200_OK;
+}
+
 static void lastExchange(lb200_culling* cs, const uint32_t** out_dev_ids, const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words) {
 	const lb200_ctx::Peer& peer = cs->ctx->peer;
 	if (out_dev_ids) *out_dev_ids = cs->last_out;
@@ -1169,12 +1228,38 @@ int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum
 	// flag round trip overlap the neighbouring steps' culls; see lb200_ctx::Peer for why 2 x lanes exchange buffers make that safe
 	rc = forkLanes(cs);
 	if (rc) return rc;
+	// default: store, publish, wait in lane order (publish_wait_kernel).  LB200_EXCHANGE_PIPELINED=1: the wait on a second stream per lane
+	// (exchangeStepPipelined) — validated at N=2, where it measured no better (profiles/r2_N2b_time_exchange.log), so it is not the default
+	static const bool pipelined = [] { const char* e = getenv("LB200_EXCHANGE_PIPELINED"); return e && atoi(e) != 0; }();
+	if (!pipelined) {
+		for (uint32_t i = 0; i < n; ++i) {
+			rc = exchangeStep(cs, frustum, type, cs->lane_stream[(ctx->peer.epoch + 1) % cs->lanes], nullptr);
+			if (rc) return rc;
+		}
+		lastExchange(cs, out_dev_ids, out_dev_slabs, out_slab_stride_words);
+		return joinLanes(cs);
+	}
+	if (!cs->wait_stream[0]) {
+		for (uint32_t l = 0; l < cs->lanes; ++l) {
+			LB200_CUDA(ctx, cudaStreamCreateWithFlags(&cs->wait_stream[l], cudaStreamNonBlocking));
+			for (int k = 0; k < 4; ++k) {
+				LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->ev_published[l][k], cudaEventDisableTiming));
+				LB200_CUDA(ctx, cudaEventCreateWithFlags(&cs->ev_waited[l][k], cudaEventDisableTiming));
+			}
+		}
+	}
 	for (uint32_t i = 0; i < n; ++i) {
-		rc = exchangeStep(cs, frustum, type, cs->lane_stream[(ctx->peer.epoch + 1) % cs->lanes], nullptr);
+		rc = exchangeStepPipelined(cs, frustum, type);
 		if (rc) return rc;
 	}
 	lastExchange(cs, out_dev_ids, out_dev_slabs, out_slab_stride_words);
-	return joinLanes(cs);
+	rc = joinLanes(cs);
+	if (rc) return rc;
+	for (uint32_t l = 0; l < cs->lanes; ++l) { // the step is over when its wait is: the main stream also joins the lanes' wait streams
+		const uint64_t k = cs->lane_cycle[l];
+		if (k) LB200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cs->ev_waited[l][(k - 1) % 4], 0));
+	}
+	return LB200_OK;
 }
 
 uint32_t lb200_culling_exchange_slab_words(lb200_culling* cs) {

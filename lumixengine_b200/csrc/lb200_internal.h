@@ -13,7 +13,7 @@
 
 #define LB200_MAX_RANKS 8
 #define LB200_CULL_STAGE_DEFAULT 0 // pages in flight per warp through the bulk-copy engine (cull_kernel.cuh); LB200_CULL_STAGE overrides
-#define LB200_MAX_LANES 8  // concurrent culls (streams / output lanes); exchange buffers = 2 x lanes
+#define LB200_MAX_LANES 8  // concurrent culls (streams / output lanes); exchange buffers = 3 x lanes
 
 struct lb200_ctx {
 	int device = -1;
@@ -31,12 +31,15 @@ struct lb200_ctx {
 	struct Peer {
 		bool ready = false;
 		size_t slab_words = 0;            // capacity of one rank's slab (header + ids)
-		// Exchange epoch e uses buffer e % n_buffers, n_buffers = 2 x lanes.  With lanes > 1 (lb200_culling_cull_exchange_n) epoch e is
-		// issued on stream e % lanes.  A rank overwrites buffer b for epoch e only after its wait for epoch e - lanes on the same
-		// stream, i.e. after every rank published e - lanes, which every rank issues behind whatever consumed e - 2 x lanes there.
-		uint32_t lanes = 1, n_buffers = 2;
+		// Exchange epoch e uses buffer e % n_buffers, n_buffers = 3 x lanes.  With lanes > 1 (lb200_culling_cull_exchange_n) epoch e is
+		// issued on stream e % lanes and its WAIT on a second stream of that lane: the lane only holds publish(e) back until wait(e - lanes)
+		// is over and the cull of e until wait(e - 2 x lanes) is over, so a peer's flag round trip never stalls the next cull.  A rank
+		// overwrites buffer b for epoch e only after its wait for e - 2 x lanes, i.e. after every rank published e - 2 x lanes, which every
+		// rank does behind its wait for (and whatever consumed) e - 3 x lanes: the previous owner of b.  tests/test_exchange_protocol_model.py
+		// replays this under a random scheduler (and shows that 2 x lanes buffers would not do).
+		uint32_t lanes = 1, n_buffers = 3;
 		void* local_block = nullptr;      // this rank's allocation: [flags n_buffers x 8 x u32 in 512 B][gather 0] .. [gather n_buffers-1]
-		uint32_t* gather[2 * LB200_MAX_LANES][LB200_MAX_RANKS] = {}; // gather[b][r] = rank r's buffer b as seen from this process
+		uint32_t* gather[3 * LB200_MAX_LANES][LB200_MAX_RANKS] = {}; // gather[b][r] = rank r's buffer b as seen from this process
 		uint32_t* flags[LB200_MAX_RANKS] = {};     // flags[r] = rank r's flag block
 		void* opened[LB200_MAX_RANKS] = {};        // cudaIpcOpenMemHandle results to close
 		uint32_t* done_counter = nullptr; // local, one per lane, for the last-block election

@@ -60,25 +60,22 @@ struct alignas(64) SkEntity {
 static_assert(sizeof(SkEntity) == 64, "one burst per entity");
 
 // ---- grid-wide barrier of a cooperative launch (every block of the grid is resident) ----
-struct GridBar { uint32_t count, gen; };
+// One word that only counts up (zeroed before the launch): barrier number k of the launch is complete when it reads k * gridDim.  Per block:
+// one release-add by thread 0 after the block barrier, then acquire-polls — no generation word, no reset by a last arriver.
+struct GridBar { uint32_t count, pad; };
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 	uint32_t v;
 	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void grid_barrier(GridBar* b) {
+__device__ __forceinline__ void grid_barrier(GridBar* b, uint32_t& passed /* barriers this block has been through; starts at 0 */) {
 	__syncthreads();
+	++passed;
 	if (threadIdx.x == 0) {
-		const uint32_t gen = ld_acquire_gpu(&b->gen); // cannot advance before this block has arrived
-		__threadfence();                              // this block's writes before the arrival
-		if (atomicAdd(&b->count, 1u) == gridDim.x - 1) {
-			b->count = 0;
-			__threadfence();
-			atomicAdd(&b->gen, 1u);
-		}
-		else {
-			while (ld_acquire_gpu(&b->gen) == gen) {}
-		}
+		__threadfence(); // the block's writes (ordered before this by the block barrier) before the arrival
+		atomicAdd(&b->count, 1u);
+		const uint32_t target = passed * gridDim.x;
+		while (ld_acquire_gpu(&b->count) < target) {}
 		__threadfence(); // gpu-scope fence: also drops this SM's L1 lines, the block's plain loads behind the barrier see the other blocks' writes
 	}
 	__syncthreads();
@@ -88,6 +85,7 @@ struct EmitParams {
 	lb200_sk_view view;
 	uint32_t type_base[4]; // offsets of the MESH / DECAL / LOCAL_LIGHT / CURVE_DECAL segments inside out_ids
 	uint32_t cap_keys, cap_recs, cap_pose, cap_dirty;
+	uint32_t prefetch_ahead; // records requested into L2 this many grid strides ahead of their use (0 = off; LB200_SK_PREFETCH, default 1)
 };
 
 // :57-60
@@ -158,9 +156,9 @@ __device__ __forceinline__ MeshKind mesh_kind(const lb200_sk_mesh& mm, uint32_t 
 // MESH renderable, pass 1 (:3868-3956): LOD selection + smoothing state + pose claim; counts what pass 2 will write
 __device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitArgs& A, const uint32_t* s_bucket_map, uint32_t* s_grp, float lod_multiplier_rcp, int32_t e, uint32_t i, Counts& c) {
 	SkEntity* rec = A.ent + e;
-	// the whole record, one 64-byte burst (plain loads: this kernel writes lod / pose_frame)
+	// the whole record, one 64-byte burst (coherent loads: this kernel writes lod / pose_frame)
 	const int4* rp = reinterpret_cast<const int4*>(rec);
-	const int4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
+	const int4 q0 = __ldcg(rp), q1 = __ldcg(rp + 1), q2 = __ldcg(rp + 2), q3 = __ldcg(rp + 3); // L2 only: a record is touched once, L1 stays with the model / mesh tables
 	const double px = __hiloint2double(q0.y, q0.x), py = __hiloint2double(q0.w, q0.z), pz = __hiloint2double(q1.y, q1.x);
 	const uint32_t model_flags = (uint32_t)q1.z;
 	float cur = __int_as_float(q1.w);
@@ -189,9 +187,9 @@ __device__ __forceinline__ uint32_t mesh_count(const EmitParams& P, const EmitAr
 	// like the visible list: pass 2 reads them coalesced and never touches the record again
 	const double rx = LB_DSUB(px, P.view.camera_pos[0]), ry = LB_DSUB(py, P.view.camera_pos[1]), rz = LB_DSUB(pz, P.view.camera_pos[2]);
 	const uint32_t depth_bits = float_flip(__float_as_uint((float)LB_DADD(LB_DADD(LB_DMUL(rx, rx), LB_DMUL(ry, ry)), LB_DMUL(rz, rz))));
-	A.stash4[i] = make_float4(__int_as_float(q2.x), __int_as_float(q2.y), __int_as_float(q2.z), __int_as_float(q2.w));                 // rot
-	A.stash4[A.stash_stride + i] = make_float4((float)rx, (float)ry, (float)rz, __uint_as_float(depth_bits));                            // Vec3(tr.pos - camera_pos), depth key
-	A.stash4[2 * (size_t)A.stash_stride + i] = make_float4(__int_as_float(q3.x), __int_as_float(q3.y), __int_as_float(q3.z), cur);    // scale, lod after the update
+	__stcs(A.stash4 + i, make_float4(__int_as_float(q2.x), __int_as_float(q2.y), __int_as_float(q2.z), __int_as_float(q2.w)));                 // rot
+	__stcs(A.stash4 + A.stash_stride + i, make_float4((float)rx, (float)ry, (float)rz, __uint_as_float(depth_bits)));                            // Vec3(tr.pos - camera_pos), depth key
+	__stcs(A.stash4 + 2 * (size_t)A.stash_stride + i, make_float4(__int_as_float(q3.x), __int_as_float(q3.y), __int_as_float(q3.z), cur));    // scale, lod after the update
 	const bool moved_not_shadow = (fl & LB200_SK_MOVED) && !is_shadow;
 	uint32_t code = model_idx | (lod0 << CODE_LOD_SHIFT) | (two ? CODE_TWO : 0u) | ((fl & LB200_SK_MOVED) ? CODE_MOVED : 0u);
 	// the meshes of lod0 and, while the lod blends over, of lod0 + 1: one loop over both ranges
@@ -236,7 +234,7 @@ __device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& 
 		if (p < P.cap_pose) A.pose_list[p] = (uint32_t)e;
 		++p;
 	}
-	const float4 s_rot = A.stash4[i], s_pos = A.stash4[A.stash_stride + i], s_scl = A.stash4[2 * (size_t)A.stash_stride + i]; // coalesced
+	const float4 s_rot = __ldcs(A.stash4 + i), s_pos = __ldcs(A.stash4 + A.stash_stride + i), s_scl = __ldcs(A.stash4 + 2 * (size_t)A.stash_stride + i); // coalesced, read once
 	const int from0 = lod_from(model, (int)lod0), to0 = lod_to(model, (int)lod0);
 	const int from1 = two ? lod_from(model, (int)lod0 + 1) : 0, to1 = two ? lod_to(model, (int)lod0 + 1) : -1;
 	const int n0 = max(to0 - from0 + 1, 0), n_all = n0 + max(to1 - from1 + 1, 0);
@@ -253,11 +251,11 @@ __device__ __forceinline__ void mesh_write(const EmitParams& P, const EmitArgs& 
 		if (kind.inst) { // instance data of the auto-instanced mesh, :3990-4008, at the group's offset + this block's slice + rank
 			const uint32_t at = s_grp ? atomicAdd(&s_grp[mm.sort_key], 1u) : warp_claim_keyed(A.group_cursor, mm.sort_key);
 			if (at < P.cap_recs) {
-				A.group_renderables[at] = mesh_value;
+				__stcs(reinterpret_cast<unsigned long long*>(A.group_renderables) + at, (unsigned long long)mesh_value);
 				float4* dst = A.instance_data + (size_t)at * 3;
-				dst[0] = s_rot;
-				dst[1] = make_float4(s_pos.x, s_pos.y, s_pos.z, LB_FSUB(s_scl.w, mm.lod)); // camera-relative position, lod - mesh.lod
-				dst[2] = make_float4(s_scl.x, s_scl.y, s_scl.z, __uint_as_float(mm.material_index));
+				__stcs(dst, s_rot);
+				__stcs(dst + 1, make_float4(s_pos.x, s_pos.y, s_pos.z, LB_FSUB(s_scl.w, mm.lod))); // camera-relative position, lod - mesh.lod
+				__stcs(dst + 2, make_float4(s_scl.x, s_scl.y, s_scl.z, __uint_as_float(mm.material_index)));
 			}
 		}
 	}
@@ -315,13 +313,18 @@ __global__ void __launch_bounds__(SK_THREADS, 4) create_keys_kernel(const __grid
 	{
 		uint32_t i = blockIdx.x * SK_THREADS + threadIdx.x;
 		uint32_t e = i < n_all ? visible_at(P, visible, i, n_mesh, n_decal) : 0u;
+		const uint32_t ahead = P.prefetch_ahead * stride;
 		for (; i < n_all; i += stride) {
 			const uint32_t i_next = i + stride;
 			uint32_t e_next = 0;
-			if (i_next < n_all) {
-				e_next = visible_at(P, visible, i_next, n_mesh, n_decal);
-				if (i_next < n_mesh) { prefetch_l2(A.ent + e_next); prefetch_l2(reinterpret_cast<const char*>(A.ent + e_next) + 32); }
-				else { prefetch_l2(A.decal_layer + e_next); prefetch_l2(A.decal_sort_key + e_next); }
+			if (i_next < n_all) e_next = visible_at(P, visible, i_next, n_mesh, n_decal);
+			if (ahead) {
+				const uint32_t i_pf = i + ahead;
+				if (i_pf < n_all) {
+					const uint32_t e_pf = ahead == stride ? e_next : visible_at(P, visible, i_pf, n_mesh, n_decal);
+					if (i_pf < n_mesh) { prefetch_l2(A.ent + e_pf); prefetch_l2(reinterpret_cast<const char*>(A.ent + e_pf) + 32); }
+					else { prefetch_l2(A.decal_layer + e_pf); prefetch_l2(A.decal_sort_key + e_pf); }
+				}
 			}
 			if (i < n_mesh) A.stash[i] = mesh_count(P, A, s_bucket_map, s_grp, lod_multiplier_rcp, (int32_t)e, i, c);
 			else { // DECAL / CURVE_DECAL renderable (:3840-3867): one key if its layer is in the view; bucket and material sort key stashed for pass 2
@@ -343,7 +346,8 @@ __global__ void __launch_bounds__(SK_THREADS, 4) create_keys_kernel(const __grid
 	}
 	// the block's slice of every group it has instances of: count -> start inside the group
 	if (s_grp) for (uint32_t g = threadIdx.x; g < n_groups; g += SK_THREADS) if (s_grp[g]) s_grp[g] = atomicAdd(&A.group_count[g], s_grp[g]);
-	grid_barrier(A.bar); // every block's counts are in: group totals are final
+	uint32_t barriers_passed = 0;
+	grid_barrier(A.bar, barriers_passed); // every block's counts are in: group totals are final
 
 	// ---- group offsets = exclusive scan of the group totals; block 0 publishes them and one key/value per non-empty group (:3958-3969) ----
 	if (s_grp || blockIdx.x == 0) {
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(SK_THREADS, 4) create_keys_kernel(const __grid
 		}
 		if (blockIdx.x == 0 && threadIdx.x == 0) { A.counts[CNT_INST] = s_carry; A.counts[CNT_RECS] = s_carry; }
 	}
-	if (!s_grp) grid_barrier(A.bar); // more groups than fit in shared memory: everybody waits for block 0's cursors in HBM
+	if (!s_grp) grid_barrier(A.bar, barriers_passed); // more groups than fit in shared memory: everybody waits for block 0's cursors in HBM
 
 	// ---- pass 2: write ----
 	uint32_t k = s_base[0] + pk, p = s_base[1] + pp;
@@ -537,6 +541,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 	__shared__ unsigned long long s_red[2][RS_WARPS];
 	const uint32_t n = min(counts[0], cap);
 	if (n < 2) return; // uniform over the grid: nothing to sort (buffer 0 already holds the result)
+	uint32_t barriers_passed = 0;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const bool in_regs = n <= gridDim.x * (uint32_t)RS_THREADS * reg_items;
 	uint32_t key_begin, key_end, tile_begin = 0, tile_end = 0, items = 0;
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 			if (key_begin < key_end) { atomicOr(&st->key_or, o); atomicOr(&st->key_or_not, a); }
 		}
 	}
-	grid_barrier(&st->bar);
+	grid_barrier(&st->bar, barriers_passed);
 	const unsigned long long varying = __ldcg(&st->key_or) & __ldcg(&st->key_or_not); // bits that are 1 in some key and 0 in another
 
 	uint32_t cur = 0;
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 				for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = s_wcnt[w][tid]; s_wcnt[w][tid] = acc; acc += t; }
 				block_hist[blockIdx.x * 256 + tid] = acc;
 			}
-			grid_barrier(&st->bar);
+			grid_barrier(&st->bar, barriers_passed);
 			digit_starts(block_hist, s_hist, s_part, s_bef, s_wsum);
 #pragma unroll
 			for (int j = 0; j < RS_REG_ITEMS; ++j) {
@@ -627,7 +632,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 					vdst[dest] = v[j];
 				}
 			}
-			grid_barrier(&st->bar);
+			grid_barrier(&st->bar, barriers_passed);
 			cur ^= 1u;
 		}
 	}
@@ -646,7 +651,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 			for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) atomicAdd(&s_hist[(uint32_t)(__ldcg(ksrc + i) >> shift) & 0xffu], 1u);
 			__syncthreads();
 			if (tid < 256) block_hist[blockIdx.x * 256 + tid] = s_hist[tid];
-			grid_barrier(&st->bar);
+			grid_barrier(&st->bar, barriers_passed);
 			digit_starts(block_hist, s_hist, s_part, s_bef, s_wsum);
 			// stable scatter, tile by tile
 			for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 				}
 				__syncthreads();
 			}
-			grid_barrier(&st->bar);
+			grid_barrier(&st->bar, barriers_passed);
 			cur ^= 1u;
 		}
 	}
@@ -930,6 +935,8 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 	EP.view = *view;
 	for (int t = 0; t < 4; ++t) EP.type_base[t] = type_base[t];
 	EP.cap_keys = sk->cap_keys; EP.cap_recs = sk->cap_recs; EP.cap_pose = sk->max_entities; EP.cap_dirty = sk->max_entities;
+	static const uint32_t prefetch_ahead = [] { const char* e = getenv("LB200_SK_PREFETCH"); const int v = e ? atoi(e) : 1; return (uint32_t)std::max(0, std::min(v, 4)); }();
+	EP.prefetch_ahead = prefetch_ahead;
 	const bool in_smem = n_groups <= SK_SMEM_GROUPS;
 	size_t smem = in_smem ? sizeof(uint32_t) * n_groups : 0;
 	uint32_t& limit = sk->keys_grid_limit[in_smem ? 0 : 1];
@@ -938,7 +945,8 @@ int lb200_sortkeys_create_keys(lb200_sortkeys* sk, lb200_culling* cs, const lb20
 		if (rc) return rc;
 	}
 	const uint32_t work = type_counts[RT_MESH] + type_counts[RT_DECAL] + type_counts[RT_CURVE_DECAL]; // upper bound of visible renderables
-	uint32_t grid = std::max(1u, std::min(limit, (work + SK_THREADS - 1) / SK_THREADS));
+	static const uint32_t blocks_per_sm = [] { const char* e = getenv("LB200_SK_BLOCKS_PER_SM"); const int v = e ? atoi(e) : 0; return (uint32_t)std::max(0, v); }(); // tuning: fewer resident blocks than fit
+	uint32_t grid = std::max(1u, std::min(blocks_per_sm ? std::min(limit, blocks_per_sm * (uint32_t)ctx->sm_count) : limit, (work + SK_THREADS - 1) / SK_THREADS));
 	EmitArgs EA = {sk->d_ent, sk->d_decal_sort_key, sk->d_decal_layer, sk->d_models, sk->d_meshes, sk->d_keys[0], sk->d_values[0], sk->d_counts,
 		sk->d_group_count, sk->d_group_offset, sk->d_group_cursor, sk->d_group_layer, sk->d_group_renderables, sk->d_instance_data, sk->d_pose_list, sk->d_dirty_list, sk->d_stash, sk->d_stash4, sk->max_entities, sk->d_bar};
 	void* args[] = {&EP, &visible, &cull_counters, &EA, &n_groups};

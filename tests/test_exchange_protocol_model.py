@@ -11,8 +11,11 @@ import random
 import pytest
 
 
-def simulate(ranks, lanes, batches, rng):
-    nbuf = 2 * lanes
+def simulate(ranks, lanes, batches, rng, pipelined=False):
+    """pipelined=False: the one-stream-per-lane form (store, publish, wait in lane order; 2L buffers).
+    pipelined=True: lb200_culling_cull_exchange_n's form — the wait of epoch e runs on a second stream of the lane, the lane itself only
+    holds publish(e) back until wait(e - L) is over and store(e) until wait(e - 2L) is over; 3L buffers."""
+    nbuf = (3 if pipelined else 2) * lanes
     # rows[r][b][src] = epoch whose rows rank `src` last stored into buffer b of rank r; flags likewise
     rows = [[[0] * ranks for _ in range(nbuf)] for _ in range(ranks)]
     flags = [[[0] * ranks for _ in range(nbuf)] for _ in range(ranks)]
@@ -21,6 +24,7 @@ def simulate(ranks, lanes, batches, rng):
     progs = []
     for r in range(ranks):
         ops, last_on = [], {}   # last_on[stream] = id of the previous op on that stream
+        wait_of = {}            # pipelined form: epoch -> id of its wait op
 
         def add(stream, kind, epoch, extra=()):
             deps = [last_on[stream]] if stream in last_on else []
@@ -38,9 +42,18 @@ def simulate(ranks, lanes, batches, rng):
                 lane = ("lane", epoch % lanes)
                 first = lane not in used
                 used.add(lane)
-                s = add(lane, "store", epoch, extra=[fork] if first else ())
-                p = add(lane, "publish", epoch)
-                w = add(lane, "wait", epoch)
+                if not pipelined:
+                    s = add(lane, "store", epoch, extra=[fork] if first else ())
+                    p = add(lane, "publish", epoch)
+                    w = add(lane, "wait", epoch)
+                else:
+                    side = ("wait", epoch % lanes)
+                    used.add(side)
+                    dep2 = [wait_of[epoch - 2 * lanes]] if epoch - 2 * lanes in wait_of else []
+                    dep1 = [wait_of[epoch - lanes]] if epoch - lanes in wait_of else []
+                    s = add(lane, "store", epoch, extra=([fork] if first else []) + dep2)
+                    p = add(lane, "publish", epoch, extra=dep1)
+                    wait_of[epoch] = add(side, "wait", epoch, extra=[p])
             tails = [last_on[l] for l in used]
             join = add("main", "join", 0, extra=tails)
             add("main", "consume", epoch)  # the out parameters describe the LAST step of the batch
@@ -82,12 +95,36 @@ def test_no_early_overwrite_and_no_deadlock(ranks, lanes):
         simulate(ranks, lanes, batches, rng)
 
 
+@pytest.mark.parametrize("ranks,lanes", [(2, 1), (2, 2), (2, 3), (3, 3), (8, 3), (4, 4), (8, 6)])
+def test_pipelined_waits_no_early_overwrite_and_no_deadlock(ranks, lanes):
+    rng = random.Random(77 * ranks + lanes)
+    for trial in range(12 if ranks < 8 else 3):
+        batches = [rng.randint(1, 14) for _ in range(rng.randint(2, 5))]
+        simulate(ranks, lanes, batches, rng, pipelined=True)
+
+
+def test_the_model_catches_too_few_buffers_for_pipelined_waits():
+    """With the waits off the lane streams, 2L buffers are not enough any more: a fast rank overwrites rows a slow rank still waits for."""
+    def broken(ranks, lanes, batches, rng):
+        g = dict(simulate.__globals__)
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if pipelined else 2) * lanes", "nbuf = 2 * lanes")
+        exec(src, g)
+        return g["simulate"](ranks, lanes, batches, rng, pipelined=True)
+    failures = 0
+    for seed in range(60):
+        try:
+            broken(2, 2, [9, 9, 9], random.Random(seed))
+        except AssertionError:
+            failures += 1
+    assert failures > 0
+
+
 def test_the_model_catches_too_few_buffers():
     """Sanity of the model itself: with only L buffers (instead of 2L) a fast rank does overwrite rows a slow rank has not consumed."""
     def broken(ranks, lanes, batches, rng):
         import types
         g = dict(simulate.__globals__)
-        src = __import__("inspect").getsource(simulate).replace("nbuf = 2 * lanes", "nbuf = lanes")
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if pipelined else 2) * lanes", "nbuf = lanes")
         exec(src, g)
         return g["simulate"](ranks, lanes, batches, rng)
     failures = 0
