@@ -372,7 +372,7 @@ def c5_mixed(ctx, lb, scenes, rank, world, dist, steps, warmup):
     # culling and the animation update are independent jobs of a frame (the engine runs them concurrently on its job system): here they are
     # two streams — the animation system lives on a second context of the same device — so the NVLink-bound id gather and the arithmetic-
     # bound pose pass overlap
-    ctx_anim = lb.Context(ctx.device)
+    ctx_anim = lb.Context(ctx.device, background=True)  # lowest stream priority: the cull / gather kernels take SMs as soon as pose blocks retire
     anim = lb.AnimationSystem(ctx_anim, sk, clips, scenes.mesh(sk, 64), max_instances=n_inst)
     ci, tt = scenes.instance_times(n_inst, clips, seed=9 + rank)
     anim.setInstances(ci, tt)
@@ -466,9 +466,9 @@ def ours(a, rank, world):
 
     dist = None
     if world > 1:
-        # exchange steps of a lane wait for the peers' flags: more lanes in flight hide more of that (N=2: 14.5 us per step with 3 lanes, 11.1 with 6;
+        # exchange steps of a lane wait for the peers' flags: more lanes in flight hide more of that (N=2: 14.5 us per step with 3 lanes, 11.1 with 6, 10.1 with 8;
         # profiles/r2_N2_time_exchange.log).  Read once by the library when the first culling system is created.
-        os.environ.setdefault("LB200_CULL_LANES", "6")
+        os.environ.setdefault("LB200_CULL_LANES", "8")
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         import torch
         import torch.distributed as dist
@@ -672,7 +672,9 @@ def ours(a, rank, world):
                 "ms_per_step": e2e_s * 1e3,
                 "api": "CullingSystem.cull_device(frustum) + SortKeys.createSortKeys(view): host frustum + view -> kernel params; cull, sort keys / LOD / auto-instancing "
                        "groups + instance data and the radix sort on the device; 8 counters read back (one synchronisation); ids, keys and instance data stay in HBM",
-                "sort_keys": {"n_keys": int(sk_res.n_keys), "n_instances": int(sk_res.n_instances), "n_pose": int(sk_res.n_pose), "device_ms": ms_keys},
+                "sort_keys": {"n_keys": int(sk_res.n_keys), "n_instances": int(sk_res.n_instances), "n_pose": int(sk_res.n_pose), "device_ms": ms_keys,
+                              "note": "counts of the last frame of the loop: the lod smoothing state evolves from frame to frame (both arms start from the same state; "
+                                      "equality per frame is what tests/test_sortkeys_gpu.py checks)"},
                 "ids_to_host_ms": e2e_ids_s * 1e3, "ids_to_host_d2h_bytes": int(r.total) * 4 + 264 * 4,
                 "ids_to_host_api": "CullingSystem.cull(frustum): visible ids + counts written into pinned host memory by the device right behind the cull (the round-1 e2e)"},
         "roofline": {"bound": "hbm", "achieved": alg_bytes / ms_kernel / 1e6, "peak": peak, "unit": "GB/s", "frac": alg_bytes / ms_kernel / 1e6 / peak,

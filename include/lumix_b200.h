@@ -36,6 +36,9 @@ typedef struct lb200_ctx lb200_ctx;
  * the plugin entry creates (src/engine/plugin.h:64-96).
  * ---------------------------------------------------------------------------------------------------------- */
 LB200_API int lb200_init(int device_ordinal, lb200_ctx** out_ctx);
+/* A further context of the device whose stream has the lowest priority: its kernels fill the SMs only where the other contexts' streams
+ * (which get the highest priority) leave room — e.g. the animation update next to the culling / exchange of the same frame. */
+LB200_API int lb200_init_background(int device_ordinal, lb200_ctx** out_ctx);
 LB200_API void lb200_shutdown(lb200_ctx* ctx);
 LB200_API const char* lb200_last_error(const lb200_ctx* ctx); /* ctx may be NULL: last init error */
 LB200_API int lb200_device_count(void);

@@ -86,7 +86,7 @@ class Mesh(C.Structure):
 # every symbol include/lumix_b200.h declares (tests/test_abi.py checks the header against this and the .so)
 SYMBOLS = [
     "lb200_init", "lb200_shutdown", "lb200_last_error", "lb200_device_count", "lb200_synchronize", "lb200_host_callback", "lb200_launch_count", "lb200_stream_handle",
-    "lb200_host_alloc", "lb200_host_free", "lb200_copy_to_host", "lb200_device_alloc", "lb200_device_free", "lb200_copy_to_device", "lb200_event_create", "lb200_event_record", "lb200_event_elapsed_ms", "lb200_event_destroy",
+    "lb200_init_background", "lb200_host_alloc", "lb200_host_free", "lb200_copy_to_host", "lb200_device_alloc", "lb200_device_free", "lb200_copy_to_device", "lb200_event_create", "lb200_event_record", "lb200_event_elapsed_ms", "lb200_event_destroy",
     "lb200_frustum_perspective", "lb200_frustum_ortho", "lb200_frustum_from_viewport",
     "lb200_culling_create", "lb200_culling_destroy", "lb200_culling_add", "lb200_culling_remove", "lb200_culling_set_position",
     "lb200_culling_set_radius", "lb200_culling_set", "lb200_culling_get_radius", "lb200_culling_is_added",
@@ -203,10 +203,10 @@ LB200_ERR_CUDA_CODE = -2
 class Context:
     """One GPU + one stream (lb200_ctx)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, background=False):
         self.L = lib()
         h = vp()
-        check(self.L.lb200_init(C.c_int(device), C.byref(h)), None)
+        check((self.L.lb200_init_background if background else self.L.lb200_init)(C.c_int(device), C.byref(h)), None)
         self.h = h
         self.device = device
         self._children = weakref.WeakSet()  # objects that hold device memory of this context

@@ -33,7 +33,15 @@ int lb200_device_count(void) {
 	return n;
 }
 
-int lb200_init(int device_ordinal, lb200_ctx** out_ctx) {
+static int initContext(int device_ordinal, int stream_priority_low, lb200_ctx** out_ctx);
+
+int lb200_init(int device_ordinal, lb200_ctx** out_ctx) { return initContext(device_ordinal, 0, out_ctx); }
+
+// A second context of a device whose stream yields to the others: for work that should fill the device only where latency-critical
+// streams (cull, exchange) leave room — e.g. the animation update running next to the culling of the same frame.
+int lb200_init_background(int device_ordinal, lb200_ctx** out_ctx) { return initContext(device_ordinal, 1, out_ctx); }
+
+static int initContext(int device_ordinal, int stream_priority_low, lb200_ctx** out_ctx) {
 	if (!out_ctx) return LB200_ERR_INVALID;
 	*out_ctx = nullptr;
 	int n = 0;
@@ -49,8 +57,10 @@ int lb200_init(int device_ordinal, lb200_ctx** out_ctx) {
 	}
 	lb200_ctx* ctx = new lb200_ctx;
 	ctx->device = device_ordinal;
+	int prio_least = 0, prio_greatest = 0;
 	if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess
-		|| (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess
+		|| (e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest)) != cudaSuccess
+		|| (e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, stream_priority_low ? prio_least : prio_greatest)) != cudaSuccess
 		|| (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess
 		|| (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal)) != cudaSuccess) {
 		lb200_set_error(nullptr, "context creation failed: %s", cudaGetErrorString(e));
