@@ -673,6 +673,11 @@ def ours(a, rank, world):
                 "api": "CullingSystem.cull_device(frustum) + SortKeys.createSortKeys(view): host frustum + view -> kernel params; cull, sort keys / LOD / auto-instancing "
                        "groups + instance data and the radix sort on the device; 8 counters read back (one synchronisation); ids, keys and instance data stay in HBM",
                 "sort_keys": {"n_keys": int(sk_res.n_keys), "n_instances": int(sk_res.n_instances), "n_pose": int(sk_res.n_pose), "device_ms": ms_keys,
+                              # 64 B record + 52 B stash written + 52 B read per visible renderable, 56 B per instance, 16 B per key written,
+                              # 8 B of ids; the radix sort's 32 B per pair and pass stay in L2 (12 MB) and are not counted
+                              "algorithmic_bytes": int(176 * int(visible) + 56 * int(sk_res.n_instances) + 16 * int(sk_res.n_keys)),
+                              "hbm_frac": (176 * int(visible) + 56 * int(sk_res.n_instances) + 16 * int(sk_res.n_keys)) / ms_keys / 1e6 / peak,
+                              "traffic": (traffic_from_profile("create_keys_kernel") or 0) + (traffic_from_profile("radix_sort_kernel") or 0),
                               "note": "counts of the last frame of the loop: the lod smoothing state evolves from frame to frame (both arms start from the same state; "
                                       "equality per frame is what tests/test_sortkeys_gpu.py checks)"},
                 "ids_to_host_ms": e2e_ids_s * 1e3, "ids_to_host_d2h_bytes": int(r.total) * 4 + 264 * 4,

@@ -401,7 +401,10 @@ typedef struct {
 typedef struct { uint16_t bone_index; uint16_t pad; float value[3]; } lb200_const_translation; /* animation.h:86-90 */
 typedef struct { uint16_t bone_index; uint16_t pad; float value[4]; } lb200_const_rotation;    /* animation.h:100-104 */
 
-/* struct Animation, animation.h:158-170 (in-memory form after Animation::load, animation.cpp:397-493) */
+/* struct Animation, animation.h:158-170 (in-memory form after Animation::load, animation.cpp:397-493).  Root motion is NOT part of this struct:
+ * for a clip with root-motion tracks the reference substitutes m_root_motion.pose_translations / pose_rotations for the root bone's tracks
+ * (animation.cpp:33-37, 321); the library would sample the packed tracks instead, so such clips must stay on the engine's own path — the
+ * engine binding (host/animation_b200.inl) leaves their animables to updateAnimable. */
 typedef struct {
 	float fps;
 	uint32_t frame_count;

@@ -143,9 +143,16 @@ __global__ void __launch_bounds__(256) pack_push_kernel(const __grid_constant__ 
 			if (gtid < head) { const uint32_t v = src[gtid]; for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][256 + off + gtid] = v; }
 			const uint32_t n4 = (lim - head) / 4;
 			const uint4* src4 = reinterpret_cast<const uint4*>(src + head);
-			for (uint32_t i = gtid; i < n4; i += gsize) {
-				const uint4 v = src4[i];
-				for (uint32_t r = 0; r < P.n_ranks; ++r) reinterpret_cast<uint4*>(P.dst[r] + 256 + off + head)[i] = v;
+			// four 128-bit loads in flight per thread before the peer stores: the stores are posted, the loads are what a thread waits for
+			for (uint32_t i0 = gtid; i0 < n4; i0 += 4 * gsize) {
+				uint4 v[4];
+#pragma unroll
+				for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * gsize; if (i < n4) v[u] = src4[i]; }
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					const uint32_t i = i0 + u * gsize;
+					if (i < n4) for (uint32_t r = 0; r < P.n_ranks; ++r) reinterpret_cast<uint4*>(P.dst[r] + 256 + off + head)[i] = v[u];
+				}
 			}
 			const uint32_t done = head + 4 * n4;
 			if (gtid < lim - done) { const uint32_t v = src[done + gtid]; for (uint32_t r = 0; r < P.n_ranks; ++r) P.dst[r][256 + off + done + gtid] = v; }

@@ -30,7 +30,10 @@ struct AnimablesB200 {
 		Array<float> pos, rot;     // read-back: bone_count * 3 / * 4 floats per member
 	};
 
-	explicit AnimablesB200(IAllocator& allocator) : m_allocator(allocator), m_groups(allocator) {}
+	explicit AnimablesB200(IAllocator& allocator) : m_allocator(allocator), m_groups(allocator), m_reference_path(allocator) {}
+	// animables update() left alone because their clip has root-motion tracks (Animation::getRelativePose substitutes its own pose arrays for
+	// those tracks, animation.cpp:33-37 — not part of lb200_clip): the module runs them through updateAnimable as before
+	const Array<u32>& referencePath() const { return m_reference_path; }
 	~AnimablesB200() { clear(); }
 	void clear() {
 		for (Group* g : m_groups) { lb200_animation_destroy(g->handle); LUMIX_DELETE(m_allocator, g); }
@@ -40,9 +43,11 @@ struct AnimablesB200 {
 	// One updateAnimables pass.  Returns false (and logs) if the library reported an error; animables already written back stay written.
 	bool update(lb200_ctx* ctx, RenderSide& render, Span<Animable> animables, float time_delta) {
 		for (Group* g : m_groups) g->members.clear();
+		m_reference_path.clear();
 		for (u32 i = 0; i < animables.length(); ++i) { // the early-outs of updateAnimable, animation_module.cpp:440-445
 			Animable& a = animables[i];
 			if (!a.animation || !a.animation->isReady()) continue;
+			if (a.animation->hasRootMotionTracksB200()) { m_reference_path.push(i); continue; }
 			Model* model = render.getModelInstanceModel(a.entity);
 			if (!model || !model->isReady()) continue;
 			Group* g = nullptr;
@@ -194,6 +199,7 @@ private:
 
 	IAllocator& m_allocator;
 	Array<Group*> m_groups;
+	Array<u32> m_reference_path;
 };
 
 } // namespace Lumix

@@ -5,3 +5,4 @@
 	const u8* getRotationStreamB200() const { return m_rotation_stream; }
 	u32 getStreamEndB200() const { return u32(m_mem.size()); } // both streams live in m_mem, which ends with the unpacker's 8 bytes of padding (animation.cpp:439)
 	const u8* getStreamBaseB200() const { return m_mem.empty() ? nullptr : &m_mem[0]; }
+	bool hasRootMotionTracksB200() const { return m_root_motion.rotation_track_idx >= 0 || m_root_motion.translation_track_idx >= 0; } // animation.cpp:33-37, 321
