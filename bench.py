@@ -386,11 +386,16 @@ def c5_mixed(ctx, lb, scenes, rank, world, dist, steps, warmup):
         t = torch.tensor([slab], dtype=torch.int64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         slab = int(t.item())
+        mapped = getattr(ctx, "p2p_slab_ids", None)
         if os.environ.get("LB200_C5_EXCHANGE", "p2p") == "p2p":
-            ctx.comm_enable_p2p(slab)  # no-op if the headline run already mapped buffers at least this large
+            if mapped is None:
+                ctx.comm_enable_p2p(slab)
+                mapped = ctx.p2p_slab_ids = slab
+        # lb200_culling_cull_gather pushes over NVLink when the slab fits the mapped peer buffers and goes through ncclAllGather otherwise
+        if mapped is not None and slab <= mapped:
             mode = "visible id lists: fused pack + NVLink peer push + epoch flags (lb200_culling_cull_gather)"
         else:
-            mode = "visible id lists: pack + ncclAllGather (lb200_culling_cull_gather without peer mapping)"
+            mode = "visible id lists: pack + ncclAllGather (lb200_culling_cull_gather; the mapped peer buffers hold %s ids, the slab needs %d)" % (mapped, slab)
 
     def step():
         if world > 1:
@@ -511,10 +516,17 @@ def ours(a, rank, world):
         if exchange == "mask":
             t = torch.tensor([cs.exchange_slab_words()], dtype=torch.int64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ctx.comm_enable_p2p(int(t.item()) - 256)
+            # the peer buffers are mapped once per process: sized for the larger of this exchange's slabs and config 5's id lists (the same view
+            # sees 18 % of the C2 distribution: 25 % of the rank's 50M / N entities + margin), so that config 5 below runs its gather over NVLink too
+            p2p_ids = int(t.item()) - 256
+            if not a.only_cull and not a.no_c5 and os.environ.get("LB200_C5_EXCHANGE", "p2p") == "p2p":
+                p2p_ids = max(p2p_ids, C5_ENTITIES // world // 4 + 4096)
+            ctx.comm_enable_p2p(p2p_ids)
+            ctx.p2p_slab_ids = p2p_ids
             exchange_desc = "visibility bitmask rows + per-type counts stored into every rank's memory by the cull kernel (NVLink peer stores, epoch flags); id lists stay sharded"
         elif os.environ.get("LB200_NO_P2P") != "1":
             ctx.comm_enable_p2p(slab)  # per-frame exchange = fused pack + NVLink peer stores + epoch flags (no NCCL call per step)
+            ctx.p2p_slab_ids = slab
             exchange_desc = "visible id lists: fused pack + NVLink peer push"
         else:
             exchange_desc = "visible id lists: pack + ncclAllGather"
@@ -558,6 +570,32 @@ def ours(a, rank, world):
         ms_total = float(t.item())
         dist.barrier()
     ms_step = ms_total / a.steps
+
+    # N>1, bitmask exchange: one exchanged step is checked — what every rank sees of rank r's slab (per-type counts, visibility rows by page
+    # id) must be what rank r holds itself, and rank r's own rows must say exactly what its own cull made visible
+    exchange_verified = None
+    if world > 1 and exchange == "mask":
+        import torch
+        _, slabs_ptr, stride = cs.cull_exchange(f)
+        ctx.synchronize()
+        seen = cs.read_exchanged(slabs_ptr, stride, world)
+
+        def slab_digest(sl):
+            rows = sl["mask"].astype(np.uint64)
+            page_w = (np.arange(rows.shape[0], dtype=np.uint64)[:, None] * np.uint64(8) + np.arange(8, dtype=np.uint64)[None, :] + np.uint64(1))
+            bits = int(np.unpackbits(sl["mask"].view(np.uint8)).sum())
+            return [int(sl["counts"].astype(np.int64).sum()), bits, int(sl["n_pages"]), int((rows * page_w).sum(dtype=np.uint64) & np.uint64(0x7fffffffffffffff))]
+        mine = torch.tensor([slab_digest(seen[r]) for r in range(world)], dtype=torch.int64, device="cuda")  # my view of every rank
+        views = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(views, mine)
+        views = [v.cpu().tolist() for v in views]
+        own = cs.cull(f)
+        ok = all(views[q][r] == views[r][r] for q in range(world) for r in range(world))          # everybody sees rank r as rank r sees itself
+        ok = ok and views[rank][rank][0] == int(own.total) and views[rank][rank][1] == int(own.total)  # counts and set bits = my visible set
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_verified = bool(flag.item())
+        dist.barrier()
 
     # algorithmic bytes of one cull (needs counts: one more cull, untimed)
     cs.cull_device(f, want_counts=True)
@@ -689,7 +727,9 @@ def ours(a, rank, world):
                      "lone_note": "one cull, device to itself, CUDA events (1 us ticks) around it; the interval costs lone_empty_interval_ms with nothing in it and lone_empty_kernel_ms with one empty kernel",
                      "scan_all_equivalent_gbs": (16 * N_ENTITIES + 8 * visible + N_ENTITIES / 8) / ms_kernel / 1e6},
         "build": build_info(),
-        "parity": {"gpu_digest": gpu_digest, "digest": "per renderable type [count, sum of ids, xor of ids] of the visible set of one C2 cull"},
+        "parity": {"gpu_digest": gpu_digest, "digest": "per renderable type [count, sum of ids, xor of ids] of the visible set of one C2 cull",
+                   **({"exchange_verified": exchange_verified, "exchange_check": "one exchanged step: every rank's view of every rank's slab (per-type counts, visibility rows "
+                       "by page id) equals that rank's own, and a rank's rows / counts say exactly what its own cull made visible"} if exchange_verified is not None else {})},
     }
     if not a.only_cull and not a.no_c5:
         try:

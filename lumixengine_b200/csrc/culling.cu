@@ -302,6 +302,7 @@ struct lb200_culling {
 	cudaStream_t wait_stream[MAX_LANES] = {};
 	cudaEvent_t ev_published[MAX_LANES][4] = {}, ev_waited[MAX_LANES][4] = {};
 	uint64_t lane_cycle[MAX_LANES] = {}; // exchange steps this lane has issued
+	uint32_t lane_owed[MAX_LANES] = {};  // deferred form: the epoch of the lane's previous step, whose wait has not been issued yet (0 = none)
 	uint64_t seq = 0;
 	uint32_t* d_out_ids = nullptr;  // lanes * out_cap
 	uint32_t out_cap = 0;
@@ -1192,6 +1193,36 @@ static int exchangeStepPipelined(lb200_culling* cs, const lb200_shifted_frustum*
 	return LB200_OK;
 }
 
+// One step of the default form of lb200_culling_cull_exchange_n on lane l = epoch % lanes (see lb200_ctx::Peer): everything on the lane's
+// stream, but the wait a step issues is the one its lane still owes for the PREVIOUS step — cull(e), wait(e - lanes), publish(e) — so the
+// flags it asks for were raised a whole lane cycle ago and the stream practically never stalls on a peer.  With 3 x lanes buffers nobody
+// overwrites early (tests/test_exchange_protocol_model.py, deferred=True).  The caller issues the waits still owed before it joins.
+static int exchangeStepDeferred(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type) {
+	lb200_ctx* ctx = cs->ctx;
+	lb200_ctx::Peer& peer = ctx->peer;
+	Exchange x;
+	x.epoch = ++peer.epoch;
+	const uint32_t l = x.epoch % cs->lanes;
+	cudaStream_t lane = cs->lane_stream[l];
+	int rc = launchCull(cs, frustum, type, &x, lane);
+	if (rc) return rc;
+	if (cs->lane_owed[l]) {
+		wait_peers_kernel<<<1, 32, 0, lane>>>(peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, cs->lane_owed[l], peer.n_buffers, peer.d_timeout);
+		LB200_CHECK_LAUNCH(ctx);
+	}
+	PublishParams PP;
+	PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = x.epoch; PP.n_buffers = peer.n_buffers;
+	PP.n_pages = cs->last_pages; PP.item_cap = cs->item_cap;
+	for (int r = 0; r < LB200_MAX_RANKS; ++r) {
+		PP.dst[r] = r < ctx->n_ranks ? peer.gather[x.epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+		PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
+	}
+	publish_kernel<<<1, 288, 0, lane>>>(PP, (const uint32_t*)cs->last_counters);
+	LB200_CHECK_LAUNCH(ctx);
+	cs->lane_owed[l] = x.epoch;
+	return LB200_OK;
+}
+
 static void lastExchange(lb200_culling* cs, const uint32_t** out_dev_ids, const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words) {
 	const lb200_ctx::Peer& peer = cs->ctx->peer;
 	if (out_dev_ids) *out_dev_ids = cs->last_out;
@@ -1235,9 +1266,27 @@ int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum
 	// flag round trip overlap the neighbouring steps' culls; see lb200_ctx::Peer for why 2 x lanes exchange buffers make that safe
 	rc = forkLanes(cs);
 	if (rc) return rc;
-	// default: store, publish, wait in lane order (publish_wait_kernel).  LB200_EXCHANGE_PIPELINED=1: the wait on a second stream per lane
-	// (exchangeStepPipelined) — validated at N=2, where it measured no better (profiles/r2_N2b_time_exchange.log), so it is not the default
+	// default: store, publish, wait in lane order — ONE kernel behind the cull (publish_wait_kernel).  Two forms that take the wait out of the
+	// lane's critical path were built and content-checked on 2 GPUs, and both measured slower (profiles/r2_N2e_time_exchange.log, r2_N2b_*):
+	// what a step costs on top of the cull is the second kernel per step and its scheduling, not the peers' flags.
+	//   LB200_EXCHANGE_DEFERRED=1  cull, the lane's previous step's wait, publish (exchangeStepDeferred)
+	//   LB200_EXCHANGE_PIPELINED=1 the wait on a second stream per lane (exchangeStepPipelined)
 	static const bool pipelined = [] { const char* e = getenv("LB200_EXCHANGE_PIPELINED"); return e && atoi(e) != 0; }();
+	static const bool deferred = [] { const char* e = getenv("LB200_EXCHANGE_DEFERRED"); return e && atoi(e) != 0; }();
+	if (deferred && !pipelined) {
+		for (uint32_t i = 0; i < n; ++i) {
+			rc = exchangeStepDeferred(cs, frustum, type);
+			if (rc) return rc;
+		}
+		for (uint32_t l = 0; l < cs->lanes; ++l) { // the waits still owed: the batch is over when every step of it is
+			if (!cs->lane_owed[l]) continue;
+			wait_peers_kernel<<<1, 32, 0, cs->lane_stream[l]>>>(ctx->peer.flags[ctx->rank], (uint32_t)ctx->n_ranks, cs->lane_owed[l], ctx->peer.n_buffers, ctx->peer.d_timeout);
+			LB200_CHECK_LAUNCH(ctx);
+			cs->lane_owed[l] = 0;
+		}
+		lastExchange(cs, out_dev_ids, out_dev_slabs, out_slab_stride_words);
+		return joinLanes(cs);
+	}
 	if (!pipelined) {
 		for (uint32_t i = 0; i < n; ++i) {
 			rc = exchangeStep(cs, frustum, type, cs->lane_stream[(ctx->peer.epoch + 1) % cs->lanes], nullptr);

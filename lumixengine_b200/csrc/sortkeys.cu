@@ -483,37 +483,42 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 4;                         // keys per thread and tile
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 2048 keys
 constexpr int RS_PASSES = 8;
-struct SortState { GridBar bar; uint32_t pad[2]; unsigned long long key_or, key_or_not; }; // zero-initialised: OR of all keys, OR of all complements
+struct SortState { // zero-initialised before every launch
+	GridBar bar; uint32_t pad[2];
+	unsigned long long key_or, key_or_not; // OR of all keys, OR of all complements
+	uint32_t digit_total[RS_PASSES][256];    // per digit window: keys of every digit, summed by the blocks with one atomic each
+};
 
 constexpr int RS_REG_ITEMS = 16;                    // keys a thread can keep in registers over all passes
 
 // Where this block's keys of digit d start: all keys of smaller digits + the keys of digit d in the blocks before this one.
-// In: block_hist[b][d] of every block (behind a grid barrier).  Out: s_hist[d].  All RS_THREADS threads.
-__device__ __forceinline__ void digit_starts(const uint32_t* block_hist, uint32_t* s_hist, uint32_t (*s_part)[256], uint32_t (*s_bef)[256], uint32_t* s_wsum) {
+// In: block_hist[b][d] of every block and digit_total[d] = their column sums (behind a grid barrier).  Out: s_hist[d].  All RS_THREADS threads.
+// A block in the first half of the grid sums the rows before it, one in the second half subtracts the rows from itself on from the total:
+// nobody reads more than half of the rows.
+__device__ __forceinline__ void digit_starts(const uint32_t* block_hist, const uint32_t* digit_total, uint32_t* s_hist, uint32_t (*s_part)[256], uint32_t* s_wsum) {
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t d = tid & 255u, part = tid >> 8;
-	uint32_t before = 0, total = 0;
+	const bool front = 2u * blockIdx.x <= gridDim.x;
+	const uint32_t row_begin = front ? 0u : blockIdx.x, row_end = front ? blockIdx.x : gridDim.x;
+	uint32_t sum = 0;
 	// 8 rows in flight per thread: the rows come from L2 and a row-at-a-time loop would pay one L2 round trip per row
-	for (uint32_t b0 = part; b0 < gridDim.x; b0 += 8 * (RS_THREADS / 256)) {
+	for (uint32_t b0 = row_begin + part; b0 < row_end; b0 += 8 * (RS_THREADS / 256)) {
 		uint32_t c[8];
 #pragma unroll
 		for (int u = 0; u < 8; ++u) {
 			const uint32_t b = b0 + u * (RS_THREADS / 256);
-			c[u] = b < gridDim.x ? __ldcg(block_hist + b * 256 + d) : 0u;
+			c[u] = b < row_end ? __ldcg(block_hist + b * 256 + d) : 0u;
 		}
 #pragma unroll
-		for (int u = 0; u < 8; ++u) {
-			const uint32_t b = b0 + u * (RS_THREADS / 256);
-			total += c[u];
-			if (b < blockIdx.x) before += c[u];
-		}
+		for (int u = 0; u < 8; ++u) sum += c[u];
 	}
-	s_part[part][d] = total;
-	s_bef[part][d] = before;
+	s_part[part][d] = sum;
 	__syncthreads();
-	uint32_t x = 0, mine = 0;
+	uint32_t x = 0, mine = 0, before = 0;
 	if (tid < 256) { // exclusive scan of the 256 digit totals by the first 8 warps
-		mine = s_part[0][tid] + s_part[1][tid];
+		mine = __ldcg(digit_total + tid);
+		const uint32_t rows = s_part[0][tid] + s_part[1][tid];
+		before = front ? rows : mine - rows;
 		x = mine;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
@@ -523,7 +528,7 @@ __device__ __forceinline__ void digit_starts(const uint32_t* block_hist, uint32_
 	if (tid < 256) {
 		uint32_t start = x - mine;
 		for (uint32_t w = 0; w < warp; ++w) start += s_wsum[w];
-		s_hist[tid] = start + s_bef[0][tid] + s_bef[1][tid];
+		s_hist[tid] = start + before;
 	}
 	__syncthreads();
 }
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 	SortState* st, uint32_t* block_hist /* [gridDim][256] */, uint32_t reg_items /* RS_REG_ITEMS; 0 forces the tiled path (tests) */)
 {
 	__shared__ uint32_t s_hist[256];              // count phase: this block's digit histogram; scatter phase: the block's running digit cursors
-	__shared__ uint32_t s_part[2][256], s_bef[2][256], s_wsum[8];
+	__shared__ uint32_t s_part[2][256], s_wsum[8];
 	__shared__ uint32_t s_wcnt[RS_WARPS][256];    // per warp: keys of digit d in the warp's part of the tile, then the warp's first destination of digit d
 	__shared__ unsigned long long s_red[2][RS_WARPS];
 	const uint32_t n = min(counts[0], cap);
@@ -575,6 +580,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 	const unsigned long long varying = __ldcg(&st->key_or) & __ldcg(&st->key_or_not); // bits that are 1 in some key and 0 in another
 
 	uint32_t cur = 0;
+	int window = 0; // at most RS_PASSES digit windows: each takes at least one differing bit out of 64 and 8 bits wide windows cover them all
 	if (in_regs) {
 		// the warp's run: [key_begin + warp * items * 32, + items * 32); item j of lane l = run + j * 32 + l, so (j, lane) is the key order
 		const uint32_t wbase = key_begin + warp * items * 32u;
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 		// digit windows: 8 bits from the lowest bit that still differs between keys, then from the next such bit above the window, ...
 		// (bytes in which every key agrees cost nothing, and a group of differing bits that straddles a byte border is one pass, not two)
 #pragma unroll 1
-		for (unsigned long long left = varying; left != 0ull;) {
+		for (unsigned long long left = varying; left != 0ull; ++window) {
 			const int shift = __ffsll((long long)left) - 1;
 			left &= ~(0xffull << shift);
 			const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
@@ -620,9 +626,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 #pragma unroll
 				for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = s_wcnt[w][tid]; s_wcnt[w][tid] = acc; acc += t; }
 				block_hist[blockIdx.x * 256 + tid] = acc;
+				if (acc) atomicAdd(&st->digit_total[window][tid], acc);
 			}
 			grid_barrier(&st->bar, barriers_passed);
-			digit_starts(block_hist, s_hist, s_part, s_bef, s_wsum);
+			digit_starts(block_hist, st->digit_total[window], s_hist, s_part, s_wsum);
 #pragma unroll
 			for (int j = 0; j < RS_REG_ITEMS; ++j) {
 				if ((uint32_t)j < items && wbase + j * 32 + lane < key_end) {
@@ -638,7 +645,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 	}
 	else {
 #pragma unroll 1
-		for (unsigned long long left = varying; left != 0ull;) {
+		for (unsigned long long left = varying; left != 0ull; ++window) {
 			const int shift = __ffsll((long long)left) - 1;
 			left &= ~(0xffull << shift);
 			const uint64_t* ksrc = cur ? kbuf1 : kbuf0;
@@ -650,9 +657,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_kernel(uint64_t* kbu
 			__syncthreads();
 			for (uint32_t i = key_begin + tid; i < key_end; i += RS_THREADS) atomicAdd(&s_hist[(uint32_t)(__ldcg(ksrc + i) >> shift) & 0xffu], 1u);
 			__syncthreads();
-			if (tid < 256) block_hist[blockIdx.x * 256 + tid] = s_hist[tid];
+			if (tid < 256) {
+				block_hist[blockIdx.x * 256 + tid] = s_hist[tid];
+				if (s_hist[tid]) atomicAdd(&st->digit_total[window][tid], s_hist[tid]);
+			}
 			grid_barrier(&st->bar, barriers_passed);
-			digit_starts(block_hist, s_hist, s_part, s_bef, s_wsum);
+			digit_starts(block_hist, st->digit_total[window], s_hist, s_part, s_wsum);
 			// stable scatter, tile by tile
 			for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
 				const uint32_t wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);

@@ -237,3 +237,22 @@ def test_bone_attachments_match_oracle(ctx, oracle):
     assert np.array_equal(got["pos"], exp["pos"]) and np.array_equal(got["rot"].view(np.uint32), exp["rot"].view(np.uint32))
     assert np.array_equal(got["scale"], exp["scale"])
     anim.close()
+
+
+def test_c4_100k_x64_palettes_equal_oracle_at_full_size(ctx, oracle):
+    """BASELINE configs[3] at its stated size: 100 k instances x 64 bones — absolute poses, dual-quaternion and matrix palettes of every
+    instance against the C restatement of updateAnimable + computeSkeletonDualQuats + computeSkinMatrices (1e-5 relative is the bound
+    north_star states; bit-exactness is reported and has held on every run)."""
+    sk = scenes.skeleton(64)
+    clips = [scenes.clip(sk, frames=60, seed=s) for s in (1, 2, 3, 4)]
+    n = 100_000
+    anim = lb.AnimationSystem(ctx, sk, clips, None, max_instances=n)
+    ci, tt = scenes.instance_times(n, clips)
+    anim.setInstances(ci, tt)
+    anim.update(0.0, lb.PALETTE_DUAL_QUAT | lb.PALETTE_MATRIX | lb.PALETTE_POSE)
+    exp = oracle.animate_instances(sk, clips, ci, tt)
+    pos, rot = anim.getPose()
+    exact = [_close(pos, exp["pos"], "pose.pos"), _close(rot, exp["rot"], "pose.rot"),
+             _close(anim.getDualQuats(), exp["dq"], "dual quats"), _close(anim.getMatrices(), exp["mtx"], "matrices")]
+    print("bit-exact at 100k x 64:", exact)
+    anim.close()

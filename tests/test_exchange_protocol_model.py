@@ -11,11 +11,14 @@ import random
 import pytest
 
 
-def simulate(ranks, lanes, batches, rng, pipelined=False):
+def simulate(ranks, lanes, batches, rng, pipelined=False, deferred=False):
     """pipelined=False: the one-stream-per-lane form (store, publish, wait in lane order; 2L buffers).
     pipelined=True: lb200_culling_cull_exchange_n's form — the wait of epoch e runs on a second stream of the lane, the lane itself only
     holds publish(e) back until wait(e - L) is over and store(e) until wait(e - 2L) is over; 3L buffers."""
-    nbuf = (3 if pipelined else 2) * lanes
+    """deferred=True: lb200_culling_cull_exchange_n's default form — everything stays on the lane's stream, but the wait a step issues is the one
+    of the lane's PREVIOUS step, between its own store and publish: store(e), wait(e - L), publish(e); the batch ends with the waits still
+    owed; 3L buffers."""
+    nbuf = (3 if (pipelined or deferred) else 2) * lanes
     # rows[r][b][src] = epoch whose rows rank `src` last stored into buffer b of rank r; flags likewise
     rows = [[[0] * ranks for _ in range(nbuf)] for _ in range(ranks)]
     flags = [[[0] * ranks for _ in range(nbuf)] for _ in range(ranks)]
@@ -25,6 +28,7 @@ def simulate(ranks, lanes, batches, rng, pipelined=False):
     for r in range(ranks):
         ops, last_on = [], {}   # last_on[stream] = id of the previous op on that stream
         wait_of = {}            # pipelined form: epoch -> id of its wait op
+        owed = {}               # deferred form: lane -> epoch whose wait has not been issued yet
 
         def add(stream, kind, epoch, extra=()):
             deps = [last_on[stream]] if stream in last_on else []
@@ -42,7 +46,13 @@ def simulate(ranks, lanes, batches, rng, pipelined=False):
                 lane = ("lane", epoch % lanes)
                 first = lane not in used
                 used.add(lane)
-                if not pipelined:
+                if deferred:
+                    s = add(lane, "store", epoch, extra=[fork] if first else ())
+                    if lane in owed:
+                        add(lane, "wait", owed.pop(lane))
+                    p = add(lane, "publish", epoch)
+                    owed[lane] = epoch
+                elif not pipelined:
                     s = add(lane, "store", epoch, extra=[fork] if first else ())
                     p = add(lane, "publish", epoch)
                     w = add(lane, "wait", epoch)
@@ -54,6 +64,9 @@ def simulate(ranks, lanes, batches, rng, pipelined=False):
                     s = add(lane, "store", epoch, extra=([fork] if first else []) + dep2)
                     p = add(lane, "publish", epoch, extra=dep1)
                     wait_of[epoch] = add(side, "wait", epoch, extra=[p])
+            if deferred:  # the batch's consumer needs every step it issued complete: the owed waits go out before the join
+                for lane in list(owed):
+                    add(lane, "wait", owed.pop(lane))
             tails = [last_on[l] for l in used]
             join = add("main", "join", 0, extra=tails)
             add("main", "consume", epoch)  # the out parameters describe the LAST step of the batch
@@ -103,11 +116,34 @@ def test_pipelined_waits_no_early_overwrite_and_no_deadlock(ranks, lanes):
         simulate(ranks, lanes, batches, rng, pipelined=True)
 
 
+@pytest.mark.parametrize("ranks,lanes", [(2, 1), (2, 2), (2, 3), (3, 3), (8, 3), (4, 4), (8, 8)])
+def test_deferred_waits_no_early_overwrite_and_no_deadlock(ranks, lanes):
+    rng = random.Random(31 * ranks + lanes)
+    for trial in range(12 if ranks < 8 else 3):
+        batches = [rng.randint(1, 20) for _ in range(rng.randint(2, 5))]
+        simulate(ranks, lanes, batches, rng, deferred=True)
+
+
+def test_the_model_catches_too_few_buffers_for_deferred_waits():
+    def broken(ranks, lanes, batches, rng):
+        g = dict(simulate.__globals__)
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred) else 2) * lanes", "nbuf = 2 * lanes - 1")
+        exec(src, g)
+        return g["simulate"](ranks, lanes, batches, rng, deferred=True)
+    failures = 0
+    for seed in range(80):
+        try:
+            broken(2, 2, [9, 9, 9], random.Random(seed))
+        except AssertionError:
+            failures += 1
+    assert failures > 0
+
+
 def test_the_model_catches_too_few_buffers_for_pipelined_waits():
     """With the waits off the lane streams, 2L buffers are not enough any more: a fast rank overwrites rows a slow rank still waits for."""
     def broken(ranks, lanes, batches, rng):
         g = dict(simulate.__globals__)
-        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if pipelined else 2) * lanes", "nbuf = 2 * lanes")
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred) else 2) * lanes", "nbuf = 2 * lanes")
         exec(src, g)
         return g["simulate"](ranks, lanes, batches, rng, pipelined=True)
     failures = 0
@@ -124,7 +160,7 @@ def test_the_model_catches_too_few_buffers():
     def broken(ranks, lanes, batches, rng):
         import types
         g = dict(simulate.__globals__)
-        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if pipelined else 2) * lanes", "nbuf = lanes")
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred) else 2) * lanes", "nbuf = lanes")
         exec(src, g)
         return g["simulate"](ranks, lanes, batches, rng)
     failures = 0

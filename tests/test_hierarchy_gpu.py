@@ -165,3 +165,22 @@ def test_compute_locals_match_oracle(ctx, oracle):
     err = np.abs(back["pos"] - moved["pos"]).max()
     assert err < 1e-5 * max(1.0, np.abs(moved["pos"]).max()), err
     h.close()
+
+
+def test_c3_1m_equals_oracle_at_full_size(ctx, oracle):
+    """BASELINE configs[2] at its stated size: the 1 M-node, depth-8 forest propagated on the GPU against the C restatement of
+    World::transformEntity (serial DFS, ~35 ms), every Transform bit for bit, and the sphere refresh behind it."""
+    parents, locals_, roots = scenes.hierarchy_forest(1_000_000, 8, 7, seed=3)
+    h = lb.Hierarchy(ctx, parents)
+    h.setLocalTransforms(locals_)
+    h.setRootTransforms(roots)
+    h.propagate()
+    got = h.getTransforms()
+    exp = oracle.propagate(parents, _as_bytes(locals_), _as_bytes(roots)).view(lb.TRANSFORM_DTYPE).reshape(-1)
+    for field in ("pos", "rot", "scale"):
+        assert got[field].tobytes() == exp[field].tobytes(), f"1 M-node propagate: {field} differs from the oracle"
+    br = np.full(len(parents), 1.0, np.float32)
+    pos, rad = h.getSpheres(br)
+    assert pos.tobytes() == np.ascontiguousarray(exp["pos"]).tobytes()
+    assert np.array_equal(rad, oracle.sphere_radius(_as_bytes(exp), br))
+    h.close()
