@@ -11,7 +11,12 @@ data-path collective for the cull itself) and each step carries the one exchange
 bitmask + per-type counts of every rank reach every other rank, stored into peer memory over NVLink by the cull kernel itself
 (lb200_culling_cull_exchange); the compacted id lists stay sharded with their entities.  LB200_EXCHANGE=ids gathers the id lists
 instead (fused pack + peer push; LB200_NO_P2P=1: pack + ncclAllGather).  `value` = all ranks' entities / max-over-ranks device time.
-The JSON line also carries the secondary BASELINE metric (M skinned verts/s) and the other stages of the path under "paths".
+The JSON line also carries the secondary BASELINE metric (M skinned verts/s) and the other stages of the path under "paths":
+configs[2] as a chain on the device (propagate -> sphere refresh -> re-binning -> cull), configs[3] (pose + palette, skin; sharded by
+instance at N>1), configs[4] (50M-entity cull + id all-gather over NVLink || pose pass of 1M instances, strong scaling).
+`e2e` = host frustum + view in -> cull -> createSortKeys -> radixSort on the device -> counters back (the reference arm's e2e is the same
+step on the host).  `parity`: the C2 digest against the reference build; at N>1 one exchanged step checked on every rank.
+DESIGN.md section 7 describes every field.
 """
 import argparse
 import json
