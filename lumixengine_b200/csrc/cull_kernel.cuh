@@ -9,8 +9,9 @@
 //       ShiftedFrustum::containsAABB / intersectsAABB arithmetic (geometry.cpp:99-118,159-178), the plane mask, and for pages that need
 //       sphere tests the plane offsets re-based to the cell origin (ShiftedFrustum::getRelative, geometry.cpp:121-149 — only d
 //       changes); pages with work go to a block-local list in shared memory.
-//   B   test, one WARP per listed page: the <=200 spheres arrive in shared memory through the bulk-copy engine (TMA, cp.async.bulk +
-//       mbarrier; two pages in flight per warp, no registers held by loads in flight); the planes of the mask are walked by a
+//   B   test, one WARP per listed page: the <=200 spheres as 7 x 128-bit streaming loads per lane (default, STAGE_DEPTH = 0) or staged in
+//       shared memory through the bulk-copy engine (STAGE_DEPTH = 1 | 2: TMA, cp.async.bulk + mbarrier, up to two pages in flight per warp;
+//       measured slower on 3.2 KB pages, LB200_CULL_STAGE); the planes of the mask are walked by a
 //       warp-uniform loop with the rows unrolled inside (no branch per sphere; rows 4-6 only for pages with more than 128 spheres), the
 //       reference's op order and sign-bit test (culling_system.cpp:284-295, simd.h:119); ballots kept in shared memory.
 //   C   claim: one global atomic per (warp, renderable type) reserves the output range of the warp's pages.
