@@ -59,6 +59,11 @@ struct CullParams {
 	// exchange mode (n_ranks > 0): {page, row} records go straight into every rank's slab (peer memory)
 	uint32_t n_ranks;
 	uint32_t* xdst[LB200_MAX_RANKS]; // rank r's exchange buffer of this epoch, already offset to MY slab inside it
+	// fused exchange steps (one kernel per step, lb200_culling_cull_exchange_n with LB200_EXCHANGE_FUSED): this cull also publishes the lane's
+	// PREVIOUS epoch (pub_epoch != 0) and holds its record stores back until every rank has published wait_epoch (!= 0)
+	uint32_t pub_epoch, wait_epoch, n_buffers, rank;
+	uint32_t* xprev[LB200_MAX_RANKS];  // rank r's exchange buffer of pub_epoch, offset to MY slab
+	uint32_t* xflags[LB200_MAX_RANKS]; // rank r's flag block: [n_buffers][LB200_MAX_RANKS]
 	uint32_t type_base[256];
 };
 // exchange slab = [256 per-type counts][n_pages, n_records, 0, item_cap, 0, 0, 0, 0][page ids: item_cap][rows: item_cap x 8]
@@ -439,6 +444,36 @@ __global__ void __launch_bounds__(CULL_THREADS, STAGE_DEPTH >= 2 ? 3 : 4) cull_p
 		// nothing above wrote global memory (A and B read scene data, results sit in shared memory); everything below does
 		// (counters, ids, mask rows) and has to wait for the previous kernel of the stream
 		if (round == 0) { trace_point(P.trace, 0, 3); cudaGridDependencySynchronize(); trace_point(P.trace, 0, 4); }
+		if (round == 0 && P.n_ranks && (P.pub_epoch | P.wait_epoch)) {
+			// Fused exchange step.  Behind the grid dependency the lane's previous cull is complete: its records lie in the peers' slabs, its
+			// counters still in `next_counters` (zeroed at the end of THIS kernel, behind the round barrier every warp of block 0 passes).
+			if (P.pub_epoch && blockIdx.x == 0 && warp == 0) { // publish that epoch: header to every rank, one system fence, the flags
+				for (uint32_t i = (uint32_t)lane; i < XHEADER_WORDS; i += 32u) {
+					uint32_t v = 0;
+					if (i < 256u) v = __ldcg(next_counters + i);
+					else if (i == 256u) v = P.n_pages;
+					else if (i == 257u) v = __ldcg(next_counters + CNT_N_REC);
+					else if (i == 259u) v = P.item_cap;
+					for (uint32_t r = 0; r < P.n_ranks; ++r) P.xprev[r][i] = v;
+				}
+				__threadfence_system();
+				__syncwarp();
+				if ((uint32_t)lane < P.n_ranks) {
+					__threadfence_system();
+					volatile uint32_t* f = P.xflags[lane] + (P.pub_epoch % P.n_buffers) * LB200_MAX_RANKS + P.rank;
+					*f = P.pub_epoch;
+				}
+				__syncwarp();
+			}
+			if (P.wait_epoch) { // flow control: nobody stores records of this epoch before every rank has published wait_epoch (= epoch - 2 x lanes)
+				if ((uint32_t)lane < P.n_ranks) {
+					const volatile uint32_t* f = P.xflags[P.rank] + (P.wait_epoch % P.n_buffers) * LB200_MAX_RANKS + lane;
+					const long long t0 = clock64();
+					while ((int)(*f - P.wait_epoch) < 0) { if (clock64() - t0 > 8000000000ll) break; } // a lost peer is reported by the batch's closing wait
+				}
+				__syncwarp();
+			}
+		}
 		// rows of pages that ended without work
 		if (mask_out && (uint32_t)tid < P.chunk && s_zpage[tid] != 0xffffffffu) {
 			uint4* row = reinterpret_cast<uint4*>(mask_out + (size_t)s_zpage[tid] * 8);

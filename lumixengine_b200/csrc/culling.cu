@@ -302,7 +302,8 @@ struct lb200_culling {
 	cudaStream_t wait_stream[MAX_LANES] = {};
 	cudaEvent_t ev_published[MAX_LANES][4] = {}, ev_waited[MAX_LANES][4] = {};
 	uint64_t lane_cycle[MAX_LANES] = {}; // exchange steps this lane has issued
-	uint32_t lane_owed[MAX_LANES] = {};  // deferred form: the epoch of the lane's previous step, whose wait has not been issued yet (0 = none)
+	uint32_t lane_owed[MAX_LANES] = {};  // deferred / fused forms: the epoch of the lane's previous step, whose wait / publish has not been issued yet (0 = none)
+	uint32_t* lane_last_counters[MAX_LANES] = {}; // fused form: the counters of the lane's last cull (the closing publish reads them)
 	uint64_t seq = 0;
 	uint32_t* d_out_ids = nullptr;  // lanes * out_cap
 	uint32_t out_cap = 0;
@@ -509,7 +510,7 @@ int flushPages(lb200_culling* cs) {
 	return LB200_OK;
 }
 
-struct Exchange { uint32_t epoch; }; // non-null: store {page, row} records + counts into every rank's slab (peer memory); lane = epoch % lanes
+struct Exchange { uint32_t epoch; uint32_t pub_epoch = 0, wait_epoch = 0; }; // non-null: store {page, row} records + counts into every rank's slab (peer memory); lane = epoch % lanes; pub / wait: fused steps (cull_kernel.cuh)
 
 // words one rank contributes to a bitmask exchange step: header + page ids + rows (cull_kernel.cuh)
 size_t exchangeSlabWords(const lb200_culling* cs) { return XHEADER_WORDS + 9 * (size_t)cs->item_cap; }
@@ -550,10 +551,17 @@ int launchCull(lb200_culling* cs, const lb200_shifted_frustum* f, uint8_t type, 
 	uint32_t* mask = cs->d_mask + (size_t)lane * cs->mask_words;
 	P.n_ranks = 0;
 	for (int r = 0; r < LB200_MAX_RANKS; ++r) P.xdst[r] = nullptr;
+	P.pub_epoch = 0; P.wait_epoch = 0; P.n_buffers = 1; P.rank = 0;
+	for (int r = 0; r < LB200_MAX_RANKS; ++r) { P.xprev[r] = nullptr; P.xflags[r] = nullptr; }
 	if (xchg) {
 		lb200_ctx::Peer& peer = ctx->peer;
 		P.n_ranks = (uint32_t)ctx->n_ranks;
 		for (int r = 0; r < ctx->n_ranks; ++r) P.xdst[r] = peer.gather[xchg->epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank;
+		P.pub_epoch = xchg->pub_epoch; P.wait_epoch = xchg->wait_epoch; P.n_buffers = peer.n_buffers; P.rank = (uint32_t)ctx->rank;
+		for (int r = 0; r < ctx->n_ranks; ++r) {
+			P.xflags[r] = peer.flags[r];
+			P.xprev[r] = xchg->pub_epoch ? peer.gather[xchg->pub_epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+		}
 	}
 	static const bool no_mask = getenv("LB200_NO_PLANE_MASKING") != nullptr;
 	P.plane_masking = (h.n_bad_radius == 0 && !no_mask) ? 1u : 0u;
@@ -1223,6 +1231,47 @@ static int exchangeStepDeferred(lb200_culling* cs, const lb200_shifted_frustum* 
 	return LB200_OK;
 }
 
+// One step of the fused form: ONE kernel.  The cull of epoch e publishes the lane's previous epoch from its own prologue and holds its
+// record stores back until every rank has published e - 2 x lanes (cull_kernel.cuh); the batch closes with publish_wait_kernel per lane.
+static int exchangeStepFused(lb200_culling* cs, const lb200_shifted_frustum* frustum, uint8_t type) {
+	lb200_ctx::Peer& peer = cs->ctx->peer;
+	Exchange x;
+	x.epoch = ++peer.epoch;
+	const uint32_t l = x.epoch % cs->lanes;
+	x.pub_epoch = cs->lane_owed[l];
+	x.wait_epoch = x.epoch > 2 * cs->lanes ? x.epoch - 2 * cs->lanes : 0u;
+	int rc = launchCull(cs, frustum, type, &x, cs->lane_stream[l]);
+	if (rc) return rc;
+	cs->lane_owed[l] = x.epoch;
+	cs->lane_last_counters[l] = cs->last_counters;
+	return LB200_OK;
+}
+
+// publish + wait of one epoch as a kernel of its own behind the lane's last cull (the closing step of a fused batch)
+static int publishAndWait(lb200_culling* cs, uint32_t epoch, const uint32_t* counters, cudaStream_t stream) {
+	lb200_ctx* ctx = cs->ctx;
+	lb200_ctx::Peer& peer = ctx->peer;
+	PublishParams PP;
+	PP.n_ranks = (uint32_t)ctx->n_ranks; PP.rank = (uint32_t)ctx->rank; PP.epoch = epoch; PP.n_buffers = peer.n_buffers;
+	PP.n_pages = cs->last_pages; PP.item_cap = cs->item_cap;
+	for (int r = 0; r < LB200_MAX_RANKS; ++r) {
+		PP.dst[r] = r < ctx->n_ranks ? peer.gather[epoch % peer.n_buffers][r] + peer.slab_words * (size_t)ctx->rank : nullptr;
+		PP.flags[r] = r < ctx->n_ranks ? peer.flags[r] : nullptr;
+	}
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(1);
+	cfg.blockDim = dim3(288);
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	LB200_CUDA(ctx, cudaLaunchKernelEx(&cfg, publish_wait_kernel, PP, counters, peer.d_timeout));
+	LB200_CHECK_LAUNCH(ctx);
+	return LB200_OK;
+}
+
 static void lastExchange(lb200_culling* cs, const uint32_t** out_dev_ids, const uint32_t** out_dev_slabs, uint32_t* out_slab_stride_words) {
 	const lb200_ctx::Peer& peer = cs->ctx->peer;
 	if (out_dev_ids) *out_dev_ids = cs->last_out;
@@ -1266,13 +1315,29 @@ int lb200_culling_cull_exchange_n(lb200_culling* cs, const lb200_shifted_frustum
 	// flag round trip overlap the neighbouring steps' culls; see lb200_ctx::Peer for why 2 x lanes exchange buffers make that safe
 	rc = forkLanes(cs);
 	if (rc) return rc;
-	// default: store, publish, wait in lane order — ONE kernel behind the cull (publish_wait_kernel).  Two forms that take the wait out of the
-	// lane's critical path were built and content-checked on 2 GPUs, and both measured slower (profiles/r2_N2e_time_exchange.log, r2_N2b_*):
-	// what a step costs on top of the cull is the second kernel per step and its scheduling, not the peers' flags.
+	// default (LB200_EXCHANGE_FUSED, on): ONE kernel per step — the cull publishes the lane's previous epoch from its own prologue and checks
+	// the flags of epoch - 2 x lanes before its record stores (exchangeStepFused, cull_kernel.cuh); the batch closes with publish + wait per lane.
+	// LB200_EXCHANGE_FUSED=0 selects one of the two-kernel forms: store, publish, wait in lane order (publish_wait_kernel behind the cull; round 1's
+	// form), or with the wait taken out of the lane's critical path — both content-checked on 2 GPUs, both slower (profiles/r2_N2*_time_exchange.log):
 	//   LB200_EXCHANGE_DEFERRED=1  cull, the lane's previous step's wait, publish (exchangeStepDeferred)
 	//   LB200_EXCHANGE_PIPELINED=1 the wait on a second stream per lane (exchangeStepPipelined)
 	static const bool pipelined = [] { const char* e = getenv("LB200_EXCHANGE_PIPELINED"); return e && atoi(e) != 0; }();
 	static const bool deferred = [] { const char* e = getenv("LB200_EXCHANGE_DEFERRED"); return e && atoi(e) != 0; }();
+	static const bool fused = [] { const char* e = getenv("LB200_EXCHANGE_FUSED"); return !e || atoi(e) != 0; }(); // the default since it measured 8.5 us per step against 10.3 (2 GPUs)
+	if (fused) {
+		for (uint32_t i = 0; i < n; ++i) {
+			rc = exchangeStepFused(cs, frustum, type);
+			if (rc) return rc;
+		}
+		for (uint32_t l = 0; l < cs->lanes; ++l) { // the closing publish + wait of every lane's last epoch
+			if (!cs->lane_owed[l]) continue;
+			rc = publishAndWait(cs, cs->lane_owed[l], cs->lane_last_counters[l], cs->lane_stream[l]);
+			if (rc) return rc;
+			cs->lane_owed[l] = 0;
+		}
+		lastExchange(cs, out_dev_ids, out_dev_slabs, out_slab_stride_words);
+		return joinLanes(cs);
+	}
 	if (deferred && !pipelined) {
 		for (uint32_t i = 0; i < n; ++i) {
 			rc = exchangeStepDeferred(cs, frustum, type);

@@ -32,11 +32,11 @@ struct lb200_ctx {
 		bool ready = false;
 		size_t slab_words = 0;            // capacity of one rank's slab (header + ids)
 		// Exchange epoch e uses buffer e % n_buffers, n_buffers = 3 x lanes.  With lanes > 1 (lb200_culling_cull_exchange_n) epoch e is
-		// issued on stream e % lanes and its WAIT on a second stream of that lane: the lane only holds publish(e) back until wait(e - lanes)
-		// is over and the cull of e until wait(e - 2 x lanes) is over, so a peer's flag round trip never stalls the next cull.  A rank
-		// overwrites buffer b for epoch e only after its wait for e - 2 x lanes, i.e. after every rank published e - 2 x lanes, which every
-		// rank does behind its wait for (and whatever consumed) e - 3 x lanes: the previous owner of b.  tests/test_exchange_protocol_model.py
-		// replays this under a random scheduler (and shows that 2 x lanes buffers would not do).
+		// issued on stream e % lanes as ONE kernel: the cull of e publishes the lane's previous epoch (e - lanes) from its prologue and
+		// holds its record stores back until every rank has published e - 2 x lanes.  So a rank overwrites buffer b for epoch e only after
+		// every rank published e - 2 x lanes, which a rank does from its cull of e - lanes — issued behind whatever consumed e - 3 x lanes,
+		// the previous owner of b.  tests/test_exchange_protocol_model.py replays this (and the two-kernel forms culling.cu keeps as
+		// options) under a random scheduler, and shows that fewer buffers or no flow control would not do.
 		uint32_t lanes = 1, n_buffers = 3;
 		void* local_block = nullptr;      // this rank's allocation: [flags n_buffers x 8 x u32 in 512 B][gather 0] .. [gather n_buffers-1]
 		uint32_t* gather[3 * LB200_MAX_LANES][LB200_MAX_RANKS] = {}; // gather[b][r] = rank r's buffer b as seen from this process

@@ -11,14 +11,16 @@ import random
 import pytest
 
 
-def simulate(ranks, lanes, batches, rng, pipelined=False, deferred=False):
+def simulate(ranks, lanes, batches, rng, pipelined=False, deferred=False, fused=False):
     """pipelined=False: the one-stream-per-lane form (store, publish, wait in lane order; 2L buffers).
     pipelined=True: lb200_culling_cull_exchange_n's form — the wait of epoch e runs on a second stream of the lane, the lane itself only
     holds publish(e) back until wait(e - L) is over and store(e) until wait(e - 2L) is over; 3L buffers."""
     """deferred=True: lb200_culling_cull_exchange_n's default form — everything stays on the lane's stream, but the wait a step issues is the one
     of the lane's PREVIOUS step, between its own store and publish: store(e), wait(e - L), publish(e); the batch ends with the waits still
     owed; 3L buffers."""
-    nbuf = (3 if (pipelined or deferred) else 2) * lanes
+    """fused=True: one kernel per step — the cull of epoch e first waits for the flags of e - 2L, then stores its records while one of its warps
+    publishes the lane's PREVIOUS epoch (either order); a batch ends with publish + wait of every lane's last epoch; 3L buffers."""
+    nbuf = (3 if (pipelined or deferred or fused) else 2) * lanes
     # rows[r][b][src] = epoch whose rows rank `src` last stored into buffer b of rank r; flags likewise
     rows = [[[0] * ranks for _ in range(nbuf)] for _ in range(ranks)]
     flags = [[[0] * ranks for _ in range(nbuf)] for _ in range(ranks)]
@@ -46,7 +48,17 @@ def simulate(ranks, lanes, batches, rng, pipelined=False, deferred=False):
                 lane = ("lane", epoch % lanes)
                 first = lane not in used
                 used.add(lane)
-                if deferred:
+                if fused:
+                    if epoch - 2 * lanes >= 1:
+                        add(lane, "wait", epoch - 2 * lanes, extra=[fork] if first else ())
+                        first = False
+                    todo = [("store", epoch)] + ([("publish", owed.pop(lane))] if lane in owed else [])
+                    rng.shuffle(todo)
+                    for kind, ep in todo:
+                        add(lane, kind, ep, extra=[fork] if first else ())
+                        first = False
+                    owed[lane] = epoch
+                elif deferred:
                     s = add(lane, "store", epoch, extra=[fork] if first else ())
                     if lane in owed:
                         add(lane, "wait", owed.pop(lane))
@@ -67,6 +79,11 @@ def simulate(ranks, lanes, batches, rng, pipelined=False, deferred=False):
             if deferred:  # the batch's consumer needs every step it issued complete: the owed waits go out before the join
                 for lane in list(owed):
                     add(lane, "wait", owed.pop(lane))
+            if fused:  # the trailing publish + wait of every lane's last epoch
+                for lane in list(owed):
+                    ep = owed.pop(lane)
+                    add(lane, "publish", ep)
+                    add(lane, "wait", ep)
             tails = [last_on[l] for l in used]
             join = add("main", "join", 0, extra=tails)
             add("main", "consume", epoch)  # the out parameters describe the LAST step of the batch
@@ -124,10 +141,34 @@ def test_deferred_waits_no_early_overwrite_and_no_deadlock(ranks, lanes):
         simulate(ranks, lanes, batches, rng, deferred=True)
 
 
+@pytest.mark.parametrize("ranks,lanes", [(2, 1), (2, 2), (2, 3), (3, 3), (8, 3), (4, 4), (8, 8)])
+def test_fused_publish_no_early_overwrite_and_no_deadlock(ranks, lanes):
+    rng = random.Random(53 * ranks + lanes)
+    for trial in range(12 if ranks < 8 else 3):
+        batches = [rng.randint(1, 20) for _ in range(rng.randint(2, 5))]
+        simulate(ranks, lanes, batches, rng, fused=True)
+
+
+def test_the_model_catches_a_fused_form_without_its_flow_control():
+    """Without the wait for e - 2L inside the cull a fast rank laps a slow one and overwrites the slab its consumer is about to read."""
+    def broken(ranks, lanes, batches, rng):
+        g = dict(simulate.__globals__)
+        src = __import__("inspect").getsource(simulate).replace("if epoch - 2 * lanes >= 1:", "if False:")
+        exec(src, g)
+        return g["simulate"](ranks, lanes, batches, rng, fused=True)
+    failures = 0
+    for seed in range(80):
+        try:
+            broken(2, 2, [9, 9, 9], random.Random(seed))
+        except AssertionError:
+            failures += 1
+    assert failures > 0
+
+
 def test_the_model_catches_too_few_buffers_for_deferred_waits():
     def broken(ranks, lanes, batches, rng):
         g = dict(simulate.__globals__)
-        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred) else 2) * lanes", "nbuf = 2 * lanes - 1")
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred or fused) else 2) * lanes", "nbuf = 2 * lanes - 1")
         exec(src, g)
         return g["simulate"](ranks, lanes, batches, rng, deferred=True)
     failures = 0
@@ -143,7 +184,7 @@ def test_the_model_catches_too_few_buffers_for_pipelined_waits():
     """With the waits off the lane streams, 2L buffers are not enough any more: a fast rank overwrites rows a slow rank still waits for."""
     def broken(ranks, lanes, batches, rng):
         g = dict(simulate.__globals__)
-        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred) else 2) * lanes", "nbuf = 2 * lanes")
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred or fused) else 2) * lanes", "nbuf = 2 * lanes")
         exec(src, g)
         return g["simulate"](ranks, lanes, batches, rng, pipelined=True)
     failures = 0
@@ -160,7 +201,7 @@ def test_the_model_catches_too_few_buffers():
     def broken(ranks, lanes, batches, rng):
         import types
         g = dict(simulate.__globals__)
-        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred) else 2) * lanes", "nbuf = lanes")
+        src = __import__("inspect").getsource(simulate).replace("nbuf = (3 if (pipelined or deferred or fused) else 2) * lanes", "nbuf = lanes")
         exec(src, g)
         return g["simulate"](ranks, lanes, batches, rng)
     failures = 0
