@@ -785,12 +785,23 @@ template <typename T> int upload_temp(lb200_ctx* ctx, const T* host, size_t n, T
 
 extern "C" {
 
+static int sortkeysAllocate(lb200_sortkeys* sk, lb200_ctx* ctx, uint32_t max_entities, uint32_t max_groups, uint32_t max_keys, uint32_t max_instances);
+
 int lb200_sortkeys_create(lb200_ctx* ctx, uint32_t max_entities, uint32_t max_groups, uint32_t max_keys, uint32_t max_instances, lb200_sortkeys** out) {
 	if (!ctx || !out || !max_entities || !max_groups) return LB200_ERR_INVALID;
+	*out = nullptr;
 	LB200_CUDA(ctx, cudaSetDevice(ctx->device));
 	lb200_sortkeys* sk = new (std::nothrow) lb200_sortkeys;
 	if (!sk) return LB200_ERR_CUDA;
-	sk->ctx = ctx; sk->max_entities = max_entities; sk->max_groups = max_groups;
+	sk->ctx = ctx;
+	const int rc = sortkeysAllocate(sk, ctx, max_entities, max_groups, max_keys, max_instances);
+	if (rc) { lb200_sortkeys_destroy(sk); return rc; } // whatever was allocated before the failure goes back (cudaFree(nullptr) is a no-op)
+	*out = sk;
+	return LB200_OK;
+}
+
+static int sortkeysAllocate(lb200_sortkeys* sk, lb200_ctx* ctx, uint32_t max_entities, uint32_t max_groups, uint32_t max_keys, uint32_t max_instances) {
+	sk->max_entities = max_entities; sk->max_groups = max_groups;
 	sk->cap_keys = max_keys ? max_keys : max_entities; sk->cap_recs = max_instances ? max_instances : max_entities;
 	const size_t E = max_entities;
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_ent, sizeof(SkEntity) * E));
@@ -823,7 +834,6 @@ int lb200_sortkeys_create(lb200_ctx* ctx, uint32_t max_entities, uint32_t max_gr
 	sk->sort_blocks = (uint32_t)ctx->sm_count * 2;
 	LB200_CUDA(ctx, cudaMalloc(&sk->d_block_hist, sizeof(uint32_t) * 256 * sk->sort_blocks));
 	LB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	*out = sk;
 	return LB200_OK;
 }
 
